@@ -1,0 +1,180 @@
+/*
+ * snaq_b200.h — C ABI of the B200-native quartet-pseudolikelihood engine.
+ *
+ * Drop-in boundary for the hot path of JuliaPhylo/SNaQ.jl (reference paths are
+ * relative to the reference repository):
+ *
+ *   extractQuartet!(net,d)              src/pseudolik.jl:503-540
+ *   calculateExpCFAll!(d,x,net)         src/pseudolik.jl:1310-1324
+ *   logPseudoLik(d)                     src/pseudolik.jl:1388-1425
+ *   parameters!(net) / upper(net)       src/snaq_optimization.jl:54-101,275-279
+ *   objective closure of optBL!         src/snaq_optimization.jl:368-380
+ *   topologyQpseudolik! (score only)    src/pseudolik.jl:1342-1378
+ *
+ * The reference has no FFI for this path (it is pure Julia); the entry points
+ * below are what a Julia `ccall` shim binds.  Plain C
+ * types only: the caller owns every host buffer, the engine copies during the
+ * call and never retains a host pointer.  Every function returns 0 on success
+ * and a nonzero SNAQ_E* code on failure; snaq_last_error() gives the message.
+ * There is no CPU fallback: without a CUDA device snaq_create() fails.
+ */
+#ifndef SNAQ_B200_H
+#define SNAQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes -------------------------------------------------------- */
+#define SNAQ_OK            0
+#define SNAQ_EINVAL        1   /* bad argument / inconsistent flat network     */
+#define SNAQ_ECUDA         2   /* CUDA runtime error (message has the detail)  */
+#define SNAQ_ENODATA       3   /* set_data / set_network not called yet        */
+#define SNAQ_ERANGE        4   /* parameter outside its bounds: gamma or gammaz
+                                  outside [0,1] (src/snaq_optimization.jl:213,
+                                  221,228) or a length < 0 (src/auxiliary.jl:119) */
+#define SNAQ_ENUMERIC      5   /* sum(expCF)==0 (src/pseudolik.jl:1391), type-5
+                                  expCF not summing to 1 (:1049), or merged
+                                  length < -log(1.5) (src/auxiliary.jl:120)    */
+#define SNAQ_ETOPOLOGY     6   /* network is not level-1 / not what the flat
+                                  format promises                              */
+#define SNAQ_ENOMEM        7
+
+/* ---- node / edge flag bits ---------------------------------------------- */
+/* Node flags mirror the PhyloNetworks slots the hot path reads through the
+ * accessors of src/types.jl:15-24.                                            */
+#define SNAQ_NODE_LEAF          0x01u
+#define SNAQ_NODE_HYBRID        0x02u
+#define SNAQ_NODE_HASHYBEDGE    0x04u  /* hasHybEdge     src/types.jl:15 */
+#define SNAQ_NODE_BADDIAMOND1   0x08u  /* isBadDiamondI  src/types.jl:16 */
+#define SNAQ_NODE_BADDIAMOND2   0x10u  /* isBadDiamondII src/types.jl:17 */
+#define SNAQ_NODE_BADTRIANGLE   0x20u  /* isBadTriangle  src/types.jl:20 */
+/* Edge flags: src/types.jl:5-7 plus the PN Edge fields hybrid/ismajor/ischild1 */
+#define SNAQ_EDGE_HYBRID        0x01u
+#define SNAQ_EDGE_MAJOR         0x02u
+#define SNAQ_EDGE_ISCHILD1      0x04u
+#define SNAQ_EDGE_IDENTIFIABLE  0x08u  /* istIdentifiable  src/types.jl:5 */
+#define SNAQ_EDGE_FROMBD1       0x10u  /* fromBadDiamondI  src/types.jl:6 */
+
+/*
+ * Flattened HybridNetwork: everything the hot path reads from the reference's
+ * object graph.  Array order IS information: node[]/edge[] are
+ * in net.node / net.edge order (the x layout follows net.edge order,
+ * src/snaq_optimization.jl:64-91), node_edge keeps each node.edge order,
+ * hybrid[] is net.hybrid order and leaf[] is net.leaf order (leaves are pruned
+ * in that order, src/pseudolik.jl:476-483).
+ */
+typedef struct snaq_flatnet {
+    int32_t n_nodes;
+    int32_t n_edges;
+    int32_t n_hybrids;
+    int32_t n_leaves;
+    /* nodes */
+    const int32_t *node_number;   /* [n_nodes] PN node.number                        */
+    const uint32_t *node_flags;   /* [n_nodes] SNAQ_NODE_* bits                       */
+    const int32_t *node_incycle;  /* [n_nodes] hybrid node NUMBER of its cycle, or -1 */
+    const double  *node_gammaz;   /* [n_nodes] gammaz, -1.0 when unset                */
+    const int32_t *node_taxon;    /* [n_nodes] taxon id (0-based index into the data's
+                                     taxon list) for leaves, -1 otherwise             */
+    const int32_t *node_edge;     /* [n_nodes*3] edge INDICES in node.edge order,
+                                     -1 padded                                         */
+    /* edges */
+    const int32_t *edge_number;   /* [n_edges] PN edge.number                         */
+    const uint32_t *edge_flags;   /* [n_edges] SNAQ_EDGE_* bits                       */
+    const int32_t *edge_incycle;  /* [n_edges] hybrid node NUMBER, or -1              */
+    const double  *edge_length;   /* [n_edges]                                        */
+    const double  *edge_gamma;    /* [n_edges] 1.0 for tree edges                     */
+    const int32_t *edge_node;     /* [n_edges*2] node INDICES in edge.node order      */
+    /* orders */
+    const int32_t *hybrid;        /* [n_hybrids] node indices, net.hybrid order       */
+    const int32_t *leaf;          /* [n_leaves]  node indices, net.leaf order         */
+} snaq_flatnet;
+
+typedef struct snaq_ctx snaq_ctx;   /* opaque: one ctx <=> one CUDA device + stream */
+
+typedef struct snaq_opts {
+    int32_t device;        /* CUDA device ordinal                                  */
+    int32_t rank;          /* quartet-sharded mode: this rank (0 if unsharded)     */
+    int32_t world_size;    /* quartet-sharded mode: number of ranks (1 if not)     */
+    int32_t reserved;
+} snaq_opts;
+
+/* ---- life cycle ---------------------------------------------------------- */
+int snaq_create(const snaq_opts *opts, snaq_ctx **out);
+int snaq_destroy(snaq_ctx *ctx);
+const char *snaq_last_error(const snaq_ctx *ctx);   /* ctx may be NULL: last create error */
+const char *snaq_version(void);
+
+/* ---- data: DataCF resident in HBM (src/types.jl:217-273) ----------------- */
+/* taxa[q*4+i] = 0-based taxon id of the i-th taxon of quartet q, in the data's
+ * own order (which fixes the 12|34, 13|24, 14|23 order of obsCF).             */
+int snaq_set_data(snaq_ctx *ctx, int32_t ntaxa, int64_t nq,
+                  const uint16_t *taxa, const double *obscf);
+/* bootstrap refresh: overwrite obsCF in place (src/readquartetdata.jl:211-217) */
+int snaq_set_obscf(snaq_ctx *ctx, const double *obscf);
+/* q.sampled mask (src/update.jl:386,406,442); NULL = all sampled             */
+int snaq_set_sampled(snaq_ctx *ctx, const uint8_t *mask);
+
+/* ---- topology: extractQuartet!(net,d) ------------------------------------ */
+/* Full rebuild of the device descriptor table from a flat network.  Also does
+ * parameters!(net): fixes the x layout.                                       */
+int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net);
+/* Incremental variant: only quartets whose taxa see one of the touched cycles /
+ * edges are re-described.  touched_taxa is a bitmap-free list of taxon ids whose
+ * pruned sub-network may have changed; quartets containing none of them keep
+ * their descriptor.  Falls back to a full rebuild when n_touched<0.            */
+int snaq_patch_network(snaq_ctx *ctx, const snaq_flatnet *net,
+                       const int32_t *touched_taxa, int32_t n_touched);
+
+/* parameters!(net): src/snaq_optimization.jl:54-101.  x = [gamma | t | gammaz].
+ * numht: edge numbers (gamma, t) and "<node><1|2>" pseudo numbers (gammaz).
+ * Any out pointer may be NULL.                                                */
+int snaq_num_params(snaq_ctx *ctx, int32_t *nparams, int32_t *n_gamma,
+                    int32_t *n_t, int32_t *n_gammaz);
+int snaq_get_params(snaq_ctx *ctx, double *x, int32_t *numht,
+                    double *upper /* upper(net), src/snaq_optimization.jl:275 */);
+
+/* ---- the hot path --------------------------------------------------------- */
+/* out[p] = logPseudoLik(d) after calculateExpCFAll!(d, X[p,:], net), for P
+ * parameter vectors (row-major P x nparams).  Stateless evaluation: every
+ * sampled quartet is recomputed (the reference's `changed` gating,
+ * src/snaq_optimization.jl:202-206, only skips work, never changes a value).
+ * In quartet-sharded mode out[p] is this rank's partial sum unless the caller
+ * all-reduces it (see snaq_eval_device).                                       */
+int snaq_eval(snaq_ctx *ctx, int32_t P, int32_t nparams,
+              const double *X, double *out);
+/* Same, X and out already in device memory (used by the in-engine optimiser,
+ * the benchmark and the NCCL-sharded path).  stream is a cudaStream_t.         */
+int snaq_eval_device(snaq_ctx *ctx, int32_t P, int32_t nparams,
+                     const double *dX, double *dout, void *stream);
+
+/* Per-quartet results for one parameter vector x (host buffers):
+ * expcf[nq*3] (q.qnet.expCF), logpl[nq] (q.logPseudoLik, src/pseudolik.jl:1407),
+ * deltacf[nq] (calculateDeltaCF, src/pseudolik.jl:491-498).  Any may be NULL.  */
+int snaq_eval_quartets(snaq_ctx *ctx, int32_t nparams, const double *x,
+                       double *expcf, double *logpl, double *deltacf);
+
+/* ---- descriptors for parity checks ------------------------ */
+/* which[nq]       : 1 tree-like, 2 four-cycle (src/types.jl:180)
+ * ntype[nq], types[nq*max_types]: typeHyb codes (2..5; type 1 dropped) of the
+ *                   hybrids that survive, in net.hybrid order
+ * formula[nq*3]   : which==1: 1 major / 2 minor (src/pseudolik.jl:1230-1247);
+ *                   which==2: 11,12,13 = which of cf1,cf2,cf3 lands there
+ *                   (src/pseudolik.jl:1008-1048)
+ * hasedge[nq*nparams] : 0/1, aligned with x (src/pseudolik.jl:392-464)
+ * Any may be NULL.                                                             */
+int snaq_get_descriptors(snaq_ctx *ctx, int8_t *which, int8_t *ntype,
+                         int8_t *types, int32_t max_types, int8_t *formula,
+                         uint8_t *hasedge);
+
+/* engine counters: [0] launches of the eval kernel, [1] quartet-evals done,
+ * [2] H2D bytes, [3] D2H bytes, [4] descriptor words in HBM, [5] launches of
+ * the descriptor-build kernels                                                 */
+int snaq_get_counters(snaq_ctx *ctx, int64_t out[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNAQ_B200_H */

@@ -1,0 +1,8 @@
+"""snaq.jl_b200 — B200-native quartet-pseudolikelihood engine for SNaQ.
+
+Host-side mirror of the reference's hot-path interface (same names, argument
+meaning and error behaviour) over the C ABI of ``include/snaq_b200.h``.
+"""
+from .network import (HybridNetwork, Node, Edge, SnaqError, readnewicklevel1,  # noqa: F401
+                      network_from_lists, hybridEdges, getOtherNode)
+from .datacf import DataCF, readtableCF  # noqa: F401

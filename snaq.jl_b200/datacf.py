@@ -1,0 +1,106 @@
+"""``Quartet`` / ``DataCF`` (src/types.jl:217-273) as flat arrays, and ``readtableCF``
+(src/readquartetdata.jl:97-217).
+
+The reference keeps one heap object per quartet; here a DataCF is four arrays
+(taxon ids nq x 4, obsCF nq x 3, ngenes, sampled) that go to HBM unchanged.
+"""
+from __future__ import annotations
+
+import csv
+import itertools
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from .network import SnaqError
+
+
+class DataCF:
+    def __init__(self, taxa: Sequence[str], quartet_taxa: np.ndarray, obscf: np.ndarray,
+                 ngenes: Optional[np.ndarray] = None):
+        self.taxa: List[str] = list(taxa)                      # tiplabels(d)
+        self.quartet_taxa = np.ascontiguousarray(quartet_taxa, dtype=np.uint16).reshape(-1, 4)
+        self.obsCF = np.ascontiguousarray(obscf, dtype=np.float64).reshape(-1, 3)
+        nq = self.quartet_taxa.shape[0]
+        if self.obsCF.shape[0] != nq:
+            raise SnaqError("observed CF table and quartet list have different lengths")
+        if np.any((self.obsCF < 0.0) | (self.obsCF > 1.0)):
+            raise SnaqError("obsCF must be between (0,1)")      # src/types.jl:237-239
+        self.ngenes = np.full(nq, -1.0) if ngenes is None else np.asarray(ngenes, dtype=np.float64)
+        self.sampled = np.ones(nq, dtype=np.uint8)             # q.sampled
+        # filled by the engine (q.qnet.expCF, q.logPseudoLik, q.deltaCF)
+        self.expCF: Optional[np.ndarray] = None
+        self.logPseudoLik: Optional[np.ndarray] = None
+        self.deltaCF: Optional[np.ndarray] = None
+
+    @property
+    def numQuartets(self) -> int:
+        return self.quartet_taxa.shape[0]
+
+    def quartet_names(self, i: int) -> List[str]:
+        return [self.taxa[t] for t in self.quartet_taxa[i]]
+
+    @classmethod
+    def from_rows(cls, rows: Iterable[Sequence], taxa: Optional[Sequence[str]] = None) -> "DataCF":
+        """rows: (t1,t2,t3,t4,cf12_34,cf13_24,cf14_23[,ngenes])."""
+        rows = [tuple(r) for r in rows]
+        if taxa is None:
+            seen = {}
+            for r in rows:
+                for t in r[:4]:
+                    seen.setdefault(str(t), None)
+            taxa = _sort_taxa(list(seen))
+        tid = {t: i for i, t in enumerate(taxa)}
+        qt = np.array([[tid[str(t)] for t in r[:4]] for r in rows], dtype=np.uint16).reshape(-1, 4)
+        cf = np.array([[float(v) for v in r[4:7]] for r in rows], dtype=np.float64).reshape(-1, 3)
+        ng = np.array([float(r[7]) if len(r) > 7 and r[7] not in ("", None) else -1.0 for r in rows])
+        return cls(taxa, qt, cf, ng)
+
+    @classmethod
+    def all_quartets(cls, taxa: Sequence[str], obscf: np.ndarray) -> "DataCF":
+        """All C(n,4) four-taxon sets in lexicographic order of taxon index
+        (``allQuartets``, src/readquartetdata.jl:272-303)."""
+        n = len(taxa)
+        qt = np.array(list(itertools.combinations(range(n), 4)), dtype=np.uint16)
+        return cls(taxa, qt, obscf)
+
+
+def _sort_taxa(names: List[str]) -> List[str]:
+    # sorttaxa!: numbers first in numeric order, then strings (src/auxiliary.jl)
+    def key(s):
+        try:
+            return (0, int(s), "")
+        except ValueError:
+            return (1, 0, s)
+    return sorted(names, key=key)
+
+
+def readtableCF(path: str, delim: str = ",") -> DataCF:
+    """``readtableCF(file)``: first 4 columns are taxa; CF columns are named
+    CF12_34/CF13_24/CF14_23 (or CF12.34 ...) or else are columns 5,6,7; an optional
+    ``ngenes`` column is kept (src/readquartetdata.jl:97-150)."""
+    with open(path, newline="") as fh:
+        rd = csv.reader(fh, delimiter=delim)
+        header = next(rd)
+        body = [r for r in rd if r]
+    low = [h.strip() for h in header]
+
+    def find(*names):
+        for nm in names:
+            if nm in low:
+                return low.index(nm)
+        return None
+
+    c1 = find("CF12_34", "CF12.34")
+    c2 = find("CF13_24", "CF13.24")
+    c3 = find("CF14_23", "CF14.23")
+    if c1 is None or c2 is None or c3 is None:
+        c1, c2, c3 = 4, 5, 6
+    cn = find("ngenes")
+    rows = []
+    for r in body:
+        row = [r[0].strip(), r[1].strip(), r[2].strip(), r[3].strip(), r[c1], r[c2], r[c3]]
+        if cn is not None:
+            row.append(r[cn])
+        rows.append(row)
+    return DataCF.from_rows(rows)

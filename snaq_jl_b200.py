@@ -1,0 +1,12 @@
+"""Import alias: the package directory is ``snaq.jl_b200/`` (a dot is not legal in a
+Python module name), so ``import snaq_jl_b200`` loads it from there."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "snaq.jl_b200")
+_spec = importlib.util.spec_from_file_location(
+    "snaq_jl_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["snaq_jl_b200"] = _mod
+_spec.loader.exec_module(_mod)
