@@ -1197,6 +1197,37 @@ int oracle_parameters(const snaq_flatnet *f, int32_t *nparams, int32_t *nh, int3
     });
 }
 
+
+/* debugging aid: dump the pruned quartet network before and after calculateExpCFAll! */
+static void dumpNet(const Net &q, const char *title) {
+    fprintf(stderr, "--- %s: numhybrids %d which %d t1 %g\n", title, q.numhybrids, q.which, q.t1);
+    for (size_t i = 0; i < q.node.size(); i++) {
+        const Node &n = q.N[q.node[i]];
+        fprintf(stderr, "  node[%zu] num %d leaf %d hyb %d deg %d inCycle %d taxon %d type %d edges:", i, n.number, n.leaf, n.hybrid, n.ne, n.inCycle, n.taxon, n.typeHyb);
+        for (int j = 0; j < n.ne; j++) fprintf(stderr, " %d", q.E[n.edge[j]].number);
+        fprintf(stderr, "\n");
+    }
+    for (size_t i = 0; i < q.edge.size(); i++) {
+        const Edge &e = q.E[q.edge[i]];
+        fprintf(stderr, "  edge %d: %d--%d len %.6f hyb %d maj %d gamma %.4f ident %d inCycle %d\n", e.number, q.N[e.node[0]].number, q.N[e.node[1]].number, e.length, e.hybrid, e.ismajor, e.gamma, e.ident, e.inCycle);
+    }
+}
+int oracle_debug_quartet(const snaq_flatnet *f, const uint16_t *taxa, const double *x) {
+    return run([&] {
+        Net g; fromFlat(f, g);
+        Params p = parameters(g);
+        if (x) applyParameters(g, p, x);
+        int tx[4] = {taxa[0], taxa[1], taxa[2], taxa[3]};
+        Net q; extractQuartet(g, p, tx, q);
+        dumpNet(q, "after extractQuartet!");
+        int perm[3] = {0, 0, 0};
+        identifyQuartet(q);
+        dumpNet(q, "after identifyQuartet!");
+        eliminateHybridization(q);
+        dumpNet(q, "after eliminateHybridization!");
+    });
+}
+
 /*
  * extractQuartet!(net,d) followed by calculateExpCFAll!(deepcopy(qnet)) per
  * quartet, under parameter vector x (NULL = the network's own values).

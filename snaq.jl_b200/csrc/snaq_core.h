@@ -1,0 +1,639 @@
+/*
+ * snaq_core.h — the per-quartet device functions of the engine.
+ *
+ *   snaq_build_quartet : structural replacement of extractQuartet! +
+ *                        identifyQuartet! + eliminateHybridization! +
+ *                        updateSplit!/updateFormula!  (reference:
+ *                        src/pseudolik.jl:472-540, :746-848, :866-1145, :1207-1247)
+ *   snaq_eval_program  : calculateExpCF! / quartetType5! (src/pseudolik.jl:1255-1275,
+ *                        :967-1052) for one parameter vector
+ *   snaq_quartet_loglik: logPseudoLik(quartet) (src/pseudolik.jl:1388-1410)
+ *
+ * The reference prunes a deep copy of the network leaf by leaf for every quartet.
+ * Here the network is summarised once per topology into small tables (blob tree
+ * with parent/depth, per-cycle ordered edge slots, per-(cycle,taxon) block index)
+ * and each quartet is classified in O(depth) from them: a level-1 network is a
+ * tree of vertex-disjoint cycles, every cycle node owns one "block" of taxa, and
+ * the way the four taxa fall into the blocks of the cycles on their connecting
+ * paths determines the reference's case.  The result is a short
+ * program of u16 words over the slots of the extended parameter vector
+ *   xe = [ x (gamma | t | gammaz, parameters!(net)) | constants ]
+ * that the evaluation kernels interpret for every candidate x.
+ *
+ * Everything here is `SNAQ_HD` so that tests/hostsim can run the exact same code
+ * on the CPU against the oracle; the shipped library only runs it on the GPU.
+ */
+#ifndef SNAQ_CORE_H
+#define SNAQ_CORE_H
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SNAQ_HD __host__ __device__ __forceinline__
+#else
+#define SNAQ_HD inline
+#endif
+
+#define SNAQ_MAX_HYB 32          /* max hybrid nodes tracked in the parity descriptor */
+#define SNAQ_MAX_SLOT 4095       /* slots are 12 bit inside term headers */
+#define SNAQ_MAX_PATH 512        /* max blob-tree nodes on a quartet's internal path */
+
+/* program header (word 0) */
+#define SNAQ_KIND_TREE   0u      /* which==1: one internal edge of length t1        */
+#define SNAQ_KIND_T5     1u      /* which==2: 4-cycle, gamma + two cycle segments   */
+#define SNAQ_KIND_T5BD1  2u      /* which==2: bad diamond I, two gammaz             */
+/* header: bits 0-1 kind | bits 2-4 perm (tree: position of the major CF; type 5:
+ * permutation index) | bits 5-8 nterms | bits 9-15 n0 (main path pieces)          */
+#define SNAQ_HDR(kind, perm, nterms, n0) ((uint16_t)((kind) | ((perm) << 2) | ((nterms) << 5) | ((n0) << 9)))
+#define SNAQ_HDR_KIND(h)   ((h) & 3u)
+#define SNAQ_HDR_PERM(h)   (((h) >> 2) & 7u)
+#define SNAQ_HDR_NTERMS(h) (((h) >> 5) & 15u)
+#define SNAQ_HDR_N0(h)     (((h) >> 9) & 127u)
+/* term header: bits 0-1 type | bit 2 flag | bits 4-15 slot */
+#define SNAQ_T2   0u   /* 3-cycle, hybrid's child is a leaf  (eliminateTriangle! case 1) */
+#define SNAQ_T3   1u   /* 2-cycle on the internal path       (eliminateLoop! internal)   */
+#define SNAQ_T4   2u   /* 3-cycle, hybrid's child internal   (eliminateTriangle! case 2) */
+#define SNAQ_TZ   3u   /* edge -log(1-gammaz) left by a pruned bad diamond I             */
+#define SNAQ_TERM(type, flag, slot) ((uint16_t)((type) | ((flag) << 2) | ((slot) << 4)))
+
+/* build errors */
+#define SNAQ_B_OK          0
+#define SNAQ_B_POLYTOMY    1   /* four taxa meet at a tree node: not a binary level-1 network */
+#define SNAQ_B_BLOCKS      2   /* block pattern inconsistent with the blob tree                */
+#define SNAQ_B_OVERFLOW    3   /* more pieces/terms than the header can count                  */
+
+/* evaluation status bits (OR-ed into a device status word) */
+#define SNAQ_S_NEGLEN      1u  /* merged length < -log(1.5): src/auxiliary.jl:120 */
+#define SNAQ_S_ZEROSUM     2u  /* sum(expCF)==0: src/pseudolik.jl:1391            */
+#define SNAQ_S_NAN         4u
+
+#define SNAQ_MINLEN (-0.4054651081081644)
+#define SNAQ_LOG3   1.0986122886681098
+
+typedef struct SnaqTables {
+    int32_t ntaxa, n_tnodes, n_cycles, nparams, n_xe, n_hybrids;
+    /* blob tree T': cycles contracted to supernodes, rooted arbitrarily */
+    const uint16_t *leaf_tnode;  /* [ntaxa]     T' node of each taxon (0xFFFF: taxon not in net) */
+    const uint16_t *parent;      /* [n_tnodes]  parent (root: itself)                     */
+    const uint16_t *depth;       /* [n_tnodes]                                            */
+    const int16_t  *tcycle;      /* [n_tnodes]  cycle index of a supernode, else -1       */
+    const uint16_t *pslot;       /* [n_tnodes]  xe slot of the edge to the parent         */
+    const uint16_t *torder;      /* [n_tnodes]  position of a tree node in net.node       */
+    /* cycles: position 0 = hybrid node, 1 = its major parent, ..., k-1 = minor parent.
+     * edge j joins positions j and (j+1)%k: j=0 major hybrid edge, j=k-1 minor one.      */
+    const uint8_t  *blk;         /* [n_cycles*ntaxa] position whose block holds the taxon */
+    const uint16_t *cyc_k;       /* [n_cycles]                                            */
+    const uint16_t *cyc_off;     /* [n_cycles]  offset of the k edge slots in cyc_slot    */
+    const uint16_t *cyc_slot;    /* edge-length slots                                     */
+    const uint16_t *cyc_gslot;   /* [n_cycles]  slot of the minor gamma; bad diamond I:
+                                    slot of gammaz(major side), minor side is +1         */
+    const uint8_t  *cyc_flags;   /* [n_cycles]  bit0 bad diamond I                        */
+    const uint8_t  *cyc_hyb;     /* [n_cycles]  index of the hybrid in net.hybrid order   */
+    const uint16_t *cyc_order;   /* per cycle position (same offsets as cyc_slot): position of
+                                    that cycle node in net.node                            */
+} SnaqTables;
+
+/* parity descriptor of one quartet */
+typedef struct SnaqQuartetInfo {
+    int8_t which;                 /* 1 or 2                                          */
+    int8_t formula[3];            /* which==1: 1 major/2 minor; which==2: 11,12,13   */
+    int8_t type[SNAQ_MAX_HYB];    /* per hybrid (net.hybrid order): 0 or 2..5        */
+} SnaqQuartetInfo;
+
+typedef struct SnaqWriter {
+    uint16_t *out;   /* NULL: count only */
+    int n, cap;
+} SnaqWriter;
+
+SNAQ_HD void snaq_put(SnaqWriter &w, unsigned v) {
+    if (w.out && w.n < w.cap) w.out[w.n] = (uint16_t)v;
+    w.n++;
+}
+
+SNAQ_HD int snaq_lca(const SnaqTables &T, int u, int v) {
+    while (T.depth[u] > T.depth[v]) u = T.parent[u];
+    while (T.depth[v] > T.depth[u]) v = T.parent[v];
+    while (u != v) { u = T.parent[u]; v = T.parent[v]; }
+    return u;
+}
+
+/* emit the slots of cycle edges j = lo .. hi-1 (the arc between positions lo and hi) */
+SNAQ_HD int snaq_put_arc(const SnaqTables &T, int c, int lo, int hi, SnaqWriter &w) {
+    const uint16_t *s = T.cyc_slot + T.cyc_off[c];
+    for (int j = lo; j < hi; j++) snaq_put(w, s[j]);
+    return hi - lo;
+}
+
+SNAQ_HD int snaq_deeper(const SnaqTables &T, int a, int b) { return T.depth[a] >= T.depth[b] ? a : b; }
+
+/* positions of the four taxa in cycle c */
+SNAQ_HD void snaq_positions(const SnaqTables &T, int c, const uint16_t tx[4], int pos[4]) {
+    const uint8_t *b = T.blk + (size_t)c * T.ntaxa;
+    for (int i = 0; i < 4; i++) pos[i] = b[tx[i]];
+}
+
+/*
+ * Classification of a supernode (cycle c) met on the internal path of a tree-like
+ * quartet.  (p,q) are the taxa on the J1 side, (r,s) on the J2 side; role 0 =
+ * interior, 1 = the supernode is J1 (p,q in different blocks), 2 = it is J2.
+ */
+#define SNAQ_C_BAD    (-1)
+#define SNAQ_C_OPEN   0   /* hybrid block not hit: the cycle is a plain path (arc lo..hi may be empty) */
+#define SNAQ_C_T2     2
+#define SNAQ_C_T3     3
+#define SNAQ_C_T4     4
+#define SNAQ_C_TZ     6
+typedef struct SnaqCyc {
+    int cls;      /* SNAQ_C_*                                                          */
+    int lo, hi;   /* OPEN: arc of plain pieces; T2: arc e; T3: hit position in lo; T4: the two hit positions */
+    int other;    /* T2/TZ: position of `other`                                         */
+    int rep;      /* position of the cycle node that ends up as the degree-3 junction (ends only) */
+} SnaqCyc;
+
+SNAQ_HD SnaqCyc snaq_classify_cycle(const SnaqTables &T, int c, const int pos[4], int p, int q, int r, int s, int role) {
+    SnaqCyc o;
+    o.cls = SNAQ_C_BAD; o.lo = o.hi = o.other = o.rep = 0;
+    const int k = T.cyc_k[c];
+    const int bd1 = T.cyc_flags[c] & 1;
+    if (role == 0) {
+        int u = pos[p], v = pos[r];
+        if (pos[q] != u || pos[s] != v || u == v) return o;
+        if (u != 0 && v != 0) { o.cls = SNAQ_C_OPEN; o.lo = u < v ? u : v; o.hi = u < v ? v : u; return o; }
+        if (bd1) return o;                            /* a bad diamond I hybrid has a single leaf below it */
+        o.cls = SNAQ_C_T3; o.lo = u ? u : v;          /* eliminateLoop!(internal=true) */
+        return o;
+    }
+    /* end of the path: cherry taxa (a,b) in two different blocks, the far taxa in a third */
+    int a = role == 1 ? p : r, b = role == 1 ? q : s, f1 = role == 1 ? r : p, f2 = role == 1 ? s : q;
+    int u1 = pos[a], u2 = pos[b], wv = pos[f1];
+    if (pos[f2] != wv || u1 == u2 || u1 == wv || u2 == wv) return o;
+    int lo = u1 < u2 ? u1 : u2, hi = u1 < u2 ? u2 : u1;
+    if (u1 != 0 && u2 != 0 && wv != 0) {              /* hybrid block not hit: path 1..k-1 */
+        int m = wv < lo ? lo : (wv > hi ? hi : wv);   /* median of the three positions: the junction */
+        o.cls = SNAQ_C_OPEN; o.lo = m < wv ? m : wv; o.hi = m < wv ? wv : m; o.rep = m;
+        return o;
+    }
+    if (wv == 0) {                                    /* type 4: the hybrid block holds the two far taxa */
+        if (bd1) return o;
+        o.cls = SNAQ_C_T4; o.lo = lo; o.hi = hi;
+        /* `other` = first of the two hit nodes in qnet.node order (src/pseudolik.jl:791-796) */
+        const uint16_t *ord = T.cyc_order + T.cyc_off[c];
+        o.rep = ord[lo] < ord[hi] ? lo : hi;
+        return o;
+    }
+    o.other = u1 ? u1 : u2;                           /* type 2: hybrid block holds one cherry taxon */
+    if (bd1) {                                        /* pruned bad diamond I: src/pseudolik.jl:206-239 */
+        if (k != 4 || wv != 2) return o;
+        o.cls = SNAQ_C_TZ; o.rep = 0;
+        return o;
+    }
+    o.cls = SNAQ_C_T2; o.rep = o.other;
+    o.lo = o.other < wv ? o.other : wv; o.hi = o.other < wv ? wv : o.other;
+    return o;
+}
+
+/* which of cf(12|34), cf(13|24), cf(14|23) a pair of roles (1..4) selects: 1,2,3 */
+SNAQ_HD int snaq_pair_class(int r1, int r2) {
+    int lo = r1 < r2 ? r1 : r2, hi = r1 < r2 ? r2 : r1;
+    if ((lo == 1 && hi == 2) || (lo == 3 && hi == 4)) return 1;
+    if ((lo == 1 && hi == 3) || (lo == 2 && hi == 4)) return 2;
+    return 3;
+}
+/* permutation index <-> (p0,p1,p2), a permutation of (1,2,3) */
+SNAQ_HD int snaq_perm_index(int p0, int p1) {
+    return (p0 - 1) * 2 + ((p1 < ((p0 == 1) ? 3 : (p0 == 2 ? 3 : 2))) ? 0 : 1);
+}
+SNAQ_HD void snaq_perm_decode(int idx, int perm[3]) {
+    const int tab[6][3] = {{1, 2, 3}, {1, 3, 2}, {2, 1, 3}, {2, 3, 1}, {3, 1, 2}, {3, 2, 1}};
+    perm[0] = tab[idx][0]; perm[1] = tab[idx][1]; perm[2] = tab[idx][2];
+}
+
+/*
+ * Build the evaluation program of one quartet.  tx = the four taxon ids in the
+ * data's order.  Returns SNAQ_B_*; w.n is the program length in words.
+ */
+SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWriter &w, SnaqQuartetInfo *info) {
+    int L[4];
+    for (int i = 0; i < 4; i++) {
+        L[i] = T.leaf_tnode[tx[i]];
+        if (L[i] == 0xFFFF) return SNAQ_B_BLOCKS;
+    }
+    if (info) {
+        info->which = 1;
+        info->formula[0] = info->formula[1] = info->formula[2] = 2;
+        for (int i = 0; i < SNAQ_MAX_HYB; i++) info->type[i] = 0;
+    }
+    int l01 = snaq_lca(T, L[0], L[1]), l23 = snaq_lca(T, L[2], L[3]);
+    int l02 = snaq_lca(T, L[0], L[2]), l13 = snaq_lca(T, L[1], L[3]);
+    int l03 = snaq_lca(T, L[0], L[3]), l12 = snaq_lca(T, L[1], L[2]);
+    int S0 = T.depth[l01] + T.depth[l23], S1 = T.depth[l02] + T.depth[l13], S2 = T.depth[l03] + T.depth[l12];
+    const int hdr_at = w.n;
+    snaq_put(w, 0);
+    int pos[4];
+    if (S0 == S1 && S1 == S2) {
+        /* the four taxa meet in one blob: it must be a cycle with four hit blocks */
+        int X = snaq_deeper(T, snaq_deeper(T, l01, l02), l12);
+        int c = T.tcycle[X];
+        if (c < 0) return SNAQ_B_POLYTOMY;
+        snaq_positions(T, c, tx, pos);
+        /* sort the four data indices by position */
+        int o[4] = {0, 1, 2, 3};
+        for (int i = 1; i < 4; i++)
+            for (int j = i; j > 0 && pos[o[j]] < pos[o[j - 1]]; j--) { int t = o[j]; o[j] = o[j - 1]; o[j - 1] = t; }
+        if (pos[o[0]] == pos[o[1]] || pos[o[1]] == pos[o[2]] || pos[o[2]] == pos[o[3]]) return SNAQ_B_BLOCKS;
+        if (pos[o[0]] == 0) {
+            /* type 5 (quartetType5!): leaf1 below the hybrid, leaf2 / leaf3 at the first hit node
+             * on the major / minor side, leaf4 in between */
+            int role[4];
+            role[o[0]] = 1; role[o[1]] = 2; role[o[3]] = 3; role[o[2]] = 4;
+            int p0 = snaq_pair_class(role[0], role[1]), p1 = snaq_pair_class(role[0], role[2]);
+            int p2 = snaq_pair_class(role[0], role[3]);
+            int pidx = snaq_perm_index(p0, p1);
+            if (info) {
+                info->which = 2;
+                info->formula[0] = (int8_t)(10 + p0); info->formula[1] = (int8_t)(10 + p1); info->formula[2] = (int8_t)(10 + p2);
+                info->type[T.cyc_hyb[c]] = 5;
+            }
+            const int g = T.cyc_gslot[c];
+            if (T.cyc_flags[c] & 1) {
+                snaq_put(w, g);
+                snaq_put(w, g + 1);
+                if (w.out && hdr_at < w.cap) w.out[hdr_at] = SNAQ_HDR(SNAQ_KIND_T5BD1, pidx, 0, 0);
+            } else {
+                int a = pos[o[1]], m = pos[o[2]], b = pos[o[3]];
+                snaq_put(w, g);
+                snaq_put(w, (unsigned)(m - a) | ((unsigned)(b - m) << 8));
+                snaq_put_arc(T, c, a, m, w);
+                snaq_put_arc(T, c, m, b, w);
+                if (w.out && hdr_at < w.cap) w.out[hdr_at] = SNAQ_HDR(SNAQ_KIND_T5, pidx, 0, 0);
+            }
+            return SNAQ_B_OK;
+        }
+        /* hybrid block not hit: the cycle is a path, internal edge between the 2nd and 3rd hit node */
+        int n0 = snaq_put_arc(T, c, pos[o[1]], pos[o[2]], w);
+        int mate = (o[0] == 0) ? o[1] : (o[1] == 0 ? o[0] : (o[2] == 0 ? o[3] : o[2]));   /* partner of data taxon 0 */
+        int maj = mate - 1;
+        if (n0 > 127) return SNAQ_B_OVERFLOW;
+        if (info) info->formula[maj] = 1;
+        if (w.out && hdr_at < w.cap) w.out[hdr_at] = SNAQ_HDR(SNAQ_KIND_TREE, maj, 0, n0);
+        return SNAQ_B_OK;
+    }
+    /* resolved split: (p,q | r,s) */
+    int maj = (S0 > S1 && S0 > S2) ? 0 : ((S1 > S0 && S1 > S2) ? 1 : 2);
+    int p = 0, q = maj + 1, r, s;
+    if (maj == 0) { r = 2; s = 3; } else if (maj == 1) { r = 1; s = 3; } else { r = 1; s = 2; }
+    int lca6[4][4];
+    lca6[0][1] = lca6[1][0] = l01; lca6[2][3] = lca6[3][2] = l23; lca6[0][2] = lca6[2][0] = l02;
+    lca6[1][3] = lca6[3][1] = l13; lca6[0][3] = lca6[3][0] = l03; lca6[1][2] = lca6[2][1] = l12;
+    int J1 = snaq_deeper(T, snaq_deeper(T, lca6[p][q], lca6[p][r]), lca6[q][r]);
+    int J2 = snaq_deeper(T, snaq_deeper(T, lca6[r][s], lca6[r][p]), lca6[s][p]);
+    if (J1 == J2) return SNAQ_B_BLOCKS;
+    int apex = snaq_lca(T, J1, J2);
+    /* the internal path in order J1 .. apex .. J2 */
+    uint16_t seq[SNAQ_MAX_PATH];
+    int ns = 0;
+    for (int v = J1;; v = T.parent[v]) {
+        if (ns >= SNAQ_MAX_PATH) return SNAQ_B_OVERFLOW;
+        seq[ns++] = (uint16_t)v;
+        if (v == apex) break;
+    }
+    const int iapex = ns - 1;
+    {
+        int cnt = 0;
+        for (int v = J2; v != apex; v = T.parent[v]) cnt++;
+        if (ns + cnt > SNAQ_MAX_PATH) return SNAQ_B_OVERFLOW;
+        int idx = ns + cnt - 1;
+        for (int v = J2; v != apex; v = T.parent[v]) seq[idx--] = (uint16_t)v;
+        ns += cnt;
+    }
+    /* classify the two ends; find the type-4 ends (the only terms that can be negative, so the only
+     * ones for which the reference's merge order matters once the 10.0 cap is reached) */
+    SnaqCyc e1, e2;
+    e1.cls = e2.cls = SNAQ_C_OPEN; e1.lo = e1.hi = e2.lo = e2.hi = 0; e1.rep = e2.rep = 0; e1.other = e2.other = 0;
+    const int c1 = T.tcycle[J1], c2 = T.tcycle[J2];
+    if (c1 >= 0) { snaq_positions(T, c1, tx, pos); e1 = snaq_classify_cycle(T, c1, pos, p, q, r, s, 1); if (e1.cls < 0) return SNAQ_B_BLOCKS; }
+    if (c2 >= 0) { snaq_positions(T, c2, tx, pos); e2 = snaq_classify_cycle(T, c2, pos, p, q, r, s, 2); if (e2.cls < 0) return SNAQ_B_BLOCKS; }
+    const int t4a = (c1 >= 0 && e1.cls == SNAQ_C_T4), t4b = (c2 >= 0 && e2.cls == SNAQ_C_T4);
+    /* chains: edges 0..ja belong to the type-4 term at J1, edges jb..ns-2 to the one at J2 */
+    int ja = -1, jb = ns - 1, nearA = 1;
+    int aArc = 0, bArc = 0;   /* the chain runs through the open end cycle at the other junction */
+    if (t4a || t4b) {
+        /* cleanUpNode! runs (and pre-merges the path below each hybrid node up to the next degree-3
+         * node) iff the pruned quartet network holds more than one hybrid: src/pseudolik.jl:826-830 */
+        int nhyb = 0;
+        for (int c = 0; c < T.n_cycles; c++) {
+            if (T.cyc_flags[c] & 1) continue;
+            int ps[4];
+            snaq_positions(T, c, tx, ps);
+            int hit = (ps[0] == 0) | (ps[1] == 0) | (ps[2] == 0) | (ps[3] == 0);
+            int same = (ps[0] == ps[1]) & (ps[1] == ps[2]) & (ps[2] == ps[3]);
+            nhyb += (hit && !same);
+        }
+        const int cleanup = nhyb > 1;
+        if (t4a) {
+            ja = 0;
+            if (cleanup) {
+                while (ja < ns - 2) {          /* extend through degree-2 nodes: anything but a type-3 loop */
+                    int c = T.tcycle[seq[ja + 1]];
+                    if (c >= 0) {
+                        snaq_positions(T, c, tx, pos);
+                        SnaqCyc m = snaq_classify_cycle(T, c, pos, p, q, r, s, 0);
+                        if (m.cls < 0) return SNAQ_B_BLOCKS;
+                        if (m.cls == SNAQ_C_T3) break;
+                    }
+                    ja++;
+                }
+                aArc = (ja == ns - 2);
+            }
+        }
+        if (t4b) {
+            jb = ns - 2;
+            if (cleanup) {
+                while (jb > 0) {
+                    int c = T.tcycle[seq[jb]];
+                    if (c >= 0) {
+                        snaq_positions(T, c, tx, pos);
+                        SnaqCyc m = snaq_classify_cycle(T, c, pos, p, q, r, s, 0);
+                        if (m.cls < 0) return SNAQ_B_BLOCKS;
+                        if (m.cls == SNAQ_C_T3) break;
+                    }
+                    jb--;
+                }
+                bArc = (jb == 0);
+            }
+        }
+        /* which end is internalLength!'s `node` (first degree-3 node in qnet.node): src/pseudolik.jl:1078 */
+        int o1 = c1 >= 0 ? T.cyc_order[T.cyc_off[c1] + e1.rep] : T.torder[J1];
+        int o2 = c2 >= 0 ? T.cyc_order[T.cyc_off[c2] + e2.rep] : T.torder[J2];
+        nearA = o1 < o2;
+        if (t4a && t4b && ja >= jb) {
+            /* both ends are type 4 and share one chain: the hybrid that comes first in net.hybrid is
+             * eliminated first and takes the whole pre-merged chain */
+            if (T.cyc_hyb[c1] < T.cyc_hyb[c2]) { ja = ns - 2; jb = ns - 1; nearA = 1; }
+            else { jb = 0; ja = -1; nearA = 0; }
+            aArc = bArc = 0;
+        }
+    }
+    /* owner of a path element: 0 main list, 1 chain of the term at J1, 2 chain of the term at J2.
+     * element kinds: edge i (between seq[i] and seq[i+1]); arc of interior node i; end arcs. */
+    int n0 = 0, nterms = 0;
+    for (int pass = 0; pass < 3; pass++) {
+        /* pass 0: main list; pass 1: the terms (with the chain of the J1-side type 4 inside);
+         * chains are emitted by the inner `want` loops */
+        if (pass == 2) break;
+        if (pass == 0) {
+            for (int want = 0; want < 1; want++) {
+                for (int i = 0; i < ns; i++) {
+                    if (i < ns - 1) {
+                        int owner = (t4a && i <= ja) ? 1 : ((t4b && i >= jb) ? 2 : 0);
+                        if (owner == 0) { snaq_put(w, i < iapex ? T.pslot[seq[i]] : T.pslot[seq[i + 1]]); n0++; }
+                    }
+                    int c = T.tcycle[seq[i]];
+                    if (c < 0) continue;
+                    if (i == 0) {
+                        if (e1.cls == SNAQ_C_OPEN && !(t4b && bArc)) n0 += snaq_put_arc(T, c, e1.lo, e1.hi, w);
+                    } else if (i == ns - 1) {
+                        if (e2.cls == SNAQ_C_OPEN && !(t4a && aArc)) n0 += snaq_put_arc(T, c, e2.lo, e2.hi, w);
+                    } else {
+                        snaq_positions(T, c, tx, pos);
+                        SnaqCyc m = snaq_classify_cycle(T, c, pos, p, q, r, s, 0);
+                        if (m.cls < 0) return SNAQ_B_BLOCKS;
+                        int owner = (t4a && i <= ja) ? 1 : ((t4b && i >= jb + 1) ? 2 : 0);
+                        if (m.cls == SNAQ_C_OPEN && owner == 0) n0 += snaq_put_arc(T, c, m.lo, m.hi, w);
+                    }
+                }
+            }
+            continue;
+        }
+        /* pass 1: terms, in path order */
+        for (int i = 0; i < ns; i++) {
+            int c = T.tcycle[seq[i]];
+            if (c < 0) continue;
+            SnaqCyc m;
+            if (i == 0) m = e1;
+            else if (i == ns - 1) m = e2;
+            else {
+                snaq_positions(T, c, tx, pos);
+                m = snaq_classify_cycle(T, c, pos, p, q, r, s, 0);
+            }
+            if (m.cls == SNAQ_C_OPEN) continue;
+            const int k = T.cyc_k[c];
+            const int g = T.cyc_gslot[c];
+            nterms++;
+            if (m.cls == SNAQ_C_T3) {
+                snaq_put(w, SNAQ_TERM(SNAQ_T3, 0, g));
+                snaq_put(w, (unsigned)m.lo | ((unsigned)(k - m.lo) << 8));
+                snaq_put_arc(T, c, 0, m.lo, w);        /* major hybrid edge + tree edges up to the hit node */
+                snaq_put_arc(T, c, m.lo, k, w);        /* tree edges from it + minor hybrid edge            */
+                if (info) info->type[T.cyc_hyb[c]] = 3;
+            } else if (m.cls == SNAQ_C_T2) {
+                /* gamma of the hybrid edge that lands on `other`: major iff `other` comes first */
+                snaq_put(w, SNAQ_TERM(SNAQ_T2, m.other == m.lo ? 1 : 0, g));
+                snaq_put(w, (unsigned)(m.hi - m.lo));
+                snaq_put_arc(T, c, m.lo, m.hi, w);
+                if (info) info->type[T.cyc_hyb[c]] = 2;
+            } else if (m.cls == SNAQ_C_TZ) {
+                snaq_put(w, SNAQ_TERM(SNAQ_TZ, 0, m.other == 1 ? g : g + 1));
+            } else {                                   /* type 4 */
+                const int isA = (i == 0);
+                const int far = isA ? !nearA : nearA;
+                snaq_put(w, SNAQ_TERM(SNAQ_T4, far, g));
+                snaq_put(w, (unsigned)m.lo | ((unsigned)(k - m.hi) << 8));
+                snaq_put(w, (unsigned)(m.hi - m.lo));
+                const int cnt_at = w.n;
+                snaq_put(w, 0);
+                snaq_put_arc(T, c, 0, m.lo, w);        /* major side: hybrid edge .. first hit node */
+                snaq_put_arc(T, c, m.hi, k, w);        /* minor side                                */
+                snaq_put_arc(T, c, m.lo, m.hi, w);     /* between the two hit nodes                 */
+                /* the chain below the hybrid node that the reference merges with this term first */
+                int nchain = 0;
+                const int me = isA ? 1 : 2;
+                for (int j = 0; j < ns; j++) {
+                    if (j < ns - 1) {
+                        int owner = (t4a && j <= ja) ? 1 : ((t4b && j >= jb) ? 2 : 0);
+                        if (owner == me) { snaq_put(w, j < iapex ? T.pslot[seq[j]] : T.pslot[seq[j + 1]]); nchain++; }
+                    }
+                    int cc = T.tcycle[seq[j]];
+                    if (cc < 0) continue;
+                    if (j == 0) {
+                        if (e1.cls == SNAQ_C_OPEN && me == 2 && bArc) nchain += snaq_put_arc(T, cc, e1.lo, e1.hi, w);
+                    } else if (j == ns - 1) {
+                        if (e2.cls == SNAQ_C_OPEN && me == 1 && aArc) nchain += snaq_put_arc(T, cc, e2.lo, e2.hi, w);
+                    } else {
+                        int owner = (t4a && j <= ja) ? 1 : ((t4b && j >= jb + 1) ? 2 : 0);
+                        if (owner != me) continue;
+                        snaq_positions(T, cc, tx, pos);
+                        SnaqCyc mm = snaq_classify_cycle(T, cc, pos, p, q, r, s, 0);
+                        if (mm.cls == SNAQ_C_OPEN) nchain += snaq_put_arc(T, cc, mm.lo, mm.hi, w);
+                    }
+                }
+                if (nchain > 65535) return SNAQ_B_OVERFLOW;
+                if (w.out && cnt_at < w.cap) w.out[cnt_at] = (uint16_t)nchain;
+                if (info) info->type[T.cyc_hyb[c]] = 4;
+            }
+        }
+    }
+    if (n0 > 127 || nterms > 15) return SNAQ_B_OVERFLOW;
+    if (info) info->formula[maj] = 1;
+    if (w.out && hdr_at < w.cap) w.out[hdr_at] = SNAQ_HDR(SNAQ_KIND_TREE, maj, nterms, n0);
+    return SNAQ_B_OK;
+}
+
+/* ------------------------------------------------------------------------------
+ * evaluation.  XF is a functor slot -> double (the candidate's xe).
+ * ------------------------------------------------------------------------------ */
+template <class XF>
+SNAQ_HD double snaq_sum(const uint16_t *&pc, int n, const XF &x) {
+    double a = 0.0;
+    for (int i = 0; i < n; i++) a += x(pc[i]);
+    pc += n;
+    return a;
+}
+SNAQ_HD double snaq_clamp10(double v) { return v > 10.0 ? 10.0 : v; }   /* setLength!: src/auxiliary.jl:122-124 */
+
+/*
+ * Expected CFs of one quartet in PROGRAM order:
+ *   tree-like: cf[0] = major (1-2/3 e^-t1), cf[1] = minor (1/3 e^-t1), t1 returned in *t1
+ *   type 5   : cf[0..2] = cf1, cf2, cf3 of quartetType5!
+ * Returns the program kind.  status gets SNAQ_S_* bits.
+ */
+template <class XF>
+SNAQ_HD unsigned snaq_eval_program(const uint16_t *pc, const XF &x, double cf[3], double *t1out, unsigned &status) {
+    const unsigned hdr = *pc++;
+    const unsigned kind = SNAQ_HDR_KIND(hdr);
+    if (kind == SNAQ_KIND_TREE) {
+        /* t1 = clamp( clamp(Bnear + R) + Bfar ): R = every non-negative piece (any merge order of
+         * those gives min(10, sum)); B = a type-4 term merged with its chain, which can be negative
+         * and is added first (near end) or last (far end) by internalLength! */
+        double R = snaq_sum(pc, (int)SNAQ_HDR_N0(hdr), x);
+        double Bn = 0.0, Bf = 0.0;
+        const int nterms = (int)SNAQ_HDR_NTERMS(hdr);
+        for (int it = 0; it < nterms; it++) {
+            const unsigned th = *pc++;
+            const unsigned ty = th & 3u;
+            const double gq = x(th >> 4);          /* minor gamma (or gammaz for TZ) */
+            if (ty == SNAQ_T2) {
+                int n = *pc++;
+                double e = snaq_clamp10(snaq_sum(pc, n, x));
+                double gh = (th & 4u) ? 1.0 - gq : gq;
+                R += snaq_clamp10(-log(1.0 - gh * (1.0 - exp(-e))));                 /* src/pseudolik.jl:938 */
+            } else if (ty == SNAQ_T3) {
+                unsigned nn = *pc++;
+                double l1 = snaq_clamp10(snaq_sum(pc, (int)(nn & 255u), x));
+                double l2 = snaq_clamp10(snaq_sum(pc, (int)(nn >> 8), x));
+                double g1 = 1.0 - gq, g2 = gq;
+                R += snaq_clamp10(-log(1.0 - g1 * g1 * (1.0 - exp(-l1)) - g2 * g2 * (1.0 - exp(-l2))));   /* :878 */
+            } else if (ty == SNAQ_T4) {
+                unsigned nn = *pc++;
+                int ne = *pc++;
+                int nchain = *pc++;
+                double la = snaq_clamp10(snaq_sum(pc, (int)(nn & 255u), x));
+                double lb = snaq_clamp10(snaq_sum(pc, (int)(nn >> 8), x));
+                double le = snaq_clamp10(snaq_sum(pc, ne, x));
+                double ch = snaq_clamp10(snaq_sum(pc, nchain, x));
+                double ga = 1.0 - gq, gb = gq;
+                double l4 = -log(gb * gb * exp(-lb) + ga * gb * (3.0 - exp(-le)) + ga * ga * exp(-la));   /* :951 */
+                if (l4 < SNAQ_MINLEN) status |= SNAQ_S_NEGLEN;
+                l4 = snaq_clamp10(l4);
+                double B = snaq_clamp10(ch + l4);                                     /* :956 */
+                if (B < SNAQ_MINLEN) status |= SNAQ_S_NEGLEN;
+                if (th & 4u) Bf = B; else Bn = B;
+            } else {
+                /* src/snaq_optimization.jl:230-234 and src/pseudolik.jl:221: -log(1-gammaz), capped at 10 */
+                R += snaq_clamp10(-log(1.0 - gq));
+            }
+        }
+        double t = snaq_clamp10(Bn + R);
+        if (t < SNAQ_MINLEN) status |= SNAQ_S_NEGLEN;
+        t = snaq_clamp10(t + Bf);
+        if (t < SNAQ_MINLEN) status |= SNAQ_S_NEGLEN;
+        const double y = exp(-t);
+        cf[0] = 1.0 - 2.0 / 3.0 * y;                                        /* src/pseudolik.jl:1259 */
+        cf[1] = 1.0 / 3.0 * y;
+        cf[2] = cf[1];
+        if (t1out) *t1out = t;
+    } else if (kind == SNAQ_KIND_T5) {
+        const double g2 = x(*pc++), g1 = 1.0 - g2;
+        unsigned nn = *pc++;
+        double y5 = exp(-snaq_clamp10(snaq_sum(pc, (int)(nn & 255u), x)));
+        double y6 = exp(-snaq_clamp10(snaq_sum(pc, (int)(nn >> 8), x)));
+        cf[0] = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;          /* src/pseudolik.jl:989-991 */
+        cf[1] = g1 * 1.0 / 3.0 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
+        cf[2] = g1 * 1.0 / 3.0 * y5 + g2 * 1.0 / 3.0 * y6;
+        if (t1out) *t1out = -1.0;
+    } else {
+        const double z1 = x(pc[0]), z2 = x(pc[1]);
+        cf[0] = (1.0 + 2.0 * z1 - z2) / 3.0;                                /* src/pseudolik.jl:985-987 */
+        cf[1] = (1.0 + 2.0 * z2 - z1) / 3.0;
+        cf[2] = (1.0 - z1 - z2) / 3.0;
+        if (t1out) *t1out = -1.0;
+    }
+    return kind;
+}
+
+/* program-order CFs -> data order (12|34, 13|24, 14|23) */
+SNAQ_HD void snaq_data_order(unsigned hdr, const double cf[3], double out[3]) {
+    const unsigned perm = SNAQ_HDR_PERM(hdr);
+    if (SNAQ_HDR_KIND(hdr) == SNAQ_KIND_TREE) {
+        out[0] = out[1] = out[2] = cf[1];
+        out[perm] = cf[0];
+    } else {
+        int pm[3];
+        snaq_perm_decode((int)perm, pm);
+        out[0] = cf[pm[0] - 1]; out[1] = cf[pm[1] - 1]; out[2] = cf[pm[2] - 1];
+    }
+}
+
+/*
+ * Per-quartet weights in program order, built once per (topology, obsCF):
+ *   W[0..2] = 100*obs of the CF that program slot j produces (tree-like: W[0] major,
+ *             W[1] = sum of the two minors, W[2] = 0), W[3] = sum_i 100*obs_i*log(obs_i).
+ * Unsampled quartets get all zeros (they contribute 0: src/pseudolik.jl:1390).
+ */
+SNAQ_HD void snaq_weights(unsigned hdr, const double obs[3], int sampled, double W[4]) {
+    W[0] = W[1] = W[2] = W[3] = 0.0;
+    if (!sampled) return;
+    const unsigned perm = SNAQ_HDR_PERM(hdr);
+    double c = 0.0;
+    for (int i = 0; i < 3; i++)
+        if (obs[i] != 0.0) c += 100.0 * obs[i] * log(obs[i]);
+    W[3] = c;
+    if (SNAQ_HDR_KIND(hdr) == SNAQ_KIND_TREE) {
+        for (int i = 0; i < 3; i++) {
+            if ((unsigned)i == perm) W[0] = 100.0 * obs[i];
+            else W[1] += 100.0 * obs[i];
+        }
+    } else {
+        int pm[3];
+        snaq_perm_decode((int)perm, pm);
+        for (int i = 0; i < 3; i++) W[pm[i] - 1] = 100.0 * obs[i];
+    }
+}
+
+/*
+ * logPseudoLik(quartet) (src/pseudolik.jl:1388-1410) from program-order CFs:
+ *   sum_i [ expCF_i<0 ? -1e15 : (obs_i==0 ? 0 : 100 obs_i log(expCF_i/obs_i)) ]
+ * written as sum_j W_j log(cf_j) - W[3]; for tree-like quartets log(minor) = -t1-log 3.
+ */
+SNAQ_HD double snaq_quartet_loglik(unsigned kind, const double cf[3], double t1, const double W[4], unsigned &status) {
+    double s;
+    if (kind == SNAQ_KIND_TREE) {
+        s = (W[0] != 0.0 ? W[0] * log(cf[0]) : 0.0) - W[1] * (t1 + SNAQ_LOG3) - W[3];
+        if (cf[0] < 0.0) status |= SNAQ_S_NEGLEN;
+    } else {
+        s = -W[3];
+        for (int j = 0; j < 3; j++) {
+            if (cf[j] < 0.0) {
+                /* -1e15 replaces this term, including its obs*log(obs) share of W[3] */
+                s += -1.e15 + (W[j] != 0.0 ? W[j] * log(W[j] / 100.0) : 0.0);
+            } else if (W[j] != 0.0) {
+                s += W[j] * log(cf[j]);
+            }
+        }
+        if (cf[0] + cf[1] + cf[2] == 0.0 && (W[0] != 0.0 || W[1] != 0.0 || W[2] != 0.0)) status |= SNAQ_S_ZEROSUM;
+    }
+    return s;
+}
+
+#endif /* SNAQ_CORE_H */

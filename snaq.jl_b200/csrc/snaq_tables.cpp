@@ -1,0 +1,312 @@
+#include "snaq_tables.h"
+
+#include <algorithm>
+#include <cstring>
+#include <queue>
+
+namespace {
+struct Fail { int code; std::string msg; };
+[[noreturn]] void fail(int code, const std::string &m) { throw Fail{code, m}; }
+
+template <class T> size_t put(std::vector<unsigned char> &blob, const std::vector<T> &v) {
+    size_t off = (blob.size() + 15) & ~size_t(15);
+    blob.resize(off + std::max<size_t>(v.size() * sizeof(T), 16), 0);
+    if (!v.empty()) std::memcpy(blob.data() + off, v.data(), v.size() * sizeof(T));
+    return off;
+}
+}  // namespace
+
+SnaqTables SnaqHostTables::view(const unsigned char *b) const {
+    SnaqTables T;
+    T.ntaxa = ntaxa; T.n_tnodes = n_tnodes; T.n_cycles = n_cycles; T.nparams = nparams; T.n_xe = n_xe; T.n_hybrids = n_hybrids;
+    T.leaf_tnode = (const uint16_t *)(b + off_leaf_tnode);
+    T.parent = (const uint16_t *)(b + off_parent);
+    T.depth = (const uint16_t *)(b + off_depth);
+    T.tcycle = (const int16_t *)(b + off_tcycle);
+    T.pslot = (const uint16_t *)(b + off_pslot);
+    T.blk = (const uint8_t *)(b + off_blk);
+    T.cyc_k = (const uint16_t *)(b + off_cyc_k);
+    T.cyc_off = (const uint16_t *)(b + off_cyc_off);
+    T.cyc_slot = (const uint16_t *)(b + off_cyc_slot);
+    T.cyc_gslot = (const uint16_t *)(b + off_cyc_gslot);
+    T.cyc_flags = (const uint8_t *)(b + off_cyc_flags);
+    T.cyc_hyb = (const uint8_t *)(b + off_cyc_hyb);
+    T.torder = (const uint16_t *)(b + off_torder);
+    T.cyc_order = (const uint16_t *)(b + off_cyc_order);
+    return T;
+}
+
+int snaq_build_tables(const snaq_flatnet *f, int ntaxa, SnaqHostTables &o, std::string &err) {
+    try {
+        if (!f) fail(SNAQ_EINVAL, "null network");
+        const int N = f->n_nodes, E = f->n_edges, H = f->n_hybrids;
+        if (N <= 0 || E <= 0 || H < 0) fail(SNAQ_EINVAL, "empty network");
+        if (H > SNAQ_MAX_HYB) fail(SNAQ_EINVAL, "more than " + std::to_string(SNAQ_MAX_HYB) + " hybrid nodes");
+        if (N > 60000) fail(SNAQ_EINVAL, "network too large for 16-bit node ids");
+        auto isLeaf = [&](int n) { return (f->node_flags[n] & SNAQ_NODE_LEAF) != 0; };
+        auto isHyb = [&](int n) { return (f->node_flags[n] & SNAQ_NODE_HYBRID) != 0; };
+        auto eHyb = [&](int e) { return (f->edge_flags[e] & SNAQ_EDGE_HYBRID) != 0; };
+        auto eMaj = [&](int e) { return (f->edge_flags[e] & SNAQ_EDGE_MAJOR) != 0; };
+        auto eIdent = [&](int e) { return (f->edge_flags[e] & SNAQ_EDGE_IDENTIFIABLE) != 0; };
+        auto other = [&](int e, int n) { return f->edge_node[2 * e] == n ? f->edge_node[2 * e + 1] : f->edge_node[2 * e]; };
+        std::vector<int> deg(N, 0);
+        for (int n = 0; n < N; n++) {
+            for (int j = 0; j < 3; j++) {
+                int e = f->node_edge[3 * n + j];
+                if (e >= E) fail(SNAQ_EINVAL, "node_edge out of range");
+                if (e >= 0) {
+                    if (f->edge_node[2 * e] != n && f->edge_node[2 * e + 1] != n) fail(SNAQ_EINVAL, "node_edge / edge_node disagree");
+                    deg[n]++;
+                }
+            }
+            if (isLeaf(n) ? deg[n] != 1 : deg[n] != 3)
+                fail(SNAQ_ETOPOLOGY, "node " + std::to_string(f->node_number[n]) + " has " + std::to_string(deg[n]) + " edges");
+        }
+        // child (hybrid) end of a hybrid edge
+        auto hybChild = [&](int e) {
+            int a = f->edge_node[2 * e], b = f->edge_node[2 * e + 1];
+            if (isHyb(a) && !isHyb(b)) return a;
+            if (isHyb(b) && !isHyb(a)) return b;
+            if (isHyb(a) && isHyb(b)) return (f->edge_flags[e] & SNAQ_EDGE_ISCHILD1) ? a : b;
+            fail(SNAQ_ETOPOLOGY, "hybrid edge " + std::to_string(f->edge_number[e]) + " does not touch a hybrid node");
+        };
+        std::vector<int> hybIndex(N, -1);
+        for (int h = 0; h < H; h++) {
+            int n = f->hybrid[h];
+            if (n < 0 || n >= N || !isHyb(n)) fail(SNAQ_EINVAL, "hybrid list entry is not a hybrid node");
+            hybIndex[n] = h;
+        }
+        for (int n = 0; n < N; n++) if (isHyb(n) && hybIndex[n] < 0) fail(SNAQ_EINVAL, "hybrid node missing from the hybrid list");
+
+        // ---- parameters(net): src/snaq_optimization.jl:54-92 --------------------------
+        std::vector<int> majE(H, -1), minE(H, -1), childE(H, -1);
+        for (int h = 0; h < H; h++) {
+            int n = f->hybrid[h];
+            for (int j = 0; j < 3; j++) {
+                int e = f->node_edge[3 * n + j];
+                if (eHyb(e) && hybChild(e) == n) { if (eMaj(e)) majE[h] = e; else minE[h] = e; }
+                else if (!eHyb(e)) childE[h] = e;
+            }
+            if (majE[h] < 0 || minE[h] < 0 || childE[h] < 0)
+                fail(SNAQ_ETOPOLOGY, "hybrid node " + std::to_string(f->node_number[n]) + " does not have one major, one minor and one tree edge");
+        }
+        std::vector<double> hv, tv, zv;
+        std::vector<int32_t> hn, tn, zn;
+        std::vector<int> gammaSlotOfHyb(H, -1), zSlotOfHyb(H, -1), tIndexOfEdge(E, -1);
+        for (int e = 0; e < E; e++) {
+            if (eIdent(e)) { tIndexOfEdge[e] = (int)tv.size(); tv.push_back(f->edge_length[e]); tn.push_back(f->edge_number[e]); }
+            if (eHyb(e) && !eMaj(e)) {
+                int node = hybChild(e);
+                int h = hybIndex[node];
+                if (!(f->node_flags[node] & SNAQ_NODE_BADDIAMOND1)) {
+                    gammaSlotOfHyb[h] = (int)hv.size();
+                    hv.push_back(f->edge_gamma[e]); hn.push_back(f->edge_number[e]);
+                } else {
+                    zSlotOfHyb[h] = (int)zv.size();
+                    int oa = other(majE[h], node), ob = other(minE[h], node);
+                    zv.push_back(f->node_gammaz[oa]); zv.push_back(f->node_gammaz[ob]);
+                    zn.push_back(std::stoi(std::to_string(f->node_number[node]) + "1"));
+                    zn.push_back(std::stoi(std::to_string(f->node_number[node]) + "2"));
+                }
+            }
+        }
+        o.nh = (int)hv.size(); o.nt = (int)tv.size(); o.nhz = (int)zv.size();
+        o.nparams = o.nh + o.nt + o.nhz;
+        o.x0 = hv; o.x0.insert(o.x0.end(), tv.begin(), tv.end()); o.x0.insert(o.x0.end(), zv.begin(), zv.end());
+        o.numht = hn; o.numht.insert(o.numht.end(), tn.begin(), tn.end()); o.numht.insert(o.numht.end(), zn.begin(), zn.end());
+        o.upper.assign(o.nparams, 1.0);
+        for (int i = o.nh; i < o.nh + o.nt; i++) o.upper[i] = 10.0;
+
+        // ---- slots of the extended parameter vector ---------------------------------------
+        o.xconst.clear();
+        o.edge_slot.assign(E, -1);
+        for (int e = 0; e < E; e++) {
+            if (eIdent(e)) o.edge_slot[e] = o.nh + tIndexOfEdge[e];
+            else if (!isLeaf(f->edge_node[2 * e]) && !isLeaf(f->edge_node[2 * e + 1])) {
+                o.edge_slot[e] = o.nparams + (int)o.xconst.size();
+                double len = f->edge_length[e];
+                o.xconst.push_back(len > 10.0 ? 10.0 : len);
+            }
+        }
+        o.n_xe = o.nparams + (int)o.xconst.size();
+        if (o.n_xe > SNAQ_MAX_SLOT) fail(SNAQ_EINVAL, "too many parameters for 12-bit slots");
+        auto slotOf = [&](int e) { return (uint16_t)(o.edge_slot[e] >= 0 ? o.edge_slot[e] : 0); };
+
+        // ---- cycles: unique path between the two parents in the tree of major edges ---------
+        std::vector<int> cycOfNode(N, -1), posOfNode(N, -1);
+        std::vector<char> inCycleEdge(E, 0);
+        std::vector<std::vector<int>> cycNodes(H), cycEdges(H);
+        for (int h = 0; h < H; h++) {
+            int Hn = f->hybrid[h];
+            int target = other(minE[h], Hn);
+            int start = other(majE[h], Hn);
+            // BFS from `start` over non-minor edges, not through Hn, not through leaves
+            std::vector<int> prevN(N, -2), prevE(N, -1);
+            std::queue<int> qu;
+            prevN[start] = -1;
+            qu.push(start);
+            bool found = (start == target);
+            while (!qu.empty() && !found) {
+                int u = qu.front(); qu.pop();
+                for (int j = 0; j < 3 && !found; j++) {
+                    int e = f->node_edge[3 * u + j];
+                    if (e < 0 || (eHyb(e) && !eMaj(e))) continue;
+                    int v = other(e, u);
+                    if (v == Hn || isLeaf(v) || prevN[v] != -2) continue;
+                    prevN[v] = u; prevE[v] = e;
+                    if (v == target) found = true; else qu.push(v);
+                }
+            }
+            if (!found) fail(SNAQ_ETOPOLOGY, "hybrid node " + std::to_string(f->node_number[Hn]) + " does not close a cycle");
+            std::vector<int> pn, pe;     // from target back to start
+            for (int v = target; v != -1; v = prevN[v]) { pn.push_back(v); if (prevE[v] >= 0) pe.push_back(prevE[v]); }
+            std::reverse(pn.begin(), pn.end());
+            std::reverse(pe.begin(), pe.end());
+            cycNodes[h].push_back(Hn);
+            for (int v : pn) cycNodes[h].push_back(v);
+            cycEdges[h].push_back(majE[h]);
+            for (int e : pe) cycEdges[h].push_back(e);
+            cycEdges[h].push_back(minE[h]);
+            int k = (int)cycNodes[h].size();
+            if (k < 3) fail(SNAQ_ETOPOLOGY, "cycle with only " + std::to_string(k) + " nodes: parallel edges");
+            if (k > 255) fail(SNAQ_EINVAL, "cycle with more than 255 nodes");
+            for (int j = 0; j < k; j++) {
+                int v = cycNodes[h][j];
+                if (cycOfNode[v] >= 0) fail(SNAQ_ETOPOLOGY, "cycles of hybrids intersect: not a level-1 network");
+                cycOfNode[v] = h; posOfNode[v] = j;
+            }
+            for (int e : cycEdges[h]) inCycleEdge[e] = 1;
+            if ((f->node_flags[Hn] & SNAQ_NODE_BADDIAMOND1) && k != 4) fail(SNAQ_ETOPOLOGY, "bad diamond I flag on a cycle that is not a 4-cycle");
+        }
+
+        // ---- blob tree T' -------------------------------------------------------------------
+        std::vector<int> tOfNode(N, -1);
+        int nt = 0;
+        std::vector<int> superOfCycle(H, -1);
+        for (int n = 0; n < N; n++) {
+            if (cycOfNode[n] < 0) tOfNode[n] = nt++;
+        }
+        for (int h = 0; h < H; h++) superOfCycle[h] = nt++;
+        for (int n = 0; n < N; n++) if (cycOfNode[n] >= 0) tOfNode[n] = superOfCycle[cycOfNode[n]];
+        o.n_tnodes = nt;
+        std::vector<std::vector<std::pair<int, int>>> adj(nt);   // (neighbour tnode, net edge)
+        int ntedges = 0;
+        for (int e = 0; e < E; e++) {
+            if (inCycleEdge[e]) continue;
+            int a = tOfNode[f->edge_node[2 * e]], b = tOfNode[f->edge_node[2 * e + 1]];
+            if (a == b) fail(SNAQ_ETOPOLOGY, "edge " + std::to_string(f->edge_number[e]) + " is a chord of a cycle: not level-1");
+            if (eHyb(e)) fail(SNAQ_ETOPOLOGY, "hybrid edge outside of its cycle");
+            adj[a].push_back({b, e}); adj[b].push_back({a, e});
+            ntedges++;
+        }
+        if (ntedges != nt - 1) fail(SNAQ_ETOPOLOGY, "network is not connected or not level-1 (blob graph is not a tree)");
+        auto bfs = [&](int src, std::vector<int> &par, std::vector<int> &pe, std::vector<int> &dep) {
+            par.assign(nt, -1); pe.assign(nt, -1); dep.assign(nt, -1);
+            std::queue<int> qu; qu.push(src); dep[src] = 0; par[src] = src;
+            int last = src;
+            while (!qu.empty()) {
+                int u = qu.front(); qu.pop(); last = u;
+                for (auto &pr : adj[u]) if (dep[pr.first] < 0) { dep[pr.first] = dep[u] + 1; par[pr.first] = u; pe[pr.first] = pr.second; qu.push(pr.first); }
+            }
+            return last;
+        };
+        std::vector<int> par, pe, dep;
+        int far1 = bfs(0, par, pe, dep);
+        for (int v = 0; v < nt; v++) if (dep[v] < 0) fail(SNAQ_ETOPOLOGY, "network is not connected");
+        int far2 = bfs(far1, par, pe, dep);
+        int root = far2;
+        for (int i = 0; i < dep[far2] / 2; i++) root = par[root];     // middle of a diameter: small depths
+        bfs(root, par, pe, dep);
+        std::vector<uint16_t> t_parent(nt), t_depth(nt), t_pslot(nt);
+        std::vector<int16_t> t_cycle(nt, -1);
+        for (int v = 0; v < nt; v++) {
+            t_parent[v] = (uint16_t)par[v]; t_depth[v] = (uint16_t)dep[v];
+            t_pslot[v] = pe[v] >= 0 ? slotOf(pe[v]) : 0;
+        }
+        for (int h = 0; h < H; h++) t_cycle[superOfCycle[h]] = (int16_t)h;
+        std::vector<uint16_t> t_order(nt, 0);
+        for (int n = 0; n < N; n++) if (cycOfNode[n] < 0) t_order[tOfNode[n]] = (uint16_t)n;   // flat nodes are in net.node order
+
+        // ---- taxa ---------------------------------------------------------------------------
+        o.ntaxa = ntaxa;
+        std::vector<uint16_t> leaf_tnode(std::max(ntaxa, 1), 0xFFFF);
+        std::vector<int> nodeOfTaxon(std::max(ntaxa, 1), -1);
+        int nleaves = 0;
+        for (int n = 0; n < N; n++) {
+            if (!isLeaf(n)) continue;
+            nleaves++;
+            int t = f->node_taxon[n];
+            if (t < 0 || t >= ntaxa) fail(SNAQ_EINVAL, "leaf " + std::to_string(f->node_number[n]) + " has taxon id " + std::to_string(t) + " outside the data's taxon list");
+            if (nodeOfTaxon[t] >= 0) fail(SNAQ_EINVAL, "two leaves carry the same taxon id");
+            nodeOfTaxon[t] = n;
+            leaf_tnode[t] = (uint16_t)tOfNode[n];
+        }
+        if (f->n_leaves != nleaves) fail(SNAQ_EINVAL, "n_leaves does not match the number of leaf nodes");
+
+        // ---- blocks: position of every taxon in every cycle -----------------------------------
+        std::vector<uint8_t> blk((size_t)std::max(H, 1) * std::max(ntaxa, 1), 0);
+        for (int h = 0; h < H; h++) {
+            int k = (int)cycNodes[h].size();
+            for (int j = 0; j < k; j++) {
+                int cn = cycNodes[h][j];
+                int e0 = -1;
+                for (int jj = 0; jj < 3; jj++) { int e = f->node_edge[3 * cn + jj]; if (!inCycleEdge[e] || cycOfNode[other(e, cn)] != h) e0 = e; }
+                if (e0 < 0) fail(SNAQ_ETOPOLOGY, "cycle node without an edge leaving the cycle");
+                // DFS away from the cycle
+                std::vector<int> st{other(e0, cn)};
+                std::vector<char> seen(N, 0);
+                seen[cn] = 1; seen[st[0]] = 1;
+                while (!st.empty()) {
+                    int u = st.back(); st.pop_back();
+                    if (cycOfNode[u] == h) fail(SNAQ_ETOPOLOGY, "block of a cycle node re-enters the cycle: not level-1");
+                    if (isLeaf(u)) blk[(size_t)h * ntaxa + f->node_taxon[u]] = (uint8_t)j;
+                    for (int jj = 0; jj < 3; jj++) {
+                        int e = f->node_edge[3 * u + jj];
+                        if (e < 0) continue;
+                        int v = other(e, u);
+                        if (!seen[v]) { seen[v] = 1; st.push_back(v); }
+                    }
+                }
+            }
+        }
+
+        // ---- cycle tables -------------------------------------------------------------------------
+        o.n_cycles = H; o.n_hybrids = H;
+        std::vector<uint16_t> cyc_k(std::max(H, 1), 0), cyc_off(std::max(H, 1), 0), cyc_slot, cyc_order, cyc_gslot(std::max(H, 1), 0);
+        std::vector<uint8_t> cyc_flags(std::max(H, 1), 0), cyc_hyb(std::max(H, 1), 0);
+        for (int h = 0; h < H; h++) {
+            cyc_k[h] = (uint16_t)cycNodes[h].size();
+            cyc_off[h] = (uint16_t)cyc_slot.size();
+            for (int e : cycEdges[h]) cyc_slot.push_back(slotOf(e));
+            for (int v : cycNodes[h]) cyc_order.push_back((uint16_t)v);
+            bool bd1 = (f->node_flags[f->hybrid[h]] & SNAQ_NODE_BADDIAMOND1) != 0;
+            cyc_flags[h] = bd1 ? 1 : 0;
+            cyc_gslot[h] = (uint16_t)(bd1 ? o.nh + o.nt + zSlotOfHyb[h] : gammaSlotOfHyb[h]);
+            cyc_hyb[h] = (uint8_t)h;
+        }
+        if (cyc_slot.empty()) { cyc_slot.push_back(0); cyc_order.push_back(0); }
+
+        o.blob.clear();
+        o.off_leaf_tnode = put(o.blob, leaf_tnode);
+        o.off_parent = put(o.blob, t_parent);
+        o.off_depth = put(o.blob, t_depth);
+        o.off_tcycle = put(o.blob, t_cycle);
+        o.off_pslot = put(o.blob, t_pslot);
+        o.off_blk = put(o.blob, blk);
+        o.off_cyc_k = put(o.blob, cyc_k);
+        o.off_cyc_off = put(o.blob, cyc_off);
+        o.off_cyc_slot = put(o.blob, cyc_slot);
+        o.off_cyc_gslot = put(o.blob, cyc_gslot);
+        o.off_cyc_flags = put(o.blob, cyc_flags);
+        o.off_cyc_hyb = put(o.blob, cyc_hyb);
+        o.off_torder = put(o.blob, t_order);
+        o.off_cyc_order = put(o.blob, cyc_order);
+        return SNAQ_OK;
+    } catch (const Fail &e) {
+        err = e.msg;
+        return e.code;
+    } catch (const std::exception &e) {
+        err = e.what();
+        return SNAQ_EINVAL;
+    }
+}
