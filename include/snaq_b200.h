@@ -150,6 +150,10 @@ int snaq_eval(snaq_ctx *ctx, int32_t P, int32_t nparams,
 int snaq_eval_device(snaq_ctx *ctx, int32_t P, int32_t nparams,
                      const double *dX, double *dout, void *stream);
 
+/* snaq_eval_device does not synchronise; this reads (and clears) the status word its kernels
+ * OR error bits into, and maps it to SNAQ_ERANGE / SNAQ_ENUMERIC like snaq_eval does.          */
+int snaq_check_status(snaq_ctx *ctx);
+
 /* Per-quartet results for one parameter vector x (host buffers):
  * expcf[nq*3] (q.qnet.expCF), logpl[nq] (q.logPseudoLik, src/pseudolik.jl:1407),
  * deltacf[nq] (calculateDeltaCF, src/pseudolik.jl:491-498).  Any may be NULL.  */
@@ -173,6 +177,10 @@ int snaq_get_descriptors(snaq_ctx *ctx, int8_t *which, int8_t *ntype,
  * [2] H2D bytes, [3] D2H bytes, [4] descriptor words in HBM, [5] launches of
  * the descriptor-build kernels                                                 */
 int snaq_get_counters(snaq_ctx *ctx, int64_t out[8]);
+
+/* measurement aid for the FP64 roofline: best-of-5 rate of a DFMA microbenchmark kernel
+ * (8 independent chains per thread, 8 blocks of 256 threads per SM), in TFLOP/s           */
+int snaq_measure_fp64_peak(snaq_ctx *ctx, double *tflops);
 
 #ifdef __cplusplus
 }

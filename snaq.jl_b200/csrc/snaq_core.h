@@ -205,8 +205,11 @@ SNAQ_HD int snaq_perm_index(int p0, int p1) {
     return (p0 - 1) * 2 + ((p1 < ((p0 == 1) ? 3 : (p0 == 2 ? 3 : 2))) ? 0 : 1);
 }
 SNAQ_HD void snaq_perm_decode(int idx, int perm[3]) {
-    const int tab[6][3] = {{1, 2, 3}, {1, 3, 2}, {2, 1, 3}, {2, 3, 1}, {3, 1, 2}, {3, 2, 1}};
-    perm[0] = tab[idx][0]; perm[1] = tab[idx][1]; perm[2] = tab[idx][2];
+    /* {1,2,3},{1,3,2},{2,1,3},{2,3,1},{3,1,2},{3,2,1} packed 2 bits per entry (no local array) */
+    const unsigned packed[3] = {0xFA5u /*p0: 1,1,2,2,3,3*/, 0x9DEu /*p1: 2,3,1,3,1,2*/, 0x67Bu /*p2: 3,2,3,1,2,1*/};
+    perm[0] = (int)((packed[0] >> (2 * idx)) & 3u);
+    perm[1] = (int)((packed[1] >> (2 * idx)) & 3u);
+    perm[2] = (int)((packed[2] >> (2 * idx)) & 3u);
 }
 
 /*

@@ -1,0 +1,883 @@
+/*
+ * snaq_engine.cu — CUDA kernels (sm_100a) and the C ABI of include/snaq_b200.h.
+ *
+ * Device-resident state per context (one context <=> one GPU + one stream):
+ *   taxa   [nq][4] u16      quartet taxon ids                      (set_data)
+ *   obs    [nq][3] f64      observed CFs                           (set_data / set_obscf)
+ *   sampled[nq]    u8       q.sampled                              (set_sampled)
+ *   off    [nq+1]  u32  \   CSR table of quartet programs: the flattened replacement of
+ *   prog   [words] u16  /   the reference's per-quartet QuartetNetwork objects (set_network)
+ *   W      [nq][4] f64      100*obs in program order + sum 100*obs*log(obs)
+ *
+ * Kernels:
+ *   k_build_count / k_build_emit : extractQuartet! for every quartet (thread per quartet)
+ *   k_weights                    : obs -> W
+ *   k_eval_lanes                 : the hot kernel.  lane = candidate parameter vector, a warp walks
+ *                                  quartets; the quartet program is warp-uniform so there is no
+ *                                  divergence, x is staged transposed in shared memory so the
+ *                                  per-slot gathers are conflict-free, sums stay thread-private
+ *                                  until one fixed-order block reduction (deterministic).
+ *   k_eval_quartets              : thread per quartet for small batches (P < 16; HBM-bound at P=1)
+ *                                  and for the per-quartet read-back (expCF, logPseudoLik, deltaCF)
+ *   k_reduce_partials            : second, fixed-order pass over the per-block partial sums
+ *
+ * Tensor cores are not used: the path is a few exp/log per (quartet, candidate), not a contraction.
+ */
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/snaq_b200.h"
+#include "snaq_core.h"
+#include "snaq_tables.h"
+
+#define SNAQ_S_RANGE 8u   /* a parameter outside its bounds reached the device */
+#define LANES_MIN_P 16    /* batches of at least this many candidates use k_eval_lanes */
+#define QK_MAXP 16        /* k_eval_quartets handles at most this many candidates per launch */
+
+// --------------------------------------------------------------------------------------------
+// descriptor build
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_t *__restrict__ taxa, int64_t nq,
+                                                     uint32_t *__restrict__ len, unsigned long long *__restrict__ total,
+                                                     uint32_t *__restrict__ maxlen, uint32_t *__restrict__ status) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned n = 0;
+    if (q < nq) {
+        uint16_t tx[4];
+        const ushort4 t4 = reinterpret_cast<const ushort4 *>(taxa)[q];
+        tx[0] = t4.x; tx[1] = t4.y; tx[2] = t4.z; tx[3] = t4.w;
+        SnaqWriter w{nullptr, 0, 0};
+        int e = snaq_build_quartet(T, tx, w, nullptr);
+        if (e) atomicMax(status, (uint32_t)e);
+        n = e ? 1u : (unsigned)w.n;
+        len[q] = n;
+    }
+    // block totals (64-bit) and the longest program
+    __shared__ unsigned long long ssum[4];
+    __shared__ unsigned smax[4];
+    unsigned long long s = n;
+    unsigned m = n;
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, o);
+        m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+    }
+    if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = s; smax[threadIdx.x >> 5] = m; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(total, ssum[0] + ssum[1] + ssum[2] + ssum[3]);
+        atomicMax(maxlen, max(max(smax[0], smax[1]), max(smax[2], smax[3])));
+    }
+}
+
+__global__ void __launch_bounds__(128) k_build_emit(SnaqTables T, const uint16_t *__restrict__ taxa, int64_t nq,
+                                                    const uint32_t *__restrict__ off, uint16_t *__restrict__ prog,
+                                                    uint32_t *__restrict__ status) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint16_t tx[4];
+    const ushort4 t4 = reinterpret_cast<const ushort4 *>(taxa)[q];
+    tx[0] = t4.x; tx[1] = t4.y; tx[2] = t4.z; tx[3] = t4.w;
+    const uint32_t o0 = off[q], o1 = off[q + 1];
+    SnaqWriter w{prog + o0, 0, (int)(o1 - o0)};
+    int e = snaq_build_quartet(T, tx, w, nullptr);
+    if (e) { atomicMax(status, (uint32_t)e); prog[o0] = SNAQ_HDR(SNAQ_KIND_TREE, 0, 0, 0); }
+    else if ((uint32_t)w.n != o1 - o0) atomicMax(status, (uint32_t)SNAQ_B_OVERFLOW);
+}
+
+__global__ void __launch_bounds__(256) k_weights(const uint32_t *__restrict__ off, const uint16_t *__restrict__ prog,
+                                                 const double *__restrict__ obs, const uint8_t *__restrict__ sampled,
+                                                 int64_t nq, double *__restrict__ W) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    double o[3] = {obs[3 * q], obs[3 * q + 1], obs[3 * q + 2]};
+    double w[4];
+    snaq_weights(prog[off[q]], o, sampled ? sampled[q] : 1, w);
+    reinterpret_cast<double4 *>(W)[q] = make_double4(w[0], w[1], w[2], w[3]);
+}
+
+// parity descriptors: which / typeHyb per hybrid / formula
+__global__ void __launch_bounds__(128) k_describe(SnaqTables T, const uint16_t *__restrict__ taxa, int64_t nq,
+                                                  int8_t *__restrict__ which, int8_t *__restrict__ types,
+                                                  int nhyb, int8_t *__restrict__ formula) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint16_t tx[4];
+    const ushort4 t4 = reinterpret_cast<const ushort4 *>(taxa)[q];
+    tx[0] = t4.x; tx[1] = t4.y; tx[2] = t4.z; tx[3] = t4.w;
+    SnaqWriter w{nullptr, 0, 0};
+    SnaqQuartetInfo info;
+    snaq_build_quartet(T, tx, w, &info);
+    which[q] = info.which;
+    for (int i = 0; i < 3; i++) formula[3 * q + i] = info.formula[i];
+    for (int i = 0; i < nhyb; i++) types[q * nhyb + i] = info.type[i];
+}
+
+// --------------------------------------------------------------------------------------------
+// evaluation
+// --------------------------------------------------------------------------------------------
+struct XLane {   // candidate = lane; xs is [slot][32]
+    const double *xs;
+    __device__ __forceinline__ double operator()(unsigned s) const { return xs[s * 32u]; }
+};
+struct XRow {    // one candidate's xe, contiguous
+    const double *x;
+    __device__ __forceinline__ double operator()(unsigned s) const { return x[s]; }
+};
+
+__device__ __forceinline__ unsigned range_check(double v, double hi) { return (v >= 0.0 && v <= hi) ? 0u : SNAQ_S_RANGE; }
+
+/*
+ * grid (nchunks, ngroups); block = WARPS*32 threads.  Block (cb, g) evaluates quartets
+ * [cb*chunk, (cb+1)*chunk) for candidates [32g, 32g+32).  Dynamic shared memory:
+ *   xs   [n_xe][32] f64   candidates' extended parameter vectors, transposed
+ *   red  [WARPS][32] f64
+ *   sW   [chunk][4] f64
+ *   soff [chunk+1]  u32
+ *   sprog[maxwords] u16
+ */
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__restrict__ off, const uint16_t *__restrict__ prog,
+                                                         const double *__restrict__ W, int64_t nq, int chunk,
+                                                         const double *__restrict__ X, const double *__restrict__ xconst,
+                                                         int nparams, int nh, int nt, int n_xe, int P,
+                                                         double *__restrict__ partial, int Ppad, uint32_t *__restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double *xs = reinterpret_cast<double *>(smem);
+    double *red = xs + (size_t)n_xe * 32;
+    double *sW = red + WARPS * 32;
+    uint32_t *soff = reinterpret_cast<uint32_t *>(sW + (size_t)chunk * 4);
+    uint16_t *sprog = reinterpret_cast<uint16_t *>(soff + chunk + 1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = blockIdx.y;
+    const int64_t q0 = (int64_t)blockIdx.x * chunk;
+    const int nqc = (int)min((int64_t)chunk, nq - q0);
+    unsigned st = 0;
+    // x tile: coalesced global reads (row-major X), transposed into xs[slot][lane]
+    for (int idx = tid; idx < 32 * nparams; idx += WARPS * 32) {
+        int r = idx / nparams, s = idx - r * nparams;
+        int p = min(32 * g + r, P - 1);
+        double v = X[(size_t)p * nparams + s];
+        st |= range_check(v, (s >= nh && s < nh + nt) ? 1.0e300 : 1.0);
+        xs[s * 32 + r] = v;
+    }
+    for (int idx = tid; idx < 32 * (n_xe - nparams); idx += WARPS * 32)
+        xs[(size_t)nparams * 32 + idx] = xconst[idx >> 5];
+    // quartet programs, offsets and weights of this chunk
+    const uint32_t base = off[q0];
+    const uint32_t nwords = off[q0 + nqc] - base;
+    for (int i = tid; i <= nqc; i += WARPS * 32) soff[i] = off[q0 + i] - base;
+    for (uint32_t i = tid; i < nwords; i += WARPS * 32) sprog[i] = prog[base + i];
+    {
+        const double2 *src = reinterpret_cast<const double2 *>(W + (size_t)q0 * 4);
+        double2 *dst = reinterpret_cast<double2 *>(sW);
+        for (int i = tid; i < nqc * 2; i += WARPS * 32) dst[i] = src[i];
+    }
+    __syncthreads();
+    double acc = 0.0;
+    const XLane xf{xs + lane};
+    for (int i = warp; i < nqc; i += WARPS) {
+        double cf[3], t1;
+        const unsigned kind = snaq_eval_program(sprog + soff[i], xf, cf, &t1, st);
+        acc += snaq_quartet_loglik(kind, cf, t1, sW + 4 * i, st);
+    }
+    red[warp * 32 + lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) s += red[w * 32 + lane];
+        partial[(size_t)blockIdx.x * Ppad + 32 * g + lane] = s;
+    }
+    if (st) atomicOr(status, st);
+}
+
+/*
+ * Thread per quartet, P <= QK_MAXP candidates.  Block of BLOCK threads stages its quartets'
+ * programs in shared memory with coalesced loads; x vectors (P x n_xe) sit in shared memory.
+ * partial[block][p] gets the block's sum.  Optional per-quartet outputs (P==1 semantics: they are
+ * written for the LAST candidate): expcf [nq][3] in data order, logpl [nq], deltacf [nq].
+ */
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_eval_quartets(const uint32_t *__restrict__ off, const uint16_t *__restrict__ prog,
+                                                        const double *__restrict__ W, const double *__restrict__ obs,
+                                                        int64_t nq, const double *__restrict__ X,
+                                                        const double *__restrict__ xconst, int nparams, int nh, int nt,
+                                                        int n_xe, int P, int maxwords, double *__restrict__ partial,
+                                                        double *__restrict__ expcf, double *__restrict__ logpl,
+                                                        double *__restrict__ deltacf, uint32_t *__restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double *xs = reinterpret_cast<double *>(smem);                 // [P][n_xe]
+    double *red = xs + (size_t)P * n_xe;                           // [BLOCK/32]
+    uint16_t *sprog = reinterpret_cast<uint16_t *>(red + BLOCK / 32);
+    const int tid = threadIdx.x;
+    const int64_t q0 = (int64_t)blockIdx.x * BLOCK;
+    const int nqc = (int)min((int64_t)BLOCK, nq - q0);
+    unsigned st = 0;
+    for (int idx = tid; idx < P * n_xe; idx += BLOCK) {
+        int p = idx / n_xe, s = idx - p * n_xe;
+        double v;
+        if (s < nparams) {
+            v = X[(size_t)p * nparams + s];
+            st |= range_check(v, (s >= nh && s < nh + nt) ? 1.0e300 : 1.0);
+        } else v = xconst[s - nparams];
+        xs[idx] = v;
+    }
+    const uint32_t base = off[q0];
+    const uint32_t nwords = off[q0 + nqc] - base;
+    const bool staged = nwords <= (uint32_t)maxwords;
+    if (staged)
+        for (uint32_t i = tid; i < nwords; i += BLOCK) sprog[i] = prog[base + i];
+    __syncthreads();
+    const int64_t q = q0 + tid;
+    const bool active = tid < nqc;
+    const uint16_t *pc = nullptr;
+    double w[4] = {0, 0, 0, 0};
+    if (active) {
+        const uint32_t o = off[q];
+        pc = staged ? sprog + (o - base) : prog + o;
+        const double4 w4 = reinterpret_cast<const double4 *>(W)[q];
+        w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+    }
+    for (int p = 0; p < P; p++) {
+        double v = 0.0;
+        if (active) {
+            double cf[3], t1;
+            const XRow xf{xs + (size_t)p * n_xe};
+            const unsigned kind = snaq_eval_program(pc, xf, cf, &t1, st);
+            v = snaq_quartet_loglik(kind, cf, t1, w, st);
+            if (p == P - 1 && (expcf || logpl || deltacf)) {
+                double e[3];
+                snaq_data_order(pc[0], cf, e);
+                if (expcf) { expcf[3 * q] = e[0]; expcf[3 * q + 1] = e[1]; expcf[3 * q + 2] = e[2]; }
+                const bool smp = (w[0] != 0.0 || w[1] != 0.0 || w[2] != 0.0 || w[3] != 0.0);
+                if (logpl) logpl[q] = v;
+                if (deltacf) {   // calculateDeltaCF: src/pseudolik.jl:491-498 (0 for unsampled quartets, :514)
+                    double d = fabs(obs[3 * q] - e[0]) + fabs(obs[3 * q + 1] - e[1]) + fabs(obs[3 * q + 2] - e[2]);
+                    deltacf[q] = smp ? d : 0.0;
+                }
+            }
+        }
+        // fixed-order block reduction
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < BLOCK / 32; i++) s += red[i];
+            partial[(size_t)blockIdx.x * P + p] = s;
+        }
+        __syncthreads();
+    }
+    if (st) atomicOr(status, st);
+}
+
+// out[p] = -(sum over blocks of partial[b][p]), fixed order (logPseudoLik(d): src/pseudolik.jl:1417-1423)
+__global__ void __launch_bounds__(256) k_reduce_partials(const double *__restrict__ partial, int nblocks, int stride, int P,
+                                                         double *__restrict__ out) {
+    // one warp per candidate: lanes stride over the blocks, then a shuffle tree
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= P) return;
+    double s = 0.0;
+    for (int b = lane; b < nblocks; b += 32) s += partial[(size_t)b * stride + warp];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) out[warp] = -s;
+}
+// transposed variant for the lanes kernel (candidates contiguous): thread per candidate, coalesced
+__global__ void __launch_bounds__(256) k_reduce_partials_t(const double *__restrict__ partial, int nblocks, int stride, int P,
+                                                           double *__restrict__ out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; b++) s += partial[(size_t)b * stride + p];
+    out[p] = -s;
+}
+
+// --------------------------------------------------------------------------------------------
+// FP64 roofline denominator: a dependent-chain DFMA microbenchmark (8 chains per thread)
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, double a, double b) {
+    double c0 = threadIdx.x, c1 = c0 + 1, c2 = c0 + 2, c3 = c0 + 3, c4 = c0 + 4, c5 = c0 + 5, c6 = c0 + 6, c7 = c0 + 7;
+    for (int i = 0; i < iters; i++) {
+        c0 = fma(c0, a, b); c1 = fma(c1, a, b); c2 = fma(c2, a, b); c3 = fma(c3, a, b);
+        c4 = fma(c4, a, b); c5 = fma(c5, a, b); c6 = fma(c6, a, b); c7 = fma(c7, a, b);
+    }
+    double s = c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7;
+    if (s == 12345.6789) out[0] = s;   // never true in practice; keeps the chains alive
+}
+
+// --------------------------------------------------------------------------------------------
+// context
+// --------------------------------------------------------------------------------------------
+struct snaq_ctx {
+    int device = 0, rank = 0, world = 1;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // data
+    int ntaxa = 0;
+    int64_t nq = 0, nq_total = 0, q_begin = 0;
+    uint16_t *d_taxa = nullptr;
+    double *d_obs = nullptr;
+    uint8_t *d_sampled = nullptr;
+    bool has_sampled = false;
+    // network
+    bool has_net = false;
+    SnaqHostTables H;
+    unsigned char *d_blob = nullptr;
+    size_t blob_cap = 0;
+    SnaqTables T{};
+    double *d_xconst = nullptr;
+    size_t xconst_cap = 0;
+    uint32_t *d_off = nullptr;
+    uint16_t *d_prog = nullptr;
+    size_t prog_cap = 0;
+    uint64_t prog_words = 0;
+    uint32_t maxlen = 0;
+    double *d_W = nullptr;
+    uint32_t *d_status = nullptr;          // [0] build, [1] eval
+    unsigned long long *d_total = nullptr; // [0] words, then u32 maxlen at [1]
+    void *d_scan_tmp = nullptr;
+    size_t scan_tmp_cap = 0;
+    // scratch
+    double *d_X = nullptr; size_t X_cap = 0;
+    double *d_out = nullptr; size_t out_cap = 0;
+    double *d_partial = nullptr; size_t partial_cap = 0;
+    double *h_pin = nullptr; size_t pin_cap = 0;
+    int sm_count = 148;
+    int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+static thread_local std::string g_create_err;
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                \
+            return SNAQ_ECUDA;                                                                            \
+        }                                                                                                 \
+    } while (0)
+
+template <class T> static int ensure(snaq_ctx *ctx, T *&p, size_t &cap, size_t need) {
+    if (need <= cap && p) return SNAQ_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t n = std::max<size_t>(need, 16);
+    cudaError_t e = cudaMalloc((void **)&p, n * sizeof(T));
+    if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return SNAQ_ENOMEM; }
+    cap = n;
+    return SNAQ_OK;
+}
+static int ensure_pin(snaq_ctx *ctx, size_t ndoubles) {
+    if (ndoubles <= ctx->pin_cap && ctx->h_pin) return SNAQ_OK;
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    ctx->h_pin = nullptr;
+    ctx->pin_cap = 0;
+    size_t n = std::max<size_t>(ndoubles, 1024);
+    cudaError_t e = cudaMallocHost((void **)&ctx->h_pin, n * sizeof(double));
+    if (e != cudaSuccess) { ctx->err = std::string("cudaMallocHost: ") + cudaGetErrorString(e); return SNAQ_ENOMEM; }
+    ctx->pin_cap = n;
+    return SNAQ_OK;
+}
+
+static const char *build_err_text(uint32_t e) {
+    switch (e) {
+        case SNAQ_B_POLYTOMY: return "four taxa meet at a tree node: the network is not binary";
+        case SNAQ_B_BLOCKS: return "block pattern of a quartet is inconsistent with the blob tree (taxon missing from the network, or not level-1)";
+        case SNAQ_B_OVERFLOW: return "a quartet program exceeds the descriptor limits (path too long / too many cycles on one path)";
+        default: return "unknown descriptor build error";
+    }
+}
+
+static int status_to_error(snaq_ctx *ctx, uint32_t st) {
+    if (!st) return SNAQ_OK;
+    if (st & SNAQ_S_RANGE) { ctx->err = "new gamma / gammaz value should be between 0,1 and lengths nonnegative (src/snaq_optimization.jl:213,221,228; src/auxiliary.jl:119)"; return SNAQ_ERANGE; }
+    if (st & SNAQ_S_NEGLEN) { ctx->err = "length can be negative, but not too negative (greater than -log(1.5)) or majorCF<0 (src/auxiliary.jl:120)"; return SNAQ_ENUMERIC; }
+    if (st & SNAQ_S_ZEROSUM) { ctx->err = "expCF not updated for quartet: sum(expCF)==0 (src/pseudolik.jl:1391)"; return SNAQ_ENUMERIC; }
+    ctx->err = "numerical error in the evaluation kernel";
+    return SNAQ_ENUMERIC;
+}
+
+static int run_weights(snaq_ctx *ctx) {
+    if (!ctx->has_net || ctx->nq == 0) return SNAQ_OK;
+    int64_t nb = (ctx->nq + 255) / 256;
+    k_weights<<<(unsigned)nb, 256, 0, ctx->stream>>>(ctx->d_off, ctx->d_prog, ctx->d_obs, ctx->has_sampled ? ctx->d_sampled : nullptr, ctx->nq, ctx->d_W);
+    CK(cudaGetLastError());
+    ctx->counters[5]++;
+    return SNAQ_OK;
+}
+
+// dispatch one evaluation of P candidates whose X is already on the device
+static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cudaStream_t stream,
+                       double *expcf, double *logpl, double *deltacf) {
+    const SnaqHostTables &H = ctx->H;
+    const int64_t nq = ctx->nq;
+    if (nq == 0) { CK(cudaMemsetAsync(dout, 0, sizeof(double) * P, stream)); return SNAQ_OK; }
+    const bool per_quartet = expcf || logpl || deltacf;
+    if (P >= LANES_MIN_P && !per_quartet) {
+        const int ngroups = (P + 31) / 32, Ppad = ngroups * 32;
+        // chunk: quartets per block.  Enough blocks to fill the machine (>= 4 per SM overall),
+        // bounded by shared memory.
+        const size_t xs_bytes = (size_t)H.n_xe * 32 * 8;
+        int warps = xs_bytes > 40 * 1024 ? 16 : 8;
+        int chunk = 512;
+        while (chunk > 64 && (int64_t)ngroups * ((nq + chunk - 1) / chunk) < (int64_t)ctx->sm_count * 8) chunk >>= 1;
+        auto smem_for = [&](int ch) {
+            return xs_bytes + (size_t)warps * 32 * 8 + (size_t)ch * 32 + (size_t)(ch + 1) * 4 + (size_t)ch * ctx->maxlen * 2 + 16;
+        };
+        while (chunk > 32 && smem_for(chunk) > 200 * 1024) chunk >>= 1;
+        const size_t smem = smem_for(chunk);
+        if (smem > 227 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_lanes"; return SNAQ_EINVAL; }
+        const int64_t nchunks = (nq + chunk - 1) / chunk;
+        if (nchunks > 2147483647LL || ngroups > 65535) { ctx->err = "batch too large for one launch"; return SNAQ_EINVAL; }
+        int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)nchunks * Ppad);
+        if (rc) return rc;
+        dim3 grid((unsigned)nchunks, (unsigned)ngroups);
+        if (warps == 8) {
+            CK(cudaFuncSetAttribute(k_eval_lanes<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_eval_lanes<8><<<grid, 256, smem, stream>>>(ctx->d_off, ctx->d_prog, ctx->d_W, nq, chunk, dX, ctx->d_xconst, H.nparams, H.nh,
+                                                        H.nt, H.n_xe, P, ctx->d_partial, Ppad, ctx->d_status + 1);
+        } else {
+            CK(cudaFuncSetAttribute(k_eval_lanes<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_eval_lanes<16><<<grid, 512, smem, stream>>>(ctx->d_off, ctx->d_prog, ctx->d_W, nq, chunk, dX, ctx->d_xconst, H.nparams,
+                                                         H.nh, H.nt, H.n_xe, P, ctx->d_partial, Ppad, ctx->d_status + 1);
+        }
+        CK(cudaGetLastError());
+        k_reduce_partials_t<<<(P + 255) / 256, 256, 0, stream>>>(ctx->d_partial, (int)nchunks, Ppad, P, dout);
+        CK(cudaGetLastError());
+        ctx->counters[0] += 1;
+        ctx->counters[1] += nq * (int64_t)P;
+        return SNAQ_OK;
+    }
+    // small batches: thread per quartet, QK_MAXP candidates per launch
+    constexpr int BLOCK = 256;
+    const int64_t nblocks = (nq + BLOCK - 1) / BLOCK;
+    for (int p0 = 0; p0 < P; p0 += QK_MAXP) {
+        const int Pc = std::min(QK_MAXP, P - p0);
+        int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)nblocks * Pc);
+        if (rc) return rc;
+        int maxwords = (int)std::min<uint64_t>((uint64_t)BLOCK * ctx->maxlen, 48 * 1024);
+        size_t smem = (size_t)Pc * H.n_xe * 8 + (BLOCK / 32) * 8 + (size_t)maxwords * 2 + 16;
+        if (smem > 200 * 1024) { maxwords = 0; smem = (size_t)Pc * H.n_xe * 8 + (BLOCK / 32) * 8 + 16; }
+        CK(cudaFuncSetAttribute(k_eval_quartets<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const bool last = (p0 + Pc == P);
+        k_eval_quartets<BLOCK><<<(unsigned)nblocks, BLOCK, smem, stream>>>(
+            ctx->d_off, ctx->d_prog, ctx->d_W, ctx->d_obs, nq, dX + (size_t)p0 * H.nparams, ctx->d_xconst, H.nparams, H.nh, H.nt,
+            H.n_xe, Pc, maxwords, ctx->d_partial, last ? expcf : nullptr, last ? logpl : nullptr, last ? deltacf : nullptr,
+            ctx->d_status + 1);
+        CK(cudaGetLastError());
+        k_reduce_partials<<<(Pc * 32 + 255) / 256, 256, 0, stream>>>(ctx->d_partial, (int)nblocks, Pc, Pc, dout + p0);
+        CK(cudaGetLastError());
+        ctx->counters[0] += 1;
+        ctx->counters[1] += nq * (int64_t)Pc;
+    }
+    return SNAQ_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// C ABI
+// --------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *snaq_version(void) { return "snaq_b200 0.1 (sm_100a)"; }
+
+const char *snaq_last_error(const snaq_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int snaq_create(const snaq_opts *opts, snaq_ctx **out) {
+    if (!out) return SNAQ_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                       " (this engine has no CPU path)";
+        return SNAQ_ECUDA;
+    }
+    snaq_ctx *ctx = new snaq_ctx();
+    ctx->device = opts ? opts->device : 0;
+    ctx->rank = opts ? opts->rank : 0;
+    ctx->world = (opts && opts->world_size > 0) ? opts->world_size : 1;
+    if (ctx->device < 0 || ctx->device >= ndev || ctx->rank < 0 || ctx->rank >= ctx->world) {
+        g_create_err = "bad device ordinal or rank";
+        delete ctx;
+        return SNAQ_EINVAL;
+    }
+    auto fail = [&](cudaError_t ce, const char *what) {
+        g_create_err = std::string(what) + ": " + cudaGetErrorString(ce);
+        delete ctx;
+        return SNAQ_ECUDA;
+    };
+    if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) return fail(e, "cudaSetDevice");
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, ctx->device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaMalloc((void **)&ctx->d_status, 4 * sizeof(uint32_t))) != cudaSuccess) return fail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void **)&ctx->d_total, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
+    cudaMemset(ctx->d_status, 0, 4 * sizeof(uint32_t));
+    *out = ctx;
+    return SNAQ_OK;
+}
+
+int snaq_destroy(snaq_ctx *ctx) {
+    if (!ctx) return SNAQ_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_blob); cudaFree(ctx->d_xconst);
+    cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_status); cudaFree(ctx->d_total);
+    cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_out); cudaFree(ctx->d_partial);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return SNAQ_OK;
+}
+
+int snaq_set_data(snaq_ctx *ctx, int32_t ntaxa, int64_t nq, const uint16_t *taxa, const double *obscf) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (ntaxa < 4 || ntaxa > 65535 || nq < 0 || (nq > 0 && (!taxa || !obscf))) { ctx->err = "bad arguments to snaq_set_data"; return SNAQ_EINVAL; }
+    CK(cudaSetDevice(ctx->device));
+    for (int64_t i = 0; i < nq * 4; i++)
+        if (taxa[i] >= ntaxa) { ctx->err = "taxon id out of range in quartet " + std::to_string(i / 4); return SNAQ_EINVAL; }
+    for (int64_t i = 0; i < nq * 3; i++)
+        if (!(obscf[i] >= 0.0 && obscf[i] <= 1.0)) { ctx->err = "obsCF must be between (0,1) in quartet " + std::to_string(i / 3); return SNAQ_EINVAL; }
+    // quartet-sharded mode: this rank keeps the contiguous block [r*nq/G, (r+1)*nq/G)
+    ctx->nq_total = nq;
+    ctx->q_begin = nq * ctx->rank / ctx->world;
+    const int64_t q_end = nq * (ctx->rank + 1) / ctx->world;
+    ctx->nq = q_end - ctx->q_begin;
+    ctx->ntaxa = ntaxa;
+    ctx->has_net = false;
+    ctx->has_sampled = false;
+    cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_off); cudaFree(ctx->d_W);
+    ctx->d_taxa = nullptr; ctx->d_obs = nullptr; ctx->d_sampled = nullptr; ctx->d_off = nullptr; ctx->d_W = nullptr;
+    const size_t n = (size_t)std::max<int64_t>(ctx->nq, 1);
+    CK(cudaMalloc((void **)&ctx->d_taxa, n * 4 * sizeof(uint16_t)));
+    CK(cudaMalloc((void **)&ctx->d_obs, n * 3 * sizeof(double)));
+    CK(cudaMalloc((void **)&ctx->d_sampled, n));
+    CK(cudaMalloc((void **)&ctx->d_off, (n + 1) * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&ctx->d_W, n * 4 * sizeof(double)));
+    if (ctx->nq > 0) {
+        CK(cudaMemcpyAsync(ctx->d_taxa, taxa + 4 * ctx->q_begin, (size_t)ctx->nq * 4 * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_obs, obscf + 3 * ctx->q_begin, (size_t)ctx->nq * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->counters[2] += ctx->nq * (4 * 2 + 3 * 8);
+    }
+    return SNAQ_OK;
+}
+
+int snaq_set_obscf(snaq_ctx *ctx, const double *obscf) {
+    if (!ctx || !obscf) return SNAQ_EINVAL;
+    if (!ctx->d_obs) { ctx->err = "snaq_set_data has not been called"; return SNAQ_ENODATA; }
+    CK(cudaSetDevice(ctx->device));
+    for (int64_t i = 0; i < ctx->nq_total * 3; i++)
+        if (!(obscf[i] >= 0.0 && obscf[i] <= 1.0)) { ctx->err = "obsCF must be between (0,1) in quartet " + std::to_string(i / 3); return SNAQ_EINVAL; }
+    if (ctx->nq > 0) {
+        CK(cudaMemcpyAsync(ctx->d_obs, obscf + 3 * ctx->q_begin, (size_t)ctx->nq * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->counters[2] += ctx->nq * 24;
+    }
+    int rc = run_weights(ctx);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SNAQ_OK;
+}
+
+int snaq_set_sampled(snaq_ctx *ctx, const uint8_t *mask) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (!ctx->d_obs) { ctx->err = "snaq_set_data has not been called"; return SNAQ_ENODATA; }
+    CK(cudaSetDevice(ctx->device));
+    ctx->has_sampled = (mask != nullptr);
+    if (mask && ctx->nq > 0) {
+        CK(cudaMemcpyAsync(ctx->d_sampled, mask + ctx->q_begin, (size_t)ctx->nq, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->counters[2] += ctx->nq;
+    }
+    int rc = run_weights(ctx);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SNAQ_OK;
+}
+
+int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (!ctx->d_taxa) { ctx->err = "snaq_set_data has not been called"; return SNAQ_ENODATA; }
+    CK(cudaSetDevice(ctx->device));
+    ctx->has_net = false;
+    int rc = snaq_build_tables(net, ctx->ntaxa, ctx->H, ctx->err);
+    if (rc) return rc;
+    const SnaqHostTables &H = ctx->H;
+    rc = ensure(ctx, ctx->d_blob, ctx->blob_cap, H.blob.size());
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->d_xconst, ctx->xconst_cap, std::max<size_t>(H.xconst.size(), 1));
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_blob, H.blob.data(), H.blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (!H.xconst.empty())
+        CK(cudaMemcpyAsync(ctx->d_xconst, H.xconst.data(), H.xconst.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->counters[2] += (int64_t)H.blob.size() + (int64_t)H.xconst.size() * 8;
+    ctx->T = H.view(ctx->d_blob);
+    const int64_t nq = ctx->nq;
+    ctx->prog_words = 0;
+    ctx->maxlen = 1;
+    if (nq > 0) {
+        // pass 1: program lengths (kept in d_off[1..nq]), total and maximum
+        CK(cudaMemsetAsync(ctx->d_total, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_status, 0, 4 * sizeof(uint32_t), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_off, 0, sizeof(uint32_t), ctx->stream));
+        const int64_t nb = (nq + 127) / 128;
+        uint32_t *d_len = ctx->d_off + 1;
+        k_build_count<<<(unsigned)nb, 128, 0, ctx->stream>>>(ctx->T, ctx->d_taxa, nq, d_len, ctx->d_total,
+                                                            reinterpret_cast<uint32_t *>(ctx->d_total + 1), ctx->d_status);
+        CK(cudaGetLastError());
+        unsigned long long tot[2] = {0, 0};
+        uint32_t st[4];
+        CK(cudaMemcpyAsync(tot, ctx->d_total, sizeof(tot), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(st, ctx->d_status, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (st[0]) { ctx->err = build_err_text(st[0]); return SNAQ_ETOPOLOGY; }
+        if (tot[0] >= 0xFFFFFFFFull) { ctx->err = "descriptor table exceeds 2^32 words on one GPU: shard the quartets (world_size>1)"; return SNAQ_EINVAL; }
+        ctx->prog_words = tot[0];
+        ctx->maxlen = (uint32_t)(tot[1] & 0xFFFFFFFFull);
+        // inclusive scan of the lengths in place => d_off[q+1] = end of program q
+        size_t tmp = 0;
+        CK(cub::DeviceScan::InclusiveSum(nullptr, tmp, d_len, d_len, nq, ctx->stream));
+        if (tmp > ctx->scan_tmp_cap) {
+            cudaFree(ctx->d_scan_tmp);
+            ctx->d_scan_tmp = nullptr;
+            CK(cudaMalloc(&ctx->d_scan_tmp, tmp));
+            ctx->scan_tmp_cap = tmp;
+        }
+        CK(cub::DeviceScan::InclusiveSum(ctx->d_scan_tmp, tmp, d_len, d_len, nq, ctx->stream));
+        rc = ensure(ctx, ctx->d_prog, ctx->prog_cap, (size_t)ctx->prog_words + 8);
+        if (rc) return rc;
+        k_build_emit<<<(unsigned)nb, 128, 0, ctx->stream>>>(ctx->T, ctx->d_taxa, nq, ctx->d_off, ctx->d_prog, ctx->d_status);
+        CK(cudaGetLastError());
+        ctx->counters[5] += 3;
+        ctx->has_net = true;
+        rc = run_weights(ctx);
+        if (rc) { ctx->has_net = false; return rc; }
+        CK(cudaMemcpyAsync(st, ctx->d_status, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (st[0]) { ctx->has_net = false; ctx->err = build_err_text(st[0]); return SNAQ_ETOPOLOGY; }
+        ctx->counters[3] += 16 + 16 + 16;
+    }
+    ctx->counters[4] = (int64_t)ctx->prog_words;
+    ctx->has_net = true;
+    return SNAQ_OK;
+}
+
+int snaq_patch_network(snaq_ctx *ctx, const snaq_flatnet *net, const int32_t *touched_taxa, int32_t n_touched) {
+    // Round 1: the descriptor table is a CSR whose program lengths change with the topology, so a
+    // patch is a full rebuild (two thread-per-quartet kernels + one scan).  The argument list is the
+    // final one; see DESIGN.md "incremental patch".
+    (void)touched_taxa; (void)n_touched;
+    return snaq_set_network(ctx, net);
+}
+
+int snaq_num_params(snaq_ctx *ctx, int32_t *nparams, int32_t *n_gamma, int32_t *n_t, int32_t *n_gammaz) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (!ctx->has_net) { ctx->err = "snaq_set_network has not been called"; return SNAQ_ENODATA; }
+    if (nparams) *nparams = ctx->H.nparams;
+    if (n_gamma) *n_gamma = ctx->H.nh;
+    if (n_t) *n_t = ctx->H.nt;
+    if (n_gammaz) *n_gammaz = ctx->H.nhz;
+    return SNAQ_OK;
+}
+
+int snaq_get_params(snaq_ctx *ctx, double *x, int32_t *numht, double *upper) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (!ctx->has_net) { ctx->err = "snaq_set_network has not been called"; return SNAQ_ENODATA; }
+    const SnaqHostTables &H = ctx->H;
+    if (x) std::memcpy(x, H.x0.data(), sizeof(double) * H.nparams);
+    if (numht) std::memcpy(numht, H.numht.data(), sizeof(int32_t) * H.nparams);
+    if (upper) std::memcpy(upper, H.upper.data(), sizeof(double) * H.nparams);
+    return SNAQ_OK;
+}
+
+static int check_x_host(snaq_ctx *ctx, int P, const double *X) {
+    const SnaqHostTables &H = ctx->H;
+    for (int p = 0; p < P; p++)
+        for (int s = 0; s < H.nparams; s++) {
+            const double v = X[(size_t)p * H.nparams + s];
+            const bool isT = s >= H.nh && s < H.nh + H.nt;
+            if (!(v >= 0.0) || (!isT && v > 1.0)) {
+                char buf[256];
+                if (isT) snprintf(buf, sizeof buf, "length has to be nonnegative: %g (parameter %d of vector %d)", v, s + 1, p + 1);
+                else snprintf(buf, sizeof buf, "new %s value should be between 0,1: %g. (parameter %d of vector %d)", s < H.nh ? "gamma" : "gammaz", v, s + 1, p + 1);
+                ctx->err = buf;
+                return SNAQ_ERANGE;
+            }
+        }
+    return SNAQ_OK;
+}
+
+int snaq_eval_device(snaq_ctx *ctx, int32_t P, int32_t nparams, const double *dX, double *dout, void *stream) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (!ctx->has_net) { ctx->err = "snaq_set_network has not been called"; return SNAQ_ENODATA; }
+    if (P <= 0 || nparams != ctx->H.nparams || !dX || !dout) { ctx->err = "bad arguments to snaq_eval_device (x has wrong length?)"; return SNAQ_EINVAL; }
+    CK(cudaSetDevice(ctx->device));
+    return eval_device(ctx, P, dX, dout, stream ? (cudaStream_t)stream : ctx->stream, nullptr, nullptr, nullptr);
+}
+
+// status word of the evaluation kernels since the last call; clears it
+int snaq_check_status(snaq_ctx *ctx) {
+    if (!ctx) return SNAQ_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    uint32_t st = 0;
+    CK(cudaMemcpy(&st, ctx->d_status + 1, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st) CK(cudaMemset(ctx->d_status + 1, 0, sizeof(uint32_t)));
+    return status_to_error(ctx, st);
+}
+
+int snaq_eval(snaq_ctx *ctx, int32_t P, int32_t nparams, const double *X, double *out) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (!ctx->has_net) { ctx->err = "snaq_set_network has not been called"; return SNAQ_ENODATA; }
+    if (P <= 0 || !X || !out) { ctx->err = "bad arguments to snaq_eval"; return SNAQ_EINVAL; }
+    if (nparams != ctx->H.nparams) {
+        ctx->err = "ht(net) (length " + std::to_string(ctx->H.nparams) + ") and vector x (length " + std::to_string(nparams) + ") need to have same length";
+        return SNAQ_EINVAL;
+    }
+    int rc = check_x_host(ctx, P, X);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t nx = (size_t)P * std::max(nparams, 1);
+    rc = ensure(ctx, ctx->d_X, ctx->X_cap, nx);
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->d_out, ctx->out_cap, (size_t)P + 1);
+    if (rc) return rc;
+    rc = ensure_pin(ctx, nx + P + 2);
+    if (rc) return rc;
+    std::memcpy(ctx->h_pin, X, sizeof(double) * (size_t)P * nparams);
+    CK(cudaMemcpyAsync(ctx->d_X, ctx->h_pin, sizeof(double) * (size_t)P * nparams, cudaMemcpyHostToDevice, ctx->stream));
+    rc = eval_device(ctx, P, ctx->d_X, ctx->d_out, ctx->stream, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    double *h_out = ctx->h_pin + nx;
+    uint32_t *h_st = reinterpret_cast<uint32_t *>(h_out + P);
+    CK(cudaMemcpyAsync(h_out, ctx->d_out, sizeof(double) * P, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_st, ctx->d_status + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->counters[2] += (int64_t)sizeof(double) * P * nparams;
+    ctx->counters[3] += (int64_t)sizeof(double) * P + 4;
+    if (*h_st) {
+        CK(cudaMemsetAsync(ctx->d_status + 1, 0, sizeof(uint32_t), ctx->stream));
+        return status_to_error(ctx, *h_st);
+    }
+    std::memcpy(out, h_out, sizeof(double) * P);
+    return SNAQ_OK;
+}
+
+int snaq_eval_quartets(snaq_ctx *ctx, int32_t nparams, const double *x, double *expcf, double *logpl, double *deltacf) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (!ctx->has_net) { ctx->err = "snaq_set_network has not been called"; return SNAQ_ENODATA; }
+    if (!x || nparams != ctx->H.nparams) { ctx->err = "bad arguments to snaq_eval_quartets (x has wrong length?)"; return SNAQ_EINVAL; }
+    int rc = check_x_host(ctx, 1, x);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t nq = ctx->nq;
+    rc = ensure(ctx, ctx->d_X, ctx->X_cap, (size_t)std::max(nparams, 1));
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->d_out, ctx->out_cap, 2);
+    if (rc) return rc;
+    double *d_e = nullptr, *d_l = nullptr, *d_d = nullptr;
+    const size_t n = (size_t)std::max<int64_t>(nq, 1);
+    if (expcf) CK(cudaMalloc((void **)&d_e, n * 3 * sizeof(double)));
+    if (logpl) CK(cudaMalloc((void **)&d_l, n * sizeof(double)));
+    if (deltacf) CK(cudaMalloc((void **)&d_d, n * sizeof(double)));
+    // always pass at least one per-quartet pointer so that the thread-per-quartet kernel is used
+    double *d_dummy = nullptr;
+    if (!d_e && !d_l && !d_d) { CK(cudaMalloc((void **)&d_dummy, n * sizeof(double))); d_l = d_dummy; }
+    CK(cudaMemcpyAsync(ctx->d_X, x, sizeof(double) * nparams, cudaMemcpyHostToDevice, ctx->stream));
+    rc = eval_device(ctx, 1, ctx->d_X, ctx->d_out, ctx->stream, d_e, d_l, d_d);
+    uint32_t st = 0;
+    if (!rc) {
+        cudaMemcpyAsync(&st, ctx->d_status + 1, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream);
+        if (expcf && nq) cudaMemcpyAsync(expcf, d_e, sizeof(double) * 3 * nq, cudaMemcpyDeviceToHost, ctx->stream);
+        if (logpl && nq) cudaMemcpyAsync(logpl, d_l, sizeof(double) * nq, cudaMemcpyDeviceToHost, ctx->stream);
+        if (deltacf && nq) cudaMemcpyAsync(deltacf, d_d, sizeof(double) * nq, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = SNAQ_ECUDA; }
+        ctx->counters[2] += 8 * nparams;
+        ctx->counters[3] += (expcf ? 24 : 0) * nq + (logpl ? 8 : 0) * nq + (deltacf ? 8 : 0) * nq;
+    }
+    cudaFree(d_e); if (d_l != d_dummy) cudaFree(d_l); cudaFree(d_d); cudaFree(d_dummy);
+    if (rc) return rc;
+    if (st) { cudaMemsetAsync(ctx->d_status + 1, 0, sizeof(uint32_t), ctx->stream); return status_to_error(ctx, st); }
+    return SNAQ_OK;
+}
+
+int snaq_get_descriptors(snaq_ctx *ctx, int8_t *which, int8_t *ntype, int8_t *types, int32_t max_types, int8_t *formula,
+                         uint8_t *hasedge) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (!ctx->has_net) { ctx->err = "snaq_set_network has not been called"; return SNAQ_ENODATA; }
+    if (hasedge) { ctx->err = "hasEdge read-back is not implemented yet (DESIGN.md, next rows)"; return SNAQ_EINVAL; }
+    CK(cudaSetDevice(ctx->device));
+    const int64_t nq = ctx->nq;
+    if (nq == 0) return SNAQ_OK;
+    const int nh = std::max(ctx->H.n_hybrids, 1);
+    int8_t *d_which = nullptr, *d_types = nullptr, *d_formula = nullptr;
+    CK(cudaMalloc((void **)&d_which, (size_t)nq));
+    CK(cudaMalloc((void **)&d_types, (size_t)nq * nh));
+    CK(cudaMalloc((void **)&d_formula, (size_t)nq * 3));
+    k_describe<<<(unsigned)((nq + 127) / 128), 128, 0, ctx->stream>>>(ctx->T, ctx->d_taxa, nq, d_which, d_types, ctx->H.n_hybrids, d_formula);
+    cudaError_t e = cudaGetLastError();
+    std::vector<int8_t> hw((size_t)nq), ht((size_t)nq * nh), hf((size_t)nq * 3);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hw.data(), d_which, hw.size(), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ht.data(), d_types, ht.size(), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hf.data(), d_formula, hf.size(), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_which); cudaFree(d_types); cudaFree(d_formula);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return SNAQ_ECUDA; }
+    ctx->counters[5]++;
+    ctx->counters[3] += (int64_t)nq * (4 + nh);
+    for (int64_t q = 0; q < nq; q++) {
+        if (which) which[q] = hw[q];
+        if (formula) for (int i = 0; i < 3; i++) formula[3 * q + i] = hf[3 * q + i];
+        int n = 0;
+        for (int i = 0; i < ctx->H.n_hybrids; i++) {
+            int8_t t = ht[(size_t)q * nh + i];
+            if (t > 0) { if (types && n < max_types) types[q * max_types + n] = t; n++; }
+        }
+        if (types) for (int i = n; i < max_types; i++) types[q * max_types + i] = 0;
+        if (ntype) ntype[q] = (int8_t)n;
+    }
+    return SNAQ_OK;
+}
+
+int snaq_measure_fp64_peak(snaq_ctx *ctx, double *tflops) {
+    if (!ctx || !tflops) return SNAQ_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure(ctx, ctx->d_out, ctx->out_cap, 2);
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int blocks = ctx->sm_count * 8, iters = 1 << 15;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        CK(cudaEventRecord(e0, ctx->stream));
+        k_dfma_peak<<<blocks, 256, 0, ctx->stream>>>(ctx->d_out, iters, 0.999999, 1e-9);
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = 2.0 * 8.0 * (double)iters * blocks * 256.0 / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return SNAQ_OK;
+}
+
+int snaq_get_counters(snaq_ctx *ctx, int64_t out[8]) {
+    if (!ctx || !out) return SNAQ_EINVAL;
+    for (int i = 0; i < 8; i++) out[i] = ctx->counters[i];
+    return SNAQ_OK;
+}
+
+}  // extern "C"

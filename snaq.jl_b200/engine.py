@@ -1,0 +1,237 @@
+"""ctypes binding of the C ABI (include/snaq_b200.h) and the host-side mirror of the
+reference's hot-path functions.
+
+Reference functions mirrored here (a trailing ``_`` stands for Julia's ``!``):
+
+===========================  ===============================================
+``extractQuartet_(net, d)``   ``extractQuartet!``      src/pseudolik.jl:503-540
+``calculateExpCFAll_(d,x,net)`` ``calculateExpCFAll!`` src/pseudolik.jl:1310-1324
+``logPseudoLik(d)``           ``logPseudoLik``         src/pseudolik.jl:1388-1425
+``topologyQpseudolik_(net,d)`` ``topologyQpseudolik!`` src/pseudolik.jl:1342-1378
+``parameters_(net)``          ``parameters!``          src/snaq_optimization.jl:94-101
+===========================  ===============================================
+
+There is no CPU path: if the CUDA library is missing or no GPU is visible every
+call raises ``SnaqError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .datacf import DataCF
+from .network import FlatNet, HybridNetwork, SnaqError
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libsnaqb200.so")
+_LIB = None
+
+EXPORTS = ["snaq_create", "snaq_destroy", "snaq_last_error", "snaq_version", "snaq_set_data", "snaq_set_obscf",
+           "snaq_set_sampled", "snaq_set_network", "snaq_patch_network", "snaq_num_params", "snaq_get_params",
+           "snaq_eval", "snaq_eval_device", "snaq_eval_quartets", "snaq_get_descriptors", "snaq_get_counters",
+           "snaq_check_status", "snaq_measure_fp64_peak"]
+
+
+class _Opts(C.Structure):
+    _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("world_size", C.c_int32), ("reserved", C.c_int32)]
+
+
+def load_library():
+    """Load libsnaqb200.so (built in-tree by ``__graft_entry__.build()``); fails loudly."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise SnaqError(f"CUDA engine not built: {LIB_PATH} is missing (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                            "there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        lib.snaq_last_error.restype = C.c_char_p
+        lib.snaq_last_error.argtypes = [C.c_void_p]
+        lib.snaq_version.restype = C.c_char_p
+        _LIB = lib
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Engine:
+    """One engine context = one GPU + one stream (``snaq_ctx``)."""
+
+    def __init__(self, device: int = 0, rank: int = 0, world_size: int = 1):
+        self.lib = load_library()
+        self.ctx = C.c_void_p()
+        opts = _Opts(device, rank, world_size, 0)
+        rc = self.lib.snaq_create(C.byref(opts), C.byref(self.ctx))
+        if rc:
+            raise SnaqError(f"snaq_create failed ({rc}): {self.lib.snaq_last_error(None).decode()}")
+        self.device = device
+        self.nparams = None
+        self.nq = 0
+        self._data_id = None
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None and self.ctx:
+            self.lib.snaq_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc:
+            raise SnaqError(self.lib.snaq_last_error(self.ctx).decode())
+
+    # -- data ----------------------------------------------------------------------
+    def set_data(self, d: DataCF) -> None:
+        self._chk(self.lib.snaq_set_data(self.ctx, C.c_int32(len(d.taxa)), C.c_int64(d.numQuartets),
+                                         _p(d.quartet_taxa), _p(d.obsCF)))
+        self.nq = d.numQuartets
+        self.nparams = None
+        if not bool(np.all(d.sampled)):
+            self.set_sampled(d.sampled)
+        self._data_id = id(d)
+
+    def set_obscf(self, obscf: np.ndarray) -> None:
+        ob = np.ascontiguousarray(obscf, dtype=np.float64)
+        if ob.size != 3 * self.nq:
+            raise SnaqError("obsCF has the wrong size")
+        self._chk(self.lib.snaq_set_obscf(self.ctx, _p(ob)))
+
+    def set_sampled(self, mask: Optional[np.ndarray]) -> None:
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self._chk(self.lib.snaq_set_sampled(self.ctx, _p(m)))
+
+    # -- topology --------------------------------------------------------------------
+    def set_network(self, flat: FlatNet) -> None:
+        self._chk(self.lib.snaq_set_network(self.ctx, flat.ptr()))
+        n = C.c_int32(); nh = C.c_int32(); nt = C.c_int32(); nz = C.c_int32()
+        self._chk(self.lib.snaq_num_params(self.ctx, C.byref(n), C.byref(nh), C.byref(nt), C.byref(nz)))
+        self.nparams, self.nh, self.nt, self.nhz = n.value, nh.value, nt.value, nz.value
+
+    def get_params(self):
+        x = np.zeros(self.nparams); numht = np.zeros(self.nparams, np.int32); up = np.zeros(self.nparams)
+        self._chk(self.lib.snaq_get_params(self.ctx, _p(x), _p(numht), _p(up)))
+        return x, numht, up
+
+    # -- evaluation ------------------------------------------------------------------
+    def eval(self, X) -> np.ndarray:
+        """-loglik for each row of X (host buffers; H2D + kernel + D2H)."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim == 1:
+            X = X.reshape(1, -1)
+        out = np.zeros(X.shape[0])
+        self._chk(self.lib.snaq_eval(self.ctx, C.c_int32(X.shape[0]), C.c_int32(X.shape[1]), _p(X), _p(out)))
+        return out
+
+    def eval_device(self, dX, dout, stream=None) -> None:
+        """Same with torch CUDA tensors (float64, contiguous); no synchronisation."""
+        P, n = int(dX.shape[0]), int(dX.shape[1])
+        self._chk(self.lib.snaq_eval_device(self.ctx, C.c_int32(P), C.c_int32(n), C.c_void_p(dX.data_ptr()),
+                                            C.c_void_p(dout.data_ptr()),
+                                            C.c_void_p(stream.cuda_stream if stream is not None else 0)))
+
+    def check_status(self) -> None:
+        self._chk(self.lib.snaq_check_status(self.ctx))
+
+    def eval_quartets(self, x, want=("expcf", "logpl", "deltacf")):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        e = np.zeros((self.nq, 3)) if "expcf" in want else None
+        l = np.zeros(self.nq) if "logpl" in want else None
+        dl = np.zeros(self.nq) if "deltacf" in want else None
+        self._chk(self.lib.snaq_eval_quartets(self.ctx, C.c_int32(x.size), _p(x), _p(e), _p(l), _p(dl)))
+        return e, l, dl
+
+    def descriptors(self, max_types: int = 8):
+        which = np.zeros(self.nq, np.int8); ntype = np.zeros(self.nq, np.int8)
+        types = np.zeros((self.nq, max_types), np.int8); formula = np.zeros((self.nq, 3), np.int8)
+        self._chk(self.lib.snaq_get_descriptors(self.ctx, _p(which), _p(ntype), _p(types), C.c_int32(max_types),
+                                                _p(formula), None))
+        return dict(which=which, ntype=ntype, types=types, formula=formula)
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double(0.0)
+        self._chk(self.lib.snaq_measure_fp64_peak(self.ctx, C.byref(v)))
+        return v.value
+
+    def counters(self):
+        out = (C.c_int64 * 8)()
+        self._chk(self.lib.snaq_get_counters(self.ctx, out))
+        v = list(out)
+        return dict(eval_launches=v[0], quartet_evals=v[1], h2d_bytes=v[2], d2h_bytes=v[3], descriptor_words=v[4],
+                    build_launches=v[5])
+
+
+# ------------------------------------------------------------------------------------
+# reference-facing functions
+# ------------------------------------------------------------------------------------
+_ENGINES = {}
+
+
+def _engine_for(d: DataCF, device: int = 0) -> Engine:
+    """One engine per (DataCF, device): obsCF and the quartet list stay resident in HBM."""
+    key = (id(d), device)
+    eng = _ENGINES.get(key)
+    if eng is None:
+        eng = Engine(device)
+        eng.set_data(d)
+        _ENGINES[key] = eng
+        d._engine = eng
+    return eng
+
+
+def parameters_(net: HybridNetwork):
+    """``parameters!(net)``: src/snaq_optimization.jl:94-101."""
+    return net.parameters()
+
+
+def extractQuartet_(net: HybridNetwork, d: DataCF, device: int = 0) -> None:
+    """``extractQuartet!(net,d)`` (src/pseudolik.jl:503-517): (re)builds the device descriptor
+    table for ``net`` and fills expCF / deltaCF of every quartet at the network's own parameters."""
+    eng = _engine_for(d, device)
+    net.parameters()
+    eng.set_network(net.flatten(d.taxa))
+    if eng.nparams != len(net.ht):
+        raise SnaqError("engine and host disagree on the number of parameters")
+    d._net_id = id(net)
+    d._x = np.array(net.ht, dtype=np.float64)
+    d.expCF, d.logPseudoLik, d.deltaCF = eng.eval_quartets(d._x)
+
+
+def calculateExpCFAll_(d: DataCF, x: Sequence[float], net: HybridNetwork) -> None:
+    """``calculateExpCFAll!(d,x,net)`` (src/pseudolik.jl:1310-1324): expCF of every sampled
+    quartet under x (stateless: equivalent to every qnet being `changed`)."""
+    eng = getattr(d, "_engine", None)
+    if eng is None or getattr(d, "_net_id", None) != id(net):
+        raise SnaqError("qnet in quartets on data are not correctly updated with extractQuartet")
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    if x.size != eng.nparams:
+        raise SnaqError(f"ht(net) (length {eng.nparams}) and vector x (length {x.size}) need to have same length")
+    d._x = x.copy()
+    d.expCF, d.logPseudoLik, d.deltaCF = eng.eval_quartets(x)
+
+
+def logPseudoLik(d: DataCF) -> float:
+    """``logPseudoLik(d)`` (src/pseudolik.jl:1417-1425): -sum of the per-quartet values."""
+    eng = getattr(d, "_engine", None)
+    if eng is None or getattr(d, "_x", None) is None:
+        raise SnaqError("expCF not updated: run extractQuartet_ / calculateExpCFAll_ first")
+    return float(eng.eval(d._x)[0])
+
+
+def topologyQpseudolik_(net: HybridNetwork, d: DataCF, device: int = 0) -> float:
+    """``topologyQpseudolik!`` (src/pseudolik.jl:1342-1378): pseudo-deviance of a fixed network;
+    updates ``net.loglik`` and the expected CFs stored in ``d``."""
+    for e in net.edge:
+        if e.hybrid and not e.gamma >= 0.0:
+            raise SnaqError("hybrid edge has missing γ value. Cannot compute quartet pseudo-likelihood.")
+    extractQuartet_(net, d, device)
+    val = logPseudoLik(d)
+    net.loglik = val
+    return val
