@@ -28,28 +28,45 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
+
+#include "snaq_math_tables.h"
 
 #if defined(__CUDACC__)
 #define SNAQ_HD __host__ __device__ __forceinline__
+#define SNAQ_HD_NOINLINE __host__ __device__ __noinline__
+#define SNAQ_UNROLL1 _Pragma("unroll 1")
 #else
 #define SNAQ_HD inline
+#define SNAQ_HD_NOINLINE inline
+#define SNAQ_UNROLL1
 #endif
 
 #define SNAQ_MAX_HYB 32          /* max hybrid nodes tracked in the parity descriptor */
 #define SNAQ_MAX_SLOT 4095       /* slots are 12 bit inside term headers */
 #define SNAQ_MAX_PATH 512        /* max blob-tree nodes on a quartet's internal path */
 
-/* program header (word 0) */
+/*
+ * Quartet programs.  Every quartet has one header BYTE (kept in a separate array, only the
+ * weight / read-back kernels need it) and a program of u16 words, padded with the NULL slot
+ * (index n_xe, value 0.0) to a multiple of 4 words so that programs are 8-byte aligned:
+ *
+ *   class A  tree-like, no cycle term : [slot]*            t1 = min(10, sum xe[slot])  (NULL pads add 0)
+ *   class B  tree-like with terms     : [n0 | nterms<<8] [slot]*n0 [term]*nterms
+ *   class C  4-cycle (which==2)       : T5   : [gslot] [n5 | n6<<8] [slot]*n5 [slot]*n6
+ *                                       T5BD1: [zslot1] [zslot2]
+ * The device table is sorted by class so that a warp / block only ever runs one of the loops.
+ */
 #define SNAQ_KIND_TREE   0u      /* which==1: one internal edge of length t1        */
 #define SNAQ_KIND_T5     1u      /* which==2: 4-cycle, gamma + two cycle segments   */
 #define SNAQ_KIND_T5BD1  2u      /* which==2: bad diamond I, two gammaz             */
-/* header: bits 0-1 kind | bits 2-4 perm (tree: position of the major CF; type 5:
- * permutation index) | bits 5-8 nterms | bits 9-15 n0 (main path pieces)          */
-#define SNAQ_HDR(kind, perm, nterms, n0) ((uint16_t)((kind) | ((perm) << 2) | ((nterms) << 5) | ((n0) << 9)))
+/* header byte: bits 0-1 kind | bits 2-4 perm (tree: position of the major CF; type 5:
+ * permutation index) | bit 5: has terms (class B)                                   */
+#define SNAQ_QHDR(kind, perm, terms) ((uint8_t)((kind) | ((perm) << 2) | ((terms) << 5)))
 #define SNAQ_HDR_KIND(h)   ((h) & 3u)
 #define SNAQ_HDR_PERM(h)   (((h) >> 2) & 7u)
-#define SNAQ_HDR_NTERMS(h) (((h) >> 5) & 15u)
-#define SNAQ_HDR_N0(h)     (((h) >> 9) & 127u)
+#define SNAQ_HDR_TERMS(h)  (((h) >> 5) & 1u)
+#define SNAQ_HDR_CLASS(h)  (SNAQ_HDR_KIND(h) == SNAQ_KIND_TREE ? SNAQ_HDR_TERMS(h) : 2u)
 /* term header: bits 0-1 type | bit 2 flag | bits 4-15 slot */
 #define SNAQ_T2   0u   /* 3-cycle, hybrid's child is a leaf  (eliminateTriangle! case 1) */
 #define SNAQ_T3   1u   /* 2-cycle on the internal path       (eliminateLoop! internal)   */
@@ -216,7 +233,7 @@ SNAQ_HD void snaq_perm_decode(int idx, int perm[3]) {
  * Build the evaluation program of one quartet.  tx = the four taxon ids in the
  * data's order.  Returns SNAQ_B_*; w.n is the program length in words.
  */
-SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWriter &w, SnaqQuartetInfo *info) {
+SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWriter &w, uint8_t *hdr, SnaqQuartetInfo *info) {
     int L[4];
     for (int i = 0; i < 4; i++) {
         L[i] = T.leaf_tnode[tx[i]];
@@ -231,9 +248,8 @@ SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWr
     int l02 = snaq_lca(T, L[0], L[2]), l13 = snaq_lca(T, L[1], L[3]);
     int l03 = snaq_lca(T, L[0], L[3]), l12 = snaq_lca(T, L[1], L[2]);
     int S0 = T.depth[l01] + T.depth[l23], S1 = T.depth[l02] + T.depth[l13], S2 = T.depth[l03] + T.depth[l12];
-    const int hdr_at = w.n;
-    snaq_put(w, 0);
     int pos[4];
+    *hdr = 0;
     if (S0 == S1 && S1 == S2) {
         /* the four taxa meet in one blob: it must be a cycle with four hit blocks */
         int X = snaq_deeper(T, snaq_deeper(T, l01, l02), l12);
@@ -262,14 +278,14 @@ SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWr
             if (T.cyc_flags[c] & 1) {
                 snaq_put(w, g);
                 snaq_put(w, g + 1);
-                if (w.out && hdr_at < w.cap) w.out[hdr_at] = SNAQ_HDR(SNAQ_KIND_T5BD1, pidx, 0, 0);
+                *hdr = SNAQ_QHDR(SNAQ_KIND_T5BD1, pidx, 0);
             } else {
                 int a = pos[o[1]], m = pos[o[2]], b = pos[o[3]];
                 snaq_put(w, g);
                 snaq_put(w, (unsigned)(m - a) | ((unsigned)(b - m) << 8));
                 snaq_put_arc(T, c, a, m, w);
                 snaq_put_arc(T, c, m, b, w);
-                if (w.out && hdr_at < w.cap) w.out[hdr_at] = SNAQ_HDR(SNAQ_KIND_T5, pidx, 0, 0);
+                *hdr = SNAQ_QHDR(SNAQ_KIND_T5, pidx, 0);
             }
             return SNAQ_B_OK;
         }
@@ -277,9 +293,9 @@ SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWr
         int n0 = snaq_put_arc(T, c, pos[o[1]], pos[o[2]], w);
         int mate = (o[0] == 0) ? o[1] : (o[1] == 0 ? o[0] : (o[2] == 0 ? o[3] : o[2]));   /* partner of data taxon 0 */
         int maj = mate - 1;
-        if (n0 > 127) return SNAQ_B_OVERFLOW;
+        if (n0 > 255) return SNAQ_B_OVERFLOW;
         if (info) info->formula[maj] = 1;
-        if (w.out && hdr_at < w.cap) w.out[hdr_at] = SNAQ_HDR(SNAQ_KIND_TREE, maj, 0, n0);
+        *hdr = SNAQ_QHDR(SNAQ_KIND_TREE, maj, 0);
         return SNAQ_B_OK;
     }
     /* resolved split: (p,q | r,s) */
@@ -380,6 +396,18 @@ SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWr
     }
     /* owner of a path element: 0 main list, 1 chain of the term at J1, 2 chain of the term at J2.
      * element kinds: edge i (between seq[i] and seq[i+1]); arc of interior node i; end arcs. */
+    /* number of cycle terms: decides between class A (bare slot list) and class B (count word first) */
+    int nterms_pre = (c1 >= 0 && e1.cls != SNAQ_C_OPEN) + (c2 >= 0 && e2.cls != SNAQ_C_OPEN);
+    for (int i = 1; i < ns - 1; i++) {
+        int c = T.tcycle[seq[i]];
+        if (c < 0) continue;
+        snaq_positions(T, c, tx, pos);
+        SnaqCyc m = snaq_classify_cycle(T, c, pos, p, q, r, s, 0);
+        if (m.cls < 0) return SNAQ_B_BLOCKS;
+        nterms_pre += (m.cls != SNAQ_C_OPEN);
+    }
+    const int cnt_word_at = w.n;
+    if (nterms_pre > 0) snaq_put(w, 0);
     int n0 = 0, nterms = 0;
     for (int pass = 0; pass < 3; pass++) {
         /* pass 0: main list; pass 1: the terms (with the chain of the J1-side type 4 inside);
@@ -477,102 +505,187 @@ SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWr
             }
         }
     }
-    if (n0 > 127 || nterms > 15) return SNAQ_B_OVERFLOW;
+    if (n0 > 255 || nterms > 255 || nterms != nterms_pre) return SNAQ_B_OVERFLOW;
     if (info) info->formula[maj] = 1;
-    if (w.out && hdr_at < w.cap) w.out[hdr_at] = SNAQ_HDR(SNAQ_KIND_TREE, maj, nterms, n0);
+    if (nterms > 0 && w.out && cnt_word_at < w.cap) w.out[cnt_word_at] = (uint16_t)(n0 | (nterms << 8));
+    *hdr = SNAQ_QHDR(SNAQ_KIND_TREE, maj, nterms > 0 ? 1 : 0);
     return SNAQ_B_OK;
 }
 
 /* ------------------------------------------------------------------------------
- * evaluation.  XF is a functor slot -> double (the candidate's xe).
+ * FP64 exp / log specialised to the ranges of this path (fewer FP64-pipe instructions than the
+ * generic library versions; <= 2e-16 relative error for exp on [-12,1], <= 2e-16 absolute or
+ * relative error, whichever is larger, for log on normal positive arguments).
+ * ------------------------------------------------------------------------------ */
+typedef struct SnaqMath {
+    const double *et;   /* [64]    2^(j/64)                                  */
+    const double *lt;   /* [128*2] 1/c_j, -log(1/c_j), c_j = 1+(j+.5)/128    */
+} SnaqMath;
+
+#if defined(__CUDA_ARCH__)
+SNAQ_HD int snaq_hi(double v) { return __double2hiint(v); }
+SNAQ_HD int snaq_lo(double v) { return __double2loint(v); }
+SNAQ_HD double snaq_mk(int hi, int lo) { return __hiloint2double(hi, lo); }
+#else
+SNAQ_HD int snaq_hi(double v) { int64_t b; memcpy(&b, &v, 8); return (int)(b >> 32); }
+SNAQ_HD int snaq_lo(double v) { int64_t b; memcpy(&b, &v, 8); return (int)(b & 0xffffffffLL); }
+SNAQ_HD double snaq_mk(int hi, int lo) { int64_t b = ((int64_t)hi << 32) | (uint32_t)lo; double v; memcpy(&v, &b, 8); return v; }
+#endif
+
+/* exp(u) for u in [-12, 1]: u = k*ln2/64 + r, exp(u) = 2^(k>>6) * 2^((k&63)/64) * exp(r), |r| <= ln2/128 */
+SNAQ_HD double snaq_exp(double u, const SnaqMath &M) {
+    const double magic = 6755399441055744.0;                 /* 1.5 * 2^52 */
+    const double kd = fma(u, SNAQ_64_LN2, magic);
+    const int k = snaq_lo(kd);
+    const double kf = kd - magic;
+    double r = fma(kf, -SNAQ_LN2_64_HI, u);
+    r = fma(kf, -SNAQ_LN2_64_LO, r);
+    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    q = fma(r, q, 1.0 / 6.0);
+    q = fma(r, q, 0.5);
+    q = fma(r, q, 1.0);
+    const double tj = M.et[k & 63];
+    const double v = fma(tj, r * q, tj);
+    return snaq_mk(snaq_hi(v) + ((k >> 6) << 20), snaq_lo(v));
+}
+
+/* rare arguments (0, negative, denormal, inf, nan): the library version, kept out of line */
+static SNAQ_HD_NOINLINE double snaq_log_slow(double z) { return log(z); }
+
+/* log(z): z = 2^e m, m in [1,2); r = m/c_j - 1 with |r| <= 2^-8; log z = e ln2 - log(1/c_j) + log1p(r) */
+SNAQ_HD double snaq_log(double z, const SnaqMath &M) {
+    if (!(z >= 2.2250738585072014e-308 && z <= 1.7976931348623157e308)) return snaq_log_slow(z);
+    const int hi = snaq_hi(z);
+    const int e = (hi >> 20) - 1023;
+    const int j = (hi >> 13) & 127;
+    const double m = snaq_mk((hi & 0x000FFFFF) | 0x3FF00000, snaq_lo(z));
+    const double inv = M.lt[2 * j], lc = M.lt[2 * j + 1];
+    const double r = fma(m, inv, -1.0);
+    double q = fma(r, -1.0 / 6.0, 0.2);
+    q = fma(r, q, -0.25);
+    q = fma(r, q, 1.0 / 3.0);
+    q = fma(r, q, -0.5);
+    const double p = fma(r * r, q, r);
+    return fma((double)e, SNAQ_LN2, lc + p);
+}
+
+/* ------------------------------------------------------------------------------
+ * evaluation.  XF is a functor slot -> double (the candidate's xe, NULL slot = 0.0).
  * ------------------------------------------------------------------------------ */
 template <class XF>
 SNAQ_HD double snaq_sum(const uint16_t *&pc, int n, const XF &x) {
     double a = 0.0;
+    SNAQ_UNROLL1
     for (int i = 0; i < n; i++) a += x(pc[i]);
     pc += n;
     return a;
 }
 SNAQ_HD double snaq_clamp10(double v) { return v > 10.0 ? 10.0 : v; }   /* setLength!: src/auxiliary.jl:122-124 */
 
-/*
- * Expected CFs of one quartet in PROGRAM order:
- *   tree-like: cf[0] = major (1-2/3 e^-t1), cf[1] = minor (1/3 e^-t1), t1 returned in *t1
- *   type 5   : cf[0..2] = cf1, cf2, cf3 of quartetType5!
- * Returns the program kind.  status gets SNAQ_S_* bits.
- */
+/* class A: t1 = min(10, sum of the slots); nwords counts the NULL padding too */
 template <class XF>
-SNAQ_HD unsigned snaq_eval_program(const uint16_t *pc, const XF &x, double cf[3], double *t1out, unsigned &status) {
-    const unsigned hdr = *pc++;
-    const unsigned kind = SNAQ_HDR_KIND(hdr);
-    if (kind == SNAQ_KIND_TREE) {
-        /* t1 = clamp( clamp(Bnear + R) + Bfar ): R = every non-negative piece (any merge order of
-         * those gives min(10, sum)); B = a type-4 term merged with its chain, which can be negative
-         * and is added first (near end) or last (far end) by internalLength! */
-        double R = snaq_sum(pc, (int)SNAQ_HDR_N0(hdr), x);
-        double Bn = 0.0, Bf = 0.0;
-        const int nterms = (int)SNAQ_HDR_NTERMS(hdr);
-        for (int it = 0; it < nterms; it++) {
-            const unsigned th = *pc++;
-            const unsigned ty = th & 3u;
-            const double gq = x(th >> 4);          /* minor gamma (or gammaz for TZ) */
-            if (ty == SNAQ_T2) {
-                int n = *pc++;
-                double e = snaq_clamp10(snaq_sum(pc, n, x));
-                double gh = (th & 4u) ? 1.0 - gq : gq;
-                R += snaq_clamp10(-log(1.0 - gh * (1.0 - exp(-e))));                 /* src/pseudolik.jl:938 */
-            } else if (ty == SNAQ_T3) {
-                unsigned nn = *pc++;
-                double l1 = snaq_clamp10(snaq_sum(pc, (int)(nn & 255u), x));
-                double l2 = snaq_clamp10(snaq_sum(pc, (int)(nn >> 8), x));
-                double g1 = 1.0 - gq, g2 = gq;
-                R += snaq_clamp10(-log(1.0 - g1 * g1 * (1.0 - exp(-l1)) - g2 * g2 * (1.0 - exp(-l2))));   /* :878 */
-            } else if (ty == SNAQ_T4) {
-                unsigned nn = *pc++;
-                int ne = *pc++;
-                int nchain = *pc++;
-                double la = snaq_clamp10(snaq_sum(pc, (int)(nn & 255u), x));
-                double lb = snaq_clamp10(snaq_sum(pc, (int)(nn >> 8), x));
-                double le = snaq_clamp10(snaq_sum(pc, ne, x));
-                double ch = snaq_clamp10(snaq_sum(pc, nchain, x));
-                double ga = 1.0 - gq, gb = gq;
-                double l4 = -log(gb * gb * exp(-lb) + ga * gb * (3.0 - exp(-le)) + ga * ga * exp(-la));   /* :951 */
-                if (l4 < SNAQ_MINLEN) status |= SNAQ_S_NEGLEN;
-                l4 = snaq_clamp10(l4);
-                double B = snaq_clamp10(ch + l4);                                     /* :956 */
-                if (B < SNAQ_MINLEN) status |= SNAQ_S_NEGLEN;
-                if (th & 4u) Bf = B; else Bn = B;
-            } else {
-                /* src/snaq_optimization.jl:230-234 and src/pseudolik.jl:221: -log(1-gammaz), capped at 10 */
-                R += snaq_clamp10(-log(1.0 - gq));
-            }
+SNAQ_HD double snaq_tree_plain_t1(const uint16_t *pc, int nwords, const XF &x) {
+    double t = 0.0;
+    for (int i = 0; i < nwords; i++) t += x(pc[i]);
+    return snaq_clamp10(t);
+}
+
+/* class B: t1 of a tree-like quartet with cycle terms.
+ * t1 = clamp( clamp(Bnear + R) + Bfar ): R = every non-negative piece (any merge order of those gives
+ * min(10, sum)); B = a type-4 term merged with its chain, which can be negative and is added first
+ * (near end) or last (far end) by internalLength! (src/pseudolik.jl:1076-1109) */
+template <class XF>
+SNAQ_HD double snaq_tree_terms_t1(const uint16_t *pc, const XF &x, const SnaqMath &M, unsigned &status) {
+    const unsigned cw = *pc++;
+    double R = snaq_sum(pc, (int)(cw & 255u), x);
+    double Bn = 0.0, Bf = 0.0;
+    const int nterms = (int)(cw >> 8);
+    for (int it = 0; it < nterms; it++) {
+        const unsigned th = *pc++;
+        const unsigned ty = th & 3u;
+        const double gq = x(th >> 4);          /* minor gamma (or gammaz for TZ) */
+        if (ty == SNAQ_T2) {
+            int n = *pc++;
+            double e = snaq_clamp10(snaq_sum(pc, n, x));
+            double gh = (th & 4u) ? 1.0 - gq : gq;
+            R += snaq_clamp10(-snaq_log(1.0 - gh * (1.0 - snaq_exp(-e, M)), M));                 /* src/pseudolik.jl:938 */
+        } else if (ty == SNAQ_T3) {
+            unsigned nn = *pc++;
+            double l1 = snaq_clamp10(snaq_sum(pc, (int)(nn & 255u), x));
+            double l2 = snaq_clamp10(snaq_sum(pc, (int)(nn >> 8), x));
+            double g1 = 1.0 - gq, g2 = gq;
+            R += snaq_clamp10(-snaq_log(1.0 - g1 * g1 * (1.0 - snaq_exp(-l1, M)) - g2 * g2 * (1.0 - snaq_exp(-l2, M)), M));   /* :878 */
+        } else if (ty == SNAQ_T4) {
+            unsigned nn = *pc++;
+            int ne = *pc++;
+            int nchain = *pc++;
+            double la = snaq_clamp10(snaq_sum(pc, (int)(nn & 255u), x));
+            double lb = snaq_clamp10(snaq_sum(pc, (int)(nn >> 8), x));
+            double le = snaq_clamp10(snaq_sum(pc, ne, x));
+            double ch = snaq_clamp10(snaq_sum(pc, nchain, x));
+            double ga = 1.0 - gq, gb = gq;
+            double l4 = -snaq_log(gb * gb * snaq_exp(-lb, M) + ga * gb * (3.0 - snaq_exp(-le, M)) + ga * ga * snaq_exp(-la, M), M);   /* :951 */
+            if (l4 < SNAQ_MINLEN) status |= SNAQ_S_NEGLEN;
+            l4 = snaq_clamp10(l4);
+            double B = snaq_clamp10(ch + l4);                                     /* :956 */
+            if (B < SNAQ_MINLEN) status |= SNAQ_S_NEGLEN;
+            if (th & 4u) Bf = B; else Bn = B;
+        } else {
+            /* src/snaq_optimization.jl:230-234 and src/pseudolik.jl:221: -log(1-gammaz), capped at 10 */
+            R += snaq_clamp10(-snaq_log(1.0 - gq, M));
         }
-        double t = snaq_clamp10(Bn + R);
-        if (t < SNAQ_MINLEN) status |= SNAQ_S_NEGLEN;
-        t = snaq_clamp10(t + Bf);
-        if (t < SNAQ_MINLEN) status |= SNAQ_S_NEGLEN;
-        const double y = exp(-t);
-        cf[0] = 1.0 - 2.0 / 3.0 * y;                                        /* src/pseudolik.jl:1259 */
-        cf[1] = 1.0 / 3.0 * y;
-        cf[2] = cf[1];
-        if (t1out) *t1out = t;
-    } else if (kind == SNAQ_KIND_T5) {
+    }
+    double t = snaq_clamp10(Bn + R);
+    if (t < SNAQ_MINLEN) status |= SNAQ_S_NEGLEN;
+    t = snaq_clamp10(t + Bf);
+    if (t < SNAQ_MINLEN) status |= SNAQ_S_NEGLEN;
+    return t;
+}
+
+/* tree-like CFs from t1: cf[0] major, cf[1] = cf[2] minor (src/pseudolik.jl:1259) */
+SNAQ_HD void snaq_tree_cf(double t, const SnaqMath &M, double cf[3]) {
+    const double y = snaq_exp(-t, M);
+    cf[0] = fma(-2.0 / 3.0, y, 1.0);
+    cf[1] = 1.0 / 3.0 * y;
+    cf[2] = cf[1];
+}
+
+/* class C: cf1, cf2, cf3 of quartetType5! (src/pseudolik.jl:985-991) */
+template <class XF>
+SNAQ_HD void snaq_t5_cf(unsigned kind, const uint16_t *pc, const XF &x, const SnaqMath &M, double cf[3]) {
+    if (kind == SNAQ_KIND_T5) {
         const double g2 = x(*pc++), g1 = 1.0 - g2;
         unsigned nn = *pc++;
-        double y5 = exp(-snaq_clamp10(snaq_sum(pc, (int)(nn & 255u), x)));
-        double y6 = exp(-snaq_clamp10(snaq_sum(pc, (int)(nn >> 8), x)));
-        cf[0] = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;          /* src/pseudolik.jl:989-991 */
+        double y5 = snaq_exp(-snaq_clamp10(snaq_sum(pc, (int)(nn & 255u), x)), M);
+        double y6 = snaq_exp(-snaq_clamp10(snaq_sum(pc, (int)(nn >> 8), x)), M);
+        cf[0] = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;
         cf[1] = g1 * 1.0 / 3.0 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
         cf[2] = g1 * 1.0 / 3.0 * y5 + g2 * 1.0 / 3.0 * y6;
-        if (t1out) *t1out = -1.0;
     } else {
         const double z1 = x(pc[0]), z2 = x(pc[1]);
-        cf[0] = (1.0 + 2.0 * z1 - z2) / 3.0;                                /* src/pseudolik.jl:985-987 */
+        cf[0] = (1.0 + 2.0 * z1 - z2) / 3.0;
         cf[1] = (1.0 + 2.0 * z2 - z1) / 3.0;
         cf[2] = (1.0 - z1 - z2) / 3.0;
-        if (t1out) *t1out = -1.0;
     }
-    return kind;
+}
+
+/*
+ * Expected CFs of one quartet of any class, in PROGRAM order (tree-like: cf[0] major, cf[1] minor,
+ * *t1 = the internal length; type 5: cf1, cf2, cf3 and *t1 = -1).  Generic path used by the
+ * per-quartet read-back and by the test harness; the hot loops call the class functions directly.
+ */
+template <class XF>
+SNAQ_HD void snaq_eval_quartet(unsigned hdr, const uint16_t *pc, int nwords, const XF &x, const SnaqMath &M, double cf[3],
+                               double *t1out, unsigned &status) {
+    const unsigned kind = SNAQ_HDR_KIND(hdr);
+    if (kind == SNAQ_KIND_TREE) {
+        const double t = SNAQ_HDR_TERMS(hdr) ? snaq_tree_terms_t1(pc, x, M, status) : snaq_tree_plain_t1(pc, nwords, x);
+        snaq_tree_cf(t, M, cf);
+        *t1out = t;
+    } else {
+        snaq_t5_cf(kind, pc, x, M, cf);
+        *t1out = -1.0;
+    }
 }
 
 /* program-order CFs -> data order (12|34, 13|24, 14|23) */
@@ -615,28 +728,33 @@ SNAQ_HD void snaq_weights(unsigned hdr, const double obs[3], int sampled, double
 }
 
 /*
- * logPseudoLik(quartet) (src/pseudolik.jl:1388-1410) from program-order CFs:
+ * logPseudoLik(quartet) (src/pseudolik.jl:1388-1410):
  *   sum_i [ expCF_i<0 ? -1e15 : (obs_i==0 ? 0 : 100 obs_i log(expCF_i/obs_i)) ]
- * written as sum_j W_j log(cf_j) - W[3]; for tree-like quartets log(minor) = -t1-log 3.
+ * written as sum_j W_j log(cf_j) - W[3]; for tree-like quartets log(minor) = -t1 - log 3.
  */
-SNAQ_HD double snaq_quartet_loglik(unsigned kind, const double cf[3], double t1, const double W[4], unsigned &status) {
-    double s;
-    if (kind == SNAQ_KIND_TREE) {
-        s = (W[0] != 0.0 ? W[0] * log(cf[0]) : 0.0) - W[1] * (t1 + SNAQ_LOG3) - W[3];
-        if (cf[0] < 0.0) status |= SNAQ_S_NEGLEN;
-    } else {
-        s = -W[3];
-        for (int j = 0; j < 3; j++) {
-            if (cf[j] < 0.0) {
-                /* -1e15 replaces this term, including its obs*log(obs) share of W[3] */
-                s += -1.e15 + (W[j] != 0.0 ? W[j] * log(W[j] / 100.0) : 0.0);
-            } else if (W[j] != 0.0) {
-                s += W[j] * log(cf[j]);
-            }
+SNAQ_HD double snaq_loglik_tree(double t, double major, const double W[4], const SnaqMath &M) {
+    return (W[0] != 0.0 ? W[0] * snaq_log(major, M) : 0.0) - W[1] * (t + SNAQ_LOG3) - W[3];
+}
+SNAQ_HD double snaq_loglik_t5(const double cf[3], const double W[4], const SnaqMath &M, unsigned &status) {
+    double s = -W[3];
+    for (int j = 0; j < 3; j++) {
+        if (cf[j] < 0.0) {
+            /* -1e15 replaces this term, including its obs*log(obs) share of W[3] */
+            s += -1.e15 + (W[j] != 0.0 ? W[j] * snaq_log_slow(W[j] / 100.0) : 0.0);
+        } else if (W[j] != 0.0) {
+            s += W[j] * snaq_log(cf[j], M);
         }
-        if (cf[0] + cf[1] + cf[2] == 0.0 && (W[0] != 0.0 || W[1] != 0.0 || W[2] != 0.0)) status |= SNAQ_S_ZEROSUM;
     }
+    if (cf[0] + cf[1] + cf[2] == 0.0 && (W[0] != 0.0 || W[1] != 0.0 || W[2] != 0.0)) status |= SNAQ_S_ZEROSUM;
     return s;
+}
+SNAQ_HD double snaq_quartet_loglik(unsigned kind, const double cf[3], double t1, const double W[4], const SnaqMath &M,
+                                   unsigned &status) {
+    if (kind == SNAQ_KIND_TREE) {
+        if (cf[0] < 0.0) status |= SNAQ_S_NEGLEN;
+        return snaq_loglik_tree(t1, cf[0], W, M);
+    }
+    return snaq_loglik_t5(cf, W, M, status);
 }
 
 #endif /* SNAQ_CORE_H */

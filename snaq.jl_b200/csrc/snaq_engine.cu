@@ -24,6 +24,7 @@
  * Tensor cores are not used: the path is a few exp/log per (quartet, candidate), not a contraction.
  */
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -42,26 +43,53 @@
 #define QK_MAXP 16        /* k_eval_quartets handles at most this many candidates per launch */
 
 // --------------------------------------------------------------------------------------------
+// math tables (copied to shared memory by every evaluation kernel)
+// --------------------------------------------------------------------------------------------
+__device__ const double g_exp_tab[SNAQ_EXP_TAB_N] = SNAQ_EXP_TAB_INIT;
+__device__ const double g_log_tab[SNAQ_LOG_TAB_N * 2] = SNAQ_LOG_TAB_INIT;
+#define MATH_TAB_DOUBLES (SNAQ_EXP_TAB_N + SNAQ_LOG_TAB_N * 2)
+
+__device__ __forceinline__ SnaqMath load_math_tables(double *dst, int tid, int nthreads) {
+    for (int i = tid; i < SNAQ_EXP_TAB_N; i += nthreads) dst[i] = g_exp_tab[i];
+    for (int i = tid; i < SNAQ_LOG_TAB_N * 2; i += nthreads) dst[SNAQ_EXP_TAB_N + i] = g_log_tab[i];
+    return SnaqMath{dst, dst + SNAQ_EXP_TAB_N};
+}
+
+// --------------------------------------------------------------------------------------------
 // descriptor build
 // --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_taxa(const uint16_t *__restrict__ taxa, int64_t q, uint16_t tx[4]) {
+    const ushort4 t4 = reinterpret_cast<const ushort4 *>(taxa)[q];
+    tx[0] = t4.x; tx[1] = t4.y; tx[2] = t4.z; tx[3] = t4.w;
+}
+
+// pass 1 (original quartet order): program length in 4-word chunks and class of every quartet
 __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_t *__restrict__ taxa, int64_t nq,
-                                                     uint32_t *__restrict__ len, unsigned long long *__restrict__ total,
-                                                     uint32_t *__restrict__ maxlen, uint32_t *__restrict__ status) {
+                                                     uint32_t *__restrict__ len4, uint8_t *__restrict__ cls,
+                                                     uint32_t *__restrict__ iota, unsigned long long *__restrict__ stats,
+                                                     uint32_t *__restrict__ status) {
+    // stats: [0] total chunks, [1] max chunks, [2..4] quartets per class
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned n = 0;
+    unsigned n = 0, c = 3;
     if (q < nq) {
         uint16_t tx[4];
-        const ushort4 t4 = reinterpret_cast<const ushort4 *>(taxa)[q];
-        tx[0] = t4.x; tx[1] = t4.y; tx[2] = t4.z; tx[3] = t4.w;
+        load_taxa(taxa, q, tx);
         SnaqWriter w{nullptr, 0, 0};
-        int e = snaq_build_quartet(T, tx, w, nullptr);
-        if (e) atomicMax(status, (uint32_t)e);
-        n = e ? 1u : (unsigned)w.n;
-        len[q] = n;
+        uint8_t hdr = 0;
+        int e = snaq_build_quartet(T, tx, w, &hdr, nullptr);
+        if (e) { atomicMax(status, (uint32_t)e); w.n = 1; hdr = 0; }
+        n = (unsigned)((w.n + 3) >> 2);
+        if (n == 0) n = 1;
+        c = SNAQ_HDR_CLASS(hdr);
+        len4[q] = n;
+        cls[q] = (uint8_t)c;
+        iota[q] = (uint32_t)q;
     }
-    // block totals (64-bit) and the longest program
     __shared__ unsigned long long ssum[4];
-    __shared__ unsigned smax[4];
+    __shared__ unsigned smax[4], scnt[3];
+    if (threadIdx.x < 3) scnt[threadIdx.x] = 0;
+    __syncthreads();
+    if (c < 3) atomicAdd(&scnt[c], 1u);
     unsigned long long s = n;
     unsigned m = n;
     for (int o = 16; o > 0; o >>= 1) {
@@ -71,49 +99,64 @@ __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_
     if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = s; smax[threadIdx.x >> 5] = m; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        atomicAdd(total, ssum[0] + ssum[1] + ssum[2] + ssum[3]);
-        atomicMax(maxlen, max(max(smax[0], smax[1]), max(smax[2], smax[3])));
+        atomicAdd(&stats[0], ssum[0] + ssum[1] + ssum[2] + ssum[3]);
+        atomicMax(&stats[1], (unsigned long long)max(max(smax[0], smax[1]), max(smax[2], smax[3])));
+        for (int k = 0; k < 3; k++) if (scnt[k]) atomicAdd(&stats[2 + k], (unsigned long long)scnt[k]);
     }
 }
 
-__global__ void __launch_bounds__(128) k_build_emit(SnaqTables T, const uint16_t *__restrict__ taxa, int64_t nq,
-                                                    const uint32_t *__restrict__ off, uint16_t *__restrict__ prog,
-                                                    uint32_t *__restrict__ status) {
-    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    uint16_t tx[4];
-    const ushort4 t4 = reinterpret_cast<const ushort4 *>(taxa)[q];
-    tx[0] = t4.x; tx[1] = t4.y; tx[2] = t4.z; tx[3] = t4.w;
-    const uint32_t o0 = off[q], o1 = off[q + 1];
-    SnaqWriter w{prog + o0, 0, (int)(o1 - o0)};
-    int e = snaq_build_quartet(T, tx, w, nullptr);
-    if (e) { atomicMax(status, (uint32_t)e); prog[o0] = SNAQ_HDR(SNAQ_KIND_TREE, 0, 0, 0); }
-    else if ((uint32_t)w.n != o1 - o0) atomicMax(status, (uint32_t)SNAQ_B_OVERFLOW);
+// lengths in class-sorted order (then scanned in place into offsets)
+__global__ void __launch_bounds__(256) k_gather_len(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ len4,
+                                                    int64_t nq, uint32_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) out[i] = len4[perm[i]];
 }
 
-__global__ void __launch_bounds__(256) k_weights(const uint32_t *__restrict__ off, const uint16_t *__restrict__ prog,
+// pass 2 (sorted order): emit the program of quartet perm[i] at chunk offset off[i], NULL-padded
+__global__ void __launch_bounds__(128) k_build_emit(SnaqTables T, const uint16_t *__restrict__ taxa, int64_t nq,
+                                                    const uint32_t *__restrict__ perm, const uint32_t *__restrict__ off,
+                                                    uint16_t *__restrict__ prog, uint8_t *__restrict__ qhdr,
+                                                    uint32_t *__restrict__ status) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    uint16_t tx[4];
+    load_taxa(taxa, perm[i], tx);
+    const uint32_t o0 = off[i], o1 = off[i + 1];
+    uint16_t *dst = prog + (size_t)o0 * 4;
+    const int cap = (int)(o1 - o0) * 4;
+    SnaqWriter w{dst, 0, cap};
+    uint8_t hdr = 0;
+    int e = snaq_build_quartet(T, tx, w, &hdr, nullptr);
+    if (e) { atomicMax(status, (uint32_t)e); w.n = 0; hdr = 0; }
+    else if (w.n > cap) { atomicMax(status, (uint32_t)SNAQ_B_OVERFLOW); w.n = cap; }
+    for (int k = w.n; k < cap; k++) dst[k] = (uint16_t)T.n_xe;      // NULL slot (value 0.0)
+    qhdr[i] = hdr;
+}
+
+__global__ void __launch_bounds__(256) k_weights(const uint32_t *__restrict__ perm, const uint8_t *__restrict__ qhdr,
                                                  const double *__restrict__ obs, const uint8_t *__restrict__ sampled,
                                                  int64_t nq, double *__restrict__ W) {
-    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const int64_t q = perm[i];
     double o[3] = {obs[3 * q], obs[3 * q + 1], obs[3 * q + 2]};
     double w[4];
-    snaq_weights(prog[off[q]], o, sampled ? sampled[q] : 1, w);
-    reinterpret_cast<double4 *>(W)[q] = make_double4(w[0], w[1], w[2], w[3]);
+    snaq_weights(qhdr[i], o, sampled ? sampled[q] : 1, w);
+    reinterpret_cast<double4 *>(W)[i] = make_double4(w[0], w[1], w[2], w[3]);
 }
 
-// parity descriptors: which / typeHyb per hybrid / formula
+// parity descriptors: which / typeHyb per hybrid / formula, original order
 __global__ void __launch_bounds__(128) k_describe(SnaqTables T, const uint16_t *__restrict__ taxa, int64_t nq,
                                                   int8_t *__restrict__ which, int8_t *__restrict__ types,
                                                   int nhyb, int8_t *__restrict__ formula) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     uint16_t tx[4];
-    const ushort4 t4 = reinterpret_cast<const ushort4 *>(taxa)[q];
-    tx[0] = t4.x; tx[1] = t4.y; tx[2] = t4.z; tx[3] = t4.w;
+    load_taxa(taxa, q, tx);
     SnaqWriter w{nullptr, 0, 0};
     SnaqQuartetInfo info;
-    snaq_build_quartet(T, tx, w, &info);
+    uint8_t hdr;
+    snaq_build_quartet(T, tx, w, &hdr, &info);
     which[q] = info.which;
     for (int i = 0; i < 3; i++) formula[3 * q + i] = info.formula[i];
     for (int i = 0; i < nhyb; i++) types[q * nhyb + i] = info.type[i];
@@ -122,7 +165,7 @@ __global__ void __launch_bounds__(128) k_describe(SnaqTables T, const uint16_t *
 // --------------------------------------------------------------------------------------------
 // evaluation
 // --------------------------------------------------------------------------------------------
-struct XLane {   // candidate = lane; xs is [slot][32]
+struct XLane {   // candidate = lane; xs is [slot][32] (already offset by the lane)
     const double *xs;
     __device__ __forceinline__ double operator()(unsigned s) const { return xs[s * 32u]; }
 };
@@ -133,31 +176,45 @@ struct XRow {    // one candidate's xe, contiguous
 
 __device__ __forceinline__ unsigned range_check(double v, double hi) { return (v >= 0.0 && v <= hi) ? 0u : SNAQ_S_RANGE; }
 
+struct ClassRanges {       // sorted quartet positions [0,nA) class A, [nA,nA+nB) class B, rest class C
+    int64_t nA, nB, nC;
+    int chA, chB, chC;     // chunks (blocks) per class
+};
+
 /*
- * grid (nchunks, ngroups); block = WARPS*32 threads.  Block (cb, g) evaluates quartets
- * [cb*chunk, (cb+1)*chunk) for candidates [32g, 32g+32).  Dynamic shared memory:
- *   xs   [n_xe][32] f64   candidates' extended parameter vectors, transposed
+ * grid (nchunks, ngroups); block = WARPS*32 threads.  Block (cb, g) evaluates one chunk of quartets
+ * of ONE class for candidates [32g, 32g+32).  Dynamic shared memory:
+ *   xs   [n_xe+1][32] f64  candidates' extended parameter vectors, transposed; last row = NULL slot (0.0)
  *   red  [WARPS][32] f64
+ *   math tables (320 f64)
  *   sW   [chunk][4] f64
- *   soff [chunk+1]  u32
- *   sprog[maxwords] u16
+ *   soff [chunk+1]  u32    (chunk units of 4 words)
+ *   sprog[.]        8-byte chunks
  */
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__restrict__ off, const uint16_t *__restrict__ prog,
-                                                         const double *__restrict__ W, int64_t nq, int chunk,
-                                                         const double *__restrict__ X, const double *__restrict__ xconst,
-                                                         int nparams, int nh, int nt, int n_xe, int P,
-                                                         double *__restrict__ partial, int Ppad, uint32_t *__restrict__ status) {
+                                                         const uint8_t *__restrict__ qhdr, const double *__restrict__ W,
+                                                         ClassRanges cr, int chunk, const double *__restrict__ X,
+                                                         const double *__restrict__ xconst, int nparams, int nh, int nt,
+                                                         int n_xe, int P, double *__restrict__ partial, int Ppad,
+                                                         uint32_t *__restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem[];
     double *xs = reinterpret_cast<double *>(smem);
-    double *red = xs + (size_t)n_xe * 32;
-    double *sW = red + WARPS * 32;
+    double *red = xs + (size_t)(n_xe + 1) * 32;
+    double *mt = red + WARPS * 32;
+    double *sW = mt + MATH_TAB_DOUBLES;
     uint32_t *soff = reinterpret_cast<uint32_t *>(sW + (size_t)chunk * 4);
-    uint16_t *sprog = reinterpret_cast<uint16_t *>(soff + chunk + 1);
+    uint2 *sprog = reinterpret_cast<uint2 *>(smem + (((size_t)(reinterpret_cast<unsigned char *>(soff + chunk + 1) - smem) + 7) & ~size_t(7)));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = blockIdx.y;
-    const int64_t q0 = (int64_t)blockIdx.x * chunk;
-    const int nqc = (int)min((int64_t)chunk, nq - q0);
+    // heavy classes first: C, B, then A
+    int cls, cb = blockIdx.x;
+    int64_t qbase, qend;
+    if (cb < cr.chC) { cls = 2; qbase = cr.nA + cr.nB; qend = qbase + cr.nC; }
+    else if (cb < cr.chC + cr.chB) { cls = 1; cb -= cr.chC; qbase = cr.nA; qend = qbase + cr.nB; }
+    else { cls = 0; cb -= cr.chC + cr.chB; qbase = 0; qend = cr.nA; }
+    const int64_t q0 = qbase + (int64_t)cb * chunk;
+    const int nqc = (int)min((int64_t)chunk, qend - q0);
     unsigned st = 0;
     // x tile: coalesced global reads (row-major X), transposed into xs[slot][lane]
     for (int idx = tid; idx < 32 * nparams; idx += WARPS * 32) {
@@ -169,23 +226,64 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
     }
     for (int idx = tid; idx < 32 * (n_xe - nparams); idx += WARPS * 32)
         xs[(size_t)nparams * 32 + idx] = xconst[idx >> 5];
-    // quartet programs, offsets and weights of this chunk
+    if (tid < 32) xs[(size_t)n_xe * 32 + tid] = 0.0;
+    const SnaqMath M = load_math_tables(mt, tid, WARPS * 32);
+    // quartet programs (8-byte chunks, coalesced), offsets and weights of this chunk
     const uint32_t base = off[q0];
-    const uint32_t nwords = off[q0 + nqc] - base;
+    const uint32_t nchunks = off[q0 + nqc] - base;
     for (int i = tid; i <= nqc; i += WARPS * 32) soff[i] = off[q0 + i] - base;
-    for (uint32_t i = tid; i < nwords; i += WARPS * 32) sprog[i] = prog[base + i];
     {
-        const double2 *src = reinterpret_cast<const double2 *>(W + (size_t)q0 * 4);
-        double2 *dst = reinterpret_cast<double2 *>(sW);
-        for (int i = tid; i < nqc * 2; i += WARPS * 32) dst[i] = src[i];
+        const uint2 *src = reinterpret_cast<const uint2 *>(prog) + base;
+        for (uint32_t i = tid; i < nchunks; i += WARPS * 32) sprog[i] = src[i];
+        const double2 *wsrc = reinterpret_cast<const double2 *>(W + (size_t)q0 * 4);
+        double2 *wdst = reinterpret_cast<double2 *>(sW);
+        for (int i = tid; i < nqc * 2; i += WARPS * 32) wdst[i] = wsrc[i];
     }
     __syncthreads();
     double acc = 0.0;
-    const XLane xf{xs + lane};
-    for (int i = warp; i < nqc; i += WARPS) {
-        double cf[3], t1;
-        const unsigned kind = snaq_eval_program(sprog + soff[i], xf, cf, &t1, st);
-        acc += snaq_quartet_loglik(kind, cf, t1, sW + 4 * i, st);
+    const double *xl = xs + lane;
+    if (cls == 0) {
+        // class A: t1 = min(10, sum of slots); two warps' worth of independent work per iteration is not
+        // needed: latency is hidden by the other warps of the SM
+#pragma unroll 1
+        for (int i = warp; i < nqc; i += WARPS) {
+            const uint32_t o0 = soff[i], o1 = soff[i + 1];
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll 1
+            for (uint32_t c = o0; c < o1; c++) {
+                const uint2 w = sprog[c];
+                t0 += xl[(w.x & 0xffffu) << 5];
+                t1 += xl[(w.x >> 16) << 5];
+                t0 += xl[(w.y & 0xffffu) << 5];
+                t1 += xl[(w.y >> 16) << 5];
+            }
+            const double t = fmin(t0 + t1, 10.0);
+            const double y = snaq_exp(-t, M);
+            const double major = fma(-2.0 / 3.0, y, 1.0);
+            const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
+            acc += fma(w4.x, snaq_log(major, M), -fma(w4.y, t + SNAQ_LOG3, w4.w));
+        }
+    } else if (cls == 1) {
+        const XLane xf{xl};
+#pragma unroll 1
+        for (int i = warp; i < nqc; i += WARPS) {
+            const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + soff[i]);
+            const double t = snaq_tree_terms_t1(pc, xf, M, st);
+            const double y = snaq_exp(-t, M);
+            const double major = fma(-2.0 / 3.0, y, 1.0);
+            if (major < 0.0) st |= SNAQ_S_NEGLEN;
+            acc += snaq_loglik_tree(t, major, sW + 4 * i, M);
+        }
+    } else {
+        const XLane xf{xl};
+        const uint8_t *hd = qhdr + q0;
+#pragma unroll 1
+        for (int i = warp; i < nqc; i += WARPS) {
+            const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + soff[i]);
+            double cf[3];
+            snaq_t5_cf(SNAQ_HDR_KIND(hd[i]), pc, xf, M, cf);
+            acc += snaq_loglik_t5(cf, sW + 4 * i, M, st);
+        }
     }
     red[warp * 32 + lane] = acc;
     __syncthreads();
@@ -199,66 +297,82 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
 }
 
 /*
- * Thread per quartet, P <= QK_MAXP candidates.  Block of BLOCK threads stages its quartets'
- * programs in shared memory with coalesced loads; x vectors (P x n_xe) sit in shared memory.
- * partial[block][p] gets the block's sum.  Optional per-quartet outputs (P==1 semantics: they are
- * written for the LAST candidate): expcf [nq][3] in data order, logpl [nq], deltacf [nq].
+ * Thread per quartet (sorted order), P <= QK_MAXP candidates.  x vectors (P x (n_xe+1)) and the math
+ * tables sit in shared memory; programs are read straight from global memory in 8-byte chunks.
+ * partial[block][p] gets the block's sum.  Optional per-quartet outputs, written for the LAST
+ * candidate at the quartet's ORIGINAL index: expcf [nq][3] in data order, logpl [nq], deltacf [nq].
  */
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_eval_quartets(const uint32_t *__restrict__ off, const uint16_t *__restrict__ prog,
+                                                        const uint8_t *__restrict__ qhdr, const uint32_t *__restrict__ perm,
                                                         const double *__restrict__ W, const double *__restrict__ obs,
-                                                        int64_t nq, const double *__restrict__ X,
+                                                        int64_t nq, int64_t nA, const double *__restrict__ X,
                                                         const double *__restrict__ xconst, int nparams, int nh, int nt,
-                                                        int n_xe, int P, int maxwords, double *__restrict__ partial,
+                                                        int n_xe, int P, double *__restrict__ partial,
                                                         double *__restrict__ expcf, double *__restrict__ logpl,
                                                         double *__restrict__ deltacf, uint32_t *__restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem[];
-    double *xs = reinterpret_cast<double *>(smem);                 // [P][n_xe]
-    double *red = xs + (size_t)P * n_xe;                           // [BLOCK/32]
-    uint16_t *sprog = reinterpret_cast<uint16_t *>(red + BLOCK / 32);
+    const int xstride = n_xe + 1;
+    double *xs = reinterpret_cast<double *>(smem);                 // [P][n_xe+1]
+    double *red = xs + (size_t)P * xstride;                        // [BLOCK/32]
+    double *mt = red + BLOCK / 32;
     const int tid = threadIdx.x;
-    const int64_t q0 = (int64_t)blockIdx.x * BLOCK;
-    const int nqc = (int)min((int64_t)BLOCK, nq - q0);
     unsigned st = 0;
-    for (int idx = tid; idx < P * n_xe; idx += BLOCK) {
-        int p = idx / n_xe, s = idx - p * n_xe;
-        double v;
+    for (int idx = tid; idx < P * xstride; idx += BLOCK) {
+        int p = idx / xstride, s = idx - p * xstride;
+        double v = 0.0;
         if (s < nparams) {
             v = X[(size_t)p * nparams + s];
             st |= range_check(v, (s >= nh && s < nh + nt) ? 1.0e300 : 1.0);
-        } else v = xconst[s - nparams];
+        } else if (s < n_xe) v = xconst[s - nparams];
         xs[idx] = v;
     }
-    const uint32_t base = off[q0];
-    const uint32_t nwords = off[q0 + nqc] - base;
-    const bool staged = nwords <= (uint32_t)maxwords;
-    if (staged)
-        for (uint32_t i = tid; i < nwords; i += BLOCK) sprog[i] = prog[base + i];
+    const SnaqMath M = load_math_tables(mt, tid, BLOCK);
     __syncthreads();
-    const int64_t q = q0 + tid;
-    const bool active = tid < nqc;
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + tid;
+    const bool active = i < nq;
     const uint16_t *pc = nullptr;
+    int nwords = 0;
+    unsigned hdr = 0;
     double w[4] = {0, 0, 0, 0};
     if (active) {
-        const uint32_t o = off[q];
-        pc = staged ? sprog + (o - base) : prog + o;
-        const double4 w4 = reinterpret_cast<const double4 *>(W)[q];
+        const uint32_t o0 = off[i], o1 = off[i + 1];
+        pc = prog + (size_t)o0 * 4;
+        nwords = (int)(o1 - o0) * 4;
+        const double4 w4 = reinterpret_cast<const double4 *>(W)[i];
         w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+        hdr = (i < nA) ? 0u : (unsigned)qhdr[i];      // class A needs nothing from its header here
     }
+    const bool want_out = expcf || logpl || deltacf;
+#pragma unroll 1
     for (int p = 0; p < P; p++) {
         double v = 0.0;
         if (active) {
+            const XRow xf{xs + (size_t)p * xstride};
             double cf[3], t1;
-            const XRow xf{xs + (size_t)p * n_xe};
-            const unsigned kind = snaq_eval_program(pc, xf, cf, &t1, st);
-            v = snaq_quartet_loglik(kind, cf, t1, w, st);
-            if (p == P - 1 && (expcf || logpl || deltacf)) {
+            if (i < nA) {
+                double t = 0.0;
+                const uint2 *pp = reinterpret_cast<const uint2 *>(pc);
+                for (int c = 0; c < (nwords >> 2); c++) {
+                    const uint2 ww = pp[c];
+                    t += xf(ww.x & 0xffffu); t += xf(ww.x >> 16); t += xf(ww.y & 0xffffu); t += xf(ww.y >> 16);
+                }
+                t1 = fmin(t, 10.0);
+                snaq_tree_cf(t1, M, cf);
+                v = fma(w[0], snaq_log(cf[0], M), -fma(w[1], t1 + SNAQ_LOG3, w[3]));
+            } else {
+                snaq_eval_quartet(hdr, pc, nwords, xf, M, cf, &t1, st);
+                v = snaq_quartet_loglik(SNAQ_HDR_KIND(hdr), cf, t1, w, M, st);
+            }
+            if (want_out && p == P - 1) {
+                const unsigned h = (unsigned)qhdr[i];
+                const int64_t q = perm[i];
                 double e[3];
-                snaq_data_order(pc[0], cf, e);
+                snaq_data_order(h, cf, e);
                 if (expcf) { expcf[3 * q] = e[0]; expcf[3 * q + 1] = e[1]; expcf[3 * q + 2] = e[2]; }
-                const bool smp = (w[0] != 0.0 || w[1] != 0.0 || w[2] != 0.0 || w[3] != 0.0);
                 if (logpl) logpl[q] = v;
                 if (deltacf) {   // calculateDeltaCF: src/pseudolik.jl:491-498 (0 for unsampled quartets, :514)
+                    const bool smp = (w[0] != 0.0 || w[1] != 0.0 || w[2] != 0.0 || w[3] != 0.0);
                     double d = fabs(obs[3 * q] - e[0]) + fabs(obs[3 * q + 1] - e[1]) + fabs(obs[3 * q + 2] - e[2]);
                     deltacf[q] = smp ? d : 0.0;
                 }
@@ -271,7 +385,7 @@ __global__ void __launch_bounds__(BLOCK) k_eval_quartets(const uint32_t *__restr
         if (tid == 0) {
             double s = 0.0;
 #pragma unroll
-            for (int i = 0; i < BLOCK / 32; i++) s += red[i];
+            for (int k = 0; k < BLOCK / 32; k++) s += red[k];
             partial[(size_t)blockIdx.x * P + p] = s;
         }
         __syncthreads();
@@ -335,14 +449,19 @@ struct snaq_ctx {
     SnaqTables T{};
     double *d_xconst = nullptr;
     size_t xconst_cap = 0;
-    uint32_t *d_off = nullptr;
+    uint32_t *d_off = nullptr;            // [nq+1] program offsets in 4-word chunks, class-sorted order
     uint16_t *d_prog = nullptr;
     size_t prog_cap = 0;
     uint64_t prog_words = 0;
-    uint32_t maxlen = 0;
+    uint32_t maxlen = 0;                  // longest program, in chunks
     double *d_W = nullptr;
+    uint32_t *d_perm = nullptr;           // [nq] sorted position -> original quartet
+    uint8_t *d_qhdr = nullptr;            // [nq] header bytes, sorted order
+    uint32_t *d_len4 = nullptr, *d_iota = nullptr;   // [nq] scratch of the build
+    uint8_t *d_cls = nullptr, *d_cls_sorted = nullptr;
+    int64_t nA = 0, nB = 0, nC = 0;
     uint32_t *d_status = nullptr;          // [0] build, [1] eval
-    unsigned long long *d_total = nullptr; // [0] words, then u32 maxlen at [1]
+    unsigned long long *d_total = nullptr; // build statistics: total chunks, max chunks, class counts
     void *d_scan_tmp = nullptr;
     size_t scan_tmp_cap = 0;
     // scratch
@@ -409,7 +528,7 @@ static int status_to_error(snaq_ctx *ctx, uint32_t st) {
 static int run_weights(snaq_ctx *ctx) {
     if (!ctx->has_net || ctx->nq == 0) return SNAQ_OK;
     int64_t nb = (ctx->nq + 255) / 256;
-    k_weights<<<(unsigned)nb, 256, 0, ctx->stream>>>(ctx->d_off, ctx->d_prog, ctx->d_obs, ctx->has_sampled ? ctx->d_sampled : nullptr, ctx->nq, ctx->d_W);
+    k_weights<<<(unsigned)nb, 256, 0, ctx->stream>>>(ctx->d_perm, ctx->d_qhdr, ctx->d_obs, ctx->has_sampled ? ctx->d_sampled : nullptr, ctx->nq, ctx->d_W);
     CK(cudaGetLastError());
     ctx->counters[5]++;
     return SNAQ_OK;
@@ -424,31 +543,34 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
     const bool per_quartet = expcf || logpl || deltacf;
     if (P >= LANES_MIN_P && !per_quartet) {
         const int ngroups = (P + 31) / 32, Ppad = ngroups * 32;
-        // chunk: quartets per block.  Enough blocks to fill the machine (>= 4 per SM overall),
-        // bounded by shared memory.
-        const size_t xs_bytes = (size_t)H.n_xe * 32 * 8;
-        int warps = xs_bytes > 40 * 1024 ? 16 : 8;
+        // chunk: quartets per block.  Enough blocks to fill the machine, bounded by shared memory.
+        const size_t xs_bytes = (size_t)(H.n_xe + 1) * 32 * 8;
+        const int warps = xs_bytes > 40 * 1024 ? 16 : 8;
         int chunk = 512;
         while (chunk > 64 && (int64_t)ngroups * ((nq + chunk - 1) / chunk) < (int64_t)ctx->sm_count * 8) chunk >>= 1;
         auto smem_for = [&](int ch) {
-            return xs_bytes + (size_t)warps * 32 * 8 + (size_t)ch * 32 + (size_t)(ch + 1) * 4 + (size_t)ch * ctx->maxlen * 2 + 16;
+            return xs_bytes + (size_t)warps * 32 * 8 + MATH_TAB_DOUBLES * 8 + (size_t)ch * 32 + (size_t)(ch + 1) * 4 + 8 +
+                   (size_t)ch * ctx->maxlen * 8 + 16;
         };
         while (chunk > 32 && smem_for(chunk) > 200 * 1024) chunk >>= 1;
         const size_t smem = smem_for(chunk);
         if (smem > 227 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_lanes"; return SNAQ_EINVAL; }
-        const int64_t nchunks = (nq + chunk - 1) / chunk;
+        ClassRanges cr;
+        cr.nA = ctx->nA; cr.nB = ctx->nB; cr.nC = ctx->nC;
+        cr.chA = (int)((cr.nA + chunk - 1) / chunk); cr.chB = (int)((cr.nB + chunk - 1) / chunk); cr.chC = (int)((cr.nC + chunk - 1) / chunk);
+        const int64_t nchunks = (int64_t)cr.chA + cr.chB + cr.chC;
         if (nchunks > 2147483647LL || ngroups > 65535) { ctx->err = "batch too large for one launch"; return SNAQ_EINVAL; }
         int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)nchunks * Ppad);
         if (rc) return rc;
         dim3 grid((unsigned)nchunks, (unsigned)ngroups);
         if (warps == 8) {
             CK(cudaFuncSetAttribute(k_eval_lanes<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_eval_lanes<8><<<grid, 256, smem, stream>>>(ctx->d_off, ctx->d_prog, ctx->d_W, nq, chunk, dX, ctx->d_xconst, H.nparams, H.nh,
-                                                        H.nt, H.n_xe, P, ctx->d_partial, Ppad, ctx->d_status + 1);
+            k_eval_lanes<8><<<grid, 256, smem, stream>>>(ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_W, cr, chunk, dX, ctx->d_xconst,
+                                                        H.nparams, H.nh, H.nt, H.n_xe, P, ctx->d_partial, Ppad, ctx->d_status + 1);
         } else {
             CK(cudaFuncSetAttribute(k_eval_lanes<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_eval_lanes<16><<<grid, 512, smem, stream>>>(ctx->d_off, ctx->d_prog, ctx->d_W, nq, chunk, dX, ctx->d_xconst, H.nparams,
-                                                         H.nh, H.nt, H.n_xe, P, ctx->d_partial, Ppad, ctx->d_status + 1);
+            k_eval_lanes<16><<<grid, 512, smem, stream>>>(ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_W, cr, chunk, dX, ctx->d_xconst,
+                                                         H.nparams, H.nh, H.nt, H.n_xe, P, ctx->d_partial, Ppad, ctx->d_status + 1);
         }
         CK(cudaGetLastError());
         k_reduce_partials_t<<<(P + 255) / 256, 256, 0, stream>>>(ctx->d_partial, (int)nchunks, Ppad, P, dout);
@@ -464,15 +586,14 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
         const int Pc = std::min(QK_MAXP, P - p0);
         int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)nblocks * Pc);
         if (rc) return rc;
-        int maxwords = (int)std::min<uint64_t>((uint64_t)BLOCK * ctx->maxlen, 48 * 1024);
-        size_t smem = (size_t)Pc * H.n_xe * 8 + (BLOCK / 32) * 8 + (size_t)maxwords * 2 + 16;
-        if (smem > 200 * 1024) { maxwords = 0; smem = (size_t)Pc * H.n_xe * 8 + (BLOCK / 32) * 8 + 16; }
+        const size_t smem = (size_t)Pc * (H.n_xe + 1) * 8 + (BLOCK / 32) * 8 + MATH_TAB_DOUBLES * 8 + 16;
+        if (smem > 200 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_quartets"; return SNAQ_EINVAL; }
         CK(cudaFuncSetAttribute(k_eval_quartets<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const bool last = (p0 + Pc == P);
         k_eval_quartets<BLOCK><<<(unsigned)nblocks, BLOCK, smem, stream>>>(
-            ctx->d_off, ctx->d_prog, ctx->d_W, ctx->d_obs, nq, dX + (size_t)p0 * H.nparams, ctx->d_xconst, H.nparams, H.nh, H.nt,
-            H.n_xe, Pc, maxwords, ctx->d_partial, last ? expcf : nullptr, last ? logpl : nullptr, last ? deltacf : nullptr,
-            ctx->d_status + 1);
+            ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_perm, ctx->d_W, ctx->d_obs, nq, ctx->nA, dX + (size_t)p0 * H.nparams,
+            ctx->d_xconst, H.nparams, H.nh, H.nt, H.n_xe, Pc, ctx->d_partial, last ? expcf : nullptr, last ? logpl : nullptr,
+            last ? deltacf : nullptr, ctx->d_status + 1);
         CK(cudaGetLastError());
         k_reduce_partials<<<(Pc * 32 + 255) / 256, 256, 0, stream>>>(ctx->d_partial, (int)nblocks, Pc, Pc, dout + p0);
         CK(cudaGetLastError());
@@ -521,7 +642,7 @@ int snaq_create(const snaq_opts *opts, snaq_ctx **out) {
     if ((e = cudaGetDeviceProperties(&prop, ctx->device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
     ctx->sm_count = prop.multiProcessorCount;
     if ((e = cudaMalloc((void **)&ctx->d_status, 4 * sizeof(uint32_t))) != cudaSuccess) return fail(e, "cudaMalloc");
-    if ((e = cudaMalloc((void **)&ctx->d_total, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void **)&ctx->d_total, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
     cudaMemset(ctx->d_status, 0, 4 * sizeof(uint32_t));
     *out = ctx;
     return SNAQ_OK;
@@ -534,6 +655,8 @@ int snaq_destroy(snaq_ctx *ctx) {
     cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_blob); cudaFree(ctx->d_xconst);
     cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_status); cudaFree(ctx->d_total);
     cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_out); cudaFree(ctx->d_partial);
+    cudaFree(ctx->d_perm); cudaFree(ctx->d_qhdr); cudaFree(ctx->d_len4); cudaFree(ctx->d_iota); cudaFree(ctx->d_cls);
+    cudaFree(ctx->d_cls_sorted);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -557,13 +680,24 @@ int snaq_set_data(snaq_ctx *ctx, int32_t ntaxa, int64_t nq, const uint16_t *taxa
     ctx->has_net = false;
     ctx->has_sampled = false;
     cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_off); cudaFree(ctx->d_W);
+    cudaFree(ctx->d_perm); cudaFree(ctx->d_qhdr); cudaFree(ctx->d_len4); cudaFree(ctx->d_iota); cudaFree(ctx->d_cls);
+    cudaFree(ctx->d_cls_sorted);
     ctx->d_taxa = nullptr; ctx->d_obs = nullptr; ctx->d_sampled = nullptr; ctx->d_off = nullptr; ctx->d_W = nullptr;
+    ctx->d_perm = nullptr; ctx->d_qhdr = nullptr; ctx->d_len4 = nullptr; ctx->d_iota = nullptr; ctx->d_cls = nullptr;
+    ctx->d_cls_sorted = nullptr;
     const size_t n = (size_t)std::max<int64_t>(ctx->nq, 1);
     CK(cudaMalloc((void **)&ctx->d_taxa, n * 4 * sizeof(uint16_t)));
     CK(cudaMalloc((void **)&ctx->d_obs, n * 3 * sizeof(double)));
     CK(cudaMalloc((void **)&ctx->d_sampled, n));
     CK(cudaMalloc((void **)&ctx->d_off, (n + 1) * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&ctx->d_W, n * 4 * sizeof(double)));
+    CK(cudaMalloc((void **)&ctx->d_perm, n * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&ctx->d_qhdr, n));
+    CK(cudaMalloc((void **)&ctx->d_len4, n * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&ctx->d_iota, n * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&ctx->d_cls, n));
+    CK(cudaMalloc((void **)&ctx->d_cls_sorted, n));
+    if (ctx->nq >= 0xFFFFFFFFLL) { ctx->err = "more than 2^32 quartets on one GPU: shard them (world_size>1)"; return SNAQ_EINVAL; }
     if (ctx->nq > 0) {
         CK(cudaMemcpyAsync(ctx->d_taxa, taxa + 4 * ctx->q_begin, (size_t)ctx->nq * 4 * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_obs, obscf + 3 * ctx->q_begin, (size_t)ctx->nq * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -624,47 +758,58 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
     const int64_t nq = ctx->nq;
     ctx->prog_words = 0;
     ctx->maxlen = 1;
+    ctx->nA = ctx->nB = ctx->nC = 0;
     if (nq > 0) {
-        // pass 1: program lengths (kept in d_off[1..nq]), total and maximum
-        CK(cudaMemsetAsync(ctx->d_total, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        // pass 1: program length (4-word chunks) and class of every quartet, original order
+        CK(cudaMemsetAsync(ctx->d_total, 0, 8 * sizeof(unsigned long long), ctx->stream));
         CK(cudaMemsetAsync(ctx->d_status, 0, 4 * sizeof(uint32_t), ctx->stream));
-        CK(cudaMemsetAsync(ctx->d_off, 0, sizeof(uint32_t), ctx->stream));
         const int64_t nb = (nq + 127) / 128;
-        uint32_t *d_len = ctx->d_off + 1;
-        k_build_count<<<(unsigned)nb, 128, 0, ctx->stream>>>(ctx->T, ctx->d_taxa, nq, d_len, ctx->d_total,
-                                                            reinterpret_cast<uint32_t *>(ctx->d_total + 1), ctx->d_status);
+        k_build_count<<<(unsigned)nb, 128, 0, ctx->stream>>>(ctx->T, ctx->d_taxa, nq, ctx->d_len4, ctx->d_cls, ctx->d_iota,
+                                                            ctx->d_total, ctx->d_status);
         CK(cudaGetLastError());
-        unsigned long long tot[2] = {0, 0};
+        unsigned long long stt[5] = {0, 0, 0, 0, 0};
         uint32_t st[4];
-        CK(cudaMemcpyAsync(tot, ctx->d_total, sizeof(tot), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(stt, ctx->d_total, sizeof(stt), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(st, ctx->d_status, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         if (st[0]) { ctx->err = build_err_text(st[0]); return SNAQ_ETOPOLOGY; }
-        if (tot[0] >= 0xFFFFFFFFull) { ctx->err = "descriptor table exceeds 2^32 words on one GPU: shard the quartets (world_size>1)"; return SNAQ_EINVAL; }
-        ctx->prog_words = tot[0];
-        ctx->maxlen = (uint32_t)(tot[1] & 0xFFFFFFFFull);
-        // inclusive scan of the lengths in place => d_off[q+1] = end of program q
-        size_t tmp = 0;
-        CK(cub::DeviceScan::InclusiveSum(nullptr, tmp, d_len, d_len, nq, ctx->stream));
+        if (stt[0] >= 0xFFFFFFFFull) { ctx->err = "descriptor table exceeds 2^32 chunks on one GPU: shard the quartets (world_size>1)"; return SNAQ_EINVAL; }
+        ctx->prog_words = stt[0] * 4;
+        ctx->maxlen = (uint32_t)stt[1];
+        ctx->nA = (int64_t)stt[2]; ctx->nB = (int64_t)stt[3]; ctx->nC = (int64_t)stt[4];
+        // stable sort of the quartet indices by class (2-bit keys): perm = sorted position -> original quartet
+        size_t tmp = 0, tmp2 = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_cls, ctx->d_cls_sorted, ctx->d_iota, ctx->d_perm, nq, 0, 2, ctx->stream));
+        uint32_t *d_len_sorted = ctx->d_off + 1;
+        CK(cub::DeviceScan::InclusiveSum(nullptr, tmp2, d_len_sorted, d_len_sorted, nq, ctx->stream));
+        tmp = std::max(tmp, tmp2);
         if (tmp > ctx->scan_tmp_cap) {
             cudaFree(ctx->d_scan_tmp);
             ctx->d_scan_tmp = nullptr;
             CK(cudaMalloc(&ctx->d_scan_tmp, tmp));
             ctx->scan_tmp_cap = tmp;
         }
-        CK(cub::DeviceScan::InclusiveSum(ctx->d_scan_tmp, tmp, d_len, d_len, nq, ctx->stream));
+        size_t t1 = ctx->scan_tmp_cap;
+        CK(cub::DeviceRadixSort::SortPairs(ctx->d_scan_tmp, t1, ctx->d_cls, ctx->d_cls_sorted, ctx->d_iota, ctx->d_perm, nq, 0, 2, ctx->stream));
+        // lengths in sorted order, scanned in place => d_off[i+1] = end of program i (chunks)
+        CK(cudaMemsetAsync(ctx->d_off, 0, sizeof(uint32_t), ctx->stream));
+        k_gather_len<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_perm, ctx->d_len4, nq, d_len_sorted);
+        CK(cudaGetLastError());
+        t1 = ctx->scan_tmp_cap;
+        CK(cub::DeviceScan::InclusiveSum(ctx->d_scan_tmp, t1, d_len_sorted, d_len_sorted, nq, ctx->stream));
         rc = ensure(ctx, ctx->d_prog, ctx->prog_cap, (size_t)ctx->prog_words + 8);
         if (rc) return rc;
-        k_build_emit<<<(unsigned)nb, 128, 0, ctx->stream>>>(ctx->T, ctx->d_taxa, nq, ctx->d_off, ctx->d_prog, ctx->d_status);
+        k_build_emit<<<(unsigned)nb, 128, 0, ctx->stream>>>(ctx->T, ctx->d_taxa, nq, ctx->d_perm, ctx->d_off, ctx->d_prog, ctx->d_qhdr,
+                                                           ctx->d_status);
         CK(cudaGetLastError());
-        ctx->counters[5] += 3;
+        ctx->counters[5] += 5;
         ctx->has_net = true;
         rc = run_weights(ctx);
         if (rc) { ctx->has_net = false; return rc; }
         CK(cudaMemcpyAsync(st, ctx->d_status, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         if (st[0]) { ctx->has_net = false; ctx->err = build_err_text(st[0]); return SNAQ_ETOPOLOGY; }
-        ctx->counters[3] += 16 + 16 + 16;
+        ctx->counters[3] += 40 + 16 + 16;
     }
     ctx->counters[4] = (int64_t)ctx->prog_words;
     ctx->has_net = true;

@@ -1,9 +1,9 @@
 /*
  * hostsim.cpp — TEST HARNESS ONLY.  Compiles the engine's device functions
  * (snaq.jl_b200/csrc/snaq_core.h) and its host table builder for the CPU so that the
- * structural descriptor build can be fuzzed against the oracle in the CPU-only test
- * tier.  It is not linked into, nor reachable from, the shipped library: the product
- * has no CPU path.
+ * structural descriptor build and the specialised exp/log can be fuzzed against the oracle
+ * in the CPU-only test tier.  It is not linked into, nor reachable from, the shipped
+ * library: the product has no CPU path.
  */
 #include <cstring>
 #include <string>
@@ -12,14 +12,24 @@
 #include "../../snaq.jl_b200/csrc/snaq_tables.h"
 
 static thread_local std::string g_err;
+static const double g_et[SNAQ_EXP_TAB_N] = SNAQ_EXP_TAB_INIT;
+static const double g_lt[SNAQ_LOG_TAB_N * 2] = SNAQ_LOG_TAB_INIT;
 
 struct XRow {
-    const double *x; const double *xc; int np;
-    double operator()(unsigned s) const { return (int)s < np ? x[s] : xc[s - np]; }
+    const double *x; const double *xc; int np, nxe;
+    double operator()(unsigned s) const { return (int)s < np ? x[s] : ((int)s < nxe ? xc[s - np] : 0.0); }
 };
 
 extern "C" {
 const char *hostsim_last_error() { return g_err.c_str(); }
+
+void hostsim_math(int n, const double *u, double *e, double *l) {
+    SnaqMath M{g_et, g_lt};
+    for (int i = 0; i < n; i++) {
+        if (e) e[i] = snaq_exp(u[i], M);
+        if (l) l[i] = snaq_log(u[i], M);
+    }
+}
 
 int hostsim_params(const snaq_flatnet *f, int ntaxa, int32_t *nparams, int32_t *n_xe, double *x0, int32_t *numht) {
     SnaqHostTables H;
@@ -39,16 +49,21 @@ int hostsim_run(const snaq_flatnet *f, int ntaxa, int64_t nq, const uint16_t *ta
     int rc = snaq_build_tables(f, ntaxa, H, g_err);
     if (rc) return rc;
     SnaqTables T = H.view(H.blob.data());
+    SnaqMath M{g_et, g_lt};
     std::vector<std::vector<uint16_t>> progs(nq);
+    std::vector<uint8_t> hdrs(nq);
     for (int64_t q = 0; q < nq; q++) {
         SnaqWriter w{nullptr, 0, 0};
         SnaqQuartetInfo info;
-        int e = snaq_build_quartet(T, taxa + 4 * q, w, &info);
+        uint8_t h1 = 0, h2 = 0;
+        int e = snaq_build_quartet(T, taxa + 4 * q, w, &h1, &info);
         if (e) { g_err = "build error " + std::to_string(e) + " at quartet " + std::to_string(q); return SNAQ_ETOPOLOGY; }
-        progs[q].assign(w.n, 0);
+        const int padded = (w.n + 3) & ~3;
+        progs[q].assign(padded, (uint16_t)H.n_xe);      // NULL-slot padding
         SnaqWriter w2{progs[q].data(), 0, w.n};
-        snaq_build_quartet(T, taxa + 4 * q, w2, nullptr);
-        if (w2.n != w.n) { g_err = "count/emit mismatch"; return SNAQ_EINVAL; }
+        snaq_build_quartet(T, taxa + 4 * q, w2, &h2, nullptr);
+        if (w2.n != w.n || h1 != h2) { g_err = "count/emit mismatch"; return SNAQ_EINVAL; }
+        hdrs[q] = h1;
         if (proglen) proglen[q] = w.n;
         if (which) which[q] = info.which;
         if (formula) for (int i = 0; i < 3; i++) formula[3 * q + i] = info.formula[i];
@@ -56,14 +71,14 @@ int hostsim_run(const snaq_flatnet *f, int ntaxa, int64_t nq, const uint16_t *ta
     }
     unsigned status = 0;
     for (int p = 0; p < P; p++) {
-        XRow xr{X + (size_t)p * H.nparams, H.xconst.data(), H.nparams};
+        XRow xr{X + (size_t)p * H.nparams, H.xconst.data(), H.nparams, H.n_xe};
         double total = 0;
         for (int64_t q = 0; q < nq; q++) {
             double cf[3], t1, W[4];
-            unsigned kind = snaq_eval_program(progs[q].data(), xr, cf, &t1, status);
-            snaq_weights(progs[q][0], obs + 3 * q, sampled ? sampled[q] : 1, W);
-            total += snaq_quartet_loglik(kind, cf, t1, W, status);
-            if (expcf_last && p == P - 1) snaq_data_order(progs[q][0], cf, expcf_last + 3 * q);
+            snaq_eval_quartet(hdrs[q], progs[q].data(), (int)progs[q].size(), xr, M, cf, &t1, status);
+            snaq_weights(hdrs[q], obs + 3 * q, sampled ? sampled[q] : 1, W);
+            total += snaq_quartet_loglik(SNAQ_HDR_KIND(hdrs[q]), cf, t1, W, M, status);
+            if (expcf_last && p == P - 1) snaq_data_order(hdrs[q], cf, expcf_last + 3 * q);
         }
         out_lik[p] = -total;
     }
