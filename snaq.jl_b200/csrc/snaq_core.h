@@ -18,7 +18,12 @@
  * paths determines the reference's case.  The result is a short
  * program of u16 words over the slots of the extended parameter vector
  *   xe = [ x (gamma | t | gammaz, parameters!(net)) | constants ]
- * that the evaluation kernels interpret for every candidate x.
+ * that the evaluation kernels interpret for every candidate x.  Before a batch is evaluated, x is
+ * expanded once per candidate (snaq_expand_x) into
+ *   xf = [ xe | 0.0 (NULL slot) | D[v] for internal blob-tree nodes | per-cycle rows ]
+ * where D[v] is the sum of the edge slots on the path from v to the root, so that the tree part
+ * of an internal path J1..J2 is (D[J1] - D[apex]) + (D[J2] - D[apex]); the per-cycle rows are the
+ * prefix sums C_j of the cycle's edge lengths plus the quartet-independent type-3 / gammaz terms.
  *
  * Everything here is `SNAQ_HD` so that tests/hostsim can run the exact same code
  * on the CPU against the oracle; the shipped library only runs it on the GPU.
@@ -35,7 +40,11 @@
 #if defined(__CUDACC__)
 #define SNAQ_HD __host__ __device__ __forceinline__
 #define SNAQ_HD_NOINLINE __host__ __device__ __noinline__
+#if defined(__CUDA_ARCH__)
 #define SNAQ_UNROLL1 _Pragma("unroll 1")
+#else
+#define SNAQ_UNROLL1
+#endif
 #else
 #define SNAQ_HD inline
 #define SNAQ_HD_NOINLINE inline
@@ -49,11 +58,16 @@
 /*
  * Quartet programs.  Every quartet has one header BYTE (kept in a separate array, only the
  * weight / read-back kernels need it) and a program of u16 words, padded with the NULL slot
- * (index n_xe, value 0.0) to a multiple of 4 words so that programs are 8-byte aligned:
+ * (index n_xe, value 0.0) to a multiple of 4 words so that programs are 8-byte aligned.
+ * Sums are lists of signed PAIRS (p, n) meaning xf[p] - xf[n]: a path of blob-tree edges is
+ * (D[J], D[apex]), an arc of an open cycle is (C_hi, C_lo), a single row r is (r, NULL).
  *
- *   class A  tree-like, no cycle term : [slot]*            t1 = min(10, sum xe[slot])  (NULL pads add 0)
- *   class B  tree-like with terms     : [n0 | nterms<<8] [slot]*n0 [term]*nterms
- *   class C  4-cycle (which==2)       : T5   : [gslot] [n5 | n6<<8] [slot]*n5 [slot]*n6
+ *   class A  tree-like, additive      : [p n]*             t1 = min(10, sum xf[p] - xf[n])
+ *            (path edges as prefix-sum rows, open cycle arcs as C rows, type-3 and gammaz terms as rows)
+ *   class B  tree-like, type 2/4 terms: [npairs | nterms<<8] [p n]*npairs [term]*nterms
+ *            T2 term: [T2|flag|gslot] [C_hi] [C_lo]
+ *            T4 term: [T4|far|gslot]  [C_lo] [C_hi] [C_k] [nchainpairs] [p n]*nchainpairs
+ *   class C  4-cycle (which==2)       : T5   : [gslot] [C_a] [C_m] [C_b]
  *                                       T5BD1: [zslot1] [zslot2]
  * The device table is sorted by class so that a warp / block only ever runs one of the loops.
  */
@@ -90,6 +104,7 @@
 
 typedef struct SnaqTables {
     int32_t ntaxa, n_tnodes, n_cycles, nparams, n_xe, n_hybrids;
+    int32_t n_int, n_full;       /* internal blob-tree nodes; rows of the expanded vector      */
     /* blob tree T': cycles contracted to supernodes, rooted arbitrarily */
     const uint16_t *leaf_tnode;  /* [ntaxa]     T' node of each taxon (0xFFFF: taxon not in net) */
     const uint16_t *parent;      /* [n_tnodes]  parent (root: itself)                     */
@@ -97,6 +112,9 @@ typedef struct SnaqTables {
     const int16_t  *tcycle;      /* [n_tnodes]  cycle index of a supernode, else -1       */
     const uint16_t *pslot;       /* [n_tnodes]  xe slot of the edge to the parent         */
     const uint16_t *torder;      /* [n_tnodes]  position of a tree node in net.node       */
+    const uint16_t *dnode;       /* [n_int]     blob-tree node of the k-th D row           */
+    const uint16_t *dslot;       /* [n_tnodes]  slot of D[v] (root-path prefix sum of the edge
+                                    slots above v) for internal nodes; 0xFFFF for leaves     */
     /* cycles: position 0 = hybrid node, 1 = its major parent, ..., k-1 = minor parent.
      * edge j joins positions j and (j+1)%k: j=0 major hybrid edge, j=k-1 minor one.      */
     const uint8_t  *blk;         /* [n_cycles*ntaxa] position whose block holds the taxon */
@@ -109,7 +127,16 @@ typedef struct SnaqTables {
     const uint8_t  *cyc_hyb;     /* [n_cycles]  index of the hybrid in net.hybrid order   */
     const uint16_t *cyc_order;   /* per cycle position (same offsets as cyc_slot): position of
                                     that cycle node in net.node                            */
+    /* rows of the expanded vector that belong to a cycle with k nodes (see snaq_expand_row):
+     *   crow[c] + j          j=0..k   C_j  = sum of the lengths of cycle edges 0..j-1
+     *   crow[c] + k+1 + o-1  o=1..k-1 type-3 term when the hit node is at position o
+     *   crow[c] + 2k + i     i=0,1    -log(1-gammaz_i) capped at 10 (bad diamond I only)          */
+    const uint16_t *crow;        /* [n_cycles] */
 } SnaqTables;
+#define SNAQ_CROW(T, c, j)   ((unsigned)(T).crow[c] + (unsigned)(j))
+#define SNAQ_T3ROW(T, c, o)  ((unsigned)(T).crow[c] + (unsigned)(T).cyc_k[c] + (unsigned)(o))
+#define SNAQ_TZROW(T, c, i)  ((unsigned)(T).crow[c] + 2u * (unsigned)(T).cyc_k[c] + (unsigned)(i))
+#define SNAQ_CYC_ROWS(k)     (2 * (k) + 2)
 
 /* parity descriptor of one quartet */
 typedef struct SnaqQuartetInfo {
@@ -136,10 +163,15 @@ SNAQ_HD int snaq_lca(const SnaqTables &T, int u, int v) {
 }
 
 /* emit the slots of cycle edges j = lo .. hi-1 (the arc between positions lo and hi) */
+SNAQ_HD int snaq_put_pair(SnaqWriter &w, unsigned plus, unsigned minus) {
+    snaq_put(w, plus);
+    snaq_put(w, minus);
+    return 1;
+}
+/* the arc between cycle positions lo and hi as the pair (C_hi, C_lo); returns the number of pairs */
 SNAQ_HD int snaq_put_arc(const SnaqTables &T, int c, int lo, int hi, SnaqWriter &w) {
-    const uint16_t *s = T.cyc_slot + T.cyc_off[c];
-    for (int j = lo; j < hi; j++) snaq_put(w, s[j]);
-    return hi - lo;
+    if (hi <= lo) return 0;
+    return snaq_put_pair(w, SNAQ_CROW(T, c, hi), SNAQ_CROW(T, c, lo));
 }
 
 SNAQ_HD int snaq_deeper(const SnaqTables &T, int a, int b) { return T.depth[a] >= T.depth[b] ? a : b; }
@@ -282,9 +314,9 @@ SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWr
             } else {
                 int a = pos[o[1]], m = pos[o[2]], b = pos[o[3]];
                 snaq_put(w, g);
-                snaq_put(w, (unsigned)(m - a) | ((unsigned)(b - m) << 8));
-                snaq_put_arc(T, c, a, m, w);
-                snaq_put_arc(T, c, m, b, w);
+                snaq_put(w, SNAQ_CROW(T, c, a));     /* y5 = exp(-(C_m - C_a)), y6 = exp(-(C_b - C_m)) */
+                snaq_put(w, SNAQ_CROW(T, c, m));
+                snaq_put(w, SNAQ_CROW(T, c, b));
                 *hdr = SNAQ_QHDR(SNAQ_KIND_T5, pidx, 0);
             }
             return SNAQ_B_OK;
@@ -395,117 +427,95 @@ SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWr
         }
     }
     /* owner of a path element: 0 main list, 1 chain of the term at J1, 2 chain of the term at J2.
-     * element kinds: edge i (between seq[i] and seq[i+1]); arc of interior node i; end arcs. */
-    /* number of cycle terms: decides between class A (bare slot list) and class B (count word first) */
-    int nterms_pre = (c1 >= 0 && e1.cls != SNAQ_C_OPEN) + (c2 >= 0 && e2.cls != SNAQ_C_OPEN);
-    for (int i = 1; i < ns - 1; i++) {
+     * element kinds: edge i (between seq[i] and seq[i+1]); arc of interior node i; end arcs.
+     * Terms evaluated on the fly (class B): type 2 and type 4.  Type 3 and gammaz terms are rows. */
+    int nfly_pre = (c1 >= 0 && (e1.cls == SNAQ_C_T2 || e1.cls == SNAQ_C_T4)) + (c2 >= 0 && (e2.cls == SNAQ_C_T2 || e2.cls == SNAQ_C_T4));
+    const int cnt_word_at = w.n;
+    if (nfly_pre > 0) snaq_put(w, 0);
+    int n0 = 0, nterms = 0;
+    /* additive part */
+    const unsigned NUL = (unsigned)T.n_xe;
+    if (!t4a && !t4b) {
+        /* all blob-tree edges of the path at once, as prefix sums: (D[J1] - D[apex]) + (D[J2] - D[apex]) */
+        if (J1 != apex) n0 += snaq_put_pair(w, T.dslot[J1], T.dslot[apex]);
+        if (J2 != apex) n0 += snaq_put_pair(w, T.dslot[J2], T.dslot[apex]);
+    }
+    for (int i = 0; i < ns; i++) {
+        if (i < ns - 1 && (t4a || t4b)) {
+            int owner = (t4a && i <= ja) ? 1 : ((t4b && i >= jb) ? 2 : 0);
+            if (owner == 0) n0 += snaq_put_pair(w, i < iapex ? T.pslot[seq[i]] : T.pslot[seq[i + 1]], NUL);
+        }
         int c = T.tcycle[seq[i]];
         if (c < 0) continue;
-        snaq_positions(T, c, tx, pos);
-        SnaqCyc m = snaq_classify_cycle(T, c, pos, p, q, r, s, 0);
-        if (m.cls < 0) return SNAQ_B_BLOCKS;
-        nterms_pre += (m.cls != SNAQ_C_OPEN);
-    }
-    const int cnt_word_at = w.n;
-    if (nterms_pre > 0) snaq_put(w, 0);
-    int n0 = 0, nterms = 0;
-    for (int pass = 0; pass < 3; pass++) {
-        /* pass 0: main list; pass 1: the terms (with the chain of the J1-side type 4 inside);
-         * chains are emitted by the inner `want` loops */
-        if (pass == 2) break;
-        if (pass == 0) {
-            for (int want = 0; want < 1; want++) {
-                for (int i = 0; i < ns; i++) {
-                    if (i < ns - 1) {
-                        int owner = (t4a && i <= ja) ? 1 : ((t4b && i >= jb) ? 2 : 0);
-                        if (owner == 0) { snaq_put(w, i < iapex ? T.pslot[seq[i]] : T.pslot[seq[i + 1]]); n0++; }
-                    }
-                    int c = T.tcycle[seq[i]];
-                    if (c < 0) continue;
-                    if (i == 0) {
-                        if (e1.cls == SNAQ_C_OPEN && !(t4b && bArc)) n0 += snaq_put_arc(T, c, e1.lo, e1.hi, w);
-                    } else if (i == ns - 1) {
-                        if (e2.cls == SNAQ_C_OPEN && !(t4a && aArc)) n0 += snaq_put_arc(T, c, e2.lo, e2.hi, w);
-                    } else {
-                        snaq_positions(T, c, tx, pos);
-                        SnaqCyc m = snaq_classify_cycle(T, c, pos, p, q, r, s, 0);
-                        if (m.cls < 0) return SNAQ_B_BLOCKS;
-                        int owner = (t4a && i <= ja) ? 1 : ((t4b && i >= jb + 1) ? 2 : 0);
-                        if (m.cls == SNAQ_C_OPEN && owner == 0) n0 += snaq_put_arc(T, c, m.lo, m.hi, w);
-                    }
-                }
-            }
-            continue;
+        SnaqCyc m;
+        int owner = 0;
+        if (i == 0) { m = e1; owner = (t4b && bArc) ? 2 : 0; }
+        else if (i == ns - 1) { m = e2; owner = (t4a && aArc) ? 1 : 0; }
+        else {
+            snaq_positions(T, c, tx, pos);
+            m = snaq_classify_cycle(T, c, pos, p, q, r, s, 0);
+            if (m.cls < 0) return SNAQ_B_BLOCKS;
+            owner = (t4a && i <= ja) ? 1 : ((t4b && i >= jb + 1) ? 2 : 0);
         }
-        /* pass 1: terms, in path order */
-        for (int i = 0; i < ns; i++) {
-            int c = T.tcycle[seq[i]];
-            if (c < 0) continue;
-            SnaqCyc m;
-            if (i == 0) m = e1;
-            else if (i == ns - 1) m = e2;
-            else {
-                snaq_positions(T, c, tx, pos);
-                m = snaq_classify_cycle(T, c, pos, p, q, r, s, 0);
-            }
-            if (m.cls == SNAQ_C_OPEN) continue;
-            const int k = T.cyc_k[c];
-            const int g = T.cyc_gslot[c];
-            nterms++;
-            if (m.cls == SNAQ_C_T3) {
-                snaq_put(w, SNAQ_TERM(SNAQ_T3, 0, g));
-                snaq_put(w, (unsigned)m.lo | ((unsigned)(k - m.lo) << 8));
-                snaq_put_arc(T, c, 0, m.lo, w);        /* major hybrid edge + tree edges up to the hit node */
-                snaq_put_arc(T, c, m.lo, k, w);        /* tree edges from it + minor hybrid edge            */
-                if (info) info->type[T.cyc_hyb[c]] = 3;
-            } else if (m.cls == SNAQ_C_T2) {
-                /* gamma of the hybrid edge that lands on `other`: major iff `other` comes first */
-                snaq_put(w, SNAQ_TERM(SNAQ_T2, m.other == m.lo ? 1 : 0, g));
-                snaq_put(w, (unsigned)(m.hi - m.lo));
-                snaq_put_arc(T, c, m.lo, m.hi, w);
-                if (info) info->type[T.cyc_hyb[c]] = 2;
-            } else if (m.cls == SNAQ_C_TZ) {
-                snaq_put(w, SNAQ_TERM(SNAQ_TZ, 0, m.other == 1 ? g : g + 1));
-            } else {                                   /* type 4 */
-                const int isA = (i == 0);
-                const int far = isA ? !nearA : nearA;
-                snaq_put(w, SNAQ_TERM(SNAQ_T4, far, g));
-                snaq_put(w, (unsigned)m.lo | ((unsigned)(k - m.hi) << 8));
-                snaq_put(w, (unsigned)(m.hi - m.lo));
-                const int cnt_at = w.n;
-                snaq_put(w, 0);
-                snaq_put_arc(T, c, 0, m.lo, w);        /* major side: hybrid edge .. first hit node */
-                snaq_put_arc(T, c, m.hi, k, w);        /* minor side                                */
-                snaq_put_arc(T, c, m.lo, m.hi, w);     /* between the two hit nodes                 */
-                /* the chain below the hybrid node that the reference merges with this term first */
-                int nchain = 0;
-                const int me = isA ? 1 : 2;
-                for (int j = 0; j < ns; j++) {
-                    if (j < ns - 1) {
-                        int owner = (t4a && j <= ja) ? 1 : ((t4b && j >= jb) ? 2 : 0);
-                        if (owner == me) { snaq_put(w, j < iapex ? T.pslot[seq[j]] : T.pslot[seq[j + 1]]); nchain++; }
-                    }
-                    int cc = T.tcycle[seq[j]];
-                    if (cc < 0) continue;
-                    if (j == 0) {
-                        if (e1.cls == SNAQ_C_OPEN && me == 2 && bArc) nchain += snaq_put_arc(T, cc, e1.lo, e1.hi, w);
-                    } else if (j == ns - 1) {
-                        if (e2.cls == SNAQ_C_OPEN && me == 1 && aArc) nchain += snaq_put_arc(T, cc, e2.lo, e2.hi, w);
-                    } else {
-                        int owner = (t4a && j <= ja) ? 1 : ((t4b && j >= jb + 1) ? 2 : 0);
-                        if (owner != me) continue;
-                        snaq_positions(T, cc, tx, pos);
-                        SnaqCyc mm = snaq_classify_cycle(T, cc, pos, p, q, r, s, 0);
-                        if (mm.cls == SNAQ_C_OPEN) nchain += snaq_put_arc(T, cc, mm.lo, mm.hi, w);
-                    }
-                }
-                if (nchain > 65535) return SNAQ_B_OVERFLOW;
-                if (w.out && cnt_at < w.cap) w.out[cnt_at] = (uint16_t)nchain;
-                if (info) info->type[T.cyc_hyb[c]] = 4;
-            }
+        if (m.cls == SNAQ_C_OPEN) {
+            if (owner == 0) n0 += snaq_put_arc(T, c, m.lo, m.hi, w);
+        } else if (m.cls == SNAQ_C_T3) {
+            n0 += snaq_put_pair(w, SNAQ_T3ROW(T, c, m.lo), NUL);
+            if (info) info->type[T.cyc_hyb[c]] = 3;
+        } else if (m.cls == SNAQ_C_TZ) {
+            n0 += snaq_put_pair(w, SNAQ_TZROW(T, c, m.other == 1 ? 0 : 1), NUL);
         }
     }
-    if (n0 > 255 || nterms > 255 || nterms != nterms_pre) return SNAQ_B_OVERFLOW;
+    /* on-the-fly terms, in path order */
+    for (int i = 0; i < ns; i += (ns > 1 ? ns - 1 : 1)) {
+        int c = T.tcycle[seq[i]];
+        if (c < 0) continue;
+        const SnaqCyc m = (i == 0) ? e1 : e2;
+        if (m.cls != SNAQ_C_T2 && m.cls != SNAQ_C_T4) continue;
+        const int k = T.cyc_k[c];
+        const int g = T.cyc_gslot[c];
+        nterms++;
+        if (m.cls == SNAQ_C_T2) {
+            /* gamma of the hybrid edge that lands on `other`: major iff `other` comes first */
+            snaq_put(w, SNAQ_TERM(SNAQ_T2, m.other == m.lo ? 1 : 0, g));
+            snaq_put(w, SNAQ_CROW(T, c, m.hi)); snaq_put(w, SNAQ_CROW(T, c, m.lo));
+            if (info) info->type[T.cyc_hyb[c]] = 2;
+        } else {                                   /* type 4 */
+            const int isA = (i == 0);
+            const int far = isA ? !nearA : nearA;
+            snaq_put(w, SNAQ_TERM(SNAQ_T4, far, g));
+            /* major side = C_lo (edges 0..lo-1), between the hit nodes = C_hi - C_lo, minor side = C_k - C_hi */
+            snaq_put(w, SNAQ_CROW(T, c, m.lo)); snaq_put(w, SNAQ_CROW(T, c, m.hi)); snaq_put(w, SNAQ_CROW(T, c, k));
+            const int cnt_at = w.n;
+            snaq_put(w, 0);
+            /* the chain below the hybrid node that the reference merges with this term first */
+            int nchain = 0;
+            const int me = isA ? 1 : 2;
+            for (int j = 0; j < ns; j++) {
+                if (j < ns - 1) {
+                    int owner = (t4a && j <= ja) ? 1 : ((t4b && j >= jb) ? 2 : 0);
+                    if (owner == me) nchain += snaq_put_pair(w, j < iapex ? T.pslot[seq[j]] : T.pslot[seq[j + 1]], NUL);
+                }
+                int cc = T.tcycle[seq[j]];
+                if (cc < 0) continue;
+                if (j == 0) {
+                    if (e1.cls == SNAQ_C_OPEN && me == 2 && bArc) nchain += snaq_put_arc(T, cc, e1.lo, e1.hi, w);
+                } else if (j == ns - 1) {
+                    if (e2.cls == SNAQ_C_OPEN && me == 1 && aArc) nchain += snaq_put_arc(T, cc, e2.lo, e2.hi, w);
+                } else {
+                    int owner = (t4a && j <= ja) ? 1 : ((t4b && j >= jb + 1) ? 2 : 0);
+                    if (owner != me) continue;
+                    snaq_positions(T, cc, tx, pos);
+                    SnaqCyc mm = snaq_classify_cycle(T, cc, pos, p, q, r, s, 0);
+                    if (mm.cls == SNAQ_C_OPEN) nchain += snaq_put_arc(T, cc, mm.lo, mm.hi, w);
+                }
+            }
+            if (nchain > 65535) return SNAQ_B_OVERFLOW;
+            if (w.out && cnt_at < w.cap) w.out[cnt_at] = (uint16_t)nchain;
+            if (info) info->type[T.cyc_hyb[c]] = 4;
+        }
+    }
+    if (n0 > 255 || nterms > 255 || nterms != nfly_pre) return SNAQ_B_OVERFLOW;
     if (info) info->formula[maj] = 1;
     if (nterms > 0 && w.out && cnt_word_at < w.cap) w.out[cnt_word_at] = (uint16_t)(n0 | (nterms << 8));
     *hdr = SNAQ_QHDR(SNAQ_KIND_TREE, maj, nterms > 0 ? 1 : 0);
@@ -517,10 +527,30 @@ SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWr
  * generic library versions; <= 2e-16 relative error for exp on [-12,1], <= 2e-16 absolute or
  * relative error, whichever is larger, for log on normal positive arguments).
  * ------------------------------------------------------------------------------ */
+/* polynomial coefficients and other FP64 constants: on the device they live in __constant__ memory */
+#define SNAQ_KC_INIT { SNAQ_16_LN2, -SNAQ_LN2_16_HI, -SNAQ_LN2_16_LO, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, \
+                       1.0 / 6.0, SNAQ_LN2, SNAQ_LOG3, -2.0 / 3.0, 6755399441055744.0,                                   \
+                       -0.1, 1.0 / 9.0, -0.125, 1.0 / 7.0, -1.0 / 6.0, 0.2, -0.25, 1.0 / 3.0 }
+#define SNAQ_KC_N 20
+#if defined(__CUDACC__)
+__constant__ double snaq_kc_dev[SNAQ_KC_N] = SNAQ_KC_INIT;
+#endif
+static const double snaq_kc_host[SNAQ_KC_N] = SNAQ_KC_INIT;
+#if defined(__CUDA_ARCH__)
+#define SNAQ_KC(i) snaq_kc_dev[i]
+#else
+#define SNAQ_KC(i) snaq_kc_host[i]
+#endif
+#define SNAQ_K_LN2   SNAQ_KC(8)
+#define SNAQ_K_LOG3  SNAQ_KC(9)
+#define SNAQ_K_M23   SNAQ_KC(10)
+
 typedef struct SnaqMath {
-    const double *et;   /* [64]    2^(j/64)                                  */
-    const double *lt;   /* [128*2] 1/c_j, -log(1/c_j), c_j = 1+(j+.5)/128    */
+    const double *et;   /* [16] 2^(j/16)                                  */
+    const double *li;   /* [16] 1/c_j,        c_j = 1+(j+.5)/16           */
+    const double *lc;   /* [16] -log(1/c_j)                               */
 } SnaqMath;
+#define SNAQ_MATH_DOUBLES 48   /* the three tables, contiguous, 128-byte aligned */
 
 #if defined(__CUDA_ARCH__)
 SNAQ_HD int snaq_hi(double v) { return __double2hiint(v); }
@@ -532,65 +562,123 @@ SNAQ_HD int snaq_lo(double v) { int64_t b; memcpy(&b, &v, 8); return (int)(b & 0
 SNAQ_HD double snaq_mk(int hi, int lo) { int64_t b = ((int64_t)hi << 32) | (uint32_t)lo; double v; memcpy(&v, &b, 8); return v; }
 #endif
 
-/* exp(u) for u in [-12, 1]: u = k*ln2/64 + r, exp(u) = 2^(k>>6) * 2^((k&63)/64) * exp(r), |r| <= ln2/128 */
+/* exp(u) for u in [-12, 1]: u = k*ln2/16 + r, exp(u) = 2^(k>>4) * 2^((k&15)/16) * exp(r), |r| <= ln2/32 */
 SNAQ_HD double snaq_exp(double u, const SnaqMath &M) {
-    const double magic = 6755399441055744.0;                 /* 1.5 * 2^52 */
-    const double kd = fma(u, SNAQ_64_LN2, magic);
+    const double magic = SNAQ_KC(11);                        /* 1.5 * 2^52 */
+    const double kd = fma(u, SNAQ_KC(0), magic);
     const int k = snaq_lo(kd);
     const double kf = kd - magic;
-    double r = fma(kf, -SNAQ_LN2_64_HI, u);
-    r = fma(kf, -SNAQ_LN2_64_LO, r);
-    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    q = fma(r, q, 1.0 / 6.0);
+    double r = fma(kf, SNAQ_KC(1), u);
+    r = fma(kf, SNAQ_KC(2), r);
+    double q = fma(r, SNAQ_KC(3), SNAQ_KC(4));
+    q = fma(r, q, SNAQ_KC(5));
+    q = fma(r, q, SNAQ_KC(6));
+    q = fma(r, q, SNAQ_KC(7));
     q = fma(r, q, 0.5);
     q = fma(r, q, 1.0);
-    const double tj = M.et[k & 63];
+    const double tj = M.et[k & 15];
     const double v = fma(tj, r * q, tj);
-    return snaq_mk(snaq_hi(v) + ((k >> 6) << 20), snaq_lo(v));
+    return snaq_mk(snaq_hi(v) + ((k >> 4) << 20), snaq_lo(v));
 }
 
 /* rare arguments (0, negative, denormal, inf, nan): the library version, kept out of line */
 static SNAQ_HD_NOINLINE double snaq_log_slow(double z) { return log(z); }
 
-/* log(z): z = 2^e m, m in [1,2); r = m/c_j - 1 with |r| <= 2^-8; log z = e ln2 - log(1/c_j) + log1p(r) */
-SNAQ_HD double snaq_log(double z, const SnaqMath &M) {
-    if (!(z >= 2.2250738585072014e-308 && z <= 1.7976931348623157e308)) return snaq_log_slow(z);
+/* log(z): z = 2^e m, m in [1,2); r = m/c_j - 1 with |r| <= 2^-5; log z = e ln2 - log(1/c_j) + log1p(r).
+ * snaq_log_pos: z must be a normal positive number (e.g. the major CF of a tree-like quartet, in [1/3,1]) */
+SNAQ_HD double snaq_log_pos(double z, const SnaqMath &M) {
     const int hi = snaq_hi(z);
     const int e = (hi >> 20) - 1023;
-    const int j = (hi >> 13) & 127;
+    const int j = (hi >> 16) & 15;
     const double m = snaq_mk((hi & 0x000FFFFF) | 0x3FF00000, snaq_lo(z));
-    const double inv = M.lt[2 * j], lc = M.lt[2 * j + 1];
-    const double r = fma(m, inv, -1.0);
-    double q = fma(r, -1.0 / 6.0, 0.2);
-    q = fma(r, q, -0.25);
-    q = fma(r, q, 1.0 / 3.0);
+    const double r = fma(m, M.li[j], -1.0);                  /* |r| <= 1/32 */
+    double q = fma(r, SNAQ_KC(12), SNAQ_KC(13));             /* log1p(r) = r - r^2/2 + ... - r^10/10 */
+    q = fma(r, q, SNAQ_KC(14));
+    q = fma(r, q, SNAQ_KC(15));
+    q = fma(r, q, SNAQ_KC(16));
+    q = fma(r, q, SNAQ_KC(17));
+    q = fma(r, q, SNAQ_KC(18));
+    q = fma(r, q, SNAQ_KC(19));
     q = fma(r, q, -0.5);
     const double p = fma(r * r, q, r);
-    return fma((double)e, SNAQ_LN2, lc + p);
+    return fma((double)e, SNAQ_K_LN2, M.lc[j] + p);
+}
+SNAQ_HD double snaq_log(double z, const SnaqMath &M) {
+    if (!(z >= 2.2250738585072014e-308 && z <= 1.7976931348623157e308)) return snaq_log_slow(z);
+    return snaq_log_pos(z, M);
+}
+
+/*
+ * One row of the expanded parameter vector xf (see the top of this file) for candidate x:
+ *   row < nparams            : x[row]
+ *   row < n_xe               : constant (length of a non-identifiable internal edge)
+ *   row == n_xe              : 0.0 (NULL slot)
+ *   row <  n_xe+1+n_int      : D[v]   = sum of x over the edges from v up to the root
+ *   else                     : -2 D[v]
+ */
+SNAQ_HD double snaq_clamp10(double v) { return v > 10.0 ? 10.0 : v; }   /* setLength!: src/auxiliary.jl:122-124 */
+
+SNAQ_HD double snaq_xe(const SnaqTables &T, const double *x, const double *xconst, int sl) {
+    return sl < T.nparams ? x[sl] : xconst[sl - T.nparams];
+}
+SNAQ_HD double snaq_expand_row(const SnaqTables &T, const SnaqMath &M, const double *x, const double *xconst, int row) {
+    if (row < T.n_xe) return snaq_xe(T, x, xconst, row);
+    if (row == T.n_xe) return 0.0;
+    int k = row - T.n_xe - 1;
+    if (k < T.n_int) {
+        double d = 0.0;
+        for (int v = T.dnode[k]; T.parent[v] != v; v = T.parent[v]) d += snaq_xe(T, x, xconst, T.pslot[v]);
+        return d;
+    }
+    /* cycle rows: find the cycle (few cycles: linear search) */
+    int c = 0;
+    while (c + 1 < T.n_cycles && row >= (int)T.crow[c + 1]) c++;
+    const int kc = T.cyc_k[c];
+    const uint16_t *es = T.cyc_slot + T.cyc_off[c];
+    int j = row - (int)T.crow[c];
+    if (j <= kc) {                               /* C_j */
+        double d = 0.0;
+        for (int i = 0; i < j; i++) d += snaq_xe(T, x, xconst, es[i]);
+        return d;
+    }
+    j -= kc + 1;
+    if (j < kc - 1) {                            /* type-3 term, hit node at position o = j+1 (src/pseudolik.jl:878) */
+        if (T.cyc_flags[c] & 1) return 0.0;
+        const int o = j + 1;
+        double l1 = 0.0, l2 = 0.0;
+        for (int i = 0; i < o; i++) l1 += snaq_xe(T, x, xconst, es[i]);
+        for (int i = o; i < kc; i++) l2 += snaq_xe(T, x, xconst, es[i]);
+        l1 = snaq_clamp10(l1); l2 = snaq_clamp10(l2);
+        const double g2 = x[T.cyc_gslot[c]], g1 = 1.0 - g2;
+        return snaq_clamp10(-snaq_log(1.0 - g1 * g1 * (1.0 - snaq_exp(-l1, M)) - g2 * g2 * (1.0 - snaq_exp(-l2, M)), M));
+    }
+    j -= kc - 1;                                  /* -log(1-gammaz), capped at 10 (src/snaq_optimization.jl:230-234) */
+    if (!(T.cyc_flags[c] & 1)) return 0.0;
+    return snaq_clamp10(-snaq_log(1.0 - x[T.cyc_gslot[c] + j], M));
 }
 
 /* ------------------------------------------------------------------------------
  * evaluation.  XF is a functor slot -> double (the candidate's xe, NULL slot = 0.0).
  * ------------------------------------------------------------------------------ */
+/* sum of n signed pairs */
 template <class XF>
 SNAQ_HD double snaq_sum(const uint16_t *&pc, int n, const XF &x) {
     double a = 0.0;
     SNAQ_UNROLL1
-    for (int i = 0; i < n; i++) a += x(pc[i]);
-    pc += n;
+    for (int i = 0; i < n; i++) a += x(pc[2 * i]) - x(pc[2 * i + 1]);
+    pc += 2 * n;
     return a;
 }
-SNAQ_HD double snaq_clamp10(double v) { return v > 10.0 ? 10.0 : v; }   /* setLength!: src/auxiliary.jl:122-124 */
 
 /* class A: t1 = min(10, sum of the slots); nwords counts the NULL padding too */
 template <class XF>
 SNAQ_HD double snaq_tree_plain_t1(const uint16_t *pc, int nwords, const XF &x) {
     double t = 0.0;
-    for (int i = 0; i < nwords; i++) t += x(pc[i]);
+    for (int i = 0; i < nwords; i += 2) t += x(pc[i]) - x(pc[i + 1]);
     return snaq_clamp10(t);
 }
 
-/* class B: t1 of a tree-like quartet with cycle terms.
+/* class B: t1 of a tree-like quartet with type-2 / type-4 terms.
  * t1 = clamp( clamp(Bnear + R) + Bfar ): R = every non-negative piece (any merge order of those gives
  * min(10, sum)); B = a type-4 term merged with its chain, which can be negative and is added first
  * (near end) or last (far end) by internalLength! (src/pseudolik.jl:1076-1109) */
@@ -600,39 +688,30 @@ SNAQ_HD double snaq_tree_terms_t1(const uint16_t *pc, const XF &x, const SnaqMat
     double R = snaq_sum(pc, (int)(cw & 255u), x);
     double Bn = 0.0, Bf = 0.0;
     const int nterms = (int)(cw >> 8);
+    SNAQ_UNROLL1
     for (int it = 0; it < nterms; it++) {
         const unsigned th = *pc++;
-        const unsigned ty = th & 3u;
-        const double gq = x(th >> 4);          /* minor gamma (or gammaz for TZ) */
-        if (ty == SNAQ_T2) {
-            int n = *pc++;
-            double e = snaq_clamp10(snaq_sum(pc, n, x));
-            double gh = (th & 4u) ? 1.0 - gq : gq;
+        const double gq = x(th >> 4);          /* minor gamma */
+        if ((th & 3u) == SNAQ_T2) {
+            const double e = snaq_clamp10(x(pc[0]) - x(pc[1]));
+            pc += 2;
+            const double gh = (th & 4u) ? 1.0 - gq : gq;
             R += snaq_clamp10(-snaq_log(1.0 - gh * (1.0 - snaq_exp(-e, M)), M));                 /* src/pseudolik.jl:938 */
-        } else if (ty == SNAQ_T3) {
-            unsigned nn = *pc++;
-            double l1 = snaq_clamp10(snaq_sum(pc, (int)(nn & 255u), x));
-            double l2 = snaq_clamp10(snaq_sum(pc, (int)(nn >> 8), x));
-            double g1 = 1.0 - gq, g2 = gq;
-            R += snaq_clamp10(-snaq_log(1.0 - g1 * g1 * (1.0 - snaq_exp(-l1, M)) - g2 * g2 * (1.0 - snaq_exp(-l2, M)), M));   /* :878 */
-        } else if (ty == SNAQ_T4) {
-            unsigned nn = *pc++;
-            int ne = *pc++;
-            int nchain = *pc++;
-            double la = snaq_clamp10(snaq_sum(pc, (int)(nn & 255u), x));
-            double lb = snaq_clamp10(snaq_sum(pc, (int)(nn >> 8), x));
-            double le = snaq_clamp10(snaq_sum(pc, ne, x));
-            double ch = snaq_clamp10(snaq_sum(pc, nchain, x));
-            double ga = 1.0 - gq, gb = gq;
+        } else {
+            const double clo = x(pc[0]), chi = x(pc[1]), ck = x(pc[2]);
+            const double la = snaq_clamp10(clo);
+            const double lb = snaq_clamp10(ck - chi);
+            const double le = snaq_clamp10(chi - clo);
+            const int nchain = pc[3];
+            pc += 4;
+            const double ch = snaq_clamp10(snaq_sum(pc, nchain, x));
+            const double ga = 1.0 - gq, gb = gq;
             double l4 = -snaq_log(gb * gb * snaq_exp(-lb, M) + ga * gb * (3.0 - snaq_exp(-le, M)) + ga * ga * snaq_exp(-la, M), M);   /* :951 */
             if (l4 < SNAQ_MINLEN) status |= SNAQ_S_NEGLEN;
             l4 = snaq_clamp10(l4);
-            double B = snaq_clamp10(ch + l4);                                     /* :956 */
+            const double B = snaq_clamp10(ch + l4);                               /* :956 */
             if (B < SNAQ_MINLEN) status |= SNAQ_S_NEGLEN;
             if (th & 4u) Bf = B; else Bn = B;
-        } else {
-            /* src/snaq_optimization.jl:230-234 and src/pseudolik.jl:221: -log(1-gammaz), capped at 10 */
-            R += snaq_clamp10(-snaq_log(1.0 - gq, M));
         }
     }
     double t = snaq_clamp10(Bn + R);
@@ -645,7 +724,7 @@ SNAQ_HD double snaq_tree_terms_t1(const uint16_t *pc, const XF &x, const SnaqMat
 /* tree-like CFs from t1: cf[0] major, cf[1] = cf[2] minor (src/pseudolik.jl:1259) */
 SNAQ_HD void snaq_tree_cf(double t, const SnaqMath &M, double cf[3]) {
     const double y = snaq_exp(-t, M);
-    cf[0] = fma(-2.0 / 3.0, y, 1.0);
+    cf[0] = fma(SNAQ_K_M23, y, 1.0);
     cf[1] = 1.0 / 3.0 * y;
     cf[2] = cf[1];
 }
@@ -654,10 +733,10 @@ SNAQ_HD void snaq_tree_cf(double t, const SnaqMath &M, double cf[3]) {
 template <class XF>
 SNAQ_HD void snaq_t5_cf(unsigned kind, const uint16_t *pc, const XF &x, const SnaqMath &M, double cf[3]) {
     if (kind == SNAQ_KIND_T5) {
-        const double g2 = x(*pc++), g1 = 1.0 - g2;
-        unsigned nn = *pc++;
-        double y5 = snaq_exp(-snaq_clamp10(snaq_sum(pc, (int)(nn & 255u), x)), M);
-        double y6 = snaq_exp(-snaq_clamp10(snaq_sum(pc, (int)(nn >> 8), x)), M);
+        const double g2 = x(pc[0]), g1 = 1.0 - g2;
+        const double ca = x(pc[1]), cm = x(pc[2]), cb = x(pc[3]);
+        const double y5 = snaq_exp(-snaq_clamp10(cm - ca), M);
+        const double y6 = snaq_exp(-snaq_clamp10(cb - cm), M);
         cf[0] = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;
         cf[1] = g1 * 1.0 / 3.0 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
         cf[2] = g1 * 1.0 / 3.0 * y5 + g2 * 1.0 / 3.0 * y6;
@@ -733,7 +812,7 @@ SNAQ_HD void snaq_weights(unsigned hdr, const double obs[3], int sampled, double
  * written as sum_j W_j log(cf_j) - W[3]; for tree-like quartets log(minor) = -t1 - log 3.
  */
 SNAQ_HD double snaq_loglik_tree(double t, double major, const double W[4], const SnaqMath &M) {
-    return (W[0] != 0.0 ? W[0] * snaq_log(major, M) : 0.0) - W[1] * (t + SNAQ_LOG3) - W[3];
+    return (W[0] != 0.0 ? W[0] * snaq_log(major, M) : 0.0) - W[1] * (t + SNAQ_K_LOG3) - W[3];
 }
 SNAQ_HD double snaq_loglik_t5(const double cf[3], const double W[4], const SnaqMath &M, unsigned &status) {
     double s = -W[3];

@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -45,14 +46,41 @@
 // --------------------------------------------------------------------------------------------
 // math tables (copied to shared memory by every evaluation kernel)
 // --------------------------------------------------------------------------------------------
-__device__ const double g_exp_tab[SNAQ_EXP_TAB_N] = SNAQ_EXP_TAB_INIT;
-__device__ const double g_log_tab[SNAQ_LOG_TAB_N * 2] = SNAQ_LOG_TAB_INIT;
-#define MATH_TAB_DOUBLES (SNAQ_EXP_TAB_N + SNAQ_LOG_TAB_N * 2)
+__device__ const double g_math_tab[SNAQ_MATH_DOUBLES] = SNAQ_EXP_TAB_INIT_LOGS;   // 2^(j/16) | 1/c_j | -log(1/c_j)
 
-__device__ __forceinline__ SnaqMath load_math_tables(double *dst, int tid, int nthreads) {
-    for (int i = tid; i < SNAQ_EXP_TAB_N; i += nthreads) dst[i] = g_exp_tab[i];
-    for (int i = tid; i < SNAQ_LOG_TAB_N * 2; i += nthreads) dst[SNAQ_EXP_TAB_N + i] = g_log_tab[i];
-    return SnaqMath{dst, dst + SNAQ_EXP_TAB_N};
+// dst must be 128-byte aligned: each 16-entry table is then one shared-memory row, so lookups with
+// arbitrary per-lane indices are bank-conflict free
+__device__ __forceinline__ SnaqMath load_math_tables(double *dst, int tid) {
+    if (tid < SNAQ_MATH_DOUBLES) dst[tid] = g_math_tab[tid];
+    return SnaqMath{dst, dst + 16, dst + 32};
+}
+
+// ---- TMA 1-D bulk copies (cp.async.bulk) completing on an mbarrier -------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
 }
 
 // --------------------------------------------------------------------------------------------
@@ -176,6 +204,41 @@ struct XRow {    // one candidate's xe, contiguous
 
 __device__ __forceinline__ unsigned range_check(double v, double hi) { return (v >= 0.0 && v <= hi) ? 0u : SNAQ_S_RANGE; }
 
+// Expanded parameter vectors (snaq_expand_row); also the one place where the bounds of the reference's
+// update! are checked on the device (src/snaq_optimization.jl:213,221,228).
+//   tiled == 0: XF[p][row]                       (thread-per-quartet kernel)
+//   tiled == 1: XF[p/32][row][p%32], P padded up to a multiple of 32 with copies of the last candidate:
+//               the lane-per-candidate kernel copies one group's tile with a single TMA bulk copy
+__global__ void __launch_bounds__(256) k_expand_x(SnaqTables T, const double *__restrict__ X, const double *__restrict__ xconst,
+                                                  int P, int nh, int nt, int tiled, double *__restrict__ XF,
+                                                  uint32_t *__restrict__ status) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const SnaqMath M{g_math_tab, g_math_tab + 16, g_math_tab + 32};
+    if (!tiled) {
+        if (idx >= (int64_t)P * T.n_full) return;
+        const int p = (int)(idx / T.n_full), row = (int)(idx - (int64_t)p * T.n_full);
+        const double *x = X + (size_t)p * T.nparams;
+        if (row < T.nparams) {
+            const unsigned st = range_check(x[row], (row >= nh && row < nh + nt) ? 1.0e300 : 1.0);
+            if (st) atomicOr(status, st);
+        }
+        XF[idx] = snaq_expand_row(T, M, x, xconst, row);
+    } else {
+        const int Ppad = (P + 31) & ~31;
+        if (idx >= (int64_t)Ppad * T.n_full) return;
+        const int lane = (int)(idx & 31);
+        const int64_t gr = idx >> 5;                       // group * n_full + row
+        const int g = (int)(gr / T.n_full), row = (int)(gr - (int64_t)g * T.n_full);
+        const int p = min(g * 32 + lane, P - 1);
+        const double *x = X + (size_t)p * T.nparams;
+        if (row < T.nparams) {
+            const unsigned st = range_check(x[row], (row >= nh && row < nh + nt) ? 1.0e300 : 1.0);
+            if (st) atomicOr(status, st);
+        }
+        XF[idx] = snaq_expand_row(T, M, x, xconst, row);
+    }
+}
+
 struct ClassRanges {       // sorted quartet positions [0,nA) class A, [nA,nA+nB) class B, rest class C
     int64_t nA, nB, nC;
     int chA, chB, chC;     // chunks (blocks) per class
@@ -183,28 +246,48 @@ struct ClassRanges {       // sorted quartet positions [0,nA) class A, [nA,nA+nB
 
 /*
  * grid (nchunks, ngroups); block = WARPS*32 threads.  Block (cb, g) evaluates one chunk of quartets
- * of ONE class for candidates [32g, 32g+32).  Dynamic shared memory:
- *   xs   [n_xe+1][32] f64  candidates' extended parameter vectors, transposed; last row = NULL slot (0.0)
+ * of ONE class for candidates [32g, 32g+32).  Dynamic shared memory (128-byte aligned):
+ *   mt   [48] f64          exp / log tables (three 128-byte rows: conflict-free lookups)
+ *   bar  mbarrier
+ *   xs   [n_full][32] f64  the group's expanded parameter vectors      <- one TMA bulk copy
+ *   sW   [chunk][4] f64    weights of the chunk's quartets             <- one TMA bulk copy
+ *   sprog 8-byte chunks    programs of the chunk's quartets            <- one TMA bulk copy
  *   red  [WARPS][32] f64
- *   math tables (320 f64)
- *   sW   [chunk][4] f64
- *   soff [chunk+1]  u32    (chunk units of 4 words)
- *   sprog[.]        8-byte chunks
+ *   soff [chunk+1] u32     program offsets relative to the chunk (4-word units)
  */
+struct LanesSmem {
+    size_t mt, bar, xs, sW, sprog, red, soff, total;
+};
+__host__ __device__ inline LanesSmem lanes_smem_layout(int n_full, int chunk, int warps, uint32_t maxlen) {
+    LanesSmem L;
+    size_t o = 0;
+    L.mt = o; o += SNAQ_MATH_DOUBLES * 8;            // 384
+    L.bar = o; o += 128;
+    L.xs = o; o += (size_t)n_full * 256;
+    L.sW = o; o += (size_t)chunk * 32;
+    L.sprog = o; o += ((size_t)chunk * maxlen + 2) * 8;
+    o = (o + 15) & ~size_t(15);
+    L.red = o; o += (size_t)warps * 256;
+    L.soff = o; o += ((size_t)chunk + 1) * 4;
+    L.total = (o + 15) & ~size_t(15);
+    return L;
+}
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__restrict__ off, const uint16_t *__restrict__ prog,
                                                          const uint8_t *__restrict__ qhdr, const double *__restrict__ W,
-                                                         ClassRanges cr, int chunk, const double *__restrict__ X,
-                                                         const double *__restrict__ xconst, int nparams, int nh, int nt,
-                                                         int n_xe, int P, double *__restrict__ partial, int Ppad,
+                                                         ClassRanges cr, int chunk, uint32_t maxlen, const double *__restrict__ XFT,
+                                                         int n_full, double *__restrict__ partial, int Ppad,
                                                          uint32_t *__restrict__ status) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    double *xs = reinterpret_cast<double *>(smem);
-    double *red = xs + (size_t)(n_xe + 1) * 32;
-    double *mt = red + WARPS * 32;
-    double *sW = mt + MATH_TAB_DOUBLES;
-    uint32_t *soff = reinterpret_cast<uint32_t *>(sW + (size_t)chunk * 4);
-    uint2 *sprog = reinterpret_cast<uint2 *>(smem + (((size_t)(reinterpret_cast<unsigned char *>(soff + chunk + 1) - smem) + 7) & ~size_t(7)));
+    extern __shared__ __align__(128) unsigned char smem[];
+    const LanesSmem L = lanes_smem_layout(n_full, chunk, WARPS, maxlen);
+    double *mt = reinterpret_cast<double *>(smem + L.mt);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.bar);
+    double *xs = reinterpret_cast<double *>(smem + L.xs);
+    double *sW = reinterpret_cast<double *>(smem + L.sW);
+    uint2 *sprog_raw = reinterpret_cast<uint2 *>(smem + L.sprog);
+    double *red = reinterpret_cast<double *>(smem + L.red);
+    uint32_t *soff = reinterpret_cast<uint32_t *>(smem + L.soff);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = blockIdx.y;
     // heavy classes first: C, B, then A
@@ -215,36 +298,32 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
     else { cls = 0; cb -= cr.chC + cr.chB; qbase = 0; qend = cr.nA; }
     const int64_t q0 = qbase + (int64_t)cb * chunk;
     const int nqc = (int)min((int64_t)chunk, qend - q0);
-    unsigned st = 0;
-    // x tile: coalesced global reads (row-major X), transposed into xs[slot][lane]
-    for (int idx = tid; idx < 32 * nparams; idx += WARPS * 32) {
-        int r = idx / nparams, s = idx - r * nparams;
-        int p = min(32 * g + r, P - 1);
-        double v = X[(size_t)p * nparams + s];
-        st |= range_check(v, (s >= nh && s < nh + nt) ? 1.0e300 : 1.0);
-        xs[s * 32 + r] = v;
-    }
-    for (int idx = tid; idx < 32 * (n_xe - nparams); idx += WARPS * 32)
-        xs[(size_t)nparams * 32 + idx] = xconst[idx >> 5];
-    if (tid < 32) xs[(size_t)n_xe * 32 + tid] = 0.0;
-    const SnaqMath M = load_math_tables(mt, tid, WARPS * 32);
-    // quartet programs (8-byte chunks, coalesced), offsets and weights of this chunk
     const uint32_t base = off[q0];
     const uint32_t nchunks = off[q0 + nqc] - base;
-    for (int i = tid; i <= nqc; i += WARPS * 32) soff[i] = off[q0 + i] - base;
-    {
-        const uint2 *src = reinterpret_cast<const uint2 *>(prog) + base;
-        for (uint32_t i = tid; i < nchunks; i += WARPS * 32) sprog[i] = src[i];
-        const double2 *wsrc = reinterpret_cast<const double2 *>(W + (size_t)q0 * 4);
-        double2 *wdst = reinterpret_cast<double2 *>(sW);
-        for (int i = tid; i < nqc * 2; i += WARPS * 32) wdst[i] = wsrc[i];
+    // programs start at an 8-byte boundary; the bulk copy needs 16: start one chunk earlier if odd
+    const uint32_t base16 = base & ~1u;
+    const unsigned prog_bytes = (((base - base16) + nchunks) * 8u + 15u) & ~15u;
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned xs_bytes = (unsigned)n_full * 256u, w_bytes = (unsigned)nqc * 32u;
+        mbar_expect_tx(bar, xs_bytes + w_bytes + prog_bytes);
+        tma_load_1d(xs, XFT + (size_t)g * n_full * 32, xs_bytes, bar);
+        tma_load_1d(sW, W + (size_t)q0 * 4, w_bytes, bar);
+        tma_load_1d(sprog_raw, reinterpret_cast<const uint2 *>(prog) + base16, prog_bytes, bar);
     }
+    const SnaqMath M = load_math_tables(mt, tid);
+    for (int i = tid; i <= nqc; i += WARPS * 32) soff[i] = off[q0 + i] - base;
+    const uint2 *sprog = sprog_raw + (base - base16);
+    unsigned st = 0;
+    mbar_wait(bar, 0);
     __syncthreads();
     double acc = 0.0;
     const double *xl = xs + lane;
     if (cls == 0) {
-        // class A: t1 = min(10, sum of slots); two warps' worth of independent work per iteration is not
-        // needed: latency is hidden by the other warps of the SM
+        // class A: t1 = min(10, sum of signed pairs).  One PRMT per slot builds the byte offset slot*256 + lane*8.
+        const unsigned lane8 = (unsigned)lane * 8u;
+        const char *xb = reinterpret_cast<const char *>(xs);
 #pragma unroll 1
         for (int i = warp; i < nqc; i += WARPS) {
             const uint32_t o0 = soff[i], o1 = soff[i + 1];
@@ -252,16 +331,16 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
 #pragma unroll 1
             for (uint32_t c = o0; c < o1; c++) {
                 const uint2 w = sprog[c];
-                t0 += xl[(w.x & 0xffffu) << 5];
-                t1 += xl[(w.x >> 16) << 5];
-                t0 += xl[(w.y & 0xffffu) << 5];
-                t1 += xl[(w.y >> 16) << 5];
+                t0 += *reinterpret_cast<const double *>(xb + __byte_perm(w.x, lane8, 0x5104));
+                t1 -= *reinterpret_cast<const double *>(xb + __byte_perm(w.x, lane8, 0x5324));
+                t0 += *reinterpret_cast<const double *>(xb + __byte_perm(w.y, lane8, 0x5104));
+                t1 -= *reinterpret_cast<const double *>(xb + __byte_perm(w.y, lane8, 0x5324));
             }
             const double t = fmin(t0 + t1, 10.0);
             const double y = snaq_exp(-t, M);
-            const double major = fma(-2.0 / 3.0, y, 1.0);
+            const double major = fma(SNAQ_K_M23, y, 1.0);
             const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
-            acc += fma(w4.x, snaq_log(major, M), -fma(w4.y, t + SNAQ_LOG3, w4.w));
+            acc += fma(w4.x, snaq_log_pos(major, M), -fma(w4.y, t + SNAQ_K_LOG3, w4.w));
         }
     } else if (cls == 1) {
         const XLane xf{xl};
@@ -270,7 +349,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
             const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + soff[i]);
             const double t = snaq_tree_terms_t1(pc, xf, M, st);
             const double y = snaq_exp(-t, M);
-            const double major = fma(-2.0 / 3.0, y, 1.0);
+            const double major = fma(SNAQ_K_M23, y, 1.0);
             if (major < 0.0) st |= SNAQ_S_NEGLEN;
             acc += snaq_loglik_tree(t, major, sW + 4 * i, M);
         }
@@ -297,7 +376,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
 }
 
 /*
- * Thread per quartet (sorted order), P <= QK_MAXP candidates.  x vectors (P x (n_xe+1)) and the math
+ * Thread per quartet (sorted order), P <= QK_MAXP candidates.  Expanded x vectors (P x n_full) and the math
  * tables sit in shared memory; programs are read straight from global memory in 8-byte chunks.
  * partial[block][p] gets the block's sum.  Optional per-quartet outputs, written for the LAST
  * candidate at the quartet's ORIGINAL index: expcf [nq][3] in data order, logpl [nq], deltacf [nq].
@@ -306,28 +385,19 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_eval_quartets(const uint32_t *__restrict__ off, const uint16_t *__restrict__ prog,
                                                         const uint8_t *__restrict__ qhdr, const uint32_t *__restrict__ perm,
                                                         const double *__restrict__ W, const double *__restrict__ obs,
-                                                        int64_t nq, int64_t nA, const double *__restrict__ X,
-                                                        const double *__restrict__ xconst, int nparams, int nh, int nt,
-                                                        int n_xe, int P, double *__restrict__ partial,
+                                                        int64_t nq, int64_t nA, const double *__restrict__ XF,
+                                                        int n_full, int P, double *__restrict__ partial,
                                                         double *__restrict__ expcf, double *__restrict__ logpl,
                                                         double *__restrict__ deltacf, uint32_t *__restrict__ status) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int xstride = n_xe + 1;
-    double *xs = reinterpret_cast<double *>(smem);                 // [P][n_xe+1]
-    double *red = xs + (size_t)P * xstride;                        // [BLOCK/32]
-    double *mt = red + BLOCK / 32;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int xstride = n_full;
+    double *mt = reinterpret_cast<double *>(smem);                 // 48 doubles, 128-byte aligned
+    double *red = mt + SNAQ_MATH_DOUBLES;                          // [BLOCK/32]
+    double *xs = red + BLOCK / 32;                                 // [P][n_full]
     const int tid = threadIdx.x;
     unsigned st = 0;
-    for (int idx = tid; idx < P * xstride; idx += BLOCK) {
-        int p = idx / xstride, s = idx - p * xstride;
-        double v = 0.0;
-        if (s < nparams) {
-            v = X[(size_t)p * nparams + s];
-            st |= range_check(v, (s >= nh && s < nh + nt) ? 1.0e300 : 1.0);
-        } else if (s < n_xe) v = xconst[s - nparams];
-        xs[idx] = v;
-    }
-    const SnaqMath M = load_math_tables(mt, tid, BLOCK);
+    for (int idx = tid; idx < P * xstride; idx += BLOCK) xs[idx] = XF[idx];
+    const SnaqMath M = load_math_tables(mt, tid);
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * BLOCK + tid;
     const bool active = i < nq;
@@ -355,11 +425,12 @@ __global__ void __launch_bounds__(BLOCK) k_eval_quartets(const uint32_t *__restr
                 const uint2 *pp = reinterpret_cast<const uint2 *>(pc);
                 for (int c = 0; c < (nwords >> 2); c++) {
                     const uint2 ww = pp[c];
-                    t += xf(ww.x & 0xffffu); t += xf(ww.x >> 16); t += xf(ww.y & 0xffffu); t += xf(ww.y >> 16);
+                    t += xf(ww.x & 0xffffu) - xf(ww.x >> 16);
+                    t += xf(ww.y & 0xffffu) - xf(ww.y >> 16);
                 }
                 t1 = fmin(t, 10.0);
                 snaq_tree_cf(t1, M, cf);
-                v = fma(w[0], snaq_log(cf[0], M), -fma(w[1], t1 + SNAQ_LOG3, w[3]));
+                v = fma(w[0], snaq_log_pos(cf[0], M), -fma(w[1], t1 + SNAQ_K_LOG3, w[3]));
             } else {
                 snaq_eval_quartet(hdr, pc, nwords, xf, M, cf, &t1, st);
                 v = snaq_quartet_loglik(SNAQ_HDR_KIND(hdr), cf, t1, w, M, st);
@@ -466,10 +537,12 @@ struct snaq_ctx {
     size_t scan_tmp_cap = 0;
     // scratch
     double *d_X = nullptr; size_t X_cap = 0;
+    double *d_XF = nullptr; size_t XF_cap = 0;   // expanded parameter vectors [P][n_full]
     double *d_out = nullptr; size_t out_cap = 0;
     double *d_partial = nullptr; size_t partial_cap = 0;
     double *h_pin = nullptr; size_t pin_cap = 0;
     int sm_count = 148;
+    int lanes_warps = 8;                  // warps per block of k_eval_lanes (SNAQ_LANES_WARPS = 8, 12 or 16)
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
@@ -541,19 +614,25 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
     const int64_t nq = ctx->nq;
     if (nq == 0) { CK(cudaMemsetAsync(dout, 0, sizeof(double) * P, stream)); return SNAQ_OK; }
     const bool per_quartet = expcf || logpl || deltacf;
-    if (P >= LANES_MIN_P && !per_quartet) {
+    const bool use_lanes = P >= LANES_MIN_P && !per_quartet;
+    {
+        const int Prows = use_lanes ? ((P + 31) & ~31) : P;
+        int rc = ensure(ctx, ctx->d_XF, ctx->XF_cap, (size_t)Prows * H.n_full);
+        if (rc) return rc;
+        const int64_t tot = (int64_t)Prows * H.n_full;
+        k_expand_x<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(ctx->T, dX, ctx->d_xconst, P, H.nh, H.nt, use_lanes ? 1 : 0,
+                                                                      ctx->d_XF, ctx->d_status + 1);
+        CK(cudaGetLastError());
+    }
+    const double *dXF = ctx->d_XF;
+    if (use_lanes) {
         const int ngroups = (P + 31) / 32, Ppad = ngroups * 32;
         // chunk: quartets per block.  Enough blocks to fill the machine, bounded by shared memory.
-        const size_t xs_bytes = (size_t)(H.n_xe + 1) * 32 * 8;
-        const int warps = xs_bytes > 40 * 1024 ? 16 : 8;
-        int chunk = 512;
+        const int warps = ctx->lanes_warps;
+        int chunk = 256;
         while (chunk > 64 && (int64_t)ngroups * ((nq + chunk - 1) / chunk) < (int64_t)ctx->sm_count * 8) chunk >>= 1;
-        auto smem_for = [&](int ch) {
-            return xs_bytes + (size_t)warps * 32 * 8 + MATH_TAB_DOUBLES * 8 + (size_t)ch * 32 + (size_t)(ch + 1) * 4 + 8 +
-                   (size_t)ch * ctx->maxlen * 8 + 16;
-        };
-        while (chunk > 32 && smem_for(chunk) > 200 * 1024) chunk >>= 1;
-        const size_t smem = smem_for(chunk);
+        while (chunk > 32 && lanes_smem_layout(H.n_full, chunk, warps, ctx->maxlen).total > 200 * 1024) chunk >>= 1;
+        const size_t smem = lanes_smem_layout(H.n_full, chunk, warps, ctx->maxlen).total;
         if (smem > 227 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_lanes"; return SNAQ_EINVAL; }
         ClassRanges cr;
         cr.nA = ctx->nA; cr.nB = ctx->nB; cr.nC = ctx->nC;
@@ -563,15 +642,16 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
         int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)nchunks * Ppad);
         if (rc) return rc;
         dim3 grid((unsigned)nchunks, (unsigned)ngroups);
-        if (warps == 8) {
-            CK(cudaFuncSetAttribute(k_eval_lanes<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_eval_lanes<8><<<grid, 256, smem, stream>>>(ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_W, cr, chunk, dX, ctx->d_xconst,
-                                                        H.nparams, H.nh, H.nt, H.n_xe, P, ctx->d_partial, Ppad, ctx->d_status + 1);
-        } else {
-            CK(cudaFuncSetAttribute(k_eval_lanes<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_eval_lanes<16><<<grid, 512, smem, stream>>>(ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_W, cr, chunk, dX, ctx->d_xconst,
-                                                         H.nparams, H.nh, H.nt, H.n_xe, P, ctx->d_partial, Ppad, ctx->d_status + 1);
-        }
+#define LAUNCH_LANES(WN)                                                                                                       \
+    do {                                                                                                                       \
+        CK(cudaFuncSetAttribute(k_eval_lanes<WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
+        k_eval_lanes<WN><<<grid, WN * 32, smem, stream>>>(ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_W, cr, chunk, ctx->maxlen, dXF, \
+                                                         H.n_full, ctx->d_partial, Ppad, ctx->d_status + 1);                    \
+    } while (0)
+        if (warps == 8) LAUNCH_LANES(8);
+        else if (warps == 12) LAUNCH_LANES(12);
+        else LAUNCH_LANES(16);
+#undef LAUNCH_LANES
         CK(cudaGetLastError());
         k_reduce_partials_t<<<(P + 255) / 256, 256, 0, stream>>>(ctx->d_partial, (int)nchunks, Ppad, P, dout);
         CK(cudaGetLastError());
@@ -586,14 +666,14 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
         const int Pc = std::min(QK_MAXP, P - p0);
         int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)nblocks * Pc);
         if (rc) return rc;
-        const size_t smem = (size_t)Pc * (H.n_xe + 1) * 8 + (BLOCK / 32) * 8 + MATH_TAB_DOUBLES * 8 + 16;
+        const size_t smem = (size_t)Pc * H.n_full * 8 + (BLOCK / 32) * 8 + SNAQ_MATH_DOUBLES * 8 + 16;
         if (smem > 200 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_quartets"; return SNAQ_EINVAL; }
         CK(cudaFuncSetAttribute(k_eval_quartets<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const bool last = (p0 + Pc == P);
         k_eval_quartets<BLOCK><<<(unsigned)nblocks, BLOCK, smem, stream>>>(
-            ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_perm, ctx->d_W, ctx->d_obs, nq, ctx->nA, dX + (size_t)p0 * H.nparams,
-            ctx->d_xconst, H.nparams, H.nh, H.nt, H.n_xe, Pc, ctx->d_partial, last ? expcf : nullptr, last ? logpl : nullptr,
-            last ? deltacf : nullptr, ctx->d_status + 1);
+            ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_perm, ctx->d_W, ctx->d_obs, nq, ctx->nA, dXF + (size_t)p0 * H.n_full,
+            H.n_full, Pc, ctx->d_partial, last ? expcf : nullptr, last ? logpl : nullptr, last ? deltacf : nullptr,
+            ctx->d_status + 1);
         CK(cudaGetLastError());
         k_reduce_partials<<<(Pc * 32 + 255) / 256, 256, 0, stream>>>(ctx->d_partial, (int)nblocks, Pc, Pc, dout + p0);
         CK(cudaGetLastError());
@@ -641,6 +721,7 @@ int snaq_create(const snaq_opts *opts, snaq_ctx **out) {
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, ctx->device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char *ev = getenv("SNAQ_LANES_WARPS")) { int v = atoi(ev); if (v == 8 || v == 12 || v == 16) ctx->lanes_warps = v; }
     if ((e = cudaMalloc((void **)&ctx->d_status, 4 * sizeof(uint32_t))) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cudaMalloc((void **)&ctx->d_total, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
     cudaMemset(ctx->d_status, 0, 4 * sizeof(uint32_t));
@@ -654,7 +735,7 @@ int snaq_destroy(snaq_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_blob); cudaFree(ctx->d_xconst);
     cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_status); cudaFree(ctx->d_total);
-    cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_out); cudaFree(ctx->d_partial);
+    cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_XF); cudaFree(ctx->d_out); cudaFree(ctx->d_partial);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_qhdr); cudaFree(ctx->d_len4); cudaFree(ctx->d_iota); cudaFree(ctx->d_cls);
     cudaFree(ctx->d_cls_sorted);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);

@@ -19,6 +19,7 @@ template <class T> size_t put(std::vector<unsigned char> &blob, const std::vecto
 SnaqTables SnaqHostTables::view(const unsigned char *b) const {
     SnaqTables T;
     T.ntaxa = ntaxa; T.n_tnodes = n_tnodes; T.n_cycles = n_cycles; T.nparams = nparams; T.n_xe = n_xe; T.n_hybrids = n_hybrids;
+    T.n_int = n_int; T.n_full = n_full;
     T.leaf_tnode = (const uint16_t *)(b + off_leaf_tnode);
     T.parent = (const uint16_t *)(b + off_parent);
     T.depth = (const uint16_t *)(b + off_depth);
@@ -33,6 +34,9 @@ SnaqTables SnaqHostTables::view(const unsigned char *b) const {
     T.cyc_hyb = (const uint8_t *)(b + off_cyc_hyb);
     T.torder = (const uint16_t *)(b + off_torder);
     T.cyc_order = (const uint16_t *)(b + off_cyc_order);
+    T.dslot = (const uint16_t *)(b + off_dslot);
+    T.dnode = (const uint16_t *)(b + off_dnode);
+    T.crow = (const uint16_t *)(b + off_crow);
     return T;
 }
 
@@ -301,6 +305,19 @@ int snaq_build_tables(const snaq_flatnet *f, int ntaxa, SnaqHostTables &o, std::
         o.off_cyc_hyb = put(o.blob, cyc_hyb);
         o.off_torder = put(o.blob, t_order);
         o.off_cyc_order = put(o.blob, cyc_order);
+        // prefix-sum rows: one D row (and one -2D row) per internal blob-tree node
+        std::vector<char> isLeafT(nt, 0);
+        for (int n = 0; n < N; n++) if (isLeaf(n)) isLeafT[tOfNode[n]] = 1;
+        std::vector<uint16_t> dslot(nt, 0xFFFF), dnode;
+        for (int v = 0; v < nt; v++) if (!isLeafT[v]) { dslot[v] = (uint16_t)(o.n_xe + 1 + (int)dnode.size()); dnode.push_back((uint16_t)v); }
+        o.n_int = (int)dnode.size();
+        o.n_full = o.n_xe + 1 + o.n_int;
+        std::vector<uint16_t> crow(std::max(H, 1), 0);
+        for (int h = 0; h < H; h++) { crow[h] = (uint16_t)o.n_full; o.n_full += SNAQ_CYC_ROWS((int)cycNodes[h].size()); }
+        if (o.n_full > 65535) fail(SNAQ_EINVAL, "network too large for 16-bit slots");
+        o.off_dslot = put(o.blob, dslot);
+        o.off_dnode = put(o.blob, dnode);
+        o.off_crow = put(o.blob, crow);
         return SNAQ_OK;
     } catch (const Fail &e) {
         err = e.msg;

@@ -17,13 +17,14 @@
 
 struct SnaqHostTables {
     int ntaxa = 0, n_tnodes = 0, n_cycles = 0, nparams = 0, n_xe = 0, n_hybrids = 0;
+    int n_int = 0, n_full = 0;                        // internal blob-tree nodes; rows of the expanded vector
     int nh = 0, nt = 0, nhz = 0;                     // x = [gamma | t | gammaz]
     std::vector<double> x0, upper, xconst;           // xconst: values of slots nparams..n_xe-1
     std::vector<int32_t> numht;
     // one contiguous blob holding every table (uploaded to the device as is)
     std::vector<unsigned char> blob;
     size_t off_leaf_tnode = 0, off_parent = 0, off_depth = 0, off_tcycle = 0, off_pslot = 0, off_blk = 0,
-           off_cyc_k = 0, off_cyc_off = 0, off_cyc_slot = 0, off_cyc_gslot = 0, off_cyc_flags = 0, off_cyc_hyb = 0, off_torder = 0, off_cyc_order = 0;
+           off_cyc_k = 0, off_cyc_off = 0, off_cyc_slot = 0, off_cyc_gslot = 0, off_cyc_flags = 0, off_cyc_hyb = 0, off_torder = 0, off_cyc_order = 0, off_dslot = 0, off_dnode = 0, off_crow = 0;
     // extra tables used only by the hasEdge (parity descriptor) kernel
     std::vector<int32_t> edge_slot;                  // per net edge: xe slot or -1
     SnaqTables view(const unsigned char *base) const;

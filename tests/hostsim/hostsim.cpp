@@ -12,19 +12,20 @@
 #include "../../snaq.jl_b200/csrc/snaq_tables.h"
 
 static thread_local std::string g_err;
-static const double g_et[SNAQ_EXP_TAB_N] = SNAQ_EXP_TAB_INIT;
-static const double g_lt[SNAQ_LOG_TAB_N * 2] = SNAQ_LOG_TAB_INIT;
+static const double g_et[16] = SNAQ_EXP_TAB_INIT;
+static const double g_li[16] = SNAQ_LOGINV_TAB_INIT;
+static const double g_lc[16] = SNAQ_LOGC_TAB_INIT;
 
 struct XRow {
-    const double *x; const double *xc; int np, nxe;
-    double operator()(unsigned s) const { return (int)s < np ? x[s] : ((int)s < nxe ? xc[s - np] : 0.0); }
+    const double *xf;
+    double operator()(unsigned s) const { return xf[s]; }
 };
 
 extern "C" {
 const char *hostsim_last_error() { return g_err.c_str(); }
 
 void hostsim_math(int n, const double *u, double *e, double *l) {
-    SnaqMath M{g_et, g_lt};
+    SnaqMath M{g_et, g_li, g_lc};
     for (int i = 0; i < n; i++) {
         if (e) e[i] = snaq_exp(u[i], M);
         if (l) l[i] = snaq_log(u[i], M);
@@ -49,7 +50,7 @@ int hostsim_run(const snaq_flatnet *f, int ntaxa, int64_t nq, const uint16_t *ta
     int rc = snaq_build_tables(f, ntaxa, H, g_err);
     if (rc) return rc;
     SnaqTables T = H.view(H.blob.data());
-    SnaqMath M{g_et, g_lt};
+    SnaqMath M{g_et, g_li, g_lc};
     std::vector<std::vector<uint16_t>> progs(nq);
     std::vector<uint8_t> hdrs(nq);
     for (int64_t q = 0; q < nq; q++) {
@@ -71,7 +72,9 @@ int hostsim_run(const snaq_flatnet *f, int ntaxa, int64_t nq, const uint16_t *ta
     }
     unsigned status = 0;
     for (int p = 0; p < P; p++) {
-        XRow xr{X + (size_t)p * H.nparams, H.xconst.data(), H.nparams, H.n_xe};
+        std::vector<double> xf(H.n_full);
+        for (int r = 0; r < H.n_full; r++) xf[r] = snaq_expand_row(T, M, X + (size_t)p * H.nparams, H.xconst.data(), r);
+        XRow xr{xf.data()};
         double total = 0;
         for (int64_t q = 0; q < nq; q++) {
             double cf[3], t1, W[4];
