@@ -320,50 +320,134 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
     __syncthreads();
     double acc = 0.0;
     const double *xl = xs + lane;
+    // One PRMT per slot builds the byte offset slot*256 + lane*8 of xf[slot] for this lane.
+    const unsigned lane8 = (unsigned)lane * 8u;
+    const char *xb = reinterpret_cast<const char *>(xs);
+#define XLO(w) (*reinterpret_cast<const double *>(xb + __byte_perm((w), lane8, 0x5104)))
+#define XHI(w) (*reinterpret_cast<const double *>(xb + __byte_perm((w), lane8, 0x5324)))
     if (cls == 0) {
-        // class A: t1 = min(10, sum of signed pairs).  One PRMT per slot builds the byte offset slot*256 + lane*8.
-        const unsigned lane8 = (unsigned)lane * 8u;
-        const char *xb = reinterpret_cast<const char *>(xs);
+        // class A: t1 = min(10, sum of signed pairs); two quartets per iteration (independent chains, the
+        // polynomial constants are fetched once for both)
+        auto pair_sum = [&](int i) {
+            uint32_t c = soff[i];
+            const uint32_t o1 = soff[i + 1];
+            uint2 w = sprog[c];
+            double t0 = XLO(w.x) - XHI(w.x), t1 = XLO(w.y) - XHI(w.y);
 #pragma unroll 1
-        for (int i = warp; i < nqc; i += WARPS) {
-            const uint32_t o0 = soff[i], o1 = soff[i + 1];
-            double t0 = 0.0, t1 = 0.0;
-#pragma unroll 1
-            for (uint32_t c = o0; c < o1; c++) {
-                const uint2 w = sprog[c];
-                t0 += *reinterpret_cast<const double *>(xb + __byte_perm(w.x, lane8, 0x5104));
-                t1 -= *reinterpret_cast<const double *>(xb + __byte_perm(w.x, lane8, 0x5324));
-                t0 += *reinterpret_cast<const double *>(xb + __byte_perm(w.y, lane8, 0x5104));
-                t1 -= *reinterpret_cast<const double *>(xb + __byte_perm(w.y, lane8, 0x5324));
+            for (++c; c < o1; ++c) {
+                w = sprog[c];
+                t0 += XLO(w.x) - XHI(w.x);
+                t1 += XLO(w.y) - XHI(w.y);
             }
-            const double t = fmin(t0 + t1, 10.0);
+            return fmin(t0 + t1, 10.0);
+        };
+        int i = warp;
+#pragma unroll 1
+        for (; i + WARPS < nqc; i += 2 * WARPS) {
+            const double ta = pair_sum(i), tb = pair_sum(i + WARPS);
+            const double ya = snaq_exp(-ta, M), yb = snaq_exp(-tb, M);
+            const double ma = fma(SNAQ_K_M23, ya, 1.0), mb = fma(SNAQ_K_M23, yb, 1.0);
+            const double la = snaq_log_pos(ma, M), lb = snaq_log_pos(mb, M);
+            const double4 wa = reinterpret_cast<const double4 *>(sW)[i], wb = reinterpret_cast<const double4 *>(sW)[i + WARPS];
+            acc += fma(wa.x, la, -fma(wa.y, ta + SNAQ_K_LOG3, wa.w));
+            acc += fma(wb.x, lb, -fma(wb.y, tb + SNAQ_K_LOG3, wb.w));
+        }
+        if (i < nqc) {
+            const double t = pair_sum(i);
             const double y = snaq_exp(-t, M);
             const double major = fma(SNAQ_K_M23, y, 1.0);
             const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
             acc += fma(w4.x, snaq_log_pos(major, M), -fma(w4.y, t + SNAQ_K_LOG3, w4.w));
         }
     } else if (cls == 1) {
-        const XLane xf{xl};
+        // class B: tree-like with type-2 / type-4 terms (same arithmetic as snaq_tree_terms_t1)
 #pragma unroll 1
         for (int i = warp; i < nqc; i += WARPS) {
             const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + soff[i]);
-            const double t = snaq_tree_terms_t1(pc, xf, M, st);
+            const unsigned cw = pc[0];
+            const int npairs = (int)(cw & 255u), nterms = (int)(cw >> 8);
+            double R = 0.0;
+            int k = 1;
+#pragma unroll 1
+            for (int j = 0; j < npairs; j++, k += 2) {
+                const unsigned wv = (unsigned)pc[k] | ((unsigned)pc[k + 1] << 16);
+                R += XLO(wv) - XHI(wv);
+            }
+            double Bn = 0.0, Bf = 0.0;
+#pragma unroll 1
+            for (int it = 0; it < nterms; it++) {
+                const unsigned th = pc[k];
+                const double gq = XLO(th >> 4);
+                if ((th & 3u) == SNAQ_T2) {
+                    const unsigned wv = (unsigned)pc[k + 1] | ((unsigned)pc[k + 2] << 16);
+                    k += 3;
+                    const double e = fmin(XLO(wv) - XHI(wv), 10.0);
+                    const double gh = (th & 4u) ? 1.0 - gq : gq;
+                    R += fmin(-snaq_log(1.0 - gh * (1.0 - snaq_exp(-e, M)), M), 10.0);
+                } else {
+                    const unsigned wv = (unsigned)pc[k + 1] | ((unsigned)pc[k + 2] << 16);
+                    const double clo = XLO(wv), chi = XHI(wv), ck = XLO((unsigned)pc[k + 3]);
+                    const int nchain = pc[k + 4];
+                    k += 5;
+                    double ch = 0.0;
+#pragma unroll 1
+                    for (int j = 0; j < nchain; j++, k += 2) {
+                        const unsigned wc = (unsigned)pc[k] | ((unsigned)pc[k + 1] << 16);
+                        ch += XLO(wc) - XHI(wc);
+                    }
+                    ch = fmin(ch, 10.0);
+                    const double ya = snaq_exp(-fmin(clo, 10.0), M), yb = snaq_exp(-fmin(ck - chi, 10.0), M);
+                    const double ye = snaq_exp(-fmin(chi - clo, 10.0), M);
+                    const double ga = 1.0 - gq, gb = gq;
+                    double l4 = -snaq_log(gb * gb * yb + ga * gb * (3.0 - ye) + ga * ga * ya, M);
+                    if (l4 < SNAQ_MINLEN) st |= SNAQ_S_NEGLEN;
+                    l4 = fmin(l4, 10.0);
+                    const double B = fmin(ch + l4, 10.0);
+                    if (B < SNAQ_MINLEN) st |= SNAQ_S_NEGLEN;
+                    if (th & 4u) Bf = B; else Bn = B;
+                }
+            }
+            double t = fmin(Bn + R, 10.0);
+            if (t < SNAQ_MINLEN) st |= SNAQ_S_NEGLEN;
+            t = fmin(t + Bf, 10.0);
+            if (t < SNAQ_MINLEN) st |= SNAQ_S_NEGLEN;
             const double y = snaq_exp(-t, M);
             const double major = fma(SNAQ_K_M23, y, 1.0);
+            const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
             if (major < 0.0) st |= SNAQ_S_NEGLEN;
-            acc += snaq_loglik_tree(t, major, sW + 4 * i, M);
+            const double lm = (w4.x != 0.0) ? snaq_log(major, M) : 0.0;      // obs == 0 contributes 0 (src/pseudolik.jl:1398)
+            acc += fma(w4.x, lm, -fma(w4.y, t + SNAQ_K_LOG3, w4.w));
         }
     } else {
+        // class C: 4-cycle quartets.  T5: [gslot, C_a, C_m, C_b] in one chunk; all three CFs are positive
         const XLane xf{xl};
         const uint8_t *hd = qhdr + q0;
 #pragma unroll 1
         for (int i = warp; i < nqc; i += WARPS) {
-            const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + soff[i]);
-            double cf[3];
-            snaq_t5_cf(SNAQ_HDR_KIND(hd[i]), pc, xf, M, cf);
-            acc += snaq_loglik_t5(cf, sW + 4 * i, M, st);
+            const uint2 w = sprog[soff[i]];
+            const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
+            if (SNAQ_HDR_KIND(hd[i]) == SNAQ_KIND_T5) {
+                const double g2 = XLO(w.x), ca = XHI(w.x), cm = XLO(w.y), cb = XHI(w.y);
+                const double g1 = 1.0 - g2;
+                const double y5 = snaq_exp(-fmin(cm - ca, 10.0), M), y6 = snaq_exp(-fmin(cb - cm, 10.0), M);
+                const double cf0 = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;
+                const double cf1 = g1 * 1.0 / 3.0 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
+                const double cf2 = g1 * 1.0 / 3.0 * y5 + g2 * 1.0 / 3.0 * y6;
+                double v = -w4.w;
+                v = fma(w4.x, snaq_log_pos(cf0, M), v);
+                v = fma(w4.y, snaq_log_pos(cf1, M), v);
+                v = fma(w4.z, snaq_log_pos(cf2, M), v);
+                acc += v;
+            } else {
+                const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + soff[i]);
+                double cf[3];
+                snaq_t5_cf(SNAQ_KIND_T5BD1, pc, xf, M, cf);
+                acc += snaq_loglik_t5(cf, sW + 4 * i, M, st);
+            }
         }
     }
+#undef XLO
+#undef XHI
     red[warp * 32 + lane] = acc;
     __syncthreads();
     if (warp == 0) {
