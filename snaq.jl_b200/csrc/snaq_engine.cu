@@ -42,6 +42,7 @@
 #define SNAQ_S_RANGE 8u   /* a parameter outside its bounds reached the device */
 #define LANES_MIN_P 16    /* batches of at least this many candidates use k_eval_lanes */
 #define QK_MAXP 16        /* k_eval_quartets handles at most this many candidates per launch */
+#define QK_STAGES 3       /* TMA stages of k_eval_quartets */
 
 // --------------------------------------------------------------------------------------------
 // math tables (copied to shared memory by every evaluation kernel)
@@ -96,9 +97,10 @@ __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_
                                                      uint32_t *__restrict__ len4, uint8_t *__restrict__ cls,
                                                      uint32_t *__restrict__ iota, unsigned long long *__restrict__ stats,
                                                      uint32_t *__restrict__ status) {
-    // stats: [0] total chunks, [1] max chunks, [2..4] quartets per class
+    // stats: [0] total chunks, [1] max chunks, [2..5] quartets per sort class
+    // sort classes: 0 = class A with a one-chunk program, 1 = other class A, 2 = class B, 3 = class C
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned n = 0, c = 3;
+    unsigned n = 0, c = 4;
     if (q < nq) {
         uint16_t tx[4];
         load_taxa(taxa, q, tx);
@@ -109,15 +111,16 @@ __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_
         n = (unsigned)((w.n + 3) >> 2);
         if (n == 0) n = 1;
         c = SNAQ_HDR_CLASS(hdr);
+        c = (c == 0) ? (n == 1 ? 0u : 1u) : c + 1u;
         len4[q] = n;
         cls[q] = (uint8_t)c;
         iota[q] = (uint32_t)q;
     }
     __shared__ unsigned long long ssum[4];
-    __shared__ unsigned smax[4], scnt[3];
-    if (threadIdx.x < 3) scnt[threadIdx.x] = 0;
+    __shared__ unsigned smax[4], scnt[4];
+    if (threadIdx.x < 4) scnt[threadIdx.x] = 0;
     __syncthreads();
-    if (c < 3) atomicAdd(&scnt[c], 1u);
+    if (c < 4) atomicAdd(&scnt[c], 1u);
     unsigned long long s = n;
     unsigned m = n;
     for (int o = 16; o > 0; o >>= 1) {
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_
     if (threadIdx.x == 0) {
         atomicAdd(&stats[0], ssum[0] + ssum[1] + ssum[2] + ssum[3]);
         atomicMax(&stats[1], (unsigned long long)max(max(smax[0], smax[1]), max(smax[2], smax[3])));
-        for (int k = 0; k < 3; k++) if (scnt[k]) atomicAdd(&stats[2 + k], (unsigned long long)scnt[k]);
+        for (int k = 0; k < 4; k++) if (scnt[k]) atomicAdd(&stats[2 + k], (unsigned long long)scnt[k]);
     }
 }
 
@@ -240,6 +243,7 @@ __global__ void __launch_bounds__(256) k_expand_x(SnaqTables T, const double *__
 }
 
 struct ClassRanges {       // sorted quartet positions [0,nA) class A, [nA,nA+nB) class B, rest class C
+    int64_t nA1;           // the first nA1 class-A quartets have one-chunk programs: off[i] == i
     int64_t nA, nB, nC;
     int chA, chB, chC;     // chunks (blocks) per class
 };
@@ -341,10 +345,15 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
             }
             return fmin(t0 + t1, 10.0);
         };
+        const bool one_chunk = (q0 + nqc <= cr.nA1);      // every program of this block is one chunk: sprog[i]
+        auto one_sum = [&](int i) {
+            const uint2 w = sprog[i];
+            return fmin((XLO(w.x) - XHI(w.x)) + (XLO(w.y) - XHI(w.y)), 10.0);
+        };
         int i = warp;
 #pragma unroll 1
         for (; i + WARPS < nqc; i += 2 * WARPS) {
-            const double ta = pair_sum(i), tb = pair_sum(i + WARPS);
+            const double ta = one_chunk ? one_sum(i) : pair_sum(i), tb = one_chunk ? one_sum(i + WARPS) : pair_sum(i + WARPS);
             const double ya = snaq_exp(-ta, M), yb = snaq_exp(-tb, M);
             const double ma = fma(SNAQ_K_M23, ya, 1.0), mb = fma(SNAQ_K_M23, yb, 1.0);
             const double la = snaq_log_pos(ma, M), lb = snaq_log_pos(mb, M);
@@ -460,104 +469,226 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
 }
 
 /*
- * Thread per quartet (sorted order), P <= QK_MAXP candidates.  Expanded x vectors (P x n_full) and the math
- * tables sit in shared memory; programs are read straight from global memory in 8-byte chunks.
- * partial[block][p] gets the block's sum.  Optional per-quartet outputs, written for the LAST
- * candidate at the quartet's ORIGINAL index: expcf [nq][3] in data order, logpl [nq], deltacf [nq].
+ * Thread per quartet (sorted order), P <= QK_MAXP candidates: the HBM-bound path of a single objective
+ * call, as ONE persistent kernel:
+ *   prologue : every block expands x into xf (snaq_expand_row) in shared memory
+ *   main loop: tiles of BLOCK quartets, statically strided over the grid; the weights (32 B per quartet)
+ *              and the programs (contiguous in the class-sorted table) of the next tiles arrive by TMA bulk
+ *              copies into a ring of shared-memory stages while the current tile is computed (one
+ *              mbarrier per stage).  Tiles that lie entirely in the one-chunk class-A region run
+ *              straight-line code; the others run the generic evaluator on the staged programs.
+ *   epilogue : the block's sums go to partial[block][p]; the last block to finish (atomic ticket) adds
+ *              all partials in a fixed order and writes out[p] = -sum (deterministic)
+ * OUT: per-quartet results of the LAST candidate at the quartet's ORIGINAL index (expcf [nq][3] in
+ * data order, logpl [nq], deltacf [nq]).
  */
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_eval_quartets(const uint32_t *__restrict__ off, const uint16_t *__restrict__ prog,
-                                                        const uint8_t *__restrict__ qhdr, const uint32_t *__restrict__ perm,
-                                                        const double *__restrict__ W, const double *__restrict__ obs,
-                                                        int64_t nq, int64_t nA, const double *__restrict__ XF,
-                                                        int n_full, int P, double *__restrict__ partial,
-                                                        double *__restrict__ expcf, double *__restrict__ logpl,
-                                                        double *__restrict__ deltacf, uint32_t *__restrict__ status) {
+template <int BLOCK, bool OUT>
+__global__ void __launch_bounds__(BLOCK, 4) k_eval_quartets(SnaqTables T, const uint32_t *__restrict__ off,
+                                                           const uint16_t *__restrict__ prog, const uint8_t *__restrict__ qhdr,
+                                                           const uint32_t *__restrict__ perm, const double *__restrict__ W,
+                                                           const double *__restrict__ obs, int64_t nq, int64_t nA1, int64_t nA,
+                                                           const double *__restrict__ X, const double *__restrict__ xconst,
+                                                           int nh, int nt, int P, int stage_chunks, double *__restrict__ partial,
+                                                           double *__restrict__ out, unsigned int *__restrict__ ticket,
+                                                           double *__restrict__ expcf, double *__restrict__ logpl,
+                                                           double *__restrict__ deltacf, uint32_t *__restrict__ status) {
+    constexpr int TILE = BLOCK;
+    constexpr int NST = QK_STAGES;
     extern __shared__ __align__(128) unsigned char smem[];
-    const int xstride = n_full;
     double *mt = reinterpret_cast<double *>(smem);                 // 48 doubles, 128-byte aligned
-    double *red = mt + SNAQ_MATH_DOUBLES;                          // [BLOCK/32]
-    double *xs = red + BLOCK / 32;                                 // [P][n_full]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 384);      // NST mbarriers
+    double4 *sW = reinterpret_cast<double4 *>(smem + 512);         // [NST][TILE] weights           <- TMA bulk copies
+    uint2 *sP = reinterpret_cast<uint2 *>(smem + 512 + (size_t)NST * TILE * 32);   // [NST][stage_chunks+2] program chunks
+    double *red = reinterpret_cast<double *>(smem + 512 + (size_t)NST * TILE * 32 + (size_t)NST * (stage_chunks + 2) * 8);
+    double *sacc = red + BLOCK / 32;                               // [QK_MAXP] block sums
+    double *xs = sacc + QK_MAXP;                                   // [P][n_full]
     const int tid = threadIdx.x;
+    const int n_full = T.n_full;
     unsigned st = 0;
-    for (int idx = tid; idx < P * xstride; idx += BLOCK) xs[idx] = XF[idx];
+    const int64_t ntiles = (nq + TILE - 1) / TILE;
+    const uint2 *prog2 = reinterpret_cast<const uint2 *>(prog);
+    auto issue = [&](int64_t tile, int s) {                        // thread 0 only
+        const int64_t ibase = tile * TILE;
+        const int nloc = (int)min((int64_t)TILE, nq - ibase);
+        const bool a1 = (ibase + nloc <= nA1);                     // one-chunk region: off[i] == i, no dependent load
+        const uint32_t c0 = a1 ? (uint32_t)ibase : off[ibase], c1 = a1 ? (uint32_t)(ibase + nloc) : off[ibase + nloc];
+        const uint32_t c16 = c0 & ~1u;                             // bulk copies need 16-byte alignment
+        const unsigned wbytes = (unsigned)nloc * 32u;
+        unsigned pbytes = ((c1 - c16) * 8u + 15u) & ~15u;
+        if (c1 - c16 > (uint32_t)stage_chunks) pbytes = 0;        // oversized tile: programs are read from global memory
+        mbar_expect_tx(&bar[s], wbytes + pbytes);
+        tma_load_1d(sW + (size_t)s * TILE, W + (size_t)ibase * 4, wbytes, &bar[s]);
+        if (pbytes) tma_load_1d(sP + (size_t)s * (stage_chunks + 2), prog2 + c16, pbytes, &bar[s]);
+    };
+    if (tid == 0) for (int k = 0; k < NST; k++) mbar_init(&bar[k], 1);
     const SnaqMath M = load_math_tables(mt, tid);
+    if (tid < QK_MAXP) sacc[tid] = 0.0;
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * BLOCK + tid;
-    const bool active = i < nq;
-    const uint16_t *pc = nullptr;
-    int nwords = 0;
-    unsigned hdr = 0;
-    double w[4] = {0, 0, 0, 0};
-    if (active) {
-        const uint32_t o0 = off[i], o1 = off[i + 1];
-        pc = prog + (size_t)o0 * 4;
-        nwords = (int)(o1 - o0) * 4;
-        const double4 w4 = reinterpret_cast<const double4 *>(W)[i];
-        w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
-        hdr = (i < nA) ? 0u : (unsigned)qhdr[i];      // class A needs nothing from its header here
+    if (tid == 0)
+        for (int k = 0; k < NST - 1; k++)
+            if ((int64_t)blockIdx.x + (int64_t)k * gridDim.x < ntiles) issue((int64_t)blockIdx.x + (int64_t)k * gridDim.x, k);
+    // prologue: expanded parameter vectors of the P candidates (and the bounds check of update!)
+    for (int idx = tid; idx < P * n_full; idx += BLOCK) {
+        const int p = idx / n_full, row = idx - p * n_full;
+        const double *x = X + (size_t)p * T.nparams;
+        if (row < T.nparams) st |= range_check(x[row], (row >= nh && row < nh + nt) ? 1.0e300 : 1.0);
+        xs[idx] = snaq_expand_row(T, M, x, xconst, row);
     }
-    const bool want_out = expcf || logpl || deltacf;
+    __syncthreads();
+    auto write_out = [&](int64_t i, const double cf[3], double lik, const double4 &w4) {
+        const unsigned h = (unsigned)qhdr[i];
+        const int64_t q = perm[i];
+        double e[3];
+        snaq_data_order(h, cf, e);
+        if (expcf) { expcf[3 * q] = e[0]; expcf[3 * q + 1] = e[1]; expcf[3 * q + 2] = e[2]; }
+        if (logpl) logpl[q] = lik;
+        if (deltacf) {   // calculateDeltaCF: src/pseudolik.jl:491-498 (0 for unsampled quartets, :514)
+            const bool smp = (w4.x != 0.0 || w4.y != 0.0 || w4.z != 0.0 || w4.w != 0.0);
+            const double d = fabs(obs[3 * q] - e[0]) + fabs(obs[3 * q + 1] - e[1]) + fabs(obs[3 * q + 2] - e[2]);
+            deltacf[q] = smp ? d : 0.0;
+        }
+    };
+    int it = 0;
+    double acc1 = 0.0;      // P == 1: thread-private sum over all tiles, reduced once at the end
 #pragma unroll 1
-    for (int p = 0; p < P; p++) {
-        double v = 0.0;
-        if (active) {
-            const XRow xf{xs + (size_t)p * xstride};
-            double cf[3], t1;
-            if (i < nA) {
-                double t = 0.0;
-                const uint2 *pp = reinterpret_cast<const uint2 *>(pc);
-                for (int c = 0; c < (nwords >> 2); c++) {
-                    const uint2 ww = pp[c];
-                    t += xf(ww.x & 0xffffu) - xf(ww.x >> 16);
-                    t += xf(ww.y & 0xffffu) - xf(ww.y >> 16);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        const int s = it % NST;
+        // the stage of tile it+NST-1 was last read in iteration it-1, which ended with a __syncthreads: refill it
+        if (tid == 0 && tile + (int64_t)(NST - 1) * gridDim.x < ntiles) issue(tile + (int64_t)(NST - 1) * gridDim.x, (it + NST - 1) % NST);
+        const int64_t ibase = tile * TILE;
+        const int nloc = (int)min((int64_t)TILE, nq - ibase);
+        const int64_t i = ibase + tid;
+        const bool active = tid < nloc;
+        const bool fast_tile = (ibase + nloc <= nA1);              // every program is one chunk and off[i] == i
+        uint32_t o0 = 0, o1 = 0, c0 = 0, c1 = 0;
+        if (!fast_tile) {
+            c0 = off[ibase]; c1 = off[ibase + nloc];
+            if (active) { o0 = off[i]; o1 = off[i + 1]; }
+        }
+        mbar_wait(&bar[s], (unsigned)((it / NST) & 1));
+        const double4 w4 = active ? sW[(size_t)s * TILE + tid] : make_double4(0, 0, 0, 0);
+        const uint2 *stage = sP + (size_t)s * (stage_chunks + 2);
+        if (fast_tile) {
+            const uint2 q2 = active ? stage[(ibase & 1) + tid] : make_uint2(0, 0);
+#pragma unroll 1
+            for (int p = 0; p < P; p++) {
+                const double *xp = xs + (size_t)p * n_full;
+                double v = 0.0;
+                if (active) {
+                    const double t1 = fmin((xp[q2.x & 0xffffu] - xp[q2.x >> 16]) + (xp[q2.y & 0xffffu] - xp[q2.y >> 16]), 10.0);
+                    const double y = snaq_exp(-t1, M);
+                    const double major = fma(SNAQ_K_M23, y, 1.0);
+                    v = fma(w4.x, snaq_log_pos(major, M), -fma(w4.y, t1 + SNAQ_K_LOG3, w4.w));
+                    if (OUT && p == P - 1) {
+                        const double cf[3] = {major, 1.0 / 3.0 * y, 1.0 / 3.0 * y};
+                        write_out(i, cf, v, w4);
+                    }
                 }
-                t1 = fmin(t, 10.0);
-                snaq_tree_cf(t1, M, cf);
-                v = fma(w[0], snaq_log_pos(cf[0], M), -fma(w[1], t1 + SNAQ_K_LOG3, w[3]));
-            } else {
-                snaq_eval_quartet(hdr, pc, nwords, xf, M, cf, &t1, st);
-                v = snaq_quartet_loglik(SNAQ_HDR_KIND(hdr), cf, t1, w, M, st);
+                if (P == 1) { acc1 += v; continue; }
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                if ((tid & 31) == 0) red[tid >> 5] = v;
+                __syncthreads();
+                if (tid == 0) {
+                    double ssum = 0.0;
+#pragma unroll
+                    for (int k = 0; k < BLOCK / 32; k++) ssum += red[k];
+                    sacc[p] += ssum;
+                }
+                __syncthreads();
             }
-            if (want_out && p == P - 1) {
-                const unsigned h = (unsigned)qhdr[i];
-                const int64_t q = perm[i];
-                double e[3];
-                snaq_data_order(h, cf, e);
-                if (expcf) { expcf[3 * q] = e[0]; expcf[3 * q + 1] = e[1]; expcf[3 * q + 2] = e[2]; }
-                if (logpl) logpl[q] = v;
-                if (deltacf) {   // calculateDeltaCF: src/pseudolik.jl:491-498 (0 for unsampled quartets, :514)
-                    const bool smp = (w[0] != 0.0 || w[1] != 0.0 || w[2] != 0.0 || w[3] != 0.0);
-                    double d = fabs(obs[3 * q] - e[0]) + fabs(obs[3 * q + 1] - e[1]) + fabs(obs[3 * q + 2] - e[2]);
-                    deltacf[q] = smp ? d : 0.0;
+        } else {
+            const bool staged = (c1 - (c0 & ~1u)) <= (uint32_t)stage_chunks;
+            const uint16_t *pc = staged ? reinterpret_cast<const uint16_t *>(stage + (o0 - (c0 & ~1u)))
+                                        : prog + (size_t)o0 * 4;
+            const unsigned hdr = (active && i >= nA) ? (unsigned)qhdr[i] : 0u;
+            const double w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll 1
+            for (int p = 0; p < P; p++) {
+                const XRow xf{xs + (size_t)p * n_full};
+                double v = 0.0;
+                if (active) {
+                    double cf[3], t1;
+                    snaq_eval_quartet(hdr, pc, (int)(o1 - o0) * 4, xf, M, cf, &t1, st);
+                    v = snaq_quartet_loglik(SNAQ_HDR_KIND(hdr), cf, t1, w, M, st);
+                    if (OUT && p == P - 1) write_out(i, cf, v, w4);
                 }
+                if (P == 1) { acc1 += v; continue; }
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                if ((tid & 31) == 0) red[tid >> 5] = v;
+                __syncthreads();
+                if (tid == 0) {
+                    double ssum = 0.0;
+#pragma unroll
+                    for (int k = 0; k < BLOCK / 32; k++) ssum += red[k];
+                    sacc[p] += ssum;
+                }
+                __syncthreads();
             }
         }
-        // fixed-order block reduction
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if ((tid & 31) == 0) red[tid >> 5] = v;
+        if (P == 1) __syncthreads();      // every thread is done with stage s before it is refilled
+    }
+    if (P == 1) {
+        for (int o = 16; o > 0; o >>= 1) acc1 += __shfl_down_sync(0xffffffffu, acc1, o);
+        if ((tid & 31) == 0) red[tid >> 5] = acc1;
         __syncthreads();
         if (tid == 0) {
-            double s = 0.0;
+            double ssum = 0.0;
 #pragma unroll
-            for (int k = 0; k < BLOCK / 32; k++) s += red[k];
-            partial[(size_t)blockIdx.x * P + p] = s;
+            for (int k = 0; k < BLOCK / 32; k++) ssum += red[k];
+            sacc[0] = ssum;
         }
         __syncthreads();
     }
     if (st) atomicOr(status, st);
+    // epilogue: publish this block's sums; the last block adds all of them in block order
+    if (tid < P) partial[(size_t)blockIdx.x * P + tid] = sacc[tid];
+    __threadfence();
+    __shared__ unsigned int s_last;
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (int p = 0; p < P; p++) {
+            double sp = 0.0;
+            for (int b = tid; b < (int)gridDim.x; b += BLOCK) sp += __ldcg(partial + (size_t)b * P + p);
+            for (int o = 16; o > 0; o >>= 1) sp += __shfl_down_sync(0xffffffffu, sp, o);
+            if ((tid & 31) == 0) red[tid >> 5] = sp;
+            __syncthreads();
+            if (tid == 0) {
+                double tot = 0.0;
+#pragma unroll
+                for (int k = 0; k < BLOCK / 32; k++) tot += red[k];
+                out[p] = -tot;
+            }
+            __syncthreads();
+        }
+        if (tid == 0) *ticket = 0u;
+    }
 }
 
-// out[p] = -(sum over blocks of partial[b][p]), fixed order (logPseudoLik(d): src/pseudolik.jl:1417-1423)
+// out[p] = -(sum over blocks of partial[b][p]), fixed order (logPseudoLik(d): src/pseudolik.jl:1417-1423).
+// One block per candidate: 256 threads stride over the per-block partial sums with 4 independent
+// accumulators each, then a fixed-order shuffle / shared-memory tree.
 __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restrict__ partial, int nblocks, int stride, int P,
                                                          double *__restrict__ out) {
-    // one warp per candidate: lanes stride over the blocks, then a shuffle tree
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= P) return;
-    double s = 0.0;
-    for (int b = lane; b < nblocks; b += 32) s += partial[(size_t)b * stride + warp];
+    const int p = blockIdx.x, tid = threadIdx.x;
+    if (p >= P) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int b = tid;
+    for (; b + 768 < nblocks; b += 1024) {
+        s0 += partial[(size_t)b * stride + p];
+        s1 += partial[(size_t)(b + 256) * stride + p];
+        s2 += partial[(size_t)(b + 512) * stride + p];
+        s3 += partial[(size_t)(b + 768) * stride + p];
+    }
+    for (; b < nblocks; b += 256) s0 += partial[(size_t)b * stride + p];
+    double s = (s0 + s1) + (s2 + s3);
+    __shared__ double red[8];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (lane == 0) out[warp] = -s;
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) out[p] = -(((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7])));
 }
 // transposed variant for the lanes kernel (candidates contiguous): thread per candidate, coalesced
 __global__ void __launch_bounds__(256) k_reduce_partials_t(const double *__restrict__ partial, int nblocks, int stride, int P,
@@ -614,8 +745,9 @@ struct snaq_ctx {
     uint8_t *d_qhdr = nullptr;            // [nq] header bytes, sorted order
     uint32_t *d_len4 = nullptr, *d_iota = nullptr;   // [nq] scratch of the build
     uint8_t *d_cls = nullptr, *d_cls_sorted = nullptr;
-    int64_t nA = 0, nB = 0, nC = 0;
+    int64_t nA1 = 0, nA = 0, nB = 0, nC = 0;   // nA1: leading class-A quartets whose program is exactly one chunk (off[i] == i)
     uint32_t *d_status = nullptr;          // [0] build, [1] eval
+    unsigned int *d_ticket = nullptr;      // last-block ticket of k_eval_quartets (reset by the kernel)
     unsigned long long *d_total = nullptr; // build statistics: total chunks, max chunks, class counts
     void *d_scan_tmp = nullptr;
     size_t scan_tmp_cap = 0;
@@ -626,6 +758,7 @@ struct snaq_ctx {
     double *d_partial = nullptr; size_t partial_cap = 0;
     double *h_pin = nullptr; size_t pin_cap = 0;
     int sm_count = 148;
+    int qk_items = 1;                     // quartets per thread of k_eval_quartets (SNAQ_QK_ITEMS = 1, 2 or 4)
     int lanes_warps = 8;                  // warps per block of k_eval_lanes (SNAQ_LANES_WARPS = 8, 12 or 16)
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -691,6 +824,46 @@ static int run_weights(snaq_ctx *ctx) {
     return SNAQ_OK;
 }
 
+static int eval_quartets_launch(snaq_ctx *ctx, int P, const double *dX, double *dout, cudaStream_t stream, double *expcf,
+                                double *logpl, double *deltacf) {
+    const SnaqHostTables &H = ctx->H;
+    const int64_t nq = ctx->nq;
+    const bool per_quartet = expcf || logpl || deltacf;
+    constexpr int BLOCK = 256, TILE = BLOCK;
+    const int64_t ntiles = (nq + TILE - 1) / TILE;
+    // program chunks staged per tile: 3 per quartet covers almost every tile; bigger tiles read from global memory
+    const int stage_chunks = TILE * (int)std::min<uint32_t>(std::max<uint32_t>(ctx->maxlen, 1u), 3u);
+    for (int p0 = 0; p0 < P; p0 += QK_MAXP) {
+        const int Pc = std::min(QK_MAXP, P - p0);
+        const size_t smem = 512 + (size_t)QK_STAGES * TILE * 32 + (size_t)QK_STAGES * (stage_chunks + 2) * 8 + (BLOCK / 32) * 8 +
+                            QK_MAXP * 8 + (size_t)Pc * H.n_full * 8 + 16;
+        if (smem > 200 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_quartets"; return SNAQ_EINVAL; }
+        int per_sm = (int)std::min<size_t>(4, (200 * 1024) / smem);
+        if (per_sm < 1) per_sm = 1;
+        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * per_sm);
+        int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)grid * Pc);
+        if (rc) return rc;
+        const bool last = (p0 + Pc == P);
+        if (last && per_quartet) {
+            CK(cudaFuncSetAttribute(k_eval_quartets<BLOCK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_eval_quartets<BLOCK, true><<<grid, BLOCK, smem, stream>>>(
+                ctx->T, ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_perm, ctx->d_W, ctx->d_obs, nq, ctx->nA1, ctx->nA,
+                dX + (size_t)p0 * H.nparams, ctx->d_xconst, H.nh, H.nt, Pc, stage_chunks, ctx->d_partial, dout + p0, ctx->d_ticket,
+                expcf, logpl, deltacf, ctx->d_status + 1);
+        } else {
+            CK(cudaFuncSetAttribute(k_eval_quartets<BLOCK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_eval_quartets<BLOCK, false><<<grid, BLOCK, smem, stream>>>(
+                ctx->T, ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_perm, ctx->d_W, ctx->d_obs, nq, ctx->nA1, ctx->nA,
+                dX + (size_t)p0 * H.nparams, ctx->d_xconst, H.nh, H.nt, Pc, stage_chunks, ctx->d_partial, dout + p0, ctx->d_ticket,
+                nullptr, nullptr, nullptr, ctx->d_status + 1);
+        }
+        CK(cudaGetLastError());
+        ctx->counters[0] += 1;
+        ctx->counters[1] += nq * (int64_t)Pc;
+    }
+    return SNAQ_OK;
+}
+
 // dispatch one evaluation of P candidates whose X is already on the device
 static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cudaStream_t stream,
                        double *expcf, double *logpl, double *deltacf) {
@@ -699,17 +872,15 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
     if (nq == 0) { CK(cudaMemsetAsync(dout, 0, sizeof(double) * P, stream)); return SNAQ_OK; }
     const bool per_quartet = expcf || logpl || deltacf;
     const bool use_lanes = P >= LANES_MIN_P && !per_quartet;
-    {
-        const int Prows = use_lanes ? ((P + 31) & ~31) : P;
-        int rc = ensure(ctx, ctx->d_XF, ctx->XF_cap, (size_t)Prows * H.n_full);
-        if (rc) return rc;
-        const int64_t tot = (int64_t)Prows * H.n_full;
-        k_expand_x<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(ctx->T, dX, ctx->d_xconst, P, H.nh, H.nt, use_lanes ? 1 : 0,
-                                                                      ctx->d_XF, ctx->d_status + 1);
-        CK(cudaGetLastError());
-    }
-    const double *dXF = ctx->d_XF;
     if (use_lanes) {
+        const int Prows = (P + 31) & ~31;
+        int rc0 = ensure(ctx, ctx->d_XF, ctx->XF_cap, (size_t)Prows * H.n_full);
+        if (rc0) return rc0;
+        const int64_t tot = (int64_t)Prows * H.n_full;
+        k_expand_x<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(ctx->T, dX, ctx->d_xconst, P, H.nh, H.nt, 1, ctx->d_XF,
+                                                                      ctx->d_status + 1);
+        CK(cudaGetLastError());
+        const double *dXF = ctx->d_XF;
         const int ngroups = (P + 31) / 32, Ppad = ngroups * 32;
         // chunk: quartets per block.  Enough blocks to fill the machine, bounded by shared memory.
         const int warps = ctx->lanes_warps;
@@ -719,7 +890,7 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
         const size_t smem = lanes_smem_layout(H.n_full, chunk, warps, ctx->maxlen).total;
         if (smem > 227 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_lanes"; return SNAQ_EINVAL; }
         ClassRanges cr;
-        cr.nA = ctx->nA; cr.nB = ctx->nB; cr.nC = ctx->nC;
+        cr.nA1 = ctx->nA1; cr.nA = ctx->nA; cr.nB = ctx->nB; cr.nC = ctx->nC;
         cr.chA = (int)((cr.nA + chunk - 1) / chunk); cr.chB = (int)((cr.nB + chunk - 1) / chunk); cr.chC = (int)((cr.nC + chunk - 1) / chunk);
         const int64_t nchunks = (int64_t)cr.chA + cr.chB + cr.chC;
         if (nchunks > 2147483647LL || ngroups > 65535) { ctx->err = "batch too large for one launch"; return SNAQ_EINVAL; }
@@ -744,27 +915,7 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
         return SNAQ_OK;
     }
     // small batches: thread per quartet, QK_MAXP candidates per launch
-    constexpr int BLOCK = 256;
-    const int64_t nblocks = (nq + BLOCK - 1) / BLOCK;
-    for (int p0 = 0; p0 < P; p0 += QK_MAXP) {
-        const int Pc = std::min(QK_MAXP, P - p0);
-        int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)nblocks * Pc);
-        if (rc) return rc;
-        const size_t smem = (size_t)Pc * H.n_full * 8 + (BLOCK / 32) * 8 + SNAQ_MATH_DOUBLES * 8 + 16;
-        if (smem > 200 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_quartets"; return SNAQ_EINVAL; }
-        CK(cudaFuncSetAttribute(k_eval_quartets<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const bool last = (p0 + Pc == P);
-        k_eval_quartets<BLOCK><<<(unsigned)nblocks, BLOCK, smem, stream>>>(
-            ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_perm, ctx->d_W, ctx->d_obs, nq, ctx->nA, dXF + (size_t)p0 * H.n_full,
-            H.n_full, Pc, ctx->d_partial, last ? expcf : nullptr, last ? logpl : nullptr, last ? deltacf : nullptr,
-            ctx->d_status + 1);
-        CK(cudaGetLastError());
-        k_reduce_partials<<<(Pc * 32 + 255) / 256, 256, 0, stream>>>(ctx->d_partial, (int)nblocks, Pc, Pc, dout + p0);
-        CK(cudaGetLastError());
-        ctx->counters[0] += 1;
-        ctx->counters[1] += nq * (int64_t)Pc;
-    }
-    return SNAQ_OK;
+    return eval_quartets_launch(ctx, P, dX, dout, stream, expcf, logpl, deltacf);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -805,10 +956,13 @@ int snaq_create(const snaq_opts *opts, snaq_ctx **out) {
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, ctx->device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char *ev = getenv("SNAQ_QK_ITEMS")) { int v = atoi(ev); if (v == 1 || v == 2 || v == 4) ctx->qk_items = v; }
     if (const char *ev = getenv("SNAQ_LANES_WARPS")) { int v = atoi(ev); if (v == 8 || v == 12 || v == 16) ctx->lanes_warps = v; }
     if ((e = cudaMalloc((void **)&ctx->d_status, 4 * sizeof(uint32_t))) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cudaMalloc((void **)&ctx->d_total, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
     cudaMemset(ctx->d_status, 0, 4 * sizeof(uint32_t));
+    if ((e = cudaMalloc((void **)&ctx->d_ticket, sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMalloc");
+    cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int));
     *out = ctx;
     return SNAQ_OK;
 }
@@ -818,7 +972,7 @@ int snaq_destroy(snaq_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_blob); cudaFree(ctx->d_xconst);
-    cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_status); cudaFree(ctx->d_total);
+    cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_status); cudaFree(ctx->d_total); cudaFree(ctx->d_ticket);
     cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_XF); cudaFree(ctx->d_out); cudaFree(ctx->d_partial);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_qhdr); cudaFree(ctx->d_len4); cudaFree(ctx->d_iota); cudaFree(ctx->d_cls);
     cudaFree(ctx->d_cls_sorted);
@@ -923,7 +1077,7 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
     const int64_t nq = ctx->nq;
     ctx->prog_words = 0;
     ctx->maxlen = 1;
-    ctx->nA = ctx->nB = ctx->nC = 0;
+    ctx->nA1 = ctx->nA = ctx->nB = ctx->nC = 0;
     if (nq > 0) {
         // pass 1: program length (4-word chunks) and class of every quartet, original order
         CK(cudaMemsetAsync(ctx->d_total, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -932,7 +1086,7 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
         k_build_count<<<(unsigned)nb, 128, 0, ctx->stream>>>(ctx->T, ctx->d_taxa, nq, ctx->d_len4, ctx->d_cls, ctx->d_iota,
                                                             ctx->d_total, ctx->d_status);
         CK(cudaGetLastError());
-        unsigned long long stt[5] = {0, 0, 0, 0, 0};
+        unsigned long long stt[6] = {0, 0, 0, 0, 0, 0};
         uint32_t st[4];
         CK(cudaMemcpyAsync(stt, ctx->d_total, sizeof(stt), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(st, ctx->d_status, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
@@ -941,7 +1095,8 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
         if (stt[0] >= 0xFFFFFFFFull) { ctx->err = "descriptor table exceeds 2^32 chunks on one GPU: shard the quartets (world_size>1)"; return SNAQ_EINVAL; }
         ctx->prog_words = stt[0] * 4;
         ctx->maxlen = (uint32_t)stt[1];
-        ctx->nA = (int64_t)stt[2]; ctx->nB = (int64_t)stt[3]; ctx->nC = (int64_t)stt[4];
+        ctx->nA1 = (int64_t)stt[2];
+        ctx->nA = (int64_t)(stt[2] + stt[3]); ctx->nB = (int64_t)stt[4]; ctx->nC = (int64_t)stt[5];
         // stable sort of the quartet indices by class (2-bit keys): perm = sorted position -> original quartet
         size_t tmp = 0, tmp2 = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_cls, ctx->d_cls_sorted, ctx->d_iota, ctx->d_perm, nq, 0, 2, ctx->stream));
