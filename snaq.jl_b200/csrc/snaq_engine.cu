@@ -470,74 +470,74 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
 
 /*
  * Thread per quartet (sorted order), P <= QK_MAXP candidates: the HBM-bound path of a single objective
- * call, as ONE persistent kernel:
+ * call.  Persistent blocks; two instantiations share the partial buffer and the completion ticket:
+ *   GENERIC=false : the class-A region [0,nA): additive programs only (lean code, 4 blocks per SM)
+ *   GENERIC=true  : the rest (type-2/4 terms, 4-cycles) through the generic evaluator
  *   prologue : every block expands x into xf (snaq_expand_row) in shared memory
  *   main loop: tiles of BLOCK quartets, statically strided over the grid; the weights (32 B per quartet)
  *              and the programs (contiguous in the class-sorted table) of the next tiles arrive by TMA bulk
  *              copies into a ring of shared-memory stages while the current tile is computed (one
- *              mbarrier per stage).  Tiles that lie entirely in the one-chunk class-A region run
- *              straight-line code; the others run the generic evaluator on the staged programs.
- *   epilogue : the block's sums go to partial[block][p]; the last block to finish (atomic ticket) adds
- *              all partials in a fixed order and writes out[p] = -sum (deterministic)
+ *              mbarrier per stage)
+ *   epilogue : the block's sums go to partial[block][p]; the last block of the last instantiation to
+ *              finish (atomic ticket) adds all partials in a fixed order and writes out[p] = -sum
  * OUT: per-quartet results of the LAST candidate at the quartet's ORIGINAL index (expcf [nq][3] in
  * data order, logpl [nq], deltacf [nq]).
  */
-template <int BLOCK, bool OUT>
-__global__ void __launch_bounds__(BLOCK, 4) k_eval_quartets(SnaqTables T, const uint32_t *__restrict__ off,
-                                                           const uint16_t *__restrict__ prog, const uint8_t *__restrict__ qhdr,
-                                                           const uint32_t *__restrict__ perm, const double *__restrict__ W,
-                                                           const double *__restrict__ obs, int64_t nq, int64_t nA1, int64_t nA,
-                                                           const double *__restrict__ X, const double *__restrict__ xconst,
-                                                           int nh, int nt, int P, int stage_chunks, double *__restrict__ partial,
-                                                           double *__restrict__ out, unsigned int *__restrict__ ticket,
-                                                           double *__restrict__ expcf, double *__restrict__ logpl,
-                                                           double *__restrict__ deltacf, uint32_t *__restrict__ status) {
+template <int BLOCK, bool GENERIC, bool OUT>
+__global__ void __launch_bounds__(BLOCK, GENERIC ? 2 : 4)
+k_eval_quartets(SnaqTables T, const uint32_t *__restrict__ off, const uint16_t *__restrict__ prog, const uint8_t *__restrict__ qhdr,
+                const uint32_t *__restrict__ perm, const double *__restrict__ W, const double *__restrict__ obs, uint32_t qlo,
+                uint32_t qhi, uint32_t nA1, const double *__restrict__ X, const double *__restrict__ xconst, int nh, int nt, int P,
+                int stage_chunks, double *__restrict__ partial, unsigned pbase, unsigned nblocks_total, double *__restrict__ out,
+                unsigned int *__restrict__ ticket, double *__restrict__ expcf, double *__restrict__ logpl,
+                double *__restrict__ deltacf, uint32_t *__restrict__ status) {
     constexpr int TILE = BLOCK;
     constexpr int NST = QK_STAGES;
     extern __shared__ __align__(128) unsigned char smem[];
     double *mt = reinterpret_cast<double *>(smem);                 // 48 doubles, 128-byte aligned
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 384);      // NST mbarriers
     double4 *sW = reinterpret_cast<double4 *>(smem + 512);         // [NST][TILE] weights           <- TMA bulk copies
+    const unsigned stage_stride = (unsigned)stage_chunks + 2u;
     uint2 *sP = reinterpret_cast<uint2 *>(smem + 512 + (size_t)NST * TILE * 32);   // [NST][stage_chunks+2] program chunks
-    double *red = reinterpret_cast<double *>(smem + 512 + (size_t)NST * TILE * 32 + (size_t)NST * (stage_chunks + 2) * 8);
+    double *red = reinterpret_cast<double *>(smem + 512 + (size_t)NST * TILE * 32 + (size_t)NST * stage_stride * 8);
     double *sacc = red + BLOCK / 32;                               // [QK_MAXP] block sums
     double *xs = sacc + QK_MAXP;                                   // [P][n_full]
-    const int tid = threadIdx.x;
+    const unsigned tid = threadIdx.x;
     const int n_full = T.n_full;
     unsigned st = 0;
-    const int64_t ntiles = (nq + TILE - 1) / TILE;
+    const unsigned ntiles = (qhi - qlo + TILE - 1) / TILE;
     const uint2 *prog2 = reinterpret_cast<const uint2 *>(prog);
-    auto issue = [&](int64_t tile, int s) {                        // thread 0 only
-        const int64_t ibase = tile * TILE;
-        const int nloc = (int)min((int64_t)TILE, nq - ibase);
+    auto issue = [&](unsigned tile, unsigned s) {                  // thread 0 only
+        const unsigned ibase = qlo + tile * TILE;
+        const unsigned nloc = min((unsigned)TILE, qhi - ibase);
         const bool a1 = (ibase + nloc <= nA1);                     // one-chunk region: off[i] == i, no dependent load
-        const uint32_t c0 = a1 ? (uint32_t)ibase : off[ibase], c1 = a1 ? (uint32_t)(ibase + nloc) : off[ibase + nloc];
+        const uint32_t c0 = a1 ? ibase : off[ibase], c1 = a1 ? ibase + nloc : off[ibase + nloc];
         const uint32_t c16 = c0 & ~1u;                             // bulk copies need 16-byte alignment
-        const unsigned wbytes = (unsigned)nloc * 32u;
+        const unsigned wbytes = nloc * 32u;
         unsigned pbytes = ((c1 - c16) * 8u + 15u) & ~15u;
         if (c1 - c16 > (uint32_t)stage_chunks) pbytes = 0;        // oversized tile: programs are read from global memory
         mbar_expect_tx(&bar[s], wbytes + pbytes);
         tma_load_1d(sW + (size_t)s * TILE, W + (size_t)ibase * 4, wbytes, &bar[s]);
-        if (pbytes) tma_load_1d(sP + (size_t)s * (stage_chunks + 2), prog2 + c16, pbytes, &bar[s]);
+        if (pbytes) tma_load_1d(sP + (size_t)s * stage_stride, prog2 + c16, pbytes, &bar[s]);
     };
     if (tid == 0) for (int k = 0; k < NST; k++) mbar_init(&bar[k], 1);
-    const SnaqMath M = load_math_tables(mt, tid);
+    const SnaqMath M = load_math_tables(mt, (int)tid);
     if (tid < QK_MAXP) sacc[tid] = 0.0;
     __syncthreads();
     if (tid == 0)
-        for (int k = 0; k < NST - 1; k++)
-            if ((int64_t)blockIdx.x + (int64_t)k * gridDim.x < ntiles) issue((int64_t)blockIdx.x + (int64_t)k * gridDim.x, k);
+        for (unsigned k = 0; k < NST - 1; k++)
+            if (blockIdx.x + k * gridDim.x < ntiles) issue(blockIdx.x + k * gridDim.x, k);
     // prologue: expanded parameter vectors of the P candidates (and the bounds check of update!)
-    for (int idx = tid; idx < P * n_full; idx += BLOCK) {
+    for (int idx = (int)tid; idx < P * n_full; idx += BLOCK) {
         const int p = idx / n_full, row = idx - p * n_full;
         const double *x = X + (size_t)p * T.nparams;
         if (row < T.nparams) st |= range_check(x[row], (row >= nh && row < nh + nt) ? 1.0e300 : 1.0);
         xs[idx] = snaq_expand_row(T, M, x, xconst, row);
     }
     __syncthreads();
-    auto write_out = [&](int64_t i, const double cf[3], double lik, const double4 &w4) {
+    auto write_out = [&](unsigned i, const double cf[3], double lik, const double4 &w4) {
         const unsigned h = (unsigned)qhdr[i];
-        const int64_t q = perm[i];
+        const size_t q = perm[i];
         double e[3];
         snaq_data_order(h, cf, e);
         if (expcf) { expcf[3 * q] = e[0]; expcf[3 * q + 1] = e[1]; expcf[3 * q + 2] = e[2]; }
@@ -548,34 +548,54 @@ __global__ void __launch_bounds__(BLOCK, 4) k_eval_quartets(SnaqTables T, const 
             deltacf[q] = smp ? d : 0.0;
         }
     };
-    int it = 0;
+    auto tile_reduce = [&](double v, int p) {                      // fixed-order block reduction of one tile
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        __syncthreads();
+        if (tid == 0) {
+            double ssum = 0.0;
+#pragma unroll
+            for (int k = 0; k < BLOCK / 32; k++) ssum += red[k];
+            sacc[p] += ssum;
+        }
+        __syncthreads();
+    };
+    unsigned s = 0, s_next = NST - 1, phase = 0;
     double acc1 = 0.0;      // P == 1: thread-private sum over all tiles, reduced once at the end
 #pragma unroll 1
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-        const int s = it % NST;
-        // the stage of tile it+NST-1 was last read in iteration it-1, which ended with a __syncthreads: refill it
-        if (tid == 0 && tile + (int64_t)(NST - 1) * gridDim.x < ntiles) issue(tile + (int64_t)(NST - 1) * gridDim.x, (it + NST - 1) % NST);
-        const int64_t ibase = tile * TILE;
-        const int nloc = (int)min((int64_t)TILE, nq - ibase);
-        const int64_t i = ibase + tid;
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // the stage s_next was last read in the previous iteration, which ended with a __syncthreads: refill it
+        if (tid == 0 && tile + (NST - 1) * gridDim.x < ntiles) issue(tile + (NST - 1) * gridDim.x, s_next);
+        const unsigned ibase = qlo + tile * TILE;
+        const unsigned nloc = min((unsigned)TILE, qhi - ibase);
+        const unsigned i = ibase + tid;
         const bool active = tid < nloc;
-        const bool fast_tile = (ibase + nloc <= nA1);              // every program is one chunk and off[i] == i
-        uint32_t o0 = 0, o1 = 0, c0 = 0, c1 = 0;
-        if (!fast_tile) {
+        uint32_t o0 = i, o1 = i + 1, c0 = ibase, c1 = ibase + nloc;
+        if (ibase + nloc > nA1) {                                  // tile-uniform
             c0 = off[ibase]; c1 = off[ibase + nloc];
             if (active) { o0 = off[i]; o1 = off[i + 1]; }
         }
-        mbar_wait(&bar[s], (unsigned)((it / NST) & 1));
+        const uint32_t c16 = c0 & ~1u;
+        const bool staged = (c1 - c16) <= (uint32_t)stage_chunks;
+        mbar_wait(&bar[s], phase);
         const double4 w4 = active ? sW[(size_t)s * TILE + tid] : make_double4(0, 0, 0, 0);
-        const uint2 *stage = sP + (size_t)s * (stage_chunks + 2);
-        if (fast_tile) {
-            const uint2 q2 = active ? stage[(ibase & 1) + tid] : make_uint2(0, 0);
+        const uint2 *pp = staged ? sP + (size_t)s * stage_stride + (o0 - c16) : prog2 + o0;
+        const unsigned nch = active ? o1 - o0 : 0u;
+        if (!GENERIC) {
 #pragma unroll 1
             for (int p = 0; p < P; p++) {
                 const double *xp = xs + (size_t)p * n_full;
                 double v = 0.0;
                 if (active) {
-                    const double t1 = fmin((xp[q2.x & 0xffffu] - xp[q2.x >> 16]) + (xp[q2.y & 0xffffu] - xp[q2.y >> 16]), 10.0);
+                    uint2 q2 = pp[0];
+                    double ta = xp[q2.x & 0xffffu] - xp[q2.x >> 16], tb = xp[q2.y & 0xffffu] - xp[q2.y >> 16];
+#pragma unroll 1
+                    for (unsigned c = 1; c < nch; c++) {
+                        q2 = pp[c];
+                        ta += xp[q2.x & 0xffffu] - xp[q2.x >> 16];
+                        tb += xp[q2.y & 0xffffu] - xp[q2.y >> 16];
+                    }
+                    const double t1 = fmin(ta + tb, 10.0);
                     const double y = snaq_exp(-t1, M);
                     const double major = fma(SNAQ_K_M23, y, 1.0);
                     v = fma(w4.x, snaq_log_pos(major, M), -fma(w4.y, t1 + SNAQ_K_LOG3, w4.w));
@@ -584,23 +604,10 @@ __global__ void __launch_bounds__(BLOCK, 4) k_eval_quartets(SnaqTables T, const 
                         write_out(i, cf, v, w4);
                     }
                 }
-                if (P == 1) { acc1 += v; continue; }
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-                if ((tid & 31) == 0) red[tid >> 5] = v;
-                __syncthreads();
-                if (tid == 0) {
-                    double ssum = 0.0;
-#pragma unroll
-                    for (int k = 0; k < BLOCK / 32; k++) ssum += red[k];
-                    sacc[p] += ssum;
-                }
-                __syncthreads();
+                if (P == 1) acc1 += v; else tile_reduce(v, p);
             }
         } else {
-            const bool staged = (c1 - (c0 & ~1u)) <= (uint32_t)stage_chunks;
-            const uint16_t *pc = staged ? reinterpret_cast<const uint16_t *>(stage + (o0 - (c0 & ~1u)))
-                                        : prog + (size_t)o0 * 4;
-            const unsigned hdr = (active && i >= nA) ? (unsigned)qhdr[i] : 0u;
+            const unsigned hdr = active ? (unsigned)qhdr[i] : 0u;
             const double w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll 1
             for (int p = 0; p < P; p++) {
@@ -608,50 +615,31 @@ __global__ void __launch_bounds__(BLOCK, 4) k_eval_quartets(SnaqTables T, const 
                 double v = 0.0;
                 if (active) {
                     double cf[3], t1;
-                    snaq_eval_quartet(hdr, pc, (int)(o1 - o0) * 4, xf, M, cf, &t1, st);
+                    snaq_eval_quartet(hdr, reinterpret_cast<const uint16_t *>(pp), (int)nch * 4, xf, M, cf, &t1, st);
                     v = snaq_quartet_loglik(SNAQ_HDR_KIND(hdr), cf, t1, w, M, st);
                     if (OUT && p == P - 1) write_out(i, cf, v, w4);
                 }
-                if (P == 1) { acc1 += v; continue; }
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-                if ((tid & 31) == 0) red[tid >> 5] = v;
-                __syncthreads();
-                if (tid == 0) {
-                    double ssum = 0.0;
-#pragma unroll
-                    for (int k = 0; k < BLOCK / 32; k++) ssum += red[k];
-                    sacc[p] += ssum;
-                }
-                __syncthreads();
+                if (P == 1) acc1 += v; else tile_reduce(v, p);
             }
         }
         if (P == 1) __syncthreads();      // every thread is done with stage s before it is refilled
+        s_next = s;
+        if (++s == NST) { s = 0; phase ^= 1u; }
     }
-    if (P == 1) {
-        for (int o = 16; o > 0; o >>= 1) acc1 += __shfl_down_sync(0xffffffffu, acc1, o);
-        if ((tid & 31) == 0) red[tid >> 5] = acc1;
-        __syncthreads();
-        if (tid == 0) {
-            double ssum = 0.0;
-#pragma unroll
-            for (int k = 0; k < BLOCK / 32; k++) ssum += red[k];
-            sacc[0] = ssum;
-        }
-        __syncthreads();
-    }
+    if (P == 1) { sacc[0] = 0.0; __syncthreads(); tile_reduce(acc1, 0); }
     if (st) atomicOr(status, st);
-    // epilogue: publish this block's sums; the last block adds all of them in block order
-    if (tid < P) partial[(size_t)blockIdx.x * P + tid] = sacc[tid];
+    // epilogue: publish this block's sums; the last block overall adds all of them in block order
+    if ((int)tid < P) partial[(size_t)(pbase + blockIdx.x) * P + tid] = sacc[tid];
     __threadfence();
     __shared__ unsigned int s_last;
     __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == nblocks_total - 1) ? 1u : 0u;
     __syncthreads();
     if (s_last) {
         __threadfence();
         for (int p = 0; p < P; p++) {
             double sp = 0.0;
-            for (int b = tid; b < (int)gridDim.x; b += BLOCK) sp += __ldcg(partial + (size_t)b * P + p);
+            for (unsigned b = tid; b < nblocks_total; b += BLOCK) sp += __ldcg(partial + (size_t)b * P + p);
             for (int o = 16; o > 0; o >>= 1) sp += __shfl_down_sync(0xffffffffu, sp, o);
             if ((tid & 31) == 0) red[tid >> 5] = sp;
             __syncthreads();
@@ -824,40 +812,55 @@ static int run_weights(snaq_ctx *ctx) {
     return SNAQ_OK;
 }
 
+template <bool GENERIC, bool OUT>
+static int launch_qk(snaq_ctx *ctx, int grid, size_t smem, cudaStream_t stream, uint32_t qlo, uint32_t qhi, const double *dX, int Pc,
+                     int stage_chunks, unsigned pbase, unsigned nblocks_total, double *dout, double *expcf, double *logpl,
+                     double *deltacf) {
+    const SnaqHostTables &H = ctx->H;
+    CK(cudaFuncSetAttribute(k_eval_quartets<256, GENERIC, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_eval_quartets<256, GENERIC, OUT><<<grid, 256, smem, stream>>>(
+        ctx->T, ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_perm, ctx->d_W, ctx->d_obs, qlo, qhi, (uint32_t)ctx->nA1, dX, ctx->d_xconst,
+        H.nh, H.nt, Pc, stage_chunks, ctx->d_partial, pbase, nblocks_total, dout, ctx->d_ticket, expcf, logpl, deltacf,
+        ctx->d_status + 1);
+    CK(cudaGetLastError());
+    return SNAQ_OK;
+}
+
 static int eval_quartets_launch(snaq_ctx *ctx, int P, const double *dX, double *dout, cudaStream_t stream, double *expcf,
                                 double *logpl, double *deltacf) {
     const SnaqHostTables &H = ctx->H;
     const int64_t nq = ctx->nq;
     const bool per_quartet = expcf || logpl || deltacf;
     constexpr int BLOCK = 256, TILE = BLOCK;
-    const int64_t ntiles = (nq + TILE - 1) / TILE;
     // program chunks staged per tile: 3 per quartet covers almost every tile; bigger tiles read from global memory
     const int stage_chunks = TILE * (int)std::min<uint32_t>(std::max<uint32_t>(ctx->maxlen, 1u), 3u);
+    const uint32_t nA = (uint32_t)ctx->nA, nQ = (uint32_t)nq;
     for (int p0 = 0; p0 < P; p0 += QK_MAXP) {
         const int Pc = std::min(QK_MAXP, P - p0);
         const size_t smem = 512 + (size_t)QK_STAGES * TILE * 32 + (size_t)QK_STAGES * (stage_chunks + 2) * 8 + (BLOCK / 32) * 8 +
                             QK_MAXP * 8 + (size_t)Pc * H.n_full * 8 + 16;
         if (smem > 200 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_quartets"; return SNAQ_EINVAL; }
-        int per_sm = (int)std::min<size_t>(4, (200 * 1024) / smem);
-        if (per_sm < 1) per_sm = 1;
-        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * per_sm);
-        int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)grid * Pc);
+        const int per_sm_a = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / smem));
+        const int per_sm_g = (int)std::max<size_t>(1, std::min<size_t>(2, (200 * 1024) / smem));
+        const int64_t tilesA = (nA + TILE - 1) / TILE, tilesG = (nQ - nA + TILE - 1) / TILE;
+        const int gridA = (int)std::min<int64_t>(tilesA, (int64_t)ctx->sm_count * per_sm_a);
+        const int gridG = (int)std::min<int64_t>(tilesG, (int64_t)ctx->sm_count * per_sm_g);
+        const unsigned nblocks_total = (unsigned)(gridA + gridG);
+        int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)nblocks_total * Pc);
         if (rc) return rc;
-        const bool last = (p0 + Pc == P);
-        if (last && per_quartet) {
-            CK(cudaFuncSetAttribute(k_eval_quartets<BLOCK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_eval_quartets<BLOCK, true><<<grid, BLOCK, smem, stream>>>(
-                ctx->T, ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_perm, ctx->d_W, ctx->d_obs, nq, ctx->nA1, ctx->nA,
-                dX + (size_t)p0 * H.nparams, ctx->d_xconst, H.nh, H.nt, Pc, stage_chunks, ctx->d_partial, dout + p0, ctx->d_ticket,
-                expcf, logpl, deltacf, ctx->d_status + 1);
-        } else {
-            CK(cudaFuncSetAttribute(k_eval_quartets<BLOCK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_eval_quartets<BLOCK, false><<<grid, BLOCK, smem, stream>>>(
-                ctx->T, ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_perm, ctx->d_W, ctx->d_obs, nq, ctx->nA1, ctx->nA,
-                dX + (size_t)p0 * H.nparams, ctx->d_xconst, H.nh, H.nt, Pc, stage_chunks, ctx->d_partial, dout + p0, ctx->d_ticket,
-                nullptr, nullptr, nullptr, ctx->d_status + 1);
+        const bool outp = (p0 + Pc == P) && per_quartet;
+        const double *dXp = dX + (size_t)p0 * H.nparams;
+        // the generic region first: it is the smaller, slower one and overlaps the tail of nothing otherwise
+        if (gridG > 0) {
+            rc = outp ? launch_qk<true, true>(ctx, gridG, smem, stream, nA, nQ, dXp, Pc, stage_chunks, (unsigned)gridA, nblocks_total, dout + p0, expcf, logpl, deltacf)
+                      : launch_qk<true, false>(ctx, gridG, smem, stream, nA, nQ, dXp, Pc, stage_chunks, (unsigned)gridA, nblocks_total, dout + p0, nullptr, nullptr, nullptr);
+            if (rc) return rc;
         }
-        CK(cudaGetLastError());
+        if (gridA > 0) {
+            rc = outp ? launch_qk<false, true>(ctx, gridA, smem, stream, 0, nA, dXp, Pc, stage_chunks, 0u, nblocks_total, dout + p0, expcf, logpl, deltacf)
+                      : launch_qk<false, false>(ctx, gridA, smem, stream, 0, nA, dXp, Pc, stage_chunks, 0u, nblocks_total, dout + p0, nullptr, nullptr, nullptr);
+            if (rc) return rc;
+        }
         ctx->counters[0] += 1;
         ctx->counters[1] += nq * (int64_t)Pc;
     }
