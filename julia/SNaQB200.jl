@@ -1,0 +1,123 @@
+# SNaQB200.jl — the shim a SNaQ.jl maintainer would add to route the quartet pseudolikelihood hot path
+# through libsnaqb200.so (include/snaq_b200.h).  NOT TESTED HERE: there is no Julia in the build image.
+# It touches nothing but the call sites listed in INTEGRATION.md; the public API (snaq!, optBL!,
+# topologyQpseudolik!, bootsnaq, readtableCF, DataCF, HybridNetwork) is unchanged.
+module SNaQB200
+
+using SNaQ, PhyloNetworks
+import SNaQ: istIdentifiable, fromBadDiamondI, inCycle, hasHybEdge, isBadDiamondI, isBadDiamondII, isBadTriangle,
+             gammaz, numBad, ht, numht, DataCF, Quartet
+
+const LIB = get(ENV, "SNAQ_B200_LIB", "libsnaqb200.so")
+
+struct FlatNet            # mirrors `snaq_flatnet` field for field
+    n_nodes::Cint; n_edges::Cint; n_hybrids::Cint; n_leaves::Cint
+    node_number::Ptr{Cint}; node_flags::Ptr{Cuint}; node_incycle::Ptr{Cint}; node_gammaz::Ptr{Cdouble}
+    node_taxon::Ptr{Cint}; node_edge::Ptr{Cint}
+    edge_number::Ptr{Cint}; edge_flags::Ptr{Cuint}; edge_incycle::Ptr{Cint}; edge_length::Ptr{Cdouble}
+    edge_gamma::Ptr{Cdouble}; edge_node::Ptr{Cint}
+    hybrid::Ptr{Cint}; leaf::Ptr{Cint}
+end
+struct Opts; device::Cint; rank::Cint; world_size::Cint; reserved::Cint; end
+
+mutable struct Engine
+    ctx::Ptr{Cvoid}
+    taxa::Vector{String}
+    nq::Int
+end
+
+check(e::Engine, rc) = rc == 0 || error(unsafe_string(ccall((:snaq_last_error, LIB), Cstring, (Ptr{Cvoid},), e.ctx)))
+
+"one engine per Julia worker process; worker i uses GPU (i-1) % ngpus (pmap over runs: src/snaq_optimization.jl:1681)"
+function Engine(d::DataCF; device::Integer = (Distributed.myid() - 1) % 8)
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:snaq_create, LIB), Cint, (Ref{Opts}, Ref{Ptr{Cvoid}}), Opts(device, 0, 1, 0), ctx)
+    rc == 0 || error(unsafe_string(ccall((:snaq_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    taxa = SNaQ.tiplabels(d)                               # src/readquartetdata.jl:440
+    tid = Dict(t => UInt16(i - 1) for (i, t) in enumerate(taxa))
+    qt = Matrix{UInt16}(undef, 4, d.numQuartets); obs = Matrix{Float64}(undef, 3, d.numQuartets)
+    for (j, q) in enumerate(d.quartet)
+        for i in 1:4 qt[i, j] = tid[q.taxon[i]] end
+        obs[:, j] = q.obsCF
+    end
+    e = Engine(ctx[], taxa, d.numQuartets)
+    check(e, ccall((:snaq_set_data, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{UInt16}, Ptr{Cdouble}),
+                   e.ctx, length(taxa), d.numQuartets, qt, obs))
+    finalizer(x -> ccall((:snaq_destroy, LIB), Cint, (Ptr{Cvoid},), x.ctx), e)
+    return e
+end
+
+"serialise exactly the fields the hot path reads (SURVEY.md App. B) in net.node / net.edge / node.edge order"
+function set_network!(e::Engine, net::HybridNetwork)
+    nidx = Dict(objectid(n) => Cint(i - 1) for (i, n) in enumerate(net.node))
+    eidx = Dict(objectid(ed) => Cint(i - 1) for (i, ed) in enumerate(net.edge))
+    tid = Dict(t => Cint(i - 1) for (i, t) in enumerate(e.taxa))
+    nn, ne = length(net.node), length(net.edge)
+    node_number = Cint[n.number for n in net.node]
+    node_flags = Cuint[(n.leaf ? 0x01 : 0) | (n.hybrid ? 0x02 : 0) | (hasHybEdge(n) ? 0x04 : 0) | (isBadDiamondI(n) ? 0x08 : 0) |
+                       (isBadDiamondII(n) ? 0x10 : 0) | (isBadTriangle(n) ? 0x20 : 0) for n in net.node]
+    node_incycle = Cint[inCycle(n) for n in net.node]
+    node_gammaz = Cdouble[gammaz(n) for n in net.node]
+    node_taxon = Cint[n.leaf ? tid[n.name] : -1 for n in net.node]
+    node_edge = fill(Cint(-1), 3, nn)
+    for (i, n) in enumerate(net.node), (j, ed) in enumerate(n.edge) node_edge[j, i] = eidx[objectid(ed)] end
+    edge_number = Cint[ed.number for ed in net.edge]
+    edge_flags = Cuint[(ed.hybrid ? 0x01 : 0) | (ed.ismajor ? 0x02 : 0) | (ed.ischild1 ? 0x04 : 0) |
+                       (istIdentifiable(ed) ? 0x08 : 0) | (fromBadDiamondI(ed) ? 0x10 : 0) for ed in net.edge]
+    edge_incycle = Cint[inCycle(ed) for ed in net.edge]
+    edge_length = Cdouble[ed.length for ed in net.edge]
+    edge_gamma = Cdouble[ed.gamma for ed in net.edge]
+    edge_node = Cint[nidx[objectid(ed.node[k])] for k in 1:2, ed in net.edge]
+    hyb = Cint[nidx[objectid(n)] for n in net.hybrid]
+    leaf = Cint[nidx[objectid(n)] for n in net.leaf]
+    GC.@preserve node_number node_flags node_incycle node_gammaz node_taxon node_edge edge_number edge_flags edge_incycle edge_length edge_gamma edge_node hyb leaf begin
+        f = FlatNet(nn, ne, length(hyb), length(leaf), pointer(node_number), pointer(node_flags), pointer(node_incycle),
+                    pointer(node_gammaz), pointer(node_taxon), pointer(node_edge), pointer(edge_number), pointer(edge_flags),
+                    pointer(edge_incycle), pointer(edge_length), pointer(edge_gamma), pointer(edge_node), pointer(hyb), pointer(leaf))
+        check(e, ccall((:snaq_set_network, LIB), Cint, (Ptr{Cvoid}, Ref{FlatNet}), e.ctx, f))
+    end
+end
+
+"objective value for one x (the body of `obj` in optBL!, src/snaq_optimization.jl:368-380)"
+function pseudodeviance(e::Engine, x::Vector{Float64})
+    out = Ref{Cdouble}(0.0)
+    check(e, ccall((:snaq_eval, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Ref{Cdouble}), e.ctx, 1, length(x), x, out))
+    return out[]
+end
+
+"batched: one row of X per candidate (used by a batched optimiser / speculative trust-region points)"
+function pseudodeviance(e::Engine, X::Matrix{Float64})          # X is nparams x P (column-major = row-major P x nparams)
+    out = Vector{Float64}(undef, size(X, 2))
+    check(e, ccall((:snaq_eval, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}), e.ctx, size(X, 2), size(X, 1), X, out))
+    return out
+end
+
+"q.qnet.expCF / q.logPseudoLik / q.deltaCF for fittedquartetCF, sampleEdgeQuartetWeighted (src/descriptive.jl:24-59)"
+function readback!(e::Engine, d::DataCF, x::Vector{Float64})
+    expcf = Matrix{Float64}(undef, 3, e.nq); lp = Vector{Float64}(undef, e.nq); dl = Vector{Float64}(undef, e.nq)
+    check(e, ccall((:snaq_eval_quartets, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                   e.ctx, length(x), x, expcf, lp, dl))
+    for (j, q) in enumerate(d.quartet)
+        q.qnet.expCF = expcf[:, j]; q.logPseudoLik = lp[j]; q.deltaCF = dl[j]
+    end
+end
+
+# ---- the replaced body of optBL! (src/snaq_optimization.jl:341-390): NLopt stays in Julia, only `obj` changes ----
+function optBL!(net::HybridNetwork, d::DataCF, e::Engine, verbose::Bool, ftolRel, ftolAbs, xtolRel, xtolAbs)
+    SNaQ.parameters!(net)                       # :353
+    set_network!(e, net)                        # replaces extractQuartet!(net,d), :354
+    nht = length(ht(net))
+    opt = SNaQ.NLopt.Opt(:LN_BOBYQA, nht)
+    SNaQ.NLopt.ftol_rel!(opt, ftolRel); SNaQ.NLopt.ftol_abs!(opt, ftolAbs)
+    SNaQ.NLopt.xtol_rel!(opt, xtolRel); SNaQ.NLopt.xtol_abs!(opt, xtolAbs)
+    SNaQ.NLopt.maxeval!(opt, 1000)
+    SNaQ.NLopt.lower_bounds!(opt, zeros(nht)); SNaQ.NLopt.upper_bounds!(opt, SNaQ.upper(net))
+    obj(x::Vector{Float64}, g::Vector{Float64}) = (SNaQ.update!(net, x); pseudodeviance(e, x))   # :368-380
+    SNaQ.NLopt.min_objective!(opt, obj)
+    fmin, xmin, ret = SNaQ.NLopt.optimize(opt, ht(net))
+    SNaQ.updateParameters!(net, xmin)           # :387
+    SNaQ.loglik!(net, fmin)                     # :388
+    readback!(e, d, xmin)                       # keeps q.qnet.expCF / deltaCF usable by the search (quirk: the reference leaves the LAST x there)
+end
+
+end # module

@@ -8,4 +8,4 @@ from .network import (HybridNetwork, Node, Edge, SnaqError, readnewicklevel1,  #
 from .datacf import DataCF, readtableCF  # noqa: F401
 from .engine import (Engine, load_library, LIB_PATH, extractQuartet_, calculateExpCFAll_, logPseudoLik,  # noqa: F401
                      topologyQpseudolik_, parameters_)
-from . import simulate  # noqa: F401
+from . import simulate, sharded  # noqa: F401

@@ -678,14 +678,25 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restric
     __syncthreads();
     if (tid == 0) out[p] = -(((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7])));
 }
-// transposed variant for the lanes kernel (candidates contiguous): thread per candidate, coalesced
+// variant for the lanes kernel (candidates contiguous in a row of partial): a block of 32 x 8 threads handles 32
+// candidates; thread (c, r) adds rows r, r+8, ... (coalesced 256-byte reads), then the 8 row groups are added
+// in a fixed order
 __global__ void __launch_bounds__(256) k_reduce_partials_t(const double *__restrict__ partial, int nblocks, int stride, int P,
                                                            double *__restrict__ out) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
+    __shared__ double sh[8][32];
+    const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int p = blockIdx.x * 32 + c;
     double s = 0.0;
-    for (int b = 0; b < nblocks; b++) s += partial[(size_t)b * stride + p];
-    out[p] = -s;
+    if (p < P)
+        for (int b = r; b < nblocks; b += 8) s += partial[(size_t)b * stride + p];
+    sh[r][c] = s;
+    __syncthreads();
+    if (r == 0 && p < P) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) t += sh[k][c];
+        out[p] = -t;
+    }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -911,7 +922,7 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
         else LAUNCH_LANES(16);
 #undef LAUNCH_LANES
         CK(cudaGetLastError());
-        k_reduce_partials_t<<<(P + 255) / 256, 256, 0, stream>>>(ctx->d_partial, (int)nchunks, Ppad, P, dout);
+        k_reduce_partials_t<<<(P + 31) / 32, 256, 0, stream>>>(ctx->d_partial, (int)nchunks, Ppad, P, dout);
         CK(cudaGetLastError());
         ctx->counters[0] += 1;
         ctx->counters[1] += nq * (int64_t)P;
