@@ -132,6 +132,10 @@ typedef struct SnaqTables {
      *   crow[c] + k+1 + o-1  o=1..k-1 type-3 term when the hit node is at position o
      *   crow[c] + 2k + i     i=0,1    -log(1-gammaz_i) capped at 10 (bad diamond I only)          */
     const uint16_t *crow;        /* [n_cycles] */
+    /* leaf deletion order (net.leaf order; only the hasEdge parity descriptor needs it): */
+    const uint16_t *blkmax;      /* per cycle position (offsets as cyc_slot): largest net.leaf index in that block */
+    const uint16_t *hmax2;       /* [n_cycles] second largest net.leaf index in the hybrid's block, 0xFFFF if single */
+    const uint16_t *hmaxtax;     /* [n_cycles] taxon with the largest net.leaf index in the hybrid's block */
 } SnaqTables;
 #define SNAQ_CROW(T, c, j)   ((unsigned)(T).crow[c] + (unsigned)(j))
 #define SNAQ_T3ROW(T, c, o)  ((unsigned)(T).crow[c] + (unsigned)(T).cyc_k[c] + (unsigned)(o))

@@ -37,6 +37,9 @@ SnaqTables SnaqHostTables::view(const unsigned char *b) const {
     T.dslot = (const uint16_t *)(b + off_dslot);
     T.dnode = (const uint16_t *)(b + off_dnode);
     T.crow = (const uint16_t *)(b + off_crow);
+    T.blkmax = (const uint16_t *)(b + off_blkmax);
+    T.hmax2 = (const uint16_t *)(b + off_hmax2);
+    T.hmaxtax = (const uint16_t *)(b + off_hmaxtax);
     return T;
 }
 
@@ -249,8 +252,10 @@ int snaq_build_tables(const snaq_flatnet *f, int ntaxa, SnaqHostTables &o, std::
 
         // ---- blocks: position of every taxon in every cycle -----------------------------------
         std::vector<uint8_t> blk((size_t)std::max(H, 1) * std::max(ntaxa, 1), 0);
+        std::vector<std::vector<char>> blockHasCycle(H);
         for (int h = 0; h < H; h++) {
             int k = (int)cycNodes[h].size();
+            blockHasCycle[h].assign(k, 0);
             for (int j = 0; j < k; j++) {
                 int cn = cycNodes[h][j];
                 int e0 = -1;
@@ -263,6 +268,7 @@ int snaq_build_tables(const snaq_flatnet *f, int ntaxa, SnaqHostTables &o, std::
                 while (!st.empty()) {
                     int u = st.back(); st.pop_back();
                     if (cycOfNode[u] == h) fail(SNAQ_ETOPOLOGY, "block of a cycle node re-enters the cycle: not level-1");
+                    if (cycOfNode[u] >= 0) blockHasCycle[h][j] = 1;
                     if (isLeaf(u)) blk[(size_t)h * ntaxa + f->node_taxon[u]] = (uint8_t)j;
                     for (int jj = 0; jj < 3; jj++) {
                         int e = f->node_edge[3 * u + jj];
@@ -318,6 +324,32 @@ int snaq_build_tables(const snaq_flatnet *f, int ntaxa, SnaqHostTables &o, std::
         o.off_dslot = put(o.blob, dslot);
         o.off_dnode = put(o.blob, dnode);
         o.off_crow = put(o.blob, crow);
+        // leaf deletion order statistics per cycle block (hasEdge parity descriptor)
+        std::vector<int> leafOrderOfTaxon(std::max(ntaxa, 1), -1);
+        for (int i = 0; i < f->n_leaves; i++) {
+            int n = f->leaf[i];
+            if (n < 0 || n >= N || !isLeaf(n)) fail(SNAQ_EINVAL, "leaf list entry is not a leaf node");
+            leafOrderOfTaxon[f->node_taxon[n]] = i;
+        }
+        std::vector<uint16_t> blkmax(cyc_slot.size(), 0), hmax2(std::max(H, 1), 0xFFFF), hmaxtax(std::max(H, 1), 0);
+        for (int h = 0; h < H; h++) {
+            int k = (int)cycNodes[h].size();
+            std::vector<int> best(k, -1), second(k, -1), besttax(k, -1);
+            for (int t = 0; t < ntaxa; t++) {
+                if (nodeOfTaxon[t] < 0) continue;
+                int j = blk[(size_t)h * ntaxa + t], lo = leafOrderOfTaxon[t];
+                if (lo > best[j]) { second[j] = best[j]; best[j] = lo; besttax[j] = t; }
+                else if (lo > second[j]) second[j] = lo;
+            }
+            // a block that contains another cycle is not reduced to a leaf hanging on the cycle node: the
+            // merge of src/pseudolik.jl:241-251 cannot fire for it; 0 makes the cascade stop there
+            for (int j = 0; j < k; j++) blkmax[cyc_off[h] + j] = blockHasCycle[h][j] ? 0 : (uint16_t)(std::max(best[j], 0) + 1);
+            hmax2[h] = second[0] < 0 ? 0xFFFF : (uint16_t)(second[0] + 1);
+            hmaxtax[h] = (uint16_t)std::max(besttax[0], 0);
+        }
+        o.off_blkmax = put(o.blob, blkmax);
+        o.off_hmax2 = put(o.blob, hmax2);
+        o.off_hmaxtax = put(o.blob, hmaxtax);
         return SNAQ_OK;
     } catch (const Fail &e) {
         err = e.msg;

@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 
+#include "../../snaq.jl_b200/csrc/snaq_hasedge.h"
 #include "../../snaq.jl_b200/csrc/snaq_tables.h"
 
 static thread_local std::string g_err;
@@ -39,6 +40,23 @@ int hostsim_params(const snaq_flatnet *f, int ntaxa, int32_t *nparams, int32_t *
     *nparams = H.nparams; *n_xe = H.n_xe;
     if (x0) std::memcpy(x0, H.x0.data(), sizeof(double) * H.nparams);
     if (numht) std::memcpy(numht, H.numht.data(), sizeof(int32_t) * H.nparams);
+    return 0;
+}
+
+/* hasEdge bits (one byte per parameter) and the "bad diamond I kept whole" flag of every quartet */
+int hostsim_hasedge(const snaq_flatnet *f, int ntaxa, int64_t nq, const uint16_t *taxa, uint8_t *hasedge, uint8_t *bd1) {
+    SnaqHostTables H;
+    int rc = snaq_build_tables(f, ntaxa, H, g_err);
+    if (rc) return rc;
+    SnaqTables T = H.view(H.blob.data());
+    std::vector<uint32_t> bits(SNAQ_HE_WORDS(H.nparams) + 1);
+    for (int64_t q = 0; q < nq; q++) {
+        int flag = 0;
+        int e = snaq_hasedge_quartet(T, taxa + 4 * q, bits.data(), &flag);
+        if (e) { g_err = "hasedge error " + std::to_string(e) + " at quartet " + std::to_string(q); return SNAQ_ETOPOLOGY; }
+        for (int i = 0; i < H.nparams; i++) hasedge[q * H.nparams + i] = (bits[i >> 5] >> (i & 31)) & 1u;
+        if (bd1) bd1[q] = (uint8_t)flag;
+    }
     return 0;
 }
 

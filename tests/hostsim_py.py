@@ -54,3 +54,15 @@ def run(flat, ntaxa, qt, obs=None, X=None, sampled=None, maxh=8):
         raise RuntimeError(lib().hostsim_last_error().decode())
     out["status"] = st.value
     return out
+
+
+def hasedge(flat, ntaxa, qt):
+    qt = np.ascontiguousarray(qt, dtype=np.uint16).reshape(-1, 4)
+    nq = qt.shape[0]
+    npar = len(params(flat, ntaxa)[0])
+    he = np.zeros((nq, max(npar, 1)), np.uint8)
+    bd1 = np.zeros(nq, np.uint8)
+    rc = lib().hostsim_hasedge(flat.ptr(), ntaxa, C.c_int64(nq), _p(qt), _p(he), _p(bd1))
+    if rc:
+        raise RuntimeError(lib().hostsim_last_error().decode())
+    return he[:, :npar], bd1
