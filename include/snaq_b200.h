@@ -175,7 +175,8 @@ int snaq_get_descriptors(snaq_ctx *ctx, int8_t *which, int8_t *ntype,
 
 /* engine counters: [0] launches of the eval kernel, [1] quartet-evals done,
  * [2] H2D bytes, [3] D2H bytes, [4] descriptor words in HBM, [5] launches of
- * the descriptor-build kernels                                                 */
+ * the descriptor-build kernels, [6] bytes one single-call evaluation (P <= 4)
+ * streams from HBM                                                             */
 int snaq_get_counters(snaq_ctx *ctx, int64_t out[8]);
 
 /* measurement aid for the FP64 roofline: best-of-5 rate of a DFMA microbenchmark kernel

@@ -17,7 +17,7 @@
  *                                  divergence, x is staged transposed in shared memory so the
  *                                  per-slot gathers are conflict-free, sums stay thread-private
  *                                  until one fixed-order block reduction (deterministic).
- *   k_eval_quartets              : thread per quartet for small batches (P < 16; HBM-bound at P=1)
+ *   k_eval_direct                : thread per quartet for small batches (P < 16; HBM-bound at P=1)
  *                                  and for the per-quartet read-back (expCF, logPseudoLik, deltaCF)
  *   k_reduce_partials            : second, fixed-order pass over the per-block partial sums
  *
@@ -41,8 +41,6 @@
 
 #define SNAQ_S_RANGE 8u   /* a parameter outside its bounds reached the device */
 #define LANES_MIN_P 16    /* batches of at least this many candidates use k_eval_lanes */
-#define QK_MAXP 16        /* k_eval_quartets handles at most this many candidates per launch */
-#define QK_STAGES 3       /* TMA stages of k_eval_quartets */
 
 // --------------------------------------------------------------------------------------------
 // math tables (copied to shared memory by every evaluation kernel)
@@ -97,10 +95,11 @@ __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_
                                                      uint32_t *__restrict__ len4, uint8_t *__restrict__ cls,
                                                      uint32_t *__restrict__ iota, unsigned long long *__restrict__ stats,
                                                      uint32_t *__restrict__ status) {
-    // stats: [0] total chunks, [1] max chunks, [2..5] quartets per sort class
-    // sort classes: 0 = class A with a one-chunk program, 1 = other class A, 2 = class B, 3 = class C
+    // stats: [0] total chunks, [1] max chunks, [2..6] quartets per sort class
+    // sort classes: 0 = class A with a one-chunk program, 1 = class A with two chunks, 2 = longer class A,
+    //               3 = class B, 4 = class C
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned n = 0, c = 4;
+    unsigned n = 0, c = 5;
     if (q < nq) {
         uint16_t tx[4];
         load_taxa(taxa, q, tx);
@@ -111,16 +110,16 @@ __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_
         n = (unsigned)((w.n + 3) >> 2);
         if (n == 0) n = 1;
         c = SNAQ_HDR_CLASS(hdr);
-        c = (c == 0) ? (n == 1 ? 0u : 1u) : c + 1u;
+        c = (c == 0) ? (n == 1 ? 0u : (n == 2 ? 1u : 2u)) : c + 2u;
         len4[q] = n;
         cls[q] = (uint8_t)c;
         iota[q] = (uint32_t)q;
     }
     __shared__ unsigned long long ssum[4];
-    __shared__ unsigned smax[4], scnt[4];
-    if (threadIdx.x < 4) scnt[threadIdx.x] = 0;
+    __shared__ unsigned smax[4], scnt[5];
+    if (threadIdx.x < 5) scnt[threadIdx.x] = 0;
     __syncthreads();
-    if (c < 4) atomicAdd(&scnt[c], 1u);
+    if (c < 5) atomicAdd(&scnt[c], 1u);
     unsigned long long s = n;
     unsigned m = n;
     for (int o = 16; o > 0; o >>= 1) {
@@ -132,7 +131,7 @@ __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_
     if (threadIdx.x == 0) {
         atomicAdd(&stats[0], ssum[0] + ssum[1] + ssum[2] + ssum[3]);
         atomicMax(&stats[1], (unsigned long long)max(max(smax[0], smax[1]), max(smax[2], smax[3])));
-        for (int k = 0; k < 4; k++) if (scnt[k]) atomicAdd(&stats[2 + k], (unsigned long long)scnt[k]);
+        for (int k = 0; k < 5; k++) if (scnt[k]) atomicAdd(&stats[2 + k], (unsigned long long)scnt[k]);
     }
 }
 
@@ -164,16 +163,28 @@ __global__ void __launch_bounds__(128) k_build_emit(SnaqTables T, const uint16_t
     qhdr[i] = hdr;
 }
 
+// W[i] (all classes) and, for the class-A quartets with one- and two-chunk programs [0,nA), the pair
+// WA[i] = (W0, W1) that the single-call kernel streams; their constants W3 are summed once into wpart (one
+// partial per block, fixed order)
 __global__ void __launch_bounds__(256) k_weights(const uint32_t *__restrict__ perm, const uint8_t *__restrict__ qhdr,
                                                  const double *__restrict__ obs, const uint8_t *__restrict__ sampled,
-                                                 int64_t nq, double *__restrict__ W) {
+                                                 int64_t nq, int64_t nA, double *__restrict__ W, double2 *__restrict__ WA,
+                                                 double *__restrict__ wpart) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq) return;
-    const int64_t q = perm[i];
-    double o[3] = {obs[3 * q], obs[3 * q + 1], obs[3 * q + 2]};
-    double w[4];
-    snaq_weights(qhdr[i], o, sampled ? sampled[q] : 1, w);
-    reinterpret_cast<double4 *>(W)[i] = make_double4(w[0], w[1], w[2], w[3]);
+    double c3 = 0.0;
+    if (i < nq) {
+        const int64_t q = perm[i];
+        double o[3] = {obs[3 * q], obs[3 * q + 1], obs[3 * q + 2]};
+        double w[4];
+        snaq_weights(qhdr[i], o, sampled ? sampled[q] : 1, w);
+        reinterpret_cast<double4 *>(W)[i] = make_double4(w[0], w[1], w[2], w[3]);
+        if (i < nA) { WA[i] = make_double2(w[0], w[1]); c3 = w[3]; }
+    }
+    __shared__ double red[8];
+    for (int o = 16; o > 0; o >>= 1) c3 += __shfl_down_sync(0xffffffffu, c3, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c3;
+    __syncthreads();
+    if (threadIdx.x == 0) wpart[blockIdx.x] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
 }
 
 // parity descriptors: which / typeHyb per hybrid / formula, original order
@@ -469,187 +480,195 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
 }
 
 /*
- * Thread per quartet (sorted order), P <= QK_MAXP candidates: the HBM-bound path of a single objective
- * call.  Persistent blocks; two instantiations share the partial buffer and the completion ticket:
- *   GENERIC=false : the class-A region [0,nA): additive programs only (lean code, 4 blocks per SM)
- *   GENERIC=true  : the rest (type-2/4 terms, 4-cycles) through the generic evaluator
- *   prologue : every block expands x into xf (snaq_expand_row) in shared memory
- *   main loop: tiles of BLOCK quartets, statically strided over the grid; the weights (32 B per quartet)
- *              and the programs (contiguous in the class-sorted table) of the next tiles arrive by TMA bulk
- *              copies into a ring of shared-memory stages while the current tile is computed (one
- *              mbarrier per stage)
- *   epilogue : the block's sums go to partial[block][p]; the last block of the last instantiation to
- *              finish (atomic ticket) adds all partials in a fixed order and writes out[p] = -sum
- * OUT: per-quartet results of the LAST candidate at the quartet's ORIGINAL index (expcf [nq][3] in
- * data order, logpl [nq], deltacf [nq]).
+ * Thread per quartet (class-sorted order), at most PC candidates per launch: the HBM-bound path of a single
+ * objective call (P = 1) and of small batches.  One persistent launch, no staging: every byte is read once by
+ * exactly one thread, so the loads are plain coalesced 8/16-byte loads, four quartets in flight per thread.
+ *   prologue : every block expands x into xf (snaq_expand_row) in shared memory, PC rows
+ *   region A1: [0,nA1)         additive one-chunk programs:  16 B weights + 8 B program per quartet,
+ *                              program i is chunk i (no offset load)
+ *   region A2: [nA1,nA1+nA2)   additive two-chunk programs: 16 B + 16 B, program i at chunk nA1 + 2 (i - nA1)
+ *   region G : the rest        (longer additive programs, type-2/4 terms, 4-cycles) through the generic
+ *                              evaluator; a warp stages the contiguous program span of its 32 quartets in
+ *                              shared memory with coalesced loads
+ *   Every region is strided over all threads of the grid, so the load is balanced by construction.
+ *   epilogue : thread-private sums -> fixed-order block reduction -> partial[block][p]; the last block to
+ *              finish (atomic ticket) adds all partials in block order: out[p] = -(sum) + sum of the class-A
+ *              constants W3 (negw3 = -sum_A W3, precomputed with the weights).  Bit-reproducible.
+ * OUT: per-quartet results (P = 1) at the quartet's ORIGINAL index (expcf [nq][3] in data order, logpl [nq],
+ * deltacf [nq]); every quartet goes through the generic evaluator.
  */
-template <int BLOCK, bool GENERIC, bool OUT>
-__global__ void __launch_bounds__(BLOCK, GENERIC ? 2 : 4)
-k_eval_quartets(SnaqTables T, const uint32_t *__restrict__ off, const uint16_t *__restrict__ prog, const uint8_t *__restrict__ qhdr,
-                const uint32_t *__restrict__ perm, const double *__restrict__ W, const double *__restrict__ obs, uint32_t qlo,
-                uint32_t qhi, uint32_t nA1, const double *__restrict__ X, const double *__restrict__ xconst, int nh, int nt, int P,
-                int stage_chunks, double *__restrict__ partial, unsigned pbase, unsigned nblocks_total, double *__restrict__ out,
-                unsigned int *__restrict__ ticket, double *__restrict__ expcf, double *__restrict__ logpl,
-                double *__restrict__ deltacf, uint32_t *__restrict__ status) {
-    constexpr int TILE = BLOCK;
-    constexpr int NST = QK_STAGES;
+#define QD_SPAN 192   /* program chunks a warp can stage for its 32 quartets (else: read from global memory) */
+template <int PC, bool OUT>
+__global__ void __launch_bounds__(256, OUT ? 2 : 3)
+k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restrict__ prog2, const uint8_t *__restrict__ qhdr,
+              const uint32_t *__restrict__ perm, const double2 *__restrict__ WA, const double4 *__restrict__ W,
+              const double *__restrict__ obs, uint32_t nA1, uint32_t nA2, uint32_t nQ, const double *__restrict__ X,
+              const double *__restrict__ xconst, int nh, int nt, int P, double *__restrict__ partial, double *__restrict__ out,
+              const double *__restrict__ negw3, unsigned int *__restrict__ ticket, double *__restrict__ expcf,
+              double *__restrict__ logpl, double *__restrict__ deltacf, uint32_t *__restrict__ status) {
+    constexpr int BLOCK = 256;
     extern __shared__ __align__(128) unsigned char smem[];
-    double *mt = reinterpret_cast<double *>(smem);                 // 48 doubles, 128-byte aligned
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 384);      // NST mbarriers
-    double4 *sW = reinterpret_cast<double4 *>(smem + 512);         // [NST][TILE] weights           <- TMA bulk copies
-    const unsigned stage_stride = (unsigned)stage_chunks + 2u;
-    uint2 *sP = reinterpret_cast<uint2 *>(smem + 512 + (size_t)NST * TILE * 32);   // [NST][stage_chunks+2] program chunks
-    double *red = reinterpret_cast<double *>(smem + 512 + (size_t)NST * TILE * 32 + (size_t)NST * stage_stride * 8);
-    double *sacc = red + BLOCK / 32;                               // [QK_MAXP] block sums
-    double *xs = sacc + QK_MAXP;                                   // [P][n_full]
-    const unsigned tid = threadIdx.x;
+    double *mt = reinterpret_cast<double *>(smem);                       // 48 doubles, 128-byte aligned
+    double *red = reinterpret_cast<double *>(smem + 384);                // [8][PC] warp sums
+    uint2 *span = reinterpret_cast<uint2 *>(smem + 384 + 8 * PC * 8);    // [8 warps][QD_SPAN] staged programs
+    double *xs = reinterpret_cast<double *>(smem + 384 + 8 * PC * 8 + 8 * QD_SPAN * 8);   // [PC][n_full]
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const int n_full = T.n_full;
     unsigned st = 0;
-    const unsigned ntiles = (qhi - qlo + TILE - 1) / TILE;
-    const uint2 *prog2 = reinterpret_cast<const uint2 *>(prog);
-    auto issue = [&](unsigned tile, unsigned s) {                  // thread 0 only
-        const unsigned ibase = qlo + tile * TILE;
-        const unsigned nloc = min((unsigned)TILE, qhi - ibase);
-        const bool a1 = (ibase + nloc <= nA1);                     // one-chunk region: off[i] == i, no dependent load
-        const uint32_t c0 = a1 ? ibase : off[ibase], c1 = a1 ? ibase + nloc : off[ibase + nloc];
-        const uint32_t c16 = c0 & ~1u;                             // bulk copies need 16-byte alignment
-        const unsigned wbytes = nloc * 32u;
-        unsigned pbytes = ((c1 - c16) * 8u + 15u) & ~15u;
-        if (c1 - c16 > (uint32_t)stage_chunks) pbytes = 0;        // oversized tile: programs are read from global memory
-        mbar_expect_tx(&bar[s], wbytes + pbytes);
-        tma_load_1d(sW + (size_t)s * TILE, W + (size_t)ibase * 4, wbytes, &bar[s]);
-        if (pbytes) tma_load_1d(sP + (size_t)s * stage_stride, prog2 + c16, pbytes, &bar[s]);
-    };
-    if (tid == 0) for (int k = 0; k < NST; k++) mbar_init(&bar[k], 1);
     const SnaqMath M = load_math_tables(mt, (int)tid);
-    if (tid < QK_MAXP) sacc[tid] = 0.0;
-    __syncthreads();
-    if (tid == 0)
-        for (unsigned k = 0; k < NST - 1; k++)
-            if (blockIdx.x + k * gridDim.x < ntiles) issue(blockIdx.x + k * gridDim.x, k);
-    // prologue: expanded parameter vectors of the P candidates (and the bounds check of update!)
-    for (int idx = (int)tid; idx < P * n_full; idx += BLOCK) {
-        const int p = idx / n_full, row = idx - p * n_full;
+    // prologue: expanded parameter vectors (and the bounds check of update!); unused rows repeat the last candidate
+    for (int idx = (int)tid; idx < PC * n_full; idx += BLOCK) {
+        const int p = min(idx / n_full, P - 1), row = idx % n_full;
         const double *x = X + (size_t)p * T.nparams;
         if (row < T.nparams) st |= range_check(x[row], (row >= nh && row < nh + nt) ? 1.0e300 : 1.0);
         xs[idx] = snaq_expand_row(T, M, x, xconst, row);
     }
     __syncthreads();
-    auto write_out = [&](unsigned i, const double cf[3], double lik, const double4 &w4) {
-        const unsigned h = (unsigned)qhdr[i];
-        const size_t q = perm[i];
-        double e[3];
-        snaq_data_order(h, cf, e);
-        if (expcf) { expcf[3 * q] = e[0]; expcf[3 * q + 1] = e[1]; expcf[3 * q + 2] = e[2]; }
-        if (logpl) logpl[q] = lik;
-        if (deltacf) {   // calculateDeltaCF: src/pseudolik.jl:491-498 (0 for unsampled quartets, :514)
-            const bool smp = (w4.x != 0.0 || w4.y != 0.0 || w4.z != 0.0 || w4.w != 0.0);
-            const double d = fabs(obs[3 * q] - e[0]) + fabs(obs[3 * q + 1] - e[1]) + fabs(obs[3 * q + 2] - e[2]);
-            deltacf[q] = smp ? d : 0.0;
-        }
-    };
-    auto tile_reduce = [&](double v, int p) {                      // fixed-order block reduction of one tile
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if ((tid & 31) == 0) red[tid >> 5] = v;
-        __syncthreads();
-        if (tid == 0) {
-            double ssum = 0.0;
+    const unsigned gtid = blockIdx.x * BLOCK + tid, nthr = gridDim.x * BLOCK;
+    double acc[PC];
 #pragma unroll
-            for (int k = 0; k < BLOCK / 32; k++) ssum += red[k];
-            sacc[p] += ssum;
-        }
-        __syncthreads();
+    for (int p = 0; p < PC; p++) acc[p] = 0.0;
+    const unsigned nullpair = (unsigned)T.n_xe * 0x10001u;
+    auto tree_term = [&](double t, const double2 &w) {                    // one additive quartet, one candidate
+        const double t1 = fmin(t, 10.0);
+        const double y = snaq_exp(-t1, M);
+        const double major = fma(SNAQ_K_M23, y, 1.0);
+        return fma(w.x, snaq_log_pos(major, M), -w.y * (t1 + SNAQ_K_LOG3));
     };
-    unsigned s = 0, s_next = NST - 1, phase = 0;
-    double acc1 = 0.0;      // P == 1: thread-private sum over all tiles, reduced once at the end
+    if (!OUT) {
+        // ---- region A1 -------------------------------------------------------------------------------
 #pragma unroll 1
-    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // the stage s_next was last read in the previous iteration, which ended with a __syncthreads: refill it
-        if (tid == 0 && tile + (NST - 1) * gridDim.x < ntiles) issue(tile + (NST - 1) * gridDim.x, s_next);
-        const unsigned ibase = qlo + tile * TILE;
-        const unsigned nloc = min((unsigned)TILE, qhi - ibase);
-        const unsigned i = ibase + tid;
-        const bool active = tid < nloc;
-        uint32_t o0 = i, o1 = i + 1, c0 = ibase, c1 = ibase + nloc;
-        if (ibase + nloc > nA1) {                                  // tile-uniform
-            c0 = off[ibase]; c1 = off[ibase + nloc];
-            if (active) { o0 = off[i]; o1 = off[i + 1]; }
-        }
-        const uint32_t c16 = c0 & ~1u;
-        const bool staged = (c1 - c16) <= (uint32_t)stage_chunks;
-        mbar_wait(&bar[s], phase);
-        const double4 w4 = active ? sW[(size_t)s * TILE + tid] : make_double4(0, 0, 0, 0);
-        const uint2 *pp = staged ? sP + (size_t)s * stage_stride + (o0 - c16) : prog2 + o0;
-        const unsigned nch = active ? o1 - o0 : 0u;
-        if (!GENERIC) {
-#pragma unroll 1
-            for (int p = 0; p < P; p++) {
-                const double *xp = xs + (size_t)p * n_full;
-                double v = 0.0;
-                if (active) {
-                    uint2 q2 = pp[0];
-                    double ta = xp[q2.x & 0xffffu] - xp[q2.x >> 16], tb = xp[q2.y & 0xffffu] - xp[q2.y >> 16];
-#pragma unroll 1
-                    for (unsigned c = 1; c < nch; c++) {
-                        q2 = pp[c];
-                        ta += xp[q2.x & 0xffffu] - xp[q2.x >> 16];
-                        tb += xp[q2.y & 0xffffu] - xp[q2.y >> 16];
-                    }
-                    const double t1 = fmin(ta + tb, 10.0);
-                    const double y = snaq_exp(-t1, M);
-                    const double major = fma(SNAQ_K_M23, y, 1.0);
-                    v = fma(w4.x, snaq_log_pos(major, M), -fma(w4.y, t1 + SNAQ_K_LOG3, w4.w));
-                    if (OUT && p == P - 1) {
-                        const double cf[3] = {major, 1.0 / 3.0 * y, 1.0 / 3.0 * y};
-                        write_out(i, cf, v, w4);
-                    }
-                }
-                if (P == 1) acc1 += v; else tile_reduce(v, p);
+        for (unsigned i0 = gtid; i0 < nA1; i0 += 4u * nthr) {
+            double2 w[4];
+            uint2 c[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned i = i0 + (unsigned)k * nthr;
+                const bool ok = i < nA1;
+                w[k] = ok ? __ldg(WA + i) : make_double2(0.0, 0.0);
+                c[k] = ok ? __ldg(prog2 + i) : make_uint2(nullpair, nullpair);
             }
-        } else {
-            const unsigned hdr = active ? (unsigned)qhdr[i] : 0u;
-            const double w[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll 1
-            for (int p = 0; p < P; p++) {
-                const XRow xf{xs + (size_t)p * n_full};
-                double v = 0.0;
-                if (active) {
-                    double cf[3], t1;
-                    snaq_eval_quartet(hdr, reinterpret_cast<const uint16_t *>(pp), (int)nch * 4, xf, M, cf, &t1, st);
-                    v = snaq_quartet_loglik(SNAQ_HDR_KIND(hdr), cf, t1, w, M, st);
-                    if (OUT && p == P - 1) write_out(i, cf, v, w4);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+#pragma unroll
+                for (int p = 0; p < PC; p++) {
+                    const double *xp = xs + p * n_full;
+                    const double t = (xp[c[k].x & 0xffffu] - xp[c[k].x >> 16]) + (xp[c[k].y & 0xffffu] - xp[c[k].y >> 16]);
+                    acc[p] += tree_term(t, w[k]);
                 }
-                if (P == 1) acc1 += v; else tile_reduce(v, p);
             }
         }
-        if (P == 1) __syncthreads();      // every thread is done with stage s before it is refilled
-        s_next = s;
-        if (++s == NST) { s = 0; phase ^= 1u; }
+        // ---- region A2 -------------------------------------------------------------------------------
+#pragma unroll 1
+        for (unsigned j0 = gtid; j0 < nA2; j0 += 2u * nthr) {
+            double2 w[2];
+            uint2 c[2][2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const unsigned j = j0 + (unsigned)k * nthr;
+                const bool ok = j < nA2;
+                w[k] = ok ? __ldg(WA + nA1 + j) : make_double2(0.0, 0.0);
+                c[k][0] = ok ? __ldg(prog2 + nA1 + 2u * j) : make_uint2(nullpair, nullpair);
+                c[k][1] = ok ? __ldg(prog2 + nA1 + 2u * j + 1u) : make_uint2(nullpair, nullpair);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+#pragma unroll
+                for (int p = 0; p < PC; p++) {
+                    const double *xp = xs + p * n_full;
+                    double ta = xp[c[k][0].x & 0xffffu] - xp[c[k][0].x >> 16], tb = xp[c[k][0].y & 0xffffu] - xp[c[k][0].y >> 16];
+                    ta += xp[c[k][1].x & 0xffffu] - xp[c[k][1].x >> 16];
+                    tb += xp[c[k][1].y & 0xffffu] - xp[c[k][1].y >> 16];
+                    acc[p] += tree_term(ta + tb, w[k]);
+                }
+            }
+        }
     }
-    if (P == 1) { sacc[0] = 0.0; __syncthreads(); tile_reduce(acc1, 0); }
+    // ---- region G (everything when OUT) ---------------------------------------------------------------
+    {
+        const unsigned g0 = OUT ? 0u : nA1 + nA2;
+        uint2 *wspan = span + warp * QD_SPAN;
+        const unsigned wstride = nthr;                        // a warp's 32 quartets are consecutive
+#pragma unroll 1
+        for (unsigned ib = g0 + (gtid - lane); ib < nQ; ib += wstride) {
+            const unsigned i = ib + lane;
+            const bool active = i < nQ;
+            const unsigned ilast = min(ib + 32u, nQ);
+            const uint32_t o0 = active ? __ldg(off + i) : 0u, o1 = active ? __ldg(off + i + 1) : 0u;
+            const uint32_t s0 = __shfl_sync(0xffffffffu, o0, 0);
+            const uint32_t s1 = __ldg(off + ilast);
+            const bool staged = (s1 - s0) <= (uint32_t)QD_SPAN;
+            __syncwarp();
+            if (staged) for (uint32_t c = s0 + lane; c < s1; c += 32u) wspan[c - s0] = __ldg(prog2 + c);
+            __syncwarp();
+            if (active) {
+                const unsigned hdr = (unsigned)qhdr[i];
+                const double4 w4 = W[i];
+                const double w[4] = {w4.x, w4.y, w4.z, w4.w};
+                const uint16_t *pc = reinterpret_cast<const uint16_t *>(staged ? wspan + (o0 - s0) : prog2 + o0);
+                const int nwords = (int)(o1 - o0) * 4;
+#pragma unroll 1
+                for (int p = 0; p < PC; p++) {
+                    if (p < P) {
+                        const XRow xf{xs + p * n_full};
+                        double cf[3], t1;
+                        snaq_eval_quartet(hdr, pc, nwords, xf, M, cf, &t1, st);
+                        const double v = snaq_quartet_loglik(SNAQ_HDR_KIND(hdr), cf, t1, w, M, st);
+#pragma unroll
+                        for (int k = 0; k < PC; k++) if (k == p) acc[k] += v;     // keeps acc[] in registers
+                        if (OUT) {
+                            const size_t q = perm[i];
+                            double e[3];
+                            snaq_data_order(hdr, cf, e);
+                            if (expcf) { expcf[3 * q] = e[0]; expcf[3 * q + 1] = e[1]; expcf[3 * q + 2] = e[2]; }
+                            if (logpl) logpl[q] = v;
+                            if (deltacf) {   // calculateDeltaCF: src/pseudolik.jl:491-498 (0 for unsampled quartets, :514)
+                                const bool smp = (w4.x != 0.0 || w4.y != 0.0 || w4.z != 0.0 || w4.w != 0.0);
+                                const double d = fabs(obs[3 * q] - e[0]) + fabs(obs[3 * q + 1] - e[1]) + fabs(obs[3 * q + 2] - e[2]);
+                                deltacf[q] = smp ? d : 0.0;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
     if (st) atomicOr(status, st);
-    // epilogue: publish this block's sums; the last block overall adds all of them in block order
-    if ((int)tid < P) partial[(size_t)(pbase + blockIdx.x) * P + tid] = sacc[tid];
+    // ---- epilogue: fixed-order block reduction, then the last block adds the partials in block order -----
+#pragma unroll
+    for (int p = 0; p < PC; p++) {
+        double v = acc[p];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp * PC + p] = v;
+    }
+    __syncthreads();
+    if ((int)tid < PC) {
+        double ssum = 0.0;
+#pragma unroll
+        for (int k = 0; k < BLOCK / 32; k++) ssum += red[k * PC + tid];
+        partial[(size_t)blockIdx.x * PC + tid] = ssum;
+    }
     __threadfence();
     __shared__ unsigned int s_last;
     __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == nblocks_total - 1) ? 1u : 0u;
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
     __syncthreads();
     if (s_last) {
         __threadfence();
+        const double cst = OUT ? 0.0 : __ldcg(negw3);
         for (int p = 0; p < P; p++) {
             double sp = 0.0;
-            for (unsigned b = tid; b < nblocks_total; b += BLOCK) sp += __ldcg(partial + (size_t)b * P + p);
+            for (unsigned b = tid; b < gridDim.x; b += BLOCK) sp += __ldcg(partial + (size_t)b * PC + p);
             for (int o = 16; o > 0; o >>= 1) sp += __shfl_down_sync(0xffffffffu, sp, o);
-            if ((tid & 31) == 0) red[tid >> 5] = sp;
+            __syncthreads();
+            if (lane == 0) red[warp] = sp;
             __syncthreads();
             if (tid == 0) {
                 double tot = 0.0;
 #pragma unroll
                 for (int k = 0; k < BLOCK / 32; k++) tot += red[k];
-                out[p] = -tot;
+                out[p] = -tot - cst;
             }
-            __syncthreads();
         }
         if (tid == 0) *ticket = 0u;
     }
@@ -740,13 +759,16 @@ struct snaq_ctx {
     uint64_t prog_words = 0;
     uint32_t maxlen = 0;                  // longest program, in chunks
     double *d_W = nullptr;
+    double2 *d_WA = nullptr;              // [nq] (only [0,nA) used): class-A weight pairs streamed by k_eval_direct
+    double *d_wpart = nullptr;            // per-block partial sums of the class-A constants W3
+    double *d_negw3 = nullptr;            // -(sum of W3 over class A)
     uint32_t *d_perm = nullptr;           // [nq] sorted position -> original quartet
     uint8_t *d_qhdr = nullptr;            // [nq] header bytes, sorted order
     uint32_t *d_len4 = nullptr, *d_iota = nullptr;   // [nq] scratch of the build
     uint8_t *d_cls = nullptr, *d_cls_sorted = nullptr;
-    int64_t nA1 = 0, nA = 0, nB = 0, nC = 0;   // nA1: leading class-A quartets whose program is exactly one chunk (off[i] == i)
+    int64_t nA1 = 0, nA2 = 0, nA = 0, nB = 0, nC = 0;   // nA1: leading class-A quartets whose program is exactly one chunk (off[i] == i)
     uint32_t *d_status = nullptr;          // [0] build, [1] eval
-    unsigned int *d_ticket = nullptr;      // last-block ticket of k_eval_quartets (reset by the kernel)
+    unsigned int *d_ticket = nullptr;      // last-block ticket of k_eval_direct (reset by the kernel)
     unsigned long long *d_total = nullptr; // build statistics: total chunks, max chunks, class counts
     void *d_scan_tmp = nullptr;
     size_t scan_tmp_cap = 0;
@@ -757,7 +779,6 @@ struct snaq_ctx {
     double *d_partial = nullptr; size_t partial_cap = 0;
     double *h_pin = nullptr; size_t pin_cap = 0;
     int sm_count = 148;
-    int qk_items = 1;                     // quartets per thread of k_eval_quartets (SNAQ_QK_ITEMS = 1, 2 or 4)
     int lanes_warps = 8;                  // warps per block of k_eval_lanes (SNAQ_LANES_WARPS = 8, 12 or 16)
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -817,63 +838,56 @@ static int status_to_error(snaq_ctx *ctx, uint32_t st) {
 static int run_weights(snaq_ctx *ctx) {
     if (!ctx->has_net || ctx->nq == 0) return SNAQ_OK;
     int64_t nb = (ctx->nq + 255) / 256;
-    k_weights<<<(unsigned)nb, 256, 0, ctx->stream>>>(ctx->d_perm, ctx->d_qhdr, ctx->d_obs, ctx->has_sampled ? ctx->d_sampled : nullptr, ctx->nq, ctx->d_W);
+    k_weights<<<(unsigned)nb, 256, 0, ctx->stream>>>(ctx->d_perm, ctx->d_qhdr, ctx->d_obs, ctx->has_sampled ? ctx->d_sampled : nullptr, ctx->nq,
+                                                    ctx->nA1 + ctx->nA2, ctx->d_W, ctx->d_WA, ctx->d_wpart);
     CK(cudaGetLastError());
-    ctx->counters[5]++;
+    k_reduce_partials<<<1, 256, 0, ctx->stream>>>(ctx->d_wpart, (int)nb, 1, 1, ctx->d_negw3);
+    CK(cudaGetLastError());
+    ctx->counters[5] += 2;
     return SNAQ_OK;
 }
 
-template <bool GENERIC, bool OUT>
-static int launch_qk(snaq_ctx *ctx, int grid, size_t smem, cudaStream_t stream, uint32_t qlo, uint32_t qhi, const double *dX, int Pc,
-                     int stage_chunks, unsigned pbase, unsigned nblocks_total, double *dout, double *expcf, double *logpl,
-                     double *deltacf) {
+template <int PC, bool OUT>
+static int launch_direct(snaq_ctx *ctx, cudaStream_t stream, const double *dX, int Pc, double *dout, double *expcf, double *logpl,
+                         double *deltacf) {
     const SnaqHostTables &H = ctx->H;
-    CK(cudaFuncSetAttribute(k_eval_quartets<256, GENERIC, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_eval_quartets<256, GENERIC, OUT><<<grid, 256, smem, stream>>>(
-        ctx->T, ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_perm, ctx->d_W, ctx->d_obs, qlo, qhi, (uint32_t)ctx->nA1, dX, ctx->d_xconst,
-        H.nh, H.nt, Pc, stage_chunks, ctx->d_partial, pbase, nblocks_total, dout, ctx->d_ticket, expcf, logpl, deltacf,
-        ctx->d_status + 1);
+    const size_t smem = 384 + 8 * PC * 8 + 8 * QD_SPAN * 8 + (size_t)PC * H.n_full * 8;
+    if (smem > 64 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_direct"; return SNAQ_EINVAL; }
+    const int per_sm = OUT ? 2 : 3;
+    const int64_t work = (ctx->nq + 255) / 256;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(work, (int64_t)ctx->sm_count * per_sm));
+    int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)grid * PC);
+    if (rc) return rc;
+    CK(cudaFuncSetAttribute(k_eval_direct<PC, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_eval_direct<PC, OUT><<<grid, 256, smem, stream>>>(
+        ctx->T, ctx->d_off, reinterpret_cast<const uint2 *>(ctx->d_prog), ctx->d_qhdr, ctx->d_perm, ctx->d_WA,
+        reinterpret_cast<const double4 *>(ctx->d_W), ctx->d_obs, (uint32_t)ctx->nA1, (uint32_t)ctx->nA2, (uint32_t)ctx->nq, dX,
+        ctx->d_xconst, H.nh, H.nt, Pc, ctx->d_partial, dout, ctx->d_negw3, ctx->d_ticket, expcf, logpl, deltacf, ctx->d_status + 1);
     CK(cudaGetLastError());
+    ctx->counters[0] += 1;
+    ctx->counters[1] += ctx->nq * (int64_t)Pc;
     return SNAQ_OK;
 }
 
+// small batches (and the per-quartet read-back, one candidate at a time): at most 4 candidates per launch
 static int eval_quartets_launch(snaq_ctx *ctx, int P, const double *dX, double *dout, cudaStream_t stream, double *expcf,
                                 double *logpl, double *deltacf) {
     const SnaqHostTables &H = ctx->H;
-    const int64_t nq = ctx->nq;
     const bool per_quartet = expcf || logpl || deltacf;
-    constexpr int BLOCK = 256, TILE = BLOCK;
-    // program chunks staged per tile: 3 per quartet covers almost every tile; bigger tiles read from global memory
-    const int stage_chunks = TILE * (int)std::min<uint32_t>(std::max<uint32_t>(ctx->maxlen, 1u), 3u);
-    const uint32_t nA = (uint32_t)ctx->nA, nQ = (uint32_t)nq;
-    for (int p0 = 0; p0 < P; p0 += QK_MAXP) {
-        const int Pc = std::min(QK_MAXP, P - p0);
-        const size_t smem = 512 + (size_t)QK_STAGES * TILE * 32 + (size_t)QK_STAGES * (stage_chunks + 2) * 8 + (BLOCK / 32) * 8 +
-                            QK_MAXP * 8 + (size_t)Pc * H.n_full * 8 + 16;
-        if (smem > 200 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_quartets"; return SNAQ_EINVAL; }
-        const int per_sm_a = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / smem));
-        const int per_sm_g = (int)std::max<size_t>(1, std::min<size_t>(2, (200 * 1024) / smem));
-        const int64_t tilesA = (nA + TILE - 1) / TILE, tilesG = (nQ - nA + TILE - 1) / TILE;
-        const int gridA = (int)std::min<int64_t>(tilesA, (int64_t)ctx->sm_count * per_sm_a);
-        const int gridG = (int)std::min<int64_t>(tilesG, (int64_t)ctx->sm_count * per_sm_g);
-        const unsigned nblocks_total = (unsigned)(gridA + gridG);
-        int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)nblocks_total * Pc);
-        if (rc) return rc;
-        const bool outp = (p0 + Pc == P) && per_quartet;
+    if (per_quartet) {
+        // the per-quartet arrays describe the LAST candidate; the totals of the others come from the plain path
+        if (P > 1) { int rc = eval_quartets_launch(ctx, P - 1, dX, dout, stream, nullptr, nullptr, nullptr); if (rc) return rc; }
+        return launch_direct<1, true>(ctx, stream, dX + (size_t)(P - 1) * H.nparams, 1, dout + (P - 1), expcf, logpl, deltacf);
+    }
+    for (int p0 = 0; p0 < P;) {
+        const int left = P - p0;
         const double *dXp = dX + (size_t)p0 * H.nparams;
-        // the generic region first: it is the smaller, slower one and overlaps the tail of nothing otherwise
-        if (gridG > 0) {
-            rc = outp ? launch_qk<true, true>(ctx, gridG, smem, stream, nA, nQ, dXp, Pc, stage_chunks, (unsigned)gridA, nblocks_total, dout + p0, expcf, logpl, deltacf)
-                      : launch_qk<true, false>(ctx, gridG, smem, stream, nA, nQ, dXp, Pc, stage_chunks, (unsigned)gridA, nblocks_total, dout + p0, nullptr, nullptr, nullptr);
-            if (rc) return rc;
-        }
-        if (gridA > 0) {
-            rc = outp ? launch_qk<false, true>(ctx, gridA, smem, stream, 0, nA, dXp, Pc, stage_chunks, 0u, nblocks_total, dout + p0, expcf, logpl, deltacf)
-                      : launch_qk<false, false>(ctx, gridA, smem, stream, 0, nA, dXp, Pc, stage_chunks, 0u, nblocks_total, dout + p0, nullptr, nullptr, nullptr);
-            if (rc) return rc;
-        }
-        ctx->counters[0] += 1;
-        ctx->counters[1] += nq * (int64_t)Pc;
+        int rc, Pc;
+        if (left == 1) { Pc = 1; rc = launch_direct<1, false>(ctx, stream, dXp, 1, dout + p0, nullptr, nullptr, nullptr); }
+        else if (left == 2) { Pc = 2; rc = launch_direct<2, false>(ctx, stream, dXp, 2, dout + p0, nullptr, nullptr, nullptr); }
+        else { Pc = std::min(left, 4); rc = launch_direct<4, false>(ctx, stream, dXp, Pc, dout + p0, nullptr, nullptr, nullptr); }
+        if (rc) return rc;
+        p0 += Pc;
     }
     return SNAQ_OK;
 }
@@ -928,7 +942,7 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
         ctx->counters[1] += nq * (int64_t)P;
         return SNAQ_OK;
     }
-    // small batches: thread per quartet, QK_MAXP candidates per launch
+    // small batches: thread per quartet, up to 4 candidates per launch
     return eval_quartets_launch(ctx, P, dX, dout, stream, expcf, logpl, deltacf);
 }
 
@@ -970,7 +984,6 @@ int snaq_create(const snaq_opts *opts, snaq_ctx **out) {
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, ctx->device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
     ctx->sm_count = prop.multiProcessorCount;
-    if (const char *ev = getenv("SNAQ_QK_ITEMS")) { int v = atoi(ev); if (v == 1 || v == 2 || v == 4) ctx->qk_items = v; }
     if (const char *ev = getenv("SNAQ_LANES_WARPS")) { int v = atoi(ev); if (v == 8 || v == 12 || v == 16) ctx->lanes_warps = v; }
     if ((e = cudaMalloc((void **)&ctx->d_status, 4 * sizeof(uint32_t))) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cudaMalloc((void **)&ctx->d_total, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
@@ -986,7 +999,7 @@ int snaq_destroy(snaq_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_blob); cudaFree(ctx->d_xconst);
-    cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_status); cudaFree(ctx->d_total); cudaFree(ctx->d_ticket);
+    cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_WA); cudaFree(ctx->d_wpart); cudaFree(ctx->d_negw3); cudaFree(ctx->d_status); cudaFree(ctx->d_total); cudaFree(ctx->d_ticket);
     cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_XF); cudaFree(ctx->d_out); cudaFree(ctx->d_partial);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_qhdr); cudaFree(ctx->d_len4); cudaFree(ctx->d_iota); cudaFree(ctx->d_cls);
     cudaFree(ctx->d_cls_sorted);
@@ -1013,6 +1026,8 @@ int snaq_set_data(snaq_ctx *ctx, int32_t ntaxa, int64_t nq, const uint16_t *taxa
     ctx->has_net = false;
     ctx->has_sampled = false;
     cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_off); cudaFree(ctx->d_W);
+    cudaFree(ctx->d_WA); cudaFree(ctx->d_wpart); cudaFree(ctx->d_negw3);
+    ctx->d_WA = nullptr; ctx->d_wpart = nullptr; ctx->d_negw3 = nullptr;
     cudaFree(ctx->d_perm); cudaFree(ctx->d_qhdr); cudaFree(ctx->d_len4); cudaFree(ctx->d_iota); cudaFree(ctx->d_cls);
     cudaFree(ctx->d_cls_sorted);
     ctx->d_taxa = nullptr; ctx->d_obs = nullptr; ctx->d_sampled = nullptr; ctx->d_off = nullptr; ctx->d_W = nullptr;
@@ -1024,6 +1039,9 @@ int snaq_set_data(snaq_ctx *ctx, int32_t ntaxa, int64_t nq, const uint16_t *taxa
     CK(cudaMalloc((void **)&ctx->d_sampled, n));
     CK(cudaMalloc((void **)&ctx->d_off, (n + 1) * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&ctx->d_W, n * 4 * sizeof(double)));
+    CK(cudaMalloc((void **)&ctx->d_WA, n * sizeof(double2)));
+    CK(cudaMalloc((void **)&ctx->d_wpart, ((n + 255) / 256) * sizeof(double)));
+    CK(cudaMalloc((void **)&ctx->d_negw3, sizeof(double)));
     CK(cudaMalloc((void **)&ctx->d_perm, n * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&ctx->d_qhdr, n));
     CK(cudaMalloc((void **)&ctx->d_len4, n * sizeof(uint32_t)));
@@ -1091,7 +1109,7 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
     const int64_t nq = ctx->nq;
     ctx->prog_words = 0;
     ctx->maxlen = 1;
-    ctx->nA1 = ctx->nA = ctx->nB = ctx->nC = 0;
+    ctx->nA1 = ctx->nA2 = ctx->nA = ctx->nB = ctx->nC = 0;
     if (nq > 0) {
         // pass 1: program length (4-word chunks) and class of every quartet, original order
         CK(cudaMemsetAsync(ctx->d_total, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -1100,7 +1118,7 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
         k_build_count<<<(unsigned)nb, 128, 0, ctx->stream>>>(ctx->T, ctx->d_taxa, nq, ctx->d_len4, ctx->d_cls, ctx->d_iota,
                                                             ctx->d_total, ctx->d_status);
         CK(cudaGetLastError());
-        unsigned long long stt[6] = {0, 0, 0, 0, 0, 0};
+        unsigned long long stt[7] = {0, 0, 0, 0, 0, 0, 0};
         uint32_t st[4];
         CK(cudaMemcpyAsync(stt, ctx->d_total, sizeof(stt), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(st, ctx->d_status, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1109,11 +1127,11 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
         if (stt[0] >= 0xFFFFFFFFull) { ctx->err = "descriptor table exceeds 2^32 chunks on one GPU: shard the quartets (world_size>1)"; return SNAQ_EINVAL; }
         ctx->prog_words = stt[0] * 4;
         ctx->maxlen = (uint32_t)stt[1];
-        ctx->nA1 = (int64_t)stt[2];
-        ctx->nA = (int64_t)(stt[2] + stt[3]); ctx->nB = (int64_t)stt[4]; ctx->nC = (int64_t)stt[5];
-        // stable sort of the quartet indices by class (2-bit keys): perm = sorted position -> original quartet
+        ctx->nA1 = (int64_t)stt[2]; ctx->nA2 = (int64_t)stt[3];
+        ctx->nA = (int64_t)(stt[2] + stt[3] + stt[4]); ctx->nB = (int64_t)stt[5]; ctx->nC = (int64_t)stt[6];
+        // stable sort of the quartet indices by class (3-bit keys): perm = sorted position -> original quartet
         size_t tmp = 0, tmp2 = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_cls, ctx->d_cls_sorted, ctx->d_iota, ctx->d_perm, nq, 0, 2, ctx->stream));
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_cls, ctx->d_cls_sorted, ctx->d_iota, ctx->d_perm, nq, 0, 3, ctx->stream));
         uint32_t *d_len_sorted = ctx->d_off + 1;
         CK(cub::DeviceScan::InclusiveSum(nullptr, tmp2, d_len_sorted, d_len_sorted, nq, ctx->stream));
         tmp = std::max(tmp, tmp2);
@@ -1124,7 +1142,7 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
             ctx->scan_tmp_cap = tmp;
         }
         size_t t1 = ctx->scan_tmp_cap;
-        CK(cub::DeviceRadixSort::SortPairs(ctx->d_scan_tmp, t1, ctx->d_cls, ctx->d_cls_sorted, ctx->d_iota, ctx->d_perm, nq, 0, 2, ctx->stream));
+        CK(cub::DeviceRadixSort::SortPairs(ctx->d_scan_tmp, t1, ctx->d_cls, ctx->d_cls_sorted, ctx->d_iota, ctx->d_perm, nq, 0, 3, ctx->stream));
         // lengths in sorted order, scanned in place => d_off[i+1] = end of program i (chunks)
         CK(cudaMemsetAsync(ctx->d_off, 0, sizeof(uint32_t), ctx->stream));
         k_gather_len<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_perm, ctx->d_len4, nq, d_len_sorted);
@@ -1146,6 +1164,11 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
         ctx->counters[3] += 40 + 16 + 16;
     }
     ctx->counters[4] = (int64_t)ctx->prog_words;
+    {   // bytes one single-call evaluation (k_eval_direct, P <= 4) streams from HBM
+        const int64_t nG = ctx->nq - ctx->nA1 - ctx->nA2;
+        const int64_t chunksG = (int64_t)(ctx->prog_words / 4) - ctx->nA1 - 2 * ctx->nA2;
+        ctx->counters[6] = ctx->nA1 * 24 + ctx->nA2 * 32 + nG * (32 + 4 + 1) + chunksG * 8;
+    }
     ctx->has_net = true;
     return SNAQ_OK;
 }

@@ -165,7 +165,7 @@ class Engine:
         self._chk(self.lib.snaq_get_counters(self.ctx, out))
         v = list(out)
         return dict(eval_launches=v[0], quartet_evals=v[1], h2d_bytes=v[2], d2h_bytes=v[3], descriptor_words=v[4],
-                    build_launches=v[5])
+                    build_launches=v[5], single_call_bytes=v[6])
 
 
 # ------------------------------------------------------------------------------------
