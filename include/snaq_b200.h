@@ -179,6 +179,11 @@ int snaq_get_descriptors(snaq_ctx *ctx, int8_t *which, int8_t *ntype,
  * streams from HBM                                                             */
 int snaq_get_counters(snaq_ctx *ctx, int64_t out[8]);
 
+/* diagnostics (only when the context was created with SNAQ_TRACE=1 in the environment): phase
+ * timestamps (globaltimer, ns) of the last single-call kernel launch, out[block*8 + k],
+ * k = 0 entry, 1 prologue done, 2 generic region done, 3 additive region done, 4 exit          */
+int snaq_get_trace(snaq_ctx *ctx, uint64_t *out, int32_t max_blocks, int32_t *nblocks);
+
 /* measurement aid for the FP64 roofline: best-of-5 rate of a DFMA microbenchmark kernel
  * (8 independent chains per thread, 8 blocks of 256 threads per SM), in TFLOP/s           */
 int snaq_measure_fp64_peak(snaq_ctx *ctx, double *tflops);

@@ -132,6 +132,10 @@ typedef struct SnaqTables {
      *   crow[c] + k+1 + o-1  o=1..k-1 type-3 term when the hit node is at position o
      *   crow[c] + 2k + i     i=0,1    -log(1-gammaz_i) capped at 10 (bad diamond I only)          */
     const uint16_t *crow;        /* [n_cycles] */
+    /* the D rows as flat slot lists (same order as the walk from the node up to the root): no pointer chasing
+     * when a kernel prologue expands x */
+    const uint32_t *dpath_off;   /* [n_int+1] */
+    const uint16_t *dpath_slot;
     /* leaf deletion order (net.leaf order; only the hasEdge parity descriptor needs it): */
     const uint16_t *blkmax;      /* per cycle position (offsets as cyc_slot): largest net.leaf index in that block */
     const uint16_t *hmax2;       /* [n_cycles] second largest net.leaf index in the hybrid's block, 0xFFFF if single */
@@ -631,7 +635,8 @@ SNAQ_HD double snaq_expand_row(const SnaqTables &T, const SnaqMath &M, const dou
     int k = row - T.n_xe - 1;
     if (k < T.n_int) {
         double d = 0.0;
-        for (int v = T.dnode[k]; T.parent[v] != v; v = T.parent[v]) d += snaq_xe(T, x, xconst, T.pslot[v]);
+        const uint32_t i1 = T.dpath_off[k + 1];
+        for (uint32_t i = T.dpath_off[k]; i < i1; i++) d += snaq_xe(T, x, xconst, T.dpath_slot[i]);
         return d;
     }
     /* cycle rows: find the cycle (few cycles: linear search) */

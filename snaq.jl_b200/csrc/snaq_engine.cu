@@ -136,10 +136,12 @@ __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_
 }
 
 // lengths in class-sorted order (then scanned in place into offsets)
+// pad_at: sorted position whose program gets one extra (all-NULL) chunk, or -1: keeps the two-chunk region
+// 16-byte aligned for the bulk copies of k_eval_direct
 __global__ void __launch_bounds__(256) k_gather_len(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ len4,
-                                                    int64_t nq, uint32_t *__restrict__ out) {
+                                                    int64_t nq, int64_t pad_at, uint32_t *__restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nq) out[i] = len4[perm[i]];
+    if (i < nq) out[i] = len4[perm[i]] + (i == pad_at ? 1u : 0u);
 }
 
 // pass 2 (sorted order): emit the program of quartet perm[i] at chunk offset off[i], NULL-padded
@@ -481,40 +483,88 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
 
 /*
  * Thread per quartet (class-sorted order), at most PC candidates per launch: the HBM-bound path of a single
- * objective call (P = 1) and of small batches.  One persistent launch, no staging: every byte is read once by
- * exactly one thread, so the loads are plain coalesced 8/16-byte loads, four quartets in flight per thread.
- *   prologue : every block expands x into xf (snaq_expand_row) in shared memory, PC rows
- *   region A1: [0,nA1)         additive one-chunk programs:  16 B weights + 8 B program per quartet,
- *                              program i is chunk i (no offset load)
- *   region A2: [nA1,nA1+nA2)   additive two-chunk programs: 16 B + 16 B, program i at chunk nA1 + 2 (i - nA1)
- *   region G : the rest        (longer additive programs, type-2/4 terms, 4-cycles) through the generic
- *                              evaluator; a warp stages the contiguous program span of its 32 quartets in
- *                              shared memory with coalesced loads
- *   Every region is strided over all threads of the grid, so the load is balanced by construction.
+ * objective call (P = 1) and of small batches.  One persistent launch, no block-level synchronisation in the
+ * main loops: every WARP owns a ring of QD_NST shared-memory stages fed by TMA bulk copies (cp.async.bulk +
+ * one mbarrier per stage), so loads stay in flight without holding registers and a warp only ever waits for
+ * its own data.
+ *   entry    : lane 0 of every warp starts the bulk copies of the warp's first QD_NST tiles, THEN
+ *   prologue : the block expands x into xf (snaq_expand_row) in shared memory, PC rows
+ *   region G : everything that is not a short additive program (longer additive programs, type-2/4 terms,
+ *              4-cycles) through the generic evaluator, 32 consecutive quartets per warp step; the warp
+ *              stages the contiguous program span of its quartets in shared memory with coalesced loads
+ *   region A : tiles of QD_TQ = 64 additive quartets, strided over all warps of the grid.  Tile of
+ *              A1 [0,nA1): 16 B weight pair + one 8 B program chunk per quartet (program i = chunk i);
+ *              A2 [nA1,nA1+nA2): 16 B + two chunks (program j at chunk a2base + 2 j; a2base is even so
+ *              that the bulk copies are 16-byte aligned).  Each tile = two bulk copies (1 KB + 0.5-1 KB).
  *   epilogue : thread-private sums -> fixed-order block reduction -> partial[block][p]; the last block to
- *              finish (atomic ticket) adds all partials in block order: out[p] = -(sum) + sum of the class-A
- *              constants W3 (negw3 = -sum_A W3, precomputed with the weights).  Bit-reproducible.
+ *              finish (atomic ticket) adds all partials in block order: out[p] = -(sum) + sum of the A1/A2
+ *              constants W3 (negw3 = -sum W3, precomputed with the weights).  Bit-reproducible.
  * OUT: per-quartet results (P = 1) at the quartet's ORIGINAL index (expcf [nq][3] in data order, logpl [nq],
  * deltacf [nq]); every quartet goes through the generic evaluator.
  */
-#define QD_SPAN 192   /* program chunks a warp can stage for its 32 quartets (else: read from global memory) */
+#define QD_SPAN 96     /* program chunks a warp can stage for its 32 quartets (else: read from global memory) */
+#define QD_TQ 64       /* additive quartets per warp tile */
+#define QD_NST 3       /* stages per warp */
+#define QD_STAGE_BYTES (QD_TQ * 32)
 template <int PC, bool OUT>
 __global__ void __launch_bounds__(256, OUT ? 2 : 3)
 k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restrict__ prog2, const uint8_t *__restrict__ qhdr,
               const uint32_t *__restrict__ perm, const double2 *__restrict__ WA, const double4 *__restrict__ W,
-              const double *__restrict__ obs, uint32_t nA1, uint32_t nA2, uint32_t nQ, const double *__restrict__ X,
-              const double *__restrict__ xconst, int nh, int nt, int P, double *__restrict__ partial, double *__restrict__ out,
-              const double *__restrict__ negw3, unsigned int *__restrict__ ticket, double *__restrict__ expcf,
-              double *__restrict__ logpl, double *__restrict__ deltacf, uint32_t *__restrict__ status) {
+              const double *__restrict__ obs, uint32_t nA1, uint32_t nA2, uint32_t a2base, uint32_t nQ,
+              const double *__restrict__ X, const double *__restrict__ xconst, int nh, int nt, int P,
+              double *__restrict__ partial, double *__restrict__ out, const double *__restrict__ negw3,
+              unsigned int *__restrict__ ticket, double *__restrict__ expcf, double *__restrict__ logpl,
+              double *__restrict__ deltacf, uint32_t *__restrict__ status, unsigned long long *__restrict__ trace) {
     constexpr int BLOCK = 256;
     extern __shared__ __align__(128) unsigned char smem[];
-    double *mt = reinterpret_cast<double *>(smem);                       // 48 doubles, 128-byte aligned
-    double *red = reinterpret_cast<double *>(smem + 384);                // [8][PC] warp sums
-    uint2 *span = reinterpret_cast<uint2 *>(smem + 384 + 8 * PC * 8);    // [8 warps][QD_SPAN] staged programs
-    double *xs = reinterpret_cast<double *>(smem + 384 + 8 * PC * 8 + 8 * QD_SPAN * 8);   // [PC][n_full]
+    double *mt = reinterpret_cast<double *>(smem);                        // 48 doubles, 128-byte aligned
+    // optional phase timeline (diagnostics, SNAQ_TRACE=1): globaltimer of thread 0 at entry / after the prologue /
+    // after region G / after region A / at exit
+    auto stamp = [&](int k) {
+        if (trace && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            trace[(size_t)blockIdx.x * 8 + k] = t;
+        }
+    };
+    stamp(0);
+    static_assert(8 * QD_NST * 8 <= 256, "mbarrier area");
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 384);            // [8 warps][QD_NST] mbarriers (<= 256 B)
+    double *red = reinterpret_cast<double *>(smem + 640);                 // [8][PC] warp sums
+    uint2 *span = reinterpret_cast<uint2 *>(smem + 640 + 8 * PC * 8);     // [8 warps][QD_SPAN] staged programs
+    unsigned char *ring = smem + 640 + 8 * PC * 8 + 8 * QD_SPAN * 8;      // [8 warps][QD_NST][QD_STAGE_BYTES]
+    double *xs = reinterpret_cast<double *>(ring + (OUT ? 0 : 8 * QD_NST * QD_STAGE_BYTES));   // [PC][n_full]
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const int n_full = T.n_full;
     unsigned st = 0;
+    const unsigned gwarp = blockIdx.x * (BLOCK / 32) + warp, nwarps = gridDim.x * (BLOCK / 32);
+    const unsigned tA1 = (nA1 + QD_TQ - 1) / QD_TQ, tA2 = (nA2 + QD_TQ - 1) / QD_TQ, tA = tA1 + tA2;
+    uint64_t *wbar = bars + warp * QD_NST;
+    unsigned char *wring = ring + (size_t)warp * QD_NST * QD_STAGE_BYTES;
+    // a tile's two bulk copies: weight pairs to the first 2 KB of the stage, program chunks behind them
+    auto issue = [&](unsigned t, unsigned s) {                            // lane 0 only
+        unsigned char *dst = wring + s * QD_STAGE_BYTES;
+        if (t < tA1) {
+            const unsigned i0 = t * QD_TQ, n = min((unsigned)QD_TQ, nA1 - i0);
+            const unsigned pb = ((n + 1u) & ~1u) * 8u;
+            mbar_expect_tx(&wbar[s], n * 16u + pb);
+            tma_load_1d(dst, WA + i0, n * 16u, &wbar[s]);
+            tma_load_1d(dst + QD_TQ * 16, prog2 + i0, pb, &wbar[s]);
+        } else {
+            const unsigned j0 = (t - tA1) * QD_TQ, n = min((unsigned)QD_TQ, nA2 - j0);
+            mbar_expect_tx(&wbar[s], n * 32u);
+            tma_load_1d(dst, WA + nA1 + j0, n * 16u, &wbar[s]);
+            tma_load_1d(dst + QD_TQ * 16, prog2 + a2base + 2u * j0, n * 16u, &wbar[s]);
+        }
+    };
+    if (!OUT) {
+        if (lane == 0) {
+            for (int k = 0; k < QD_NST; k++) mbar_init(&wbar[k], 1);
+            for (unsigned k = 0; k < QD_NST; k++)
+                if (gwarp + k * nwarps < tA) issue(gwarp + k * nwarps, k);
+        }
+        __syncwarp();
+    }
     const SnaqMath M = load_math_tables(mt, (int)tid);
     // prologue: expanded parameter vectors (and the bounds check of update!); unused rows repeat the last candidate
     for (int idx = (int)tid; idx < PC * n_full; idx += BLOCK) {
@@ -524,77 +574,22 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
         xs[idx] = snaq_expand_row(T, M, x, xconst, row);
     }
     __syncthreads();
-    const unsigned gtid = blockIdx.x * BLOCK + tid, nthr = gridDim.x * BLOCK;
+    stamp(1);
     double acc[PC];
 #pragma unroll
     for (int p = 0; p < PC; p++) acc[p] = 0.0;
-    const unsigned nullpair = (unsigned)T.n_xe * 0x10001u;
-    auto tree_term = [&](double t, const double2 &w) {                    // one additive quartet, one candidate
-        const double t1 = fmin(t, 10.0);
-        const double y = snaq_exp(-t1, M);
-        const double major = fma(SNAQ_K_M23, y, 1.0);
-        return fma(w.x, snaq_log_pos(major, M), -w.y * (t1 + SNAQ_K_LOG3));
-    };
-    if (!OUT) {
-        // ---- region A1 -------------------------------------------------------------------------------
-#pragma unroll 1
-        for (unsigned i0 = gtid; i0 < nA1; i0 += 4u * nthr) {
-            double2 w[4];
-            uint2 c[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const unsigned i = i0 + (unsigned)k * nthr;
-                const bool ok = i < nA1;
-                w[k] = ok ? __ldg(WA + i) : make_double2(0.0, 0.0);
-                c[k] = ok ? __ldg(prog2 + i) : make_uint2(nullpair, nullpair);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-#pragma unroll
-                for (int p = 0; p < PC; p++) {
-                    const double *xp = xs + p * n_full;
-                    const double t = (xp[c[k].x & 0xffffu] - xp[c[k].x >> 16]) + (xp[c[k].y & 0xffffu] - xp[c[k].y >> 16]);
-                    acc[p] += tree_term(t, w[k]);
-                }
-            }
-        }
-        // ---- region A2 -------------------------------------------------------------------------------
-#pragma unroll 1
-        for (unsigned j0 = gtid; j0 < nA2; j0 += 2u * nthr) {
-            double2 w[2];
-            uint2 c[2][2];
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const unsigned j = j0 + (unsigned)k * nthr;
-                const bool ok = j < nA2;
-                w[k] = ok ? __ldg(WA + nA1 + j) : make_double2(0.0, 0.0);
-                c[k][0] = ok ? __ldg(prog2 + nA1 + 2u * j) : make_uint2(nullpair, nullpair);
-                c[k][1] = ok ? __ldg(prog2 + nA1 + 2u * j + 1u) : make_uint2(nullpair, nullpair);
-            }
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-#pragma unroll
-                for (int p = 0; p < PC; p++) {
-                    const double *xp = xs + p * n_full;
-                    double ta = xp[c[k][0].x & 0xffffu] - xp[c[k][0].x >> 16], tb = xp[c[k][0].y & 0xffffu] - xp[c[k][0].y >> 16];
-                    ta += xp[c[k][1].x & 0xffffu] - xp[c[k][1].x >> 16];
-                    tb += xp[c[k][1].y & 0xffffu] - xp[c[k][1].y >> 16];
-                    acc[p] += tree_term(ta + tb, w[k]);
-                }
-            }
-        }
-    }
     // ---- region G (everything when OUT) ---------------------------------------------------------------
     {
         const unsigned g0 = OUT ? 0u : nA1 + nA2;
         uint2 *wspan = span + warp * QD_SPAN;
-        const unsigned wstride = nthr;                        // a warp's 32 quartets are consecutive
 #pragma unroll 1
-        for (unsigned ib = g0 + (gtid - lane); ib < nQ; ib += wstride) {
+        for (unsigned ib = g0 + gwarp * 32u; ib < nQ; ib += nwarps * 32u) {
             const unsigned i = ib + lane;
             const bool active = i < nQ;
             const unsigned ilast = min(ib + 32u, nQ);
             const uint32_t o0 = active ? __ldg(off + i) : 0u, o1 = active ? __ldg(off + i + 1) : 0u;
+            const unsigned hdr = active ? (unsigned)qhdr[i] : 0u;
+            const double4 w4 = active ? W[i] : make_double4(0, 0, 0, 0);
             const uint32_t s0 = __shfl_sync(0xffffffffu, o0, 0);
             const uint32_t s1 = __ldg(off + ilast);
             const bool staged = (s1 - s0) <= (uint32_t)QD_SPAN;
@@ -602,8 +597,6 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
             if (staged) for (uint32_t c = s0 + lane; c < s1; c += 32u) wspan[c - s0] = __ldg(prog2 + c);
             __syncwarp();
             if (active) {
-                const unsigned hdr = (unsigned)qhdr[i];
-                const double4 w4 = W[i];
                 const double w[4] = {w4.x, w4.y, w4.z, w4.w};
                 const uint16_t *pc = reinterpret_cast<const uint16_t *>(staged ? wspan + (o0 - s0) : prog2 + o0);
                 const int nwords = (int)(o1 - o0) * 4;
@@ -633,7 +626,64 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
             }
         }
     }
+    stamp(2);
+    // ---- region A: warp-private TMA ring ------------------------------------------------------------------
+    if (!OUT) {
+        const unsigned nullpair = (unsigned)T.n_xe * 0x10001u;
+        auto tree_term = [&](double t, const double2 &w) {                // one additive quartet, one candidate
+            const double t1 = fmin(t, 10.0);
+            const double y = snaq_exp(-t1, M);
+            const double major = fma(SNAQ_K_M23, y, 1.0);
+            return fma(w.x, snaq_log_pos(major, M), -w.y * (t1 + SNAQ_K_LOG3));
+        };
+        unsigned s = 0, phase = 0;
+#pragma unroll 1
+        for (unsigned t = gwarp; t < tA; t += nwarps) {
+            mbar_wait(&wbar[s], phase);
+            const unsigned char *stg = wring + s * QD_STAGE_BYTES;
+            const double2 *sw = reinterpret_cast<const double2 *>(stg);
+            if (t < tA1) {
+                const unsigned n = min((unsigned)QD_TQ, nA1 - t * QD_TQ);
+                const uint2 *sp = reinterpret_cast<const uint2 *>(stg + QD_TQ * 16);
+#pragma unroll
+                for (int k = 0; k < QD_TQ / 32; k++) {
+                    const unsigned idx = (unsigned)k * 32u + lane;
+                    const bool ok = idx < n;
+                    const double2 w = ok ? sw[idx] : make_double2(0.0, 0.0);
+                    const uint2 c = ok ? sp[idx] : make_uint2(nullpair, nullpair);
+#pragma unroll
+                    for (int p = 0; p < PC; p++) {
+                        const double *xp = xs + p * n_full;
+                        const double tt = (xp[c.x & 0xffffu] - xp[c.x >> 16]) + (xp[c.y & 0xffffu] - xp[c.y >> 16]);
+                        acc[p] += tree_term(tt, w);
+                    }
+                }
+            } else {
+                const unsigned n = min((unsigned)QD_TQ, nA2 - (t - tA1) * QD_TQ);
+                const uint4 *sp = reinterpret_cast<const uint4 *>(stg + QD_TQ * 16);
+#pragma unroll
+                for (int k = 0; k < QD_TQ / 32; k++) {
+                    const unsigned idx = (unsigned)k * 32u + lane;
+                    const bool ok = idx < n;
+                    const double2 w = ok ? sw[idx] : make_double2(0.0, 0.0);
+                    const uint4 c = ok ? sp[idx] : make_uint4(nullpair, nullpair, nullpair, nullpair);
+#pragma unroll
+                    for (int p = 0; p < PC; p++) {
+                        const double *xp = xs + p * n_full;
+                        double ta = xp[c.x & 0xffffu] - xp[c.x >> 16], tb = xp[c.y & 0xffffu] - xp[c.y >> 16];
+                        ta += xp[c.z & 0xffffu] - xp[c.z >> 16];
+                        tb += xp[c.w & 0xffffu] - xp[c.w >> 16];
+                        acc[p] += tree_term(ta + tb, w);
+                    }
+                }
+            }
+            __syncwarp();                                                  // every lane is done with stage s
+            if (lane == 0 && t + QD_NST * nwarps < tA) issue(t + QD_NST * nwarps, s);
+            if (++s == QD_NST) { s = 0; phase ^= 1u; }
+        }
+    }
     if (st) atomicOr(status, st);
+    stamp(3);
     // ---- epilogue: fixed-order block reduction, then the last block adds the partials in block order -----
 #pragma unroll
     for (int p = 0; p < PC; p++) {
@@ -672,6 +722,7 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
         }
         if (tid == 0) *ticket = 0u;
     }
+    stamp(4);
 }
 
 // out[p] = -(sum over blocks of partial[b][p]), fixed order (logPseudoLik(d): src/pseudolik.jl:1417-1423).
@@ -768,6 +819,8 @@ struct snaq_ctx {
     uint8_t *d_cls = nullptr, *d_cls_sorted = nullptr;
     int64_t nA1 = 0, nA2 = 0, nA = 0, nB = 0, nC = 0;   // nA1: leading class-A quartets whose program is exactly one chunk (off[i] == i)
     uint32_t *d_status = nullptr;          // [0] build, [1] eval
+    unsigned long long *d_trace = nullptr; // SNAQ_TRACE=1: [blocks][8] phase timestamps of the last k_eval_direct launch
+    int trace_blocks = 0;
     unsigned int *d_ticket = nullptr;      // last-block ticket of k_eval_direct (reset by the kernel)
     unsigned long long *d_total = nullptr; // build statistics: total chunks, max chunks, class counts
     void *d_scan_tmp = nullptr;
@@ -851,18 +904,20 @@ template <int PC, bool OUT>
 static int launch_direct(snaq_ctx *ctx, cudaStream_t stream, const double *dX, int Pc, double *dout, double *expcf, double *logpl,
                          double *deltacf) {
     const SnaqHostTables &H = ctx->H;
-    const size_t smem = 384 + 8 * PC * 8 + 8 * QD_SPAN * 8 + (size_t)PC * H.n_full * 8;
-    if (smem > 64 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_direct"; return SNAQ_EINVAL; }
-    const int per_sm = OUT ? 2 : 3;
+    const size_t smem = 640 + 8 * PC * 8 + 8 * QD_SPAN * 8 + (OUT ? 0 : 8 * QD_NST * QD_STAGE_BYTES) + (size_t)PC * H.n_full * 8;
+    if (smem > 200 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_direct"; return SNAQ_EINVAL; }
+    const int per_sm = (int)std::min<size_t>(OUT ? 2 : 3, (225 * 1024) / (smem + 1024));
     const int64_t work = (ctx->nq + 255) / 256;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(work, (int64_t)ctx->sm_count * per_sm));
     int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)grid * PC);
     if (rc) return rc;
+    if (ctx->d_trace) ctx->trace_blocks = grid;
     CK(cudaFuncSetAttribute(k_eval_direct<PC, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_eval_direct<PC, OUT><<<grid, 256, smem, stream>>>(
         ctx->T, ctx->d_off, reinterpret_cast<const uint2 *>(ctx->d_prog), ctx->d_qhdr, ctx->d_perm, ctx->d_WA,
-        reinterpret_cast<const double4 *>(ctx->d_W), ctx->d_obs, (uint32_t)ctx->nA1, (uint32_t)ctx->nA2, (uint32_t)ctx->nq, dX,
-        ctx->d_xconst, H.nh, H.nt, Pc, ctx->d_partial, dout, ctx->d_negw3, ctx->d_ticket, expcf, logpl, deltacf, ctx->d_status + 1);
+        reinterpret_cast<const double4 *>(ctx->d_W), ctx->d_obs, (uint32_t)ctx->nA1, (uint32_t)ctx->nA2,
+        (uint32_t)(ctx->nA1 + (ctx->nA1 & 1)), (uint32_t)ctx->nq, dX,
+        ctx->d_xconst, H.nh, H.nt, Pc, ctx->d_partial, dout, ctx->d_negw3, ctx->d_ticket, expcf, logpl, deltacf, ctx->d_status + 1, ctx->d_trace);
     CK(cudaGetLastError());
     ctx->counters[0] += 1;
     ctx->counters[1] += ctx->nq * (int64_t)Pc;
@@ -984,6 +1039,9 @@ int snaq_create(const snaq_opts *opts, snaq_ctx **out) {
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, ctx->device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char *ev = getenv("SNAQ_TRACE")) {
+        if (atoi(ev) > 0 && cudaMalloc((void **)&ctx->d_trace, (size_t)ctx->sm_count * 4 * 8 * sizeof(unsigned long long)) != cudaSuccess) ctx->d_trace = nullptr;
+    }
     if (const char *ev = getenv("SNAQ_LANES_WARPS")) { int v = atoi(ev); if (v == 8 || v == 12 || v == 16) ctx->lanes_warps = v; }
     if ((e = cudaMalloc((void **)&ctx->d_status, 4 * sizeof(uint32_t))) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cudaMalloc((void **)&ctx->d_total, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
@@ -999,7 +1057,7 @@ int snaq_destroy(snaq_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_blob); cudaFree(ctx->d_xconst);
-    cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_WA); cudaFree(ctx->d_wpart); cudaFree(ctx->d_negw3); cudaFree(ctx->d_status); cudaFree(ctx->d_total); cudaFree(ctx->d_ticket);
+    cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_WA); cudaFree(ctx->d_wpart); cudaFree(ctx->d_negw3); cudaFree(ctx->d_status); cudaFree(ctx->d_total); cudaFree(ctx->d_ticket); cudaFree(ctx->d_trace);
     cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_XF); cudaFree(ctx->d_out); cudaFree(ctx->d_partial);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_qhdr); cudaFree(ctx->d_len4); cudaFree(ctx->d_iota); cudaFree(ctx->d_cls);
     cudaFree(ctx->d_cls_sorted);
@@ -1145,7 +1203,9 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
         CK(cub::DeviceRadixSort::SortPairs(ctx->d_scan_tmp, t1, ctx->d_cls, ctx->d_cls_sorted, ctx->d_iota, ctx->d_perm, nq, 0, 3, ctx->stream));
         // lengths in sorted order, scanned in place => d_off[i+1] = end of program i (chunks)
         CK(cudaMemsetAsync(ctx->d_off, 0, sizeof(uint32_t), ctx->stream));
-        k_gather_len<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_perm, ctx->d_len4, nq, d_len_sorted);
+        const int64_t pad_at = (ctx->nA1 & 1) ? ctx->nA1 - 1 : -1;
+        if (pad_at >= 0) ctx->prog_words += 4;
+        k_gather_len<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_perm, ctx->d_len4, nq, pad_at, d_len_sorted);
         CK(cudaGetLastError());
         t1 = ctx->scan_tmp_cap;
         CK(cub::DeviceScan::InclusiveSum(ctx->d_scan_tmp, t1, d_len_sorted, d_len_sorted, nq, ctx->stream));
@@ -1373,6 +1433,18 @@ int snaq_measure_fp64_peak(snaq_ctx *ctx, double *tflops) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *tflops = best;
+    return SNAQ_OK;
+}
+
+int snaq_get_trace(snaq_ctx *ctx, uint64_t *out, int32_t max_blocks, int32_t *nblocks) {
+    if (!ctx || !nblocks) return SNAQ_EINVAL;
+    *nblocks = 0;
+    if (!ctx->d_trace) return SNAQ_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int n = std::min(ctx->trace_blocks, (int)max_blocks);
+    if (n > 0 && out) CK(cudaMemcpy(out, ctx->d_trace, (size_t)n * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    *nblocks = n;
     return SNAQ_OK;
 }
 

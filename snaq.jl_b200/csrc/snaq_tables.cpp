@@ -37,6 +37,8 @@ SnaqTables SnaqHostTables::view(const unsigned char *b) const {
     T.dslot = (const uint16_t *)(b + off_dslot);
     T.dnode = (const uint16_t *)(b + off_dnode);
     T.crow = (const uint16_t *)(b + off_crow);
+    T.dpath_off = (const uint32_t *)(b + off_dpath_off);
+    T.dpath_slot = (const uint16_t *)(b + off_dpath_slot);
     T.blkmax = (const uint16_t *)(b + off_blkmax);
     T.hmax2 = (const uint16_t *)(b + off_hmax2);
     T.hmaxtax = (const uint16_t *)(b + off_hmaxtax);
@@ -324,6 +326,14 @@ int snaq_build_tables(const snaq_flatnet *f, int ntaxa, SnaqHostTables &o, std::
         o.off_dslot = put(o.blob, dslot);
         o.off_dnode = put(o.blob, dnode);
         o.off_crow = put(o.blob, crow);
+        std::vector<uint32_t> dpath_off(1, 0);
+        std::vector<uint16_t> dpath_slot;
+        for (uint16_t v0 : dnode) {
+            for (int v = v0; t_parent[v] != v; v = t_parent[v]) dpath_slot.push_back(t_pslot[v]);
+            dpath_off.push_back((uint32_t)dpath_slot.size());
+        }
+        o.off_dpath_off = put(o.blob, dpath_off);
+        o.off_dpath_slot = put(o.blob, dpath_slot);
         // leaf deletion order statistics per cycle block (hasEdge parity descriptor)
         std::vector<int> leafOrderOfTaxon(std::max(ntaxa, 1), -1);
         for (int i = 0; i < f->n_leaves; i++) {

@@ -24,7 +24,7 @@ struct SnaqHostTables {
     // one contiguous blob holding every table (uploaded to the device as is)
     std::vector<unsigned char> blob;
     size_t off_leaf_tnode = 0, off_parent = 0, off_depth = 0, off_tcycle = 0, off_pslot = 0, off_blk = 0,
-           off_cyc_k = 0, off_cyc_off = 0, off_cyc_slot = 0, off_cyc_gslot = 0, off_cyc_flags = 0, off_cyc_hyb = 0, off_torder = 0, off_cyc_order = 0, off_dslot = 0, off_dnode = 0, off_crow = 0, off_blkmax = 0, off_hmax2 = 0, off_hmaxtax = 0;
+           off_cyc_k = 0, off_cyc_off = 0, off_cyc_slot = 0, off_cyc_gslot = 0, off_cyc_flags = 0, off_cyc_hyb = 0, off_torder = 0, off_cyc_order = 0, off_dslot = 0, off_dnode = 0, off_crow = 0, off_dpath_off = 0, off_dpath_slot = 0, off_blkmax = 0, off_hmax2 = 0, off_hmaxtax = 0;
     // extra tables used only by the hasEdge (parity descriptor) kernel
     std::vector<int32_t> edge_slot;                  // per net edge: xe slot or -1
     SnaqTables view(const unsigned char *base) const;
