@@ -103,5 +103,9 @@ with open(f"profiles/{tag}_ncu_summary.md", "w") as fh:
     fh.write("## launch list (`ncu --metrics gpu__time_duration.sum -c 400`)\n\n")
     launches(f"{GO}/{tag}_launches.csv", fh)
     kernel_summary(f"{GO}/{tag}_lanes.ncu-rep", "k_eval_lanes (config 2: 27,405 quartets x 4096 vectors)", fh)
-    kernel_summary(f"{GO}/{tag}_quartets.ncu-rep", "k_eval_quartets (100 taxa, 3.92 M quartets, P=1)", fh)
+    import os
+    if os.path.exists(f"{GO}/{tag}_quartets.ncu-rep"):
+        kernel_summary(f"{GO}/{tag}_quartets.ncu-rep", "k_eval_quartets (100 taxa, 3.92 M quartets, P=1)", fh)
+    if os.path.exists(f"{GO}/{tag}_direct.ncu-rep"):
+        kernel_summary(f"{GO}/{tag}_direct.ncu-rep", "k_eval_direct (100 taxa, 3.92 M quartets, P=1; `python profiles/run_single_call.py`)", fh)
 print("wrote", f"profiles/{tag}_ncu_summary.md")

@@ -32,7 +32,7 @@ _LIB = None
 EXPORTS = ["snaq_create", "snaq_destroy", "snaq_last_error", "snaq_version", "snaq_set_data", "snaq_set_obscf",
            "snaq_set_sampled", "snaq_set_network", "snaq_patch_network", "snaq_num_params", "snaq_get_params",
            "snaq_eval", "snaq_eval_device", "snaq_eval_quartets", "snaq_get_descriptors", "snaq_get_counters",
-           "snaq_check_status", "snaq_measure_fp64_peak"]
+           "snaq_check_status", "snaq_measure_fp64_peak", "snaq_get_trace"]
 
 
 class _Opts(C.Structure):
