@@ -160,6 +160,41 @@ int snaq_check_status(snaq_ctx *ctx);
 int snaq_eval_quartets(snaq_ctx *ctx, int32_t nparams, const double *x,
                        double *expcf, double *logpl, double *deltacf);
 
+/* ---- optBL!: src/snaq_optimization.jl:341-390 --------------------------- */
+/* Objective and its gradient in ONE pass over the quartets: *f = logPseudoLik at x, grad[i] = d f / d x[i]
+ * (analytic, through the closed forms of src/pseudolik.jl:878,938,951,985-991,1259; one-sided at the
+ * 10.0 caps of setLength!, where the reference's objective has a kink; inside the flat -1e15 plateau of a
+ * negative expCF, src/pseudolik.jl:1394-1396, the slope of 1e6*expCF so that a descent method can leave it).
+ * hdiag[i] (may be NULL; costs extra work) = the contribution of the tree-like quartets without hybrid terms
+ * to d2 f / d x[i]^2 for edge lengths, 0 for gammas: the initial metric of the quasi-Newton update.           */
+int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f,
+                   double *grad, double *hdiag);
+
+#define SNAQ_OPTBL_FD       1u   /* flags: finite-difference gradients (2n vectors per launch) instead of snaq_eval_grad */
+/* result status, NLopt's numbering (the reference only prints it: src/snaq_optimization.jl:384-386) */
+#define SNAQ_OPTBL_FTOL     3
+#define SNAQ_OPTBL_XTOL     4
+#define SNAQ_OPTBL_MAXEVAL  5
+typedef struct snaq_optbl_opts {
+    double ftol_rel, ftol_abs, xtol_rel, xtol_abs;   /* optBL!'s ftolRel, ftolAbs, xtolRel, xtolAbs (all > 0, :350) */
+    int32_t maxeval;     /* NLopt.maxeval! = 1000 in the reference (:365); here: engine launches (each a batch)    */
+    int32_t ladder;      /* step lengths tried per line-search launch (default 20)                              */
+    uint32_t flags;      /* SNAQ_OPTBL_*                                                                         */
+    uint32_t reserved;
+} snaq_optbl_opts;
+typedef struct snaq_optbl_result {
+    double fmin;         /* loglik!(net, fmin): :388                                                            */
+    double proj_grad;    /* max-norm of the projected gradient at xmin                                          */
+    int32_t nevals;      /* parameter vectors evaluated                                                         */
+    int32_t nlaunches;   /* engine launches (batches)                                                           */
+    int32_t niter;
+    int32_t status;      /* SNAQ_OPTBL_FTOL / XTOL / MAXEVAL                                                    */
+} snaq_optbl_result;
+/* Optimises every parameter of the current network within [0, upper(net)].  x: in = ht(net) (the start, as
+ * NLopt.optimize(opt, ht(net)) :383), out = xmin (what updateParameters!(net, xmin) :387 receives).
+ * opts may be NULL (the search-time tolerances fRel, fAbs, xRel, xAbs of :36-39).                          */
+int snaq_optbl(snaq_ctx *ctx, const snaq_optbl_opts *opts, double *x, snaq_optbl_result *res);
+
 /* ---- descriptors for parity checks ------------------------ */
 /* which[nq]       : 1 tree-like, 2 four-cycle (src/types.jl:180)
  * ntype[nq], types[nq*max_types]: typeHyb codes (2..5; type 1 dropped) of the

@@ -99,6 +99,7 @@
 #define SNAQ_S_ZEROSUM     2u  /* sum(expCF)==0: src/pseudolik.jl:1391            */
 #define SNAQ_S_NAN         4u
 
+#define SNAQ_PENALTY_SLOPE 1.0e6
 #define SNAQ_MINLEN (-0.4054651081081644)
 #define SNAQ_LOG3   1.0986122886681098
 
@@ -843,6 +844,233 @@ SNAQ_HD double snaq_quartet_loglik(unsigned kind, const double cf[3], double t1,
         return snaq_loglik_tree(t1, cf[0], W, M);
     }
     return snaq_loglik_t5(cf, W, M, status);
+}
+
+/* ------------------------------------------------------------------------------
+ * objective + gradient (snaq_eval_grad).  For one quartet: returns its value v (what snaq_quartet_loglik
+ * returns) and calls add(slot, dv/d xf[slot]) for every slot of the expanded vector its program reads.
+ * The chain rule through the rows of xf that are not plain parameters (prefix sums, type-3 terms,
+ * -log(1-gammaz)) is snaq_grad_backprop below.  At a 10.0 cap (setLength!: src/auxiliary.jl:122-124) the
+ * derivative of the capped quantity is taken as 0 (the side on which the cap is active).
+ * ------------------------------------------------------------------------------ */
+template <class XF, class ADD>
+SNAQ_HD void snaq_grad_pairs(const uint16_t *&pc, int n, const XF &x, unsigned nul, double gcoef, ADD &add) {
+    SNAQ_UNROLL1
+    for (int i = 0; i < n; i++) {
+        const unsigned p = pc[2 * i], m = pc[2 * i + 1];
+        if (p != nul) add(p, gcoef);
+        if (m != nul) add(m, -gcoef);
+    }
+    pc += 2 * n;
+}
+
+/* d v / d t1 of a tree-like quartet: v = W0 log(1 - 2/3 e^-t) - W1 (t + log 3) - W3 */
+SNAQ_HD double snaq_dv_dt_tree(double t1, const double W[4], const SnaqMath &M, double *major_out, double *curv_out = nullptr) {
+    const double a = 2.0 / 3.0 * snaq_exp(-t1, M);
+    const double major = 1.0 - a;
+    *major_out = major;
+    const double r = W[0] * a / major;
+    if (curv_out) *curv_out = r / major;      /* -d2 v / d t1^2 = W0 a / (1-a)^2 >= 0 */
+    return r - W[1];
+}
+
+/* addh(slot, c): curvature bins.  For an additive quartet t1 is a 0/1 combination of edge lengths, so the signed
+ * sums of -d2v/dt1^2 over the program's slots transpose (like the gradient) into the exact contribution of these
+ * quartets to the DIAGONAL of the Hessian of f with respect to the edge lengths; the other classes add nothing
+ * (the diagonal is only used as the initial metric of the quasi-Newton update). */
+template <class XF, class ADD, class ADDH>
+SNAQ_HD double snaq_grad_quartet(unsigned hdr, const uint16_t *pc, int nwords, const XF &x, const SnaqMath &M, const double W[4],
+                                 unsigned nul, ADD &add, ADDH &addh, unsigned &status) {
+    const unsigned kind = SNAQ_HDR_KIND(hdr);
+    if (kind == SNAQ_KIND_TREE && !SNAQ_HDR_TERMS(hdr)) {
+        /* class A */
+        double t = 0.0;
+        for (int i = 0; i < nwords; i += 2) t += x(pc[i]) - x(pc[i + 1]);
+        const double t1 = snaq_clamp10(t);
+        double major, curv;
+        const double gt = snaq_dv_dt_tree(t1, W, M, &major, &curv);
+        if (t <= 10.0) {
+            const uint16_t *p2 = pc;
+            snaq_grad_pairs(pc, nwords / 2, x, nul, gt, add);
+            snaq_grad_pairs(p2, nwords / 2, x, nul, curv, addh);
+        }
+        return snaq_loglik_tree(t1, major, W, M);
+    }
+    if (kind == SNAQ_KIND_TREE) {
+        /* class B: forward pass exactly as snaq_tree_terms_t1, remembering what the reverse pass needs */
+        const uint16_t *p0 = pc;
+        const double t1 = snaq_tree_terms_t1(pc, x, M, status);
+        double major;
+        const double gt1 = snaq_dv_dt_tree(t1, W, M, &major);
+        if (major < 0.0) status |= SNAQ_S_NEGLEN;
+        const double v = snaq_loglik_tree(t1, major, W, M);
+        /* recompute the intermediate sums (cheap) to know which caps are active */
+        pc = p0;
+        const unsigned cw = *pc++;
+        const int n0 = (int)(cw & 255u), nterms = (int)(cw >> 8);
+        const uint16_t *ppairs = pc;
+        double R = snaq_sum(pc, n0, x);
+        const uint16_t *pterms = pc;
+        double Bn = 0.0, Bf = 0.0;
+        for (int it = 0; it < nterms; it++) {
+            const unsigned th = *pc++;
+            const double gq = x(th >> 4);
+            if ((th & 3u) == SNAQ_T2) {
+                const double e = snaq_clamp10(x(pc[0]) - x(pc[1]));
+                pc += 2;
+                const double gh = (th & 4u) ? 1.0 - gq : gq;
+                R += snaq_clamp10(-snaq_log(1.0 - gh * (1.0 - snaq_exp(-e, M)), M));
+            } else {
+                const double clo = x(pc[0]), chi = x(pc[1]), ck = x(pc[2]);
+                const double la = snaq_clamp10(clo), lb = snaq_clamp10(ck - chi), le = snaq_clamp10(chi - clo);
+                const int nchain = pc[3];
+                pc += 4;
+                const double ch = snaq_clamp10(snaq_sum(pc, nchain, x));
+                const double ga = 1.0 - gq, gb = gq;
+                const double l4 = snaq_clamp10(-snaq_log(gb * gb * snaq_exp(-lb, M) + ga * gb * (3.0 - snaq_exp(-le, M)) + ga * ga * snaq_exp(-la, M), M));
+                const double B = snaq_clamp10(ch + l4);
+                if (th & 4u) Bf = B; else Bn = B;
+            }
+        }
+        const double u = Bn + R, tt = snaq_clamp10(u) + Bf;
+        const double gBf = (tt <= 10.0) ? gt1 : 0.0;
+        const double gR = (u <= 10.0) ? gBf : 0.0;          /* = d v / d R = d v / d Bn */
+        /* reverse pass */
+        pc = ppairs;
+        snaq_grad_pairs(pc, n0, x, nul, gR, add);
+        pc = pterms;
+        for (int it = 0; it < nterms; it++) {
+            const unsigned th = *pc++;
+            const unsigned gs = th >> 4;
+            const double gq = x(gs);
+            if ((th & 3u) == SNAQ_T2) {
+                const unsigned s0 = pc[0], s1 = pc[1];
+                pc += 2;
+                const double er = x(s0) - x(s1), e = snaq_clamp10(er);
+                const double gh = (th & 4u) ? 1.0 - gq : gq;
+                const double ye = snaq_exp(-e, M);
+                const double A = 1.0 - gh * (1.0 - ye);
+                const double term_raw = -snaq_log(A, M);
+                if (term_raw <= 10.0 && gR != 0.0) {
+                    const double dgh = gR * (1.0 - ye) / A;
+                    add(gs, (th & 4u) ? -dgh : dgh);
+                    if (er <= 10.0) {
+                        const double de = gR * gh * ye / A;
+                        if (s0 != nul) add(s0, de);
+                        if (s1 != nul) add(s1, -de);
+                    }
+                }
+            } else {
+                const unsigned slo = pc[0], shi = pc[1], sk = pc[2];
+                const double clo = x(slo), chi = x(shi), ck = x(sk);
+                const int nchain = pc[3];
+                pc += 4;
+                const double la = snaq_clamp10(clo), lb = snaq_clamp10(ck - chi), le = snaq_clamp10(chi - clo);
+                const uint16_t *pchain = pc;
+                const double ch_raw = snaq_sum(pc, nchain, x);
+                const double ga = 1.0 - gq, gb = gq;
+                const double yb = snaq_exp(-lb, M), ye = snaq_exp(-le, M), ya = snaq_exp(-la, M);
+                const double S = gb * gb * yb + ga * gb * (3.0 - ye) + ga * ga * ya;
+                const double l4_raw = -snaq_log(S, M);
+                const double B_raw = snaq_clamp10(ch_raw) + snaq_clamp10(l4_raw);
+                double gB = (th & 4u) ? gBf : gR;
+                if (B_raw > 10.0) gB = 0.0;
+                if (gB != 0.0) {
+                    if (ch_raw <= 10.0) { const uint16_t *pp = pchain; snaq_grad_pairs(pp, nchain, x, nul, gB, add); }
+                    if (l4_raw <= 10.0) {
+                        const double gS = -gB / S;
+                        const double dlb = gS * (-gb * gb * yb), dle = gS * (ga * gb * ye), dla = gS * (-ga * ga * ya);
+                        const double dgb = 2.0 * gb * yb + ga * (3.0 - ye), dga = gb * (3.0 - ye) + 2.0 * ga * ya;
+                        add(gs, gS * (dgb - dga));
+                        double glo = 0.0, ghi = 0.0, gk = 0.0;
+                        if (clo <= 10.0) glo += dla;
+                        if (ck - chi <= 10.0) { gk += dlb; ghi -= dlb; }
+                        if (chi - clo <= 10.0) { ghi += dle; glo -= dle; }
+                        if (slo != nul) add(slo, glo);
+                        if (shi != nul) add(shi, ghi);
+                        if (sk != nul) add(sk, gk);
+                    }
+                }
+            }
+        }
+        return v;
+    }
+    /* class C */
+    double cf[3], dz[4] = {0.0, 0.0, 0.0, 0.0};
+    snaq_t5_cf(kind, pc, x, M, cf);
+    double dcf[3];
+    /* a negative expCF costs a flat -1e15 (src/pseudolik.jl:1394-1396): the objective has no slope there, so the
+     * reported "gradient" of such a term is the slope of SNAQ_PENALTY_SLOPE * cf, which points out of the region */
+    for (int j = 0; j < 3; j++) dcf[j] = cf[j] < 0.0 ? SNAQ_PENALTY_SLOPE : ((W[j] != 0.0 && cf[j] > 0.0) ? W[j] / cf[j] : 0.0);
+    if (kind == SNAQ_KIND_T5) {
+        const double g2 = x(pc[0]), g1 = 1.0 - g2;
+        const double a5 = x(pc[2]) - x(pc[1]), a6 = x(pc[3]) - x(pc[2]);
+        const double y5 = snaq_exp(-snaq_clamp10(a5), M), y6 = snaq_exp(-snaq_clamp10(a6), M);
+        const double dy5 = dcf[0] * (-2.0 / 3.0 * g1) + dcf[1] * (g1 / 3.0) + dcf[2] * (g1 / 3.0);
+        const double dy6 = dcf[0] * (g2 / 3.0) + dcf[1] * (-2.0 / 3.0 * g2) + dcf[2] * (g2 / 3.0);
+        const double dg2 = dcf[0] * (-(1.0 - 2.0 / 3.0 * y5) + y6 / 3.0) + dcf[1] * (-y5 / 3.0 + (1.0 - 2.0 / 3.0 * y6)) +
+                           dcf[2] * (-y5 / 3.0 + y6 / 3.0);
+        const double da5 = (a5 <= 10.0) ? -y5 * dy5 : 0.0, da6 = (a6 <= 10.0) ? -y6 * dy6 : 0.0;
+        dz[0] = dg2; dz[1] = -da5; dz[2] = da5 - da6; dz[3] = da6;
+        for (int j = 0; j < 4; j++) if (pc[j] != nul && dz[j] != 0.0) add(pc[j], dz[j]);
+    } else {
+        dz[0] = (2.0 * dcf[0] - dcf[1] - dcf[2]) / 3.0;
+        dz[1] = (-dcf[0] + 2.0 * dcf[1] - dcf[2]) / 3.0;
+        add(pc[0], dz[0]);
+        add(pc[1], dz[1]);
+    }
+    return snaq_loglik_t5(cf, W, M, status);
+}
+
+/*
+ * Chain rule through the expansion x -> xf (snaq_expand_row): gx[i] += sum_rows gxf[row] * d xf[row] / d x[i].
+ * gx must hold nparams zeros on entry.  Runs on the host (the table pointers of T are host pointers).
+ */
+SNAQ_HD void snaq_grad_backprop(const SnaqTables &T, const SnaqMath &M, const double *x, const double *xconst, const double *gxf,
+                                double *gx, bool linear_rows_only = false) {
+    for (int row = 0; row < T.nparams; row++) gx[row] += gxf[row];
+    for (int k = 0; k < T.n_int; k++) {
+        const double gr = gxf[T.n_xe + 1 + k];
+        if (gr == 0.0) continue;
+        for (uint32_t i = T.dpath_off[k]; i < T.dpath_off[k + 1]; i++) { const int sl = T.dpath_slot[i]; if (sl < T.nparams) gx[sl] += gr; }
+    }
+    for (int c = 0; c < T.n_cycles; c++) {
+        const int kc = T.cyc_k[c];
+        const uint16_t *es = T.cyc_slot + T.cyc_off[c];
+        const int r0 = (int)T.crow[c];
+        for (int j = 1; j <= kc; j++) {                         /* C_j */
+            const double gr = gxf[r0 + j];
+            if (gr == 0.0) continue;
+            for (int i = 0; i < j; i++) if (es[i] < T.nparams) gx[es[i]] += gr;
+        }
+        if (linear_rows_only) continue;
+        if (!(T.cyc_flags[c] & 1)) {
+            for (int o = 1; o < kc; o++) {                      /* type-3 term rows */
+                const double gr = gxf[r0 + kc + 1 + (o - 1)];
+                if (gr == 0.0) continue;
+                double l1 = 0.0, l2 = 0.0;
+                for (int i = 0; i < o; i++) l1 += snaq_xe(T, x, xconst, es[i]);
+                for (int i = o; i < kc; i++) l2 += snaq_xe(T, x, xconst, es[i]);
+                const double l1c = snaq_clamp10(l1), l2c = snaq_clamp10(l2);
+                const double g2 = x[T.cyc_gslot[c]], g1 = 1.0 - g2;
+                const double y1 = snaq_exp(-l1c, M), y2 = snaq_exp(-l2c, M);
+                const double A = 1.0 - g1 * g1 * (1.0 - y1) - g2 * g2 * (1.0 - y2);
+                if (-snaq_log(A, M) > 10.0) continue;
+                const double s = gr / A;                        /* d row = -dA / A */
+                gx[T.cyc_gslot[c]] += s * (-(2.0 * g1 * (1.0 - y1) - 2.0 * g2 * (1.0 - y2)));
+                if (l1 <= 10.0) for (int i = 0; i < o; i++) if (es[i] < T.nparams) gx[es[i]] += s * g1 * g1 * y1;
+                if (l2 <= 10.0) for (int i = o; i < kc; i++) if (es[i] < T.nparams) gx[es[i]] += s * g2 * g2 * y2;
+            }
+        } else {
+            for (int j = 0; j < 2; j++) {                       /* -log(1-gammaz) rows */
+                const double gr = gxf[r0 + 2 * kc + j];
+                if (gr == 0.0) continue;
+                const double z = x[T.cyc_gslot[c] + j];
+                if (-snaq_log(1.0 - z, M) > 10.0) continue;
+                gx[T.cyc_gslot[c] + j] += gr / (1.0 - z);
+            }
+        }
+    }
 }
 
 #endif /* SNAQ_CORE_H */

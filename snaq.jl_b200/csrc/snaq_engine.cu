@@ -725,6 +725,184 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
     stamp(4);
 }
 
+/*
+ * Objective AND gradient in one pass (snaq_eval_grad): thread per quartet, one parameter vector.
+ * Every quartet adds d v / d xf[slot] for the slots its program reads into per-block bins in shared
+ * memory.  The bins are 64-bit fixed point (2^-32): integer atomics make the sums independent of the order
+ * in which threads arrive, so the result is bit-reproducible.  A 64-bit shared-memory atomic add is a
+ * compare-and-swap loop on this architecture, so a bin is two 32-bit words updated by two native 32-bit
+ * atomic adds, the carry of the low word (known from the value the first add returns) folded into the second.
+ * A block's bins are exact in double, and the last block adds the per-block rows in block order.  The chain rule through the expansion x -> xf is
+ * snaq_grad_backprop on the host (a few hundred rows).
+ */
+#define QG_SCALE 4294967296.0
+template <bool WANT_H>
+__global__ void __launch_bounds__(256, 2)
+k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restrict__ prog2, const uint8_t *__restrict__ qhdr,
+            const double2 *__restrict__ WA, const double4 *__restrict__ W, uint32_t nA1, uint32_t nA2, uint32_t a2base, uint32_t nQ,
+            const double *__restrict__ X, const double *__restrict__ xconst, int nh, int nt, double *__restrict__ partial,
+            double *__restrict__ out, const double *__restrict__ negw3, unsigned int *__restrict__ ticket,
+            double *__restrict__ gpart, double *__restrict__ gout, uint32_t *__restrict__ status) {
+    constexpr int BLOCK = 256;
+    extern __shared__ __align__(128) unsigned char smem[];
+    double *mt = reinterpret_cast<double *>(smem);                        // 48 doubles, 128-byte aligned
+    double *red = reinterpret_cast<double *>(smem + 384);                 // [8] warp sums
+    uint2 *span = reinterpret_cast<uint2 *>(smem + 512);                  // [8 warps][QD_SPAN] staged programs
+    double *xs = reinterpret_cast<double *>(smem + 512 + 8 * QD_SPAN * 8);
+    const int n_full = T.n_full;
+    unsigned int *bins_lo = reinterpret_cast<unsigned int *>(xs + n_full);   // [n_full] low words
+    unsigned int *bins_hi = bins_lo + n_full;                                // [n_full] high words
+    unsigned int *hb_lo = bins_hi + n_full, *hb_hi = hb_lo + n_full;         // WANT_H: curvature bins (same format)
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    unsigned st = 0;
+    const SnaqMath M = load_math_tables(mt, (int)tid);
+    for (int row = (int)tid; row < n_full; row += BLOCK) {
+        if (row < T.nparams) st |= range_check(X[row], (row >= nh && row < nh + nt) ? 1.0e300 : 1.0);
+        xs[row] = snaq_expand_row(T, M, X, xconst, row);
+        bins_lo[row] = 0u;
+        bins_hi[row] = 0u;
+        if (WANT_H) { hb_lo[row] = 0u; hb_hi[row] = 0u; }
+    }
+    __syncthreads();
+    const unsigned gtid = blockIdx.x * BLOCK + tid, nthr = gridDim.x * BLOCK;
+    const unsigned gwarp = blockIdx.x * (BLOCK / 32) + warp, nwarps = gridDim.x * (BLOCK / 32);
+    const unsigned nul = (unsigned)T.n_xe;
+    double acc = 0.0;
+    auto addq = [&](unsigned slot, long long q) {
+        if (slot != nul) {
+            const unsigned lo = (unsigned)q, hi = (unsigned)((unsigned long long)q >> 32);
+            const unsigned old = atomicAdd(&bins_lo[slot], lo);
+            atomicAdd(&bins_hi[slot], hi + ((old + lo < old) ? 1u : 0u));
+        }
+    };
+    auto add = [&](unsigned slot, double v) { addq(slot, __double2ll_rn(v * QG_SCALE)); };
+    auto addhq = [&](unsigned slot, long long q) {
+        if (WANT_H && slot != nul) {
+            const unsigned lo = (unsigned)q, hi = (unsigned)((unsigned long long)q >> 32);
+            const unsigned old = atomicAdd(&hb_lo[slot], lo);
+            atomicAdd(&hb_hi[slot], hi + ((old + lo < old) ? 1u : 0u));
+        }
+    };
+    auto addh = [&](unsigned slot, double v) { if (WANT_H) addhq(slot, __double2ll_rn(v * QG_SCALE)); };
+    auto tree = [&](double t, const double2 &w, long long *gq, long long *hq) {   // additive quartet: value, dv/dt, -d2v/dt2
+        const double t1 = fmin(t, 10.0);
+        const double a = 2.0 / 3.0 * snaq_exp(-t1, M);
+        const double major = 1.0 - a;
+        const double r = w.x * a / major;
+        const bool in = t <= 10.0;
+        *gq = in ? __double2ll_rn((r - w.y) * QG_SCALE) : 0ll;
+        if (WANT_H) *hq = in ? __double2ll_rn(r / major * QG_SCALE) : 0ll;
+        return fma(w.x, snaq_log_pos(major, M), -w.y * (t1 + SNAQ_K_LOG3));
+    };
+    // ---- region A1: one chunk (two signed pairs) ---------------------------------------------------------
+#pragma unroll 1
+    for (unsigned i0 = gtid; i0 < nA1; i0 += 2u * nthr) {
+        double2 w[2];
+        uint2 c[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const unsigned i = i0 + (unsigned)k * nthr;
+            const bool ok = i < nA1;
+            w[k] = ok ? __ldg(WA + i) : make_double2(0.0, 0.0);
+            c[k] = ok ? __ldg(prog2 + i) : make_uint2(nul * 0x10001u, nul * 0x10001u);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const unsigned a = c[k].x & 0xffffu, b = c[k].x >> 16, cc = c[k].y & 0xffffu, d = c[k].y >> 16;
+            long long gq, hq = 0;
+            acc += tree((xs[a] - xs[b]) + (xs[cc] - xs[d]), w[k], &gq, &hq);
+            if (gq != 0) { addq(a, gq); addq(b, -gq); addq(cc, gq); addq(d, -gq); }
+            if (WANT_H && hq != 0) { addhq(a, hq); addhq(b, -hq); addhq(cc, hq); addhq(d, -hq); }
+        }
+    }
+    // ---- region A2: two chunks -----------------------------------------------------------------------------
+#pragma unroll 1
+    for (unsigned j = gtid; j < nA2; j += nthr) {
+        const double2 w = __ldg(WA + nA1 + j);
+        const uint4 c = __ldg(reinterpret_cast<const uint4 *>(prog2 + a2base) + j);
+        const unsigned s[8] = {c.x & 0xffffu, c.x >> 16, c.y & 0xffffu, c.y >> 16, c.z & 0xffffu, c.z >> 16, c.w & 0xffffu, c.w >> 16};
+        double ta = xs[s[0]] - xs[s[1]], tb = xs[s[2]] - xs[s[3]];
+        ta += xs[s[4]] - xs[s[5]];
+        tb += xs[s[6]] - xs[s[7]];
+        long long gq, hq = 0;
+        acc += tree(ta + tb, w, &gq, &hq);
+        if (gq != 0) {
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) { addq(s[k], gq); addq(s[k + 1], -gq); }
+        }
+        if (WANT_H && hq != 0) {
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) { addhq(s[k], hq); addhq(s[k + 1], -hq); }
+        }
+    }
+    // ---- region G: everything else through the generic evaluator ------------------------------------------
+    {
+        uint2 *wspan = span + warp * QD_SPAN;
+#pragma unroll 1
+        for (unsigned ib = nA1 + nA2 + gwarp * 32u; ib < nQ; ib += nwarps * 32u) {
+            const unsigned i = ib + lane;
+            const bool active = i < nQ;
+            const unsigned ilast = min(ib + 32u, nQ);
+            const uint32_t o0 = active ? __ldg(off + i) : 0u, o1 = active ? __ldg(off + i + 1) : 0u;
+            const unsigned hdr = active ? (unsigned)qhdr[i] : 0u;
+            const double4 w4 = active ? W[i] : make_double4(0, 0, 0, 0);
+            const uint32_t s0 = __shfl_sync(0xffffffffu, o0, 0);
+            const uint32_t s1 = __ldg(off + ilast);
+            const bool staged = (s1 - s0) <= (uint32_t)QD_SPAN;
+            __syncwarp();
+            if (staged) for (uint32_t c = s0 + lane; c < s1; c += 32u) wspan[c - s0] = __ldg(prog2 + c);
+            __syncwarp();
+            if (active) {
+                const double w[4] = {w4.x, w4.y, w4.z, w4.w};
+                const uint16_t *pc = reinterpret_cast<const uint16_t *>(staged ? wspan + (o0 - s0) : prog2 + o0);
+                const XRow xf{xs};
+                acc += snaq_grad_quartet(hdr, pc, (int)(o1 - o0) * 4, xf, M, w, nul, add, addh, st);
+            }
+        }
+    }
+    if (st) atomicOr(status, st);
+    // ---- epilogue ---------------------------------------------------------------------------------------------
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();                                                      // also: every atomic on bins is done
+    if (tid == 0) {
+        double ssum = 0.0;
+#pragma unroll
+        for (int k = 0; k < BLOCK / 32; k++) ssum += red[k];
+        partial[blockIdx.x] = ssum;
+    }
+    const int nrows = WANT_H ? 2 * n_full : n_full;                       // the curvature bins follow the gradient bins
+    for (int row = (int)tid; row < nrows; row += BLOCK)
+        gpart[(size_t)blockIdx.x * nrows + row] =
+            (double)(long long)(((unsigned long long)bins_hi[row + (row >= n_full ? n_full : 0)] << 32) |
+                                (unsigned long long)bins_lo[row + (row >= n_full ? n_full : 0)]) * (1.0 / QG_SCALE);
+    __threadfence();
+    __shared__ unsigned int s_last;
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double sp = 0.0;
+        for (unsigned b = tid; b < gridDim.x; b += BLOCK) sp += __ldcg(partial + b);
+        for (int o = 16; o > 0; o >>= 1) sp += __shfl_down_sync(0xffffffffu, sp, o);
+        if (lane == 0) red[warp] = sp;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int k = 0; k < BLOCK / 32; k++) tot += red[k];
+            out[0] = -tot - __ldcg(negw3);
+        }
+        for (int row = (int)tid; row < nrows; row += BLOCK) {
+            double s = 0.0;
+            for (unsigned b = 0; b < gridDim.x; b++) s += __ldcg(gpart + (size_t)b * nrows + row);
+            gout[row] = row < n_full ? -s : s;                            // f = -(sum of v); the curvature is already that of f
+        }
+        if (tid == 0) *ticket = 0u;
+    }
+}
+
 // out[p] = -(sum over blocks of partial[b][p]), fixed order (logPseudoLik(d): src/pseudolik.jl:1417-1423).
 // One block per candidate: 256 threads stride over the per-block partial sums with 4 independent
 // accumulators each, then a fixed-order shuffle / shared-memory tree.
@@ -830,6 +1008,8 @@ struct snaq_ctx {
     double *d_XF = nullptr; size_t XF_cap = 0;   // expanded parameter vectors [P][n_full]
     double *d_out = nullptr; size_t out_cap = 0;
     double *d_partial = nullptr; size_t partial_cap = 0;
+    double *d_gpart = nullptr; size_t gpart_cap = 0;     // k_eval_grad: [blocks][n_full] per-block gradient rows
+    double *d_gout = nullptr; size_t gout_cap = 0;       // [1 + n_full]: f, then d f / d xf
     double *h_pin = nullptr; size_t pin_cap = 0;
     int sm_count = 148;
     int lanes_warps = 8;                  // warps per block of k_eval_lanes (SNAQ_LANES_WARPS = 8, 12 or 16)
@@ -1058,7 +1238,7 @@ int snaq_destroy(snaq_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_blob); cudaFree(ctx->d_xconst);
     cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_WA); cudaFree(ctx->d_wpart); cudaFree(ctx->d_negw3); cudaFree(ctx->d_status); cudaFree(ctx->d_total); cudaFree(ctx->d_ticket); cudaFree(ctx->d_trace);
-    cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_XF); cudaFree(ctx->d_out); cudaFree(ctx->d_partial);
+    cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_XF); cudaFree(ctx->d_out); cudaFree(ctx->d_partial); cudaFree(ctx->d_gpart); cudaFree(ctx->d_gout);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_qhdr); cudaFree(ctx->d_len4); cudaFree(ctx->d_iota); cudaFree(ctx->d_cls);
     cudaFree(ctx->d_cls_sorted);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -1330,6 +1510,69 @@ int snaq_eval(snaq_ctx *ctx, int32_t P, int32_t nparams, const double *X, double
         return status_to_error(ctx, *h_st);
     }
     std::memcpy(out, h_out, sizeof(double) * P);
+    return SNAQ_OK;
+}
+
+int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, double *grad, double *hdiag) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (!ctx->has_net) { ctx->err = "snaq_set_network has not been called"; return SNAQ_ENODATA; }
+    if (!x || !f || !grad || nparams != ctx->H.nparams) { ctx->err = "bad arguments to snaq_eval_grad (x has wrong length?)"; return SNAQ_EINVAL; }
+    int rc = check_x_host(ctx, 1, x);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const SnaqHostTables &H = ctx->H;
+    const int n_full = H.n_full;
+    for (int i = 0; i < nparams; i++) grad[i] = 0.0;
+    if (hdiag) for (int i = 0; i < nparams; i++) hdiag[i] = 0.0;
+    if (ctx->nq == 0) { *f = 0.0; return SNAQ_OK; }
+    const int nrows = hdiag ? 2 * n_full : n_full;
+    const size_t smem = 512 + 8 * QD_SPAN * 8 + (size_t)n_full * 8 + (size_t)nrows * 8;
+    if (smem > 100 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_grad"; return SNAQ_EINVAL; }
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->nq + 255) / 256, (int64_t)ctx->sm_count * 2));
+    rc = ensure(ctx, ctx->d_X, ctx->X_cap, (size_t)std::max(nparams, 1));
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)grid);
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->d_gpart, ctx->gpart_cap, (size_t)grid * nrows);
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->d_gout, ctx->gout_cap, (size_t)nrows + 1);
+    if (rc) return rc;
+    rc = ensure_pin(ctx, (size_t)nparams + nrows + 4);
+    if (rc) return rc;
+    std::memcpy(ctx->h_pin, x, sizeof(double) * nparams);
+    CK(cudaMemcpyAsync(ctx->d_X, ctx->h_pin, sizeof(double) * nparams, cudaMemcpyHostToDevice, ctx->stream));
+#define LAUNCH_GRAD(WH)                                                                                                        \
+    do {                                                                                                                       \
+        CK(cudaFuncSetAttribute(k_eval_grad<WH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
+        k_eval_grad<WH><<<grid, 256, smem, ctx->stream>>>(                                                                      \
+            ctx->T, ctx->d_off, reinterpret_cast<const uint2 *>(ctx->d_prog), ctx->d_qhdr, ctx->d_WA,                           \
+            reinterpret_cast<const double4 *>(ctx->d_W), (uint32_t)ctx->nA1, (uint32_t)ctx->nA2,                                \
+            (uint32_t)(ctx->nA1 + (ctx->nA1 & 1)), (uint32_t)ctx->nq, ctx->d_X, ctx->d_xconst, H.nh, H.nt, ctx->d_partial,      \
+            ctx->d_gout, ctx->d_negw3, ctx->d_ticket, ctx->d_gpart, ctx->d_gout + 1, ctx->d_status + 1);                        \
+    } while (0)
+    if (hdiag) LAUNCH_GRAD(true); else LAUNCH_GRAD(false);
+#undef LAUNCH_GRAD
+    CK(cudaGetLastError());
+    double *h_g = ctx->h_pin + nparams;
+    uint32_t *h_st = reinterpret_cast<uint32_t *>(h_g + nrows + 1);
+    CK(cudaMemcpyAsync(h_g, ctx->d_gout, sizeof(double) * (nrows + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_st, ctx->d_status + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->counters[0] += 1;
+    ctx->counters[1] += ctx->nq;
+    ctx->counters[2] += 8 * nparams;
+    ctx->counters[3] += 8 * (nrows + 1) + 4;
+    if (*h_st) {
+        CK(cudaMemsetAsync(ctx->d_status + 1, 0, sizeof(uint32_t), ctx->stream));
+        return status_to_error(ctx, *h_st);
+    }
+    *f = h_g[0];
+    // chain rule through the expansion x -> xf, on the host tables
+    const SnaqTables Th = H.view(H.blob.data());
+    static const double tab[SNAQ_MATH_DOUBLES] = SNAQ_EXP_TAB_INIT_LOGS;
+    const SnaqMath Mh{tab, tab + 16, tab + 32};
+    snaq_grad_backprop(Th, Mh, x, H.xconst.data(), h_g + 1, grad);
+    if (hdiag) snaq_grad_backprop(Th, Mh, x, H.xconst.data(), h_g + 1 + n_full, hdiag, true);
     return SNAQ_OK;
 }
 

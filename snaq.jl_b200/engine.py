@@ -32,7 +32,17 @@ _LIB = None
 EXPORTS = ["snaq_create", "snaq_destroy", "snaq_last_error", "snaq_version", "snaq_set_data", "snaq_set_obscf",
            "snaq_set_sampled", "snaq_set_network", "snaq_patch_network", "snaq_num_params", "snaq_get_params",
            "snaq_eval", "snaq_eval_device", "snaq_eval_quartets", "snaq_get_descriptors", "snaq_get_counters",
-           "snaq_check_status", "snaq_measure_fp64_peak", "snaq_get_trace"]
+           "snaq_check_status", "snaq_measure_fp64_peak", "snaq_get_trace", "snaq_eval_grad", "snaq_optbl"]
+
+
+class _OptblOpts(C.Structure):
+    _fields_ = [("ftol_rel", C.c_double), ("ftol_abs", C.c_double), ("xtol_rel", C.c_double), ("xtol_abs", C.c_double),
+                ("maxeval", C.c_int32), ("ladder", C.c_int32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class _OptblResult(C.Structure):
+    _fields_ = [("fmin", C.c_double), ("proj_grad", C.c_double), ("nevals", C.c_int32), ("nlaunches", C.c_int32),
+                ("niter", C.c_int32), ("status", C.c_int32)]
 
 
 class _Opts(C.Structure):
@@ -147,6 +157,28 @@ class Engine:
         dl = np.zeros(self.nq) if "deltacf" in want else None
         self._chk(self.lib.snaq_eval_quartets(self.ctx, C.c_int32(x.size), _p(x), _p(e), _p(l), _p(dl)))
         return e, l, dl
+
+    def eval_grad(self, x, want_hdiag=False):
+        """objective and its gradient at x in one pass over the quartets (snaq_eval_grad)"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        g = np.zeros_like(x)
+        h = np.zeros_like(x) if want_hdiag else None
+        f = C.c_double(0.0)
+        self._chk(self.lib.snaq_eval_grad(self.ctx, C.c_int32(x.size), _p(x), C.byref(f), _p(g), _p(h)))
+        return (f.value, g, h) if want_hdiag else (f.value, g)
+
+    def optbl(self, x0, ftol_rel=1e-6, ftol_abs=1e-6, xtol_rel=1e-2, xtol_abs=1e-3, maxeval=1000, ladder=20, fd=False):
+        """``optBL!`` on the current network (snaq_optbl): returns (xmin, dict(fmin, nevals, nlaunches, niter, status, proj_grad))"""
+        x = np.array(x0, dtype=np.float64, copy=True)
+        if x.size != self.nparams:
+            raise SnaqError(f"ht(net) (length {self.nparams}) and vector x (length {x.size}) need to have same length")
+        o = _OptblOpts(ftol_rel, ftol_abs, xtol_rel, xtol_abs, maxeval, ladder, 1 if fd else 0, 0)
+        r = _OptblResult()
+        rc = self.lib.snaq_optbl(self.ctx, C.byref(o), _p(x), C.byref(r))
+        if rc:
+            msg = self.lib.snaq_last_error(self.ctx).decode()
+            raise SnaqError(msg or "tolerances have to be positive, ftol (rel,abs), xtol (rel,abs)")
+        return x, dict(fmin=r.fmin, proj_grad=r.proj_grad, nevals=r.nevals, nlaunches=r.nlaunches, niter=r.niter, status=r.status)
 
     def descriptors(self, max_types: int = 8):
         which = np.zeros(self.nq, np.int8); ntype = np.zeros(self.nq, np.int8)

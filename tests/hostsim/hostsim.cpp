@@ -5,6 +5,7 @@
  * in the CPU-only test tier.  It is not linked into, nor reachable from, the shipped
  * library: the product has no CPU path.
  */
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -105,5 +106,128 @@ int hostsim_run(const snaq_flatnet *f, int ntaxa, int64_t nq, const uint16_t *ta
     }
     if (status_out) *status_out = status;
     return 0;
+}
+
+/* objective and analytic gradient of one parameter vector (the device functions of snaq_eval_grad, on the CPU) */
+int hostsim_grad(const snaq_flatnet *f, int ntaxa, int64_t nq, const uint16_t *taxa, const double *obs,
+                 const uint8_t *sampled, const double *x, double *out_lik, double *grad, uint32_t *status_out) {
+    SnaqHostTables H;
+    int rc = snaq_build_tables(f, ntaxa, H, g_err);
+    if (rc) return rc;
+    SnaqTables T = H.view(H.blob.data());
+    SnaqMath M{g_et, g_li, g_lc};
+    std::vector<double> xf(H.n_full), gxf(H.n_full, 0.0);
+    for (int r = 0; r < H.n_full; r++) xf[r] = snaq_expand_row(T, M, x, H.xconst.data(), r);
+    XRow xr{xf.data()};
+    unsigned status = 0;
+    double total = 0;
+    auto add = [&](unsigned slot, double v) { gxf[slot] += v; };
+    auto addh = [&](unsigned, double) {};
+    for (int64_t q = 0; q < nq; q++) {
+        SnaqWriter w{nullptr, 0, 0};
+        uint8_t h1 = 0;
+        int e = snaq_build_quartet(T, taxa + 4 * q, w, &h1, nullptr);
+        if (e) { g_err = "build error " + std::to_string(e) + " at quartet " + std::to_string(q); return SNAQ_ETOPOLOGY; }
+        std::vector<uint16_t> prog((w.n + 3) & ~3, (uint16_t)H.n_xe);
+        SnaqWriter w2{prog.data(), 0, w.n};
+        snaq_build_quartet(T, taxa + 4 * q, w2, &h1, nullptr);
+        double W[4];
+        snaq_weights(h1, obs + 3 * q, sampled ? sampled[q] : 1, W);
+        total += snaq_grad_quartet(h1, prog.data(), (int)prog.size(), xr, M, W, (unsigned)H.n_xe, add, addh, status);
+    }
+    for (int r = 0; r < H.n_full; r++) gxf[r] = -gxf[r];            /* f = -sum v */
+    for (int i = 0; i < H.nparams; i++) grad[i] = 0.0;
+    snaq_grad_backprop(T, M, x, H.xconst.data(), gxf.data(), grad);
+    *out_lik = -total;
+    if (status_out) *status_out = status;
+    return 0;
+}
+
+/*
+ * CPU stand-in for the engine's context, so that the host-side optimiser (snaq.jl_b200/csrc/snaq_optbl.cpp,
+ * which only uses the public C ABI) can be exercised in the CPU-only test tier: the four ABI calls it makes
+ * are implemented here on top of the same device functions.  Test harness only.
+ */
+struct snaq_ctx {
+    SnaqHostTables H;
+    SnaqTables T;
+    int64_t nq = 0;
+    std::vector<std::vector<uint16_t>> progs;
+    std::vector<uint8_t> hdrs;
+    std::vector<double> W;
+};
+
+int snaq_num_params(snaq_ctx *c, int32_t *nparams, int32_t *n_gamma, int32_t *n_t, int32_t *n_gammaz) {
+    if (nparams) *nparams = c->H.nparams;
+    if (n_gamma) *n_gamma = c->H.nh;
+    if (n_t) *n_t = c->H.nt;
+    if (n_gammaz) *n_gammaz = c->H.nparams - c->H.nh - c->H.nt;
+    return 0;
+}
+int snaq_get_params(snaq_ctx *c, double *x, int32_t *numht, double *upper) {
+    for (int i = 0; i < c->H.nparams; i++) {
+        if (x) x[i] = c->H.x0[i];
+        if (numht) numht[i] = c->H.numht[i];
+        if (upper) upper[i] = (i >= c->H.nh && i < c->H.nh + c->H.nt) ? 10.0 : 1.0;
+    }
+    return 0;
+}
+int snaq_eval(snaq_ctx *c, int32_t P, int32_t nparams, const double *X, double *out) {
+    SnaqMath M{g_et, g_li, g_lc};
+    unsigned status = 0;
+    std::vector<double> xf(c->H.n_full);
+    for (int p = 0; p < P; p++) {
+        for (int r = 0; r < c->H.n_full; r++) xf[r] = snaq_expand_row(c->T, M, X + (size_t)p * nparams, c->H.xconst.data(), r);
+        XRow xr{xf.data()};
+        double total = 0;
+        for (int64_t q = 0; q < c->nq; q++) {
+            double cf[3], t1;
+            snaq_eval_quartet(c->hdrs[q], c->progs[q].data(), (int)c->progs[q].size(), xr, M, cf, &t1, status);
+            total += snaq_quartet_loglik(SNAQ_HDR_KIND(c->hdrs[q]), cf, t1, &c->W[4 * q], M, status);
+        }
+        out[p] = -total;
+    }
+    return status ? SNAQ_ENUMERIC : 0;
+}
+int snaq_eval_grad(snaq_ctx *c, int32_t nparams, const double *x, double *f, double *grad, double *hdiag) {
+    SnaqMath M{g_et, g_li, g_lc};
+    unsigned status = 0;
+    std::vector<double> xf(c->H.n_full), gxf(c->H.n_full, 0.0), hxf(c->H.n_full, 0.0);
+    for (int r = 0; r < c->H.n_full; r++) xf[r] = snaq_expand_row(c->T, M, x, c->H.xconst.data(), r);
+    XRow xr{xf.data()};
+    auto add = [&](unsigned slot, double v) { gxf[slot] += v; };
+    auto addh = [&](unsigned slot, double v) { hxf[slot] += v; };
+    double total = 0;
+    for (int64_t q = 0; q < c->nq; q++)
+        total += snaq_grad_quartet(c->hdrs[q], c->progs[q].data(), (int)c->progs[q].size(), xr, M, &c->W[4 * q], (unsigned)c->H.n_xe, add, addh, status);
+    for (auto &v : gxf) v = -v;
+    for (int i = 0; i < nparams; i++) { grad[i] = 0.0; if (hdiag) hdiag[i] = 0.0; }
+    snaq_grad_backprop(c->T, M, x, c->H.xconst.data(), gxf.data(), grad);
+    if (hdiag && !getenv("HOSTSIM_NO_HDIAG")) snaq_grad_backprop(c->T, M, x, c->H.xconst.data(), hxf.data(), hdiag, true);
+    *f = -total;
+    return status ? SNAQ_ENUMERIC : 0;
+}
+
+/* optBL! on the CPU stand-in: the optimiser code is the product's, the objective is the harness's */
+int hostsim_optbl(const snaq_flatnet *f, int ntaxa, int64_t nq, const uint16_t *taxa, const double *obs, const snaq_optbl_opts *opts,
+                  double *x, snaq_optbl_result *res) {
+    snaq_ctx c;
+    int rc = snaq_build_tables(f, ntaxa, c.H, g_err);
+    if (rc) return rc;
+    c.T = c.H.view(c.H.blob.data());
+    c.nq = nq;
+    c.progs.resize(nq); c.hdrs.resize(nq); c.W.resize(4 * nq);
+    for (int64_t q = 0; q < nq; q++) {
+        SnaqWriter w{nullptr, 0, 0};
+        uint8_t h1 = 0;
+        int e = snaq_build_quartet(c.T, taxa + 4 * q, w, &h1, nullptr);
+        if (e) { g_err = "build error " + std::to_string(e) + " at quartet " + std::to_string(q); return SNAQ_ETOPOLOGY; }
+        c.progs[q].assign((w.n + 3) & ~3, (uint16_t)c.H.n_xe);
+        SnaqWriter w2{c.progs[q].data(), 0, w.n};
+        snaq_build_quartet(c.T, taxa + 4 * q, w2, &h1, nullptr);
+        c.hdrs[q] = h1;
+        snaq_weights(h1, obs + 3 * q, 1, &c.W[4 * q]);
+    }
+    return snaq_optbl(&c, opts, x, res);
 }
 }

@@ -66,3 +66,41 @@ def hasedge(flat, ntaxa, qt):
     if rc:
         raise RuntimeError(lib().hostsim_last_error().decode())
     return he[:, :npar], bd1
+
+
+def grad(flat, ntaxa, qt, obs, x, sampled=None):
+    """objective and analytic gradient at x (the device functions behind snaq_eval_grad, compiled for the CPU)"""
+    qt = np.ascontiguousarray(qt, dtype=np.uint16).reshape(-1, 4)
+    obs = np.ascontiguousarray(obs, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    g = np.zeros_like(x)
+    f = C.c_double(0.0)
+    st = C.c_uint32(0)
+    sm = None if sampled is None else np.ascontiguousarray(sampled, dtype=np.uint8)
+    rc = lib().hostsim_grad(flat.ptr(), ntaxa, C.c_int64(qt.shape[0]), _p(qt), _p(obs), _p(sm), _p(x), C.byref(f), _p(g), C.byref(st))
+    if rc:
+        raise RuntimeError(lib().hostsim_last_error().decode())
+    return f.value, g, st.value
+
+
+class _OptblOpts(C.Structure):
+    _fields_ = [("ftol_rel", C.c_double), ("ftol_abs", C.c_double), ("xtol_rel", C.c_double), ("xtol_abs", C.c_double),
+                ("maxeval", C.c_int32), ("ladder", C.c_int32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class _OptblResult(C.Structure):
+    _fields_ = [("fmin", C.c_double), ("proj_grad", C.c_double), ("nevals", C.c_int32), ("nlaunches", C.c_int32),
+                ("niter", C.c_int32), ("status", C.c_int32)]
+
+
+def optbl(flat, ntaxa, qt, obs, x0, ftol_rel=1e-6, ftol_abs=1e-6, xtol_rel=1e-2, xtol_abs=1e-3, maxeval=1000, ladder=20, fd=False):
+    """the product's optimiser (snaq_optbl.cpp) over the CPU stand-in objective"""
+    qt = np.ascontiguousarray(qt, dtype=np.uint16).reshape(-1, 4)
+    obs = np.ascontiguousarray(obs, dtype=np.float64)
+    x = np.array(x0, dtype=np.float64, copy=True)
+    o = _OptblOpts(ftol_rel, ftol_abs, xtol_rel, xtol_abs, maxeval, ladder, 1 if fd else 0, 0)
+    r = _OptblResult()
+    rc = lib().hostsim_optbl(flat.ptr(), ntaxa, C.c_int64(qt.shape[0]), _p(qt), _p(obs), C.byref(o), _p(x), C.byref(r))
+    if rc:
+        raise RuntimeError(f"optbl failed with code {rc}: " + lib().hostsim_last_error().decode())
+    return x, dict(fmin=r.fmin, proj_grad=r.proj_grad, nevals=r.nevals, nlaunches=r.nlaunches, niter=r.niter, status=r.status)

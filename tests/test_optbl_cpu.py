@@ -1,0 +1,107 @@
+"""CPU tier: the device functions behind snaq_eval_grad (analytic gradient) and the host-side optimiser
+snaq_optbl.cpp (optBL!, src/snaq_optimization.jl:341-390), run over the CPU stand-in objective of
+tests/hostsim and checked against the oracle.  NLopt's BOBYQA iterates are not reproducible:
+the statement is on the optimum."""
+import numpy as np
+import pytest
+
+import snaq_jl_b200 as S
+from snaq_jl_b200 import simulate
+from tests import hostsim_py as hs
+
+
+def make(oracle, n, h, seed, ngenes=None):
+    net = None
+    for attempt in range(30):
+        try:
+            net = simulate.random_level1_network(n, h, seed + 1000 * attempt, min_cycle=3 if seed % 3 == 0 else 4)
+            break
+        except S.SnaqError:
+            continue
+    assert net is not None
+    taxa = [f"t{i + 1}" for i in range(n)]
+    flat = net.flatten(taxa)
+    qt = simulate.all_quartets(n)
+    p = oracle.parameters(flat)
+    e = oracle.extract(flat, qt)["expcf"]
+    obs = e if ngenes is None else simulate.obs_from_expcf(e, ngenes, seed)
+    return flat, qt, obs, p["x"], p["upper"]
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_analytic_gradient_matches_central_differences_of_the_oracle(oracle, seed):
+    h = seed % 6
+    n = 8 + seed % 9 + 2 * h
+    flat, qt, obs, x0, upper = make(oracle, n, h, seed, ngenes=50)
+    x = np.clip(simulate.parameter_batch(x0, upper, 4, seed)[2], 1e-3, upper - 1e-3)
+    f, g, st = hs.grad(flat, n, qt, obs, x)
+    assert st == 0
+    assert abs(f - oracle.evaluate(flat, qt, obs, x)[0]) <= 1e-11 * abs(f)
+    hstep = 1e-6
+    X = np.tile(x, (2 * len(x), 1))
+    for i in range(len(x)):
+        X[2 * i, i] += hstep
+        X[2 * i + 1, i] -= hstep
+    ff = oracle.evaluate(flat, qt, obs, X)
+    gfd = (ff[0::2] - ff[1::2]) / (2 * hstep)
+    assert np.max(np.abs(g - gfd) / (1 + np.abs(gfd))) < 2e-5
+
+
+def test_gradient_is_zero_beyond_the_caps_and_at_the_simulating_parameters(oracle):
+    flat, qt, obs, x0, upper = make(oracle, 12, 2, 77)
+    f, g, _ = hs.grad(flat, 12, qt, obs, x0)                     # perfect data: x0 is the minimiser
+    assert abs(f) < 1e-9 and np.max(np.abs(g)) < 1e-6
+    x = np.where(upper > 1.5, 10.0, x0)                          # every length at its cap of 10: t1 = 10 everywhere
+    f, g, _ = hs.grad(flat, 12, qt, obs, x)
+    assert np.isfinite(f) and np.all(np.isfinite(g))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_optbl_finds_the_known_optimum_on_perfect_data(oracle, seed):
+    n, h = 10 + 3 * seed, 1 + seed % 3
+    flat, qt, obs, x0, upper = make(oracle, n, h, 500 + seed)
+    rng = np.random.default_rng(seed)
+    start = np.clip(x0 * rng.uniform(0.6, 1.5, len(x0)) + rng.uniform(0, 0.05, len(x0)), 0, upper)
+    xmin, res = hs.optbl(flat, n, qt, obs, start, 1e-12, 1e-10, 1e-10, 1e-10)     # fRelBL, fAbsBL, xRelBL, xAbsBL (:44-47)
+    assert res["fmin"] < 1e-7 and res["status"] in (3, 4, 5)
+    assert abs(oracle.evaluate(flat, qt, obs, xmin)[0] - res["fmin"]) < 1e-9
+    # perfect data: the fitted expected CFs are the observed ones; the parameters themselves are recovered
+    # where the data determine them (some directions are nearly flat: Hessian condition numbers reach 1e8)
+    assert np.max(np.abs(oracle.extract(flat, qt, x=xmin)["expcf"] - obs)) < 2e-5
+    if seed in (0, 3):
+        assert np.max(np.abs(xmin - x0)) < 1e-4
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_optbl_matches_a_tight_optimisation_of_the_oracle_objective(oracle, seed):
+    from scipy.optimize import minimize
+    n, h = 8 + seed, seed % 3
+    flat, qt, obs, x0, upper = make(oracle, n, h, 700 + seed, ngenes=100)
+    rng = np.random.default_rng(seed)
+    start = np.clip(x0 * rng.uniform(0.7, 1.3, len(x0)), 1e-3, upper - 1e-3)
+
+    def fo(x):
+        return float(oracle.evaluate(flat, qt, obs, x.reshape(1, -1))[0])
+
+    ref = minimize(fo, start, method="L-BFGS-B", bounds=list(zip(np.zeros_like(upper), upper)),
+                   options=dict(ftol=1e-15, gtol=1e-9, maxiter=2000, maxfun=200000))
+    xmin, res = hs.optbl(flat, n, qt, obs, start, 1e-12, 1e-10, 1e-10, 1e-10)
+    assert res["fmin"] <= ref.fun + 1e-7 * max(1.0, abs(ref.fun))            # at least as good as the reference optimum
+    assert abs(fo(xmin) - res["fmin"]) <= 1e-10 * max(1.0, abs(res["fmin"]))
+    xfd, rfd = hs.optbl(flat, n, qt, obs, start, 1e-12, 1e-10, 1e-10, 1e-10, fd=True)   # batched finite differences
+    assert abs(rfd["fmin"] - res["fmin"]) <= 1e-7 * max(1.0, abs(res["fmin"]))
+
+
+def test_optbl_stopping_rules(oracle):
+    flat, qt, obs, x0, upper = make(oracle, 14, 2, 901, ngenes=200)
+    start = np.clip(x0 * 1.2, 0, upper)
+    f0 = oracle.evaluate(flat, qt, obs, start)[0]
+    xa, ra = hs.optbl(flat, 14, qt, obs, start, 1e-12, 1e-10, 1e-10, 1e-10)
+    xc, rc = hs.optbl(flat, 14, qt, obs, start)                  # search-time tolerances fRel, fAbs, xRel, xAbs (:36-39)
+    assert ra["fmin"] <= rc["fmin"] <= f0
+    assert rc["nlaunches"] <= ra["nlaunches"]
+    xm, rm = hs.optbl(flat, 14, qt, obs, start, 1e-12, 1e-10, 1e-10, 1e-10, maxeval=7)
+    assert rm["status"] == 5 and rm["nlaunches"] <= 9 and rm["fmin"] <= f0
+    assert np.all(xa >= 0) and np.all(xa <= upper)
+    with pytest.raises(RuntimeError):
+        hs.optbl(flat, 14, qt, obs, start, ftol_rel=0.0)          # "tolerances have to be positive" (:350)
