@@ -195,6 +195,15 @@ typedef struct snaq_optbl_result {
  * opts may be NULL (the search-time tolerances fRel, fAbs, xRel, xAbs of :36-39).                          */
 int snaq_optbl(snaq_ctx *ctx, const snaq_optbl_opts *opts, double *x, snaq_optbl_result *res);
 
+/* ---- updateBL!: src/readquartetdata.jl:838-861 -------------------------- */
+/* The current network must be a tree.  For each edge-length parameter (the t block of x, numht order):
+ * nquartets[i] = data quartets that correspond exactly to the edge (one taxon in each of the four subtrees
+ * around it: edgesParts :866-889, makeTable :935-960) and edgeL[i] = -log(3/2 (1 - mean obsCF of the tree's
+ * resolution over them)) (:846; 0 when nquartets[i]==0).  Not available on a quartet-sharded context (a mean
+ * over one rank's quartets is not the mean).  The caller applies the rule of :850-858
+ * (only lengths < 0 or == 1.0 are replaced, by max(edgeL,0); edges without quartets get 1.0).               */
+int snaq_update_bl(snaq_ctx *ctx, int64_t *nquartets, double *edgeL);
+
 /* ---- descriptors for parity checks ------------------------ */
 /* which[nq]       : 1 tree-like, 2 four-cycle (src/types.jl:180)
  * ntype[nq], types[nq*max_types]: typeHyb codes (2..5; type 1 dropped) of the

@@ -903,6 +903,32 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
     }
 }
 
+// updateBL! (src/readquartetdata.jl:838-861): per internal edge of a TREE, the number of data quartets whose internal
+// path is exactly that edge (one taxon in each of the four subtrees around it: edgesParts/makeTable, :866-889, :935-960)
+// and the sum of their observed CF of the tree's resolution.  Such a quartet has a one-pair program (D[v], D[parent v]).
+// bins[2*slot] = count, bins[2*slot+1] = sum in 2^-36 fixed point (64-bit integer atomics: order independent).
+#define UBL_SCALE 68719476736.0
+__global__ void __launch_bounds__(256) k_update_bl(SnaqTables T, const uint2 *__restrict__ prog2, const uint8_t *__restrict__ qhdr,
+                                                   const uint32_t *__restrict__ perm, const double *__restrict__ obs, uint32_t nA1,
+                                                   unsigned long long *__restrict__ bins) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nA1) return;
+    const uint2 c = prog2[i];
+    const unsigned nul = (unsigned)T.n_xe;
+    if (c.y != nul * 0x10001u) return;
+    const unsigned plus = c.x & 0xffffu, minus = c.x >> 16;
+    const int first = T.n_xe + 1;
+    if ((int)plus < first || (int)plus >= first + T.n_int || (int)minus < first || (int)minus >= first + T.n_int) return;
+    const int v = T.dnode[plus - first], u = T.dnode[minus - first];
+    if (T.parent[v] != u) return;                                  // a longer path that happens to need one pair
+    const unsigned slot = T.pslot[v];
+    if ((int)slot >= T.nparams) return;
+    const unsigned h = qhdr[i];
+    const double cf = obs[3 * (size_t)perm[i] + SNAQ_HDR_PERM(h)];
+    atomicAdd(&bins[2 * slot], 1ull);
+    atomicAdd(&bins[2 * slot + 1], (unsigned long long)__double2ll_rn(cf * UBL_SCALE));
+}
+
 // out[p] = -(sum over blocks of partial[b][p]), fixed order (logPseudoLik(d): src/pseudolik.jl:1417-1423).
 // One block per candidate: 256 threads stride over the per-block partial sums with 4 independent
 // accumulators each, then a fixed-order shuffle / shared-memory tree.
@@ -1573,6 +1599,44 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
     const SnaqMath Mh{tab, tab + 16, tab + 32};
     snaq_grad_backprop(Th, Mh, x, H.xconst.data(), h_g + 1, grad);
     if (hdiag) snaq_grad_backprop(Th, Mh, x, H.xconst.data(), h_g + 1 + n_full, hdiag, true);
+    return SNAQ_OK;
+}
+
+int snaq_update_bl(snaq_ctx *ctx, int64_t *nquartets, double *edgeL) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (!ctx->has_net) { ctx->err = "snaq_set_network has not been called"; return SNAQ_ENODATA; }
+    if (!nquartets || !edgeL) { ctx->err = "bad arguments to snaq_update_bl"; return SNAQ_EINVAL; }
+    const SnaqHostTables &H = ctx->H;
+    if (ctx->world > 1) { ctx->err = "snaq_update_bl needs an unsharded context"; return SNAQ_EINVAL; }
+    if (H.n_hybrids > 0) { ctx->err = "updateBL! was created for a tree, and net here is not a tree, so no branch lengths updated (src/readquartetdata.jl:839-841)"; return SNAQ_EINVAL; }
+    CK(cudaSetDevice(ctx->device));
+    const int np = H.nparams;
+    for (int i = 0; i < H.nt; i++) { nquartets[i] = 0; edgeL[i] = 0.0; }
+    if (np == 0 || ctx->nq == 0) return SNAQ_OK;
+    unsigned long long *d_bins = nullptr;
+    CK(cudaMalloc((void **)&d_bins, (size_t)np * 2 * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d_bins, 0, (size_t)np * 2 * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess && ctx->nA1 > 0) {
+        k_update_bl<<<(unsigned)((ctx->nA1 + 255) / 256), 256, 0, ctx->stream>>>(ctx->T, reinterpret_cast<const uint2 *>(ctx->d_prog), ctx->d_qhdr,
+                                                                                 ctx->d_perm, ctx->d_obs, (uint32_t)ctx->nA1, d_bins);
+        e = cudaGetLastError();
+    }
+    std::vector<unsigned long long> hb((size_t)np * 2);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hb.data(), d_bins, hb.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_bins);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return SNAQ_ECUDA; }
+    ctx->counters[5]++;
+    ctx->counters[3] += (int64_t)hb.size() * 8;
+    for (int i = 0; i < H.nt; i++) {
+        const int slot = H.nh + i;
+        const unsigned long long n = hb[2 * slot];
+        nquartets[i] = (int64_t)n;
+        if (n > 0) {
+            const double mean = (double)(long long)hb[2 * slot + 1] / UBL_SCALE / (double)n;
+            edgeL[i] = -std::log(1.5 * (1.0 - mean));              // :846
+        }
+    }
     return SNAQ_OK;
 }
 

@@ -23,7 +23,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from .datacf import DataCF
-from .network import FlatNet, HybridNetwork, SnaqError
+from .network import FlatNet, HybridNetwork, SnaqError, set_length
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libsnaqb200.so")
@@ -32,7 +32,7 @@ _LIB = None
 EXPORTS = ["snaq_create", "snaq_destroy", "snaq_last_error", "snaq_version", "snaq_set_data", "snaq_set_obscf",
            "snaq_set_sampled", "snaq_set_network", "snaq_patch_network", "snaq_num_params", "snaq_get_params",
            "snaq_eval", "snaq_eval_device", "snaq_eval_quartets", "snaq_get_descriptors", "snaq_get_counters",
-           "snaq_check_status", "snaq_measure_fp64_peak", "snaq_get_trace", "snaq_eval_grad", "snaq_optbl"]
+           "snaq_check_status", "snaq_measure_fp64_peak", "snaq_get_trace", "snaq_eval_grad", "snaq_optbl", "snaq_update_bl"]
 
 
 class _OptblOpts(C.Structure):
@@ -180,6 +180,13 @@ class Engine:
             raise SnaqError(msg or "tolerances have to be positive, ftol (rel,abs), xtol (rel,abs)")
         return x, dict(fmin=r.fmin, proj_grad=r.proj_grad, nevals=r.nevals, nlaunches=r.nlaunches, niter=r.niter, status=r.status)
 
+    def update_bl(self):
+        """per edge-length parameter: (Nquartets, edgeL) of ``updateBL!`` (src/readquartetdata.jl:838-861)"""
+        nq = np.zeros(max(self.nt, 1), np.int64)
+        el = np.zeros(max(self.nt, 1), np.float64)
+        self._chk(self.lib.snaq_update_bl(self.ctx, _p(nq), _p(el)))
+        return nq[: self.nt], el[: self.nt]
+
     def descriptors(self, max_types: int = 8):
         which = np.zeros(self.nq, np.int8); ntype = np.zeros(self.nq, np.int8)
         types = np.zeros((self.nq, max_types), np.int8); formula = np.zeros((self.nq, 3), np.int8)
@@ -255,6 +262,43 @@ def logPseudoLik(d: DataCF) -> float:
     if eng is None or getattr(d, "_x", None) is None:
         raise SnaqError("expCF not updated: run extractQuartet_ / calculateExpCFAll_ first")
     return float(eng.eval(d._x)[0])
+
+
+def optBL_(net: HybridNetwork, d: DataCF, ftolRel: float = 1e-6, ftolAbs: float = 1e-6, xtolRel: float = 1e-2,
+           xtolAbs: float = 1e-3, device: int = 0):
+    """``optBL!`` (src/snaq_optimization.jl:341-390): optimises every gamma / branch length / gammaz of ``net`` on the
+    device (snaq_optbl), then ``updateParameters!(net, xmin)`` and ``loglik!(net, fmin)``.  Defaults are the
+    search-time tolerances fRel, fAbs, xRel, xAbs (:36-39)."""
+    if not (ftolRel > 0 and ftolAbs > 0 and xtolAbs > 0 and xtolRel > 0):
+        raise SnaqError(f"tolerances have to be positive, ftol (rel,abs), xtol (rel,abs): {[ftolRel, ftolAbs, xtolRel, xtolAbs]}")
+    extractQuartet_(net, d, device)
+    eng = d._engine
+    xmin, res = eng.optbl(np.array(net.ht, dtype=np.float64), ftolRel, ftolAbs, xtolRel, xtolAbs)
+    net.update_parameters(list(xmin))
+    net.loglik = res["fmin"]
+    d._x = xmin.copy()
+    return res
+
+
+def updateBL_(net: HybridNetwork, d: DataCF, device: int = 0):
+    """``updateBL!`` (src/readquartetdata.jl:838-861): rough starting branch lengths of a TREE from the mean observed CF
+    of the quartets that correspond exactly to each internal edge; returns {edge number: (Nquartets, edgeL)}."""
+    if net.numhybrids > 0:
+        raise SnaqError("updateBL! was created for a tree, and net here is not a tree, so no branch lengths updated")
+    eng = _engine_for(d, device)
+    net.parameters()
+    eng.set_network(net.flatten(d.taxa))
+    d._net_id = None                                   # the lengths change below: extractQuartet_ must run again
+    _, numht, _ = eng.get_params()
+    nq, el = eng.update_bl()
+    tab = {int(numht[eng.nh + i]): (int(nq[i]), float(el[i])) for i in range(eng.nt) if nq[i] > 0}
+    for e in net.edge:
+        if e.number in tab and (e.length < 0.0 or e.length == 1.0):      # :850-853
+            set_length(e, tab[e.number][1] if tab[e.number][1] > 0 else 0.0)
+    for e in net.edge:
+        if e.length < 0.0:                                                # :855-858
+            set_length(e, 1.0)
+    return tab
 
 
 def topologyQpseudolik_(net: HybridNetwork, d: DataCF, device: int = 0) -> float:
