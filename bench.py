@@ -343,7 +343,25 @@ def hbm_leg(S, Engine, local, torch, peak_tf=None):
                "achieved_tflops": len(qt) * Pb * fpe / (msb * 1e-3) / 1e12}
     if peak_tf:
         batched["frac_fp64"] = batched["achieved_tflops"] / peak_tf
-    return {"batched": batched, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": src,
+    # optBL! on the same table (src/snaq_optimization.jl:341-390): whole optimisations through snaq_optbl, from a
+    # start 30 % off the simulating parameters, with the search-time and the final tolerances of the reference
+    exp0, _, _ = eng.eval_quartets(x0)
+    eng.set_obscf(S.simulate.obs_from_expcf(exp0, 300, 5))
+    rng = np.random.default_rng(0)
+    start = np.clip(x0 * rng.uniform(0.7, 1.3, len(x0)), 0, upper)
+    optbl = {"nparams": int(len(x0)), "f_start": float(eng.eval(start)[0]), "f_at_simulating_x": float(eng.eval(x0)[0])}
+    for _ in range(3):
+        eng.eval_grad(start)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        eng.eval_grad(start)
+    optbl["objective_plus_gradient_pass_us"] = (time.perf_counter() - t0) / 20 * 1e6
+    for name, tol in (("search_tolerances", (1e-6, 1e-6, 1e-2, 1e-3)), ("final_tolerances", (1e-12, 1e-10, 1e-10, 1e-10))):
+        t0 = time.perf_counter()
+        _, r = eng.optbl(start, *tol)
+        r["seconds"] = time.perf_counter() - t0
+        optbl[name] = r
+    return {"batched": batched, "optbl": optbl, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": src,
             "workload": f"100-taxon h=3, {len(qt)} quartets, P=1 (one objective call), L2 flushed before every timed call",
             "ms_per_call": ms, "ms_per_call_warm_l2": ms_warm, "evals_per_s_warm_l2": len(qt) / (ms_warm * 1e-3),
             "achieved_at_survey_8d_56B_per_quartet": len(qt) * 56 / (ms * 1e-3) / 1e9,

@@ -992,6 +992,8 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, doubl
 struct snaq_ctx {
     int device = 0, rank = 0, world = 1;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // snaq_eval: host->device copies of the next chunk while the current one is evaluated
+    cudaEvent_t copy_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     // data
     int ntaxa = 0;
@@ -1038,6 +1040,7 @@ struct snaq_ctx {
     double *d_gout = nullptr; size_t gout_cap = 0;       // [1 + n_full]: f, then d f / d xf
     double *h_pin = nullptr; size_t pin_cap = 0;
     int sm_count = 148;
+    int eval_chunks = 2;                  // snaq_eval pipelines large batches in this many chunks (SNAQ_EVAL_CHUNKS = 1..4)
     int lanes_warps = 8;                  // warps per block of k_eval_lanes (SNAQ_LANES_WARPS = 8, 12 or 16)
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -1248,6 +1251,7 @@ int snaq_create(const snaq_opts *opts, snaq_ctx **out) {
     if (const char *ev = getenv("SNAQ_TRACE")) {
         if (atoi(ev) > 0 && cudaMalloc((void **)&ctx->d_trace, (size_t)ctx->sm_count * 4 * 8 * sizeof(unsigned long long)) != cudaSuccess) ctx->d_trace = nullptr;
     }
+    if (const char *ev = getenv("SNAQ_EVAL_CHUNKS")) { int v = atoi(ev); if (v >= 1 && v <= 4) ctx->eval_chunks = v; }
     if (const char *ev = getenv("SNAQ_LANES_WARPS")) { int v = atoi(ev); if (v == 8 || v == 12 || v == 16) ctx->lanes_warps = v; }
     if ((e = cudaMalloc((void **)&ctx->d_status, 4 * sizeof(uint32_t))) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cudaMalloc((void **)&ctx->d_total, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
@@ -1268,6 +1272,7 @@ int snaq_destroy(snaq_ctx *ctx) {
     cudaFree(ctx->d_perm); cudaFree(ctx->d_qhdr); cudaFree(ctx->d_len4); cudaFree(ctx->d_iota); cudaFree(ctx->d_cls);
     cudaFree(ctx->d_cls_sorted);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    if (ctx->copy_stream) { for (int k = 0; k < 4; k++) cudaEventDestroy(ctx->copy_ev[k]); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SNAQ_OK;
@@ -1510,20 +1515,49 @@ int snaq_eval(snaq_ctx *ctx, int32_t P, int32_t nparams, const double *X, double
         ctx->err = "ht(net) (length " + std::to_string(ctx->H.nparams) + ") and vector x (length " + std::to_string(nparams) + ") need to have same length";
         return SNAQ_EINVAL;
     }
-    int rc = check_x_host(ctx, P, X);
-    if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     const size_t nx = (size_t)P * std::max(nparams, 1);
-    rc = ensure(ctx, ctx->d_X, ctx->X_cap, nx);
+    int rc = ensure(ctx, ctx->d_X, ctx->X_cap, nx);
     if (rc) return rc;
     rc = ensure(ctx, ctx->d_out, ctx->out_cap, (size_t)P + 1);
     if (rc) return rc;
     rc = ensure_pin(ctx, nx + P + 2);
     if (rc) return rc;
-    std::memcpy(ctx->h_pin, X, sizeof(double) * (size_t)P * nparams);
-    CK(cudaMemcpyAsync(ctx->d_X, ctx->h_pin, sizeof(double) * (size_t)P * nparams, cudaMemcpyHostToDevice, ctx->stream));
-    rc = eval_device(ctx, P, ctx->d_X, ctx->d_out, ctx->stream, nullptr, nullptr, nullptr);
-    if (rc) return rc;
+    // the bounds of update! (src/snaq_optimization.jl:213,221,228) are checked on the device; only when the device
+    // reports a violation is the batch scanned on the host for the message.  A caller buffer that is already
+    // page-locked is copied from directly; otherwise it is staged through the context's pinned buffer.
+    cudaPointerAttributes attr;
+    const bool user_pinned = cudaPointerGetAttributes(&attr, X) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const double *src = X;
+    if (!user_pinned) { std::memcpy(ctx->h_pin, X, sizeof(double) * (size_t)P * nparams); src = ctx->h_pin; }
+    // large batches: the copy of chunk k+1 (copy stream) overlaps the evaluation of chunk k (compute stream)
+    const int nchunk = (P >= 2048 && nparams > 0) ? ctx->eval_chunks : 1;
+    if (nchunk > 1) {
+        if (!ctx->copy_stream) {
+            CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            for (int k = 0; k < 4; k++) CK(cudaEventCreateWithFlags(&ctx->copy_ev[k], cudaEventDisableTiming));
+        }
+        const int Pc = ((P + nchunk - 1) / nchunk + 31) & ~31;
+        int k = 0;
+        for (int p0 = 0; p0 < P; p0 += Pc, k++) {
+            const int pn = std::min(Pc, P - p0);
+            CK(cudaMemcpyAsync(ctx->d_X + (size_t)p0 * nparams, src + (size_t)p0 * nparams, sizeof(double) * (size_t)pn * nparams,
+                               cudaMemcpyHostToDevice, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream));
+        }
+        k = 0;
+        for (int p0 = 0; p0 < P; p0 += Pc, k++) {
+            const int pn = std::min(Pc, P - p0);
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0));
+            rc = eval_device(ctx, pn, ctx->d_X + (size_t)p0 * nparams, ctx->d_out + p0, ctx->stream, nullptr, nullptr, nullptr);
+            if (rc) return rc;
+        }
+    } else {
+        CK(cudaMemcpyAsync(ctx->d_X, src, sizeof(double) * (size_t)P * nparams, cudaMemcpyHostToDevice, ctx->stream));
+        rc = eval_device(ctx, P, ctx->d_X, ctx->d_out, ctx->stream, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+    }
     double *h_out = ctx->h_pin + nx;
     uint32_t *h_st = reinterpret_cast<uint32_t *>(h_out + P);
     CK(cudaMemcpyAsync(h_out, ctx->d_out, sizeof(double) * P, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1533,6 +1567,7 @@ int snaq_eval(snaq_ctx *ctx, int32_t P, int32_t nparams, const double *X, double
     ctx->counters[3] += (int64_t)sizeof(double) * P + 4;
     if (*h_st) {
         CK(cudaMemsetAsync(ctx->d_status + 1, 0, sizeof(uint32_t), ctx->stream));
+        if (*h_st & SNAQ_S_RANGE) { rc = check_x_host(ctx, P, X); if (rc) return rc; }
         return status_to_error(ctx, *h_st);
     }
     std::memcpy(out, h_out, sizeof(double) * P);
