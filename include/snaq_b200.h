@@ -211,11 +211,19 @@ int snaq_update_bl(snaq_ctx *ctx, int64_t *nquartets, double *edgeL);
  * formula[nq*3]   : which==1: 1 major / 2 minor (src/pseudolik.jl:1230-1247);
  *                   which==2: 11,12,13 = which of cf1,cf2,cf3 lands there
  *                   (src/pseudolik.jl:1008-1048)
- * hasedge[nq*nparams] : 0/1, aligned with x (src/pseudolik.jl:392-464)
+ * hasedge[nq*nparams] : 0/1, aligned with x (src/pseudolik.jl:392-464); see snaq_get_hasedge
  * Any may be NULL.                                                             */
 int snaq_get_descriptors(snaq_ctx *ctx, int8_t *which, int8_t *ntype,
                          int8_t *types, int32_t max_types, int8_t *formula,
                          uint8_t *hasedge);
+
+/* q.qnet.hasEdge and q.qnet.indexht (updateHasEdge!, src/pseudolik.jl:392-464; parameters!(qnet,net),
+ * src/snaq_optimization.jl:106-180): hasedge[nq*nparams] 0/1 aligned with x; indexht[nq*nparams] the 1-based
+ * positions of x the quartet uses, -1 padded, nindexht[nq] their number (either may be NULL).  Networks with at
+ * most one hybrid node only (the reference defines hasEdge operationally and, with nested cycles, by the order in
+ * which leaves are pruned): otherwise SNAQ_EINVAL.  These arrays only gate recomputation in the
+ * reference (src/snaq_optimization.jl:185-206); they never change a value.                                      */
+int snaq_get_hasedge(snaq_ctx *ctx, uint8_t *hasedge, int32_t *indexht, int32_t *nindexht);
 
 /* engine counters: [0] launches of the eval kernel, [1] quartet-evals done,
  * [2] H2D bytes, [3] D2H bytes, [4] descriptor words in HBM, [5] launches of

@@ -37,6 +37,7 @@
 
 #include "../../include/snaq_b200.h"
 #include "snaq_core.h"
+#include "snaq_hasedge.h"
 #include "snaq_tables.h"
 
 #define SNAQ_S_RANGE 8u   /* a parameter outside its bounds reached the device */
@@ -204,6 +205,22 @@ __global__ void __launch_bounds__(128) k_describe(SnaqTables T, const uint16_t *
     which[q] = info.which;
     for (int i = 0; i < 3; i++) formula[3 * q + i] = info.formula[i];
     for (int i = 0; i < nhyb; i++) types[q * nhyb + i] = info.type[i];
+}
+
+// hasEdge (updateHasEdge!, src/pseudolik.jl:392-464) and the "keeps a bad diamond I whole" flag that decides the form
+// of indexht (parameters!(qnet,net), src/snaq_optimization.jl:120-146), original quartet order
+__global__ void __launch_bounds__(128) k_hasedge(SnaqTables T, const uint16_t *__restrict__ taxa, int64_t nq, uint8_t *__restrict__ hasedge,
+                                                 uint8_t *__restrict__ bd1, uint32_t *__restrict__ status) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint16_t tx[4];
+    load_taxa(taxa, q, tx);
+    uint32_t bits[SNAQ_HE_WORDS(SNAQ_MAX_SLOT + 1)];
+    int flag = 0;
+    const int e = snaq_hasedge_quartet(T, tx, bits, &flag);
+    if (e) atomicMax(status, (uint32_t)e);
+    for (int i = 0; i < T.nparams; i++) hasedge[q * T.nparams + i] = e ? 0 : (uint8_t)((bits[i >> 5] >> (i & 31)) & 1u);
+    bd1[q] = (uint8_t)flag;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -1714,11 +1731,59 @@ int snaq_eval_quartets(snaq_ctx *ctx, int32_t nparams, const double *x, double *
     return SNAQ_OK;
 }
 
+int snaq_get_hasedge(snaq_ctx *ctx, uint8_t *hasedge, int32_t *indexht, int32_t *nindexht) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (!ctx->has_net) { ctx->err = "snaq_set_network has not been called"; return SNAQ_ENODATA; }
+    if (!hasedge) { ctx->err = "bad arguments to snaq_get_hasedge"; return SNAQ_EINVAL; }
+    const SnaqHostTables &H = ctx->H;
+    if (H.n_hybrids > 1) {
+        // with two or more hybrids what extractQuartet! leaves behind depends on the ORDER in which the other leaves are
+        // deleted across nested cycles; the structural rule is exact (checked against the oracle) for h <= 1
+        ctx->err = "hasEdge read-back is implemented for networks with at most one hybrid node";
+        return SNAQ_EINVAL;
+    }
+    CK(cudaSetDevice(ctx->device));
+    const int64_t nq = ctx->nq;
+    const int np = H.nparams;
+    if (nq == 0 || np == 0) { if (nindexht) for (int64_t q = 0; q < nq; q++) nindexht[q] = 0; return SNAQ_OK; }
+    uint8_t *d_he = nullptr, *d_bd1 = nullptr;
+    CK(cudaMalloc((void **)&d_he, (size_t)nq * np));
+    CK(cudaMalloc((void **)&d_bd1, (size_t)nq));
+    CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream));
+    k_hasedge<<<(unsigned)((nq + 127) / 128), 128, 0, ctx->stream>>>(ctx->T, ctx->d_taxa, nq, d_he, d_bd1, ctx->d_status);
+    cudaError_t e = cudaGetLastError();
+    std::vector<uint8_t> hb((size_t)nq);
+    uint32_t st = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hasedge, d_he, (size_t)nq * np, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hb.data(), d_bd1, (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&st, ctx->d_status, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_he); cudaFree(d_bd1);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return SNAQ_ECUDA; }
+    if (st) { ctx->err = build_err_text(st); return SNAQ_ETOPOLOGY; }
+    ctx->counters[5]++;
+    ctx->counters[3] += (int64_t)nq * (np + 1);
+    if (indexht || nindexht) {
+        // parameters!(qnet,net): positions of x the quartet uses, 1-based, in x order; a quartet that keeps a bad
+        // diamond I hybrid lists only its two gammaz (src/snaq_optimization.jl:120-146)
+        for (int64_t q = 0; q < nq; q++) {
+            int n = 0;
+            for (int i = 0; i < np; i++) {
+                const bool on = hasedge[(size_t)q * np + i] != 0 && (!hb[q] || i >= H.nh + H.nt);
+                if (on) { if (indexht) indexht[(size_t)q * np + n] = i + 1; n++; }
+            }
+            if (indexht) for (int i = n; i < np; i++) indexht[(size_t)q * np + i] = -1;
+            if (nindexht) nindexht[q] = n;
+        }
+    }
+    return SNAQ_OK;
+}
+
 int snaq_get_descriptors(snaq_ctx *ctx, int8_t *which, int8_t *ntype, int8_t *types, int32_t max_types, int8_t *formula,
                          uint8_t *hasedge) {
     if (!ctx) return SNAQ_EINVAL;
     if (!ctx->has_net) { ctx->err = "snaq_set_network has not been called"; return SNAQ_ENODATA; }
-    if (hasedge) { ctx->err = "hasEdge read-back is not implemented yet (DESIGN.md, next rows)"; return SNAQ_EINVAL; }
+    if (hasedge) { int rc = snaq_get_hasedge(ctx, hasedge, nullptr, nullptr); if (rc) return rc; }
     CK(cudaSetDevice(ctx->device));
     const int64_t nq = ctx->nq;
     if (nq == 0) return SNAQ_OK;

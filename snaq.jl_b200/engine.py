@@ -32,7 +32,7 @@ _LIB = None
 EXPORTS = ["snaq_create", "snaq_destroy", "snaq_last_error", "snaq_version", "snaq_set_data", "snaq_set_obscf",
            "snaq_set_sampled", "snaq_set_network", "snaq_patch_network", "snaq_num_params", "snaq_get_params",
            "snaq_eval", "snaq_eval_device", "snaq_eval_quartets", "snaq_get_descriptors", "snaq_get_counters",
-           "snaq_check_status", "snaq_measure_fp64_peak", "snaq_get_trace", "snaq_eval_grad", "snaq_optbl", "snaq_update_bl"]
+           "snaq_check_status", "snaq_measure_fp64_peak", "snaq_get_trace", "snaq_eval_grad", "snaq_optbl", "snaq_update_bl", "snaq_get_hasedge"]
 
 
 class _OptblOpts(C.Structure):
@@ -179,6 +179,15 @@ class Engine:
             msg = self.lib.snaq_last_error(self.ctx).decode()
             raise SnaqError(msg or "tolerances have to be positive, ftol (rel,abs), xtol (rel,abs)")
         return x, dict(fmin=r.fmin, proj_grad=r.proj_grad, nevals=r.nevals, nlaunches=r.nlaunches, niter=r.niter, status=r.status)
+
+    def hasedge(self):
+        """(hasEdge [nq, nparams] 0/1, indexht lists) of every quartet: updateHasEdge! / parameters!(qnet,net)"""
+        npar = max(self.nparams, 1)
+        he = np.zeros((self.nq, npar), np.uint8)
+        ix = np.full((self.nq, npar), -1, np.int32)
+        nix = np.zeros(self.nq, np.int32)
+        self._chk(self.lib.snaq_get_hasedge(self.ctx, _p(he), _p(ix), _p(nix)))
+        return he[:, : self.nparams], [list(ix[i, : nix[i]]) for i in range(self.nq)]
 
     def update_bl(self):
         """per edge-length parameter: (Nquartets, edgeL) of ``updateBL!`` (src/readquartetdata.jl:838-861)"""
