@@ -120,4 +120,51 @@ function optBL!(net::HybridNetwork, d::DataCF, e::Engine, verbose::Bool, ftolRel
     readback!(e, d, xmin)                       # keeps q.qnet.expCF / deltaCF usable by the search (quirk: the reference leaves the LAST x there)
 end
 
+# ---- phase 2: the optimiser itself on the device (snaq_optbl): analytic gradient in one pass, batched line searches ----
+struct OptblOpts; ftol_rel::Cdouble; ftol_abs::Cdouble; xtol_rel::Cdouble; xtol_abs::Cdouble; maxeval::Cint; ladder::Cint; flags::Cuint; reserved::Cuint; end
+mutable struct OptblResult; fmin::Cdouble; proj_grad::Cdouble; nevals::Cint; nlaunches::Cint; niter::Cint; status::Cint; end
+
+"optBL! without NLopt: same arguments, same post-conditions (ht(net), loglik(net) updated); iterates differ from BOBYQA's"
+function optBL_device!(net::HybridNetwork, d::DataCF, e::Engine, ftolRel = SNaQ.fRel, ftolAbs = SNaQ.fAbs, xtolRel = SNaQ.xRel, xtolAbs = SNaQ.xAbs)
+    (ftolRel > 0 && ftolAbs > 0 && xtolAbs > 0 && xtolRel > 0) || error("tolerances have to be positive, ftol (rel,abs), xtol (rel,abs): $([ftolRel, ftolAbs, xtolRel, xtolAbs])")
+    SNaQ.parameters!(net)
+    set_network!(e, net)
+    x = copy(ht(net))
+    res = OptblResult(0, 0, 0, 0, 0, 0)
+    check(e, ccall((:snaq_optbl, LIB), Cint, (Ptr{Cvoid}, Ref{OptblOpts}, Ptr{Cdouble}, Ref{OptblResult}), e.ctx,
+                   OptblOpts(ftolRel, ftolAbs, xtolRel, xtolAbs, 1000, 0, 0, 0), x, res))
+    SNaQ.updateParameters!(net, x)
+    SNaQ.loglik!(net, res.fmin)
+    readback!(e, d, x)
+    return res
+end
+
+"objective and gradient in one pass (for NLopt's :LD_LBFGS / :LD_MMA if NLopt is kept: fill g in the callback)"
+function pseudodeviance_grad!(e::Engine, x::Vector{Float64}, g::Vector{Float64})
+    f = Ref{Cdouble}(0.0)
+    check(e, ccall((:snaq_eval_grad, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ref{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                   e.ctx, length(x), x, f, g, C_NULL))
+    return f[]
+end
+
+"updateBL! (src/readquartetdata.jl:838-861) with the table built on the device; net must be a tree"
+function updateBL_device!(net::HybridNetwork, d::DataCF, e::Engine)
+    SNaQ.parameters!(net)
+    set_network!(e, net)
+    nh = net.numhybrids - numBad(net)
+    nt = count(istIdentifiable, net.edge)
+    nq = Vector{Int64}(undef, nt); el = Vector{Float64}(undef, nt)
+    check(e, ccall((:snaq_update_bl, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Cdouble}), e.ctx, nq, el))
+    for i in 1:nt
+        nq[i] > 0 || continue
+        ed = net.edge[SNaQ.getIndexEdge(numht(net)[nh + i], net)]
+        if ed.length < 0.0 || ed.length == 1.0                  # :850-853
+            SNaQ.setLength!(ed, el[i] > 0 ? el[i] : 0.0)
+        end
+    end
+    for ed in net.edge
+        ed.length < 0.0 && SNaQ.setLength!(ed, 1.0)             # :855-858
+    end
+end
+
 end # module
