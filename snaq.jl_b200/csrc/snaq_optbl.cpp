@@ -142,6 +142,7 @@ extern "C" int snaq_optbl(snaq_ctx *ctx, const snaq_optbl_opts *o, double *x_io,
     int status = SNAQ_OPTBL_MAXEVAL, iter = 0, small_f = 0;
     std::vector<double> d(n), q(n), xn(n), Xls, fls, gn, hdn;
     const double bnd_eps = 1e-12;
+    const bool no_unit_step = getenv("SNAQ_OPTBL_NO_UNIT_STEP") != nullptr;
     const int hd_every = getenv("SNAQ_OPTBL_HD_EVERY") ? std::max(1, atoi(getenv("SNAQ_OPTBL_HD_EVERY"))) : 8;
     const bool verbose = getenv("SNAQ_OPTBL_VERBOSE") != nullptr;      // "inside obj with x ..." of the reference (:369-378)
     while (pb.nlaunches < maxeval) {
@@ -199,6 +200,32 @@ extern "C" int snaq_optbl(snaq_ctx *ctx, const snaq_optbl_opts *o, double *x_io,
             for (int i = 0; i < n; i++) big = std::max(big, std::fabs(d[i]) / (pb.hi[i] - pb.lo[i]));
             if (big > 0.25) { const double sc = 0.25 / big; gd *= sc; for (int i = 0; i < n; i++) d[i] *= sc; }
         }
+        const bool want_h = pb.use_fd || (iter % hd_every == 0);      // curvature diagonal: refreshed now and then
+        if (!want_h) hdn = hd;
+        // with curvature pairs in hand the unit step is usually right: try it (then the minimiser of the parabola through
+        // f(0), f'(0), f(1)) with a fused objective+gradient pass and accept on sufficient decrease; the ladder is the fallback
+        bool accepted = false;
+        double fn = 0.0, a_try = 1.0;
+        if (!pb.use_fd && !mem.empty() && !plateau && !no_unit_step) {
+            double a = 1.0;
+            for (int attempt = 0; attempt < 2 && !accepted; attempt++) {
+                double gs = 0.0;
+                for (int i = 0; i < n; i++) { xn[i] = clampd(x[i] + a * d[i], pb.lo[i], pb.hi[i]); gs += g[i] * (xn[i] - x[i]); }
+                double fr = 0.0;
+                rc = gradient(pb, xn, fr, false, gn, hdn, want_h);
+                if (rc) return rc;
+                if (std::isfinite(fr) && gs < 0.0 && fr <= f + 1e-4 * gs) { accepted = true; fn = fr; a_try = a; break; }
+                if (!std::isfinite(fr) || !(gs < 0.0)) break;
+                const double denom = 2.0 * (fr - f - gs);            // gs = slope * a for an interior step
+                if (!(denom > 0.0)) break;
+                const double aq = a * (-gs / denom);
+                if (!(aq > 1e-3 * a && aq < 0.9 * a)) break;
+                a = aq;
+            }
+            if (accepted && verbose)
+                fprintf(stderr, "OPTBL iter %d: f %.12g -> %.12g (unit-step path, alpha %g, mem %zu, pg %.3g, g.d %.3g)\n", iter, f, fn, a_try, mem.size(), pg, gd);
+        }
+        if (!accepted) {
         // line search: one launch over a ladder of projected steps
         Xls.assign((size_t)ladder * n, 0.0);
         std::vector<double> alphas(ladder);
@@ -218,11 +245,9 @@ extern "C" int snaq_optbl(snaq_ctx *ctx, const snaq_optbl_opts *o, double *x_io,
             status = SNAQ_OPTBL_FTOL;                              // no decrease along the gradient: stationary to rounding
             break;
         }
-        const bool want_h = pb.use_fd || (iter % hd_every == 0);      // curvature diagonal: refreshed now and then
-        if (!want_h) hdn = hd;
         // refine the step with the parabola through the best rung and its neighbours; the refined point is
         // evaluated by the gradient pass itself (no extra launch) and kept only if it is not worse
-        double a_try = alphas[best];
+        a_try = alphas[best];
         if (best > 0 && best + 1 < ladder && std::isfinite(fls[best - 1]) && std::isfinite(fls[best + 1])) {
             const double a0 = alphas[best + 1], a1 = alphas[best], a2 = alphas[best - 1];
             const double f0 = fls[best + 1], f1 = fls[best], f2 = fls[best - 1];
@@ -233,7 +258,7 @@ extern "C" int snaq_optbl(snaq_ctx *ctx, const snaq_optbl_opts *o, double *x_io,
             }
         }
         for (int i = 0; i < n; i++) xn[i] = clampd(x[i] + a_try * d[i], pb.lo[i], pb.hi[i]);
-        double fn = fls[best];
+        fn = fls[best];
         if (a_try != alphas[best]) {
             double fr = 0.0;
             rc = gradient(pb, xn, fr, false, gn, hdn, want_h);
@@ -251,6 +276,7 @@ extern "C" int snaq_optbl(snaq_ctx *ctx, const snaq_optbl_opts *o, double *x_io,
             rc = gradient(pb, xn, fn, true, gn, hdn, want_h);
             if (rc) return rc;
         }
+        }   // ladder
         // quasi-Newton pair
         Pair p;
         p.s.resize(n); p.y.resize(n);
