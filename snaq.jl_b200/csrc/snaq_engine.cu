@@ -41,6 +41,10 @@
 #include "snaq_tables.h"
 
 #define SNAQ_S_RANGE 8u   /* a parameter outside its bounds reached the device */
+// Small batches from the host travel as a kernel ARGUMENT (no host->device copy call, no staging buffer), and the
+// results are written by the last block straight into page-locked host memory (no device->host copy call).
+#define XARG_MAX 448      /* doubles (3.5 KB of kernel parameter space) */
+struct XArg { double v[XARG_MAX]; };
 #define LANES_MIN_P 16    /* batches of at least this many candidates use k_eval_lanes */
 
 // --------------------------------------------------------------------------------------------
@@ -531,7 +535,8 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
               const double *__restrict__ X, const double *__restrict__ xconst, int nh, int nt, int P,
               double *__restrict__ partial, double *__restrict__ out, const double *__restrict__ negw3,
               unsigned int *__restrict__ ticket, double *__restrict__ expcf, double *__restrict__ logpl,
-              double *__restrict__ deltacf, uint32_t *__restrict__ status, unsigned long long *__restrict__ trace) {
+              double *__restrict__ deltacf, uint32_t *__restrict__ status, unsigned long long *__restrict__ trace,
+              uint32_t *__restrict__ status_out, const int use_xarg, const __grid_constant__ XArg xarg) {
     constexpr int BLOCK = 256;
     extern __shared__ __align__(128) unsigned char smem[];
     double *mt = reinterpret_cast<double *>(smem);                        // 48 doubles, 128-byte aligned
@@ -553,6 +558,7 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
     double *xs = reinterpret_cast<double *>(ring + (OUT ? 0 : 8 * QD_NST * QD_STAGE_BYTES));   // [PC][n_full]
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const int n_full = T.n_full;
+    double *xraw = xs + PC * n_full;                                      // [PC][nparams] the candidates themselves
     unsigned st = 0;
     const unsigned gwarp = blockIdx.x * (BLOCK / 32) + warp, nwarps = gridDim.x * (BLOCK / 32);
     const unsigned tA1 = (nA1 + QD_TQ - 1) / QD_TQ, tA2 = (nA2 + QD_TQ - 1) / QD_TQ, tA = tA1 + tA2;
@@ -583,12 +589,18 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
         __syncwarp();
     }
     const SnaqMath M = load_math_tables(mt, (int)tid);
-    // prologue: expanded parameter vectors (and the bounds check of update!); unused rows repeat the last candidate
+    // prologue: the candidates (kernel argument or device memory) -> shared memory, with the bounds check of update!;
+    // then the expanded parameter vectors; unused rows repeat the last candidate
+    for (int idx = (int)tid; idx < PC * T.nparams; idx += BLOCK) {
+        const int p = min(idx / T.nparams, P - 1), row = idx % T.nparams;
+        const double v = use_xarg ? xarg.v[p * T.nparams + row] : X[(size_t)p * T.nparams + row];
+        st |= range_check(v, (row >= nh && row < nh + nt) ? 1.0e300 : 1.0);
+        xraw[idx] = v;
+    }
+    __syncthreads();
     for (int idx = (int)tid; idx < PC * n_full; idx += BLOCK) {
-        const int p = min(idx / n_full, P - 1), row = idx % n_full;
-        const double *x = X + (size_t)p * T.nparams;
-        if (row < T.nparams) st |= range_check(x[row], (row >= nh && row < nh + nt) ? 1.0e300 : 1.0);
-        xs[idx] = snaq_expand_row(T, M, x, xconst, row);
+        const int p = idx / n_full, row = idx % n_full;
+        xs[idx] = snaq_expand_row(T, M, xraw + p * T.nparams, xconst, row);
     }
     __syncthreads();
     stamp(1);
@@ -737,7 +749,10 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
                 out[p] = -tot - cst;
             }
         }
-        if (tid == 0) *ticket = 0u;
+        if (tid == 0) {
+            *ticket = 0u;
+            if (status_out) *status_out = *reinterpret_cast<volatile uint32_t *>(status);   // every block's bits are in by now
+        }
     }
     stamp(4);
 }
@@ -759,7 +774,8 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
             const double2 *__restrict__ WA, const double4 *__restrict__ W, uint32_t nA1, uint32_t nA2, uint32_t a2base, uint32_t nQ,
             const double *__restrict__ X, const double *__restrict__ xconst, int nh, int nt, double *__restrict__ partial,
             double *__restrict__ out, const double *__restrict__ negw3, unsigned int *__restrict__ ticket,
-            double *__restrict__ gpart, double *__restrict__ gout, uint32_t *__restrict__ status) {
+            double *__restrict__ gpart, double *__restrict__ gout, uint32_t *__restrict__ status, uint32_t *__restrict__ status_out,
+            const int use_xarg, const __grid_constant__ XArg xarg) {
     constexpr int BLOCK = 256;
     extern __shared__ __align__(128) unsigned char smem[];
     double *mt = reinterpret_cast<double *>(smem);                        // 48 doubles, 128-byte aligned
@@ -773,9 +789,15 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     unsigned st = 0;
     const SnaqMath M = load_math_tables(mt, (int)tid);
+    double *xraw = reinterpret_cast<double *>(bins_lo + (WANT_H ? 4 : 2) * n_full);     // [nparams] the candidate itself
+    for (int row = (int)tid; row < T.nparams; row += BLOCK) {
+        const double v = use_xarg ? xarg.v[row] : X[row];
+        st |= range_check(v, (row >= nh && row < nh + nt) ? 1.0e300 : 1.0);
+        xraw[row] = v;
+    }
+    __syncthreads();
     for (int row = (int)tid; row < n_full; row += BLOCK) {
-        if (row < T.nparams) st |= range_check(X[row], (row >= nh && row < nh + nt) ? 1.0e300 : 1.0);
-        xs[row] = snaq_expand_row(T, M, X, xconst, row);
+        xs[row] = snaq_expand_row(T, M, xraw, xconst, row);
         bins_lo[row] = 0u;
         bins_hi[row] = 0u;
         if (WANT_H) { hb_lo[row] = 0u; hb_hi[row] = 0u; }
@@ -916,7 +938,10 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
             for (unsigned b = 0; b < gridDim.x; b++) s += __ldcg(gpart + (size_t)b * nrows + row);
             gout[row] = row < n_full ? -s : s;                            // f = -(sum of v); the curvature is already that of f
         }
-        if (tid == 0) *ticket = 0u;
+        if (tid == 0) {
+            *ticket = 0u;
+            if (status_out) *status_out = *reinterpret_cast<volatile uint32_t *>(status);
+        }
     }
 }
 
@@ -1009,6 +1034,11 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, doubl
 struct snaq_ctx {
     int device = 0, rank = 0, world = 1;
     cudaStream_t stream = nullptr;
+    XArg xarg;                            // kernel-argument copy of a small host batch
+    bool xarg_on = false;
+    const double *xarg_src = nullptr;     // host batch being evaluated through kernel arguments (else nullptr)
+    const double *xarg_base = nullptr;    // the (never dereferenced) device alias eval_device indexes for that batch
+    uint32_t *status_out = nullptr;       // page-locked word the last block mirrors the status into (else nullptr)
     cudaStream_t copy_stream = nullptr;   // snaq_eval: host->device copies of the next chunk while the current one is evaluated
     cudaEvent_t copy_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
@@ -1130,7 +1160,12 @@ template <int PC, bool OUT>
 static int launch_direct(snaq_ctx *ctx, cudaStream_t stream, const double *dX, int Pc, double *dout, double *expcf, double *logpl,
                          double *deltacf) {
     const SnaqHostTables &H = ctx->H;
-    const size_t smem = 640 + 8 * PC * 8 + 8 * QD_SPAN * 8 + (OUT ? 0 : 8 * QD_NST * QD_STAGE_BYTES) + (size_t)PC * H.n_full * 8;
+    if (ctx->xarg_src) {                       // host-resident candidates: this launch's slice travels as the kernel argument
+        std::memcpy(ctx->xarg.v, ctx->xarg_src + (dX - ctx->xarg_base), sizeof(double) * (size_t)Pc * H.nparams);
+        ctx->xarg_on = true;
+    } else ctx->xarg_on = false;
+    const size_t smem = 640 + 8 * PC * 8 + 8 * QD_SPAN * 8 + (OUT ? 0 : 8 * QD_NST * QD_STAGE_BYTES) +
+                        (size_t)PC * (H.n_full + H.nparams) * 8;
     if (smem > 200 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_direct"; return SNAQ_EINVAL; }
     const int per_sm = (int)std::min<size_t>(OUT ? 2 : 3, (225 * 1024) / (smem + 1024));
     const int64_t work = (ctx->nq + 255) / 256;
@@ -1143,7 +1178,8 @@ static int launch_direct(snaq_ctx *ctx, cudaStream_t stream, const double *dX, i
         ctx->T, ctx->d_off, reinterpret_cast<const uint2 *>(ctx->d_prog), ctx->d_qhdr, ctx->d_perm, ctx->d_WA,
         reinterpret_cast<const double4 *>(ctx->d_W), ctx->d_obs, (uint32_t)ctx->nA1, (uint32_t)ctx->nA2,
         (uint32_t)(ctx->nA1 + (ctx->nA1 & 1)), (uint32_t)ctx->nq, dX,
-        ctx->d_xconst, H.nh, H.nt, Pc, ctx->d_partial, dout, ctx->d_negw3, ctx->d_ticket, expcf, logpl, deltacf, ctx->d_status + 1, ctx->d_trace);
+        ctx->d_xconst, H.nh, H.nt, Pc, ctx->d_partial, dout, ctx->d_negw3, ctx->d_ticket, expcf, logpl, deltacf, ctx->d_status + 1, ctx->d_trace,
+        ctx->status_out, ctx->xarg_on ? 1 : 0, ctx->xarg);
     CK(cudaGetLastError());
     ctx->counters[0] += 1;
     ctx->counters[1] += ctx->nq * (int64_t)Pc;
@@ -1540,6 +1576,31 @@ int snaq_eval(snaq_ctx *ctx, int32_t P, int32_t nparams, const double *X, double
     if (rc) return rc;
     rc = ensure_pin(ctx, nx + P + 2);
     if (rc) return rc;
+    if (P < LANES_MIN_P && ctx->nq > 0 && (size_t)std::min(P, 4) * nparams <= XARG_MAX) {
+        // small batch (a single objective call of the optimiser): the candidates travel as kernel arguments and the last
+        // block writes the results and the status word straight into page-locked host memory: no copy calls at all
+        double *h_out = ctx->h_pin;
+        uint32_t *h_st = reinterpret_cast<uint32_t *>(h_out + P);
+        *h_st = 0;
+        ctx->xarg_src = X;
+        ctx->xarg_base = ctx->d_X;
+        ctx->status_out = h_st;
+        rc = eval_device(ctx, P, ctx->d_X, h_out, ctx->stream, nullptr, nullptr, nullptr);
+        ctx->xarg_src = nullptr;
+        ctx->status_out = nullptr;
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->counters[2] += (int64_t)sizeof(double) * P * nparams;
+        ctx->counters[3] += (int64_t)sizeof(double) * P + 4;
+        if (*h_st) {
+            const uint32_t st = *h_st;
+            CK(cudaMemsetAsync(ctx->d_status + 1, 0, sizeof(uint32_t), ctx->stream));
+            if (st & SNAQ_S_RANGE) { rc = check_x_host(ctx, P, X); if (rc) return rc; }
+            return status_to_error(ctx, st);
+        }
+        std::memcpy(out, h_out, sizeof(double) * P);
+        return SNAQ_OK;
+    }
     // the bounds of update! (src/snaq_optimization.jl:213,221,228) are checked on the device; only when the device
     // reports a violation is the batch scanned on the host for the message.  A caller buffer that is already
     // page-locked is copied from directly; otherwise it is staged through the context's pinned buffer.
@@ -1604,7 +1665,7 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
     if (hdiag) for (int i = 0; i < nparams; i++) hdiag[i] = 0.0;
     if (ctx->nq == 0) { *f = 0.0; return SNAQ_OK; }
     const int nrows = hdiag ? 2 * n_full : n_full;
-    const size_t smem = 512 + 8 * QD_SPAN * 8 + (size_t)n_full * 8 + (size_t)nrows * 8;
+    const size_t smem = 512 + 8 * QD_SPAN * 8 + (size_t)n_full * 8 + (size_t)nrows * 8 + (size_t)nparams * 8;
     if (smem > 100 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_grad"; return SNAQ_EINVAL; }
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->nq + 255) / 256, (int64_t)ctx->sm_count * 2));
     rc = ensure(ctx, ctx->d_X, ctx->X_cap, (size_t)std::max(nparams, 1));
@@ -1617,8 +1678,17 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
     if (rc) return rc;
     rc = ensure_pin(ctx, (size_t)nparams + nrows + 4);
     if (rc) return rc;
-    std::memcpy(ctx->h_pin, x, sizeof(double) * nparams);
-    CK(cudaMemcpyAsync(ctx->d_X, ctx->h_pin, sizeof(double) * nparams, cudaMemcpyHostToDevice, ctx->stream));
+    // x travels as a kernel argument when it fits; the value, the gradient rows and the status word are written by the last
+    // block straight into page-locked host memory: the call is one launch and one stream synchronisation
+    const bool by_arg = nparams <= XARG_MAX;
+    double *h_g = ctx->h_pin + nparams;
+    uint32_t *h_st = reinterpret_cast<uint32_t *>(h_g + nrows + 1);
+    *h_st = 0;
+    if (by_arg) std::memcpy(ctx->xarg.v, x, sizeof(double) * nparams);
+    else {
+        std::memcpy(ctx->h_pin, x, sizeof(double) * nparams);
+        CK(cudaMemcpyAsync(ctx->d_X, ctx->h_pin, sizeof(double) * nparams, cudaMemcpyHostToDevice, ctx->stream));
+    }
 #define LAUNCH_GRAD(WH)                                                                                                        \
     do {                                                                                                                       \
         CK(cudaFuncSetAttribute(k_eval_grad<WH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
@@ -1626,15 +1696,11 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
             ctx->T, ctx->d_off, reinterpret_cast<const uint2 *>(ctx->d_prog), ctx->d_qhdr, ctx->d_WA,                           \
             reinterpret_cast<const double4 *>(ctx->d_W), (uint32_t)ctx->nA1, (uint32_t)ctx->nA2,                                \
             (uint32_t)(ctx->nA1 + (ctx->nA1 & 1)), (uint32_t)ctx->nq, ctx->d_X, ctx->d_xconst, H.nh, H.nt, ctx->d_partial,      \
-            ctx->d_gout, ctx->d_negw3, ctx->d_ticket, ctx->d_gpart, ctx->d_gout + 1, ctx->d_status + 1);                        \
+            h_g, ctx->d_negw3, ctx->d_ticket, ctx->d_gpart, h_g + 1, ctx->d_status + 1, h_st, by_arg ? 1 : 0, ctx->xarg);        \
     } while (0)
     if (hdiag) LAUNCH_GRAD(true); else LAUNCH_GRAD(false);
 #undef LAUNCH_GRAD
     CK(cudaGetLastError());
-    double *h_g = ctx->h_pin + nparams;
-    uint32_t *h_st = reinterpret_cast<uint32_t *>(h_g + nrows + 1);
-    CK(cudaMemcpyAsync(h_g, ctx->d_gout, sizeof(double) * (nrows + 1), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(h_st, ctx->d_status + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->counters[0] += 1;
     ctx->counters[1] += ctx->nq;
