@@ -769,7 +769,7 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
  */
 #define QG_SCALE 4294967296.0
 template <bool WANT_H>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restrict__ prog2, const uint8_t *__restrict__ qhdr,
             const double2 *__restrict__ WA, const double4 *__restrict__ W, uint32_t nA1, uint32_t nA2, uint32_t a2base, uint32_t nQ,
             const double *__restrict__ X, const double *__restrict__ xconst, int nh, int nt, double *__restrict__ partial,
@@ -1667,7 +1667,7 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
     const int nrows = hdiag ? 2 * n_full : n_full;
     const size_t smem = 512 + 8 * QD_SPAN * 8 + (size_t)n_full * 8 + (size_t)nrows * 8 + (size_t)nparams * 8;
     if (smem > 100 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_grad"; return SNAQ_EINVAL; }
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->nq + 255) / 256, (int64_t)ctx->sm_count * 2));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->nq + 255) / 256, (int64_t)ctx->sm_count * 3));
     rc = ensure(ctx, ctx->d_X, ctx->X_cap, (size_t)std::max(nparams, 1));
     if (rc) return rc;
     rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)grid);

@@ -108,6 +108,26 @@ int hostsim_run(const snaq_flatnet *f, int ntaxa, int64_t nq, const uint16_t *ta
     return 0;
 }
 
+/* the first 8 words of every program (NULL padded), its length in words and its header byte: layout statistics */
+int hostsim_progs(const snaq_flatnet *f, int ntaxa, int64_t nq, const uint16_t *taxa, uint16_t *words8, int32_t *len, uint8_t *hdr) {
+    SnaqHostTables H;
+    int rc = snaq_build_tables(f, ntaxa, H, g_err);
+    if (rc) return rc;
+    SnaqTables T = H.view(H.blob.data());
+    for (int64_t q = 0; q < nq; q++) {
+        uint16_t buf[256];
+        for (auto &b : buf) b = (uint16_t)H.n_xe;
+        SnaqWriter w{buf, 0, 256};
+        uint8_t h1 = 0;
+        int e = snaq_build_quartet(T, taxa + 4 * q, w, &h1, nullptr);
+        if (e) { g_err = "build error"; return SNAQ_ETOPOLOGY; }
+        for (int k = 0; k < 8; k++) words8[8 * q + k] = buf[k];
+        len[q] = w.n;
+        hdr[q] = h1;
+    }
+    return 0;
+}
+
 /* objective and analytic gradient of one parameter vector (the device functions of snaq_eval_grad, on the CPU) */
 int hostsim_grad(const snaq_flatnet *f, int ntaxa, int64_t nq, const uint16_t *taxa, const double *obs,
                  const uint8_t *sampled, const double *x, double *out_lik, double *grad, uint32_t *status_out) {
