@@ -377,12 +377,12 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
                 t0 += XLO(w.x) - XHI(w.x);
                 t1 += XLO(w.y) - XHI(w.y);
             }
-            return fmin(t0 + t1, 10.0);
+            return snaq_clamp10(t0 + t1);
         };
         const bool one_chunk = (q0 + nqc <= cr.nA1);      // every program of this block is one chunk: sprog[i]
         auto one_sum = [&](int i) {
             const uint2 w = sprog[i];
-            return fmin((XLO(w.x) - XHI(w.x)) + (XLO(w.y) - XHI(w.y)), 10.0);
+            return snaq_clamp10((XLO(w.x) - XHI(w.x)) + (XLO(w.y) - XHI(w.y)));
         };
         int i = warp;
 #pragma unroll 1
@@ -424,9 +424,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
                 if ((th & 3u) == SNAQ_T2) {
                     const unsigned wv = (unsigned)pc[k + 1] | ((unsigned)pc[k + 2] << 16);
                     k += 3;
-                    const double e = fmin(XLO(wv) - XHI(wv), 10.0);
+                    const double e = snaq_clamp10(XLO(wv) - XHI(wv));
                     const double gh = (th & 4u) ? 1.0 - gq : gq;
-                    R += fmin(-snaq_log(1.0 - gh * (1.0 - snaq_exp(-e, M)), M), 10.0);
+                    R += snaq_clamp10(-snaq_log(1.0 - gh * (1.0 - snaq_exp(-e, M)), M));
                 } else {
                     const unsigned wv = (unsigned)pc[k + 1] | ((unsigned)pc[k + 2] << 16);
                     const double clo = XLO(wv), chi = XHI(wv), ck = XLO((unsigned)pc[k + 3]);
@@ -438,21 +438,21 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
                         const unsigned wc = (unsigned)pc[k] | ((unsigned)pc[k + 1] << 16);
                         ch += XLO(wc) - XHI(wc);
                     }
-                    ch = fmin(ch, 10.0);
-                    const double ya = snaq_exp(-fmin(clo, 10.0), M), yb = snaq_exp(-fmin(ck - chi, 10.0), M);
-                    const double ye = snaq_exp(-fmin(chi - clo, 10.0), M);
+                    ch = snaq_clamp10(ch);
+                    const double ya = snaq_exp(-snaq_clamp10(clo), M), yb = snaq_exp(-snaq_clamp10(ck - chi), M);
+                    const double ye = snaq_exp(-snaq_clamp10(chi - clo), M);
                     const double ga = 1.0 - gq, gb = gq;
                     double l4 = -snaq_log(gb * gb * yb + ga * gb * (3.0 - ye) + ga * ga * ya, M);
                     if (l4 < SNAQ_MINLEN) st |= SNAQ_S_NEGLEN;
-                    l4 = fmin(l4, 10.0);
-                    const double B = fmin(ch + l4, 10.0);
+                    l4 = snaq_clamp10(l4);
+                    const double B = snaq_clamp10(ch + l4);
                     if (B < SNAQ_MINLEN) st |= SNAQ_S_NEGLEN;
                     if (th & 4u) Bf = B; else Bn = B;
                 }
             }
-            double t = fmin(Bn + R, 10.0);
+            double t = snaq_clamp10(Bn + R);
             if (t < SNAQ_MINLEN) st |= SNAQ_S_NEGLEN;
-            t = fmin(t + Bf, 10.0);
+            t = snaq_clamp10(t + Bf);
             if (t < SNAQ_MINLEN) st |= SNAQ_S_NEGLEN;
             const double y = snaq_exp(-t, M);
             const double major = fma(SNAQ_K_M23, y, 1.0);
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
             if (SNAQ_HDR_KIND(hd[i]) == SNAQ_KIND_T5) {
                 const double g2 = XLO(w.x), ca = XHI(w.x), cm = XLO(w.y), cb = XHI(w.y);
                 const double g1 = 1.0 - g2;
-                const double y5 = snaq_exp(-fmin(cm - ca, 10.0), M), y6 = snaq_exp(-fmin(cb - cm, 10.0), M);
+                const double y5 = snaq_exp(-snaq_clamp10(cm - ca), M), y6 = snaq_exp(-snaq_clamp10(cb - cm), M);
                 const double cf0 = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;
                 const double cf1 = g1 * 1.0 / 3.0 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
                 const double cf2 = g1 * 1.0 / 3.0 * y5 + g2 * 1.0 / 3.0 * y6;
@@ -660,7 +660,7 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
     if (!OUT) {
         const unsigned nullpair = (unsigned)T.n_xe * 0x10001u;
         auto tree_term = [&](double t, const double2 &w) {                // one additive quartet, one candidate
-            const double t1 = fmin(t, 10.0);
+            const double t1 = snaq_clamp10(t);
             const double y = snaq_exp(-t1, M);
             const double major = fma(SNAQ_K_M23, y, 1.0);
             return fma(w.x, snaq_log_pos(major, M), -w.y * (t1 + SNAQ_K_LOG3));
@@ -824,7 +824,7 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
     };
     auto addh = [&](unsigned slot, double v) { if (WANT_H) addhq(slot, __double2ll_rn(v * QG_SCALE)); };
     auto tree = [&](double t, const double2 &w, long long *gq, long long *hq) {   // additive quartet: value, dv/dt, -d2v/dt2
-        const double t1 = fmin(t, 10.0);
+        const double t1 = snaq_clamp10(t);
         const double a = 2.0 / 3.0 * snaq_exp(-t1, M);
         const double major = 1.0 - a;
         const double r = w.x * a / major;
