@@ -112,6 +112,29 @@ def test_optbl_matches_a_tight_optimisation_of_the_oracle_objective(oracle, seed
         assert np.max(np.abs(xmin - ref.x)[interior]) < 5e-4
 
 
+def test_optbl_reaches_the_optima_the_reference_published():
+    """examples/net0.out, net1.out, net1_snaq.out: same -Ploglik and same branch lengths / gammas (1e-6) as the reference's
+    own final optimisation, from a different start; the search-time-only networks of net1.networks: not worse."""
+    import os
+    from tests import kat
+    from tests.test_optbl_cpu import _published_optima
+    here, best, others = _published_optima()
+    for nw, lik, table in best + others:
+        d = S.readtableCF(os.path.join(here, "golden", table))
+        net = S.readnewicklevel1(nw)
+        x_ref = np.array(net.parameters(), dtype=np.float64)
+        upper = np.array(net.upper(), dtype=np.float64)
+        rng = np.random.default_rng(1)
+        start = np.clip(np.where(upper > 1.5, 1.0, 0.3) * rng.uniform(0.5, 1.5, len(x_ref)), 0, upper)
+        net.update_parameters(list(start))
+        res = S.optBL_(net, d, 1e-12, 1e-10, 1e-10, 1e-10)                      # fRelBL, fAbsBL, xRelBL, xAbsBL
+        if (nw, lik, table) in best:
+            assert abs(net.loglik - lik) <= 1e-10 * lik
+            assert np.max(np.abs(np.array(net.ht) - x_ref)) < 2e-6
+        else:
+            assert net.loglik <= lik + 1e-9
+
+
 def test_optbl_default_tolerances_and_fd_mode_agree():
     eng, flat, qt, obs, x0, upper = make(14, 2, 901, ngenes=200)
     start = np.clip(x0 * 1.2, 0, upper)

@@ -82,6 +82,20 @@ def test_golden_example_outputs(newick, lik):
     assert abs(-d.logPseudoLik.sum() - val) <= 1e-12 * val
 
 
+@pytest.mark.parametrize("i", range(8))
+def test_golden_more_example_outputs(i):
+    # examples/net1.networks (5 scored topologies), net2.out:1, net3.out:1 on tableCF.txt; net1_snaq.out:1 on tableCFCI.csv
+    cases = [(nw, lik, "tableCF.txt") for nw, lik in kat.NET1_NETWORKS]
+    cases += [(kat.NET2_OUT[0], kat.NET2_OUT[1], "tableCF.txt"), (kat.NET3_OUT[0], kat.NET3_OUT[1], "tableCF.txt"),
+              (kat.NET1_SNAQ_OUT[0], kat.NET1_SNAQ_OUT[1], "tableCFCI.csv")]
+    newick, lik, table = cases[i]
+    d = S.readtableCF(os.path.join(HERE, "golden", table))
+    net = S.readnewicklevel1(newick)
+    assert abs(S.topologyQpseudolik_(net, d) - lik) <= 1e-12 * lik
+    f, g = d._engine.eval_grad(np.array(net.ht))
+    assert abs(f - lik) <= 1e-12 * lik
+
+
 def test_golden_four_cycle_and_negative_expcf():
     net = S.readnewicklevel1(kat.NET_4CYCLE)                       # test/test_multipleAlleles.jl:66-72
     perms = np.array(list(itertools.permutations(range(4))), dtype=np.uint16)

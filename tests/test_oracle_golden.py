@@ -116,6 +116,27 @@ def test_example_outputs(oracle, newick, lik):
     assert abs(val - lik) <= 2e-14 * lik, (val, lik)
 
 
+def _more_examples():
+    cases = [(nw, lik, "tableCF.txt") for nw, lik in kat.NET1_NETWORKS]
+    cases += [(kat.NET2_OUT[0], kat.NET2_OUT[1], "tableCF.txt"), (kat.NET3_OUT[0], kat.NET3_OUT[1], "tableCF.txt"),
+              (kat.NET1_SNAQ_OUT[0], kat.NET1_SNAQ_OUT[1], "tableCFCI.csv")]
+    return cases
+
+
+@pytest.mark.parametrize("i", range(8))
+def test_more_example_outputs(oracle, i):
+    # examples/net1.networks (5 scored topologies), net2.out:1, net3.out:1, net1_snaq.out:1 (a second data set, with zeros)
+    newick, lik, table = _more_examples()[i]
+    d = S.readtableCF(os.path.join(HERE, "golden", table))
+    net = S.readnewicklevel1(newick)
+    flat = net.flatten(d.taxa)
+    val = oracle.evaluate(flat, d.quartet_taxa, d.obsCF, oracle.parameters(flat)["x"])[0]
+    assert abs(val - lik) <= 2e-14 * lik, (val, lik)
+    from tests import hostsim_py as hs                          # the engine's device functions, compiled for the host
+    r = hs.run(flat, len(d.taxa), d.quartet_taxa, obs=d.obsCF)
+    assert abs(r["lik"][0] - lik) <= 1e-13 * lik
+
+
 def test_four_cycle_expcf(oracle):
     # test/test_multipleAlleles.jl:66-72: every ordering of the 4 taxa of a 4-taxon network
     net = S.readnewicklevel1(kat.NET_4CYCLE)
