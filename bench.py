@@ -32,6 +32,10 @@ NET_SEED, OBS_SEED, X_SEED = 20261020, 1, 7
 FLOP_TREE, FLOP_T5_EXTRA, FLOP_PER_TERM = 110.0, 75.0, 90.0
 
 
+NCU_TRAFFIC_LANES_BYTES = 4466688          # profiles/r01b_ncu_summary.md: 4.466688 MB read, 0 written per launch
+NCU_TRAFFIC_DIRECT_BYTES = 113885184       # profiles/r01b_ncu_summary.md: 109.730816 MB read + 4.154368 MB written per launch
+
+
 def workload(ntaxa=NTAXA, nhyb=NHYB, nvec=NVEC):
     import snaq_jl_b200 as S
     net = S.simulate.random_level1_network(ntaxa, nhyb, NET_SEED)
@@ -243,7 +247,8 @@ def main():
         achieved_tf = evals_per_step * flop_per_eval / kernel_s / 1e12
         peak_tf = eng.measure_fp64_peak()
         roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                    "traffic": None, "flop_per_eval": flop_per_eval, "f5": f5, "cbar": cbar,
+                    "traffic": NCU_TRAFFIC_LANES_BYTES, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_eval_lanes "
+                    "launch in the committed ncu --set full capture (profiles/*_ncu_summary.md); inputs are L2/shared-memory resident", "flop_per_eval": flop_per_eval, "f5": f5, "cbar": cbar,
                     "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)"}
         line = {"metric": "quartet pseudolik evals/s (FP64)", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": float(ms.mean()), "higher_is_better": True, "scaling": "weak",
@@ -361,7 +366,7 @@ def hbm_leg(S, Engine, local, torch, peak_tf=None):
         _, r = eng.optbl(start, *tol)
         r["seconds"] = time.perf_counter() - t0
         optbl[name] = r
-    return {"batched": batched, "optbl": optbl, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": src,
+    return {"batched": batched, "optbl": optbl, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_DIRECT_BYTES, "peak_source": src,
             "workload": f"100-taxon h=3, {len(qt)} quartets, P=1 (one objective call), L2 flushed before every timed call",
             "ms_per_call": ms, "ms_per_call_warm_l2": ms_warm, "evals_per_s_warm_l2": len(qt) / (ms_warm * 1e-3),
             "achieved_at_survey_8d_56B_per_quartet": len(qt) * 56 / (ms * 1e-3) / 1e9,

@@ -128,6 +128,11 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net);
 int snaq_patch_network(snaq_ctx *ctx, const snaq_flatnet *net,
                        const int32_t *touched_taxa, int32_t n_touched);
 
+/* topologyQpseudolik! (src/pseudolik.jl:1342-1378) for a list of candidate topologies on the resident data:
+ * out[c] = pseudo-deviance of nets[c] at its own parameters (each is a descriptor rebuild + one objective call).
+ * The context is left holding the LAST network.                                                              */
+int snaq_eval_topologies(snaq_ctx *ctx, int32_t C, const snaq_flatnet *nets, double *out);
+
 /* parameters!(net): src/snaq_optimization.jl:54-101.  x = [gamma | t | gammaz].
  * numht: edge numbers (gamma, t) and "<node><1|2>" pseudo numbers (gammaz).
  * Any out pointer may be NULL.                                                */

@@ -1505,6 +1505,19 @@ int snaq_patch_network(snaq_ctx *ctx, const snaq_flatnet *net, const int32_t *to
     return snaq_set_network(ctx, net);
 }
 
+int snaq_eval_topologies(snaq_ctx *ctx, int32_t C, const snaq_flatnet *nets, double *out) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (C < 0 || (C > 0 && (!nets || !out))) { ctx->err = "bad arguments to snaq_eval_topologies"; return SNAQ_EINVAL; }
+    for (int32_t c = 0; c < C; c++) {
+        int rc = snaq_set_network(ctx, &nets[c]);
+        if (rc) { ctx->err = "topology " + std::to_string(c + 1) + ": " + ctx->err; return rc; }
+        const int np = ctx->H.nparams;
+        rc = snaq_eval(ctx, 1, np, np > 0 ? ctx->H.x0.data() : &out[c], &out[c]);    // np == 0: X is not read
+        if (rc) { ctx->err = "topology " + std::to_string(c + 1) + ": " + ctx->err; return rc; }
+    }
+    return SNAQ_OK;
+}
+
 int snaq_num_params(snaq_ctx *ctx, int32_t *nparams, int32_t *n_gamma, int32_t *n_t, int32_t *n_gammaz) {
     if (!ctx) return SNAQ_EINVAL;
     if (!ctx->has_net) { ctx->err = "snaq_set_network has not been called"; return SNAQ_ENODATA; }

@@ -118,7 +118,7 @@ extern "C" int snaq_optbl(snaq_ctx *ctx, const snaq_optbl_opts *o, double *x_io,
     const double ftol_rel = o ? o->ftol_rel : 1e-6, ftol_abs = o ? o->ftol_abs : 1e-6;
     const double xtol_rel = o ? o->xtol_rel : 1e-2, xtol_abs = o ? o->xtol_abs : 1e-3;
     const int maxeval = (o && o->maxeval > 0) ? o->maxeval : 1000;
-    int ladder = (o && o->ladder > 0) ? std::min(o->ladder, 64) : 20;
+    const int ladder_full = (o && o->ladder > 0) ? std::min(o->ladder, 64) : 20;
     if (!(ftol_rel > 0 && ftol_abs > 0 && xtol_rel > 0 && xtol_abs > 0)) return SNAQ_EINVAL;   // :350
     Problem pb;
     pb.ctx = ctx;
@@ -227,6 +227,9 @@ extern "C" int snaq_optbl(snaq_ctx *ctx, const snaq_optbl_opts *o, double *x_io,
         }
         if (!accepted) {
         // line search: one launch over a ladder of projected steps
+        // with curvature pairs the step length is near 1: eight rungs (4 .. 1/32) in one small launch; the full ladder is
+        // for the first iteration, the plateau, and the retry after a failed short ladder
+        const int ladder = (mem.empty() || plateau) ? ladder_full : std::min(ladder_full, 8);
         Xls.assign((size_t)ladder * n, 0.0);
         std::vector<double> alphas(ladder);
         for (int j = 0; j < ladder; j++) {

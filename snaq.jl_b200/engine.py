@@ -32,7 +32,8 @@ _LIB = None
 EXPORTS = ["snaq_create", "snaq_destroy", "snaq_last_error", "snaq_version", "snaq_set_data", "snaq_set_obscf",
            "snaq_set_sampled", "snaq_set_network", "snaq_patch_network", "snaq_num_params", "snaq_get_params",
            "snaq_eval", "snaq_eval_device", "snaq_eval_quartets", "snaq_get_descriptors", "snaq_get_counters",
-           "snaq_check_status", "snaq_measure_fp64_peak", "snaq_get_trace", "snaq_eval_grad", "snaq_optbl", "snaq_update_bl", "snaq_get_hasedge"]
+           "snaq_check_status", "snaq_measure_fp64_peak", "snaq_get_trace", "snaq_eval_grad", "snaq_optbl", "snaq_update_bl", "snaq_get_hasedge",
+           "snaq_eval_topologies"]
 
 
 class _OptblOpts(C.Structure):
@@ -121,9 +122,22 @@ class Engine:
     # -- topology --------------------------------------------------------------------
     def set_network(self, flat: FlatNet) -> None:
         self._chk(self.lib.snaq_set_network(self.ctx, flat.ptr()))
+        self.set_network_meta()
+
+    def set_network_meta(self) -> None:
         n = C.c_int32(); nh = C.c_int32(); nt = C.c_int32(); nz = C.c_int32()
         self._chk(self.lib.snaq_num_params(self.ctx, C.byref(n), C.byref(nh), C.byref(nt), C.byref(nz)))
         self.nparams, self.nh, self.nt, self.nhz = n.value, nh.value, nt.value, nz.value
+
+    def eval_topologies(self, flats) -> np.ndarray:
+        """pseudo-deviance of each flat network at its own parameters (topologyQpseudolik! over a list of candidates)"""
+        from .network import _CFlat
+        arr = (_CFlat * len(flats))(*[f.c for f in flats])
+        out = np.zeros(len(flats))
+        self._chk(self.lib.snaq_eval_topologies(self.ctx, C.c_int32(len(flats)), arr, _p(out)))
+        if flats:
+            self.set_network_meta()
+        return out
 
     def get_params(self):
         x = np.zeros(self.nparams); numht = np.zeros(self.nparams, np.int32); up = np.zeros(self.nparams)

@@ -96,6 +96,19 @@ def test_golden_more_example_outputs(i):
     assert abs(f - lik) <= 1e-12 * lik
 
 
+def test_golden_scored_topologies_in_one_call():
+    """examples/net1.networks: the five candidate topologies of the h=1 run scored by ONE snaq_eval_topologies call."""
+    d = S.readtableCF(os.path.join(HERE, "golden", "tableCF.txt"))
+    eng = S.Engine(0)
+    eng.set_data(d)
+    flats = [S.readnewicklevel1(nw).flatten(d.taxa) for nw, _ in kat.NET1_NETWORKS]
+    got = eng.eval_topologies(flats)
+    np.testing.assert_allclose(got, [lik for _, lik in kat.NET1_NETWORKS], rtol=1e-12)
+    x_last, _, _ = eng.get_params()                                   # the context holds the last network
+    assert abs(eng.eval(x_last)[0] - kat.NET1_NETWORKS[-1][1]) <= 1e-12 * kat.NET1_NETWORKS[-1][1]
+    assert eng.eval_topologies([]).shape == (0,)
+
+
 def test_golden_four_cycle_and_negative_expcf():
     net = S.readnewicklevel1(kat.NET_4CYCLE)                       # test/test_multipleAlleles.jl:66-72
     perms = np.array(list(itertools.permutations(range(4))), dtype=np.uint16)
