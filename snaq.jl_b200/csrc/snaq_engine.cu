@@ -280,6 +280,8 @@ struct ClassRanges {       // sorted quartet positions [0,nA) class A, [nA,nA+nB
     int64_t nA1;           // the first nA1 class-A quartets have one-chunk programs: off[i] == i
     int64_t nA, nB, nC;
     int chA, chB, chC;     // chunks (blocks) per class
+    int64_t nA2;           // the next nA2 class-A quartets have two-chunk programs at chunk a2base + 2 j
+    uint32_t a2base;
 };
 
 /*
@@ -499,6 +501,260 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
         for (int w = 0; w < WARPS; w++) s += red[w * 32 + lane];
         partial[(size_t)blockIdx.x * Ppad + 32 * g + lane] = s;
     }
+    if (st) atomicOr(status, st);
+}
+
+/*
+ * Persistent variant of k_eval_lanes: grid (gx, ngroups).  A block keeps its group's xf tile in shared memory and walks
+ * the quartet chunks cb = blockIdx.x, blockIdx.x + gx, ...: the weights and programs of chunk k+1 arrive by TMA bulk
+ * copies into the other of two stages while chunk k is evaluated.  The tile is loaded once per block instead of once
+ * per chunk (it is 150 KB at 200 taxa), the per-block prologue and epilogue are paid once, and the second pass adds gx
+ * rows instead of one row per chunk.  Chunks inside the one- and two-chunk class-A regions need no offset table.
+ */
+struct LanesPSmem {
+    size_t mt, bar, xs, stage, stage_bytes, sprog_off, red, soff, total;
+};
+__host__ __device__ inline LanesPSmem lanesp_smem_layout(int n_full, int chunk, int warps, uint32_t maxlen) {
+    LanesPSmem L;
+    size_t o = 0;
+    L.mt = o; o += SNAQ_MATH_DOUBLES * 8;
+    L.bar = o; o += 128;
+    L.xs = o; o += (size_t)n_full * 256;
+    L.sprog_off = (size_t)chunk * 32;
+    L.stage_bytes = (L.sprog_off + ((size_t)chunk * maxlen + 2) * 8 + 15) & ~size_t(15);
+    L.stage = o; o += 2 * L.stage_bytes;
+    L.red = o; o += (size_t)warps * 256;
+    L.soff = o; o += ((size_t)chunk + 1) * 4;
+    L.total = (o + 15) & ~size_t(15);
+    return L;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__restrict__ off, const uint16_t *__restrict__ prog,
+                                                           const uint8_t *__restrict__ qhdr, const double *__restrict__ W,
+                                                           ClassRanges cr, int chunk, uint32_t maxlen, const double *__restrict__ XFT,
+                                                           int n_full, double *__restrict__ partial, int Ppad,
+                                                           uint32_t *__restrict__ status, const int LANESP_SUPER) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const LanesPSmem L = lanesp_smem_layout(n_full, chunk, WARPS, maxlen);
+    double *mt = reinterpret_cast<double *>(smem + L.mt);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.bar);          // [0] xf tile, [1], [2] the two chunk stages
+    double *xs = reinterpret_cast<double *>(smem + L.xs);
+    double *red = reinterpret_cast<double *>(smem + L.red);
+    uint32_t *soff = reinterpret_cast<uint32_t *>(smem + L.soff);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = blockIdx.y;
+    const int nchunks_tot = cr.chA + cr.chB + cr.chC;
+    const uint2 *prog2 = reinterpret_cast<const uint2 *>(prog);
+    struct Meta { int cls; int64_t q0; int nqc; bool implicit; uint32_t mult, base, nch; };
+    // heavy classes first: C, B, then A
+    auto meta = [&](int cb) {
+        Meta m;
+        int64_t qbase, qend;
+        if (cb < cr.chC) { m.cls = 2; qbase = cr.nA + cr.nB; qend = qbase + cr.nC; }
+        else if (cb < cr.chC + cr.chB) { m.cls = 1; cb -= cr.chC; qbase = cr.nA; qend = qbase + cr.nB; }
+        else { m.cls = 0; cb -= cr.chC + cr.chB; qbase = 0; qend = cr.nA; }
+        m.q0 = qbase + (int64_t)cb * chunk;
+        m.nqc = (int)min((int64_t)chunk, qend - m.q0);
+        m.implicit = false; m.mult = 1u;
+        if (m.cls == 0 && m.q0 + m.nqc <= cr.nA1) { m.implicit = true; m.base = (uint32_t)m.q0; m.nch = (uint32_t)m.nqc; }
+        else if (m.cls == 0 && m.q0 >= cr.nA1 && m.q0 + m.nqc <= cr.nA1 + cr.nA2) {
+            m.implicit = true; m.mult = 2u; m.base = cr.a2base + 2u * (uint32_t)(m.q0 - cr.nA1); m.nch = 2u * (uint32_t)m.nqc;
+        } else { m.base = off[m.q0]; m.nch = off[m.q0 + m.nqc] - m.base; }
+        return m;
+    };
+    auto issue = [&](const Meta &m, int s) {                             // thread 0 only
+        unsigned char *st = smem + L.stage + (size_t)s * L.stage_bytes;
+        const uint32_t base16 = m.base & ~1u;                            // programs start at 8 bytes; the bulk copy needs 16
+        const unsigned prog_bytes = (((m.base - base16) + m.nch) * 8u + 15u) & ~15u, w_bytes = (unsigned)m.nqc * 32u;
+        mbar_expect_tx(&bar[1 + s], w_bytes + prog_bytes);
+        tma_load_1d(st, W + (size_t)m.q0 * 4, w_bytes, &bar[1 + s]);
+        tma_load_1d(st + L.sprog_off, prog2 + base16, prog_bytes, &bar[1 + s]);
+    };
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1); }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar[0], (unsigned)n_full * 256u);
+        tma_load_1d(xs, XFT + (size_t)g * n_full * 32, (unsigned)n_full * 256u, &bar[0]);
+        if ((int)blockIdx.x * LANESP_SUPER < nchunks_tot) issue(meta((int)blockIdx.x * LANESP_SUPER), 0);
+    }
+    const SnaqMath M = load_math_tables(mt, tid);
+    unsigned st = 0;
+    mbar_wait(&bar[0], 0);
+    __syncthreads();
+    double acc = 0.0;
+    const double *xl = xs + lane;
+    // One PRMT per slot builds the byte offset slot*256 + lane*8 of xf[slot] for this lane.
+    const unsigned lane8 = (unsigned)lane * 8u;
+    const char *xb = reinterpret_cast<const char *>(xs);
+#define XLO(w) (*reinterpret_cast<const double *>(xb + __byte_perm((w), lane8, 0x5104)))
+#define XHI(w) (*reinterpret_cast<const double *>(xb + __byte_perm((w), lane8, 0x5324)))
+    // A block walks SUPER-CHUNKS (LANESP_SUPER consecutive chunks; the host derives it from the table size only) sc = blockIdx.x, blockIdx.x + gx, ... and writes one
+    // partial row per super-chunk: the sums do not depend on how many blocks the launch has (hence not on P).
+    auto next_chunk = [&](int cb) {
+        if ((cb % LANESP_SUPER) != LANESP_SUPER - 1 && cb + 1 < nchunks_tot) return cb + 1;
+        const int nx = (cb / LANESP_SUPER + (int)gridDim.x) * LANESP_SUPER;
+        return nx < nchunks_tot ? nx : -1;
+    };
+    int it = 0;
+#pragma unroll 1
+    for (int cbi = (int)blockIdx.x * LANESP_SUPER; cbi >= 0 && cbi < nchunks_tot; it++) {
+        const int sidx = it & 1;
+        const Meta m = meta(cbi);
+        const int cnext = next_chunk(cbi);
+        // the other stage was last read in the previous iteration, which ended with a __syncthreads: refill it
+        if (tid == 0 && cnext >= 0) issue(meta(cnext), sidx ^ 1);
+        const int cls = m.cls, nqc = m.nqc;
+        const bool implicit = m.implicit;
+        const uint32_t mult = m.mult;
+        if (!implicit) for (int i = tid; i <= nqc; i += WARPS * 32) soff[i] = off[m.q0 + i] - m.base;
+        auto SO = [&](int i) { return implicit ? (uint32_t)i * mult : soff[i]; };
+        const unsigned char *stg = smem + L.stage + (size_t)sidx * L.stage_bytes;
+        const double *sW = reinterpret_cast<const double *>(stg);
+        const uint2 *sprog = reinterpret_cast<const uint2 *>(stg + L.sprog_off) + (m.base - (m.base & ~1u));
+        const int64_t q0 = m.q0;
+        mbar_wait(&bar[1 + sidx], (unsigned)(it >> 1) & 1u);
+        __syncthreads();
+        if (cls == 0) {
+            // class A: t1 = min(10, sum of signed pairs); two quartets per iteration (independent chains, the
+            // polynomial constants are fetched once for both)
+            auto pair_sum = [&](int i) {
+                uint32_t c = SO(i);
+                const uint32_t o1 = SO(i + 1);
+                uint2 w = sprog[c];
+                double t0 = XLO(w.x) - XHI(w.x), t1 = XLO(w.y) - XHI(w.y);
+    #pragma unroll 1
+                for (++c; c < o1; ++c) {
+                    w = sprog[c];
+                    t0 += XLO(w.x) - XHI(w.x);
+                    t1 += XLO(w.y) - XHI(w.y);
+                }
+                return snaq_clamp10(t0 + t1);
+            };
+            const bool one_chunk = implicit && mult == 1u;   // every program of this chunk is one 8-byte chunk: sprog[i]
+            auto one_sum = [&](int i) {
+                const uint2 w = sprog[i];
+                return snaq_clamp10((XLO(w.x) - XHI(w.x)) + (XLO(w.y) - XHI(w.y)));
+            };
+            int i = warp;
+    #pragma unroll 1
+            for (; i + WARPS < nqc; i += 2 * WARPS) {
+                const double ta = one_chunk ? one_sum(i) : pair_sum(i), tb = one_chunk ? one_sum(i + WARPS) : pair_sum(i + WARPS);
+                const double ya = snaq_exp(-ta, M), yb = snaq_exp(-tb, M);
+                const double ma = fma(SNAQ_K_M23, ya, 1.0), mb = fma(SNAQ_K_M23, yb, 1.0);
+                const double la = snaq_log_pos(ma, M), lb = snaq_log_pos(mb, M);
+                const double4 wa = reinterpret_cast<const double4 *>(sW)[i], wb = reinterpret_cast<const double4 *>(sW)[i + WARPS];
+                acc += fma(wa.x, la, -fma(wa.y, ta + SNAQ_K_LOG3, wa.w));
+                acc += fma(wb.x, lb, -fma(wb.y, tb + SNAQ_K_LOG3, wb.w));
+            }
+            if (i < nqc) {
+                const double t = pair_sum(i);
+                const double y = snaq_exp(-t, M);
+                const double major = fma(SNAQ_K_M23, y, 1.0);
+                const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
+                acc += fma(w4.x, snaq_log_pos(major, M), -fma(w4.y, t + SNAQ_K_LOG3, w4.w));
+            }
+        } else if (cls == 1) {
+            // class B: tree-like with type-2 / type-4 terms (same arithmetic as snaq_tree_terms_t1)
+    #pragma unroll 1
+            for (int i = warp; i < nqc; i += WARPS) {
+                const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + SO(i));
+                const unsigned cw = pc[0];
+                const int npairs = (int)(cw & 255u), nterms = (int)(cw >> 8);
+                double R = 0.0;
+                int k = 1;
+    #pragma unroll 1
+                for (int j = 0; j < npairs; j++, k += 2) {
+                    const unsigned wv = (unsigned)pc[k] | ((unsigned)pc[k + 1] << 16);
+                    R += XLO(wv) - XHI(wv);
+                }
+                double Bn = 0.0, Bf = 0.0;
+    #pragma unroll 1
+                for (int it = 0; it < nterms; it++) {
+                    const unsigned th = pc[k];
+                    const double gq = XLO(th >> 4);
+                    if ((th & 3u) == SNAQ_T2) {
+                        const unsigned wv = (unsigned)pc[k + 1] | ((unsigned)pc[k + 2] << 16);
+                        k += 3;
+                        const double e = snaq_clamp10(XLO(wv) - XHI(wv));
+                        const double gh = (th & 4u) ? 1.0 - gq : gq;
+                        R += snaq_clamp10(-snaq_log(1.0 - gh * (1.0 - snaq_exp(-e, M)), M));
+                    } else {
+                        const unsigned wv = (unsigned)pc[k + 1] | ((unsigned)pc[k + 2] << 16);
+                        const double clo = XLO(wv), chi = XHI(wv), ck = XLO((unsigned)pc[k + 3]);
+                        const int nchain = pc[k + 4];
+                        k += 5;
+                        double ch = 0.0;
+    #pragma unroll 1
+                        for (int j = 0; j < nchain; j++, k += 2) {
+                            const unsigned wc = (unsigned)pc[k] | ((unsigned)pc[k + 1] << 16);
+                            ch += XLO(wc) - XHI(wc);
+                        }
+                        ch = snaq_clamp10(ch);
+                        const double ya = snaq_exp(-snaq_clamp10(clo), M), yb = snaq_exp(-snaq_clamp10(ck - chi), M);
+                        const double ye = snaq_exp(-snaq_clamp10(chi - clo), M);
+                        const double ga = 1.0 - gq, gb = gq;
+                        double l4 = -snaq_log(gb * gb * yb + ga * gb * (3.0 - ye) + ga * ga * ya, M);
+                        if (l4 < SNAQ_MINLEN) st |= SNAQ_S_NEGLEN;
+                        l4 = snaq_clamp10(l4);
+                        const double B = snaq_clamp10(ch + l4);
+                        if (B < SNAQ_MINLEN) st |= SNAQ_S_NEGLEN;
+                        if (th & 4u) Bf = B; else Bn = B;
+                    }
+                }
+                double t = snaq_clamp10(Bn + R);
+                if (t < SNAQ_MINLEN) st |= SNAQ_S_NEGLEN;
+                t = snaq_clamp10(t + Bf);
+                if (t < SNAQ_MINLEN) st |= SNAQ_S_NEGLEN;
+                const double y = snaq_exp(-t, M);
+                const double major = fma(SNAQ_K_M23, y, 1.0);
+                const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
+                if (major < 0.0) st |= SNAQ_S_NEGLEN;
+                const double lm = (w4.x != 0.0) ? snaq_log(major, M) : 0.0;      // obs == 0 contributes 0 (src/pseudolik.jl:1398)
+                acc += fma(w4.x, lm, -fma(w4.y, t + SNAQ_K_LOG3, w4.w));
+            }
+        } else {
+            // class C: 4-cycle quartets.  T5: [gslot, C_a, C_m, C_b] in one chunk; all three CFs are positive
+            const XLane xf{xl};
+            const uint8_t *hd = qhdr + q0;
+    #pragma unroll 1
+            for (int i = warp; i < nqc; i += WARPS) {
+                const uint2 w = sprog[SO(i)];
+                const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
+                if (SNAQ_HDR_KIND(hd[i]) == SNAQ_KIND_T5) {
+                    const double g2 = XLO(w.x), ca = XHI(w.x), cm = XLO(w.y), cb = XHI(w.y);
+                    const double g1 = 1.0 - g2;
+                    const double y5 = snaq_exp(-snaq_clamp10(cm - ca), M), y6 = snaq_exp(-snaq_clamp10(cb - cm), M);
+                    const double cf0 = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;
+                    const double cf1 = g1 * 1.0 / 3.0 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
+                    const double cf2 = g1 * 1.0 / 3.0 * y5 + g2 * 1.0 / 3.0 * y6;
+                    double v = -w4.w;
+                    v = fma(w4.x, snaq_log_pos(cf0, M), v);
+                    v = fma(w4.y, snaq_log_pos(cf1, M), v);
+                    v = fma(w4.z, snaq_log_pos(cf2, M), v);
+                    acc += v;
+                } else {
+                    const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + SO(i));
+                    double cf[3];
+                    snaq_t5_cf(SNAQ_KIND_T5BD1, pc, xf, M, cf);
+                    acc += snaq_loglik_t5(cf, sW + 4 * i, M, st);
+                }
+            }
+        }
+
+        const bool last_of_super = (cnext != cbi + 1);
+        if (last_of_super) { red[warp * 32 + lane] = acc; acc = 0.0; }
+        __syncthreads();                                                  // every warp is done with this stage and with soff
+        if (last_of_super && warp == 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) s += red[w * 32 + lane];
+            partial[(size_t)(cbi / LANESP_SUPER) * Ppad + 32 * g + lane] = s;
+        }
+        cbi = cnext;
+    }
+#undef XLO
+#undef XHI
     if (st) atomicOr(status, st);
 }
 
@@ -1088,6 +1344,7 @@ struct snaq_ctx {
     double *h_pin = nullptr; size_t pin_cap = 0;
     int sm_count = 148;
     int eval_chunks = 2;                  // snaq_eval pipelines large batches in this many chunks (SNAQ_EVAL_CHUNKS = 1..4)
+    int lanes_persistent = 1;             // SNAQ_LANES_PERSISTENT: 0 never, 1 for big xf tiles (default), 2 always
     int lanes_warps = 8;                  // warps per block of k_eval_lanes (SNAQ_LANES_WARPS = 8, 12 or 16)
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -1227,18 +1484,59 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
         CK(cudaGetLastError());
         const double *dXF = ctx->d_XF;
         const int ngroups = (P + 31) / 32, Ppad = ngroups * 32;
-        // chunk: quartets per block.  Enough blocks to fill the machine, bounded by shared memory.
+        ClassRanges cr;
+        cr.nA1 = ctx->nA1; cr.nA = ctx->nA; cr.nB = ctx->nB; cr.nC = ctx->nC;
+        cr.nA2 = ctx->nA2; cr.a2base = (uint32_t)(ctx->nA1 + (ctx->nA1 & 1));
+        if (ngroups > 65535) { ctx->err = "batch too large for one launch"; return SNAQ_EINVAL; }
+        // Big xf tiles (>= ~100 KB: 150+ taxa) leave room for one block per SM, and reloading the tile for every chunk of
+        // quartets dominates: there the persistent variant keeps the tile resident (measured at 200 taxa, P = 64:
+        // 31.2 -> 16.9 ms).  With small tiles the one-block-per-chunk kernel is faster (more, independent blocks per SM).
+        const bool big_tile = lanesp_smem_layout(H.n_full, 64, 8, ctx->maxlen).total > 110 * 1024;
+        if (ctx->lanes_persistent == 1 ? big_tile : ctx->lanes_persistent > 1) {
+            // persistent blocks: the xf tile stays in shared memory, chunks stream through two TMA stages; 16 warps per block
+            int warps = big_tile ? 16 : ctx->lanes_warps, chunk = 256;
+            while (chunk > 32 && lanesp_smem_layout(H.n_full, chunk, warps, ctx->maxlen).total > 200 * 1024) chunk >>= 1;
+            const size_t smem = lanesp_smem_layout(H.n_full, chunk, warps, ctx->maxlen).total;
+            if (smem > 227 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_lanes"; return SNAQ_EINVAL; }
+            cr.chA = (int)((cr.nA + chunk - 1) / chunk); cr.chB = (int)((cr.nB + chunk - 1) / chunk); cr.chC = (int)((cr.nC + chunk - 1) / chunk);
+            const int64_t nchunks = (int64_t)cr.chA + cr.chB + cr.chC;
+            if (nchunks > 2147483647LL) { ctx->err = "batch too large for one launch"; return SNAQ_EINVAL; }
+            // blocks per group: about two rounds of resident blocks over the whole grid
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(warps == 8 ? 4 : (warps == 12 ? 3 : 2), (225 * 1024) / (smem + 1024)));
+            const int64_t slots = (int64_t)ctx->sm_count * per_sm;
+            const int LANESP_SUPER = (int)std::max<int64_t>(1, std::min<int64_t>(8, nchunks / 1024));   // depends on the table only, not on P
+            const int64_t nsuper = (nchunks + LANESP_SUPER - 1) / LANESP_SUPER;
+            const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(nsuper, (2 * slots) / ngroups));
+            int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)nsuper * Ppad);
+            if (rc) return rc;
+            dim3 grid((unsigned)gx, (unsigned)ngroups);
+#define LAUNCH_LANESP(WN)                                                                                                      \
+    do {                                                                                                                       \
+        CK(cudaFuncSetAttribute(k_eval_lanes_p<WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
+        k_eval_lanes_p<WN><<<grid, WN * 32, smem, stream>>>(ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_W, cr, chunk, ctx->maxlen, \
+                                                           dXF, H.n_full, ctx->d_partial, Ppad, ctx->d_status + 1, LANESP_SUPER); \
+    } while (0)
+            if (warps == 8) LAUNCH_LANESP(8);
+            else if (warps == 12) LAUNCH_LANESP(12);
+            else LAUNCH_LANESP(16);
+#undef LAUNCH_LANESP
+            CK(cudaGetLastError());
+            k_reduce_partials_t<<<(P + 31) / 32, 256, 0, stream>>>(ctx->d_partial, (int)nsuper, Ppad, P, dout);
+            CK(cudaGetLastError());
+            ctx->counters[0] += 1;
+            ctx->counters[1] += nq * (int64_t)P;
+            return SNAQ_OK;
+        }
+        // one block per (chunk, group): quartets per block.  Enough blocks to fill the machine, bounded by shared memory.
         const int warps = ctx->lanes_warps;
         int chunk = 256;
         while (chunk > 64 && (int64_t)ngroups * ((nq + chunk - 1) / chunk) < (int64_t)ctx->sm_count * 8) chunk >>= 1;
         while (chunk > 32 && lanes_smem_layout(H.n_full, chunk, warps, ctx->maxlen).total > 200 * 1024) chunk >>= 1;
         const size_t smem = lanes_smem_layout(H.n_full, chunk, warps, ctx->maxlen).total;
         if (smem > 227 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_lanes"; return SNAQ_EINVAL; }
-        ClassRanges cr;
-        cr.nA1 = ctx->nA1; cr.nA = ctx->nA; cr.nB = ctx->nB; cr.nC = ctx->nC;
         cr.chA = (int)((cr.nA + chunk - 1) / chunk); cr.chB = (int)((cr.nB + chunk - 1) / chunk); cr.chC = (int)((cr.nC + chunk - 1) / chunk);
         const int64_t nchunks = (int64_t)cr.chA + cr.chB + cr.chC;
-        if (nchunks > 2147483647LL || ngroups > 65535) { ctx->err = "batch too large for one launch"; return SNAQ_EINVAL; }
+        if (nchunks > 2147483647LL) { ctx->err = "batch too large for one launch"; return SNAQ_EINVAL; }
         int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)nchunks * Ppad);
         if (rc) return rc;
         dim3 grid((unsigned)nchunks, (unsigned)ngroups);
@@ -1305,6 +1603,7 @@ int snaq_create(const snaq_opts *opts, snaq_ctx **out) {
         if (atoi(ev) > 0 && cudaMalloc((void **)&ctx->d_trace, (size_t)ctx->sm_count * 4 * 8 * sizeof(unsigned long long)) != cudaSuccess) ctx->d_trace = nullptr;
     }
     if (const char *ev = getenv("SNAQ_EVAL_CHUNKS")) { int v = atoi(ev); if (v >= 1 && v <= 4) ctx->eval_chunks = v; }
+    if (const char *ev = getenv("SNAQ_LANES_PERSISTENT")) ctx->lanes_persistent = atoi(ev);
     if (const char *ev = getenv("SNAQ_LANES_WARPS")) { int v = atoi(ev); if (v == 8 || v == 12 || v == 16) ctx->lanes_warps = v; }
     if ((e = cudaMalloc((void **)&ctx->d_status, 4 * sizeof(uint32_t))) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cudaMalloc((void **)&ctx->d_total, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
