@@ -233,18 +233,16 @@ class Engine:
 # ------------------------------------------------------------------------------------
 # reference-facing functions
 # ------------------------------------------------------------------------------------
-_ENGINES = {}
-
-
 def _engine_for(d: DataCF, device: int = 0) -> Engine:
-    """One engine per (DataCF, device): obsCF and the quartet list stay resident in HBM."""
-    key = (id(d), device)
-    eng = _ENGINES.get(key)
+    """One engine per (DataCF, device): obsCF and the quartet list stay resident in HBM.  The engine lives on the
+    DataCF object itself (no global cache keyed by id(): ids are reused once an object is collected)."""
+    engines = d.__dict__.setdefault("_engines", {})
+    eng = engines.get(device)
     if eng is None:
         eng = Engine(device)
         eng.set_data(d)
-        _ENGINES[key] = eng
-        d._engine = eng
+        engines[device] = eng
+    d._engine = eng
     return eng
 
 
