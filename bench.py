@@ -32,8 +32,8 @@ NET_SEED, OBS_SEED, X_SEED = 20261020, 1, 7
 FLOP_TREE, FLOP_T5_EXTRA, FLOP_PER_TERM = 110.0, 75.0, 90.0
 
 
-NCU_TRAFFIC_LANES_BYTES = 4466688          # profiles/r01b_ncu_summary.md: 4.466688 MB read, 0 written per launch
-NCU_TRAFFIC_DIRECT_BYTES = 113885184       # profiles/r01b_ncu_summary.md: 109.730816 MB read + 4.154368 MB written per launch
+NCU_TRAFFIC_LANES_BYTES = 4465920          # profiles/r01d_ncu_summary.md: 4.465920 MB read, 0 written per launch
+NCU_TRAFFIC_DIRECT_BYTES = 114077696       # profiles/r01d_ncu_summary.md: 109.735936 MB read + 4.341760 MB written per launch
 
 
 def workload(ntaxa=NTAXA, nhyb=NHYB, nvec=NVEC):

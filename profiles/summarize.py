@@ -18,7 +18,9 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_op_read.sum",
-        "smsp__thread_inst_executed_per_inst_executed.ratio"]
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__inst_executed_op_shared_atom.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum.pct_of_peak_sustained_elapsed"]
 
 
 def raw(rep):
@@ -106,6 +108,8 @@ with open(f"profiles/{tag}_ncu_summary.md", "w") as fh:
     import os
     if os.path.exists(f"{GO}/{tag}_quartets.ncu-rep"):
         kernel_summary(f"{GO}/{tag}_quartets.ncu-rep", "k_eval_quartets (100 taxa, 3.92 M quartets, P=1)", fh)
+    if os.path.exists(f"{GO}/{tag}_grad.ncu-rep"):
+        kernel_summary(f"{GO}/{tag}_grad.ncu-rep", "k_eval_grad (100 taxa, 3.92 M quartets, objective + gradient; `python profiles/run_optbl.py 100 3`)", fh)
     if os.path.exists(f"{GO}/{tag}_direct.ncu-rep"):
         kernel_summary(f"{GO}/{tag}_direct.ncu-rep", "k_eval_direct (100 taxa, 3.92 M quartets, P=1; `python profiles/run_single_call.py`)", fh)
 print("wrote", f"profiles/{tag}_ncu_summary.md")
