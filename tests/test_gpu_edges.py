@@ -116,3 +116,24 @@ def test_all_unsampled_and_context_reuse(oracle):
     eng.set_network(net3.flatten(taxa3))
     x3, _, _ = eng.get_params()
     assert np.isfinite(eng.eval(x3)[0])
+
+
+def test_persistent_batched_kernel_matches_the_default_and_the_oracle(oracle, monkeypatch):
+    """k_eval_lanes_p is selected for big xf tiles (>= ~150 taxa); SNAQ_LANES_PERSISTENT=2 forces it on a small network."""
+    net, taxa, qt = build(16, 3, 51)
+    flat = net.flatten(taxa)
+    obs = simulate.obs_from_expcf(oracle.extract(flat, qt)["expcf"], 60, 3)
+    x0 = None
+    got = {}
+    for mode in ("0", "2"):
+        monkeypatch.setenv("SNAQ_LANES_PERSISTENT", mode)
+        eng = S.Engine(0)
+        eng.set_data(S.DataCF(taxa, qt, obs))
+        eng.set_network(flat)
+        x0, _, upper = eng.get_params()
+        X = simulate.parameter_batch(x0, upper, 200, 4)
+        got[mode] = eng.eval(X)
+        assert np.array_equal(eng.eval(X[:64]), got[mode][:64])          # batch composition does not change a value
+        assert np.array_equal(eng.eval(X), got[mode])                    # nor does repeating the launch
+    np.testing.assert_allclose(got["2"], got["0"], rtol=1e-13)
+    np.testing.assert_allclose(got["2"], oracle.evaluate(flat, qt, obs, X), rtol=1e-10)
