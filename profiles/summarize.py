@@ -107,7 +107,7 @@ with open(f"profiles/{tag}_ncu_summary.md", "w") as fh:
     kernel_summary(f"{GO}/{tag}_lanes.ncu-rep", "k_eval_lanes (config 2: 27,405 quartets x 4096 vectors)", fh)
     import os
     if os.path.exists(f"{GO}/{tag}_quartets.ncu-rep"):
-        kernel_summary(f"{GO}/{tag}_quartets.ncu-rep", "k_eval_quartets (100 taxa, 3.92 M quartets, P=1)", fh)
+        kernel_summary(f"{GO}/{tag}_quartets.ncu-rep", "first-version single-call kernel (100 taxa, 3.92 M quartets, P=1)", fh)
     if os.path.exists(f"{GO}/{tag}_grad.ncu-rep"):
         kernel_summary(f"{GO}/{tag}_grad.ncu-rep", "k_eval_grad (100 taxa, 3.92 M quartets, objective + gradient; `python profiles/run_optbl.py 100 3`)", fh)
     if os.path.exists(f"{GO}/{tag}_direct.ncu-rep"):

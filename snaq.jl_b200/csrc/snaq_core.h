@@ -623,7 +623,8 @@ SNAQ_HD double snaq_log(double z, const SnaqMath &M) {
  *   row < n_xe               : constant (length of a non-identifiable internal edge)
  *   row == n_xe              : 0.0 (NULL slot)
  *   row <  n_xe+1+n_int      : D[v]   = sum of x over the edges from v up to the root
- *   else                     : -2 D[v]
+ *   else                     : the rows of a cycle (SnaqTables::crow): prefix sums C_j of its edge lengths, its
+ *                              type-3 terms, and -log(1-gammaz) for a bad diamond I
  */
 SNAQ_HD double snaq_clamp10(double v) { return v > 10.0 ? 10.0 : v; }   /* setLength!: src/auxiliary.jl:122-124 */
 
