@@ -18,7 +18,7 @@ struct FlatNet            # mirrors `snaq_flatnet` field for field
     edge_gamma::Ptr{Cdouble}; edge_node::Ptr{Cint}
     hybrid::Ptr{Cint}; leaf::Ptr{Cint}
 end
-struct Opts; device::Cint; rank::Cint; world_size::Cint; reserved::Cint; end
+struct Opts; device::Cint; rank::Cint; world_size::Cint; flags::Cuint; end     # flags: 1 = program deduplication
 
 mutable struct Engine
     ctx::Ptr{Cvoid}

@@ -96,8 +96,18 @@ __device__ __forceinline__ void load_taxa(const uint16_t *__restrict__ taxa, int
 }
 
 // pass 1 (original quartet order): program length in 4-word chunks and class of every quartet
-__global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_t *__restrict__ taxa, int64_t nq,
-                                                     uint32_t *__restrict__ len4, uint8_t *__restrict__ cls,
+// SORT KEY: (sort class << 28) | 28-bit hash of the quartet's hybridisation term (classes B and C; 0 for class A,
+// which keeps the data's order).  Quartets with the same term (same cycle, same hit positions) become neighbours, so the
+// batched kernel can reuse the term it has just computed (see the memo_* variables of k_eval_lanes).
+__device__ __forceinline__ uint32_t term_hash(unsigned a, unsigned b, unsigned c, unsigned d) {
+    uint32_t h = a * 0x9E3779B1u;
+    h = (h ^ b) * 0x85EBCA77u;
+    h = (h ^ c) * 0xC2B2AE3Du;
+    h = (h ^ d) * 0x27D4EB2Fu;
+    return (h ^ (h >> 15)) & 0x0FFFFFFFu;
+}
+__global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_t *__restrict__ taxa, int64_t nq, const int dedup,
+                                                     uint32_t *__restrict__ len4, uint32_t *__restrict__ cls,
                                                      uint32_t *__restrict__ iota, unsigned long long *__restrict__ stats,
                                                      uint32_t *__restrict__ status) {
     // stats: [0] total chunks, [1] max chunks, [2..6] quartets per sort class
@@ -108,7 +118,8 @@ __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_
     if (q < nq) {
         uint16_t tx[4];
         load_taxa(taxa, q, tx);
-        SnaqWriter w{nullptr, 0, 0};
+        uint16_t head[24];                                     // the first words of the program: enough for the term key
+        SnaqWriter w{head, 0, 24};
         uint8_t hdr = 0;
         int e = snaq_build_quartet(T, tx, w, &hdr, nullptr);
         if (e) { atomicMax(status, (uint32_t)e); w.n = 1; hdr = 0; }
@@ -116,8 +127,23 @@ __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_
         if (n == 0) n = 1;
         c = SNAQ_HDR_CLASS(hdr);
         c = (c == 0) ? (n == 1 ? 0u : (n == 2 ? 1u : 2u)) : c + 2u;
+        uint32_t key = 0;
+        if (c == 4u && w.n >= 4) key = term_hash(head[0], head[1], head[2], head[3]);
+        else if (c == 3u) {
+            const int pos = 1 + 2 * (int)(head[0] & 255u);     // first term header, behind the count word and the plain pairs
+            if (pos + 3 < 24 && pos + 3 < w.n) key = (head[pos] & 3u) == SNAQ_T2 ? term_hash(head[pos], head[pos + 1], head[pos + 2], 0u)
+                                                   : term_hash(head[pos] & ~4u, head[pos + 1], head[pos + 2], head[pos + 3]);
+        }
+        if (dedup) {
+            // program deduplication: the key is a hash of the WHOLE program, so that identical programs become neighbours
+            // (programs longer than the captured head hash only its first 24 words: they may be split into several runs)
+            uint32_t h = (uint32_t)w.n * 0x9E3779B1u;
+            const int m = w.n < 24 ? w.n : 24;
+            for (int i = 0; i < m; i++) h = (h ^ head[i]) * 0x85EBCA77u;
+            key = (h ^ (h >> 15)) & 0x0FFFFFFFu;
+        }
         len4[q] = n;
-        cls[q] = (uint8_t)c;
+        cls[q] = (c << 28) | key;
         iota[q] = (uint32_t)q;
     }
     __shared__ unsigned long long ssum[4];
@@ -168,6 +194,85 @@ __global__ void __launch_bounds__(128) k_build_emit(SnaqTables T, const uint16_t
     else if (w.n > cap) { atomicMax(status, (uint32_t)SNAQ_B_OVERFLOW); w.n = cap; }
     for (int k = w.n; k < cap; k++) dst[k] = (uint16_t)T.n_xe;      // NULL slot (value 0.0)
     qhdr[i] = hdr;
+}
+
+// ---- program deduplication (opt-in: SNAQ_OPT_DEDUP) ----------------------------------------------------------------
+// The expected CFs of a quartet depend on its program only (split, internal path, cycle terms), and the pseudo-deviance is
+// linear in the weights 100*obsCF: quartets with the SAME program can be evaluated once with the SUM of their weights.
+// After the sort by program hash, equal programs are neighbours: flag the first of every run (exact comparison of class,
+// length and words), number the runs, copy one program per run into a second, compressed table, and add up the weights.
+__global__ void __launch_bounds__(256) k_dedup_flags(const uint32_t *__restrict__ off, const uint2 *__restrict__ prog2,
+                                                     const uint8_t *__restrict__ qhdr, int64_t nq, int64_t pad_at,
+                                                     uint32_t *__restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    uint32_t f = 1;
+    if (i > 0) {
+        const uint32_t a0 = off[i - 1], a1 = off[i], b1 = off[i + 1];
+        const uint32_t la = a1 - a0 - (i - 1 == pad_at ? 1u : 0u), lb = b1 - a1 - (i == pad_at ? 1u : 0u);
+        const unsigned ha = qhdr[i - 1], hb = qhdr[i];
+        if (la == lb && SNAQ_HDR_KIND(ha) == SNAQ_HDR_KIND(hb) && SNAQ_HDR_TERMS(ha) == SNAQ_HDR_TERMS(hb)) {
+            f = 0;
+            for (uint32_t c = 0; c < la; c++) {
+                const uint2 x = prog2[a0 + c], y = prog2[a1 + c];
+                if (x.x != y.x || x.y != y.y) { f = 1; break; }
+            }
+        }
+    }
+    flags[i] = f;
+}
+// uidx = inclusive scan of flags (1-based run number).  Per run: first position, length (+1 pad chunk at pad_u), header.
+__global__ void __launch_bounds__(256) k_dedup_heads(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ uidx,
+                                                     const uint32_t *__restrict__ off, const uint8_t *__restrict__ qhdr, int64_t nq,
+                                                     int64_t pad_at, int64_t pad_u, uint32_t *__restrict__ rstart,
+                                                     uint32_t *__restrict__ ulen, uint8_t *__restrict__ qhdr_u) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq || !flags[i]) return;
+    const uint32_t u = uidx[i] - 1u;
+    rstart[u] = (uint32_t)i;
+    ulen[u] = off[i + 1] - off[i] - (i == pad_at ? 1u : 0u) + ((int64_t)u == pad_u ? 1u : 0u);
+    qhdr_u[u] = qhdr[i];
+}
+__global__ void __launch_bounds__(256) k_dedup_copy(const uint32_t *__restrict__ rstart, const uint32_t *__restrict__ off,
+                                                    const uint2 *__restrict__ prog2, const uint32_t *__restrict__ off_u, int64_t nu,
+                                                    int64_t pad_u, unsigned nullslot, uint2 *__restrict__ prog_u) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nu) return;
+    const uint32_t src = off[rstart[u]], dst = off_u[u], n = off_u[u + 1] - dst - (u == pad_u ? 1u : 0u);
+    for (uint32_t c = 0; c < n; c++) prog_u[dst + c] = prog2[src + c];
+    if (u == pad_u) prog_u[dst + n] = make_uint2(nullslot * 0x10001u, nullslot * 0x10001u);
+}
+// weights of a run = sum of the weights of its quartets, in table order (deterministic); see k_weights for WA / wpart
+__global__ void __launch_bounds__(256) k_weights_u(const uint32_t *__restrict__ rstart, const double4 *__restrict__ W, int64_t nu,
+                                                   int64_t nq, int64_t nA12u, double4 *__restrict__ Wu, double2 *__restrict__ WAu,
+                                                   double *__restrict__ wpart) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double c3 = 0.0;
+    if (u < nu) {
+        const int64_t i0 = rstart[u], i1 = (u + 1 < nu) ? (int64_t)rstart[u + 1] : nq;
+        // compensated (Kahan) sums: a run can hold tens of thousands of quartets, and on data that fit well the deviance
+        // is a small difference of these sums
+        double s[4] = {0.0, 0.0, 0.0, 0.0}, c[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int64_t i = i0; i < i1; i++) {
+            const double4 w = W[i];
+            const double v[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const double y = __dsub_rn(v[k], c[k]);
+                const double t = __dadd_rn(s[k], y);
+                c[k] = __dsub_rn(__dsub_rn(t, s[k]), y);
+                s[k] = t;
+            }
+        }
+        const double4 a = make_double4(s[0], s[1], s[2], s[3]);
+        Wu[u] = a;
+        if (u < nA12u) { WAu[u] = make_double2(a.x, a.y); c3 = a.w; }
+    }
+    __shared__ double red[8];
+    for (int o = 16; o > 0; o >>= 1) c3 += __shfl_down_sync(0xffffffffu, c3, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c3;
+    __syncthreads();
+    if (threadIdx.x == 0) wpart[blockIdx.x] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
 }
 
 // W[i] (all classes) and, for the class-A quartets with one- and two-chunk programs [0,nA), the pair
@@ -405,7 +510,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
             acc += fma(w4.x, snaq_log_pos(major, M), -fma(w4.y, t + SNAQ_K_LOG3, w4.w));
         }
     } else if (cls == 1) {
-        // class B: tree-like with type-2 / type-4 terms (same arithmetic as snaq_tree_terms_t1)
+        // class B: tree-like with type-2 / type-4 terms (same arithmetic as snaq_tree_terms_t1).  The class is sorted by
+        // term, so the next quartet usually has the SAME term (cycle and hit positions): the value just computed is reused
+        // (the program is warp-uniform: the test does not diverge).
+        unsigned m4_k0 = 0xffffffffu, m4_k1 = 0xffffffffu, m2_k0 = 0xffffffffu, m2_k1 = 0xffffffffu;
+        double m4_l4 = 0.0, m2_v = 0.0;
 #pragma unroll 1
         for (int i = warp; i < nqc; i += WARPS) {
             const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + soff[i]);
@@ -426,12 +535,16 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
                 if ((th & 3u) == SNAQ_T2) {
                     const unsigned wv = (unsigned)pc[k + 1] | ((unsigned)pc[k + 2] << 16);
                     k += 3;
-                    const double e = snaq_clamp10(XLO(wv) - XHI(wv));
-                    const double gh = (th & 4u) ? 1.0 - gq : gq;
-                    R += snaq_clamp10(-snaq_log(1.0 - gh * (1.0 - snaq_exp(-e, M)), M));
+                    if (th != m2_k0 || wv != m2_k1) {
+                        const double e = snaq_clamp10(XLO(wv) - XHI(wv));
+                        const double gh = (th & 4u) ? 1.0 - gq : gq;
+                        m2_v = snaq_clamp10(-snaq_log(1.0 - gh * (1.0 - snaq_exp(-e, M)), M));
+                        m2_k0 = th; m2_k1 = wv;
+                    }
+                    R += m2_v;
                 } else {
                     const unsigned wv = (unsigned)pc[k + 1] | ((unsigned)pc[k + 2] << 16);
-                    const double clo = XLO(wv), chi = XHI(wv), ck = XLO((unsigned)pc[k + 3]);
+                    const unsigned kk0 = (th & ~4u) | ((unsigned)pc[k + 3] << 16);
                     const int nchain = pc[k + 4];
                     k += 5;
                     double ch = 0.0;
@@ -441,10 +554,15 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
                         ch += XLO(wc) - XHI(wc);
                     }
                     ch = snaq_clamp10(ch);
-                    const double ya = snaq_exp(-snaq_clamp10(clo), M), yb = snaq_exp(-snaq_clamp10(ck - chi), M);
-                    const double ye = snaq_exp(-snaq_clamp10(chi - clo), M);
-                    const double ga = 1.0 - gq, gb = gq;
-                    double l4 = -snaq_log(gb * gb * yb + ga * gb * (3.0 - ye) + ga * ga * ya, M);
+                    if (kk0 != m4_k0 || wv != m4_k1) {
+                        const double clo = XLO(wv), chi = XHI(wv), ck = XLO((unsigned)pc[k - 2 * nchain - 2]);
+                        const double ya = snaq_exp(-snaq_clamp10(clo), M), yb = snaq_exp(-snaq_clamp10(ck - chi), M);
+                        const double ye = snaq_exp(-snaq_clamp10(chi - clo), M);
+                        const double ga = 1.0 - gq, gb = gq;
+                        m4_l4 = -snaq_log(gb * gb * yb + ga * gb * (3.0 - ye) + ga * ga * ya, M);
+                        m4_k0 = kk0; m4_k1 = wv;
+                    }
+                    double l4 = m4_l4;
                     if (l4 < SNAQ_MINLEN) st |= SNAQ_S_NEGLEN;
                     l4 = snaq_clamp10(l4);
                     const double B = snaq_clamp10(ch + l4);
@@ -464,24 +582,31 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
             acc += fma(w4.x, lm, -fma(w4.y, t + SNAQ_K_LOG3, w4.w));
         }
     } else {
-        // class C: 4-cycle quartets.  T5: [gslot, C_a, C_m, C_b] in one chunk; all three CFs are positive
+        // class C: 4-cycle quartets.  T5: [gslot, C_a, C_m, C_b] in one chunk; all three CFs are positive.  Sorted by these
+        // four slots: the three logs are reused while they repeat.
         const XLane xf{xl};
+        unsigned m5_k0 = 0xffffffffu, m5_k1 = 0xffffffffu;
+        double m5_l0 = 0.0, m5_l1 = 0.0, m5_l2 = 0.0;
         const uint8_t *hd = qhdr + q0;
 #pragma unroll 1
         for (int i = warp; i < nqc; i += WARPS) {
             const uint2 w = sprog[soff[i]];
             const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
             if (SNAQ_HDR_KIND(hd[i]) == SNAQ_KIND_T5) {
-                const double g2 = XLO(w.x), ca = XHI(w.x), cm = XLO(w.y), cb = XHI(w.y);
-                const double g1 = 1.0 - g2;
-                const double y5 = snaq_exp(-snaq_clamp10(cm - ca), M), y6 = snaq_exp(-snaq_clamp10(cb - cm), M);
-                const double cf0 = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;
-                const double cf1 = g1 * 1.0 / 3.0 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
-                const double cf2 = g1 * 1.0 / 3.0 * y5 + g2 * 1.0 / 3.0 * y6;
+                if (w.x != m5_k0 || w.y != m5_k1) {
+                    const double g2 = XLO(w.x), ca = XHI(w.x), cm = XLO(w.y), cb = XHI(w.y);
+                    const double g1 = 1.0 - g2;
+                    const double y5 = snaq_exp(-snaq_clamp10(cm - ca), M), y6 = snaq_exp(-snaq_clamp10(cb - cm), M);
+                    const double cf0 = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;
+                    const double cf1 = g1 * 1.0 / 3.0 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
+                    const double cf2 = g1 * 1.0 / 3.0 * y5 + g2 * 1.0 / 3.0 * y6;
+                    m5_l0 = snaq_log_pos(cf0, M); m5_l1 = snaq_log_pos(cf1, M); m5_l2 = snaq_log_pos(cf2, M);
+                    m5_k0 = w.x; m5_k1 = w.y;
+                }
                 double v = -w4.w;
-                v = fma(w4.x, snaq_log_pos(cf0, M), v);
-                v = fma(w4.y, snaq_log_pos(cf1, M), v);
-                v = fma(w4.z, snaq_log_pos(cf2, M), v);
+                v = fma(w4.x, m5_l0, v);
+                v = fma(w4.y, m5_l1, v);
+                v = fma(w4.z, m5_l2, v);
                 acc += v;
             } else {
                 const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + soff[i]);
@@ -623,7 +748,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
                 const uint32_t o1 = SO(i + 1);
                 uint2 w = sprog[c];
                 double t0 = XLO(w.x) - XHI(w.x), t1 = XLO(w.y) - XHI(w.y);
-    #pragma unroll 1
+#pragma unroll 1
                 for (++c; c < o1; ++c) {
                     w = sprog[c];
                     t0 += XLO(w.x) - XHI(w.x);
@@ -637,7 +762,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
                 return snaq_clamp10((XLO(w.x) - XHI(w.x)) + (XLO(w.y) - XHI(w.y)));
             };
             int i = warp;
-    #pragma unroll 1
+#pragma unroll 1
             for (; i + WARPS < nqc; i += 2 * WARPS) {
                 const double ta = one_chunk ? one_sum(i) : pair_sum(i), tb = one_chunk ? one_sum(i + WARPS) : pair_sum(i + WARPS);
                 const double ya = snaq_exp(-ta, M), yb = snaq_exp(-tb, M);
@@ -655,46 +780,58 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
                 acc += fma(w4.x, snaq_log_pos(major, M), -fma(w4.y, t + SNAQ_K_LOG3, w4.w));
             }
         } else if (cls == 1) {
-            // class B: tree-like with type-2 / type-4 terms (same arithmetic as snaq_tree_terms_t1)
-    #pragma unroll 1
+            // class B: tree-like with type-2 / type-4 terms (same arithmetic as snaq_tree_terms_t1); terms are reused while
+            // they repeat (see k_eval_lanes)
+            unsigned m4_k0 = 0xffffffffu, m4_k1 = 0xffffffffu, m2_k0 = 0xffffffffu, m2_k1 = 0xffffffffu;
+            double m4_l4 = 0.0, m2_v = 0.0;
+#pragma unroll 1
             for (int i = warp; i < nqc; i += WARPS) {
                 const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + SO(i));
                 const unsigned cw = pc[0];
                 const int npairs = (int)(cw & 255u), nterms = (int)(cw >> 8);
                 double R = 0.0;
                 int k = 1;
-    #pragma unroll 1
+#pragma unroll 1
                 for (int j = 0; j < npairs; j++, k += 2) {
                     const unsigned wv = (unsigned)pc[k] | ((unsigned)pc[k + 1] << 16);
                     R += XLO(wv) - XHI(wv);
                 }
                 double Bn = 0.0, Bf = 0.0;
-    #pragma unroll 1
+#pragma unroll 1
                 for (int it = 0; it < nterms; it++) {
                     const unsigned th = pc[k];
                     const double gq = XLO(th >> 4);
                     if ((th & 3u) == SNAQ_T2) {
                         const unsigned wv = (unsigned)pc[k + 1] | ((unsigned)pc[k + 2] << 16);
                         k += 3;
-                        const double e = snaq_clamp10(XLO(wv) - XHI(wv));
-                        const double gh = (th & 4u) ? 1.0 - gq : gq;
-                        R += snaq_clamp10(-snaq_log(1.0 - gh * (1.0 - snaq_exp(-e, M)), M));
+                        if (th != m2_k0 || wv != m2_k1) {
+                            const double e = snaq_clamp10(XLO(wv) - XHI(wv));
+                            const double gh = (th & 4u) ? 1.0 - gq : gq;
+                            m2_v = snaq_clamp10(-snaq_log(1.0 - gh * (1.0 - snaq_exp(-e, M)), M));
+                            m2_k0 = th; m2_k1 = wv;
+                        }
+                        R += m2_v;
                     } else {
                         const unsigned wv = (unsigned)pc[k + 1] | ((unsigned)pc[k + 2] << 16);
-                        const double clo = XLO(wv), chi = XHI(wv), ck = XLO((unsigned)pc[k + 3]);
+                        const unsigned kk0 = (th & ~4u) | ((unsigned)pc[k + 3] << 16);
                         const int nchain = pc[k + 4];
                         k += 5;
                         double ch = 0.0;
-    #pragma unroll 1
+#pragma unroll 1
                         for (int j = 0; j < nchain; j++, k += 2) {
                             const unsigned wc = (unsigned)pc[k] | ((unsigned)pc[k + 1] << 16);
                             ch += XLO(wc) - XHI(wc);
                         }
                         ch = snaq_clamp10(ch);
-                        const double ya = snaq_exp(-snaq_clamp10(clo), M), yb = snaq_exp(-snaq_clamp10(ck - chi), M);
-                        const double ye = snaq_exp(-snaq_clamp10(chi - clo), M);
-                        const double ga = 1.0 - gq, gb = gq;
-                        double l4 = -snaq_log(gb * gb * yb + ga * gb * (3.0 - ye) + ga * ga * ya, M);
+                        if (kk0 != m4_k0 || wv != m4_k1) {
+                            const double clo = XLO(wv), chi = XHI(wv), ck = XLO((unsigned)pc[k - 2 * nchain - 2]);
+                            const double ya = snaq_exp(-snaq_clamp10(clo), M), yb = snaq_exp(-snaq_clamp10(ck - chi), M);
+                            const double ye = snaq_exp(-snaq_clamp10(chi - clo), M);
+                            const double ga = 1.0 - gq, gb = gq;
+                            m4_l4 = -snaq_log(gb * gb * yb + ga * gb * (3.0 - ye) + ga * ga * ya, M);
+                            m4_k0 = kk0; m4_k1 = wv;
+                        }
+                        double l4 = m4_l4;
                         if (l4 < SNAQ_MINLEN) st |= SNAQ_S_NEGLEN;
                         l4 = snaq_clamp10(l4);
                         const double B = snaq_clamp10(ch + l4);
@@ -714,24 +851,31 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
                 acc += fma(w4.x, lm, -fma(w4.y, t + SNAQ_K_LOG3, w4.w));
             }
         } else {
-            // class C: 4-cycle quartets.  T5: [gslot, C_a, C_m, C_b] in one chunk; all three CFs are positive
+            // class C: 4-cycle quartets.  T5: [gslot, C_a, C_m, C_b] in one chunk; all three CFs are positive.  Sorted by these
+            // four slots: the three logs are reused while they repeat.
             const XLane xf{xl};
+            unsigned m5_k0 = 0xffffffffu, m5_k1 = 0xffffffffu;
+            double m5_l0 = 0.0, m5_l1 = 0.0, m5_l2 = 0.0;
             const uint8_t *hd = qhdr + q0;
-    #pragma unroll 1
+#pragma unroll 1
             for (int i = warp; i < nqc; i += WARPS) {
                 const uint2 w = sprog[SO(i)];
                 const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
                 if (SNAQ_HDR_KIND(hd[i]) == SNAQ_KIND_T5) {
-                    const double g2 = XLO(w.x), ca = XHI(w.x), cm = XLO(w.y), cb = XHI(w.y);
-                    const double g1 = 1.0 - g2;
-                    const double y5 = snaq_exp(-snaq_clamp10(cm - ca), M), y6 = snaq_exp(-snaq_clamp10(cb - cm), M);
-                    const double cf0 = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;
-                    const double cf1 = g1 * 1.0 / 3.0 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
-                    const double cf2 = g1 * 1.0 / 3.0 * y5 + g2 * 1.0 / 3.0 * y6;
+                    if (w.x != m5_k0 || w.y != m5_k1) {
+                        const double g2 = XLO(w.x), ca = XHI(w.x), cm = XLO(w.y), cb = XHI(w.y);
+                        const double g1 = 1.0 - g2;
+                        const double y5 = snaq_exp(-snaq_clamp10(cm - ca), M), y6 = snaq_exp(-snaq_clamp10(cb - cm), M);
+                        const double cf0 = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;
+                        const double cf1 = g1 * 1.0 / 3.0 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
+                        const double cf2 = g1 * 1.0 / 3.0 * y5 + g2 * 1.0 / 3.0 * y6;
+                        m5_l0 = snaq_log_pos(cf0, M); m5_l1 = snaq_log_pos(cf1, M); m5_l2 = snaq_log_pos(cf2, M);
+                        m5_k0 = w.x; m5_k1 = w.y;
+                    }
                     double v = -w4.w;
-                    v = fma(w4.x, snaq_log_pos(cf0, M), v);
-                    v = fma(w4.y, snaq_log_pos(cf1, M), v);
-                    v = fma(w4.z, snaq_log_pos(cf2, M), v);
+                    v = fma(w4.x, m5_l0, v);
+                    v = fma(w4.y, m5_l1, v);
+                    v = fma(w4.z, m5_l2, v);
                     acc += v;
                 } else {
                     const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + SO(i));
@@ -1325,8 +1469,16 @@ struct snaq_ctx {
     uint32_t *d_perm = nullptr;           // [nq] sorted position -> original quartet
     uint8_t *d_qhdr = nullptr;            // [nq] header bytes, sorted order
     uint32_t *d_len4 = nullptr, *d_iota = nullptr;   // [nq] scratch of the build
-    uint8_t *d_cls = nullptr, *d_cls_sorted = nullptr;
+    uint32_t *d_cls = nullptr, *d_cls_sorted = nullptr;   // sort keys (class, term hash)
     int64_t nA1 = 0, nA2 = 0, nA = 0, nB = 0, nC = 0;   // nA1: leading class-A quartets whose program is exactly one chunk (off[i] == i)
+    // program deduplication (SNAQ_OPT_DEDUP): the compressed table the evaluation kernels read instead of the full one
+    bool dedup = false;
+    int64_t nU = 0, uA1 = 0, uA2 = 0, uA = 0, uB = 0, uC = 0;
+    uint32_t *d_flags = nullptr, *d_uidx = nullptr;              // [nq]
+    uint32_t *d_rstart = nullptr, *d_ulen = nullptr, *d_off_u = nullptr; size_t u_cap = 0;
+    uint8_t *d_qhdr_u = nullptr;
+    uint16_t *d_prog_u = nullptr; size_t prog_u_cap = 0; uint64_t prog_u_words = 0;
+    double *d_W_u = nullptr; double2 *d_WA_u = nullptr; double *d_wpart_u = nullptr, *d_negw3_u = nullptr;
     uint32_t *d_status = nullptr;          // [0] build, [1] eval
     unsigned long long *d_trace = nullptr; // SNAQ_TRACE=1: [blocks][8] phase timestamps of the last k_eval_direct launch
     int trace_blocks = 0;
@@ -1401,6 +1553,17 @@ static int status_to_error(snaq_ctx *ctx, uint32_t st) {
     return SNAQ_ENUMERIC;
 }
 
+// the table an evaluation kernel walks: the full one, or the deduplicated one (one entry per distinct program)
+struct EvalTable {
+    const uint32_t *off; const uint16_t *prog; const uint8_t *qhdr; const double *W; const double2 *WA; const double *negw3;
+    int64_t nq, nA1, nA2, nA, nB, nC;
+};
+static EvalTable eval_table(const snaq_ctx *ctx, bool full) {
+    if (ctx->dedup && !full) return EvalTable{ctx->d_off_u, ctx->d_prog_u, ctx->d_qhdr_u, ctx->d_W_u, ctx->d_WA_u, ctx->d_negw3_u,
+                                              ctx->nU, ctx->uA1, ctx->uA2, ctx->uA, ctx->uB, ctx->uC};
+    return EvalTable{ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_W, ctx->d_WA, ctx->d_negw3, ctx->nq, ctx->nA1, ctx->nA2, ctx->nA, ctx->nB, ctx->nC};
+}
+
 static int run_weights(snaq_ctx *ctx) {
     if (!ctx->has_net || ctx->nq == 0) return SNAQ_OK;
     int64_t nb = (ctx->nq + 255) / 256;
@@ -1410,6 +1573,68 @@ static int run_weights(snaq_ctx *ctx) {
     k_reduce_partials<<<1, 256, 0, ctx->stream>>>(ctx->d_wpart, (int)nb, 1, 1, ctx->d_negw3);
     CK(cudaGetLastError());
     ctx->counters[5] += 2;
+    if (ctx->dedup && ctx->nU > 0) {
+        const int64_t nbu = (ctx->nU + 255) / 256;
+        // no separate class-A constant for the compressed table (nA12u = 0 => negw3_u = 0): see launch_direct
+        k_weights_u<<<(unsigned)nbu, 256, 0, ctx->stream>>>(ctx->d_rstart, reinterpret_cast<const double4 *>(ctx->d_W), ctx->nU, ctx->nq,
+                                                           0, reinterpret_cast<double4 *>(ctx->d_W_u), ctx->d_WA_u, ctx->d_wpart_u);
+        CK(cudaGetLastError());
+        k_reduce_partials<<<1, 256, 0, ctx->stream>>>(ctx->d_wpart_u, (int)nbu, 1, 1, ctx->d_negw3_u);
+        CK(cudaGetLastError());
+        ctx->counters[5] += 2;
+    }
+    return SNAQ_OK;
+}
+
+// build the deduplicated table from the sorted full table (set_network, after k_build_emit)
+static int build_dedup(snaq_ctx *ctx, int64_t pad_at) {
+    const int64_t nq = ctx->nq;
+    const uint2 *prog2 = reinterpret_cast<const uint2 *>(ctx->d_prog);
+    k_dedup_flags<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_off, prog2, ctx->d_qhdr, nq, pad_at, ctx->d_flags);
+    CK(cudaGetLastError());
+    size_t t1 = ctx->scan_tmp_cap;
+    CK(cub::DeviceScan::InclusiveSum(ctx->d_scan_tmp, t1, ctx->d_flags, ctx->d_uidx, nq, ctx->stream));
+    // runs per class region: the run numbers at the region boundaries
+    const int64_t bnd[5] = {ctx->nA1, ctx->nA1 + ctx->nA2, ctx->nA, ctx->nA + ctx->nB, nq};
+    uint32_t ub[5] = {0, 0, 0, 0, 0};
+    for (int k = 0; k < 5; k++)
+        if (bnd[k] > 0) CK(cudaMemcpyAsync(&ub[k], ctx->d_uidx + (bnd[k] - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->uA1 = ub[0]; ctx->uA2 = (int64_t)ub[1] - ub[0]; ctx->uA = ub[2]; ctx->uB = (int64_t)ub[3] - ub[2]; ctx->uC = (int64_t)ub[4] - ub[3];
+    ctx->nU = ub[4];
+    const int64_t nu = ctx->nU;
+    if ((size_t)nu + 1 > ctx->u_cap) {
+        cudaFree(ctx->d_rstart); cudaFree(ctx->d_ulen); cudaFree(ctx->d_off_u); cudaFree(ctx->d_qhdr_u); cudaFree(ctx->d_W_u); cudaFree(ctx->d_WA_u);
+        cudaFree(ctx->d_wpart_u);
+        ctx->u_cap = 0;
+        const size_t n = (size_t)nu + 1 + (size_t)nu / 8;
+        CK(cudaMalloc((void **)&ctx->d_rstart, (n + 1) * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&ctx->d_ulen, (n + 1) * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&ctx->d_off_u, (n + 2) * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&ctx->d_qhdr_u, n + 1));
+        CK(cudaMalloc((void **)&ctx->d_W_u, (n + 1) * 4 * sizeof(double)));
+        CK(cudaMalloc((void **)&ctx->d_WA_u, (n + 1) * sizeof(double2)));
+        CK(cudaMalloc((void **)&ctx->d_wpart_u, ((n + 255) / 256 + 1) * sizeof(double)));
+        ctx->u_cap = n;
+    }
+    if (!ctx->d_negw3_u) CK(cudaMalloc((void **)&ctx->d_negw3_u, sizeof(double)));
+    const int64_t pad_u = (ctx->uA1 & 1) ? ctx->uA1 - 1 : -1;
+    k_dedup_heads<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_flags, ctx->d_uidx, ctx->d_off, ctx->d_qhdr, nq, pad_at, pad_u,
+                                                                        ctx->d_rstart, ctx->d_ulen, ctx->d_qhdr_u);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(ctx->d_off_u, 0, sizeof(uint32_t), ctx->stream));
+    t1 = ctx->scan_tmp_cap;
+    CK(cub::DeviceScan::InclusiveSum(ctx->d_scan_tmp, t1, ctx->d_ulen, ctx->d_off_u + 1, nu, ctx->stream));
+    uint32_t total = 0;
+    CK(cudaMemcpyAsync(&total, ctx->d_off_u + nu, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->prog_u_words = (uint64_t)total * 4;
+    int rc = ensure(ctx, ctx->d_prog_u, ctx->prog_u_cap, (size_t)ctx->prog_u_words + 8);
+    if (rc) return rc;
+    k_dedup_copy<<<(unsigned)((nu + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_rstart, ctx->d_off, prog2, ctx->d_off_u, nu, pad_u,
+                                                                       (unsigned)ctx->H.n_xe, reinterpret_cast<uint2 *>(ctx->d_prog_u));
+    CK(cudaGetLastError());
+    ctx->counters[5] += 5;
     return SNAQ_OK;
 }
 
@@ -1425,17 +1650,21 @@ static int launch_direct(snaq_ctx *ctx, cudaStream_t stream, const double *dX, i
                         (size_t)PC * (H.n_full + H.nparams) * 8;
     if (smem > 200 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_direct"; return SNAQ_EINVAL; }
     const int per_sm = (int)std::min<size_t>(OUT ? 2 : 3, (225 * 1024) / (smem + 1024));
-    const int64_t work = (ctx->nq + 255) / 256;
+    EvalTable tb = eval_table(ctx, OUT);                    // the per-quartet read-back walks the full table
+    // deduplicated table: every entry through the generic path, which subtracts the run's own constant W3 entry by entry
+    // (the separate class-A constant would turn the deviance into the difference of two large sums); the table is tiny
+    if (ctx->dedup && !OUT) tb.nA1 = tb.nA2 = 0;
+    const int64_t work = (tb.nq + 255) / 256;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(work, (int64_t)ctx->sm_count * per_sm));
     int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)grid * PC);
     if (rc) return rc;
     if (ctx->d_trace) ctx->trace_blocks = grid;
     CK(cudaFuncSetAttribute(k_eval_direct<PC, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_eval_direct<PC, OUT><<<grid, 256, smem, stream>>>(
-        ctx->T, ctx->d_off, reinterpret_cast<const uint2 *>(ctx->d_prog), ctx->d_qhdr, ctx->d_perm, ctx->d_WA,
-        reinterpret_cast<const double4 *>(ctx->d_W), ctx->d_obs, (uint32_t)ctx->nA1, (uint32_t)ctx->nA2,
-        (uint32_t)(ctx->nA1 + (ctx->nA1 & 1)), (uint32_t)ctx->nq, dX,
-        ctx->d_xconst, H.nh, H.nt, Pc, ctx->d_partial, dout, ctx->d_negw3, ctx->d_ticket, expcf, logpl, deltacf, ctx->d_status + 1, ctx->d_trace,
+        ctx->T, tb.off, reinterpret_cast<const uint2 *>(tb.prog), tb.qhdr, ctx->d_perm, tb.WA,
+        reinterpret_cast<const double4 *>(tb.W), ctx->d_obs, (uint32_t)tb.nA1, (uint32_t)tb.nA2,
+        (uint32_t)(tb.nA1 + (tb.nA1 & 1)), (uint32_t)tb.nq, dX,
+        ctx->d_xconst, H.nh, H.nt, Pc, ctx->d_partial, dout, tb.negw3, ctx->d_ticket, expcf, logpl, deltacf, ctx->d_status + 1, ctx->d_trace,
         ctx->status_out, ctx->xarg_on ? 1 : 0, ctx->xarg);
     CK(cudaGetLastError());
     ctx->counters[0] += 1;
@@ -1470,9 +1699,10 @@ static int eval_quartets_launch(snaq_ctx *ctx, int P, const double *dX, double *
 static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cudaStream_t stream,
                        double *expcf, double *logpl, double *deltacf) {
     const SnaqHostTables &H = ctx->H;
-    const int64_t nq = ctx->nq;
-    if (nq == 0) { CK(cudaMemsetAsync(dout, 0, sizeof(double) * P, stream)); return SNAQ_OK; }
+    if (ctx->nq == 0) { CK(cudaMemsetAsync(dout, 0, sizeof(double) * P, stream)); return SNAQ_OK; }
     const bool per_quartet = expcf || logpl || deltacf;
+    const EvalTable tb = eval_table(ctx, per_quartet);
+    const int64_t nq = tb.nq;
     const bool use_lanes = P >= LANES_MIN_P && !per_quartet;
     if (use_lanes) {
         const int Prows = (P + 31) & ~31;
@@ -1485,8 +1715,8 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
         const double *dXF = ctx->d_XF;
         const int ngroups = (P + 31) / 32, Ppad = ngroups * 32;
         ClassRanges cr;
-        cr.nA1 = ctx->nA1; cr.nA = ctx->nA; cr.nB = ctx->nB; cr.nC = ctx->nC;
-        cr.nA2 = ctx->nA2; cr.a2base = (uint32_t)(ctx->nA1 + (ctx->nA1 & 1));
+        cr.nA1 = tb.nA1; cr.nA = tb.nA; cr.nB = tb.nB; cr.nC = tb.nC;
+        cr.nA2 = tb.nA2; cr.a2base = (uint32_t)(tb.nA1 + (tb.nA1 & 1));
         if (ngroups > 65535) { ctx->err = "batch too large for one launch"; return SNAQ_EINVAL; }
         // Big xf tiles (>= ~100 KB: 150+ taxa) leave room for one block per SM, and reloading the tile for every chunk of
         // quartets dominates: there the persistent variant keeps the tile resident (measured at 200 taxa, P = 64:
@@ -1513,7 +1743,7 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
 #define LAUNCH_LANESP(WN)                                                                                                      \
     do {                                                                                                                       \
         CK(cudaFuncSetAttribute(k_eval_lanes_p<WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
-        k_eval_lanes_p<WN><<<grid, WN * 32, smem, stream>>>(ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_W, cr, chunk, ctx->maxlen, \
+        k_eval_lanes_p<WN><<<grid, WN * 32, smem, stream>>>(tb.off, tb.prog, tb.qhdr, tb.W, cr, chunk, ctx->maxlen,             \
                                                            dXF, H.n_full, ctx->d_partial, Ppad, ctx->d_status + 1, LANESP_SUPER); \
     } while (0)
             if (warps == 8) LAUNCH_LANESP(8);
@@ -1524,7 +1754,7 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
             k_reduce_partials_t<<<(P + 31) / 32, 256, 0, stream>>>(ctx->d_partial, (int)nsuper, Ppad, P, dout);
             CK(cudaGetLastError());
             ctx->counters[0] += 1;
-            ctx->counters[1] += nq * (int64_t)P;
+            ctx->counters[1] += ctx->nq * (int64_t)P;
             return SNAQ_OK;
         }
         // one block per (chunk, group): quartets per block.  Enough blocks to fill the machine, bounded by shared memory.
@@ -1543,7 +1773,7 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
 #define LAUNCH_LANES(WN)                                                                                                       \
     do {                                                                                                                       \
         CK(cudaFuncSetAttribute(k_eval_lanes<WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
-        k_eval_lanes<WN><<<grid, WN * 32, smem, stream>>>(ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_W, cr, chunk, ctx->maxlen, dXF, \
+        k_eval_lanes<WN><<<grid, WN * 32, smem, stream>>>(tb.off, tb.prog, tb.qhdr, tb.W, cr, chunk, ctx->maxlen, dXF,         \
                                                          H.n_full, ctx->d_partial, Ppad, ctx->d_status + 1);                    \
     } while (0)
         if (warps == 8) LAUNCH_LANES(8);
@@ -1554,7 +1784,7 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
         k_reduce_partials_t<<<(P + 31) / 32, 256, 0, stream>>>(ctx->d_partial, (int)nchunks, Ppad, P, dout);
         CK(cudaGetLastError());
         ctx->counters[0] += 1;
-        ctx->counters[1] += nq * (int64_t)P;
+        ctx->counters[1] += ctx->nq * (int64_t)P;
         return SNAQ_OK;
     }
     // small batches: thread per quartet, up to 4 candidates per launch
@@ -1584,6 +1814,7 @@ int snaq_create(const snaq_opts *opts, snaq_ctx **out) {
     ctx->device = opts ? opts->device : 0;
     ctx->rank = opts ? opts->rank : 0;
     ctx->world = (opts && opts->world_size > 0) ? opts->world_size : 1;
+    ctx->dedup = (opts && (opts->flags & SNAQ_OPT_DEDUP)) || (getenv("SNAQ_DEDUP") && atoi(getenv("SNAQ_DEDUP")) != 0);
     if (ctx->device < 0 || ctx->device >= ndev || ctx->rank < 0 || ctx->rank >= ctx->world) {
         g_create_err = "bad device ordinal or rank";
         delete ctx;
@@ -1620,6 +1851,8 @@ int snaq_destroy(snaq_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_blob); cudaFree(ctx->d_xconst);
     cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_WA); cudaFree(ctx->d_wpart); cudaFree(ctx->d_negw3); cudaFree(ctx->d_status); cudaFree(ctx->d_total); cudaFree(ctx->d_ticket); cudaFree(ctx->d_trace);
+    cudaFree(ctx->d_flags); cudaFree(ctx->d_uidx); cudaFree(ctx->d_rstart); cudaFree(ctx->d_ulen); cudaFree(ctx->d_off_u); cudaFree(ctx->d_qhdr_u);
+    cudaFree(ctx->d_prog_u); cudaFree(ctx->d_W_u); cudaFree(ctx->d_WA_u); cudaFree(ctx->d_wpart_u); cudaFree(ctx->d_negw3_u);
     cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_XF); cudaFree(ctx->d_out); cudaFree(ctx->d_partial); cudaFree(ctx->d_gpart); cudaFree(ctx->d_gout);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_qhdr); cudaFree(ctx->d_len4); cudaFree(ctx->d_iota); cudaFree(ctx->d_cls);
     cudaFree(ctx->d_cls_sorted);
@@ -1667,8 +1900,14 @@ int snaq_set_data(snaq_ctx *ctx, int32_t ntaxa, int64_t nq, const uint16_t *taxa
     CK(cudaMalloc((void **)&ctx->d_qhdr, n));
     CK(cudaMalloc((void **)&ctx->d_len4, n * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&ctx->d_iota, n * sizeof(uint32_t)));
-    CK(cudaMalloc((void **)&ctx->d_cls, n));
-    CK(cudaMalloc((void **)&ctx->d_cls_sorted, n));
+    cudaFree(ctx->d_flags); cudaFree(ctx->d_uidx);
+    ctx->d_flags = ctx->d_uidx = nullptr;
+    if (ctx->dedup) {
+        CK(cudaMalloc((void **)&ctx->d_flags, n * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&ctx->d_uidx, n * sizeof(uint32_t)));
+    }
+    CK(cudaMalloc((void **)&ctx->d_cls, n * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&ctx->d_cls_sorted, n * sizeof(uint32_t)));
     if (ctx->nq >= 0xFFFFFFFFLL) { ctx->err = "more than 2^32 quartets on one GPU: shard them (world_size>1)"; return SNAQ_EINVAL; }
     if (ctx->nq > 0) {
         CK(cudaMemcpyAsync(ctx->d_taxa, taxa + 4 * ctx->q_begin, (size_t)ctx->nq * 4 * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -1736,7 +1975,7 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
         CK(cudaMemsetAsync(ctx->d_total, 0, 8 * sizeof(unsigned long long), ctx->stream));
         CK(cudaMemsetAsync(ctx->d_status, 0, 4 * sizeof(uint32_t), ctx->stream));
         const int64_t nb = (nq + 127) / 128;
-        k_build_count<<<(unsigned)nb, 128, 0, ctx->stream>>>(ctx->T, ctx->d_taxa, nq, ctx->d_len4, ctx->d_cls, ctx->d_iota,
+        k_build_count<<<(unsigned)nb, 128, 0, ctx->stream>>>(ctx->T, ctx->d_taxa, nq, ctx->dedup ? 1 : 0, ctx->d_len4, ctx->d_cls, ctx->d_iota,
                                                             ctx->d_total, ctx->d_status);
         CK(cudaGetLastError());
         unsigned long long stt[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -1750,9 +1989,9 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
         ctx->maxlen = (uint32_t)stt[1];
         ctx->nA1 = (int64_t)stt[2]; ctx->nA2 = (int64_t)stt[3];
         ctx->nA = (int64_t)(stt[2] + stt[3] + stt[4]); ctx->nB = (int64_t)stt[5]; ctx->nC = (int64_t)stt[6];
-        // stable sort of the quartet indices by class (3-bit keys): perm = sorted position -> original quartet
+        // stable sort of the quartet indices by (class, term hash) (31-bit keys): perm = sorted position -> original quartet
         size_t tmp = 0, tmp2 = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_cls, ctx->d_cls_sorted, ctx->d_iota, ctx->d_perm, nq, 0, 3, ctx->stream));
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_cls, ctx->d_cls_sorted, ctx->d_iota, ctx->d_perm, nq, 0, 31, ctx->stream));
         uint32_t *d_len_sorted = ctx->d_off + 1;
         CK(cub::DeviceScan::InclusiveSum(nullptr, tmp2, d_len_sorted, d_len_sorted, nq, ctx->stream));
         tmp = std::max(tmp, tmp2);
@@ -1763,7 +2002,7 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
             ctx->scan_tmp_cap = tmp;
         }
         size_t t1 = ctx->scan_tmp_cap;
-        CK(cub::DeviceRadixSort::SortPairs(ctx->d_scan_tmp, t1, ctx->d_cls, ctx->d_cls_sorted, ctx->d_iota, ctx->d_perm, nq, 0, 3, ctx->stream));
+        CK(cub::DeviceRadixSort::SortPairs(ctx->d_scan_tmp, t1, ctx->d_cls, ctx->d_cls_sorted, ctx->d_iota, ctx->d_perm, nq, 0, 31, ctx->stream));
         // lengths in sorted order, scanned in place => d_off[i+1] = end of program i (chunks)
         CK(cudaMemsetAsync(ctx->d_off, 0, sizeof(uint32_t), ctx->stream));
         const int64_t pad_at = (ctx->nA1 & 1) ? ctx->nA1 - 1 : -1;
@@ -1778,6 +2017,8 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
                                                            ctx->d_status);
         CK(cudaGetLastError());
         ctx->counters[5] += 5;
+        ctx->nU = 0;
+        if (ctx->dedup) { rc = build_dedup(ctx, pad_at); if (rc) return rc; }
         ctx->has_net = true;
         rc = run_weights(ctx);
         if (rc) { ctx->has_net = false; return rc; }
@@ -1791,6 +2032,7 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
         const int64_t nG = ctx->nq - ctx->nA1 - ctx->nA2;
         const int64_t chunksG = (int64_t)(ctx->prog_words / 4) - ctx->nA1 - 2 * ctx->nA2;
         ctx->counters[6] = ctx->nA1 * 24 + ctx->nA2 * 32 + nG * (32 + 4 + 1) + chunksG * 8;
+        ctx->counters[7] = ctx->dedup ? ctx->nU : 0;
     }
     ctx->has_net = true;
     return SNAQ_OK;
@@ -1979,7 +2221,9 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
     const int nrows = hdiag ? 2 * n_full : n_full;
     const size_t smem = 512 + 8 * QD_SPAN * 8 + (size_t)n_full * 8 + (size_t)nrows * 8 + (size_t)nparams * 8;
     if (smem > 100 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_grad"; return SNAQ_EINVAL; }
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->nq + 255) / 256, (int64_t)ctx->sm_count * 3));
+    EvalTable tb = eval_table(ctx, false);
+    if (ctx->dedup) tb.nA1 = tb.nA2 = 0;                    // see launch_direct
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((tb.nq + 255) / 256, (int64_t)ctx->sm_count * 3));
     rc = ensure(ctx, ctx->d_X, ctx->X_cap, (size_t)std::max(nparams, 1));
     if (rc) return rc;
     rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)grid);
@@ -2005,10 +2249,10 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
     do {                                                                                                                       \
         CK(cudaFuncSetAttribute(k_eval_grad<WH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
         k_eval_grad<WH><<<grid, 256, smem, ctx->stream>>>(                                                                      \
-            ctx->T, ctx->d_off, reinterpret_cast<const uint2 *>(ctx->d_prog), ctx->d_qhdr, ctx->d_WA,                           \
-            reinterpret_cast<const double4 *>(ctx->d_W), (uint32_t)ctx->nA1, (uint32_t)ctx->nA2,                                \
-            (uint32_t)(ctx->nA1 + (ctx->nA1 & 1)), (uint32_t)ctx->nq, ctx->d_X, ctx->d_xconst, H.nh, H.nt, ctx->d_partial,      \
-            h_g, ctx->d_negw3, ctx->d_ticket, ctx->d_gpart, h_g + 1, ctx->d_status + 1, h_st, by_arg ? 1 : 0, ctx->xarg);        \
+            ctx->T, tb.off, reinterpret_cast<const uint2 *>(tb.prog), tb.qhdr, tb.WA,                                           \
+            reinterpret_cast<const double4 *>(tb.W), (uint32_t)tb.nA1, (uint32_t)tb.nA2,                                        \
+            (uint32_t)(tb.nA1 + (tb.nA1 & 1)), (uint32_t)tb.nq, ctx->d_X, ctx->d_xconst, H.nh, H.nt, ctx->d_partial,            \
+            h_g, tb.negw3, ctx->d_ticket, ctx->d_gpart, h_g + 1, ctx->d_status + 1, h_st, by_arg ? 1 : 0, ctx->xarg);        \
     } while (0)
     if (hdiag) LAUNCH_GRAD(true); else LAUNCH_GRAD(false);
 #undef LAUNCH_GRAD

@@ -47,7 +47,7 @@ class _OptblResult(C.Structure):
 
 
 class _Opts(C.Structure):
-    _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("world_size", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("world_size", C.c_int32), ("flags", C.c_uint32)]
 
 
 def load_library():
@@ -72,10 +72,11 @@ def _p(a):
 class Engine:
     """One engine context = one GPU + one stream (``snaq_ctx``)."""
 
-    def __init__(self, device: int = 0, rank: int = 0, world_size: int = 1):
+    def __init__(self, device: int = 0, rank: int = 0, world_size: int = 1, dedup: bool = False):
+        """dedup: evaluate each distinct quartet program once with summed weights (SNAQ_OPT_DEDUP, include/snaq_b200.h)"""
         self.lib = load_library()
         self.ctx = C.c_void_p()
-        opts = _Opts(device, rank, world_size, 0)
+        opts = _Opts(device, rank, world_size, 1 if dedup else 0)
         rc = self.lib.snaq_create(C.byref(opts), C.byref(self.ctx))
         if rc:
             raise SnaqError(f"snaq_create failed ({rc}): {self.lib.snaq_last_error(None).decode()}")
@@ -227,7 +228,7 @@ class Engine:
         self._chk(self.lib.snaq_get_counters(self.ctx, out))
         v = list(out)
         return dict(eval_launches=v[0], quartet_evals=v[1], h2d_bytes=v[2], d2h_bytes=v[3], descriptor_words=v[4],
-                    build_launches=v[5], single_call_bytes=v[6])
+                    build_launches=v[5], single_call_bytes=v[6], distinct_programs=v[7])
 
 
 # ------------------------------------------------------------------------------------
