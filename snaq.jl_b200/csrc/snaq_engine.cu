@@ -242,37 +242,50 @@ __global__ void __launch_bounds__(256) k_dedup_copy(const uint32_t *__restrict__
     for (uint32_t c = 0; c < n; c++) prog_u[dst + c] = prog2[src + c];
     if (u == pad_u) prog_u[dst + n] = make_uint2(nullslot * 0x10001u, nullslot * 0x10001u);
 }
-// weights of a run = sum of the weights of its quartets, in table order (deterministic); see k_weights for WA / wpart
-__global__ void __launch_bounds__(256) k_weights_u(const uint32_t *__restrict__ rstart, const double4 *__restrict__ W, int64_t nu,
-                                                   int64_t nq, int64_t nA12u, double4 *__restrict__ Wu, double2 *__restrict__ WAu,
-                                                   double *__restrict__ wpart) {
-    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double c3 = 0.0;
-    if (u < nu) {
-        const int64_t i0 = rstart[u], i1 = (u + 1 < nu) ? (int64_t)rstart[u + 1] : nq;
-        // compensated (Kahan) sums: a run can hold tens of thousands of quartets, and on data that fit well the deviance
-        // is a small difference of these sums
-        double s[4] = {0.0, 0.0, 0.0, 0.0}, c[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int64_t i = i0; i < i1; i++) {
-            const double4 w = W[i];
-            const double v[4] = {w.x, w.y, w.z, w.w};
+// weights of a run = sum of the weights of its quartets.  One block per run (runs are very uneven: from one quartet to
+// hundreds of thousands).  Every thread keeps a compensated (Kahan) sum of its strided share, then the 128 (sum, error)
+// pairs are combined by a fixed tree of error-free additions: deterministic, and accurate to about one rounding, which
+// matters because on data that fit well the deviance is a small difference of these sums.
+__device__ __forceinline__ void two_sum(double a, double b, double &s, double &e) {
+    s = __dadd_rn(a, b);
+    const double bb = __dsub_rn(s, a);
+    e = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
+}
+__global__ void __launch_bounds__(128) k_weights_u(const uint32_t *__restrict__ rstart, const double4 *__restrict__ W, int64_t nu,
+                                                   int64_t nq, double4 *__restrict__ Wu) {
+    const int64_t u = blockIdx.x;
+    const int64_t i0 = rstart[u], i1 = (u + 1 < nu) ? (int64_t)rstart[u + 1] : nq;
+    double s[4] = {0.0, 0.0, 0.0, 0.0}, c[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += 128) {
+        const double4 w = W[i];
+        const double v[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const double y = __dsub_rn(v[k], c[k]);
+            const double t = __dadd_rn(s[k], y);
+            c[k] = __dsub_rn(__dsub_rn(t, s[k]), y);
+            s[k] = t;
+        }
+    }
+    __shared__ double sh[2][4][128];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { sh[0][k][threadIdx.x] = s[k]; sh[1][k][threadIdx.x] = -c[k]; }   // value = sum + error
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const double y = __dsub_rn(v[k], c[k]);
-                const double t = __dadd_rn(s[k], y);
-                c[k] = __dsub_rn(__dsub_rn(t, s[k]), y);
-                s[k] = t;
+                double ss, ee;
+                two_sum(sh[0][k][threadIdx.x], sh[0][k][threadIdx.x + o], ss, ee);
+                sh[0][k][threadIdx.x] = ss;
+                sh[1][k][threadIdx.x] = __dadd_rn(__dadd_rn(sh[1][k][threadIdx.x], sh[1][k][threadIdx.x + o]), ee);
             }
         }
-        const double4 a = make_double4(s[0], s[1], s[2], s[3]);
-        Wu[u] = a;
-        if (u < nA12u) { WAu[u] = make_double2(a.x, a.y); c3 = a.w; }
+        __syncthreads();
     }
-    __shared__ double red[8];
-    for (int o = 16; o > 0; o >>= 1) c3 += __shfl_down_sync(0xffffffffu, c3, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c3;
-    __syncthreads();
-    if (threadIdx.x == 0) wpart[blockIdx.x] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+    if (threadIdx.x == 0)
+        Wu[u] = make_double4(__dadd_rn(sh[0][0][0], sh[1][0][0]), __dadd_rn(sh[0][1][0], sh[1][1][0]), __dadd_rn(sh[0][2][0], sh[1][2][0]),
+                             __dadd_rn(sh[0][3][0], sh[1][3][0]));
 }
 
 // W[i] (all classes) and, for the class-A quartets with one- and two-chunk programs [0,nA), the pair
@@ -1574,14 +1587,11 @@ static int run_weights(snaq_ctx *ctx) {
     CK(cudaGetLastError());
     ctx->counters[5] += 2;
     if (ctx->dedup && ctx->nU > 0) {
-        const int64_t nbu = (ctx->nU + 255) / 256;
-        // no separate class-A constant for the compressed table (nA12u = 0 => negw3_u = 0): see launch_direct
-        k_weights_u<<<(unsigned)nbu, 256, 0, ctx->stream>>>(ctx->d_rstart, reinterpret_cast<const double4 *>(ctx->d_W), ctx->nU, ctx->nq,
-                                                           0, reinterpret_cast<double4 *>(ctx->d_W_u), ctx->d_WA_u, ctx->d_wpart_u);
+        // no separate class-A constant for the compressed table (negw3_u stays 0): see launch_direct
+        k_weights_u<<<(unsigned)ctx->nU, 128, 0, ctx->stream>>>(ctx->d_rstart, reinterpret_cast<const double4 *>(ctx->d_W), ctx->nU, ctx->nq,
+                                                               reinterpret_cast<double4 *>(ctx->d_W_u));
         CK(cudaGetLastError());
-        k_reduce_partials<<<1, 256, 0, ctx->stream>>>(ctx->d_wpart_u, (int)nbu, 1, 1, ctx->d_negw3_u);
-        CK(cudaGetLastError());
-        ctx->counters[5] += 2;
+        ctx->counters[5] += 1;
     }
     return SNAQ_OK;
 }
@@ -1617,7 +1627,7 @@ static int build_dedup(snaq_ctx *ctx, int64_t pad_at) {
         CK(cudaMalloc((void **)&ctx->d_wpart_u, ((n + 255) / 256 + 1) * sizeof(double)));
         ctx->u_cap = n;
     }
-    if (!ctx->d_negw3_u) CK(cudaMalloc((void **)&ctx->d_negw3_u, sizeof(double)));
+    if (!ctx->d_negw3_u) { CK(cudaMalloc((void **)&ctx->d_negw3_u, sizeof(double))); CK(cudaMemsetAsync(ctx->d_negw3_u, 0, sizeof(double), ctx->stream)); }
     const int64_t pad_u = (ctx->uA1 & 1) ? ctx->uA1 - 1 : -1;
     k_dedup_heads<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_flags, ctx->d_uidx, ctx->d_off, ctx->d_qhdr, nq, pad_at, pad_u,
                                                                         ctx->d_rstart, ctx->d_ulen, ctx->d_qhdr_u);
