@@ -258,6 +258,13 @@ def main():
                            "nparams": npar, "l2": "flushed between timed iterations (inputs < L2)", "descriptor_build_s": t_build},
                 "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(P * npar * 8), "d2h_bytes_per_step": int(P * 8 + 4)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+        # ---- opt-in program deduplication (SNAQ_OPT_DEDUP): the same batch on the table with one entry per DISTINCT program.
+        # Reported apart from `value`: it evaluates fewer programs, so it says nothing about the kernel's roofline.
+        try:
+            line["dedup"] = dedup_leg(S, eng.__class__, local, torch, taxa, qt, obs, flat, dX, dout, stream, flush, evals_per_step,
+                                      with_100_taxa=not args.no_hbm)
+        except Exception as exc:  # noqa: BLE001
+            line["dedup"] = {"error": str(exc)[:200]}
         # ---- secondary: the 100-taxon table (3.92 M quartets): one objective call (P=1, HBM-bound) and a batch
         if not args.no_hbm:
             try:
@@ -273,6 +280,69 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def dedup_leg(S, Engine, local, torch, taxa, qt, obs, flat, dX, dout, stream, flush, evals_per_step, with_100_taxa=True):
+    """Same work as the main step, on an engine created with dedup=True (include/snaq_b200.h: SNAQ_OPT_DEDUP)."""
+    eng = Engine(local, dedup=True)
+    eng.set_data(S.DataCF(taxa, qt, obs))
+    eng.set_network(flat)
+    out = {"note": "opt-in: quartets with identical evaluation programs are evaluated once with the sum of their weights; "
+                   "'effective' rates count every quartet of the table", "quartets": int(len(qt)),
+           "distinct_programs": int(eng.counters()["distinct_programs"])}
+    ref = dout.clone()
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            eng.eval_device(dX, dout, stream)
+    torch.cuda.synchronize()
+    out["max_rel_diff_vs_plain"] = float(((dout - ref).abs() / ref.abs()).max().item())
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+    with torch.cuda.stream(stream):
+        for a, b in ev:
+            flush.fill_(1)
+            a.record(stream)
+            eng.eval_device(dX, dout, stream)
+            b.record(stream)
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    out["config2_ms_per_step"] = ms
+    out["config2_effective_evals_per_s"] = evals_per_step / (ms * 1e-3)
+    if with_100_taxa:
+        n = 100
+        net = S.simulate.random_level1_network(n, 3, 20261021)
+        tx = [f"t{i + 1}" for i in range(n)]
+        q100 = S.simulate.all_quartets(n)
+        e2 = Engine(local, dedup=True)
+        e2.set_data(S.DataCF(tx, q100, np.full((len(q100), 3), 1 / 3)))
+        fl = net.flatten(tx)
+        e2.set_network(fl)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            e2.set_network(fl)
+        out["t100_set_network_ms"] = (time.perf_counter() - t0) / 5 * 1e3
+        out["t100_quartets"] = int(len(q100))
+        out["t100_distinct_programs"] = int(e2.counters()["distinct_programs"])
+        x0, _, upper = e2.get_params()
+        exp0, _, _ = e2.eval_quartets(x0)
+        e2.set_obscf(S.simulate.obs_from_expcf(exp0, 300, 5))
+        rng = np.random.default_rng(0)
+        start = np.clip(x0 * rng.uniform(0.7, 1.3, len(x0)), 0, upper)
+        for _ in range(3):
+            e2.eval(start)
+            e2.eval_grad(start)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            e2.eval(start)
+        out["t100_objective_call_from_host_us"] = (time.perf_counter() - t0) / 50 * 1e6
+        t0 = time.perf_counter()
+        for _ in range(50):
+            e2.eval_grad(start)
+        out["t100_objective_plus_gradient_pass_us"] = (time.perf_counter() - t0) / 50 * 1e6
+        for name, tol in (("search_tolerances", (1e-6, 1e-6, 1e-2, 1e-3)), ("final_tolerances", (1e-12, 1e-10, 1e-10, 1e-10))):
+            t0 = time.perf_counter()
+            _, r = e2.optbl(start, *tol)
+            out["t100_optbl_" + name] = {"seconds": time.perf_counter() - t0, "fmin": r["fmin"], "nlaunches": r["nlaunches"]}
+    return out
 
 
 def hbm_leg(S, Engine, local, torch, peak_tf=None):
