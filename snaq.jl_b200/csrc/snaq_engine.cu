@@ -96,9 +96,9 @@ __device__ __forceinline__ void load_taxa(const uint16_t *__restrict__ taxa, int
 }
 
 // pass 1 (original quartet order): program length in 4-word chunks and class of every quartet
-// SORT KEY: (sort class << 28) | 28-bit hash of the quartet's hybridisation term (classes B and C; 0 for class A,
-// which keeps the data's order).  Quartets with the same term (same cycle, same hit positions) become neighbours, so the
-// batched kernel can reuse the term it has just computed (see the memo_* variables of k_eval_lanes).
+// SORT KEY: (sort class << 28) | 28-bit hash: of the whole program for class A, of the hybridisation term for classes B
+// and C.  Quartets with the same additive program / the same term (same cycle, same hit positions) become neighbours, so
+// the batched kernels can reuse what they have just computed (see the m*_ variables of k_eval_lanes).
 __device__ __forceinline__ uint32_t term_hash(unsigned a, unsigned b, unsigned c, unsigned d) {
     uint32_t h = a * 0x9E3779B1u;
     h = (h ^ b) * 0x85EBCA77u;
@@ -134,9 +134,10 @@ __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_
             if (pos + 3 < 24 && pos + 3 < w.n) key = (head[pos] & 3u) == SNAQ_T2 ? term_hash(head[pos], head[pos + 1], head[pos + 2], 0u)
                                                    : term_hash(head[pos] & ~4u, head[pos + 1], head[pos + 2], head[pos + 3]);
         }
-        if (dedup) {
-            // program deduplication: the key is a hash of the WHOLE program, so that identical programs become neighbours
-            // (programs longer than the captured head hash only its first 24 words: they may be split into several runs)
+        if (dedup || c <= 2u) {
+            // class A (always) and program deduplication (every class): the key is a hash of the WHOLE program, so that
+            // identical programs become neighbours (programs longer than the captured head hash only its first 24 words:
+            // they may be split into several runs)
             uint32_t h = (uint32_t)w.n * 0x9E3779B1u;
             const int m = w.n < 24 ? w.n : 24;
             for (int i = 0; i < m; i++) h = (h ^ head[i]) * 0x85EBCA77u;
@@ -484,8 +485,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
 #define XLO(w) (*reinterpret_cast<const double *>(xb + __byte_perm((w), lane8, 0x5104)))
 #define XHI(w) (*reinterpret_cast<const double *>(xb + __byte_perm((w), lane8, 0x5324)))
     if (cls == 0) {
-        // class A: t1 = min(10, sum of signed pairs); two quartets per iteration (independent chains, the
-        // polynomial constants are fetched once for both)
+        // class A: t1 = min(10, sum of signed pairs).  The class is sorted by program, and a quartet's expected CFs depend
+        // on its program only: while the program repeats (quartets that differ in taxa of the same clades) t1, exp and log
+        // are reused and the quartet costs its two weight FMAs (the program is warp-uniform: the test does not diverge).
         auto pair_sum = [&](int i) {
             uint32_t c = soff[i];
             const uint32_t o1 = soff[i + 1];
@@ -499,28 +501,25 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
             }
             return snaq_clamp10(t0 + t1);
         };
-        const bool one_chunk = (q0 + nqc <= cr.nA1);      // every program of this block is one chunk: sprog[i]
-        auto one_sum = [&](int i) {
-            const uint2 w = sprog[i];
-            return snaq_clamp10((XLO(w.x) - XHI(w.x)) + (XLO(w.y) - XHI(w.y)));
-        };
-        int i = warp;
+    (void)cr;
+        uint2 mw = make_uint2(0xffffffffu, 0xffffffffu), mw2 = mw;
+        double m_t = 0.0, m_l = 0.0;
 #pragma unroll 1
-        for (; i + WARPS < nqc; i += 2 * WARPS) {
-            const double ta = one_chunk ? one_sum(i) : pair_sum(i), tb = one_chunk ? one_sum(i + WARPS) : pair_sum(i + WARPS);
-            const double ya = snaq_exp(-ta, M), yb = snaq_exp(-tb, M);
-            const double ma = fma(SNAQ_K_M23, ya, 1.0), mb = fma(SNAQ_K_M23, yb, 1.0);
-            const double la = snaq_log_pos(ma, M), lb = snaq_log_pos(mb, M);
-            const double4 wa = reinterpret_cast<const double4 *>(sW)[i], wb = reinterpret_cast<const double4 *>(sW)[i + WARPS];
-            acc += fma(wa.x, la, -fma(wa.y, ta + SNAQ_K_LOG3, wa.w));
-            acc += fma(wb.x, lb, -fma(wb.y, tb + SNAQ_K_LOG3, wb.w));
-        }
-        if (i < nqc) {
-            const double t = pair_sum(i);
-            const double y = snaq_exp(-t, M);
-            const double major = fma(SNAQ_K_M23, y, 1.0);
-            const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
-            acc += fma(w4.x, snaq_log_pos(major, M), -fma(w4.y, t + SNAQ_K_LOG3, w4.w));
+        for (int i = warp; i < nqc; i += WARPS) {
+            const uint32_t c0 = soff[i];
+            const uint32_t len = soff[i + 1] - c0;
+            const uint2 w = sprog[c0];
+            const uint2 w2 = (len == 2u) ? sprog[c0 + 1] : make_uint2(0xfffffffeu, len);
+            if (len > 2u || w.x != mw.x || w.y != mw.y || w2.x != mw2.x || w2.y != mw2.y) {
+                if (len == 1u) m_t = snaq_clamp10((XLO(w.x) - XHI(w.x)) + (XLO(w.y) - XHI(w.y)));
+                else m_t = pair_sum(i);
+                const double y = snaq_exp(-m_t, M);
+                m_l = snaq_log_pos(fma(SNAQ_K_M23, y, 1.0), M);
+                mw = w; mw2 = w2;
+                if (len > 2u) mw = make_uint2(0xffffffffu, 0xffffffffu);          // longer programs are not compared: never reused
+            }
+            const double4 wa = reinterpret_cast<const double4 *>(sW)[i];
+            acc += fma(wa.x, m_l, -fma(wa.y, m_t + SNAQ_K_LOG3, wa.w));
         }
     } else if (cls == 1) {
         // class B: tree-like with type-2 / type-4 terms (same arithmetic as snaq_tree_terms_t1).  The class is sorted by
@@ -754,8 +753,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
         mbar_wait(&bar[1 + sidx], (unsigned)(it >> 1) & 1u);
         __syncthreads();
         if (cls == 0) {
-            // class A: t1 = min(10, sum of signed pairs); two quartets per iteration (independent chains, the
-            // polynomial constants are fetched once for both)
+            // class A: t1 = min(10, sum of signed pairs).  The class is sorted by program, and a quartet's expected CFs depend
+            // on its program only: while the program repeats (quartets that differ in taxa of the same clades) t1, exp and log
+            // are reused and the quartet costs its two weight FMAs (the program is warp-uniform: the test does not diverge).
             auto pair_sum = [&](int i) {
                 uint32_t c = SO(i);
                 const uint32_t o1 = SO(i + 1);
@@ -769,28 +769,25 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
                 }
                 return snaq_clamp10(t0 + t1);
             };
-            const bool one_chunk = implicit && mult == 1u;   // every program of this chunk is one 8-byte chunk: sprog[i]
-            auto one_sum = [&](int i) {
-                const uint2 w = sprog[i];
-                return snaq_clamp10((XLO(w.x) - XHI(w.x)) + (XLO(w.y) - XHI(w.y)));
-            };
-            int i = warp;
+        (void)mult;
+            uint2 mw = make_uint2(0xffffffffu, 0xffffffffu), mw2 = mw;
+            double m_t = 0.0, m_l = 0.0;
 #pragma unroll 1
-            for (; i + WARPS < nqc; i += 2 * WARPS) {
-                const double ta = one_chunk ? one_sum(i) : pair_sum(i), tb = one_chunk ? one_sum(i + WARPS) : pair_sum(i + WARPS);
-                const double ya = snaq_exp(-ta, M), yb = snaq_exp(-tb, M);
-                const double ma = fma(SNAQ_K_M23, ya, 1.0), mb = fma(SNAQ_K_M23, yb, 1.0);
-                const double la = snaq_log_pos(ma, M), lb = snaq_log_pos(mb, M);
-                const double4 wa = reinterpret_cast<const double4 *>(sW)[i], wb = reinterpret_cast<const double4 *>(sW)[i + WARPS];
-                acc += fma(wa.x, la, -fma(wa.y, ta + SNAQ_K_LOG3, wa.w));
-                acc += fma(wb.x, lb, -fma(wb.y, tb + SNAQ_K_LOG3, wb.w));
-            }
-            if (i < nqc) {
-                const double t = pair_sum(i);
-                const double y = snaq_exp(-t, M);
-                const double major = fma(SNAQ_K_M23, y, 1.0);
-                const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
-                acc += fma(w4.x, snaq_log_pos(major, M), -fma(w4.y, t + SNAQ_K_LOG3, w4.w));
+            for (int i = warp; i < nqc; i += WARPS) {
+                const uint32_t c0 = SO(i);
+                const uint32_t len = SO(i + 1) - c0;
+                const uint2 w = sprog[c0];
+                const uint2 w2 = (len == 2u) ? sprog[c0 + 1] : make_uint2(0xfffffffeu, len);
+                if (len > 2u || w.x != mw.x || w.y != mw.y || w2.x != mw2.x || w2.y != mw2.y) {
+                    if (len == 1u) m_t = snaq_clamp10((XLO(w.x) - XHI(w.x)) + (XLO(w.y) - XHI(w.y)));
+                    else m_t = pair_sum(i);
+                    const double y = snaq_exp(-m_t, M);
+                    m_l = snaq_log_pos(fma(SNAQ_K_M23, y, 1.0), M);
+                    mw = w; mw2 = w2;
+                    if (len > 2u) mw = make_uint2(0xffffffffu, 0xffffffffu);          // longer programs are not compared: never reused
+                }
+                const double4 wa = reinterpret_cast<const double4 *>(sW)[i];
+                acc += fma(wa.x, m_l, -fma(wa.y, m_t + SNAQ_K_LOG3, wa.w));
             }
         } else if (cls == 1) {
             // class B: tree-like with type-2 / type-4 terms (same arithmetic as snaq_tree_terms_t1); terms are reused while
