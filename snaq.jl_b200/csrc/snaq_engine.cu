@@ -484,6 +484,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
     const char *xb = reinterpret_cast<const char *>(xs);
 #define XLO(w) (*reinterpret_cast<const double *>(xb + __byte_perm((w), lane8, 0x5104)))
 #define XHI(w) (*reinterpret_cast<const double *>(xb + __byte_perm((w), lane8, 0x5324)))
+    // a warp takes a CONTIGUOUS share of the chunk: neighbours in the sorted table share programs / terms
+    const int wper = (nqc + WARPS - 1) / WARPS, wbeg = min(warp * wper, nqc), wend = min(wbeg + wper, nqc);
     if (cls == 0) {
         // class A: t1 = min(10, sum of signed pairs).  The class is sorted by program, and a quartet's expected CFs depend
         // on its program only: while the program repeats (quartets that differ in taxa of the same clades) t1, exp and log
@@ -505,7 +507,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
         uint2 mw = make_uint2(0xffffffffu, 0xffffffffu), mw2 = mw;
         double m_t = 0.0, m_l = 0.0;
 #pragma unroll 1
-        for (int i = warp; i < nqc; i += WARPS) {
+        for (int i = wbeg; i < wend; i++) {
             const uint32_t c0 = soff[i];
             const uint32_t len = soff[i + 1] - c0;
             const uint2 w = sprog[c0];
@@ -528,7 +530,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
         unsigned m4_k0 = 0xffffffffu, m4_k1 = 0xffffffffu, m2_k0 = 0xffffffffu, m2_k1 = 0xffffffffu;
         double m4_l4 = 0.0, m2_v = 0.0;
 #pragma unroll 1
-        for (int i = warp; i < nqc; i += WARPS) {
+        for (int i = wbeg; i < wend; i++) {
             const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + soff[i]);
             const unsigned cw = pc[0];
             const int npairs = (int)(cw & 255u), nterms = (int)(cw >> 8);
@@ -601,7 +603,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
         double m5_l0 = 0.0, m5_l1 = 0.0, m5_l2 = 0.0;
         const uint8_t *hd = qhdr + q0;
 #pragma unroll 1
-        for (int i = warp; i < nqc; i += WARPS) {
+        for (int i = wbeg; i < wend; i++) {
             const uint2 w = sprog[soff[i]];
             const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
             if (SNAQ_HDR_KIND(hd[i]) == SNAQ_KIND_T5) {
@@ -752,6 +754,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
         const int64_t q0 = m.q0;
         mbar_wait(&bar[1 + sidx], (unsigned)(it >> 1) & 1u);
         __syncthreads();
+        // a warp takes a CONTIGUOUS share of the chunk: neighbours in the sorted table share programs / terms
+        const int wper = (nqc + WARPS - 1) / WARPS, wbeg = min(warp * wper, nqc), wend = min(wbeg + wper, nqc);
         if (cls == 0) {
             // class A: t1 = min(10, sum of signed pairs).  The class is sorted by program, and a quartet's expected CFs depend
             // on its program only: while the program repeats (quartets that differ in taxa of the same clades) t1, exp and log
@@ -773,7 +777,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
             uint2 mw = make_uint2(0xffffffffu, 0xffffffffu), mw2 = mw;
             double m_t = 0.0, m_l = 0.0;
 #pragma unroll 1
-            for (int i = warp; i < nqc; i += WARPS) {
+            for (int i = wbeg; i < wend; i++) {
                 const uint32_t c0 = SO(i);
                 const uint32_t len = SO(i + 1) - c0;
                 const uint2 w = sprog[c0];
@@ -795,7 +799,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
             unsigned m4_k0 = 0xffffffffu, m4_k1 = 0xffffffffu, m2_k0 = 0xffffffffu, m2_k1 = 0xffffffffu;
             double m4_l4 = 0.0, m2_v = 0.0;
 #pragma unroll 1
-            for (int i = warp; i < nqc; i += WARPS) {
+            for (int i = wbeg; i < wend; i++) {
                 const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + SO(i));
                 const unsigned cw = pc[0];
                 const int npairs = (int)(cw & 255u), nterms = (int)(cw >> 8);
@@ -868,7 +872,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
             double m5_l0 = 0.0, m5_l1 = 0.0, m5_l2 = 0.0;
             const uint8_t *hd = qhdr + q0;
 #pragma unroll 1
-            for (int i = warp; i < nqc; i += WARPS) {
+            for (int i = wbeg; i < wend; i++) {
                 const uint2 w = sprog[SO(i)];
                 const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
                 if (SNAQ_HDR_KIND(hd[i]) == SNAQ_KIND_T5) {
