@@ -1729,11 +1729,13 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
         cr.nA1 = tb.nA1; cr.nA = tb.nA; cr.nB = tb.nB; cr.nC = tb.nC;
         cr.nA2 = tb.nA2; cr.a2base = (uint32_t)(tb.nA1 + (tb.nA1 & 1));
         if (ngroups > 65535) { ctx->err = "batch too large for one launch"; return SNAQ_EINVAL; }
-        // Big xf tiles (>= ~100 KB: 150+ taxa) leave room for one block per SM, and reloading the tile for every chunk of
-        // quartets dominates: there the persistent variant keeps the tile resident (measured at 200 taxa, P = 64:
-        // 31.2 -> 16.9 ms).  With small tiles the one-block-per-chunk kernel is faster (more, independent blocks per SM).
+        // xf tiles of 48 KB and more (~100 taxa and up): reloading the tile for every chunk of quartets is most of the
+        // L2 traffic, and from ~100 KB only one block fits per SM: the persistent variant keeps the tile resident
+        // (200 taxa, P = 64: 31.2 -> 16.9 ms; 100 taxa, P = 256: 339 -> 383 G evals/s).  With small tiles the
+        // one-block-per-chunk kernel is faster (config 2: 329 vs 254 G evals/s): more, independent blocks per SM.
         const bool big_tile = lanesp_smem_layout(H.n_full, 64, 8, ctx->maxlen).total > 110 * 1024;
-        if (ctx->lanes_persistent == 1 ? big_tile : ctx->lanes_persistent > 1) {
+        const bool mid_tile = (size_t)H.n_full * 256 >= 48 * 1024;      // ~100 taxa: the tile reload is most of the L2 traffic
+        if (ctx->lanes_persistent == 1 ? (big_tile || mid_tile) : ctx->lanes_persistent > 1) {
             // persistent blocks: the xf tile stays in shared memory, chunks stream through two TMA stages; 16 warps per block
             int warps = big_tile ? 16 : ctx->lanes_warps, chunk = 256;
             while (chunk > 32 && lanesp_smem_layout(H.n_full, chunk, warps, ctx->maxlen).total > 200 * 1024) chunk >>= 1;
