@@ -1217,7 +1217,6 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
         if (WANT_H) { hb_lo[row] = 0u; hb_hi[row] = 0u; }
     }
     __syncthreads();
-    const unsigned gtid = blockIdx.x * BLOCK + tid, nthr = gridDim.x * BLOCK;
     const unsigned gwarp = blockIdx.x * (BLOCK / 32) + warp, nwarps = gridDim.x * (BLOCK / 32);
     const unsigned nul = (unsigned)T.n_xe;
     double acc = 0.0;
@@ -1247,45 +1246,91 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
         if (WANT_H) *hq = in ? __double2ll_rn(r / major * QG_SCALE) : 0ll;
         return fma(w.x, snaq_log_pos(major, M), -w.y * (t1 + SNAQ_K_LOG3));
     };
+    // A warp holds 32 CONSECUTIVE entries of the table, and class A is sorted by program: most of the time the 32 lanes
+    // read the SAME slots.  wadd: when a slot is warp-uniform the 32 values are summed with integer warp reductions (three
+    // 21-bit limbs, REDUX) and lane 0 issues ONE atomic; otherwise every lane adds its own.
+    auto warp_sum = [&](long long q) {
+        const unsigned l0 = (unsigned)(q & 0x1FFFFFll), l1 = (unsigned)((q >> 21) & 0x1FFFFFll);
+        const int l2 = (int)(q >> 42);
+        const unsigned s0 = __reduce_add_sync(0xffffffffu, l0), s1 = __reduce_add_sync(0xffffffffu, l1);
+        const int s2 = __reduce_add_sync(0xffffffffu, l2);
+        return (long long)s0 + ((long long)s1 << 21) + ((long long)s2 << 42);
+    };
+    auto wadd = [&](unsigned slot, long long q, long long hq) {          // called by all 32 lanes
+        const unsigned s0 = __shfl_sync(0xffffffffu, slot, 0);
+        if (__all_sync(0xffffffffu, slot == s0)) {
+            if (s0 == nul) return;
+            const long long tq = warp_sum(q);
+            long long th = 0;
+            if (WANT_H) th = warp_sum(hq);
+            if (lane == 0) { if (tq != 0) addq(s0, tq); if (WANT_H && th != 0) addhq(s0, th); }
+        } else {
+            if (q != 0) addq(slot, q);
+            if (WANT_H && hq != 0) addhq(slot, hq);
+        }
+    };
     // ---- region A1: one chunk (two signed pairs) ---------------------------------------------------------
 #pragma unroll 1
-    for (unsigned i0 = gtid; i0 < nA1; i0 += 2u * nthr) {
+    for (unsigned ib = gwarp * 32u; ib < nA1; ib += 2u * nwarps * 32u) {
         double2 w[2];
         uint2 c[2];
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            const unsigned i = i0 + (unsigned)k * nthr;
+            const unsigned i = ib + (unsigned)k * nwarps * 32u + lane;
             const bool ok = i < nA1;
             w[k] = ok ? __ldg(WA + i) : make_double2(0.0, 0.0);
             c[k] = ok ? __ldg(prog2 + i) : make_uint2(nul * 0x10001u, nul * 0x10001u);
         }
 #pragma unroll
         for (int k = 0; k < 2; k++) {
+            if (ib + (unsigned)k * nwarps * 32u >= nA1) break;           // warp-uniform
             const unsigned a = c[k].x & 0xffffu, b = c[k].x >> 16, cc = c[k].y & 0xffffu, d = c[k].y >> 16;
             long long gq, hq = 0;
             acc += tree((xs[a] - xs[b]) + (xs[cc] - xs[d]), w[k], &gq, &hq);
-            if (gq != 0) { addq(a, gq); addq(b, -gq); addq(cc, gq); addq(d, -gq); }
-            if (WANT_H && hq != 0) { addhq(a, hq); addhq(b, -hq); addhq(cc, hq); addhq(d, -hq); }
+            // the whole program is usually the same in all 32 lanes (the class is sorted by program): one reduction, then
+            // lane 0 adds the warp's total to the four slots
+            const unsigned px = __shfl_sync(0xffffffffu, c[k].x, 0), py = __shfl_sync(0xffffffffu, c[k].y, 0);
+            if (__all_sync(0xffffffffu, c[k].x == px && c[k].y == py)) {
+                const long long tq = warp_sum(gq);
+                long long th = 0;
+                if (WANT_H) th = warp_sum(hq);
+                if (lane == 0) {
+                    if (tq != 0) { addq(a, tq); addq(b, -tq); addq(cc, tq); addq(d, -tq); }
+                    if (WANT_H && th != 0) { addhq(a, th); addhq(b, -th); addhq(cc, th); addhq(d, -th); }
+                }
+            } else { wadd(a, gq, hq); wadd(b, -gq, -hq); wadd(cc, gq, hq); wadd(d, -gq, -hq); }
         }
     }
     // ---- region A2: two chunks -----------------------------------------------------------------------------
 #pragma unroll 1
-    for (unsigned j = gtid; j < nA2; j += nthr) {
-        const double2 w = __ldg(WA + nA1 + j);
-        const uint4 c = __ldg(reinterpret_cast<const uint4 *>(prog2 + a2base) + j);
+    for (unsigned jb = gwarp * 32u; jb < nA2; jb += nwarps * 32u) {
+        const unsigned j = jb + lane;
+        const bool ok = j < nA2;
+        const double2 w = ok ? __ldg(WA + nA1 + j) : make_double2(0.0, 0.0);
+        const unsigned np2 = nul * 0x10001u;
+        const uint4 c = ok ? __ldg(reinterpret_cast<const uint4 *>(prog2 + a2base) + j) : make_uint4(np2, np2, np2, np2);
         const unsigned s[8] = {c.x & 0xffffu, c.x >> 16, c.y & 0xffffu, c.y >> 16, c.z & 0xffffu, c.z >> 16, c.w & 0xffffu, c.w >> 16};
         double ta = xs[s[0]] - xs[s[1]], tb = xs[s[2]] - xs[s[3]];
         ta += xs[s[4]] - xs[s[5]];
         tb += xs[s[6]] - xs[s[7]];
         long long gq, hq = 0;
         acc += tree(ta + tb, w, &gq, &hq);
-        if (gq != 0) {
+        const unsigned p0 = __shfl_sync(0xffffffffu, c.x, 0), p1 = __shfl_sync(0xffffffffu, c.y, 0);
+        const unsigned p2 = __shfl_sync(0xffffffffu, c.z, 0), p3 = __shfl_sync(0xffffffffu, c.w, 0);
+        if (__all_sync(0xffffffffu, c.x == p0 && c.y == p1 && c.z == p2 && c.w == p3)) {
+            const long long tq = warp_sum(gq);
+            long long th = 0;
+            if (WANT_H) th = warp_sum(hq);
+            if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < 8; k += 2) { addq(s[k], gq); addq(s[k + 1], -gq); }
-        }
-        if (WANT_H && hq != 0) {
+                for (int k = 0; k < 8; k += 2) {
+                    if (tq != 0) { addq(s[k], tq); addq(s[k + 1], -tq); }
+                    if (WANT_H && th != 0) { addhq(s[k], th); addhq(s[k + 1], -th); }
+                }
+            }
+        } else {
 #pragma unroll
-            for (int k = 0; k < 8; k += 2) { addhq(s[k], hq); addhq(s[k + 1], -hq); }
+            for (int k = 0; k < 8; k += 2) { wadd(s[k], gq, hq); wadd(s[k + 1], -gq, -hq); }
         }
     }
     // ---- region G: everything else through the generic evaluator ------------------------------------------
