@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_
             if (pos + 3 < 24 && pos + 3 < w.n) key = (head[pos] & 3u) == SNAQ_T2 ? term_hash(head[pos], head[pos + 1], head[pos + 2], 0u)
                                                    : term_hash(head[pos] & ~4u, head[pos + 1], head[pos + 2], head[pos + 3]);
         }
-        if (dedup || c <= 2u) {
+        const uint32_t term_key = key;
+        if (dedup || c <= 3u) {
             // class A (always) and program deduplication (every class): the key is a hash of the WHOLE program, so that
             // identical programs become neighbours (programs longer than the captured head hash only its first 24 words:
             // they may be split into several runs)
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_
             const int m = w.n < 24 ? w.n : 24;
             for (int i = 0; i < m; i++) h = (h ^ head[i]) * 0x85EBCA77u;
             key = (h ^ (h >> 15)) & 0x0FFFFFFFu;
+            if (!dedup && c == 3u) key = ((term_key & 0x3FFFu) << 14) | (key & 0x3FFFu);     // class B: by term, then by program
         }
         len4[q] = n;
         cls[q] = (c << 28) | key;
@@ -529,9 +531,24 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
         // (the program is warp-uniform: the test does not diverge).
         unsigned m4_k0 = 0xffffffffu, m4_k1 = 0xffffffffu, m2_k0 = 0xffffffffu, m2_k1 = 0xffffffffu;
         double m4_l4 = 0.0, m2_v = 0.0;
+        unsigned mB_len = 0xffffffffu;
+        uint2 mB_w0 = make_uint2(0u, 0u), mB_w1 = mB_w0, mB_w2 = mB_w0;
+        double mB_t = 0.0, mB_lm = 0.0;
 #pragma unroll 1
         for (int i = wbeg; i < wend; i++) {
-            const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + soff[i]);
+            // the WHOLE program is often the previous one (the class is sorted by term, then by program): reuse t and log(major)
+            const uint32_t bc0 = soff[i], blen = soff[i + 1] - bc0;
+            const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
+            bool same = (blen == mB_len);
+            if (same) {
+                const uint2 a0 = sprog[bc0], a1 = blen > 1u ? sprog[bc0 + 1] : mB_w1, a2 = blen > 2u ? sprog[bc0 + 2] : mB_w2;
+                same = a0.x == mB_w0.x && a0.y == mB_w0.y && a1.x == mB_w1.x && a1.y == mB_w1.y && a2.x == mB_w2.x && a2.y == mB_w2.y;
+            }
+            if (same) {
+                acc += fma(w4.x, (w4.x != 0.0) ? mB_lm : 0.0, -fma(w4.y, mB_t + SNAQ_K_LOG3, w4.w));
+                continue;
+            }
+            const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + bc0);
             const unsigned cw = pc[0];
             const int npairs = (int)(cw & 255u), nterms = (int)(cw >> 8);
             double R = 0.0;
@@ -590,10 +607,16 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
             if (t < SNAQ_MINLEN) st |= SNAQ_S_NEGLEN;
             const double y = snaq_exp(-t, M);
             const double major = fma(SNAQ_K_M23, y, 1.0);
-            const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
             if (major < 0.0) st |= SNAQ_S_NEGLEN;
-            const double lm = (w4.x != 0.0) ? snaq_log(major, M) : 0.0;      // obs == 0 contributes 0 (src/pseudolik.jl:1398)
-            acc += fma(w4.x, lm, -fma(w4.y, t + SNAQ_K_LOG3, w4.w));
+            mB_lm = snaq_log(major, M);
+            mB_t = t;
+            if (blen <= 3u) {                                            // longer programs are not remembered
+                mB_len = blen;
+                mB_w0 = sprog[bc0];
+                mB_w1 = blen > 1u ? sprog[bc0 + 1] : make_uint2(0u, 0u);
+                mB_w2 = blen > 2u ? sprog[bc0 + 2] : make_uint2(0u, 0u);
+            } else mB_len = 0xffffffffu;
+            acc += fma(w4.x, (w4.x != 0.0) ? mB_lm : 0.0, -fma(w4.y, t + SNAQ_K_LOG3, w4.w));      // obs == 0 contributes 0 (src/pseudolik.jl:1398)
         }
     } else {
         // class C: 4-cycle quartets.  T5: [gslot, C_a, C_m, C_b] in one chunk; all three CFs are positive.  Sorted by these
@@ -798,9 +821,24 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
             // they repeat (see k_eval_lanes)
             unsigned m4_k0 = 0xffffffffu, m4_k1 = 0xffffffffu, m2_k0 = 0xffffffffu, m2_k1 = 0xffffffffu;
             double m4_l4 = 0.0, m2_v = 0.0;
+            unsigned mB_len = 0xffffffffu;
+            uint2 mB_w0 = make_uint2(0u, 0u), mB_w1 = mB_w0, mB_w2 = mB_w0;
+            double mB_t = 0.0, mB_lm = 0.0;
 #pragma unroll 1
             for (int i = wbeg; i < wend; i++) {
-                const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + SO(i));
+                // the WHOLE program is often the previous one (the class is sorted by term, then by program): reuse t and log(major)
+                const uint32_t bc0 = SO(i), blen = SO(i + 1) - bc0;
+                const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
+                bool same = (blen == mB_len);
+                if (same) {
+                    const uint2 a0 = sprog[bc0], a1 = blen > 1u ? sprog[bc0 + 1] : mB_w1, a2 = blen > 2u ? sprog[bc0 + 2] : mB_w2;
+                    same = a0.x == mB_w0.x && a0.y == mB_w0.y && a1.x == mB_w1.x && a1.y == mB_w1.y && a2.x == mB_w2.x && a2.y == mB_w2.y;
+                }
+                if (same) {
+                    acc += fma(w4.x, (w4.x != 0.0) ? mB_lm : 0.0, -fma(w4.y, mB_t + SNAQ_K_LOG3, w4.w));
+                    continue;
+                }
+                const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + bc0);
                 const unsigned cw = pc[0];
                 const int npairs = (int)(cw & 255u), nterms = (int)(cw >> 8);
                 double R = 0.0;
@@ -859,10 +897,16 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
                 if (t < SNAQ_MINLEN) st |= SNAQ_S_NEGLEN;
                 const double y = snaq_exp(-t, M);
                 const double major = fma(SNAQ_K_M23, y, 1.0);
-                const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
                 if (major < 0.0) st |= SNAQ_S_NEGLEN;
-                const double lm = (w4.x != 0.0) ? snaq_log(major, M) : 0.0;      // obs == 0 contributes 0 (src/pseudolik.jl:1398)
-                acc += fma(w4.x, lm, -fma(w4.y, t + SNAQ_K_LOG3, w4.w));
+                mB_lm = snaq_log(major, M);
+                mB_t = t;
+                if (blen <= 3u) {                                            // longer programs are not remembered
+                    mB_len = blen;
+                    mB_w0 = sprog[bc0];
+                    mB_w1 = blen > 1u ? sprog[bc0 + 1] : make_uint2(0u, 0u);
+                    mB_w2 = blen > 2u ? sprog[bc0 + 2] : make_uint2(0u, 0u);
+                } else mB_len = 0xffffffffu;
+                acc += fma(w4.x, (w4.x != 0.0) ? mB_lm : 0.0, -fma(w4.y, t + SNAQ_K_LOG3, w4.w));      // obs == 0 contributes 0 (src/pseudolik.jl:1398)
             }
         } else {
             // class C: 4-cycle quartets.  T5: [gslot, C_a, C_m, C_b] in one chunk; all three CFs are positive.  Sorted by these
