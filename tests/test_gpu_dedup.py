@@ -1,6 +1,8 @@
 """GPU tier: program deduplication (SNAQ_OPT_DEDUP, include/snaq_b200.h).  Quartets whose evaluation programs are identical
 have the same expected CFs, and the pseudo-deviance is linear in the weights 100*obsCF, so one evaluation per distinct
 program with the summed weights gives the same value.  Checked against the plain path and the oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -38,7 +40,9 @@ def test_dedup_matches_the_plain_path_and_the_oracle(oracle, seed):
     n, h = 10 + 3 * seed, seed % 5
     plain, dd, flat, qt, obs, x0, upper = pair(n, h, 40 + seed)
     nu = dd.counters()["distinct_programs"]
-    assert 0 < nu < len(qt) and plain.counters()["distinct_programs"] == 0
+    assert 0 < nu < len(qt)
+    if not os.environ.get("SNAQ_DEDUP"):                        # the environment variable switches every context
+        assert plain.counters()["distinct_programs"] == 0
     X = simulate.parameter_batch(x0, upper, 70, seed)
     X[3] = np.where(upper > 1.5, 10.0, 0.5)                      # every length at its cap
     want = oracle.evaluate(flat, qt, obs, X)
