@@ -5,21 +5,27 @@
  *   taxa   [nq][4] u16      quartet taxon ids                      (set_data)
  *   obs    [nq][3] f64      observed CFs                           (set_data / set_obscf)
  *   sampled[nq]    u8       q.sampled                              (set_sampled)
- *   off    [nq+1]  u32  \   CSR table of quartet programs: the flattened replacement of
- *   prog   [words] u16  /   the reference's per-quartet QuartetNetwork objects (set_network)
- *   W      [nq][4] f64      100*obs in program order + sum 100*obs*log(obs)
+ *   off    [nq+1]  u32  \   CSR table of quartet programs, sorted by (class, program / term hash): the flattened
+ *   prog   [words] u16  /   replacement of the reference's per-quartet QuartetNetwork objects (set_network)
+ *   W      [nq][4] f64      100*obs in program order + sum 100*obs*log(obs);  WA [nA12][2]: the pairs of the short
+ *                           additive programs
+ *   (SNAQ_OPT_DEDUP) off_u / prog_u / W_u: the same table with one entry per DISTINCT program, weights summed
  *
  * Kernels:
- *   k_build_count / k_build_emit : extractQuartet! for every quartet (thread per quartet)
- *   k_weights                    : obs -> W
- *   k_eval_lanes                 : the hot kernel.  lane = candidate parameter vector, a warp walks
- *                                  quartets; the quartet program is warp-uniform so there is no
- *                                  divergence, x is staged transposed in shared memory so the
- *                                  per-slot gathers are conflict-free, sums stay thread-private
- *                                  until one fixed-order block reduction (deterministic).
- *   k_eval_direct                : thread per quartet for small batches (P < 16; HBM-bound at P=1)
- *                                  and for the per-quartet read-back (expCF, logPseudoLik, deltaCF)
- *   k_reduce_partials            : second, fixed-order pass over the per-block partial sums
+ *   k_build_count / k_build_emit : extractQuartet! for every quartet (thread per quartet), sort keys
+ *   k_dedup_* / k_weights_u      : runs of identical programs -> compressed table, compensated weight sums
+ *   k_weights                    : obs -> W, WA, class-A constant
+ *   k_eval_lanes / k_eval_lanes_p: the batched kernels.  lane = candidate parameter vector, a warp walks a contiguous
+ *                                  share of a chunk of quartets; the quartet program is warp-uniform so there is no
+ *                                  divergence, x is staged transposed in shared memory so the per-slot gathers are
+ *                                  conflict-free, t1/exp/log and hybridisation terms are reused while the (sorted)
+ *                                  programs repeat, sums stay thread-private until a fixed-order block reduction.
+ *                                  _p: persistent blocks, xf tile resident, chunks through two TMA stages (big tiles)
+ *   k_eval_direct                : thread per quartet for small batches (P < 16; HBM-bound at P=1): warp-private TMA
+ *                                  rings; also the per-quartet read-back (expCF, logPseudoLik, deltaCF)
+ *   k_eval_grad                  : objective + analytic gradient (+ curvature diagonal) in one pass, fixed-point bins
+ *   k_reduce_partials*           : second, fixed-order pass over per-block partial sums
+ *   k_update_bl, k_describe, k_hasedge : updateBL! table, parity descriptors
  *
  * Tensor cores are not used: the path is a few exp/log per (quartet, candidate), not a contraction.
  */
