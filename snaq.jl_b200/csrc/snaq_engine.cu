@@ -1549,7 +1549,7 @@ struct snaq_ctx {
     const double *xarg_base = nullptr;    // the (never dereferenced) device alias eval_device indexes for that batch
     uint32_t *status_out = nullptr;       // page-locked word the last block mirrors the status into (else nullptr)
     cudaStream_t copy_stream = nullptr;   // snaq_eval: host->device copies of the next chunk while the current one is evaluated
-    cudaEvent_t copy_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t copy_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
     // data
     int ntaxa = 0;
@@ -1965,7 +1965,7 @@ int snaq_destroy(snaq_ctx *ctx) {
     cudaFree(ctx->d_perm); cudaFree(ctx->d_qhdr); cudaFree(ctx->d_len4); cudaFree(ctx->d_iota); cudaFree(ctx->d_cls);
     cudaFree(ctx->d_cls_sorted);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
-    if (ctx->copy_stream) { for (int k = 0; k < 4; k++) cudaEventDestroy(ctx->copy_ev[k]); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->copy_stream) { for (int k = 0; k < 8; k++) cudaEventDestroy(ctx->copy_ev[k]); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SNAQ_OK;
@@ -2269,26 +2269,24 @@ int snaq_eval(snaq_ctx *ctx, int32_t P, int32_t nparams, const double *X, double
     cudaPointerAttributes attr;
     const bool user_pinned = cudaPointerGetAttributes(&attr, X) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    const double *src = X;
-    if (!user_pinned) { std::memcpy(ctx->h_pin, X, sizeof(double) * (size_t)P * nparams); src = ctx->h_pin; }
-    // large batches: the copy of chunk k+1 (copy stream) overlaps the evaluation of chunk k (compute stream)
-    const int nchunk = (P >= 2048 && nparams > 0) ? ctx->eval_chunks : 1;
+    const double *src = user_pinned ? X : ctx->h_pin;
+    // large batches: the copy of chunk k+1 (copy stream) overlaps the evaluation of chunk k (compute stream); a pageable
+    // caller buffer is staged chunk by chunk, so that the host memcpy of chunk k+1 also overlaps the device work of chunk k
+    const int nchunk = (P >= 2048 && nparams > 0) ? (user_pinned ? ctx->eval_chunks : 2 * ctx->eval_chunks) : 1;
+    if (nchunk == 1 && !user_pinned) std::memcpy(ctx->h_pin, X, sizeof(double) * (size_t)P * nparams);
     if (nchunk > 1) {
         if (!ctx->copy_stream) {
             CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-            for (int k = 0; k < 4; k++) CK(cudaEventCreateWithFlags(&ctx->copy_ev[k], cudaEventDisableTiming));
+            for (int k = 0; k < 8; k++) CK(cudaEventCreateWithFlags(&ctx->copy_ev[k], cudaEventDisableTiming));
         }
         const int Pc = ((P + nchunk - 1) / nchunk + 31) & ~31;
         int k = 0;
         for (int p0 = 0; p0 < P; p0 += Pc, k++) {
             const int pn = std::min(Pc, P - p0);
+            if (!user_pinned) std::memcpy(ctx->h_pin + (size_t)p0 * nparams, X + (size_t)p0 * nparams, sizeof(double) * (size_t)pn * nparams);
             CK(cudaMemcpyAsync(ctx->d_X + (size_t)p0 * nparams, src + (size_t)p0 * nparams, sizeof(double) * (size_t)pn * nparams,
                                cudaMemcpyHostToDevice, ctx->copy_stream));
             CK(cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream));
-        }
-        k = 0;
-        for (int p0 = 0; p0 < P; p0 += Pc, k++) {
-            const int pn = std::min(Pc, P - p0);
             CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0));
             rc = eval_device(ctx, pn, ctx->d_X + (size_t)p0 * nparams, ctx->d_out + p0, ctx->stream, nullptr, nullptr, nullptr);
             if (rc) return rc;
