@@ -511,11 +511,32 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
             }
             return snaq_clamp10(t0 + t1);
         };
-    (void)cr;
         uint2 mw = make_uint2(0xffffffffu, 0xffffffffu), mw2 = mw;
         double m_t = 0.0, m_l = 0.0;
+        int i = wbeg;
+        if (q0 + nqc <= cr.nA1) {
+            // every program of this chunk is ONE chunk at sprog[i]: no offsets, two quartets per iteration (the loads of the
+            // second do not wait for the first)
+            auto one = [&](const uint2 &w, const double4 &wa) {
+                if (w.x != mw.x || w.y != mw.y) {
+                    m_t = snaq_clamp10((XLO(w.x) - XHI(w.x)) + (XLO(w.y) - XHI(w.y)));
+                    m_l = snaq_log_pos(fma(SNAQ_K_M23, snaq_exp(-m_t, M), 1.0), M);
+                    mw = w;
+                }
+                acc += fma(wa.x, m_l, -fma(wa.y, m_t + SNAQ_K_LOG3, wa.w));
+            };
 #pragma unroll 1
-        for (int i = wbeg; i < wend; i++) {
+            for (; i + 1 < wend; i += 2) {
+                const uint2 wA = sprog[i], wB = sprog[i + 1];
+                const double4 waA = reinterpret_cast<const double4 *>(sW)[i], waB = reinterpret_cast<const double4 *>(sW)[i + 1];
+                one(wA, waA);
+                one(wB, waB);
+            }
+            if (i < wend) { one(sprog[i], reinterpret_cast<const double4 *>(sW)[i]); i = wend; }
+            mw2 = make_uint2(0xfffffffeu, 1u);                     // consistent with the general loop below (not entered)
+        }
+#pragma unroll 1
+        for (; i < wend; i++) {
             const uint32_t c0 = soff[i];
             const uint32_t len = soff[i + 1] - c0;
             const uint2 w = sprog[c0];
@@ -802,11 +823,32 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
                 }
                 return snaq_clamp10(t0 + t1);
             };
-        (void)mult;
             uint2 mw = make_uint2(0xffffffffu, 0xffffffffu), mw2 = mw;
             double m_t = 0.0, m_l = 0.0;
+            int i = wbeg;
+            if (implicit && mult == 1u) {
+                // every program of this chunk is ONE chunk at sprog[i]: no offsets, two quartets per iteration (the loads of the
+                // second do not wait for the first)
+                auto one = [&](const uint2 &w, const double4 &wa) {
+                    if (w.x != mw.x || w.y != mw.y) {
+                        m_t = snaq_clamp10((XLO(w.x) - XHI(w.x)) + (XLO(w.y) - XHI(w.y)));
+                        m_l = snaq_log_pos(fma(SNAQ_K_M23, snaq_exp(-m_t, M), 1.0), M);
+                        mw = w;
+                    }
+                    acc += fma(wa.x, m_l, -fma(wa.y, m_t + SNAQ_K_LOG3, wa.w));
+                };
 #pragma unroll 1
-            for (int i = wbeg; i < wend; i++) {
+                for (; i + 1 < wend; i += 2) {
+                    const uint2 wA = sprog[i], wB = sprog[i + 1];
+                    const double4 waA = reinterpret_cast<const double4 *>(sW)[i], waB = reinterpret_cast<const double4 *>(sW)[i + 1];
+                    one(wA, waA);
+                    one(wB, waB);
+                }
+                if (i < wend) { one(sprog[i], reinterpret_cast<const double4 *>(sW)[i]); i = wend; }
+                mw2 = make_uint2(0xfffffffeu, 1u);                     // consistent with the general loop below (not entered)
+            }
+#pragma unroll 1
+            for (; i < wend; i++) {
                 const uint32_t c0 = SO(i);
                 const uint32_t len = SO(i + 1) - c0;
                 const uint2 w = sprog[c0];
