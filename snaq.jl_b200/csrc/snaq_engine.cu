@@ -534,6 +534,25 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
             }
             if (i < wend) { one(sprog[i], reinterpret_cast<const double4 *>(sW)[i]); i = wend; }
             mw2 = make_uint2(0xfffffffeu, 1u);                     // consistent with the general loop below (not entered)
+        } else if (q0 >= cr.nA1 && q0 + nqc <= cr.nA1 + cr.nA2) {
+            // every program of this chunk is TWO chunks at sprog[2 i]
+            auto two = [&](const uint2 &w, const uint2 &w2, const double4 &wa) {
+                if (w.x != mw.x || w.y != mw.y || w2.x != mw2.x || w2.y != mw2.y) {
+                    const double t0 = (XLO(w.x) - XHI(w.x)) + (XLO(w2.x) - XHI(w2.x)), t1 = (XLO(w.y) - XHI(w.y)) + (XLO(w2.y) - XHI(w2.y));
+                    m_t = snaq_clamp10(t0 + t1);
+                    m_l = snaq_log_pos(fma(SNAQ_K_M23, snaq_exp(-m_t, M), 1.0), M);
+                    mw = w; mw2 = w2;
+                }
+                acc += fma(wa.x, m_l, -fma(wa.y, m_t + SNAQ_K_LOG3, wa.w));
+            };
+#pragma unroll 1
+            for (; i + 1 < wend; i += 2) {
+                const uint2 a0 = sprog[2 * i], a1 = sprog[2 * i + 1], b0 = sprog[2 * i + 2], b1 = sprog[2 * i + 3];
+                const double4 waA = reinterpret_cast<const double4 *>(sW)[i], waB = reinterpret_cast<const double4 *>(sW)[i + 1];
+                two(a0, a1, waA);
+                two(b0, b1, waB);
+            }
+            if (i < wend) { two(sprog[2 * i], sprog[2 * i + 1], reinterpret_cast<const double4 *>(sW)[i]); i = wend; }
         }
 #pragma unroll 1
         for (; i < wend; i++) {
@@ -846,6 +865,25 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
                 }
                 if (i < wend) { one(sprog[i], reinterpret_cast<const double4 *>(sW)[i]); i = wend; }
                 mw2 = make_uint2(0xfffffffeu, 1u);                     // consistent with the general loop below (not entered)
+            } else if (implicit && mult == 2u) {
+                // every program of this chunk is TWO chunks at sprog[2 i]
+                auto two = [&](const uint2 &w, const uint2 &w2, const double4 &wa) {
+                    if (w.x != mw.x || w.y != mw.y || w2.x != mw2.x || w2.y != mw2.y) {
+                        const double t0 = (XLO(w.x) - XHI(w.x)) + (XLO(w2.x) - XHI(w2.x)), t1 = (XLO(w.y) - XHI(w.y)) + (XLO(w2.y) - XHI(w2.y));
+                        m_t = snaq_clamp10(t0 + t1);
+                        m_l = snaq_log_pos(fma(SNAQ_K_M23, snaq_exp(-m_t, M), 1.0), M);
+                        mw = w; mw2 = w2;
+                    }
+                    acc += fma(wa.x, m_l, -fma(wa.y, m_t + SNAQ_K_LOG3, wa.w));
+                };
+#pragma unroll 1
+                for (; i + 1 < wend; i += 2) {
+                    const uint2 a0 = sprog[2 * i], a1 = sprog[2 * i + 1], b0 = sprog[2 * i + 2], b1 = sprog[2 * i + 3];
+                    const double4 waA = reinterpret_cast<const double4 *>(sW)[i], waB = reinterpret_cast<const double4 *>(sW)[i + 1];
+                    two(a0, a1, waA);
+                    two(b0, b1, waB);
+                }
+                if (i < wend) { two(sprog[2 * i], sprog[2 * i + 1], reinterpret_cast<const double4 *>(sW)[i]); i = wend; }
             }
 #pragma unroll 1
             for (; i < wend; i++) {
