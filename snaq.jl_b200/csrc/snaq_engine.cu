@@ -1686,6 +1686,7 @@ struct snaq_ctx {
     int sm_count = 148;
     int eval_chunks = 2;                  // snaq_eval pipelines large batches in this many chunks (SNAQ_EVAL_CHUNKS = 1..4)
     int lanes_persistent = 1;             // SNAQ_LANES_PERSISTENT: 0 never, 1 for big xf tiles (default), 2 always
+    int lanes_chunk = 256;                // quartets per block of k_eval_lanes (SNAQ_LANES_CHUNK)
     int lanes_warps = 8;                  // warps per block of k_eval_lanes (SNAQ_LANES_WARPS = 8, 12 or 16)
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -1947,7 +1948,7 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
         }
         // one block per (chunk, group): quartets per block.  Enough blocks to fill the machine, bounded by shared memory.
         const int warps = ctx->lanes_warps;
-        int chunk = 256;
+        int chunk = ctx->lanes_chunk;
         while (chunk > 64 && (int64_t)ngroups * ((nq + chunk - 1) / chunk) < (int64_t)ctx->sm_count * 8) chunk >>= 1;
         while (chunk > 32 && lanes_smem_layout(H.n_full, chunk, warps, ctx->maxlen).total > 200 * 1024) chunk >>= 1;
         const size_t smem = lanes_smem_layout(H.n_full, chunk, warps, ctx->maxlen).total;
@@ -2022,6 +2023,7 @@ int snaq_create(const snaq_opts *opts, snaq_ctx **out) {
         if (atoi(ev) > 0 && cudaMalloc((void **)&ctx->d_trace, (size_t)ctx->sm_count * 4 * 8 * sizeof(unsigned long long)) != cudaSuccess) ctx->d_trace = nullptr;
     }
     if (const char *ev = getenv("SNAQ_EVAL_CHUNKS")) { int v = atoi(ev); if (v >= 1 && v <= 4) ctx->eval_chunks = v; }
+    if (const char *ev = getenv("SNAQ_LANES_CHUNK")) { int v = atoi(ev); if (v == 128 || v == 256 || v == 512 || v == 1024) ctx->lanes_chunk = v; }
     if (const char *ev = getenv("SNAQ_LANES_PERSISTENT")) ctx->lanes_persistent = atoi(ev);
     if (const char *ev = getenv("SNAQ_LANES_WARPS")) { int v = atoi(ev); if (v == 8 || v == 12 || v == 16) ctx->lanes_warps = v; }
     if ((e = cudaMalloc((void **)&ctx->d_status, 4 * sizeof(uint32_t))) != cudaSuccess) return fail(e, "cudaMalloc");
