@@ -262,6 +262,37 @@ def main():
                            "nparams": npar, "l2": "flushed between timed iterations (inputs < L2)", "descriptor_build_s": t_build},
                 "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(P * npar * 8), "d2h_bytes_per_step": int(P * 8 + 4)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+        # ---- the same launch with the reuse between neighbouring quartets switched off (SNAQ_REUSE=0): every quartet gets its
+        # own exp/log and its own terms, which is what SURVEY 8d's flop count describes
+        try:
+            os.environ["SNAQ_REUSE"] = "0"
+            eng0 = eng.__class__(local)
+            del os.environ["SNAQ_REUSE"]
+            eng0.set_data(S.DataCF(taxa, qt, obs))
+            eng0.set_network(flat)
+            out0 = torch.zeros(P, dtype=torch.float64, device=dev)
+            with torch.cuda.stream(stream):
+                for _ in range(3):
+                    eng0.eval_device(dX, out0, stream)
+            torch.cuda.synchronize()
+            ev0 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            with torch.cuda.stream(stream):
+                for a, b in ev0:
+                    flush.fill_(1)
+                    a.record(stream)
+                    eng0.eval_device(dX, out0, stream)
+                    b.record(stream)
+            torch.cuda.synchronize()
+            ms0 = float(np.mean([a.elapsed_time(b) for a, b in ev0]))
+            tf0 = evals_per_step * flop_per_eval / (ms0 * 1e-3) / 1e12
+            line["roofline_no_reuse"] = {"bound": "fp64", "value": evals_per_step / (ms0 * 1e-3), "unit_value": "evals/s", "ms_per_step": ms0,
+                                         "achieved": tf0, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf0 / peak_tf,
+                                         "max_rel_diff_vs_default": float(((out0 - dout).abs() / dout.abs()).max().item()),
+                                         "note": "same kernel, same sorted table, reuse disabled: one full evaluation per (quartet, vector)"}
+            del eng0
+        except Exception as exc:  # noqa: BLE001
+            os.environ.pop("SNAQ_REUSE", None)
+            line["roofline_no_reuse"] = {"error": str(exc)[:200]}
         # ---- opt-in program deduplication (SNAQ_OPT_DEDUP): the same batch on the table with one entry per DISTINCT program.
         # Reported apart from `value`: it evaluates fewer programs, so it says nothing about the kernel's roofline.
         try:

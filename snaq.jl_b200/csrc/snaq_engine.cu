@@ -409,6 +409,7 @@ struct ClassRanges {       // sorted quartet positions [0,nA) class A, [nA,nA+nB
     int chA, chB, chC;     // chunks (blocks) per class
     int64_t nA2;           // the next nA2 class-A quartets have two-chunk programs at chunk a2base + 2 j
     uint32_t a2base;
+    int noreuse;           // 1: do not reuse t1 / exp / log / terms between neighbouring quartets (measurement aid)
 };
 
 /*
@@ -457,6 +458,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
     uint32_t *soff = reinterpret_cast<uint32_t *>(smem + L.soff);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = blockIdx.y;
+    const bool noreuse = cr.noreuse != 0;          // measurement aid (SNAQ_REUSE=0): every quartet evaluated in full
     // heavy classes first: C, B, then A
     int cls, cb = blockIdx.x;
     int64_t qbase, qend;
@@ -518,7 +520,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
             // every program of this chunk is ONE chunk at sprog[i]: no offsets, two quartets per iteration (the loads of the
             // second do not wait for the first)
             auto one = [&](const uint2 &w, const double4 &wa) {
-                if (w.x != mw.x || w.y != mw.y) {
+                if (noreuse || w.x != mw.x || w.y != mw.y) {
                     m_t = snaq_clamp10((XLO(w.x) - XHI(w.x)) + (XLO(w.y) - XHI(w.y)));
                     m_l = snaq_log_pos(fma(SNAQ_K_M23, snaq_exp(-m_t, M), 1.0), M);
                     mw = w;
@@ -537,7 +539,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
         } else if (q0 >= cr.nA1 && q0 + nqc <= cr.nA1 + cr.nA2) {
             // every program of this chunk is TWO chunks at sprog[2 i]
             auto two = [&](const uint2 &w, const uint2 &w2, const double4 &wa) {
-                if (w.x != mw.x || w.y != mw.y || w2.x != mw2.x || w2.y != mw2.y) {
+                if (noreuse || w.x != mw.x || w.y != mw.y || w2.x != mw2.x || w2.y != mw2.y) {
                     const double t0 = (XLO(w.x) - XHI(w.x)) + (XLO(w2.x) - XHI(w2.x)), t1 = (XLO(w.y) - XHI(w.y)) + (XLO(w2.y) - XHI(w2.y));
                     m_t = snaq_clamp10(t0 + t1);
                     m_l = snaq_log_pos(fma(SNAQ_K_M23, snaq_exp(-m_t, M), 1.0), M);
@@ -560,7 +562,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
             const uint32_t len = soff[i + 1] - c0;
             const uint2 w = sprog[c0];
             const uint2 w2 = (len == 2u) ? sprog[c0 + 1] : make_uint2(0xfffffffeu, len);
-            if (len > 2u || w.x != mw.x || w.y != mw.y || w2.x != mw2.x || w2.y != mw2.y) {
+            if (noreuse || len > 2u || w.x != mw.x || w.y != mw.y || w2.x != mw2.x || w2.y != mw2.y) {
                 if (len == 1u) m_t = snaq_clamp10((XLO(w.x) - XHI(w.x)) + (XLO(w.y) - XHI(w.y)));
                 else m_t = pair_sum(i);
                 const double y = snaq_exp(-m_t, M);
@@ -585,7 +587,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
             // the WHOLE program is often the previous one (the class is sorted by term, then by program): reuse t and log(major)
             const uint32_t bc0 = soff[i], blen = soff[i + 1] - bc0;
             const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
-            bool same = (blen == mB_len);
+            bool same = (blen == mB_len) && !noreuse;
             if (same) {
                 const uint2 a0 = sprog[bc0], a1 = blen > 1u ? sprog[bc0 + 1] : mB_w1, a2 = blen > 2u ? sprog[bc0 + 2] : mB_w2;
                 same = a0.x == mB_w0.x && a0.y == mB_w0.y && a1.x == mB_w1.x && a1.y == mB_w1.y && a2.x == mB_w2.x && a2.y == mB_w2.y;
@@ -612,7 +614,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
                 if ((th & 3u) == SNAQ_T2) {
                     const unsigned wv = (unsigned)pc[k + 1] | ((unsigned)pc[k + 2] << 16);
                     k += 3;
-                    if (th != m2_k0 || wv != m2_k1) {
+                    if (noreuse || th != m2_k0 || wv != m2_k1) {
                         const double e = snaq_clamp10(XLO(wv) - XHI(wv));
                         const double gh = (th & 4u) ? 1.0 - gq : gq;
                         m2_v = snaq_clamp10(-snaq_log(1.0 - gh * (1.0 - snaq_exp(-e, M)), M));
@@ -631,7 +633,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
                         ch += XLO(wc) - XHI(wc);
                     }
                     ch = snaq_clamp10(ch);
-                    if (kk0 != m4_k0 || wv != m4_k1) {
+                    if (noreuse || kk0 != m4_k0 || wv != m4_k1) {
                         const double clo = XLO(wv), chi = XHI(wv), ck = XLO((unsigned)pc[k - 2 * nchain - 2]);
                         const double ya = snaq_exp(-snaq_clamp10(clo), M), yb = snaq_exp(-snaq_clamp10(ck - chi), M);
                         const double ye = snaq_exp(-snaq_clamp10(chi - clo), M);
@@ -676,7 +678,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
             const uint2 w = sprog[soff[i]];
             const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
             if (SNAQ_HDR_KIND(hd[i]) == SNAQ_KIND_T5) {
-                if (w.x != m5_k0 || w.y != m5_k1) {
+                if (noreuse || w.x != m5_k0 || w.y != m5_k1) {
                     const double g2 = XLO(w.x), ca = XHI(w.x), cm = XLO(w.y), cb = XHI(w.y);
                     const double g1 = 1.0 - g2;
                     const double y5 = snaq_exp(-snaq_clamp10(cm - ca), M), y6 = snaq_exp(-snaq_clamp10(cb - cm), M);
@@ -752,6 +754,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
     uint32_t *soff = reinterpret_cast<uint32_t *>(smem + L.soff);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = blockIdx.y;
+    const bool noreuse = cr.noreuse != 0;          // measurement aid (SNAQ_REUSE=0): every quartet evaluated in full
     const int nchunks_tot = cr.chA + cr.chB + cr.chC;
     const uint2 *prog2 = reinterpret_cast<const uint2 *>(prog);
     struct Meta { int cls; int64_t q0; int nqc; bool implicit; uint32_t mult, base, nch; };
@@ -849,7 +852,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
                 // every program of this chunk is ONE chunk at sprog[i]: no offsets, two quartets per iteration (the loads of the
                 // second do not wait for the first)
                 auto one = [&](const uint2 &w, const double4 &wa) {
-                    if (w.x != mw.x || w.y != mw.y) {
+                    if (noreuse || w.x != mw.x || w.y != mw.y) {
                         m_t = snaq_clamp10((XLO(w.x) - XHI(w.x)) + (XLO(w.y) - XHI(w.y)));
                         m_l = snaq_log_pos(fma(SNAQ_K_M23, snaq_exp(-m_t, M), 1.0), M);
                         mw = w;
@@ -868,7 +871,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
             } else if (implicit && mult == 2u) {
                 // every program of this chunk is TWO chunks at sprog[2 i]
                 auto two = [&](const uint2 &w, const uint2 &w2, const double4 &wa) {
-                    if (w.x != mw.x || w.y != mw.y || w2.x != mw2.x || w2.y != mw2.y) {
+                    if (noreuse || w.x != mw.x || w.y != mw.y || w2.x != mw2.x || w2.y != mw2.y) {
                         const double t0 = (XLO(w.x) - XHI(w.x)) + (XLO(w2.x) - XHI(w2.x)), t1 = (XLO(w.y) - XHI(w.y)) + (XLO(w2.y) - XHI(w2.y));
                         m_t = snaq_clamp10(t0 + t1);
                         m_l = snaq_log_pos(fma(SNAQ_K_M23, snaq_exp(-m_t, M), 1.0), M);
@@ -891,7 +894,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
                 const uint32_t len = SO(i + 1) - c0;
                 const uint2 w = sprog[c0];
                 const uint2 w2 = (len == 2u) ? sprog[c0 + 1] : make_uint2(0xfffffffeu, len);
-                if (len > 2u || w.x != mw.x || w.y != mw.y || w2.x != mw2.x || w2.y != mw2.y) {
+                if (noreuse || len > 2u || w.x != mw.x || w.y != mw.y || w2.x != mw2.x || w2.y != mw2.y) {
                     if (len == 1u) m_t = snaq_clamp10((XLO(w.x) - XHI(w.x)) + (XLO(w.y) - XHI(w.y)));
                     else m_t = pair_sum(i);
                     const double y = snaq_exp(-m_t, M);
@@ -915,7 +918,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
                 // the WHOLE program is often the previous one (the class is sorted by term, then by program): reuse t and log(major)
                 const uint32_t bc0 = SO(i), blen = SO(i + 1) - bc0;
                 const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
-                bool same = (blen == mB_len);
+                bool same = (blen == mB_len) && !noreuse;
                 if (same) {
                     const uint2 a0 = sprog[bc0], a1 = blen > 1u ? sprog[bc0 + 1] : mB_w1, a2 = blen > 2u ? sprog[bc0 + 2] : mB_w2;
                     same = a0.x == mB_w0.x && a0.y == mB_w0.y && a1.x == mB_w1.x && a1.y == mB_w1.y && a2.x == mB_w2.x && a2.y == mB_w2.y;
@@ -942,7 +945,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
                     if ((th & 3u) == SNAQ_T2) {
                         const unsigned wv = (unsigned)pc[k + 1] | ((unsigned)pc[k + 2] << 16);
                         k += 3;
-                        if (th != m2_k0 || wv != m2_k1) {
+                        if (noreuse || th != m2_k0 || wv != m2_k1) {
                             const double e = snaq_clamp10(XLO(wv) - XHI(wv));
                             const double gh = (th & 4u) ? 1.0 - gq : gq;
                             m2_v = snaq_clamp10(-snaq_log(1.0 - gh * (1.0 - snaq_exp(-e, M)), M));
@@ -961,7 +964,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
                             ch += XLO(wc) - XHI(wc);
                         }
                         ch = snaq_clamp10(ch);
-                        if (kk0 != m4_k0 || wv != m4_k1) {
+                        if (noreuse || kk0 != m4_k0 || wv != m4_k1) {
                             const double clo = XLO(wv), chi = XHI(wv), ck = XLO((unsigned)pc[k - 2 * nchain - 2]);
                             const double ya = snaq_exp(-snaq_clamp10(clo), M), yb = snaq_exp(-snaq_clamp10(ck - chi), M);
                             const double ye = snaq_exp(-snaq_clamp10(chi - clo), M);
@@ -1006,7 +1009,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
                 const uint2 w = sprog[SO(i)];
                 const double4 w4 = reinterpret_cast<const double4 *>(sW)[i];
                 if (SNAQ_HDR_KIND(hd[i]) == SNAQ_KIND_T5) {
-                    if (w.x != m5_k0 || w.y != m5_k1) {
+                    if (noreuse || w.x != m5_k0 || w.y != m5_k1) {
                         const double g2 = XLO(w.x), ca = XHI(w.x), cm = XLO(w.y), cb = XHI(w.y);
                         const double g1 = 1.0 - g2;
                         const double y5 = snaq_exp(-snaq_clamp10(cm - ca), M), y6 = snaq_exp(-snaq_clamp10(cb - cm), M);
@@ -1686,6 +1689,7 @@ struct snaq_ctx {
     int sm_count = 148;
     int eval_chunks = 2;                  // snaq_eval pipelines large batches in this many chunks (SNAQ_EVAL_CHUNKS = 1..4)
     int lanes_persistent = 1;             // SNAQ_LANES_PERSISTENT: 0 never, 1 for big xf tiles (default), 2 always
+    bool reuse = true;                    // SNAQ_REUSE=0: the batched kernels evaluate every quartet in full (measurement aid)
     int lanes_chunk = 256;                // quartets per block of k_eval_lanes (SNAQ_LANES_CHUNK)
     int lanes_warps = 8;                  // warps per block of k_eval_lanes (SNAQ_LANES_WARPS = 8, 12 or 16)
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -1904,6 +1908,7 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
         ClassRanges cr;
         cr.nA1 = tb.nA1; cr.nA = tb.nA; cr.nB = tb.nB; cr.nC = tb.nC;
         cr.nA2 = tb.nA2; cr.a2base = (uint32_t)(tb.nA1 + (tb.nA1 & 1));
+        cr.noreuse = ctx->reuse ? 0 : 1;
         if (ngroups > 65535) { ctx->err = "batch too large for one launch"; return SNAQ_EINVAL; }
         // xf tiles of 48 KB and more (~100 taxa and up): reloading the tile for every chunk of quartets is most of the
         // L2 traffic, and from ~100 KB only one block fits per SM: the persistent variant keeps the tile resident
@@ -2023,6 +2028,7 @@ int snaq_create(const snaq_opts *opts, snaq_ctx **out) {
         if (atoi(ev) > 0 && cudaMalloc((void **)&ctx->d_trace, (size_t)ctx->sm_count * 4 * 8 * sizeof(unsigned long long)) != cudaSuccess) ctx->d_trace = nullptr;
     }
     if (const char *ev = getenv("SNAQ_EVAL_CHUNKS")) { int v = atoi(ev); if (v >= 1 && v <= 4) ctx->eval_chunks = v; }
+    if (const char *ev = getenv("SNAQ_REUSE")) ctx->reuse = atoi(ev) != 0;
     if (const char *ev = getenv("SNAQ_LANES_CHUNK")) { int v = atoi(ev); if (v == 128 || v == 256 || v == 512 || v == 1024) ctx->lanes_chunk = v; }
     if (const char *ev = getenv("SNAQ_LANES_PERSISTENT")) ctx->lanes_persistent = atoi(ev);
     if (const char *ev = getenv("SNAQ_LANES_WARPS")) { int v = atoi(ev); if (v == 8 || v == 12 || v == 16) ctx->lanes_warps = v; }
