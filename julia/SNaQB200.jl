@@ -29,9 +29,9 @@ end
 check(e::Engine, rc) = rc == 0 || error(unsafe_string(ccall((:snaq_last_error, LIB), Cstring, (Ptr{Cvoid},), e.ctx)))
 
 "one engine per Julia worker process; worker i uses GPU (i-1) % ngpus (pmap over runs: src/snaq_optimization.jl:1681)"
-function Engine(d::DataCF; device::Integer = (Distributed.myid() - 1) % 8)
-    ctx = Ref{Ptr{Cvoid}}(C_NULL)
-    rc = ccall((:snaq_create, LIB), Cint, (Ref{Opts}, Ref{Ptr{Cvoid}}), Opts(device, 0, 1, 0), ctx)
+function Engine(d::DataCF; device::Integer = (Distributed.myid() - 1) % 8, dedup::Bool = false)
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)   # dedup: evaluate each distinct quartet program once with summed weights (SNAQ_OPT_DEDUP)
+    rc = ccall((:snaq_create, LIB), Cint, (Ref{Opts}, Ref{Ptr{Cvoid}}), Opts(device, 0, 1, dedup ? 1 : 0), ctx)
     rc == 0 || error(unsafe_string(ccall((:snaq_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
     taxa = SNaQ.tiplabels(d)                               # src/readquartetdata.jl:440
     tid = Dict(t => UInt16(i - 1) for (i, t) in enumerate(taxa))
