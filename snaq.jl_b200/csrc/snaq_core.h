@@ -472,7 +472,9 @@ SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWr
             n0 += snaq_put_pair(w, SNAQ_T3ROW(T, c, m.lo), NUL);
             if (info) info->type[T.cyc_hyb[c]] = 3;
         } else if (m.cls == SNAQ_C_TZ) {
-            n0 += snaq_put_pair(w, SNAQ_TZROW(T, c, m.other == 1 ? 0 : 1), NUL);
+            /* the edge -log(1-gammaz) of a pruned bad diamond I already exists when cleanUpNode! runs: if the chain of a
+             * type-4 term at the other end reaches this junction, the edge is merged with that chain (owner != 0) */
+            if (owner == 0) n0 += snaq_put_pair(w, SNAQ_TZROW(T, c, m.other == 1 ? 0 : 1), NUL);
         }
     }
     /* on-the-fly terms, in path order */
@@ -509,8 +511,10 @@ SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWr
                 if (cc < 0) continue;
                 if (j == 0) {
                     if (e1.cls == SNAQ_C_OPEN && me == 2 && bArc) nchain += snaq_put_arc(T, cc, e1.lo, e1.hi, w);
+                    if (e1.cls == SNAQ_C_TZ && me == 2 && bArc) nchain += snaq_put_pair(w, SNAQ_TZROW(T, cc, e1.other == 1 ? 0 : 1), NUL);
                 } else if (j == ns - 1) {
                     if (e2.cls == SNAQ_C_OPEN && me == 1 && aArc) nchain += snaq_put_arc(T, cc, e2.lo, e2.hi, w);
+                    if (e2.cls == SNAQ_C_TZ && me == 1 && aArc) nchain += snaq_put_pair(w, SNAQ_TZROW(T, cc, e2.other == 1 ? 0 : 1), NUL);
                 } else {
                     int owner = (t4a && j <= ja) ? 1 : ((t4b && j >= jb + 1) ? 2 : 0);
                     if (owner != me) continue;

@@ -87,3 +87,32 @@ def test_random_networks_descriptors_and_values(oracle, block):
         assert np.max(np.abs(r["expcf"] - ex)) <= 1e-13
         nbad += 0
     assert nbad == 0
+
+
+@pytest.mark.parametrize("seed", [61, 95, 103, 115, 7, 200, 333])
+def test_cap_corner_with_a_pruned_bad_diamond_behind_a_type4_chain(oracle, seed):
+    """Regression (found by a randomized sweep): when the pruned quartet holds more than one hybrid, cleanUpNode!
+    (src/pseudolik.jl:852-857) merges the chain below a type-4 hybrid up to the next degree-3 node BEFORE the type-4
+    length is computed; if the other junction is a pruned bad diamond I, its edge -log(1-gammaz) already exists and is
+    part of that chain.  Only visible when lengths sit at the 10.0 cap and the type-4 term is negative."""
+    n, h = 8 + seed % 22, seed % 7
+    try:
+        net = simulate.random_level1_network(n, h, 9000 + seed, min_cycle=3 if seed % 3 == 0 else 4)
+    except S.SnaqError:
+        pytest.skip("no network for this seed")
+    taxa = [f"t{i + 1}" for i in range(n)]
+    flat = net.flatten(taxa)
+    qt = simulate.all_quartets(n)
+    p = oracle.parameters(flat)
+    rng = np.random.default_rng(seed)
+    X = np.zeros((4, len(p["x"])))
+    for k in range(4):
+        X[k] = np.where(p["upper"] > 1.5, rng.choice([0.0, 10.0, 5.0, 0.3], size=len(p["x"])), rng.choice([0.01, 0.5, 0.3, 0.99], size=len(p["x"])))
+    obs = np.full((len(qt), 3), 1 / 3)
+    for k in range(4):
+        try:
+            want, ex = oracle.evaluate(flat, qt, obs, X[k:k + 1], want_expcf=True)
+        except Exception:
+            continue                                               # a vector the reference rejects (negative length too negative)
+        r = hs.run(flat, n, qt, obs=obs, X=X[k:k + 1])
+        assert np.max(np.abs(r["expcf"] - ex)) <= 1e-12
