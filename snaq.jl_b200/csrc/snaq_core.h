@@ -829,12 +829,17 @@ SNAQ_HD void snaq_weights(unsigned hdr, const double obs[3], int sampled, double
 SNAQ_HD double snaq_loglik_tree(double t, double major, const double W[4], const SnaqMath &M) {
     return (W[0] != 0.0 ? W[0] * snaq_log(major, M) : 0.0) - W[1] * (t + SNAQ_K_LOG3) - W[3];
 }
-SNAQ_HD double snaq_loglik_t5(const double cf[3], const double W[4], const SnaqMath &M, unsigned &status) {
+/* pen (deduplicated table only, else NULL): {E0, E1, E2, n} of the run this entry stands for, E_j = sum over its sampled
+ * quartets of 100 obs_j log(obs_j), n = number of sampled quartets.  The -1e15 of a negative expCF is per QUARTET and
+ * replaces that quartet's term including its obs*log(obs) share of W[3], so it is not linear in the weights. */
+SNAQ_HD double snaq_loglik_t5(const double cf[3], const double W[4], const SnaqMath &M, unsigned &status, const double *pen = nullptr) {
+    if (W[0] == 0.0 && W[1] == 0.0 && W[2] == 0.0) return 0.0;      /* unsampled: contributes 0, penalty included (src/pseudolik.jl:1390) */
     double s = -W[3];
     for (int j = 0; j < 3; j++) {
         if (cf[j] < 0.0) {
             /* -1e15 replaces this term, including its obs*log(obs) share of W[3] */
-            s += -1.e15 + (W[j] != 0.0 ? W[j] * snaq_log_slow(W[j] / 100.0) : 0.0);
+            if (pen) s += -1.e15 * pen[3] + pen[j];
+            else s += -1.e15 + (W[j] != 0.0 ? W[j] * snaq_log_slow(W[j] / 100.0) : 0.0);
         } else if (W[j] != 0.0) {
             s += W[j] * snaq_log(cf[j], M);
         }
@@ -843,12 +848,12 @@ SNAQ_HD double snaq_loglik_t5(const double cf[3], const double W[4], const SnaqM
     return s;
 }
 SNAQ_HD double snaq_quartet_loglik(unsigned kind, const double cf[3], double t1, const double W[4], const SnaqMath &M,
-                                   unsigned &status) {
+                                   unsigned &status, const double *pen = nullptr) {
     if (kind == SNAQ_KIND_TREE) {
         if (cf[0] < 0.0) status |= SNAQ_S_NEGLEN;
         return snaq_loglik_tree(t1, cf[0], W, M);
     }
-    return snaq_loglik_t5(cf, W, M, status);
+    return snaq_loglik_t5(cf, W, M, status, pen);
 }
 
 /* ------------------------------------------------------------------------------
@@ -885,7 +890,7 @@ SNAQ_HD double snaq_dv_dt_tree(double t1, const double W[4], const SnaqMath &M, 
  * (the diagonal is only used as the initial metric of the quasi-Newton update). */
 template <class XF, class ADD, class ADDH>
 SNAQ_HD double snaq_grad_quartet(unsigned hdr, const uint16_t *pc, int nwords, const XF &x, const SnaqMath &M, const double W[4],
-                                 unsigned nul, ADD &add, ADDH &addh, unsigned &status) {
+                                 unsigned nul, ADD &add, ADDH &addh, unsigned &status, const double *pen = nullptr) {
     const unsigned kind = SNAQ_HDR_KIND(hdr);
     if (kind == SNAQ_KIND_TREE && !SNAQ_HDR_TERMS(hdr)) {
         /* class A */
@@ -1006,7 +1011,9 @@ SNAQ_HD double snaq_grad_quartet(unsigned hdr, const uint16_t *pc, int nwords, c
     double dcf[3];
     /* a negative expCF costs a flat -1e15 (src/pseudolik.jl:1394-1396): the objective has no slope there, so the
      * reported "gradient" of such a term is the slope of SNAQ_PENALTY_SLOPE * cf, which points out of the region */
-    for (int j = 0; j < 3; j++) dcf[j] = cf[j] < 0.0 ? SNAQ_PENALTY_SLOPE : ((W[j] != 0.0 && cf[j] > 0.0) ? W[j] / cf[j] : 0.0);
+    const bool smp = (W[0] != 0.0 || W[1] != 0.0 || W[2] != 0.0);     /* an unsampled quartet contributes nothing, slope included */
+    for (int j = 0; j < 3; j++)
+        dcf[j] = !smp ? 0.0 : (cf[j] < 0.0 ? SNAQ_PENALTY_SLOPE * (pen ? pen[3] : 1.0) : ((W[j] != 0.0 && cf[j] > 0.0) ? W[j] / cf[j] : 0.0));
     if (kind == SNAQ_KIND_T5) {
         const double g2 = x(pc[0]), g1 = 1.0 - g2;
         const double a5 = x(pc[2]) - x(pc[1]), a6 = x(pc[3]) - x(pc[2]);
@@ -1024,7 +1031,7 @@ SNAQ_HD double snaq_grad_quartet(unsigned hdr, const uint16_t *pc, int nwords, c
         add(pc[0], dz[0]);
         add(pc[1], dz[1]);
     }
-    return snaq_loglik_t5(cf, W, M, status);
+    return snaq_loglik_t5(cf, W, M, status, pen);
 }
 
 /*

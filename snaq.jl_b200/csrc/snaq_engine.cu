@@ -261,29 +261,36 @@ __device__ __forceinline__ void two_sum(double a, double b, double &s, double &e
     e = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
 }
 __global__ void __launch_bounds__(128) k_weights_u(const uint32_t *__restrict__ rstart, const double4 *__restrict__ W, int64_t nu,
-                                                   int64_t nq, double4 *__restrict__ Wu) {
+                                                   int64_t nq, double4 *__restrict__ Wu, double4 *__restrict__ pen) {
+    // components 0..3: the weights; 4..6: E_j = sum of w_j log(w_j / 100) (the obs*log(obs) share of program slot j);
+    // 7: number of sampled quartets of the run.  4..7 are only read when an expected CF is negative (snaq_loglik_t5).
+    constexpr int NC = 8;
     const int64_t u = blockIdx.x;
     const int64_t i0 = rstart[u], i1 = (u + 1 < nu) ? (int64_t)rstart[u + 1] : nq;
-    double s[4] = {0.0, 0.0, 0.0, 0.0}, c[4] = {0.0, 0.0, 0.0, 0.0};
+    double s[NC], c[NC];
+#pragma unroll
+    for (int k = 0; k < NC; k++) { s[k] = 0.0; c[k] = 0.0; }
     for (int64_t i = i0 + threadIdx.x; i < i1; i += 128) {
         const double4 w = W[i];
-        const double v[4] = {w.x, w.y, w.z, w.w};
+        const bool smp = (w.x != 0.0 || w.y != 0.0 || w.z != 0.0);
+        const double v[NC] = {w.x, w.y, w.z, w.w, w.x != 0.0 ? w.x * log(w.x / 100.0) : 0.0, w.y != 0.0 ? w.y * log(w.y / 100.0) : 0.0,
+                              w.z != 0.0 ? w.z * log(w.z / 100.0) : 0.0, smp ? 1.0 : 0.0};
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < NC; k++) {
             const double y = __dsub_rn(v[k], c[k]);
             const double t = __dadd_rn(s[k], y);
             c[k] = __dsub_rn(__dsub_rn(t, s[k]), y);
             s[k] = t;
         }
     }
-    __shared__ double sh[2][4][128];
+    __shared__ double sh[2][NC][128];
 #pragma unroll
-    for (int k = 0; k < 4; k++) { sh[0][k][threadIdx.x] = s[k]; sh[1][k][threadIdx.x] = -c[k]; }   // value = sum + error
+    for (int k = 0; k < NC; k++) { sh[0][k][threadIdx.x] = s[k]; sh[1][k][threadIdx.x] = -c[k]; }   // value = sum + error
     __syncthreads();
     for (int o = 64; o > 0; o >>= 1) {
         if ((int)threadIdx.x < o) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < NC; k++) {
                 double ss, ee;
                 two_sum(sh[0][k][threadIdx.x], sh[0][k][threadIdx.x + o], ss, ee);
                 sh[0][k][threadIdx.x] = ss;
@@ -292,9 +299,12 @@ __global__ void __launch_bounds__(128) k_weights_u(const uint32_t *__restrict__ 
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
         Wu[u] = make_double4(__dadd_rn(sh[0][0][0], sh[1][0][0]), __dadd_rn(sh[0][1][0], sh[1][1][0]), __dadd_rn(sh[0][2][0], sh[1][2][0]),
                              __dadd_rn(sh[0][3][0], sh[1][3][0]));
+        pen[u] = make_double4(__dadd_rn(sh[0][4][0], sh[1][4][0]), __dadd_rn(sh[0][5][0], sh[1][5][0]), __dadd_rn(sh[0][6][0], sh[1][6][0]),
+                              __dadd_rn(sh[0][7][0], sh[1][7][0]));
+    }
 }
 
 // W[i] (all classes) and, for the class-A quartets with one- and two-chunk programs [0,nA), the pair
@@ -410,6 +420,7 @@ struct ClassRanges {       // sorted quartet positions [0,nA) class A, [nA,nA+nB
     int64_t nA2;           // the next nA2 class-A quartets have two-chunk programs at chunk a2base + 2 j
     uint32_t a2base;
     int noreuse;           // 1: do not reuse t1 / exp / log / terms between neighbouring quartets (measurement aid)
+    const double *pen;     // deduplicated table: per-entry penalty data {E0, E1, E2, n}, else nullptr
 };
 
 /*
@@ -697,7 +708,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
                 const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + soff[i]);
                 double cf[3];
                 snaq_t5_cf(SNAQ_KIND_T5BD1, pc, xf, M, cf);
-                acc += snaq_loglik_t5(cf, sW + 4 * i, M, st);
+                acc += snaq_loglik_t5(cf, sW + 4 * i, M, st, cr.pen ? cr.pen + 4 * (q0 + i) : nullptr);
             }
         }
     }
@@ -1028,7 +1039,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
                     const uint16_t *pc = reinterpret_cast<const uint16_t *>(sprog + SO(i));
                     double cf[3];
                     snaq_t5_cf(SNAQ_KIND_T5BD1, pc, xf, M, cf);
-                    acc += snaq_loglik_t5(cf, sW + 4 * i, M, st);
+                    acc += snaq_loglik_t5(cf, sW + 4 * i, M, st, cr.pen ? cr.pen + 4 * (q0 + i) : nullptr);
                 }
             }
         }
@@ -1083,7 +1094,7 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
               double *__restrict__ partial, double *__restrict__ out, const double *__restrict__ negw3,
               unsigned int *__restrict__ ticket, double *__restrict__ expcf, double *__restrict__ logpl,
               double *__restrict__ deltacf, uint32_t *__restrict__ status, unsigned long long *__restrict__ trace,
-              uint32_t *__restrict__ status_out, const int use_xarg, const __grid_constant__ XArg xarg) {
+              uint32_t *__restrict__ status_out, const int use_xarg, const double *__restrict__ pen, const __grid_constant__ XArg xarg) {
     constexpr int BLOCK = 256;
     extern __shared__ __align__(128) unsigned char smem[];
     double *mt = reinterpret_cast<double *>(smem);                        // 48 doubles, 128-byte aligned
@@ -1182,7 +1193,7 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
                         const XRow xf{xs + p * n_full};
                         double cf[3], t1;
                         snaq_eval_quartet(hdr, pc, nwords, xf, M, cf, &t1, st);
-                        const double v = snaq_quartet_loglik(SNAQ_HDR_KIND(hdr), cf, t1, w, M, st);
+                        const double v = snaq_quartet_loglik(SNAQ_HDR_KIND(hdr), cf, t1, w, M, st, (pen && !OUT) ? pen + 4 * (size_t)i : nullptr);
 #pragma unroll
                         for (int k = 0; k < PC; k++) if (k == p) acc[k] += v;     // keeps acc[] in registers
                         if (OUT) {
@@ -1322,7 +1333,7 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
             const double *__restrict__ X, const double *__restrict__ xconst, int nh, int nt, double *__restrict__ partial,
             double *__restrict__ out, const double *__restrict__ negw3, unsigned int *__restrict__ ticket,
             double *__restrict__ gpart, double *__restrict__ gout, uint32_t *__restrict__ status, uint32_t *__restrict__ status_out,
-            const int use_xarg, const __grid_constant__ XArg xarg) {
+            const int use_xarg, const double *__restrict__ pen, const __grid_constant__ XArg xarg) {
     constexpr int BLOCK = 256;
     extern __shared__ __align__(128) unsigned char smem[];
     double *mt = reinterpret_cast<double *>(smem);                        // 48 doubles, 128-byte aligned
@@ -1487,7 +1498,7 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
                 const double w[4] = {w4.x, w4.y, w4.z, w4.w};
                 const uint16_t *pc = reinterpret_cast<const uint16_t *>(staged ? wspan + (o0 - s0) : prog2 + o0);
                 const XRow xf{xs};
-                acc += snaq_grad_quartet(hdr, pc, (int)(o1 - o0) * 4, xf, M, w, nul, add, addh, st);
+                acc += snaq_grad_quartet(hdr, pc, (int)(o1 - o0) * 4, xf, M, w, nul, add, addh, st, pen ? pen + 4 * (size_t)i : nullptr);
             }
         }
     }
@@ -1671,6 +1682,7 @@ struct snaq_ctx {
     uint8_t *d_qhdr_u = nullptr;
     uint16_t *d_prog_u = nullptr; size_t prog_u_cap = 0; uint64_t prog_u_words = 0;
     double *d_W_u = nullptr; double2 *d_WA_u = nullptr; double *d_wpart_u = nullptr, *d_negw3_u = nullptr;
+    double *d_pen_u = nullptr;            // [nU][4] per-run data of the -1e15 penalty (snaq_loglik_t5)
     uint32_t *d_status = nullptr;          // [0] build, [1] eval
     unsigned long long *d_trace = nullptr; // SNAQ_TRACE=1: [blocks][8] phase timestamps of the last k_eval_direct launch
     int trace_blocks = 0;
@@ -1751,11 +1763,13 @@ static int status_to_error(snaq_ctx *ctx, uint32_t st) {
 struct EvalTable {
     const uint32_t *off; const uint16_t *prog; const uint8_t *qhdr; const double *W; const double2 *WA; const double *negw3;
     int64_t nq, nA1, nA2, nA, nB, nC;
+    const double *pen;      // deduplicated table: per-run penalty data, else nullptr
 };
 static EvalTable eval_table(const snaq_ctx *ctx, bool full) {
     if (ctx->dedup && !full) return EvalTable{ctx->d_off_u, ctx->d_prog_u, ctx->d_qhdr_u, ctx->d_W_u, ctx->d_WA_u, ctx->d_negw3_u,
-                                              ctx->nU, ctx->uA1, ctx->uA2, ctx->uA, ctx->uB, ctx->uC};
-    return EvalTable{ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_W, ctx->d_WA, ctx->d_negw3, ctx->nq, ctx->nA1, ctx->nA2, ctx->nA, ctx->nB, ctx->nC};
+                                              ctx->nU, ctx->uA1, ctx->uA2, ctx->uA, ctx->uB, ctx->uC, ctx->d_pen_u};
+    return EvalTable{ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_W, ctx->d_WA, ctx->d_negw3, ctx->nq, ctx->nA1, ctx->nA2, ctx->nA, ctx->nB, ctx->nC,
+                     nullptr};
 }
 
 static int run_weights(snaq_ctx *ctx) {
@@ -1770,7 +1784,7 @@ static int run_weights(snaq_ctx *ctx) {
     if (ctx->dedup && ctx->nU > 0) {
         // no separate class-A constant for the compressed table (negw3_u stays 0): see launch_direct
         k_weights_u<<<(unsigned)ctx->nU, 128, 0, ctx->stream>>>(ctx->d_rstart, reinterpret_cast<const double4 *>(ctx->d_W), ctx->nU, ctx->nq,
-                                                               reinterpret_cast<double4 *>(ctx->d_W_u));
+                                                               reinterpret_cast<double4 *>(ctx->d_W_u), reinterpret_cast<double4 *>(ctx->d_pen_u));
         CK(cudaGetLastError());
         ctx->counters[5] += 1;
     }
@@ -1796,7 +1810,7 @@ static int build_dedup(snaq_ctx *ctx, int64_t pad_at) {
     const int64_t nu = ctx->nU;
     if ((size_t)nu + 1 > ctx->u_cap) {
         cudaFree(ctx->d_rstart); cudaFree(ctx->d_ulen); cudaFree(ctx->d_off_u); cudaFree(ctx->d_qhdr_u); cudaFree(ctx->d_W_u); cudaFree(ctx->d_WA_u);
-        cudaFree(ctx->d_wpart_u);
+        cudaFree(ctx->d_wpart_u); cudaFree(ctx->d_pen_u);
         ctx->u_cap = 0;
         const size_t n = (size_t)nu + 1 + (size_t)nu / 8;
         CK(cudaMalloc((void **)&ctx->d_rstart, (n + 1) * sizeof(uint32_t)));
@@ -1804,6 +1818,7 @@ static int build_dedup(snaq_ctx *ctx, int64_t pad_at) {
         CK(cudaMalloc((void **)&ctx->d_off_u, (n + 2) * sizeof(uint32_t)));
         CK(cudaMalloc((void **)&ctx->d_qhdr_u, n + 1));
         CK(cudaMalloc((void **)&ctx->d_W_u, (n + 1) * 4 * sizeof(double)));
+        CK(cudaMalloc((void **)&ctx->d_pen_u, (n + 1) * 4 * sizeof(double)));
         CK(cudaMalloc((void **)&ctx->d_WA_u, (n + 1) * sizeof(double2)));
         CK(cudaMalloc((void **)&ctx->d_wpart_u, ((n + 255) / 256 + 1) * sizeof(double)));
         ctx->u_cap = n;
@@ -1856,7 +1871,7 @@ static int launch_direct(snaq_ctx *ctx, cudaStream_t stream, const double *dX, i
         reinterpret_cast<const double4 *>(tb.W), ctx->d_obs, (uint32_t)tb.nA1, (uint32_t)tb.nA2,
         (uint32_t)(tb.nA1 + (tb.nA1 & 1)), (uint32_t)tb.nq, dX,
         ctx->d_xconst, H.nh, H.nt, Pc, ctx->d_partial, dout, tb.negw3, ctx->d_ticket, expcf, logpl, deltacf, ctx->d_status + 1, ctx->d_trace,
-        ctx->status_out, ctx->xarg_on ? 1 : 0, ctx->xarg);
+        ctx->status_out, ctx->xarg_on ? 1 : 0, tb.pen, ctx->xarg);
     CK(cudaGetLastError());
     ctx->counters[0] += 1;
     ctx->counters[1] += ctx->nq * (int64_t)Pc;
@@ -1909,6 +1924,7 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
         cr.nA1 = tb.nA1; cr.nA = tb.nA; cr.nB = tb.nB; cr.nC = tb.nC;
         cr.nA2 = tb.nA2; cr.a2base = (uint32_t)(tb.nA1 + (tb.nA1 & 1));
         cr.noreuse = ctx->reuse ? 0 : 1;
+        cr.pen = tb.pen;
         if (ngroups > 65535) { ctx->err = "batch too large for one launch"; return SNAQ_EINVAL; }
         // xf tiles of 48 KB and more (~100 taxa and up): reloading the tile for every chunk of quartets is most of the
         // L2 traffic, and from ~100 KB only one block fits per SM: the persistent variant keeps the tile resident
@@ -2048,7 +2064,7 @@ int snaq_destroy(snaq_ctx *ctx) {
     cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_blob); cudaFree(ctx->d_xconst);
     cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_WA); cudaFree(ctx->d_wpart); cudaFree(ctx->d_negw3); cudaFree(ctx->d_status); cudaFree(ctx->d_total); cudaFree(ctx->d_ticket); cudaFree(ctx->d_trace);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_uidx); cudaFree(ctx->d_rstart); cudaFree(ctx->d_ulen); cudaFree(ctx->d_off_u); cudaFree(ctx->d_qhdr_u);
-    cudaFree(ctx->d_prog_u); cudaFree(ctx->d_W_u); cudaFree(ctx->d_WA_u); cudaFree(ctx->d_wpart_u); cudaFree(ctx->d_negw3_u);
+    cudaFree(ctx->d_prog_u); cudaFree(ctx->d_W_u); cudaFree(ctx->d_WA_u); cudaFree(ctx->d_wpart_u); cudaFree(ctx->d_negw3_u); cudaFree(ctx->d_pen_u);
     cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_XF); cudaFree(ctx->d_out); cudaFree(ctx->d_partial); cudaFree(ctx->d_gpart); cudaFree(ctx->d_gout);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_qhdr); cudaFree(ctx->d_len4); cudaFree(ctx->d_iota); cudaFree(ctx->d_cls);
     cudaFree(ctx->d_cls_sorted);
@@ -2446,7 +2462,7 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
             ctx->T, tb.off, reinterpret_cast<const uint2 *>(tb.prog), tb.qhdr, tb.WA,                                           \
             reinterpret_cast<const double4 *>(tb.W), (uint32_t)tb.nA1, (uint32_t)tb.nA2,                                        \
             (uint32_t)(tb.nA1 + (tb.nA1 & 1)), (uint32_t)tb.nq, ctx->d_X, ctx->d_xconst, H.nh, H.nt, ctx->d_partial,            \
-            h_g, tb.negw3, ctx->d_ticket, ctx->d_gpart, h_g + 1, ctx->d_status + 1, h_st, by_arg ? 1 : 0, ctx->xarg);        \
+            h_g, tb.negw3, ctx->d_ticket, ctx->d_gpart, h_g + 1, ctx->d_status + 1, h_st, by_arg ? 1 : 0, tb.pen, ctx->xarg);        \
     } while (0)
     if (hdiag) LAUNCH_GRAD(true); else LAUNCH_GRAD(false);
 #undef LAUNCH_GRAD

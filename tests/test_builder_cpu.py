@@ -116,3 +116,19 @@ def test_cap_corner_with_a_pruned_bad_diamond_behind_a_type4_chain(oracle, seed)
             continue                                               # a vector the reference rejects (negative length too negative)
         r = hs.run(flat, n, qt, obs=obs, X=X[k:k + 1])
         assert np.max(np.abs(r["expcf"] - ex)) <= 1e-12
+
+
+def test_negative_expcf_penalty_skips_unsampled_quartets(oracle):
+    """-1e15 per negative expCF (src/pseudolik.jl:1394-1396) applies to SAMPLED quartets only (:1390)."""
+    net = S.readnewicklevel1(kat.NET_NEG)
+    taxa = [str(i) for i in range(1, 7)]
+    flat = net.flatten(taxa)
+    qt = simulate.all_quartets(6)
+    obs = np.tile([0.5, 0.3, 0.2], (len(qt), 1))
+    x = oracle.parameters(flat)["x"].copy()
+    x[-2:] = [0.9, 0.8]                                           # gammaz sum > 1: negative expCFs
+    for mask in (None, np.zeros(len(qt), np.uint8), (np.arange(len(qt)) % 2).astype(np.uint8)):
+        want = oracle.evaluate(flat, qt, obs, x, sampled=mask)[0]
+        got = hs.run(flat, 6, qt, obs=obs, X=x, sampled=mask)["lik"][0]
+        assert abs(got - want) <= 1e-12 * max(1.0, abs(want)), (mask, got, want)
+    assert oracle.evaluate(flat, qt, obs, x)[0] > 1e15

@@ -94,3 +94,32 @@ def test_dedup_at_100_taxa_collapses_the_table():
     X = simulate.parameter_batch(x0, upper, 40, 5)
     np.testing.assert_allclose(dd.eval(X), plain.eval(X), rtol=1e-12)
     np.testing.assert_allclose(dd.eval(X[:1]), plain.eval(X[:1]), rtol=1e-12)
+
+
+@pytest.mark.parametrize("dedup", [False, True])
+def test_negative_expcf_penalty_is_per_sampled_quartet(oracle, dedup):
+    """The -1e15 of a negative expCF (src/pseudolik.jl:1394-1396) is per sampled quartet: not linear in the weights, so the
+    deduplicated table carries the number of sampled quartets and the obs*log(obs) shares of every run."""
+    from tests import kat
+    net = S.readnewicklevel1(kat.NET_NEG)
+    taxa = [str(i) for i in range(1, 7)]
+    flat = net.flatten(taxa)
+    qt = np.concatenate([simulate.all_quartets(6)] * 3)            # repeated rows: runs of identical programs
+    rng = np.random.default_rng(2)
+    obs = rng.dirichlet([3, 2, 2], size=len(qt))
+    eng = S.Engine(0, dedup=dedup)
+    eng.set_data(S.DataCF(taxa, qt, obs))
+    eng.set_network(flat)
+    x0, _, upper = eng.get_params()
+    x = x0.copy()
+    x[-2:] = [0.9, 0.8]                                            # gammaz sum > 1: negative expCFs
+    X = np.stack([x0, x, x0 * 0.9, x])
+    for mask in (None, np.zeros(len(qt), np.uint8), (np.arange(len(qt)) % 2).astype(np.uint8), (np.arange(len(qt)) % 3 != 0).astype(np.uint8)):
+        eng.set_sampled(mask)
+        want = oracle.evaluate(flat, qt, obs, X, sampled=mask)
+        for P in (1, 2, 4):
+            np.testing.assert_allclose(eng.eval(X[:P]), want[:P], rtol=1e-12, atol=1e-9)
+        np.testing.assert_allclose(eng.eval(np.tile(X, (10, 1))), np.tile(want, 10), rtol=1e-12, atol=1e-9)    # batched kernels
+        f, g = eng.eval_grad(x)
+        assert abs(f - want[1]) <= 1e-12 * max(1.0, abs(want[1]))
+    assert want.max() > 1e15
