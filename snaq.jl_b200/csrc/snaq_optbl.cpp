@@ -136,6 +136,13 @@ extern "C" int snaq_optbl(snaq_ctx *ctx, const snaq_optbl_opts *o, double *x_io,
     std::vector<double> g, hd;
     rc = gradient(pb, x, f, false, g, hd, true);
     if (rc) return rc;
+    if (!std::isfinite(f)) {
+        // a start on the boundary can have an expected CF of exactly 0 under a positive observed CF (deviance +Inf, no slope):
+        // step a hair inside the box and start from there
+        for (int i = 0; i < n; i++) { const double m = 1e-4 * (pb.hi[i] - pb.lo[i]); x[i] = clampd(x[i], pb.lo[i] + m, pb.hi[i] - m); }
+        rc = gradient(pb, x, f, false, g, hd, true);
+        if (rc) return rc;
+    }
     if (n == 0) { res->fmin = f; res->nevals = (int32_t)pb.nevals; res->nlaunches = (int32_t)pb.nlaunches; res->status = SNAQ_OPTBL_XTOL; return SNAQ_OK; }
     const int M = std::max(12, std::min(n, 64));   // quasi-Newton pairs kept (full memory for small networks)
     std::deque<Pair> mem;

@@ -138,3 +138,14 @@ def test_optbl_stopping_rules(oracle):
     assert np.all(xa >= 0) and np.all(xa <= upper)
     with pytest.raises(RuntimeError):
         hs.optbl(flat, 14, qt, obs, start, ftol_rel=0.0)          # "tolerances have to be positive" (:350)
+
+
+def test_optbl_from_a_start_on_the_boundary_with_infinite_deviance(oracle):
+    flat, qt, obs, x0, upper = make(oracle, 12, 2, 77, ngenes=100)
+    start = np.where(np.arange(len(x0)) % 2 == 0, 0.0, upper)        # every parameter at a bound
+    f0 = oracle.evaluate(flat, qt, obs, start)[0]
+    xmin, res = hs.optbl(flat, 12, qt, obs, start, 1e-12, 1e-10, 1e-10, 1e-10)
+    assert np.isfinite(res["fmin"]) and (not np.isfinite(f0) or res["fmin"] <= f0)
+    inside = np.clip(start, 1e-4 * upper, upper * (1 - 1e-4))
+    assert res["fmin"] <= oracle.evaluate(flat, qt, obs, inside)[0]  # a local optimum reachable from there (not necessarily the global one)
+    assert np.all(xmin >= 0) and np.all(xmin <= upper)
