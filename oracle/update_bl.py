@@ -72,7 +72,8 @@ def update_bl_table(flat, quartet_taxa, obscf):
                 mate = d.index(t2) if d[0] == t1 else (d.index(t1) if d[0] == t2 else (d.index(t4) if d[0] == t3 else d.index(t3)))
                 cfs.append(obs[r, mate - 1])
         if cfs:
-            out[enum] = (len(cfs), -math.log(1.5 * (1.0 - float(np.mean(cfs)))))
+            arg = 1.5 * (1.0 - float(np.mean(cfs)))
+            out[enum] = (len(cfs), -math.log(arg) if arg > 0.0 else math.inf)   # Julia: -log(0.0) == Inf
     return out
 
 

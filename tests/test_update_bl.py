@@ -38,6 +38,26 @@ def test_oracle_update_bl_inverts_the_tree_formula(oracle):
     assert np.allclose(lengths, flat.edge_length)          # nothing is < 0 or == 1.0 among the internal edges here
 
 
+def test_oracle_update_bl_all_concordant_gives_an_infinite_length():
+    """every quartet of an edge fully concordant: -log(3/2 * 0) is Inf in the reference (:846), not an error"""
+    net, taxa, qt = tree_and_data(5, 1)
+    flat = net.flatten(taxa)
+    parts = dict(ubl._parts(flat))
+    enum, ps = next(iter(parts.items()))
+    obs = np.full((len(qt), 3), 1 / 3)
+    for i, q in enumerate(qt):                             # the split of each quartet that edge `enum` induces gets CF 1
+        d = [int(t) for t in q]
+        side = [next(k for k, p in enumerate(ps) if t in p) // 2 for t in d]
+        if sorted(side) == [0, 0, 1, 1] and len({next(k for k, p in enumerate(ps) if t in p) for t in d}) == 4:
+            mate = next(j for j in (1, 2, 3) if side[j] == side[0])
+            obs[i] = 0.0
+            obs[i, mate - 1] = 1.0
+    tab = ubl.update_bl_table(flat, qt, obs)
+    assert tab[enum][1] == np.inf
+    lengths, _ = ubl.update_bl(flat, qt, obs)
+    assert np.all(lengths >= 0)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed", range(5))
 def test_device_update_bl_matches_the_oracle(oracle, seed):
