@@ -207,6 +207,19 @@ typedef struct snaq_optbl_result {
  * opts may be NULL (the search-time tolerances fRel, fAbs, xRel, xAbs of :36-39).                          */
 int snaq_optbl(snaq_ctx *ctx, const snaq_optbl_opts *opts, double *x, snaq_optbl_result *res);
 
+/* Candidate-move batching: optBL! of C candidate networks over the resident data, run concurrently
+ * on this context's GPU.  It replaces a loop of `optBL!(proposed net, d)` calls, src/snaq_optimization.jl:1362-1432
+ * (one per proposed topology), for callers that can propose several candidates before looking at a result.
+ * `workers` (1..32, 0 = 8) worker contexts are kept inside ctx: each has its own stream and table and a device copy of
+ * ctx's data (taxa, obsCF, sampling mask), refreshed when ctx's data changes.  Candidate c starts at the parameters its
+ * flat network carries (ht(net)); xmin + c*ldx receives its optimum, nparams[c] its parameter count (ldx >= every
+ * count), results[c] the summary.  Each result is bit-identical to snaq_set_network + snaq_optbl on one context, whatever
+ * runs beside it.  A candidate that fails gets results[c].status = -(error code); the call then returns the first such
+ * code with "topology <c>: ..." as message, the other candidates' results stay valid.  ctx's own network is untouched.
+ * Not available in quartet-sharded mode.                                                                              */
+int snaq_optbl_topologies(snaq_ctx *ctx, int32_t C, const snaq_flatnet *nets, const snaq_optbl_opts *opts,
+                          int32_t workers, double *xmin, int32_t ldx, int32_t *nparams, snaq_optbl_result *results);
+
 /* ---- updateBL!: src/readquartetdata.jl:838-861 -------------------------- */
 /* The current network must be a tree.  For each edge-length parameter (the t block of x, numht order):
  * nquartets[i] = data quartets that correspond exactly to the edge (one taxon in each of the four subtrees

@@ -34,11 +34,14 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/snaq_b200.h"
@@ -1705,6 +1708,10 @@ struct snaq_ctx {
     int lanes_chunk = 256;                // quartets per block of k_eval_lanes (SNAQ_LANES_CHUNK)
     int lanes_warps = 8;                  // warps per block of k_eval_lanes (SNAQ_LANES_WARPS = 8, 12 or 16)
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // snaq_optbl_topologies: worker contexts on the same device, each with a copy of this context's data
+    uint64_t data_version = 1;            // bumped by snaq_set_data / snaq_set_obscf / snaq_set_sampled
+    std::vector<snaq_ctx *> workers;
+    std::vector<uint64_t> worker_version;
 };
 
 static thread_local std::string g_create_err;
@@ -1713,10 +1720,33 @@ static thread_local std::string g_create_err;
     do {                                                                                                  \
         cudaError_t e_ = (call);                                                                          \
         if (e_ != cudaSuccess) {                                                                          \
-            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (snaq_engine.cu:" +         \
+                       std::to_string(__LINE__) + ")";                                                    \
             return SNAQ_ECUDA;                                                                            \
         }                                                                                                 \
     } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the kernel, shared by every context and host thread of
+// the process: raise it monotonically under a lock, so a launch prepared by one thread is never invalidated by a smaller
+// value set for another context between its cudaFuncSetAttribute and its launch.
+template <class K> static cudaError_t raise_smem_limit(K kernel, size_t smem) {
+    struct Limit { const void *kernel; int device; size_t smem; };
+    static std::mutex mu;
+    static std::vector<Limit> limits;                        // per (kernel, device): the attribute lives in the device's module
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    Limit *l = nullptr;
+    for (auto &x : limits)
+        if (x.kernel == (const void *)kernel && x.device == dev) l = &x;
+    if (l && smem <= l->smem) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (l) l->smem = smem;
+    else limits.push_back({(const void *)kernel, dev, smem});
+    return cudaSuccess;
+}
 
 template <class T> static int ensure(snaq_ctx *ctx, T *&p, size_t &cap, size_t need) {
     if (need <= cap && p) return SNAQ_OK;
@@ -1865,7 +1895,7 @@ static int launch_direct(snaq_ctx *ctx, cudaStream_t stream, const double *dX, i
     int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)grid * PC);
     if (rc) return rc;
     if (ctx->d_trace) ctx->trace_blocks = grid;
-    CK(cudaFuncSetAttribute(k_eval_direct<PC, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(raise_smem_limit(k_eval_direct<PC, OUT>, smem));
     k_eval_direct<PC, OUT><<<grid, 256, smem, stream>>>(
         ctx->T, tb.off, reinterpret_cast<const uint2 *>(tb.prog), tb.qhdr, ctx->d_perm, tb.WA,
         reinterpret_cast<const double4 *>(tb.W), ctx->d_obs, (uint32_t)tb.nA1, (uint32_t)tb.nA2,
@@ -1952,7 +1982,7 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
             dim3 grid((unsigned)gx, (unsigned)ngroups);
 #define LAUNCH_LANESP(WN)                                                                                                      \
     do {                                                                                                                       \
-        CK(cudaFuncSetAttribute(k_eval_lanes_p<WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
+        CK(raise_smem_limit(k_eval_lanes_p<WN>, smem));                                                                          \
         k_eval_lanes_p<WN><<<grid, WN * 32, smem, stream>>>(tb.off, tb.prog, tb.qhdr, tb.W, cr, chunk, ctx->maxlen,             \
                                                            dXF, H.n_full, ctx->d_partial, Ppad, ctx->d_status + 1, LANESP_SUPER); \
     } while (0)
@@ -1982,7 +2012,7 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
         dim3 grid((unsigned)nchunks, (unsigned)ngroups);
 #define LAUNCH_LANES(WN)                                                                                                       \
     do {                                                                                                                       \
-        CK(cudaFuncSetAttribute(k_eval_lanes<WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
+        CK(raise_smem_limit(k_eval_lanes<WN>, smem));                                                                            \
         k_eval_lanes<WN><<<grid, WN * 32, smem, stream>>>(tb.off, tb.prog, tb.qhdr, tb.W, cr, chunk, ctx->maxlen, dXF,         \
                                                          H.n_full, ctx->d_partial, Ppad, ctx->d_status + 1);                    \
     } while (0)
@@ -2059,6 +2089,8 @@ int snaq_create(const snaq_opts *opts, snaq_ctx **out) {
 
 int snaq_destroy(snaq_ctx *ctx) {
     if (!ctx) return SNAQ_OK;
+    for (snaq_ctx *w : ctx->workers) snaq_destroy(w);
+    ctx->workers.clear();
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_blob); cudaFree(ctx->d_xconst);
@@ -2091,6 +2123,7 @@ int snaq_set_data(snaq_ctx *ctx, int32_t ntaxa, int64_t nq, const uint16_t *taxa
     ctx->ntaxa = ntaxa;
     ctx->has_net = false;
     ctx->has_sampled = false;
+    ctx->data_version++;
     cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_off); cudaFree(ctx->d_W);
     cudaFree(ctx->d_WA); cudaFree(ctx->d_wpart); cudaFree(ctx->d_negw3);
     ctx->d_WA = nullptr; ctx->d_wpart = nullptr; ctx->d_negw3 = nullptr;
@@ -2134,6 +2167,7 @@ int snaq_set_obscf(snaq_ctx *ctx, const double *obscf) {
     if (!ctx || !obscf) return SNAQ_EINVAL;
     if (!ctx->d_obs) { ctx->err = "snaq_set_data has not been called"; return SNAQ_ENODATA; }
     CK(cudaSetDevice(ctx->device));
+    ctx->data_version++;
     for (int64_t i = 0; i < ctx->nq_total * 3; i++)
         if (!(obscf[i] >= 0.0 && obscf[i] <= 1.0)) { ctx->err = "obsCF must be between (0,1) in quartet " + std::to_string(i / 3); return SNAQ_EINVAL; }
     if (ctx->nq > 0) {
@@ -2150,6 +2184,7 @@ int snaq_set_sampled(snaq_ctx *ctx, const uint8_t *mask) {
     if (!ctx) return SNAQ_EINVAL;
     if (!ctx->d_obs) { ctx->err = "snaq_set_data has not been called"; return SNAQ_ENODATA; }
     CK(cudaSetDevice(ctx->device));
+    ctx->data_version++;
     ctx->has_sampled = (mask != nullptr);
     if (mask && ctx->nq > 0) {
         CK(cudaMemcpyAsync(ctx->d_sampled, mask + ctx->q_begin, (size_t)ctx->nq, cudaMemcpyHostToDevice, ctx->stream));
@@ -2268,6 +2303,94 @@ int snaq_eval_topologies(snaq_ctx *ctx, int32_t C, const snaq_flatnet *nets, dou
         rc = snaq_eval(ctx, 1, np, np > 0 ? ctx->H.x0.data() : &out[c], &out[c]);    // np == 0: X is not read
         if (rc) { ctx->err = "topology " + std::to_string(c + 1) + ": " + ctx->err; return rc; }
     }
+    return SNAQ_OK;
+}
+
+// Brings worker w's data up to date with ctx's: a device-to-device copy of the three data arrays (allocation through
+// snaq_set_data only when the shape changed).
+static int sync_worker(snaq_ctx *ctx, size_t w) {
+    snaq_ctx *wk = ctx->workers[w];
+    if (ctx->worker_version[w] == ctx->data_version) return SNAQ_OK;
+    if (wk->nq != ctx->nq || wk->ntaxa != ctx->ntaxa || !wk->d_taxa) {
+        std::vector<uint16_t> taxa((size_t)ctx->nq * 4);
+        std::vector<double> obs((size_t)ctx->nq * 3);
+        if (ctx->nq > 0) {
+            CK(cudaMemcpy(taxa.data(), ctx->d_taxa, taxa.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(obs.data(), ctx->d_obs, obs.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        }
+        int rc = snaq_set_data(wk, ctx->ntaxa, ctx->nq, taxa.data(), obs.data());
+        if (rc) { ctx->err = "worker context: " + wk->err; return rc; }
+    } else if (ctx->nq > 0) {
+        CK(cudaMemcpyAsync(wk->d_obs, ctx->d_obs, (size_t)ctx->nq * 3 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    wk->has_sampled = ctx->has_sampled;
+    if (ctx->has_sampled && ctx->nq > 0)
+        CK(cudaMemcpyAsync(wk->d_sampled, ctx->d_sampled, (size_t)ctx->nq, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    wk->has_net = false;                                     // the weights of its table are rebuilt by the next snaq_set_network
+    wk->data_version++;
+    ctx->worker_version[w] = ctx->data_version;
+    return SNAQ_OK;
+}
+
+int snaq_optbl_topologies(snaq_ctx *ctx, int32_t C, const snaq_flatnet *nets, const snaq_optbl_opts *opts, int32_t workers,
+                          double *xmin, int32_t ldx, int32_t *nparams, snaq_optbl_result *results) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (C < 0 || workers < 0 || workers > 32 || (C > 0 && (!nets || !xmin || !results || ldx < 0))) {
+        ctx->err = "bad arguments to snaq_optbl_topologies";
+        return SNAQ_EINVAL;
+    }
+    if (!ctx->d_taxa) { ctx->err = "snaq_set_data has not been called"; return SNAQ_ENODATA; }
+    if (ctx->world > 1) { ctx->err = "snaq_optbl_topologies is not available in quartet-sharded mode"; return SNAQ_EINVAL; }
+    if (C == 0) return SNAQ_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t W = (size_t)std::min<int32_t>(workers > 0 ? workers : 8, C);
+    while (ctx->workers.size() < W) {
+        snaq_opts o{ctx->device, 0, 1, ctx->dedup ? SNAQ_OPT_DEDUP : 0u};
+        snaq_ctx *wk = nullptr;
+        int rc = snaq_create(&o, &wk);
+        if (rc) { ctx->err = std::string("worker context: ") + snaq_last_error(nullptr); return rc; }
+        wk->reuse = ctx->reuse; wk->eval_chunks = ctx->eval_chunks; wk->lanes_persistent = ctx->lanes_persistent;
+        wk->lanes_chunk = ctx->lanes_chunk; wk->lanes_warps = ctx->lanes_warps;
+        ctx->workers.push_back(wk);
+        ctx->worker_version.push_back(0);
+    }
+    for (size_t w = 0; w < W; w++) {
+        int rc = sync_worker(ctx, w);
+        if (rc) return rc;
+    }
+    std::atomic<int32_t> next{0};
+    std::vector<int> rcs((size_t)C, SNAQ_OK);
+    std::vector<std::string> msgs((size_t)C);
+    auto body = [&](size_t w) {
+        snaq_ctx *wk = ctx->workers[w];
+        for (;;) {
+            const int32_t c = next.fetch_add(1);
+            if (c >= C) break;
+            snaq_optbl_result r{};
+            int32_t np = 0;
+            int rc = snaq_set_network(wk, &nets[c]);
+            if (!rc) rc = snaq_num_params(wk, &np, nullptr, nullptr, nullptr);
+            if (!rc && np > ldx) { wk->err = "ldx is smaller than the number of parameters"; rc = SNAQ_EINVAL; }
+            if (!rc) {
+                double *x = xmin + (size_t)c * ldx;
+                rc = snaq_get_params(wk, x, nullptr, nullptr);
+                if (!rc) rc = snaq_optbl(wk, opts, x, &r);
+            }
+            if (nparams) nparams[c] = np;
+            if (rc) { r = snaq_optbl_result{}; r.status = -rc; msgs[c] = wk->err; }
+            rcs[c] = rc;
+            results[c] = r;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (size_t w = 1; w < W; w++) pool.emplace_back(body, w);
+    body(0);
+    for (auto &t : pool) t.join();
+    for (size_t w = 0; w < W; w++)
+        for (int k : {0, 1, 2, 3, 5}) { ctx->counters[k] += ctx->workers[w]->counters[k]; ctx->workers[w]->counters[k] = 0; }   // the cumulative ones
+    for (int32_t c = 0; c < C; c++)
+        if (rcs[c]) { ctx->err = "topology " + std::to_string(c + 1) + ": " + msgs[c]; return rcs[c]; }
     return SNAQ_OK;
 }
 
@@ -2457,7 +2580,7 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
     }
 #define LAUNCH_GRAD(WH)                                                                                                        \
     do {                                                                                                                       \
-        CK(cudaFuncSetAttribute(k_eval_grad<WH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
+        CK(raise_smem_limit(k_eval_grad<WH>, smem));                                                                             \
         k_eval_grad<WH><<<grid, 256, smem, ctx->stream>>>(                                                                      \
             ctx->T, tb.off, reinterpret_cast<const uint2 *>(tb.prog), tb.qhdr, tb.WA,                                           \
             reinterpret_cast<const double4 *>(tb.W), (uint32_t)tb.nA1, (uint32_t)tb.nA2,                                        \

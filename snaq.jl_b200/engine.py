@@ -33,7 +33,7 @@ EXPORTS = ["snaq_create", "snaq_destroy", "snaq_last_error", "snaq_version", "sn
            "snaq_set_sampled", "snaq_set_network", "snaq_patch_network", "snaq_num_params", "snaq_get_params",
            "snaq_eval", "snaq_eval_device", "snaq_eval_quartets", "snaq_get_descriptors", "snaq_get_counters",
            "snaq_check_status", "snaq_measure_fp64_peak", "snaq_get_trace", "snaq_eval_grad", "snaq_optbl", "snaq_update_bl", "snaq_get_hasedge",
-           "snaq_eval_topologies"]
+           "snaq_eval_topologies", "snaq_optbl_topologies"]
 
 
 class _OptblOpts(C.Structure):
@@ -139,6 +139,25 @@ class Engine:
         if flats:
             self.set_network_meta()
         return out
+
+    def optbl_topologies(self, flats, workers=0, ftol_rel=1e-6, ftol_abs=1e-6, xtol_rel=1e-2, xtol_abs=1e-3, maxeval=1000,
+                         ladder=20, fd=False):
+        """``optBL!`` of every candidate flat network, run concurrently on this GPU (snaq_optbl_topologies): returns a list
+        of (xmin, info) in the order of ``flats``.  Each entry equals ``set_network`` + ``optbl`` on one context, bit for
+        bit.  The first candidate that fails raises SnaqError ("topology <c>: ...") after all candidates have run."""
+        from .network import _CFlat
+        n = len(flats)
+        arr = (_CFlat * max(n, 1))(*[f.c for f in flats])
+        ldx = max([8] + [4 * len(f.edge_number) for f in flats])          # nparams <= #edges + 2 * #hybrids
+        xmin = np.zeros((max(n, 1), ldx))
+        npar = np.zeros(max(n, 1), np.int32)
+        res = (_OptblResult * max(n, 1))()
+        o = _OptblOpts(ftol_rel, ftol_abs, xtol_rel, xtol_abs, maxeval, ladder, 1 if fd else 0, 0)
+        self._chk(self.lib.snaq_optbl_topologies(self.ctx, C.c_int32(n), arr, C.byref(o), C.c_int32(workers), _p(xmin),
+                                                 C.c_int32(ldx), _p(npar), res))
+        return [(xmin[c, : npar[c]].copy(), dict(fmin=res[c].fmin, proj_grad=res[c].proj_grad, nevals=res[c].nevals,
+                                                 nlaunches=res[c].nlaunches, niter=res[c].niter, status=res[c].status))
+                for c in range(n)]
 
     def get_params(self):
         x = np.zeros(self.nparams); numht = np.zeros(self.nparams, np.int32); up = np.zeros(self.nparams)
