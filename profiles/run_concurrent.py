@@ -77,4 +77,19 @@ for T in (1, 1, 2, 4, 8, 16):
         ref = out[0]
     assert out[0] == ref                                  # same candidates, same result whatever runs beside them
     res["threads"][T] = {"optbl_per_s": T * reps / dt, "ms_per_optbl_per_thread": dt / reps * 1e3}
+# the same through the C ABI's own worker pool (snaq_optbl_topologies)
+batch = [cands[(r) % len(cands)] for r in range(4 * len(cands))]
+main = engines[0]
+res["native"] = {}
+for W in (1, 2, 4, 8, 16):
+    main.optbl_topologies(batch[:W], workers=W)            # creates / syncs the workers
+    t0 = time.perf_counter()
+    out = main.optbl_topologies(batch, workers=W)
+    dt = time.perf_counter() - t0
+    res["native"][W] = {"optbl_per_s": len(batch) / dt}
+res["per_optbl"] = {k: float(np.mean([o[1][k] for o in out])) for k in ("nevals", "nlaunches", "niter")}
+t0 = time.perf_counter()
+for c in batch:
+    main.set_network(c)
+res["set_network_ms"] = (time.perf_counter() - t0) / len(batch) * 1e3
 print(json.dumps(res))

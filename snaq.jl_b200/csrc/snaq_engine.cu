@@ -54,6 +54,7 @@
 // results are written by the last block straight into page-locked host memory (no device->host copy call).
 #define XARG_MAX 448      /* doubles (3.5 KB of kernel parameter space) */
 struct XArg { double v[XARG_MAX]; };
+#define SNAQ_S_DONE 0x80000000u   /* status word in page-locked memory: the kernel has written its results */
 #define LANES_MIN_P 16    /* batches of at least this many candidates use k_eval_lanes */
 
 // --------------------------------------------------------------------------------------------
@@ -1312,7 +1313,11 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
         }
         if (tid == 0) {
             *ticket = 0u;
-            if (status_out) *status_out = *reinterpret_cast<volatile uint32_t *>(status);   // every block's bits are in by now
+            if (status_out) {                            // every block's bits are in by now; the host polls for the DONE bit
+                const uint32_t st = *reinterpret_cast<volatile uint32_t *>(status);
+                __threadfence_system();                  // out[] (same thread, page-locked host memory) lands before the flag
+                *reinterpret_cast<volatile uint32_t *>(status_out) = st | SNAQ_S_DONE;
+            }
         }
     }
     stamp(4);
@@ -1544,9 +1549,11 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
             for (unsigned b = 0; b < gridDim.x; b++) s += __ldcg(gpart + (size_t)b * nrows + row);
             gout[row] = row < n_full ? -s : s;                            // f = -(sum of v); the curvature is already that of f
         }
+        __threadfence_system();                          // every thread's rows are in host memory before the flag
+        __syncthreads();
         if (tid == 0) {
             *ticket = 0u;
-            if (status_out) *status_out = *reinterpret_cast<volatile uint32_t *>(status);
+            if (status_out) *reinterpret_cast<volatile uint32_t *>(status_out) = *reinterpret_cast<volatile uint32_t *>(status) | SNAQ_S_DONE;
         }
     }
 }
@@ -1748,6 +1755,29 @@ template <class K> static cudaError_t raise_smem_limit(K kernel, size_t smem) {
     return cudaSuccess;
 }
 
+// The single-call kernels finish by writing their results and then a status word with the DONE bit into page-locked
+// host memory: the host spins on that word instead of waiting for the stream's completion semaphore (a few microseconds
+// per objective call).  Every 4096 spins the stream is queried, so a failed launch or kernel surfaces as an error.
+static cudaError_t wait_done(cudaStream_t stream, volatile uint32_t *flag) {
+    for (unsigned spin = 1;; spin++) {
+        if (*flag & SNAQ_S_DONE) break;
+        if ((spin & 0xfffu) == 0) {
+            cudaError_t e = cudaStreamQuery(stream);
+            if (e == cudaSuccess) {                          // the kernel has ended: the flag is there, or something is wrong
+                if (*flag & SNAQ_S_DONE) break;
+                return cudaStreamSynchronize(stream) == cudaSuccess ? cudaErrorUnknown : cudaGetLastError();
+            }
+            if (e != cudaErrorNotReady) return e;
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    *flag &= ~SNAQ_S_DONE;
+    return cudaSuccess;
+}
+
 template <class T> static int ensure(snaq_ctx *ctx, T *&p, size_t &cap, size_t need) {
     if (need <= cap && p) return SNAQ_OK;
     if (p) cudaFree(p);
@@ -1918,16 +1948,19 @@ static int eval_quartets_launch(snaq_ctx *ctx, int P, const double *dX, double *
         if (P > 1) { int rc = eval_quartets_launch(ctx, P - 1, dX, dout, stream, nullptr, nullptr, nullptr); if (rc) return rc; }
         return launch_direct<1, true>(ctx, stream, dX + (size_t)(P - 1) * H.nparams, 1, dout + (P - 1), expcf, logpl, deltacf);
     }
+    uint32_t *const status_out = ctx->status_out;
     for (int p0 = 0; p0 < P;) {
         const int left = P - p0;
         const double *dXp = dX + (size_t)p0 * H.nparams;
         int rc, Pc;
+        ctx->status_out = left <= 4 ? status_out : nullptr;   // only the last launch raises the DONE flag the host polls
         if (left == 1) { Pc = 1; rc = launch_direct<1, false>(ctx, stream, dXp, 1, dout + p0, nullptr, nullptr, nullptr); }
         else if (left == 2) { Pc = 2; rc = launch_direct<2, false>(ctx, stream, dXp, 2, dout + p0, nullptr, nullptr, nullptr); }
         else { Pc = std::min(left, 4); rc = launch_direct<4, false>(ctx, stream, dXp, Pc, dout + p0, nullptr, nullptr, nullptr); }
-        if (rc) return rc;
+        if (rc) { ctx->status_out = status_out; return rc; }
         p0 += Pc;
     }
+    ctx->status_out = status_out;
     return SNAQ_OK;
 }
 
@@ -2478,7 +2511,7 @@ int snaq_eval(snaq_ctx *ctx, int32_t P, int32_t nparams, const double *X, double
         ctx->xarg_src = nullptr;
         ctx->status_out = nullptr;
         if (rc) return rc;
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(wait_done(ctx->stream, h_st));
         ctx->counters[2] += (int64_t)sizeof(double) * P * nparams;
         ctx->counters[3] += (int64_t)sizeof(double) * P + 4;
         if (*h_st) {
@@ -2590,7 +2623,7 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
     if (hdiag) LAUNCH_GRAD(true); else LAUNCH_GRAD(false);
 #undef LAUNCH_GRAD
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(wait_done(ctx->stream, h_st));
     ctx->counters[0] += 1;
     ctx->counters[1] += ctx->nq;
     ctx->counters[2] += 8 * nparams;
