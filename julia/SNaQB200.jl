@@ -47,8 +47,9 @@ function Engine(d::DataCF; device::Integer = (Distributed.myid() - 1) % 8, dedup
     return e
 end
 
-"serialise exactly the fields the hot path reads (SURVEY.md App. B) in net.node / net.edge / node.edge order"
-function set_network!(e::Engine, net::HybridNetwork)
+"serialise exactly the fields the hot path reads (SURVEY.md App. B) in net.node / net.edge / node.edge order;
+returns the struct and the arrays it points into (keep them alive with GC.@preserve while the struct is in use)"
+function flatnet(e::Engine, net::HybridNetwork)
     nidx = Dict(objectid(n) => Cint(i - 1) for (i, n) in enumerate(net.node))
     eidx = Dict(objectid(ed) => Cint(i - 1) for (i, ed) in enumerate(net.edge))
     tid = Dict(t => Cint(i - 1) for (i, t) in enumerate(e.taxa))
@@ -70,12 +71,17 @@ function set_network!(e::Engine, net::HybridNetwork)
     edge_node = Cint[nidx[objectid(ed.node[k])] for k in 1:2, ed in net.edge]
     hyb = Cint[nidx[objectid(n)] for n in net.hybrid]
     leaf = Cint[nidx[objectid(n)] for n in net.leaf]
-    GC.@preserve node_number node_flags node_incycle node_gammaz node_taxon node_edge edge_number edge_flags edge_incycle edge_length edge_gamma edge_node hyb leaf begin
-        f = FlatNet(nn, ne, length(hyb), length(leaf), pointer(node_number), pointer(node_flags), pointer(node_incycle),
-                    pointer(node_gammaz), pointer(node_taxon), pointer(node_edge), pointer(edge_number), pointer(edge_flags),
-                    pointer(edge_incycle), pointer(edge_length), pointer(edge_gamma), pointer(edge_node), pointer(hyb), pointer(leaf))
-        check(e, ccall((:snaq_set_network, LIB), Cint, (Ptr{Cvoid}, Ref{FlatNet}), e.ctx, f))
-    end
+    keep = (node_number, node_flags, node_incycle, node_gammaz, node_taxon, node_edge, edge_number, edge_flags, edge_incycle,
+            edge_length, edge_gamma, edge_node, hyb, leaf)
+    f = FlatNet(nn, ne, length(hyb), length(leaf), pointer(node_number), pointer(node_flags), pointer(node_incycle),
+                pointer(node_gammaz), pointer(node_taxon), pointer(node_edge), pointer(edge_number), pointer(edge_flags),
+                pointer(edge_incycle), pointer(edge_length), pointer(edge_gamma), pointer(edge_node), pointer(hyb), pointer(leaf))
+    return f, keep
+end
+
+function set_network!(e::Engine, net::HybridNetwork)
+    f, keep = flatnet(e, net)
+    GC.@preserve keep check(e, ccall((:snaq_set_network, LIB), Cint, (Ptr{Cvoid}, Ref{FlatNet}), e.ctx, f))
 end
 
 "objective value for one x (the body of `obj` in optBL!, src/snaq_optimization.jl:368-380)"
@@ -136,6 +142,30 @@ function optBL_device!(net::HybridNetwork, d::DataCF, e::Engine, ftolRel = SNaQ.
     SNaQ.updateParameters!(net, x)
     SNaQ.loglik!(net, res.fmin)
     readback!(e, d, x)
+    return res
+end
+
+"optBL! of several proposed networks at once (snaq_optbl_topologies): the opt-in candidate batching of SURVEY 8f rank 2.
+Each net gets what optBL_device! would have given it (ht, loglik); e's own network is left as it was."
+function optBL_candidates!(nets::Vector{HybridNetwork}, d::DataCF, e::Engine; workers::Integer = 0,
+                           ftolRel = SNaQ.fRel, ftolAbs = SNaQ.fAbs, xtolRel = SNaQ.xRel, xtolAbs = SNaQ.xAbs)
+    foreach(SNaQ.parameters!, nets)
+    flats = [flatnet(e, n) for n in nets]
+    fs = FlatNet[f for (f, _) in flats]
+    ldx = maximum(length(ht(n)) for n in nets; init = 1)
+    xmin = zeros(Cdouble, ldx, length(nets))                  # column c = candidate c (row-major C x ldx on the C side)
+    npar = zeros(Cint, length(nets))
+    res = [OptblResult(0, 0, 0, 0, 0, 0) for _ in nets]
+    raw = zeros(UInt8, 32 * length(nets))                     # OptblResult is mutable: a plain buffer, sizeof(snaq_optbl_result) = 2*8 + 4*4
+    GC.@preserve flats check(e, ccall((:snaq_optbl_topologies, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{FlatNet}, Ref{OptblOpts}, Cint, Ptr{Cdouble}, Cint, Ptr{Cint}, Ptr{UInt8}),
+        e.ctx, length(nets), fs, OptblOpts(ftolRel, ftolAbs, xtolRel, xtolAbs, 1000, 0, 0, 0), workers, xmin, ldx, npar, raw))
+    for (c, net) in enumerate(nets)
+        r = reinterpret(Float64, raw[32 * (c - 1) + 1:32 * (c - 1) + 16]); i = reinterpret(Int32, raw[32 * (c - 1) + 17:32 * c])
+        res[c] = OptblResult(r[1], r[2], i[1], i[2], i[3], i[4])
+        SNaQ.updateParameters!(net, xmin[1:npar[c], c])
+        SNaQ.loglik!(net, res[c].fmin)
+    end
     return res
 end
 

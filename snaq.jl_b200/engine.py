@@ -321,6 +321,22 @@ def optBL_(net: HybridNetwork, d: DataCF, ftolRel: float = 1e-6, ftolAbs: float 
     return res
 
 
+def optBL_candidates_(nets, d: DataCF, workers: int = 0, ftolRel: float = 1e-6, ftolAbs: float = 1e-6, xtolRel: float = 1e-2,
+                      xtolAbs: float = 1e-3, device: int = 0):
+    """``optBL!`` of several proposed networks over the same data, concurrently on one GPU (snaq_optbl_topologies; the
+    loop it batches: src/snaq_optimization.jl:1362-1432).  Every net ends as ``optBL_`` would leave it (ht, loglik)."""
+    if not (ftolRel > 0 and ftolAbs > 0 and xtolAbs > 0 and xtolRel > 0):
+        raise SnaqError(f"tolerances have to be positive, ftol (rel,abs), xtol (rel,abs): {[ftolRel, ftolAbs, xtolRel, xtolAbs]}")
+    eng = _engine_for(d, device)
+    for net in nets:
+        net.parameters()
+    out = eng.optbl_topologies([net.flatten(d.taxa) for net in nets], workers, ftolRel, ftolAbs, xtolRel, xtolAbs)
+    for net, (xmin, res) in zip(nets, out):
+        net.update_parameters(list(xmin))
+        net.loglik = res["fmin"]
+    return [res for _, res in out]
+
+
 def updateBL_(net: HybridNetwork, d: DataCF, device: int = 0):
     """``updateBL!`` (src/readquartetdata.jl:838-861): rough starting branch lengths of a TREE from the mean observed CF
     of the quartets that correspond exactly to each internal edge; returns {edge number: (Nquartets, edgeL)}."""

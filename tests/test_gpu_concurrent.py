@@ -140,3 +140,21 @@ def test_optbl_topologies_with_deduplicated_tables():
     eng.set_data(S.DataCF(taxa, qt, obs))
     for (xm, info), (xw, iw) in zip(eng.optbl_topologies(cands, workers=4), want):
         assert np.array_equal(xm, xw) and info == iw
+
+
+def test_optBL_candidates_on_the_reference_example_networks():
+    """examples/net1.networks: five topologies the reference optimised and scored on examples/tableCF.txt.  Optimising
+    them again, all at once, can only keep or lower each score, and must agree with one optBL_ per network."""
+    import os
+    from . import kat
+    here = os.path.dirname(os.path.abspath(__file__))
+    d = S.readtableCF(os.path.join(here, "golden", "tableCF.txt"))
+    nets = [S.readnewicklevel1(nw) for nw, _ in kat.NET1_NETWORKS]
+    res = S.optBL_candidates_(nets, d, workers=5)
+    for net, r, (nw, lik) in zip(nets, res, kat.NET1_NETWORKS):
+        assert r["status"] in (3, 4, 5)
+        assert net.loglik == r["fmin"] <= lik * (1 + 1e-9)
+        assert r["fmin"] >= 0.9 * lik - 1e-6                 # the reference's optimum is a good one already
+        one = S.readnewicklevel1(nw)
+        r1 = S.optBL_(one, d)
+        assert r1 == r and one.ht == net.ht
