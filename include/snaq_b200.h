@@ -229,6 +229,17 @@ int snaq_optbl_topologies(snaq_ctx *ctx, int32_t C, const snaq_flatnet *nets, co
  * (only lengths < 0 or == 1.0 are replaced, by max(edgeL,0); edges without quartets get 1.0).               */
 int snaq_update_bl(snaq_ctx *ctx, int64_t *nquartets, double *edgeL);
 
+/* ---- weighted quartet sampling of the move proposals ---- */
+/* Step 1 of sampleEdgeQuartetWeighted (src/moves_snaq.jl:1443-1449): a weighted sample of quartets with weights
+ * q.deltaCF = sum_i |obsCF_i - expCF_i| at the parameters x (0 for unsampled quartets, src/pseudolik.jl:503-517).
+ * The reference copies all nq weights to a vector per proposal and calls StatsBase.sample(indices, Weights(w), 1):
+ * for one draw that is the inverse-CDF walk `t = rand()*sum(w); i = first index with cumsum(w)[i] >= t`.  Here the
+ * weights never leave the device: idx[k] (0-based, the data's quartet order) is that index for the caller's uniform
+ * draw u[k] in [0,1).  The prefix sums are formed in fixed chunks of 4096 quartets (serial inside a chunk and over the
+ * chunk totals), so the result is reproducible and equals the serial walk unless u*sum falls within rounding distance
+ * of a boundary.  Not available on a quartet-sharded context.                                                      */
+int snaq_sample_quartets(snaq_ctx *ctx, int32_t nparams, const double *x, int32_t n, const double *u, int64_t *idx);
+
 /* ---- descriptors for parity checks ------------------------ */
 /* which[nq]       : 1 tree-like, 2 four-cycle (src/types.jl:180)
  * ntype[nq], types[nq*max_types]: typeHyb codes (2..5; type 1 dropped) of the

@@ -177,6 +177,14 @@ function pseudodeviance_grad!(e::Engine, x::Vector{Float64}, g::Vector{Float64})
     return f[]
 end
 
+"weighted draw of a quartet (weights deltaCF at x) for sampleEdgeQuartetWeighted, src/moves_snaq.jl:1443-1449: 1-based index"
+function sample_quartet(e::Engine, x::Vector{Float64}, u::Float64 = rand())
+    idx = Ref{Int64}(0)
+    check(e, ccall((:snaq_sample_quartets, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cint, Ref{Cdouble}, Ref{Int64}),
+                   e.ctx, length(x), x, 1, u, idx))
+    return idx[] + 1
+end
+
 "updateBL! (src/readquartetdata.jl:838-861) with the table built on the device; net must be a tree"
 function updateBL_device!(net::HybridNetwork, d::DataCF, e::Engine)
     SNaQ.parameters!(net)

@@ -1558,6 +1558,55 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
     }
 }
 
+// Weighted sampling of quartets (step 1 of sampleEdgeQuartetWeighted, src/moves_snaq.jl:1443-1449): inverse-CDF walk over
+// the deltaCF weights.  k_chunk_sums: one block per chunk of SQ_CHUNK weights, every thread adds its 16 consecutive weights
+// serially, then a fixed-order tree: the same bits on every run.  k_sample: thread 0 turns the chunk totals into running
+// totals (serial), then one thread per draw finds the chunk by bisection and walks it serially from the chunk's base.
+#define SQ_CHUNK 4096
+__global__ void __launch_bounds__(256) k_chunk_sums(const double *__restrict__ w, const int64_t nq, double *__restrict__ sums) {
+    __shared__ double red[8];
+    const int64_t base = (int64_t)blockIdx.x * SQ_CHUNK + (int64_t)threadIdx.x * (SQ_CHUNK / 256);
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < SQ_CHUNK / 256; k++) s += (base + k < nq) ? w[base + k] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) t += red[k];
+        sums[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(256) k_sample(const double *__restrict__ w, const int64_t nq, double *__restrict__ cum,
+                                                const int nchunks, const double *__restrict__ u, const int n,
+                                                long long *__restrict__ idx) {
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int c = 0; c < nchunks; c++) { t += cum[c]; cum[c] = t; }
+    }
+    __syncthreads();
+    const double total = cum[nchunks - 1];
+    for (int k = threadIdx.x; k < n; k += 256) {
+        const double t = u[k] * total;                       // t = rand() * sum(wv)
+        int lo = 0, hi = nchunks - 1;                        // first chunk whose running total reaches t (the last one if none)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cum[mid] >= t) hi = mid; else lo = mid + 1;
+        }
+        double cw = lo > 0 ? cum[lo - 1] : 0.0;
+        const int64_t i0 = (int64_t)lo * SQ_CHUNK, i1 = min(i0 + (int64_t)SQ_CHUNK, nq);
+        int64_t i = i0;
+        cw += w[i];
+        while (cw < t && i < i1 - 1) { i++; cw += w[i]; }    // `while cw < t && i < n` of the reference's walk
+        // rounding between the chunk total and the serial walk can leave cw < t at the end of a chunk that is not the last:
+        // the draw then belongs to the first quartet of positive weight after it
+        if (cw < t && i1 < nq) { i = i1; while (i < nq - 1 && !(w[i] > 0.0)) i++; }
+        idx[k] = i;
+    }
+}
+
 // updateBL! (src/readquartetdata.jl:838-861): per internal edge of a TREE, the number of data quartets whose internal
 // path is exactly that edge (one taxon in each of the four subtrees around it: edgesParts/makeTable, :866-889, :935-960)
 // and the sum of their observed CF of the tree's resolution.  Such a quartet has a one-pair program (D[v], D[parent v]).
@@ -2715,6 +2764,54 @@ int snaq_eval_quartets(snaq_ctx *ctx, int32_t nparams, const double *x, double *
     }
     cudaFree(d_e); if (d_l != d_dummy) cudaFree(d_l); cudaFree(d_d); cudaFree(d_dummy);
     if (rc) return rc;
+    if (st) { cudaMemsetAsync(ctx->d_status + 1, 0, sizeof(uint32_t), ctx->stream); return status_to_error(ctx, st); }
+    return SNAQ_OK;
+}
+
+int snaq_sample_quartets(snaq_ctx *ctx, int32_t nparams, const double *x, int32_t n, const double *u, int64_t *idx) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (!ctx->has_net) { ctx->err = "snaq_set_network has not been called"; return SNAQ_ENODATA; }
+    if (!x || nparams != ctx->H.nparams || n < 0 || (n > 0 && (!u || !idx))) { ctx->err = "bad arguments to snaq_sample_quartets"; return SNAQ_EINVAL; }
+    if (ctx->world > 1) { ctx->err = "snaq_sample_quartets is not available in quartet-sharded mode"; return SNAQ_EINVAL; }
+    for (int k = 0; k < n; k++)
+        if (!(u[k] >= 0.0 && u[k] < 1.0)) { ctx->err = "uniform draws must be in [0,1)"; return SNAQ_EINVAL; }
+    if (ctx->nq == 0) { ctx->err = "no quartets to sample from"; return SNAQ_ENODATA; }
+    int rc = check_x_host(ctx, 1, x);
+    if (rc) return rc;
+    if (n == 0) return SNAQ_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t nq = ctx->nq;
+    const int nchunks = (int)((nq + SQ_CHUNK - 1) / SQ_CHUNK);
+    rc = ensure(ctx, ctx->d_X, ctx->X_cap, (size_t)std::max(nparams, 1));
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->d_out, ctx->out_cap, 2);
+    if (rc) return rc;
+    double *d_w = nullptr, *d_cum = nullptr, *d_u = nullptr;
+    long long *d_idx = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_w, (size_t)nq * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_cum, (size_t)nchunks * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_u, (size_t)n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_idx, (size_t)n * sizeof(long long));
+    uint32_t st = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_X, x, sizeof(double) * nparams, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_u, u, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        rc = eval_device(ctx, 1, ctx->d_X, ctx->d_out, ctx->stream, nullptr, nullptr, d_w);     // deltaCF, the data's quartet order
+        if (!rc) {
+            k_chunk_sums<<<nchunks, 256, 0, ctx->stream>>>(d_w, nq, d_cum);
+            k_sample<<<1, 256, 0, ctx->stream>>>(d_w, nq, d_cum, nchunks, d_u, n, d_idx);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&st, ctx->d_status + 1, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(idx, d_idx, sizeof(long long) * n, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        }
+    }
+    cudaFree(d_w); cudaFree(d_cum); cudaFree(d_u); cudaFree(d_idx);
+    if (rc) return rc;
+    if (e != cudaSuccess) { ctx->err = std::string("snaq_sample_quartets: ") + cudaGetErrorString(e); return SNAQ_ECUDA; }
+    ctx->counters[2] += 8 * (nparams + n);
+    ctx->counters[3] += 8 * n;
+    ctx->counters[5] += 2;
     if (st) { cudaMemsetAsync(ctx->d_status + 1, 0, sizeof(uint32_t), ctx->stream); return status_to_error(ctx, st); }
     return SNAQ_OK;
 }

@@ -33,7 +33,7 @@ EXPORTS = ["snaq_create", "snaq_destroy", "snaq_last_error", "snaq_version", "sn
            "snaq_set_sampled", "snaq_set_network", "snaq_patch_network", "snaq_num_params", "snaq_get_params",
            "snaq_eval", "snaq_eval_device", "snaq_eval_quartets", "snaq_get_descriptors", "snaq_get_counters",
            "snaq_check_status", "snaq_measure_fp64_peak", "snaq_get_trace", "snaq_eval_grad", "snaq_optbl", "snaq_update_bl", "snaq_get_hasedge",
-           "snaq_eval_topologies", "snaq_optbl_topologies"]
+           "snaq_eval_topologies", "snaq_optbl_topologies", "snaq_sample_quartets"]
 
 
 class _OptblOpts(C.Structure):
@@ -191,6 +191,15 @@ class Engine:
         dl = np.zeros(self.nq) if "deltacf" in want else None
         self._chk(self.lib.snaq_eval_quartets(self.ctx, C.c_int32(x.size), _p(x), _p(e), _p(l), _p(dl)))
         return e, l, dl
+
+    def sample_quartets(self, x, u) -> np.ndarray:
+        """indices (0-based, data order) of quartets drawn with weights deltaCF at x, one per uniform draw in ``u``:
+        step 1 of sampleEdgeQuartetWeighted (src/moves_snaq.jl:1443-1449) without copying the weights to the host"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        u = np.ascontiguousarray(np.atleast_1d(u), dtype=np.float64)
+        idx = np.zeros(u.size, np.int64)
+        self._chk(self.lib.snaq_sample_quartets(self.ctx, C.c_int32(x.size), _p(x), C.c_int32(u.size), _p(u), _p(idx)))
+        return idx
 
     def eval_grad(self, x, want_hdiag=False):
         """objective and its gradient at x in one pass over the quartets (snaq_eval_grad)"""
