@@ -306,6 +306,12 @@ def main():
                 line["roofline_hbm"] = hbm_leg(S, eng.__class__, local, torch, peak_tf)
             except Exception as exc:  # noqa: BLE001
                 line["roofline_hbm"] = {"error": str(exc)[:200]}
+        # ---- secondary: candidate topologies optimised concurrently on this GPU (snaq_optbl_topologies)
+        if not args.no_hbm:
+            try:
+                line["candidates"] = candidates_leg(S, eng, taxa, qt, obs)
+            except Exception as exc:  # noqa: BLE001
+                line["candidates"] = {"error": str(exc)[:200]}
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             v, dt = cpu_port(S, net, taxa, qt, obs, Xh[: args.cpu_vectors], cores)
@@ -378,6 +384,33 @@ def dedup_leg(S, Engine, local, torch, taxa, qt, obs, flat, dX, dout, stream, fl
             t0 = time.perf_counter()
             _, r = e2.optbl(start, *tol)
             out["t100_optbl_" + name] = {"seconds": time.perf_counter() - t0, "fmin": r["fmin"], "nlaunches": r["nlaunches"]}
+    return out
+
+
+def candidates_leg(S, eng, taxa, qt, obs, ncand=32):
+    """optBL! of `ncand` random candidate topologies (0-2 hybrids) on the bench's own 30-taxon data: one context after the
+    other (workers = 1) against the worker pool of snaq_optbl_topologies.  The results are identical, only the
+    throughput changes."""
+    n = len(taxa)
+    flats, seed = [], 0
+    while len(flats) < ncand:
+        seed += 1
+        try:
+            flats.append(S.simulate.random_level1_network(n, seed % 3, 90000 + seed).flatten(taxa))
+        except S.SnaqError:
+            pass
+    out = {"workload": f"{ncand} random candidate topologies (0-2 hybrids) on the {n}-taxon table, search-time tolerances",
+           "host_cores": os.cpu_count()}
+    ref = None
+    for w in (1, 8, 16):
+        eng.optbl_topologies(flats[:w], workers=w)                 # untimed: creates the worker contexts
+        t0 = time.perf_counter()
+        res = eng.optbl_topologies(flats, workers=w)
+        dt = time.perf_counter() - t0
+        f = [r[1]["fmin"] for r in res]
+        ref = ref or f
+        out[f"workers_{w}"] = {"optbl_per_s": ncand / dt, "identical_to_workers_1": f == ref}
+    out["launches_per_optbl"] = float(np.mean([r[1]["nlaunches"] for r in res]))
     return out
 
 
