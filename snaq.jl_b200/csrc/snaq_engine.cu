@@ -1334,9 +1334,16 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
  * snaq_grad_backprop on the host (a few hundred rows).
  */
 #define QG_SCALE 4294967296.0
+#define QG_SMALL_GRID 32  /* grids up to this many blocks reduce their gradient rows through per-block rows, larger ones through atomics */
+#ifndef QG_RUN
+#define QG_RUN 4        /* consecutive 64-quartet tiles a warp takes before the next warp's run begins */
+#endif
+// The same pass for SMALL tables (less than half a 64-quartet class-A tile per warp): rows dealt to the warps one by one,
+// plain loads, per-block gradient rows added by the last block.  A small table is all latency: no ring to set up, no
+// atomics to drain, the shortest dependent chain per warp (k_eval_grad below is the streaming variant for large tables).
 template <bool WANT_H>
 __global__ void __launch_bounds__(256, 3)
-k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restrict__ prog2, const uint8_t *__restrict__ qhdr,
+k_eval_grad_small(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restrict__ prog2, const uint8_t *__restrict__ qhdr,
             const double2 *__restrict__ WA, const double4 *__restrict__ W, uint32_t nA1, uint32_t nA2, uint32_t a2base, uint32_t nQ,
             const double *__restrict__ X, const double *__restrict__ xconst, int nh, int nt, double *__restrict__ partial,
             double *__restrict__ out, const double *__restrict__ negw3, unsigned int *__restrict__ ticket,
@@ -1558,6 +1565,371 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
     }
 }
 
+template <bool WANT_H>
+__global__ void __launch_bounds__(256, 3)
+k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restrict__ prog2, const uint8_t *__restrict__ qhdr,
+            const double2 *__restrict__ WA, const double4 *__restrict__ W, uint32_t nA1, uint32_t nA2, uint32_t a2base, uint32_t nQ,
+            const double *__restrict__ X, const double *__restrict__ xconst, int nh, int nt, double *__restrict__ partial,
+            double *__restrict__ out, const double *__restrict__ negw3, unsigned int *__restrict__ ticket,
+            unsigned long long *__restrict__ gbins, double *__restrict__ gout, uint32_t *__restrict__ status, uint32_t *__restrict__ status_out,
+            const int use_xarg /* bit 0: x is in xarg; bit 1: no warp aggregation in the generic path; bit 2: TMA ring */,
+            const double *__restrict__ pen,
+            unsigned long long *__restrict__ trace, const __grid_constant__ XArg xarg) {
+    constexpr int BLOCK = 256;
+    extern __shared__ __align__(128) unsigned char smem[];
+    // optional phase timeline (SNAQ_TRACE=1): entry / prologue / A1 / A2 / G / partials written / exit
+    auto stamp = [&](int k) {
+        if (trace && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            trace[(size_t)blockIdx.x * 8 + k] = t;
+        }
+    };
+    stamp(0);
+    double *mt = reinterpret_cast<double *>(smem);                        // 48 doubles, 128-byte aligned
+    double *red = reinterpret_cast<double *>(smem + 384);                 // [8] warp sums (64 B)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 448);            // [8 warps][QD_NST] mbarriers (192 B)
+    uint2 *span = reinterpret_cast<uint2 *>(smem + 640);                  // [8 warps][QD_SPAN] staged programs
+    unsigned char *ring = smem + 640 + 8 * QD_SPAN * 8;                   // [8 warps][QD_NST][QD_STAGE_BYTES] class-A tiles
+    const bool use_ring = (use_xarg & 4) != 0;                            // the host sizes the shared memory accordingly
+    double *xs = reinterpret_cast<double *>(ring + (use_ring ? 8 * QD_NST * QD_STAGE_BYTES : 0));
+    const int n_full = T.n_full;
+    unsigned int *bins_lo = reinterpret_cast<unsigned int *>(xs + n_full);   // [n_full] low words
+    unsigned int *bins_hi = bins_lo + n_full;                                // [n_full] high words
+    unsigned int *hb_lo = bins_hi + n_full, *hb_hi = hb_lo + n_full;         // WANT_H: curvature bins (same format)
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    unsigned st = 0;
+    // class A (one- and two-chunk additive programs) is streamed through a warp-private ring of TMA bulk copies; every
+    // warp walks runs of consecutive 64-quartet tiles of the class (the class is sorted by program)
+    const unsigned gwarp = blockIdx.x * (BLOCK / 32) + warp, nwarps = gridDim.x * (BLOCK / 32);
+    const unsigned tA1 = (nA1 + QD_TQ - 1) / QD_TQ, tA2 = (nA2 + QD_TQ - 1) / QD_TQ, tA = tA1 + tA2;
+    // the k-th tile of this warp: runs of QG_RUN consecutive tiles, the runs dealt round-robin to the warps (consecutive
+    // tiles share programs, which is what the memo below lives on; dealing short runs evens out the cost per warp: a tile
+    // full of short program runs costs ten times a tile inside one long run)
+    // (small classes: shorter runs, so that every warp has a tile before any warp has two)
+    const unsigned run = max(1u, min((unsigned)QG_RUN, tA / nwarps));
+    auto tile_of = [&](unsigned k) { return (gwarp + (k / run) * nwarps) * run + k % run; };
+    uint64_t *wbar = bars + warp * QD_NST;
+    unsigned char *wring = ring + (size_t)warp * QD_NST * QD_STAGE_BYTES;
+    auto issue = [&](unsigned t, unsigned sg) {                           // lane 0 only: weight pairs, then program chunks
+        unsigned char *dst = wring + sg * QD_STAGE_BYTES;
+        if (t < tA1) {
+            const unsigned i0 = t * QD_TQ, n = min((unsigned)QD_TQ, nA1 - i0);
+            const unsigned pb = ((n + 1u) & ~1u) * 8u;
+            mbar_expect_tx(&wbar[sg], n * 16u + pb);
+            tma_load_1d(dst, WA + i0, n * 16u, &wbar[sg]);
+            tma_load_1d(dst + QD_TQ * 16, prog2 + i0, pb, &wbar[sg]);
+        } else {
+            const unsigned j0 = (t - tA1) * QD_TQ, n = min((unsigned)QD_TQ, nA2 - j0);
+            mbar_expect_tx(&wbar[sg], n * 32u);
+            tma_load_1d(dst, WA + nA1 + j0, n * 16u, &wbar[sg]);
+            tma_load_1d(dst + QD_TQ * 16, prog2 + a2base + 2u * j0, n * 16u, &wbar[sg]);
+        }
+    };
+    // a class of fewer than two tiles per warp is read with plain loads: the ring's set-up (barrier initialisation, fence,
+    // first copies) costs more than it hides there, and small tables are all latency
+    if (use_ring && lane == 0) {
+        for (int k = 0; k < QD_NST; k++) mbar_init(&wbar[k], 1);
+        for (unsigned k = 0; k < QD_NST; k++)
+            if (tile_of(k) < tA) issue(tile_of(k), k);
+    }
+    __syncwarp();
+    const SnaqMath M = load_math_tables(mt, (int)tid);
+    double *xraw = reinterpret_cast<double *>(bins_lo + (WANT_H ? 4 : 2) * n_full);     // [nparams] the candidate itself
+    for (int row = (int)tid; row < T.nparams; row += BLOCK) {
+        const double v = (use_xarg & 1) ? xarg.v[row] : X[row];
+        st |= range_check(v, (row >= nh && row < nh + nt) ? 1.0e300 : 1.0);
+        xraw[row] = v;
+    }
+    __syncthreads();
+    for (int row = (int)tid; row < n_full; row += BLOCK) {
+        xs[row] = snaq_expand_row(T, M, xraw, xconst, row);
+        bins_lo[row] = 0u;
+        bins_hi[row] = 0u;
+        if (WANT_H) { hb_lo[row] = 0u; hb_hi[row] = 0u; }
+    }
+    __syncthreads();
+    stamp(1);
+    const unsigned nul = (unsigned)T.n_xe;
+    double acc = 0.0;
+    auto addq = [&](unsigned slot, long long q) {
+        if (slot != nul) {
+            const unsigned lo = (unsigned)q, hi = (unsigned)((unsigned long long)q >> 32);
+            const unsigned old = atomicAdd(&bins_lo[slot], lo);
+            atomicAdd(&bins_hi[slot], hi + ((old + lo < old) ? 1u : 0u));
+        }
+    };
+    // generic path: the lanes of a warp mostly run the SAME program (the classes are sorted by term and program), so they
+    // add to the same slot at the same instruction; 32 atomics on one shared-memory word are served one after the other.
+    // Lanes that are converged here and hold the same slot sum their fixed-point values with integer warp reductions
+    // (exact, so the bins stay order independent) and the group's first lane issues the one atomic.
+    const bool agg_on = (use_xarg & 2) == 0;                  // off for deduplicated (neighbouring programs all differ) and small tables
+    auto agg = [&](unsigned slot, long long q, bool curv) {
+        // (only the all-equal case is aggregated: shuffle + vote; a general match.any costs more than the conflicts)
+        unsigned peers = 1u << lane;
+        if (agg_on) {
+            const unsigned act = __activemask();
+            const unsigned s0 = __shfl_sync(act, slot, __ffs(act) - 1);
+            if (__all_sync(act, slot == s0)) peers = act;
+        }
+        if (peers != (1u << lane)) {
+            const unsigned l0 = (unsigned)(q & 0x1FFFFFll), l1 = (unsigned)((q >> 21) & 0x1FFFFFll);
+            const int l2 = (int)(q >> 42);
+            const unsigned s0 = __reduce_add_sync(peers, l0), s1 = __reduce_add_sync(peers, l1);
+            const int s2 = __reduce_add_sync(peers, l2);
+            if (lane != (unsigned)(__ffs(peers) - 1)) return;
+            q = (long long)s0 + ((long long)s1 << 21) + ((long long)s2 << 42);
+        }
+        if (q == 0) return;
+        const unsigned lo = (unsigned)q, hi = (unsigned)((unsigned long long)q >> 32);
+        unsigned *blo = curv ? hb_lo : bins_lo, *bhi = curv ? hb_hi : bins_hi;
+        const unsigned old = atomicAdd(&blo[slot], lo);
+        atomicAdd(&bhi[slot], hi + ((old + lo < old) ? 1u : 0u));
+    };
+    auto add = [&](unsigned slot, double v) { if (slot != nul) agg(slot, __double2ll_rn(v * QG_SCALE), false); };
+    auto addhq = [&](unsigned slot, long long q) {
+        if (WANT_H && slot != nul) {
+            const unsigned lo = (unsigned)q, hi = (unsigned)((unsigned long long)q >> 32);
+            const unsigned old = atomicAdd(&hb_lo[slot], lo);
+            atomicAdd(&hb_hi[slot], hi + ((old + lo < old) ? 1u : 0u));
+        }
+    };
+    auto addh = [&](unsigned slot, double v) { if (WANT_H && slot != nul) agg(slot, __double2ll_rn(v * QG_SCALE), true); };
+    // additive quartet: everything that depends on the program only (t -> log of the major CF, t1 + log 3, the two
+    // derivative factors); the quartet's own weights enter linearly
+    struct TreeConsts { double L, T, r, h; bool in; };
+    auto tree_consts = [&](double t) {
+        TreeConsts k;
+        const double t1 = snaq_clamp10(t);
+        const double a = 2.0 / 3.0 * snaq_exp(-t1, M);
+        const double major = 1.0 - a;
+        k.L = snaq_log_pos(major, M);
+        k.T = t1 + SNAQ_K_LOG3;
+        k.r = a / major;
+        k.h = k.r / major;
+        k.in = t <= 10.0;
+        return k;
+    };
+    // A warp holds 32 CONSECUTIVE entries of the table, and class A is sorted by program: most of the time the 32 lanes
+    // read the SAME slots.  wadd: when a slot is warp-uniform the 32 values are summed with integer warp reductions (three
+    // 21-bit limbs, REDUX) and lane 0 issues ONE atomic; otherwise every lane adds its own.
+    auto warp_sum = [&](long long q) {
+        const unsigned l0 = (unsigned)(q & 0x1FFFFFll), l1 = (unsigned)((q >> 21) & 0x1FFFFFll);
+        const int l2 = (int)(q >> 42);
+        const unsigned s0 = __reduce_add_sync(0xffffffffu, l0), s1 = __reduce_add_sync(0xffffffffu, l1);
+        const int s2 = __reduce_add_sync(0xffffffffu, l2);
+        return (long long)s0 + ((long long)s1 << 21) + ((long long)s2 << 42);
+    };
+    auto wadd = [&](unsigned slot, long long q, long long hq) {          // called by all 32 lanes
+        const unsigned s0 = __shfl_sync(0xffffffffu, slot, 0);
+        if (__all_sync(0xffffffffu, slot == s0)) {
+            if (s0 == nul) return;
+            const long long tq = warp_sum(q);
+            long long th = 0;
+            if (WANT_H) th = warp_sum(hq);
+            if (lane == 0) { if (tq != 0) addq(s0, tq); if (WANT_H && th != 0) addhq(s0, th); }
+        } else {
+            if (q != 0) addq(slot, q);
+            if (WANT_H && hq != 0) addhq(slot, hq);
+        }
+    };
+    // ---- region A: the warp's tiles, 32 consecutive entries (a row) at a time --------------------------------
+    // A row usually holds ONE program, and so do the rows after it: the program's constants are computed once (memo) and
+    // every lane keeps its quartets' fixed-point derivative sums in registers; the warp reduction and the atomics on the
+    // block's bins happen only when the program changes.  The sums are integers: the bins do not depend on where the
+    // flushes fall.  A one-chunk program is handled as a two-chunk program whose second chunk reads the null slot.
+    {
+        const unsigned nullpair = nul * 0x10001u;
+        TreeConsts mk{0.0, 0.0, 0.0, 0.0, false};
+        long long gacc = 0, hacc = 0;
+        bool m_on = false;
+        uint4 mp = make_uint4(0u, 0u, 0u, 0u);
+        auto slots = [&](const uint4 &c, unsigned *sl) {
+            sl[0] = c.x & 0xffffu; sl[1] = c.x >> 16; sl[2] = c.y & 0xffffu; sl[3] = c.y >> 16;
+            sl[4] = c.z & 0xffffu; sl[5] = c.z >> 16; sl[6] = c.w & 0xffffu; sl[7] = c.w >> 16;
+        };
+        auto tsum = [&](const unsigned *sl) {
+            double ta = xs[sl[0]] - xs[sl[1]], tb2 = xs[sl[2]] - xs[sl[3]];
+            ta += xs[sl[4]] - xs[sl[5]];
+            tb2 += xs[sl[6]] - xs[sl[7]];
+            return ta + tb2;
+        };
+        auto flush = [&]() {
+            if (!m_on) return;
+            const long long tq = warp_sum(gacc);
+            long long th = 0;
+            if (WANT_H) th = warp_sum(hacc);
+            if (lane == 0) {
+                unsigned sl[8];
+                slots(mp, sl);
+#pragma unroll
+                for (int k = 0; k < 8; k += 2) {
+                    if (tq != 0) { addq(sl[k], tq); addq(sl[k + 1], -tq); }
+                    if (WANT_H && th != 0) { addhq(sl[k], th); addhq(sl[k + 1], -th); }
+                }
+            }
+            gacc = 0; hacc = 0;
+        };
+        unsigned sg = 0, phase = 0;
+#pragma unroll 1
+        for (unsigned kt = 0;; kt++) {
+            const unsigned t = tile_of(kt);
+            if (t >= tA) break;
+            if (use_ring) mbar_wait(&wbar[sg], phase);
+            const unsigned char *stg = wring + sg * QD_STAGE_BYTES;
+            const bool one = t < tA1;
+            const unsigned q0 = one ? t * QD_TQ : (t - tA1) * QD_TQ;     // first entry of the tile inside its sub-class
+            const unsigned n = one ? min((unsigned)QD_TQ, nA1 - q0) : min((unsigned)QD_TQ, nA2 - q0);
+            // the tile's weight pairs and programs: in the stage (ring) or in global memory (plain loads)
+            const double2 *sw = use_ring ? reinterpret_cast<const double2 *>(stg) : WA + (one ? q0 : nA1 + q0);
+            const uint2 *sp2 = use_ring ? reinterpret_cast<const uint2 *>(stg + QD_TQ * 16) : prog2 + q0;
+            const uint4 *sp4 = use_ring ? reinterpret_cast<const uint4 *>(stg + QD_TQ * 16)
+                                        : reinterpret_cast<const uint4 *>(prog2 + a2base) + q0;
+#pragma unroll 1
+            for (unsigned r0 = 0; r0 < n; r0 += 32u) {
+                const unsigned idx = r0 + lane;
+                const bool ok = idx < n;
+                const double2 w = ok ? sw[idx] : make_double2(0.0, 0.0);
+                uint4 c = make_uint4(0u, 0u, nullpair, nullpair);
+                if (ok) {
+                    if (one) { const uint2 c2 = sp2[idx]; c.x = c2.x; c.y = c2.y; }
+                    else c = sp4[idx];
+                }
+                uint4 pz;                                                // the row's first program
+                pz.x = __shfl_sync(0xffffffffu, c.x, 0); pz.y = __shfl_sync(0xffffffffu, c.y, 0);
+                pz.z = __shfl_sync(0xffffffffu, c.z, 0); pz.w = __shfl_sync(0xffffffffu, c.w, 0);
+                if (!ok) c = pz;                                         // lanes past the end: zero weights, add nothing
+                if (__all_sync(0xffffffffu, c.x == pz.x && c.y == pz.y && c.z == pz.z && c.w == pz.w)) {
+                    if (!(m_on && pz.x == mp.x && pz.y == mp.y && pz.z == mp.z && pz.w == mp.w)) {
+                        flush();
+                        mp = pz; m_on = true;
+                        unsigned sl[8];
+                        slots(pz, sl);
+                        mk = tree_consts(tsum(sl));
+                    }
+                    acc += fma(w.x, mk.L, -w.y * mk.T);
+                    if (mk.in) {
+                        gacc += __double2ll_rn(fma(mk.r, w.x, -w.y) * QG_SCALE);
+                        if (WANT_H) hacc += __double2ll_rn(mk.h * w.x * QG_SCALE);
+                    }
+                } else {
+                    flush();
+                    m_on = false;
+                    unsigned sl[8];
+                    slots(c, sl);
+                    const TreeConsts k = tree_consts(tsum(sl));
+                    acc += fma(w.x, k.L, -w.y * k.T);
+                    const long long gq = k.in ? __double2ll_rn(fma(k.r, w.x, -w.y) * QG_SCALE) : 0ll;
+                    const long long hq = (WANT_H && k.in) ? __double2ll_rn(k.h * w.x * QG_SCALE) : 0ll;
+#pragma unroll
+                    for (int q = 0; q < 8; q += 2) { wadd(sl[q], gq, hq); wadd(sl[q + 1], -gq, -hq); }
+                }
+            }
+            __syncwarp();                                                  // every lane is done with stage sg
+            if (use_ring && lane == 0 && tile_of(kt + QD_NST) < tA) issue(tile_of(kt + QD_NST), sg);
+            if (++sg == QD_NST) { sg = 0; phase ^= 1u; }
+        }
+        flush();
+    }
+    stamp(2);
+    stamp(3);
+    // ---- region G: everything else through the generic evaluator ------------------------------------------
+    {
+        uint2 *wspan = span + warp * QD_SPAN;
+#pragma unroll 1
+        for (unsigned ib = nA1 + nA2 + gwarp * 32u; ib < nQ; ib += nwarps * 32u) {
+            const unsigned i = ib + lane;
+            const bool active = i < nQ;
+            const unsigned ilast = min(ib + 32u, nQ);
+            const uint32_t o0 = active ? __ldg(off + i) : 0u, o1 = active ? __ldg(off + i + 1) : 0u;
+            const unsigned hdr = active ? (unsigned)qhdr[i] : 0u;
+            const double4 w4 = active ? W[i] : make_double4(0, 0, 0, 0);
+            const uint32_t s0 = __shfl_sync(0xffffffffu, o0, 0);
+            const uint32_t s1 = __ldg(off + ilast);
+            const bool staged = (s1 - s0) <= (uint32_t)QD_SPAN;
+            __syncwarp();
+            if (staged) for (uint32_t c = s0 + lane; c < s1; c += 32u) wspan[c - s0] = __ldg(prog2 + c);
+            __syncwarp();
+            if (active) {
+                const double w[4] = {w4.x, w4.y, w4.z, w4.w};
+                const uint16_t *pc = reinterpret_cast<const uint16_t *>(staged ? wspan + (o0 - s0) : prog2 + o0);
+                const XRow xf{xs};
+                acc += snaq_grad_quartet(hdr, pc, (int)(o1 - o0) * 4, xf, M, w, nul, add, addh, st, pen ? pen + 4 * (size_t)i : nullptr);
+            }
+        }
+    }
+    if (st) atomicOr(status, st);
+    stamp(4);
+    // ---- epilogue ---------------------------------------------------------------------------------------------
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();                                                      // also: every atomic on bins is done
+    stamp(5);
+    if (tid == 0) {
+        double ssum = 0.0;
+#pragma unroll
+        for (int k = 0; k < BLOCK / 32; k++) ssum += red[k];
+        partial[blockIdx.x] = ssum;
+    }
+    const int nrows = WANT_H ? 2 * n_full : n_full;                       // the curvature bins follow the gradient bins
+    // the block's bins go to the grid's bins with 64-bit integer reductions (order independent, so bit-reproducible):
+    // gbins[row] takes the fraction words, gbins[nrows + row] the sign-extended integer words, each with 2^31 blocks of
+    // headroom; the last block only converts (no serial pass over per-block rows)
+    // (a grid of at most QG_SMALL_GRID blocks writes its rows to gpart instead and the last block adds them in block order:
+    // a handful of plain stores and loads is quicker than waiting for the atomics to drain)
+    const bool small_grid = gridDim.x <= QG_SMALL_GRID;
+    double *gpart = reinterpret_cast<double *>(gbins + 4 * (size_t)n_full);
+    for (int row = (int)tid; row < nrows; row += BLOCK) {
+        const unsigned lo = bins_lo[row + (row >= n_full ? n_full : 0)], hi = bins_hi[row + (row >= n_full ? n_full : 0)];
+        if (small_grid) {
+            gpart[(size_t)blockIdx.x * nrows + row] = (double)(long long)(((unsigned long long)hi << 32) | (unsigned long long)lo) * (1.0 / QG_SCALE);
+        } else {
+            if (lo) atomicAdd(gbins + row, (unsigned long long)lo);
+            if (hi) atomicAdd(gbins + nrows + row, (unsigned long long)(long long)(int)hi);
+        }
+    }
+    stamp(7);
+    __threadfence();
+    __shared__ unsigned int s_last;
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double sp = 0.0;
+        for (unsigned b = tid; b < gridDim.x; b += BLOCK) sp += __ldcg(partial + b);
+        for (int o = 16; o > 0; o >>= 1) sp += __shfl_down_sync(0xffffffffu, sp, o);
+        if (lane == 0) red[warp] = sp;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int k = 0; k < BLOCK / 32; k++) tot += red[k];
+            out[0] = -tot - __ldcg(negw3);
+        }
+        for (int row = (int)tid; row < nrows; row += BLOCK) {
+            double s = 0.0;
+            if (small_grid) {
+                for (unsigned b = 0; b < gridDim.x; b++) s += __ldcg(gpart + (size_t)b * nrows + row);
+            } else {
+                const unsigned long long fr = __ldcg(gbins + row);
+                const long long in = (long long)__ldcg(gbins + nrows + row);
+                gbins[row] = 0ull;                                        // ready for the next launch
+                gbins[nrows + row] = 0ull;
+                s = (double)in + (double)fr * (1.0 / QG_SCALE);
+            }
+            gout[row] = row < n_full ? -s : s;                            // f = -(sum of v); the curvature is already that of f
+        }
+        __threadfence_system();                          // every thread's rows are in host memory before the flag
+        __syncthreads();
+        if (tid == 0) {
+            *ticket = 0u;
+            if (status_out) *reinterpret_cast<volatile uint32_t *>(status_out) = *reinterpret_cast<volatile uint32_t *>(status) | SNAQ_S_DONE;
+        }
+    }
+    stamp(6);
+}
+
 // Weighted sampling of quartets (step 1 of sampleEdgeQuartetWeighted, src/moves_snaq.jl:1443-1449): inverse-CDF walk over
 // the deltaCF weights.  k_chunk_sums: one block per chunk of SQ_CHUNK weights, every thread adds its 16 consecutive weights
 // serially, then a fixed-order tree: the same bits on every run.  k_sample: thread 0 turns the chunk totals into running
@@ -1754,7 +2126,8 @@ struct snaq_ctx {
     double *d_XF = nullptr; size_t XF_cap = 0;   // expanded parameter vectors [P][n_full]
     double *d_out = nullptr; size_t out_cap = 0;
     double *d_partial = nullptr; size_t partial_cap = 0;
-    double *d_gpart = nullptr; size_t gpart_cap = 0;     // k_eval_grad: [blocks][n_full] per-block gradient rows
+    double *d_gpart = nullptr; size_t gpart_cap = 0;     // k_eval_grad_small: [blocks][rows] per-block gradient rows
+    unsigned long long *d_gbins = nullptr; size_t gbins_cap = 0;   // k_eval_grad: [2][rows] grid-wide fixed-point gradient bins (zero between launches)
     double *d_gout = nullptr; size_t gout_cap = 0;       // [1 + n_full]: f, then d f / d xf
     double *h_pin = nullptr; size_t pin_cap = 0;
     int sm_count = 148;
@@ -2179,7 +2552,7 @@ int snaq_destroy(snaq_ctx *ctx) {
     cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_WA); cudaFree(ctx->d_wpart); cudaFree(ctx->d_negw3); cudaFree(ctx->d_status); cudaFree(ctx->d_total); cudaFree(ctx->d_ticket); cudaFree(ctx->d_trace);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_uidx); cudaFree(ctx->d_rstart); cudaFree(ctx->d_ulen); cudaFree(ctx->d_off_u); cudaFree(ctx->d_qhdr_u);
     cudaFree(ctx->d_prog_u); cudaFree(ctx->d_W_u); cudaFree(ctx->d_WA_u); cudaFree(ctx->d_wpart_u); cudaFree(ctx->d_negw3_u); cudaFree(ctx->d_pen_u);
-    cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_XF); cudaFree(ctx->d_out); cudaFree(ctx->d_partial); cudaFree(ctx->d_gpart); cudaFree(ctx->d_gout);
+    cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_XF); cudaFree(ctx->d_out); cudaFree(ctx->d_partial); cudaFree(ctx->d_gbins); cudaFree(ctx->d_gpart); cudaFree(ctx->d_gout);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_qhdr); cudaFree(ctx->d_len4); cudaFree(ctx->d_iota); cudaFree(ctx->d_cls);
     cudaFree(ctx->d_cls_sorted);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -2634,17 +3007,33 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
     if (hdiag) for (int i = 0; i < nparams; i++) hdiag[i] = 0.0;
     if (ctx->nq == 0) { *f = 0.0; return SNAQ_OK; }
     const int nrows = hdiag ? 2 * n_full : n_full;
-    const size_t smem = 512 + 8 * QD_SPAN * 8 + (size_t)n_full * 8 + (size_t)nrows * 8 + (size_t)nparams * 8;
-    if (smem > 100 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_grad"; return SNAQ_EINVAL; }
+    const size_t smem_base = 640 + 8 * QD_SPAN * 8 + (size_t)n_full * 8 + (size_t)nrows * 8 + (size_t)nparams * 8;
+    if (smem_base + 8 * QD_NST * QD_STAGE_BYTES > 110 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_grad"; return SNAQ_EINVAL; }
     EvalTable tb = eval_table(ctx, false);
     if (ctx->dedup) tb.nA1 = tb.nA2 = 0;                    // see launch_direct
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((tb.nq + 255) / 256, (int64_t)ctx->sm_count * 3));
+    // the streaming kernel (class-A ring, program memo, grid-wide integer bins) pays from half a 64-quartet tile per warp on
+    // (measured: 50 taxa and up); below that k_eval_grad_small
+    const int64_t tilesA = (tb.nA1 + QD_TQ - 1) / QD_TQ + (tb.nA2 + QD_TQ - 1) / QD_TQ;
+    const bool use_ring = 2 * tilesA >= (int64_t)grid * 8;
+    const bool agg_on = !ctx->dedup && tb.nq >= 65536;
+    // (k_eval_grad_small lays its shared memory out without the barrier area: 128 bytes less)
+    const size_t smem = use_ring ? smem_base + 8 * QD_NST * QD_STAGE_BYTES : smem_base - 128;
+    if (!use_ring) {
+        rc = ensure(ctx, ctx->d_gpart, ctx->gpart_cap, (size_t)grid * nrows);
+        if (rc) return rc;
+    }
+    const int kflags = (agg_on ? 0 : 2) | (use_ring ? 4 : 0);
     rc = ensure(ctx, ctx->d_X, ctx->X_cap, (size_t)std::max(nparams, 1));
     if (rc) return rc;
     rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)grid);
     if (rc) return rc;
-    rc = ensure(ctx, ctx->d_gpart, ctx->gpart_cap, (size_t)grid * nrows);
-    if (rc) return rc;
+    const size_t gb_need = (size_t)(4 + 2 * QG_SMALL_GRID) * n_full;      // [2][2 n_full] grid bins (curvature variant too) + gpart of a small grid
+    if (gb_need > ctx->gbins_cap || !ctx->d_gbins) {                      // zero once, the kernel re-zeroes its bins
+        rc = ensure(ctx, ctx->d_gbins, ctx->gbins_cap, gb_need);
+        if (rc) return rc;
+        CK(cudaMemsetAsync(ctx->d_gbins, 0, ctx->gbins_cap * sizeof(unsigned long long), ctx->stream));
+    }
     rc = ensure(ctx, ctx->d_gout, ctx->gout_cap, (size_t)nrows + 1);
     if (rc) return rc;
     rc = ensure_pin(ctx, (size_t)nparams + nrows + 4);
@@ -2660,14 +3049,25 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
         std::memcpy(ctx->h_pin, x, sizeof(double) * nparams);
         CK(cudaMemcpyAsync(ctx->d_X, ctx->h_pin, sizeof(double) * nparams, cudaMemcpyHostToDevice, ctx->stream));
     }
+    if (ctx->d_trace) ctx->trace_blocks = use_ring ? grid : 0;
 #define LAUNCH_GRAD(WH)                                                                                                        \
     do {                                                                                                                       \
-        CK(raise_smem_limit(k_eval_grad<WH>, smem));                                                                             \
-        k_eval_grad<WH><<<grid, 256, smem, ctx->stream>>>(                                                                      \
-            ctx->T, tb.off, reinterpret_cast<const uint2 *>(tb.prog), tb.qhdr, tb.WA,                                           \
-            reinterpret_cast<const double4 *>(tb.W), (uint32_t)tb.nA1, (uint32_t)tb.nA2,                                        \
-            (uint32_t)(tb.nA1 + (tb.nA1 & 1)), (uint32_t)tb.nq, ctx->d_X, ctx->d_xconst, H.nh, H.nt, ctx->d_partial,            \
-            h_g, tb.negw3, ctx->d_ticket, ctx->d_gpart, h_g + 1, ctx->d_status + 1, h_st, by_arg ? 1 : 0, tb.pen, ctx->xarg);        \
+        if (use_ring) {                                                                                                        \
+            CK(raise_smem_limit(k_eval_grad<WH>, smem));                                                                         \
+            k_eval_grad<WH><<<grid, 256, smem, ctx->stream>>>(                                                                  \
+                ctx->T, tb.off, reinterpret_cast<const uint2 *>(tb.prog), tb.qhdr, tb.WA,                                       \
+                reinterpret_cast<const double4 *>(tb.W), (uint32_t)tb.nA1, (uint32_t)tb.nA2,                                    \
+                (uint32_t)(tb.nA1 + (tb.nA1 & 1)), (uint32_t)tb.nq, ctx->d_X, ctx->d_xconst, H.nh, H.nt, ctx->d_partial,        \
+                h_g, tb.negw3, ctx->d_ticket, ctx->d_gbins, h_g + 1, ctx->d_status + 1, h_st, (by_arg ? 1 : 0) | kflags,        \
+                tb.pen, ctx->d_trace, ctx->xarg);                                                                               \
+        } else {                                                                                                               \
+            CK(raise_smem_limit(k_eval_grad_small<WH>, smem));                                                                   \
+            k_eval_grad_small<WH><<<grid, 256, smem, ctx->stream>>>(                                                            \
+                ctx->T, tb.off, reinterpret_cast<const uint2 *>(tb.prog), tb.qhdr, tb.WA,                                       \
+                reinterpret_cast<const double4 *>(tb.W), (uint32_t)tb.nA1, (uint32_t)tb.nA2,                                    \
+                (uint32_t)(tb.nA1 + (tb.nA1 & 1)), (uint32_t)tb.nq, ctx->d_X, ctx->d_xconst, H.nh, H.nt, ctx->d_partial,        \
+                h_g, tb.negw3, ctx->d_ticket, ctx->d_gpart, h_g + 1, ctx->d_status + 1, h_st, by_arg ? 1 : 0, tb.pen, ctx->xarg); \
+        }                                                                                                                      \
     } while (0)
     if (hdiag) LAUNCH_GRAD(true); else LAUNCH_GRAD(false);
 #undef LAUNCH_GRAD
