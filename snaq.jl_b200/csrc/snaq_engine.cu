@@ -1338,7 +1338,7 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
 #ifndef QG_RUN
 #define QG_RUN 4        /* consecutive 64-quartet tiles a warp takes before the next warp's run begins */
 #endif
-// The same pass for SMALL tables (less than half a 64-quartet class-A tile per warp): rows dealt to the warps one by one,
+// The same pass for SMALL tables (fewer than 1024 class-A tiles of 64 quartets): rows dealt to the warps one by one,
 // plain loads, per-block gradient rows added by the last block.  A small table is all latency: no ring to set up, no
 // atomics to drain, the shortest dependent chain per warp (k_eval_grad below is the streaming variant for large tables).
 template <bool WANT_H>
@@ -3012,10 +3012,10 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
     EvalTable tb = eval_table(ctx, false);
     if (ctx->dedup) tb.nA1 = tb.nA2 = 0;                    // see launch_direct
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((tb.nq + 255) / 256, (int64_t)ctx->sm_count * 3));
-    // the streaming kernel (class-A ring, program memo, grid-wide integer bins) pays from half a 64-quartet tile per warp on
-    // (measured: 50 taxa and up); below that k_eval_grad_small
+    // the streaming kernel (class-A ring, program memo, grid-wide integer bins) pays from about 65,000 class-A quartets on
+    // (measured: 50 taxa and up; at 30 taxa the two are equal, below the small kernel wins by 4-8 us); else k_eval_grad_small
     const int64_t tilesA = (tb.nA1 + QD_TQ - 1) / QD_TQ + (tb.nA2 + QD_TQ - 1) / QD_TQ;
-    const bool use_ring = 2 * tilesA >= (int64_t)grid * 8;
+    const bool use_ring = tilesA >= 1024;
     const bool agg_on = !ctx->dedup && tb.nq >= 65536;
     // (k_eval_grad_small lays its shared memory out without the barrier area: 128 bytes less)
     const size_t smem = use_ring ? smem_base + 8 * QD_NST * QD_STAGE_BYTES : smem_base - 128;
