@@ -32,8 +32,8 @@ NET_SEED, OBS_SEED, X_SEED = 20261020, 1, 7
 FLOP_TREE, FLOP_T5_EXTRA, FLOP_PER_TERM = 110.0, 75.0, 90.0
 
 
-NCU_TRAFFIC_LANES_BYTES = 4463360          # profiles/r01g_ncu_summary.md: 4.463360 MB read, 0 written per launch
-NCU_TRAFFIC_DIRECT_BYTES = 113900000       # profiles/r01g_ncu_summary.md: 109.73 MB read + 4.2 MB written per launch
+NCU_TRAFFIC_LANES_BYTES = 4477952          # profiles/r01h_ncu_summary.md: 4.477952 MB read, 0 written per launch
+NCU_TRAFFIC_DIRECT_BYTES = 113707776       # profiles/r01h_ncu_summary.md: 109.73 MB read + 3.97 MB written per launch
 
 
 def workload(ntaxa=NTAXA, nhyb=NHYB, nvec=NVEC):
