@@ -2194,6 +2194,7 @@ static cudaError_t wait_done(cudaStream_t stream, volatile uint32_t *flag) {
 #if defined(__x86_64__)
         __builtin_ia32_pause();
 #endif
+        if (spin > 8192u && (spin & 0x3ffu) == 0) std::this_thread::yield();   // long kernel: let other host threads (workers) run
     }
     std::atomic_thread_fence(std::memory_order_acquire);
     *flag &= ~SNAQ_S_DONE;
