@@ -3009,14 +3009,14 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
     if (ctx->nq == 0) { *f = 0.0; return SNAQ_OK; }
     const int nrows = hdiag ? 2 * n_full : n_full;
     const size_t smem_base = 640 + 8 * QD_SPAN * 8 + (size_t)n_full * 8 + (size_t)nrows * 8 + (size_t)nparams * 8;
-    if (smem_base + 8 * QD_NST * QD_STAGE_BYTES > 110 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_grad"; return SNAQ_EINVAL; }
+    if (smem_base - 128 > 100 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_grad"; return SNAQ_EINVAL; }
     EvalTable tb = eval_table(ctx, false);
     if (ctx->dedup) tb.nA1 = tb.nA2 = 0;                    // see launch_direct
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((tb.nq + 255) / 256, (int64_t)ctx->sm_count * 3));
     // the streaming kernel (class-A ring, program memo, grid-wide integer bins) pays from about 65,000 class-A quartets on
     // (measured: 50 taxa and up; at 30 taxa the two are equal, below the small kernel wins by 4-8 us); else k_eval_grad_small
     const int64_t tilesA = (tb.nA1 + QD_TQ - 1) / QD_TQ + (tb.nA2 + QD_TQ - 1) / QD_TQ;
-    const bool use_ring = tilesA >= 1024;
+    const bool use_ring = tilesA >= 1024 && smem_base + 8 * QD_NST * QD_STAGE_BYTES <= 110 * 1024;   // (a very large network: no room for the ring)
     const bool agg_on = !ctx->dedup && tb.nq >= 65536;
     // (k_eval_grad_small lays its shared memory out without the barrier area: 128 bytes less)
     const size_t smem = use_ring ? smem_base + 8 * QD_NST * QD_STAGE_BYTES : smem_base - 128;
