@@ -55,6 +55,49 @@ def test_gradient_matches_central_differences_of_the_oracle(oracle, seed):
     assert f2 == f and np.array_equal(g, g2)
 
 
+@pytest.mark.parametrize("n,h,seed", [(45, 3, 11), (60, 4, 12)])
+def test_streaming_gradient_kernel_on_large_tables(oracle, n, h, seed):
+    """tables with more than 65,536 additive quartets take k_eval_grad (TMA ring, program memo, grid-wide integer bins);
+    the deduplicated engine takes the small kernel and the generic path for every entry: two independent routes to the
+    same gradient and curvature, plus central differences of the oracle on a few coordinates"""
+    eng, flat, qt, obs, x0, upper = make(n, h, seed, ngenes=80)
+    rng = np.random.default_rng(seed)
+    mask = (rng.uniform(size=len(qt)) < 0.8).astype(np.uint8)
+    eng.set_sampled(mask)
+    x = np.clip(simulate.parameter_batch(x0, upper, 4, seed)[3], 1e-3, upper - 1e-3)
+    f, g, hd = eng.eval_grad(x, want_hdiag=True)
+    f1, g1 = eng.eval_grad(x)
+    assert f1 == f and np.array_equal(g1, g)
+    assert abs(f - eng.eval(x)[0]) <= 1e-11 * abs(f)
+    want = oracle.evaluate(flat, qt, obs, x[None], sampled=mask)[0]
+    assert abs(f - want) <= 1e-10 * abs(want)
+    ded = S.Engine(0, dedup=True)
+    ded.set_data(S.DataCF([f"t{i + 1}" for i in range(n)], qt, obs))
+    ded.set_sampled(mask)
+    ded.set_network(flat)
+    fd_, gd, hdd = ded.eval_grad(x, want_hdiag=True)
+    assert abs(fd_ - f) <= 1e-10 * abs(f)
+    assert np.max(np.abs(g - gd) / (1 + np.abs(gd))) < 1e-7
+    assert np.max(np.abs(hd - hdd) / (1 + np.abs(hdd))) < 1e-7
+    coords = rng.choice(len(x), size=6, replace=False)
+    hstep = 1e-6
+    X = np.tile(x, (2 * len(coords), 1))
+    for k, i in enumerate(coords):
+        X[2 * k, i] += hstep
+        X[2 * k + 1, i] -= hstep
+    ff = oracle.evaluate(flat, qt, obs, X, sampled=mask)
+    gfd = (ff[0::2] - ff[1::2]) / (2 * hstep)
+    noise = 4e-15 * abs(want) / (2 * hstep)
+    assert np.max(np.abs(g[coords] - gfd) / (1 + np.abs(gfd))) < 2e-5 + noise
+    # out-of-range candidates are reported by the streaming kernel too
+    bad = x.copy()
+    bad[0] = -0.1
+    with pytest.raises(S.SnaqError):
+        eng.eval_grad(bad)
+    f3, g3 = eng.eval_grad(x)                                   # and the bins are clean for the next call
+    assert f3 == f and np.array_equal(g3, g)
+
+
 def test_curvature_diagonal_is_the_hessian_diagonal_on_a_tree(oracle):
     eng, flat, qt, obs, x0, upper = make(12, 0, 41, ngenes=80)
     x = np.clip(x0 * 1.1, 1e-2, upper - 1e-2)
