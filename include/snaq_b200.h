@@ -235,9 +235,9 @@ int snaq_update_bl(snaq_ctx *ctx, int64_t *nquartets, double *edgeL);
  * The reference copies all nq weights to a vector per proposal and calls StatsBase.sample(indices, Weights(w), 1):
  * for one draw that is the inverse-CDF walk `t = rand()*sum(w); i = first index with cumsum(w)[i] >= t`.  Here the
  * weights never leave the device: idx[k] (0-based, the data's quartet order) is that index for the caller's uniform
- * draw u[k] in [0,1).  The prefix sums are formed in fixed chunks of 4096 quartets (serial inside a chunk and over the
- * chunk totals), so the result is reproducible and equals the serial walk unless u*sum falls within rounding distance
- * of a boundary.  Not available on a quartet-sharded context.                                                      */
+ * draw u[k] in [0,1).  The prefix sums are formed in fixed chunks of 4096 quartets (chunk totals added serially, a
+ * chunk walked 32 quartets at a time in a fixed order), so the result is reproducible and equals the serial walk
+ * unless u*sum falls within rounding distance of a boundary.  Not available on a quartet-sharded context.            */
 int snaq_sample_quartets(snaq_ctx *ctx, int32_t nparams, const double *x, int32_t n, const double *u, int64_t *idx);
 
 /* ---- descriptors for parity checks ------------------------ */

@@ -13,7 +13,7 @@ import numpy as np
 import snaq_jl_b200 as S
 
 res = {}
-for n, h in ((8, 1), (12, 1), (20, 2), (30, 2), (50, 2)):
+for n, h in ((8, 1), (12, 1), (20, 2), (30, 2), (50, 2), (100, 3)):
     net = S.simulate.random_level1_network(n, h, 20261021)
     taxa = [f"t{i + 1}" for i in range(n)]
     qt = S.simulate.all_quartets(n)
@@ -45,6 +45,23 @@ for n, h in ((8, 1), (12, 1), (20, 2), (30, 2), (50, 2)):
     for _ in range(1000):
         lib.snaq_eval(ctx, 20, npar, pX, po)
     r["eval_P20_us"] = (time.perf_counter() - t) / 1000 * 1e6
+    # the weighted quartet draw of a move proposal: on the device, against reading all the weights back (what the
+    # reference does per proposal: weights = [q.deltaCF for q in d.quartet])
+    u = np.array([0.37]); idx = np.zeros(1, np.int64)
+    pu, pi = u.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p)
+    for _ in range(20):
+        lib.snaq_sample_quartets(ctx, npar, px, 1, pu, pi)
+    t = time.perf_counter()
+    for _ in range(300):
+        lib.snaq_sample_quartets(ctx, npar, px, 1, pu, pi)
+    r["sample_quartet_us"] = (time.perf_counter() - t) / 300 * 1e6
+    dl = np.zeros(len(qt)); pdl = dl.ctypes.data_as(C.c_void_p)
+    for _ in range(5):
+        lib.snaq_eval_quartets(ctx, npar, px, None, None, pdl)
+    t = time.perf_counter()
+    for _ in range(50):
+        lib.snaq_eval_quartets(ctx, npar, px, None, None, pdl)
+    r["deltacf_readback_us"] = (time.perf_counter() - t) / 50 * 1e6
     if not TRACE:
         res[n] = r
         continue

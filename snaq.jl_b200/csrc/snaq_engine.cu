@@ -1933,7 +1933,7 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
 // Weighted sampling of quartets (step 1 of sampleEdgeQuartetWeighted, src/moves_snaq.jl:1443-1449): inverse-CDF walk over
 // the deltaCF weights.  k_chunk_sums: one block per chunk of SQ_CHUNK weights, every thread adds its 16 consecutive weights
 // serially, then a fixed-order tree: the same bits on every run.  k_sample: thread 0 turns the chunk totals into running
-// totals (serial), then one thread per draw finds the chunk by bisection and walks it serially from the chunk's base.
+// totals (serial, in shared memory), then one warp per draw finds the chunk by bisection and walks it 32 entries at a time.
 #define SQ_CHUNK 4096
 __global__ void __launch_bounds__(256) k_chunk_sums(const double *__restrict__ w, const int64_t nq, double *__restrict__ sums) {
     __shared__ double red[8];
@@ -1952,30 +1952,52 @@ __global__ void __launch_bounds__(256) k_chunk_sums(const double *__restrict__ w
     }
 }
 __global__ void __launch_bounds__(256) k_sample(const double *__restrict__ w, const int64_t nq, double *__restrict__ cum,
-                                                const int nchunks, const double *__restrict__ u, const int n,
+                                                const int nchunks, const int in_smem, const double *__restrict__ u, const int n,
                                                 long long *__restrict__ idx) {
+    extern __shared__ double s_cum[];
+    double *c = in_smem ? s_cum : cum;                       // running chunk totals: shared memory when they fit
+    if (in_smem) for (int k = threadIdx.x; k < nchunks; k += 256) s_cum[k] = cum[k];
+    __syncthreads();
     if (threadIdx.x == 0) {
         double t = 0.0;
-        for (int c = 0; c < nchunks; c++) { t += cum[c]; cum[c] = t; }
+        for (int k = 0; k < nchunks; k++) { t += c[k]; c[k] = t; }          // serial, as the reference's walk
     }
     __syncthreads();
-    const double total = cum[nchunks - 1];
-    for (int k = threadIdx.x; k < n; k += 256) {
+    const double total = c[nchunks - 1];
+    const unsigned lane = threadIdx.x & 31u;
+    for (int k = threadIdx.x >> 5; k < n; k += 8) {          // one warp per draw
         const double t = u[k] * total;                       // t = rand() * sum(wv)
         int lo = 0, hi = nchunks - 1;                        // first chunk whose running total reaches t (the last one if none)
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if (cum[mid] >= t) hi = mid; else lo = mid + 1;
+            if (c[mid] >= t) hi = mid; else lo = mid + 1;
         }
-        double cw = lo > 0 ? cum[lo - 1] : 0.0;
+        double cw = lo > 0 ? c[lo - 1] : 0.0;
         const int64_t i0 = (int64_t)lo * SQ_CHUNK, i1 = min(i0 + (int64_t)SQ_CHUNK, nq);
-        int64_t i = i0;
-        cw += w[i];
-        while (cw < t && i < i1 - 1) { i++; cw += w[i]; }    // `while cw < t && i < n` of the reference's walk
-        // rounding between the chunk total and the serial walk can leave cw < t at the end of a chunk that is not the last:
-        // the draw then belongs to the first quartet of positive weight after it
-        if (cw < t && i1 < nq) { i = i1; while (i < nq - 1 && !(w[i] > 0.0)) i++; }
-        idx[k] = i;
+        // `while cw < t && i < n` of the reference's walk, 32 entries at a time: inclusive scan of the 32 weights in a
+        // fixed order, first lane whose running sum reaches t
+        long long found = -1;
+        for (int64_t b = i0; b < i1 && found < 0; b += 32) {
+            const int64_t i = b + lane;
+            double v = i < i1 ? w[i] : 0.0;
+            for (int o = 1; o < 32; o <<= 1) {
+                const double y = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= (unsigned)o) v += y;
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, i < i1 && cw + v >= t);
+            if (hit) found = b + (__ffs(hit) - 1);
+            cw += __shfl_sync(0xffffffffu, v, 31);
+        }
+        if (found < 0) {
+            // rounding between the chunk total and the walk can leave cw < t at the end of a chunk: the draw belongs to the
+            // first quartet of positive weight after it (the last quartet if there is none, as `i < n` ends the walk)
+            found = i1 - 1;
+            if (i1 < nq) {
+                if (lane == 0) { int64_t i = i1; while (i < nq - 1 && !(w[i] > 0.0)) i++; found = i; }
+                found = __shfl_sync(0xffffffffu, found, 0);
+            }
+        }
+        if (lane == 0) idx[k] = found;
     }
 }
 
@@ -2126,6 +2148,8 @@ struct snaq_ctx {
     double *d_XF = nullptr; size_t XF_cap = 0;   // expanded parameter vectors [P][n_full]
     double *d_out = nullptr; size_t out_cap = 0;
     double *d_partial = nullptr; size_t partial_cap = 0;
+    double *d_sq_w = nullptr, *d_sq_cum = nullptr, *d_sq_u = nullptr; long long *d_sq_idx = nullptr;   // snaq_sample_quartets
+    size_t sq_w_cap = 0, sq_cum_cap = 0, sq_u_cap = 0, sq_idx_cap = 0;
     double *d_gpart = nullptr; size_t gpart_cap = 0;     // k_eval_grad_small: [blocks][rows] per-block gradient rows
     unsigned long long *d_gbins = nullptr; size_t gbins_cap = 0;   // k_eval_grad: [2][rows] grid-wide fixed-point gradient bins (zero between launches)
     double *d_gout = nullptr; size_t gout_cap = 0;       // [1 + n_full]: f, then d f / d xf
@@ -2553,7 +2577,7 @@ int snaq_destroy(snaq_ctx *ctx) {
     cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_WA); cudaFree(ctx->d_wpart); cudaFree(ctx->d_negw3); cudaFree(ctx->d_status); cudaFree(ctx->d_total); cudaFree(ctx->d_ticket); cudaFree(ctx->d_trace);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_uidx); cudaFree(ctx->d_rstart); cudaFree(ctx->d_ulen); cudaFree(ctx->d_off_u); cudaFree(ctx->d_qhdr_u);
     cudaFree(ctx->d_prog_u); cudaFree(ctx->d_W_u); cudaFree(ctx->d_WA_u); cudaFree(ctx->d_wpart_u); cudaFree(ctx->d_negw3_u); cudaFree(ctx->d_pen_u);
-    cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_XF); cudaFree(ctx->d_out); cudaFree(ctx->d_partial); cudaFree(ctx->d_gbins); cudaFree(ctx->d_gpart); cudaFree(ctx->d_gout);
+    cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_XF); cudaFree(ctx->d_out); cudaFree(ctx->d_partial); cudaFree(ctx->d_gbins); cudaFree(ctx->d_gpart); cudaFree(ctx->d_sq_w); cudaFree(ctx->d_sq_cum); cudaFree(ctx->d_sq_u); cudaFree(ctx->d_sq_idx); cudaFree(ctx->d_gout);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_qhdr); cudaFree(ctx->d_len4); cudaFree(ctx->d_iota); cudaFree(ctx->d_cls);
     cudaFree(ctx->d_cls_sorted);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -3187,12 +3211,18 @@ int snaq_sample_quartets(snaq_ctx *ctx, int32_t nparams, const double *x, int32_
     if (rc) return rc;
     rc = ensure(ctx, ctx->d_out, ctx->out_cap, 2);
     if (rc) return rc;
-    double *d_w = nullptr, *d_cum = nullptr, *d_u = nullptr;
-    long long *d_idx = nullptr;
-    cudaError_t e = cudaMalloc((void **)&d_w, (size_t)nq * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_cum, (size_t)nchunks * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_u, (size_t)n * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_idx, (size_t)n * sizeof(long long));
+    // the weights, the chunk totals and the draws live in buffers of the context: a search proposes thousands of moves
+    rc = ensure(ctx, ctx->d_sq_w, ctx->sq_w_cap, (size_t)nq);
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->d_sq_cum, ctx->sq_cum_cap, (size_t)nchunks);
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->d_sq_u, ctx->sq_u_cap, (size_t)n);
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->d_sq_idx, ctx->sq_idx_cap, (size_t)n);
+    if (rc) return rc;
+    double *d_w = ctx->d_sq_w, *d_cum = ctx->d_sq_cum, *d_u = ctx->d_sq_u;
+    long long *d_idx = ctx->d_sq_idx;
+    cudaError_t e = cudaSuccess;
     uint32_t st = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_X, x, sizeof(double) * nparams, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_u, u, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream);
@@ -3200,14 +3230,16 @@ int snaq_sample_quartets(snaq_ctx *ctx, int32_t nparams, const double *x, int32_
         rc = eval_device(ctx, 1, ctx->d_X, ctx->d_out, ctx->stream, nullptr, nullptr, d_w);     // deltaCF, the data's quartet order
         if (!rc) {
             k_chunk_sums<<<nchunks, 256, 0, ctx->stream>>>(d_w, nq, d_cum);
-            k_sample<<<1, 256, 0, ctx->stream>>>(d_w, nq, d_cum, nchunks, d_u, n, d_idx);
+            const int in_smem = nchunks <= 24 * 1024 ? 1 : 0;                    // 192 KB of running totals: 100 M quartets
+            const size_t smem = in_smem ? (size_t)nchunks * sizeof(double) : 0;
+            if (e == cudaSuccess) e = raise_smem_limit(k_sample, smem);
+            k_sample<<<1, 256, smem, ctx->stream>>>(d_w, nq, d_cum, nchunks, in_smem, d_u, n, d_idx);
             e = cudaGetLastError();
             if (e == cudaSuccess) e = cudaMemcpyAsync(&st, ctx->d_status + 1, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream);
             if (e == cudaSuccess) e = cudaMemcpyAsync(idx, d_idx, sizeof(long long) * n, cudaMemcpyDeviceToHost, ctx->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         }
     }
-    cudaFree(d_w); cudaFree(d_cum); cudaFree(d_u); cudaFree(d_idx);
     if (rc) return rc;
     if (e != cudaSuccess) { ctx->err = std::string("snaq_sample_quartets: ") + cudaGetErrorString(e); return SNAQ_ECUDA; }
     ctx->counters[2] += 8 * (nparams + n);
