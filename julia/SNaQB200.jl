@@ -109,7 +109,10 @@ function readback!(e::Engine, d::DataCF, x::Vector{Float64})
 end
 
 # ---- the replaced body of optBL! (src/snaq_optimization.jl:341-390): NLopt stays in Julia, only `obj` changes ----
-function optBL!(net::HybridNetwork, d::DataCF, e::Engine, verbose::Bool, ftolRel, ftolAbs, xtolRel, xtolAbs)
+# `readback`: copy expCF / logPseudoLik / deltaCF of every quartet into the Quartet objects afterwards, as the reference
+# leaves them (156 bytes per quartet: 20 ms at 3.9 M quartets, several optBL! calls' worth).  Only the final report
+# (fittedquartetCF, writeExpCF) needs them once the weighted draw of the proposals uses `sample_quartet`: off by default.
+function optBL!(net::HybridNetwork, d::DataCF, e::Engine, verbose::Bool, ftolRel, ftolAbs, xtolRel, xtolAbs; readback::Bool = false)
     SNaQ.parameters!(net)                       # :353
     set_network!(e, net)                        # replaces extractQuartet!(net,d), :354
     nht = length(ht(net))
@@ -123,7 +126,7 @@ function optBL!(net::HybridNetwork, d::DataCF, e::Engine, verbose::Bool, ftolRel
     fmin, xmin, ret = SNaQ.NLopt.optimize(opt, ht(net))
     SNaQ.updateParameters!(net, xmin)           # :387
     SNaQ.loglik!(net, fmin)                     # :388
-    readback!(e, d, xmin)                       # keeps q.qnet.expCF / deltaCF usable by the search (quirk: the reference leaves the LAST x there)
+    readback && readback!(e, d, xmin)           # (quirk: the reference leaves the LAST x it tried there, not xmin)
 end
 
 # ---- phase 2: the optimiser itself on the device (snaq_optbl): analytic gradient in one pass, batched line searches ----
@@ -131,7 +134,8 @@ struct OptblOpts; ftol_rel::Cdouble; ftol_abs::Cdouble; xtol_rel::Cdouble; xtol_
 mutable struct OptblResult; fmin::Cdouble; proj_grad::Cdouble; nevals::Cint; nlaunches::Cint; niter::Cint; status::Cint; end
 
 "optBL! without NLopt: same arguments, same post-conditions (ht(net), loglik(net) updated); iterates differ from BOBYQA's"
-function optBL_device!(net::HybridNetwork, d::DataCF, e::Engine, ftolRel = SNaQ.fRel, ftolAbs = SNaQ.fAbs, xtolRel = SNaQ.xRel, xtolAbs = SNaQ.xAbs)
+function optBL_device!(net::HybridNetwork, d::DataCF, e::Engine, ftolRel = SNaQ.fRel, ftolAbs = SNaQ.fAbs, xtolRel = SNaQ.xRel, xtolAbs = SNaQ.xAbs;
+                       readback::Bool = false)
     (ftolRel > 0 && ftolAbs > 0 && xtolAbs > 0 && xtolRel > 0) || error("tolerances have to be positive, ftol (rel,abs), xtol (rel,abs): $([ftolRel, ftolAbs, xtolRel, xtolAbs])")
     SNaQ.parameters!(net)
     set_network!(e, net)
@@ -141,7 +145,7 @@ function optBL_device!(net::HybridNetwork, d::DataCF, e::Engine, ftolRel = SNaQ.
                    OptblOpts(ftolRel, ftolAbs, xtolRel, xtolAbs, 1000, 0, 0, 0), x, res))
     SNaQ.updateParameters!(net, x)
     SNaQ.loglik!(net, res.fmin)
-    readback!(e, d, x)
+    readback && readback!(e, d, x)
     return res
 end
 
