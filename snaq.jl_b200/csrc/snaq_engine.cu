@@ -23,7 +23,10 @@
  *                                  _p: persistent blocks, xf tile resident, chunks through two TMA stages (big tiles)
  *   k_eval_direct                : thread per quartet for small batches (P < 16; HBM-bound at P=1): warp-private TMA
  *                                  rings; also the per-quartet read-back (expCF, logPseudoLik, deltaCF)
- *   k_eval_grad                  : objective + analytic gradient (+ curvature diagonal) in one pass, fixed-point bins
+ *   k_eval_grad / _small         : objective + analytic gradient (+ curvature diagonal) in one pass, fixed-point bins.
+ *                                  Large tables: class A through a TMA ring in runs of consecutive tiles, per-program
+ *                                  memo, grid-wide 64-bit integer bins; small tables: plain loads, per-block rows
+ *   k_chunk_sums / k_sample      : deltaCF-weighted quartet draw of the move proposals (inverse-CDF walk)
  *   k_reduce_partials*           : second, fixed-order pass over per-block partial sums
  *   k_update_bl, k_describe, k_hasedge : updateBL! table, parity descriptors
  *
