@@ -124,6 +124,21 @@ def test_optbl_topologies_follows_the_data_of_the_context():
         assert np.array_equal(a[0], b[0]) and a[1] == b[1]
 
 
+def test_optbl_topologies_after_the_context_gets_another_table():
+    """snaq_set_data with a table of another size: the worker contexts are re-created from the new data"""
+    taxa, qt, obs, cands = data_and_candidates(12, 1, 4, 13)
+    eng = S.Engine(0)
+    eng.set_data(S.DataCF(taxa, qt, obs))
+    eng.optbl_topologies(cands, workers=3)
+    keep = np.arange(len(qt)) % 3 != 0
+    qt2, obs2 = qt[keep], obs[keep]
+    eng.set_data(S.DataCF(taxa, qt2, obs2))
+    got = eng.optbl_topologies(cands, workers=3)
+    want = sequential(taxa, qt2, obs2, cands)
+    for (xm, info), (xw, iw) in zip(got, want):
+        assert np.array_equal(xm, xw) and info == iw
+
+
 def test_optbl_topologies_reports_the_failing_candidate():
     taxa, qt, obs, cands = data_and_candidates(10, 1, 3, 9)
     bad = simulate.random_level1_network(9, 0, 4).flatten(taxa)     # a network that misses taxon t10 of the data
