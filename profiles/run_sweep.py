@@ -1,5 +1,5 @@
 """Randomized parity sweep on the GPU: updateBL! tables, hasEdge/indexht (<= 1 hybrid) and the per-quartet
-read-backs under a sampling mask, each against the oracle.  Usage: python profiles/run_sweep.py [n_seeds]"""
+read-backs under a sampling mask, each against the oracle.  Usage: python profiles/run_sweep.py [n_seeds [first_seed]]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -8,8 +8,9 @@ from snaq_jl_b200 import simulate
 from oracle import oracle, update_bl as ubl
 
 nseeds = int(sys.argv[1]) if len(sys.argv) > 1 else 80
+first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 nb = nh = nq_ = 0
-for seed in range(nseeds):
+for seed in range(first, first + nseeds):
     rng = np.random.default_rng(seed)
     # updateBL! on random trees, ragged permuted tables
     n = 6 + seed % 16
