@@ -121,6 +121,17 @@ int snaq_set_data(snaq_ctx *ctx, int32_t ntaxa, int64_t nq,
                   const uint16_t *taxa, const double *obscf);
 /* bootstrap refresh: overwrite obsCF in place (src/readquartetdata.jl:211-217) */
 int snaq_set_obscf(snaq_ctx *ctx, const double *obscf);
+/* Bootstrap tables on the device: sampleCFfromCI!, src/bootstrap.jl:52-70, followed by
+ * readtableCF!, src/readquartetdata.jl:211-217.  snaq_set_ci keeps the credibility intervals lo/hi [nq][3] of the
+ * three CFs resident (0 <= lo <= hi <= 1, some hi > 0 in every quartet); snaq_resample_obscf then overwrites obsCF:
+ *     c_i = (hi_i - lo_i) * U_i + lo_i,   obsCF_i = c_i / (c_1 + c_2 + c_3)          (:60-67)
+ * The reference draws U from Julia's task-local RNG after Random.seed!(seed), which cannot be reproduced outside Julia;
+ * here U_i = (splitmix64(seed + (3*q + i) * 0x9E3779B97F4A7C15) >> 11) * 2^-53 with q the quartet's index in the data
+ * (the same table on every rank of a quartet-sharded run, reproducible on the host: tests/test_gpu_bootstrap.py).
+ * snaq_get_obscf reads the current table back.                                                                      */
+int snaq_set_ci(snaq_ctx *ctx, const double *lo, const double *hi);
+int snaq_resample_obscf(snaq_ctx *ctx, uint64_t seed);
+int snaq_get_obscf(snaq_ctx *ctx, double *obscf);
 /* q.sampled mask (src/update.jl:386,406,442); NULL = all sampled             */
 int snaq_set_sampled(snaq_ctx *ctx, const uint8_t *mask);
 

@@ -189,6 +189,15 @@ function sample_quartet(e::Engine, x::Vector{Float64}, u::Float64 = rand())
     return idx[] + 1
 end
 
+"bootstrap replicate on the device: keep the CI columns resident once (set_ci!), then one call per replicate.
+The draws come from the engine's counter-based generator, not from Julia's RNG: replicates differ from bootsnaq's for
+the same seed (same distribution, src/bootstrap.jl:60-67)."
+function set_ci!(e::Engine, lo::Matrix{Float64}, hi::Matrix{Float64})          # 3 x nq each (column-major = [nq][3])
+    check(e, ccall((:snaq_set_ci, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), e.ctx, lo, hi))
+end
+resample_obscf!(e::Engine, seed::Integer) =
+    check(e, ccall((:snaq_resample_obscf, LIB), Cint, (Ptr{Cvoid}, UInt64), e.ctx, UInt64(seed)))
+
 "updateBL! (src/readquartetdata.jl:838-861) with the table built on the device; net must be a tree"
 function updateBL_device!(net::HybridNetwork, d::DataCF, e::Engine)
     SNaQ.parameters!(net)

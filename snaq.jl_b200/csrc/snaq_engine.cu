@@ -317,6 +317,31 @@ __global__ void __launch_bounds__(128) k_weights_u(const uint32_t *__restrict__ 
 // W[i] (all classes) and, for the class-A quartets with one- and two-chunk programs [0,nA), the pair
 // WA[i] = (W0, W1) that the single-call kernel streams; their constants W3 are summed once into wpart (one
 // partial per block, fixed order)
+// sampleCFfromCI! (src/bootstrap.jl:52-70) for every quartet: three uniforms from a counter-based generator keyed by the
+// seed and the quartet's index in the data, c_i = (hi_i - lo_i) * U_i + lo_i, renormalised.  No fused multiply-add: the
+// host restatement (numpy) gives the same bits.
+__device__ __forceinline__ unsigned long long snaq_splitmix64(unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256) k_resample_ci(const double *__restrict__ lo, const double *__restrict__ hi, const int64_t nq,
+                                                     const int64_t q_begin, const unsigned long long seed, double *__restrict__ obs) {
+    const int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (q >= nq) return;
+    double c[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const unsigned long long ctr = (unsigned long long)(3 * (q_begin + q) + i);
+        const double u = (double)(snaq_splitmix64(seed + ctr * 0x9E3779B97F4A7C15ull) >> 11) * 0x1.0p-53;
+        c[i] = __dadd_rn(__dmul_rn(__dadd_rn(hi[3 * q + i], -lo[3 * q + i]), u), lo[3 * q + i]);
+    }
+    const double suma = __dadd_rn(__dadd_rn(c[0], c[1]), c[2]);
+#pragma unroll
+    for (int i = 0; i < 3; i++) obs[3 * q + i] = __ddiv_rn(c[i], suma);
+}
+
 __global__ void __launch_bounds__(256) k_weights(const uint32_t *__restrict__ perm, const uint8_t *__restrict__ qhdr,
                                                  const double *__restrict__ obs, const uint8_t *__restrict__ sampled,
                                                  int64_t nq, int64_t nA, double *__restrict__ W, double2 *__restrict__ WA,
@@ -2108,6 +2133,8 @@ struct snaq_ctx {
     double *d_obs = nullptr;
     uint8_t *d_sampled = nullptr;
     bool has_sampled = false;
+    double *d_ci_lo = nullptr, *d_ci_hi = nullptr;   // snaq_set_ci: [nq][3] each
+    bool has_ci = false;
     // network
     bool has_net = false;
     SnaqHostTables H;
@@ -2575,6 +2602,7 @@ int snaq_destroy(snaq_ctx *ctx) {
     for (snaq_ctx *w : ctx->workers) snaq_destroy(w);
     ctx->workers.clear();
     cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_ci_lo); cudaFree(ctx->d_ci_hi);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_blob); cudaFree(ctx->d_xconst);
     cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_WA); cudaFree(ctx->d_wpart); cudaFree(ctx->d_negw3); cudaFree(ctx->d_status); cudaFree(ctx->d_total); cudaFree(ctx->d_ticket); cudaFree(ctx->d_trace);
@@ -2606,6 +2634,9 @@ int snaq_set_data(snaq_ctx *ctx, int32_t ntaxa, int64_t nq, const uint16_t *taxa
     ctx->ntaxa = ntaxa;
     ctx->has_net = false;
     ctx->has_sampled = false;
+    ctx->has_ci = false;
+    cudaFree(ctx->d_ci_lo); cudaFree(ctx->d_ci_hi);
+    ctx->d_ci_lo = ctx->d_ci_hi = nullptr;
     ctx->data_version++;
     cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_off); cudaFree(ctx->d_W);
     cudaFree(ctx->d_WA); cudaFree(ctx->d_wpart); cudaFree(ctx->d_negw3);
@@ -2660,6 +2691,61 @@ int snaq_set_obscf(snaq_ctx *ctx, const double *obscf) {
     int rc = run_weights(ctx);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
+    return SNAQ_OK;
+}
+
+int snaq_set_ci(snaq_ctx *ctx, const double *lo, const double *hi) {
+    if (!ctx || !lo || !hi) return SNAQ_EINVAL;
+    if (!ctx->d_obs) { ctx->err = "snaq_set_data has not been called"; return SNAQ_ENODATA; }
+    CK(cudaSetDevice(ctx->device));
+    for (int64_t q = 0; q < ctx->nq_total; q++) {
+        double top = 0.0;
+        for (int i = 0; i < 3; i++) {
+            const double a = lo[3 * q + i], b = hi[3 * q + i];
+            if (!(a >= 0.0 && a <= b && b <= 1.0)) { ctx->err = "credibility interval must satisfy 0 <= lo <= hi <= 1 in quartet " + std::to_string(q); return SNAQ_EINVAL; }
+            top += b;
+        }
+        if (!(top > 0.0)) { ctx->err = "credibility intervals of quartet " + std::to_string(q) + " are all zero"; return SNAQ_EINVAL; }
+    }
+    const size_t n = (size_t)std::max<int64_t>(ctx->nq, 1) * 3;
+    if (!ctx->d_ci_lo) CK(cudaMalloc((void **)&ctx->d_ci_lo, n * sizeof(double)));
+    if (!ctx->d_ci_hi) CK(cudaMalloc((void **)&ctx->d_ci_hi, n * sizeof(double)));
+    if (ctx->nq > 0) {
+        CK(cudaMemcpyAsync(ctx->d_ci_lo, lo + 3 * ctx->q_begin, (size_t)ctx->nq * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_ci_hi, hi + 3 * ctx->q_begin, (size_t)ctx->nq * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->counters[2] += ctx->nq * 48;
+    }
+    ctx->has_ci = true;
+    return SNAQ_OK;
+}
+
+int snaq_resample_obscf(snaq_ctx *ctx, uint64_t seed) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (!ctx->has_ci) { ctx->err = "snaq_set_ci has not been called"; return SNAQ_ENODATA; }
+    CK(cudaSetDevice(ctx->device));
+    ctx->data_version++;
+    if (ctx->nq > 0) {
+        k_resample_ci<<<(unsigned)((ctx->nq + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_ci_lo, ctx->d_ci_hi, ctx->nq, ctx->q_begin,
+                                                                                 (unsigned long long)seed, ctx->d_obs);
+        CK(cudaGetLastError());
+        ctx->counters[5] += 1;
+    }
+    int rc = run_weights(ctx);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SNAQ_OK;
+}
+
+int snaq_get_obscf(snaq_ctx *ctx, double *obscf) {
+    if (!ctx || !obscf) return SNAQ_EINVAL;
+    if (!ctx->d_obs) { ctx->err = "snaq_set_data has not been called"; return SNAQ_ENODATA; }
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->nq > 0) {
+        CK(cudaMemcpyAsync(obscf + 3 * ctx->q_begin, ctx->d_obs, (size_t)ctx->nq * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->counters[3] += ctx->nq * 24;
+    }
     return SNAQ_OK;
 }
 

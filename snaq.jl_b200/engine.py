@@ -33,7 +33,7 @@ EXPORTS = ["snaq_create", "snaq_destroy", "snaq_last_error", "snaq_version", "sn
            "snaq_set_sampled", "snaq_set_network", "snaq_patch_network", "snaq_num_params", "snaq_get_params",
            "snaq_eval", "snaq_eval_device", "snaq_eval_quartets", "snaq_get_descriptors", "snaq_get_counters",
            "snaq_check_status", "snaq_measure_fp64_peak", "snaq_get_trace", "snaq_eval_grad", "snaq_optbl", "snaq_update_bl", "snaq_get_hasedge",
-           "snaq_eval_topologies", "snaq_optbl_topologies", "snaq_sample_quartets"]
+           "snaq_eval_topologies", "snaq_optbl_topologies", "snaq_sample_quartets", "snaq_set_ci", "snaq_resample_obscf", "snaq_get_obscf"]
 
 
 class _OptblOpts(C.Structure):
@@ -115,6 +115,23 @@ class Engine:
         if ob.size != 3 * self.nq:
             raise SnaqError("obsCF has the wrong size")
         self._chk(self.lib.snaq_set_obscf(self.ctx, _p(ob)))
+
+    def set_ci(self, lo: np.ndarray, hi: np.ndarray) -> None:
+        """credibility intervals of the three CFs of every quartet, [nq, 3] each (the CI columns of the bootstrap table)"""
+        lo = np.ascontiguousarray(lo, dtype=np.float64).reshape(-1, 3)
+        hi = np.ascontiguousarray(hi, dtype=np.float64).reshape(-1, 3)
+        if lo.shape != (self.nq, 3) or hi.shape != lo.shape:
+            raise SnaqError("lo and hi must have one row of three values per quartet")
+        self._chk(self.lib.snaq_set_ci(self.ctx, _p(lo), _p(hi)))
+
+    def resample_obscf(self, seed: int) -> None:
+        """``sampleCFfromCI!`` + ``readtableCF!`` on the device (src/bootstrap.jl:52-70): a new bootstrap table in HBM"""
+        self._chk(self.lib.snaq_resample_obscf(self.ctx, C.c_uint64(seed)))
+
+    def get_obscf(self) -> np.ndarray:
+        out = np.zeros((self.nq, 3))
+        self._chk(self.lib.snaq_get_obscf(self.ctx, _p(out)))
+        return out
 
     def set_sampled(self, mask: Optional[np.ndarray]) -> None:
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
