@@ -2180,6 +2180,7 @@ struct snaq_ctx {
     double *d_partial = nullptr; size_t partial_cap = 0;
     double *d_sq_w = nullptr, *d_sq_cum = nullptr, *d_sq_u = nullptr; long long *d_sq_idx = nullptr;   // snaq_sample_quartets
     size_t sq_w_cap = 0, sq_cum_cap = 0, sq_u_cap = 0, sq_idx_cap = 0;
+    double *d_rb_e = nullptr, *d_rb_l = nullptr, *d_rb_d = nullptr; size_t rb_e_cap = 0, rb_l_cap = 0, rb_d_cap = 0;   // snaq_eval_quartets
     double *d_gpart = nullptr; size_t gpart_cap = 0;     // k_eval_grad_small: [blocks][rows] per-block gradient rows
     unsigned long long *d_gbins = nullptr; size_t gbins_cap = 0;   // k_eval_grad: [2][rows] grid-wide fixed-point gradient bins (zero between launches)
     double *d_gout = nullptr; size_t gout_cap = 0;       // [1 + n_full]: f, then d f / d xf
@@ -2608,7 +2609,7 @@ int snaq_destroy(snaq_ctx *ctx) {
     cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_WA); cudaFree(ctx->d_wpart); cudaFree(ctx->d_negw3); cudaFree(ctx->d_status); cudaFree(ctx->d_total); cudaFree(ctx->d_ticket); cudaFree(ctx->d_trace);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_uidx); cudaFree(ctx->d_rstart); cudaFree(ctx->d_ulen); cudaFree(ctx->d_off_u); cudaFree(ctx->d_qhdr_u);
     cudaFree(ctx->d_prog_u); cudaFree(ctx->d_W_u); cudaFree(ctx->d_WA_u); cudaFree(ctx->d_wpart_u); cudaFree(ctx->d_negw3_u); cudaFree(ctx->d_pen_u);
-    cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_XF); cudaFree(ctx->d_out); cudaFree(ctx->d_partial); cudaFree(ctx->d_gbins); cudaFree(ctx->d_gpart); cudaFree(ctx->d_sq_w); cudaFree(ctx->d_sq_cum); cudaFree(ctx->d_sq_u); cudaFree(ctx->d_sq_idx); cudaFree(ctx->d_gout);
+    cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_XF); cudaFree(ctx->d_out); cudaFree(ctx->d_partial); cudaFree(ctx->d_gbins); cudaFree(ctx->d_gpart); cudaFree(ctx->d_rb_e); cudaFree(ctx->d_rb_l); cudaFree(ctx->d_rb_d); cudaFree(ctx->d_sq_w); cudaFree(ctx->d_sq_cum); cudaFree(ctx->d_sq_u); cudaFree(ctx->d_sq_idx); cudaFree(ctx->d_gout);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_qhdr); cudaFree(ctx->d_len4); cudaFree(ctx->d_iota); cudaFree(ctx->d_cls);
     cudaFree(ctx->d_cls_sorted);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -3255,14 +3256,12 @@ int snaq_eval_quartets(snaq_ctx *ctx, int32_t nparams, const double *x, double *
     if (rc) return rc;
     rc = ensure(ctx, ctx->d_out, ctx->out_cap, 2);
     if (rc) return rc;
+    // the per-quartet arrays live in buffers of the context (a read-back per search step should not pay cudaMalloc)
     double *d_e = nullptr, *d_l = nullptr, *d_d = nullptr;
     const size_t n = (size_t)std::max<int64_t>(nq, 1);
-    if (expcf) CK(cudaMalloc((void **)&d_e, n * 3 * sizeof(double)));
-    if (logpl) CK(cudaMalloc((void **)&d_l, n * sizeof(double)));
-    if (deltacf) CK(cudaMalloc((void **)&d_d, n * sizeof(double)));
-    // always pass at least one per-quartet pointer so that the thread-per-quartet kernel is used
-    double *d_dummy = nullptr;
-    if (!d_e && !d_l && !d_d) { CK(cudaMalloc((void **)&d_dummy, n * sizeof(double))); d_l = d_dummy; }
+    if (expcf) { rc = ensure(ctx, ctx->d_rb_e, ctx->rb_e_cap, n * 3); if (rc) return rc; d_e = ctx->d_rb_e; }
+    if (logpl || (!expcf && !deltacf)) { rc = ensure(ctx, ctx->d_rb_l, ctx->rb_l_cap, n); if (rc) return rc; d_l = ctx->d_rb_l; }
+    if (deltacf) { rc = ensure(ctx, ctx->d_rb_d, ctx->rb_d_cap, n); if (rc) return rc; d_d = ctx->d_rb_d; }   // (at least one per-quartet pointer selects the thread-per-quartet kernel)
     CK(cudaMemcpyAsync(ctx->d_X, x, sizeof(double) * nparams, cudaMemcpyHostToDevice, ctx->stream));
     rc = eval_device(ctx, 1, ctx->d_X, ctx->d_out, ctx->stream, d_e, d_l, d_d);
     uint32_t st = 0;
@@ -3276,7 +3275,6 @@ int snaq_eval_quartets(snaq_ctx *ctx, int32_t nparams, const double *x, double *
         ctx->counters[2] += 8 * nparams;
         ctx->counters[3] += (expcf ? 24 : 0) * nq + (logpl ? 8 : 0) * nq + (deltacf ? 8 : 0) * nq;
     }
-    cudaFree(d_e); if (d_l != d_dummy) cudaFree(d_l); cudaFree(d_d); cudaFree(d_dummy);
     if (rc) return rc;
     if (st) { cudaMemsetAsync(ctx->d_status + 1, 0, sizeof(uint32_t), ctx->stream); return status_to_error(ctx, st); }
     return SNAQ_OK;
