@@ -1362,7 +1362,6 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
  * snaq_grad_backprop on the host (a few hundred rows).
  */
 #define QG_SCALE 4294967296.0
-#define QG_SMALL_GRID 32  /* grids up to this many blocks reduce their gradient rows through per-block rows, larger ones through atomics */
 #ifndef QG_RUN
 #define QG_RUN 4        /* consecutive 64-quartet tiles a warp takes before the next warp's run begins */
 #endif
@@ -1600,7 +1599,7 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
             const double *__restrict__ X, const double *__restrict__ xconst, int nh, int nt, double *__restrict__ partial,
             double *__restrict__ out, const double *__restrict__ negw3, unsigned int *__restrict__ ticket,
             unsigned long long *__restrict__ gbins, double *__restrict__ gout, uint32_t *__restrict__ status, uint32_t *__restrict__ status_out,
-            const int use_xarg /* bit 0: x is in xarg; bit 1: no warp aggregation in the generic path; bit 2: TMA ring */,
+            const int use_xarg /* bit 0: x is in xarg; bit 1: no warp aggregation in the generic path */,
             const double *__restrict__ pen,
             unsigned long long *__restrict__ trace, const __grid_constant__ XArg xarg) {
     constexpr int BLOCK = 256;
@@ -1619,8 +1618,7 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 448);            // [8 warps][QD_NST] mbarriers (192 B)
     uint2 *span = reinterpret_cast<uint2 *>(smem + 640);                  // [8 warps][QD_SPAN] staged programs
     unsigned char *ring = smem + 640 + 8 * QD_SPAN * 8;                   // [8 warps][QD_NST][QD_STAGE_BYTES] class-A tiles
-    const bool use_ring = (use_xarg & 4) != 0;                            // the host sizes the shared memory accordingly
-    double *xs = reinterpret_cast<double *>(ring + (use_ring ? 8 * QD_NST * QD_STAGE_BYTES : 0));
+    double *xs = reinterpret_cast<double *>(ring + 8 * QD_NST * QD_STAGE_BYTES);
     const int n_full = T.n_full;
     unsigned int *bins_lo = reinterpret_cast<unsigned int *>(xs + n_full);   // [n_full] low words
     unsigned int *bins_hi = bins_lo + n_full;                                // [n_full] high words
@@ -1654,9 +1652,7 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
             tma_load_1d(dst + QD_TQ * 16, prog2 + a2base + 2u * j0, n * 16u, &wbar[sg]);
         }
     };
-    // a class of fewer than two tiles per warp is read with plain loads: the ring's set-up (barrier initialisation, fence,
-    // first copies) costs more than it hides there, and small tables are all latency
-    if (use_ring && lane == 0) {
+    if (lane == 0) {
         for (int k = 0; k < QD_NST; k++) mbar_init(&wbar[k], 1);
         for (unsigned k = 0; k < QD_NST; k++)
             if (tile_of(k) < tA) issue(tile_of(k), k);
@@ -1803,16 +1799,14 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
         for (unsigned kt = 0;; kt++) {
             const unsigned t = tile_of(kt);
             if (t >= tA) break;
-            if (use_ring) mbar_wait(&wbar[sg], phase);
+            mbar_wait(&wbar[sg], phase);
             const unsigned char *stg = wring + sg * QD_STAGE_BYTES;
             const bool one = t < tA1;
             const unsigned q0 = one ? t * QD_TQ : (t - tA1) * QD_TQ;     // first entry of the tile inside its sub-class
             const unsigned n = one ? min((unsigned)QD_TQ, nA1 - q0) : min((unsigned)QD_TQ, nA2 - q0);
-            // the tile's weight pairs and programs: in the stage (ring) or in global memory (plain loads)
-            const double2 *sw = use_ring ? reinterpret_cast<const double2 *>(stg) : WA + (one ? q0 : nA1 + q0);
-            const uint2 *sp2 = use_ring ? reinterpret_cast<const uint2 *>(stg + QD_TQ * 16) : prog2 + q0;
-            const uint4 *sp4 = use_ring ? reinterpret_cast<const uint4 *>(stg + QD_TQ * 16)
-                                        : reinterpret_cast<const uint4 *>(prog2 + a2base) + q0;
+            const double2 *sw = reinterpret_cast<const double2 *>(stg);    // the tile's weight pairs, then its programs
+            const uint2 *sp2 = reinterpret_cast<const uint2 *>(stg + QD_TQ * 16);
+            const uint4 *sp4 = reinterpret_cast<const uint4 *>(stg + QD_TQ * 16);
 #pragma unroll 1
             for (unsigned r0 = 0; r0 < n; r0 += 32u) {
                 const unsigned idx = r0 + lane;
@@ -1854,7 +1848,7 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
                 }
             }
             __syncwarp();                                                  // every lane is done with stage sg
-            if (use_ring && lane == 0 && tile_of(kt + QD_NST) < tA) issue(tile_of(kt + QD_NST), sg);
+            if (lane == 0 && tile_of(kt + QD_NST) < tA) issue(tile_of(kt + QD_NST), sg);
             if (++sg == QD_NST) { sg = 0; phase ^= 1u; }
         }
         flush();
@@ -1903,18 +1897,10 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
     // the block's bins go to the grid's bins with 64-bit integer reductions (order independent, so bit-reproducible):
     // gbins[row] takes the fraction words, gbins[nrows + row] the sign-extended integer words, each with 2^31 blocks of
     // headroom; the last block only converts (no serial pass over per-block rows)
-    // (a grid of at most QG_SMALL_GRID blocks writes its rows to gpart instead and the last block adds them in block order:
-    // a handful of plain stores and loads is quicker than waiting for the atomics to drain)
-    const bool small_grid = gridDim.x <= QG_SMALL_GRID;
-    double *gpart = reinterpret_cast<double *>(gbins + 4 * (size_t)n_full);
     for (int row = (int)tid; row < nrows; row += BLOCK) {
         const unsigned lo = bins_lo[row + (row >= n_full ? n_full : 0)], hi = bins_hi[row + (row >= n_full ? n_full : 0)];
-        if (small_grid) {
-            gpart[(size_t)blockIdx.x * nrows + row] = (double)(long long)(((unsigned long long)hi << 32) | (unsigned long long)lo) * (1.0 / QG_SCALE);
-        } else {
-            if (lo) atomicAdd(gbins + row, (unsigned long long)lo);
-            if (hi) atomicAdd(gbins + nrows + row, (unsigned long long)(long long)(int)hi);
-        }
+        if (lo) atomicAdd(gbins + row, (unsigned long long)lo);
+        if (hi) atomicAdd(gbins + nrows + row, (unsigned long long)(long long)(int)hi);
     }
     stamp(7);
     __threadfence();
@@ -1936,16 +1922,11 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
             out[0] = -tot - __ldcg(negw3);
         }
         for (int row = (int)tid; row < nrows; row += BLOCK) {
-            double s = 0.0;
-            if (small_grid) {
-                for (unsigned b = 0; b < gridDim.x; b++) s += __ldcg(gpart + (size_t)b * nrows + row);
-            } else {
-                const unsigned long long fr = __ldcg(gbins + row);
-                const long long in = (long long)__ldcg(gbins + nrows + row);
-                gbins[row] = 0ull;                                        // ready for the next launch
-                gbins[nrows + row] = 0ull;
-                s = (double)in + (double)fr * (1.0 / QG_SCALE);
-            }
+            const unsigned long long fr = __ldcg(gbins + row);
+            const long long in = (long long)__ldcg(gbins + nrows + row);
+            gbins[row] = 0ull;                                            // ready for the next launch
+            gbins[nrows + row] = 0ull;
+            const double s = (double)in + (double)fr * (1.0 / QG_SCALE);
             gout[row] = row < n_full ? -s : s;                            // f = -(sum of v); the curvature is already that of f
         }
         __threadfence_system();                          // every thread's rows are in host memory before the flag
@@ -3138,12 +3119,12 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
         rc = ensure(ctx, ctx->d_gpart, ctx->gpart_cap, (size_t)grid * nrows);
         if (rc) return rc;
     }
-    const int kflags = (agg_on ? 0 : 2) | (use_ring ? 4 : 0);
+    const int kflags = agg_on ? 0 : 2;
     rc = ensure(ctx, ctx->d_X, ctx->X_cap, (size_t)std::max(nparams, 1));
     if (rc) return rc;
     rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)grid);
     if (rc) return rc;
-    const size_t gb_need = (size_t)(4 + 2 * QG_SMALL_GRID) * n_full;      // [2][2 n_full] grid bins (curvature variant too) + gpart of a small grid
+    const size_t gb_need = (size_t)4 * n_full;                            // [2][2 n_full] grid bins (sized for the curvature variant too)
     if (gb_need > ctx->gbins_cap || !ctx->d_gbins) {                      // zero once, the kernel re-zeroes its bins
         rc = ensure(ctx, ctx->d_gbins, ctx->gbins_cap, gb_need);
         if (rc) return rc;
