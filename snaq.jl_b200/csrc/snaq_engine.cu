@@ -3050,7 +3050,7 @@ int snaq_eval(snaq_ctx *ctx, int32_t P, int32_t nparams, const double *X, double
     const double *src = user_pinned ? X : ctx->h_pin;
     // large batches: the copy of chunk k+1 (copy stream) overlaps the evaluation of chunk k (compute stream); a pageable
     // caller buffer is staged chunk by chunk, so that the host memcpy of chunk k+1 also overlaps the device work of chunk k
-    const int nchunk = (P >= 2048 && nparams > 0) ? (user_pinned ? ctx->eval_chunks : 2 * ctx->eval_chunks) : 1;
+    const int nchunk = (P >= 2048 && nparams > 0) ? ctx->eval_chunks : 1;   // (measured: two chunks are best for pinned and pageable alike)
     if (nchunk == 1 && !user_pinned) std::memcpy(ctx->h_pin, X, sizeof(double) * (size_t)P * nparams);
     if (nchunk > 1) {
         if (!ctx->copy_stream) {
