@@ -203,7 +203,8 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f,
 #define SNAQ_OPTBL_MAXEVAL  5
 typedef struct snaq_optbl_opts {
     double ftol_rel, ftol_abs, xtol_rel, xtol_abs;   /* optBL!'s ftolRel, ftolAbs, xtolRel, xtolAbs (all > 0, :350) */
-    int32_t maxeval;     /* NLopt.maxeval! = 1000 in the reference (:365); here: engine launches (each a batch)    */
+    int32_t maxeval;     /* NLopt.maxeval! = 1000 in the reference (:365): parameter vectors evaluated (a batch that
+                            starts below the bound is finished, so nevals can exceed it by one ladder)              */
     int32_t ladder;      /* step lengths tried per line-search launch (default 20)                              */
     uint32_t flags;      /* SNAQ_OPTBL_*                                                                         */
     uint32_t reserved;

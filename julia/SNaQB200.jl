@@ -5,6 +5,7 @@
 module SNaQB200
 
 using SNaQ, PhyloNetworks
+import Distributed
 import SNaQ: istIdentifiable, fromBadDiamondI, inCycle, hasHybEdge, isBadDiamondI, isBadDiamondII, isBadTriangle,
              gammaz, numBad, ht, numht, DataCF, Quartet
 

@@ -2330,6 +2330,8 @@ static int build_dedup(snaq_ctx *ctx, int64_t pad_at) {
     if ((size_t)nu + 1 > ctx->u_cap) {
         cudaFree(ctx->d_rstart); cudaFree(ctx->d_ulen); cudaFree(ctx->d_off_u); cudaFree(ctx->d_qhdr_u); cudaFree(ctx->d_W_u); cudaFree(ctx->d_WA_u);
         cudaFree(ctx->d_wpart_u); cudaFree(ctx->d_pen_u);
+        ctx->d_rstart = ctx->d_ulen = ctx->d_off_u = nullptr; ctx->d_qhdr_u = nullptr; ctx->d_W_u = nullptr; ctx->d_WA_u = nullptr;
+        ctx->d_wpart_u = nullptr; ctx->d_pen_u = nullptr;         // a failed cudaMalloc below must not leave dangling pointers
         ctx->u_cap = 0;
         const size_t n = (size_t)nu + 1 + (size_t)nu / 8;
         CK(cudaMalloc((void **)&ctx->d_rstart, (n + 1) * sizeof(uint32_t)));

@@ -146,13 +146,15 @@ extern "C" int snaq_optbl(snaq_ctx *ctx, const snaq_optbl_opts *o, double *x_io,
     if (n == 0) { res->fmin = f; res->nevals = (int32_t)pb.nevals; res->nlaunches = (int32_t)pb.nlaunches; res->status = SNAQ_OPTBL_XTOL; return SNAQ_OK; }
     const int M = std::max(12, std::min(n, 64));   // quasi-Newton pairs kept (full memory for small networks)
     std::deque<Pair> mem;
-    int status = SNAQ_OPTBL_MAXEVAL, iter = 0, small_f = 0;
+    int status = SNAQ_OPTBL_MAXEVAL, iter = 0, small_f = 0, small_x = 0;
     std::vector<double> d(n), q(n), xn(n), Xls, fls, gn, hdn;
     const double bnd_eps = 1e-12;
     const bool no_unit_step = getenv("SNAQ_OPTBL_NO_UNIT_STEP") != nullptr;
     const int hd_every = getenv("SNAQ_OPTBL_HD_EVERY") ? std::max(1, atoi(getenv("SNAQ_OPTBL_HD_EVERY"))) : 8;
     const bool verbose = getenv("SNAQ_OPTBL_VERBOSE") != nullptr;      // "inside obj with x ..." of the reference (:369-378)
-    while (pb.nlaunches < maxeval) {
+    // maxeval bounds the number of parameter vectors evaluated, as NLopt.maxeval! does (:365); a ladder launch that starts
+    // below the bound is finished
+    while (pb.nevals < maxeval) {
         iter++;
         // free variables: not pinned at a bound by the gradient
         std::vector<char> freev(n, 1);
@@ -303,7 +305,10 @@ extern "C" int snaq_optbl(snaq_ctx *ctx, const snaq_optbl_opts *o, double *x_io,
         x = xn; f = fn; g = gn; hd = hdn;
         if (df <= ftol_abs || df <= ftol_rel * std::fabs(fn)) small_f++; else small_f = 0;
         if (small_f >= 2) { status = SNAQ_OPTBL_FTOL; break; }
-        if (xsmall) { status = SNAQ_OPTBL_XTOL; break; }
+        // XTOL: two consecutive small steps, both taken with curvature information (one short rung of the first
+        // scaled-gradient iteration says nothing about the distance to the optimum)
+        if (xsmall && !mem.empty()) small_x++; else small_x = 0;
+        if (small_x >= 2) { status = SNAQ_OPTBL_XTOL; break; }
     }
     std::memcpy(x_io, x.data(), sizeof(double) * n);
     res->fmin = f;

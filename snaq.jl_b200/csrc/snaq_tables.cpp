@@ -58,11 +58,18 @@ int snaq_build_tables(const snaq_flatnet *f, int ntaxa, SnaqHostTables &o, std::
         auto eMaj = [&](int e) { return (f->edge_flags[e] & SNAQ_EDGE_MAJOR) != 0; };
         auto eIdent = [&](int e) { return (f->edge_flags[e] & SNAQ_EDGE_IDENTIFIABLE) != 0; };
         auto other = [&](int e, int n) { return f->edge_node[2 * e] == n ? f->edge_node[2 * e + 1] : f->edge_node[2 * e]; };
+        // every index a caller hands over is range-checked before it is used as one
+        for (int e = 0; e < E; e++)
+            for (int j = 0; j < 2; j++) {
+                const int n = f->edge_node[2 * e + j];
+                if (n < 0 || n >= N) fail(SNAQ_EINVAL, "edge_node out of range (edge " + std::to_string(f->edge_number[e]) + ")");
+            }
+        if (f->n_leaves < 0 || f->n_leaves > N) fail(SNAQ_EINVAL, "n_leaves out of range");
         std::vector<int> deg(N, 0);
         for (int n = 0; n < N; n++) {
             for (int j = 0; j < 3; j++) {
                 int e = f->node_edge[3 * n + j];
-                if (e >= E) fail(SNAQ_EINVAL, "node_edge out of range");
+                if (e >= E || e < -1) fail(SNAQ_EINVAL, "node_edge out of range");
                 if (e >= 0) {
                     if (f->edge_node[2 * e] != n && f->edge_node[2 * e + 1] != n) fail(SNAQ_EINVAL, "node_edge / edge_node disagree");
                     deg[n]++;

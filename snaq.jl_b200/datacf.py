@@ -76,9 +76,9 @@ def _sort_taxa(names: List[str]) -> List[str]:
 
 
 def readtableCF(path: str, delim: str = ",") -> DataCF:
-    """``readtableCF(file)``: first 4 columns are taxa; CF columns are named
-    CF12_34/CF13_24/CF14_23 (or CF12.34 ...) or else are columns 5,6,7; an optional
-    ``ngenes`` column is kept (src/readquartetdata.jl:97-150)."""
+    """``readtableCF(file)`` (src/readquartetdata.jl:97-140): taxon columns are found by name (t1 | tx1 | tax1 | taxon1,
+    ...), CF columns by name (CF12_34 | CF12.34 | obsCF12 | CF1234, ...); an optional ``ngenes`` column is kept.
+    Like the reference, a table whose columns cannot be identified is an error, not a guess."""
     with open(path, newline="") as fh:
         rd = csv.reader(fh, delimiter=delim)
         header = next(rd)
@@ -86,20 +86,24 @@ def readtableCF(path: str, delim: str = ",") -> DataCF:
     low = [h.strip() for h in header]
 
     def find(*names):
-        for nm in names:
-            if nm in low:
-                return low.index(nm)
+        for i, h in enumerate(low):
+            if h in names:
+                return i
         return None
 
-    c1 = find("CF12_34", "CF12.34")
-    c2 = find("CF13_24", "CF13.24")
-    c3 = find("CF14_23", "CF14.23")
+    tcol = [find(f"t{i}", f"tx{i}", f"tax{i}", f"taxon{i}") for i in (1, 2, 3, 4)]
+    if any(c is None for c in tcol):
+        raise SnaqError("columns for taxon names were not found")
+    c1 = find("CF12_34", "CF12.34", "obsCF12", "CF1234")
+    c2 = find("CF13_24", "CF13.24", "obsCF13", "CF1324")
+    c3 = find("CF14_23", "CF14.23", "obsCF14", "CF1423")
     if c1 is None or c2 is None or c3 is None:
-        c1, c2, c3 = 4, 5, 6
+        raise SnaqError("Could not identify columns with quartet concordance factors (qCFs). Was expecting CF12_34, CF13_24 "
+                        "and CF14_23 for the columns with CF values, or CF12.34 or obsCF12, etc.")
     cn = find("ngenes")
     rows = []
     for r in body:
-        row = [r[0].strip(), r[1].strip(), r[2].strip(), r[3].strip(), r[c1], r[c2], r[c3]]
+        row = [r[tcol[0]].strip(), r[tcol[1]].strip(), r[tcol[2]].strip(), r[tcol[3]].strip(), r[c1], r[c2], r[c3]]
         if cn is not None:
             row.append(r[cn])
         rows.append(row)
