@@ -114,6 +114,28 @@ int snaq_destroy(snaq_ctx *ctx);
 const char *snaq_last_error(const snaq_ctx *ctx);   /* ctx may be NULL: last create error */
 const char *snaq_version(void);
 
+/* ---- quartet-sharded mode: the exchange step -------------------- */
+/* A context created with world_size > 1 keeps the contiguous block [rank*nq/G, (rank+1)*nq/G) of the quartets passed to
+ * snaq_set_data; every rank evaluates the SAME parameter vectors and the per-candidate partial sums of logPseudoLik
+ * (src/pseudolik.jl:1417-1423 is a plain sum over quartets) are combined over NVLink / NVSwitch.  The collective lives
+ * in the library (NCCL is resolved at run time with dlopen; a caller does not bind it):
+ *   snaq_comm_unique_id : rank 0 obtains the 128-byte id (ncclGetUniqueId) and hands it to the other ranks by whatever
+ *                         means the host program has (Julia: Distributed / a file / MPI);
+ *   snaq_comm_init      : every rank, same id: ncclCommInitRank on the context's device, plus the peer mailboxes of the
+ *                         fused epilogue (CUDA IPC).  Collective: all ranks must call it.
+ * Afterwards snaq_eval, snaq_eval_device, snaq_eval_grad and snaq_optbl return the TOTALS over all ranks, bit-identical
+ * on every rank, and every rank must make the same sequence of these calls with the same parameter vectors (they are
+ * collectives).  Small batches (P < 16, the optimiser's objective calls) use ONE kernel launch per <= 4 candidates: the
+ * last block of every rank stores its partial sums into every peer's mailbox through peer memory and adds the entries
+ * in rank order once all have arrived (no second kernel, no NCCL call); larger batches end with an ncclAllReduce of P
+ * doubles on the caller's stream.  Without a communicator snaq_eval / snaq_eval_device return this rank's partial
+ * sums (the caller all-reduces them), and snaq_eval_grad / snaq_optbl are refused (SNAQ_EINVAL).
+ * snaq_comm_info: any out pointer may be NULL.                                                                   */
+#define SNAQ_COMM_ID_BYTES 128
+int snaq_comm_unique_id(void *id128);
+int snaq_comm_init(snaq_ctx *ctx, const void *id128);
+int snaq_comm_info(snaq_ctx *ctx, int32_t *rank, int32_t *world_size, int32_t *has_comm, int32_t *fused_epilogue);
+
 /* ---- data: DataCF resident in HBM (src/types.jl:217-273) ----------------- */
 /* taxa[q*4+i] = 0-based taxon id of the i-th taxon of quartet q, in the data's
  * own order (which fixes the 12|34, 13|24, 14|23 order of obsCF).             */
@@ -164,8 +186,8 @@ int snaq_get_params(snaq_ctx *ctx, double *x, int32_t *numht,
  * parameter vectors (row-major P x nparams).  Stateless evaluation: every
  * sampled quartet is recomputed (the reference's `changed` gating,
  * src/snaq_optimization.jl:202-206, only skips work, never changes a value).
- * In quartet-sharded mode out[p] is this rank's partial sum unless the caller
- * all-reduces it (see snaq_eval_device).                                       */
+ * In quartet-sharded mode out[p] is the total over all ranks once snaq_comm_init
+ * has been called, else this rank's partial sum.                               */
 int snaq_eval(snaq_ctx *ctx, int32_t P, int32_t nparams,
               const double *X, double *out);
 /* Same, X and out already in device memory (used by the in-engine optimiser,
@@ -192,7 +214,10 @@ int snaq_eval_quartets(snaq_ctx *ctx, int32_t nparams, const double *x,
  * to d2 f / d x[i]^2 for edge lengths, 0 for gammas: the initial metric of the quasi-Newton update.
  * f is the per-quartet sum of snaq_eval (same value to rounding).  The derivative sums are formed in 2^-32 fixed point
  * (integer sums: bit-reproducible whatever the order of arrival), every quartet's contribution rounded once: an
- * absolute error of about 1e-10 * sqrt(number of quartets that touch the slot) per entry (a few 1e-7 at 5e5 quartets). */
+ * absolute error of about 1e-10 * sqrt(number of quartets that touch the slot) per entry (a few 1e-7 at 5e5 quartets).
+ * The bins are 96 bits wide (range +-2^63): no table size and no parameter vector inside the bounds can wrap them.
+ * Quartet-sharded contexts: with a communicator attached (snaq_comm_init) f and grad are the totals over all ranks
+ * (identical on every rank); without one the call is refused (SNAQ_EINVAL), as is snaq_optbl.                      */
 int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f,
                    double *grad, double *hdiag);
 
@@ -203,8 +228,9 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f,
 #define SNAQ_OPTBL_MAXEVAL  5
 typedef struct snaq_optbl_opts {
     double ftol_rel, ftol_abs, xtol_rel, xtol_abs;   /* optBL!'s ftolRel, ftolAbs, xtolRel, xtolAbs (all > 0, :350) */
-    int32_t maxeval;     /* NLopt.maxeval! = 1000 in the reference (:365): parameter vectors evaluated (a batch that
-                            starts below the bound is finished, so nevals can exceed it by one ladder)              */
+    int32_t maxeval;     /* NLopt.maxeval! = 1000 in the reference (:365): objective values asked for (every rung of a
+                            ladder counts, a gradient pass counts once; a batch that starts below the bound is
+                            finished, so the count can exceed it by one ladder)                                     */
     int32_t ladder;      /* step lengths tried per line-search launch (default 20)                              */
     uint32_t flags;      /* SNAQ_OPTBL_*                                                                         */
     uint32_t reserved;

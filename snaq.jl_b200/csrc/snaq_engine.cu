@@ -33,6 +33,8 @@
  * Tensor cores are not used: the path is a few exp/log per (quartet, candidate), not a contraction.
  */
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>            // types and prototypes only: the library is resolved at run time (snaq_comm_init), never linked
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -58,7 +60,25 @@
 #define XARG_MAX 448      /* doubles (3.5 KB of kernel parameter space) */
 struct XArg { double v[XARG_MAX]; };
 #define SNAQ_S_DONE 0x80000000u   /* status word in page-locked memory: the kernel has written its results */
-#define LANES_MIN_P 16    /* batches of at least this many candidates use k_eval_lanes */
+#define LANES_MIN_P 16    /* batches of at least this many candidates use the batched kernels */
+#define SNAQ_S_COMM 16u   /* quartet-sharded mode: a peer's partial sums did not arrive (fused epilogue of k_eval_direct) */
+// Quartet-sharded mode, small batches: the all-reduce of the per-candidate partial sums is FUSED into the epilogue of
+// k_eval_direct.  Every rank owns a mailbox array in its own HBM, mapped into every peer through CUDA IPC (NVLink /
+// NVSwitch peer memory): box[slot][sender] = {v[4], seq}.  The last block of rank r stores its partial sums and then the
+// launch's sequence number into box[seq & 1][r] of EVERY rank (plain stores over NVLink, fence.sys in between), spins
+// until the sequence number has arrived in all `world` entries of its own box[seq & 1], and adds the entries in rank
+// order: every rank gets the same bits, with one launch and no second kernel.  Two slots, because a fast rank may
+// already deliver launch k+1 while a slow one still reads launch k (it cannot deliver k+2 before the slow one has
+// delivered k+1, i.e. finished k).
+struct PeerMail { double v[4]; unsigned long long seq; unsigned long long pad[3]; };   // 64 bytes
+#define SNAQ_MAX_WORLD 16
+struct PeerBox {
+    PeerMail *peer[SNAQ_MAX_WORLD];   // peer[r]: rank r's box array [2][world] as mapped into this process (peer[rank] = own)
+    int rank, world;
+    unsigned long long seq;            // 0: not sharded / no fused epilogue for this launch
+};
+#define RN_TQ 64          /* k_eval_runs: quartets per tree-like tile (64 x 16 B weight pairs) */
+#define RN_TQC 32         /*              quartets per 4-cycle tile (32 x 32 B weights)        */
 
 // --------------------------------------------------------------------------------------------
 // math tables (copied to shared memory by every evaluation kernel)
@@ -344,23 +364,42 @@ __global__ void __launch_bounds__(256) k_resample_ci(const double *__restrict__ 
 
 __global__ void __launch_bounds__(256) k_weights(const uint32_t *__restrict__ perm, const uint8_t *__restrict__ qhdr,
                                                  const double *__restrict__ obs, const uint8_t *__restrict__ sampled,
-                                                 int64_t nq, int64_t nA, double *__restrict__ W, double2 *__restrict__ WA,
-                                                 double *__restrict__ wpart) {
+                                                 int64_t nq, int64_t nA, int64_t nAB, double *__restrict__ W, double2 *__restrict__ WA,
+                                                 double *__restrict__ wpart, const uint32_t *__restrict__ rec_off, uint32_t ntAB,
+                                                 unsigned char *__restrict__ pack) {
+    // WA[i] = (W0, W1) for every tree-like quartet i < nAB (k_eval_direct / k_eval_grad stream [0, nA), k_eval_runs all of
+    // them); wpart[2 b] = the block's sum of W3 over the short additive programs [0, nA), wpart[2 b + 1] = over every
+    // quartet that is not a bad-diamond-I 4-cycle (those keep their W3 with the per-quartet penalty rule)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double c3 = 0.0;
+    double c3 = 0.0, c3b = 0.0;
     if (i < nq) {
         const int64_t q = perm[i];
         double o[3] = {obs[3 * q], obs[3 * q + 1], obs[3 * q + 2]};
         double w[4];
-        snaq_weights(qhdr[i], o, sampled ? sampled[q] : 1, w);
+        const unsigned h = qhdr[i];
+        snaq_weights(h, o, sampled ? sampled[q] : 1, w);
         reinterpret_cast<double4 *>(W)[i] = make_double4(w[0], w[1], w[2], w[3]);
-        if (i < nA) { WA[i] = make_double2(w[0], w[1]); c3 = w[3]; }
+        if (i < nAB) WA[i] = make_double2(w[0], w[1]);
+        if (pack) {                                   // the packed tile stream of k_eval_runs carries its own copy of the weights
+            if (i < nAB) {
+                const uint32_t t = (uint32_t)(i / RN_TQ), j = (uint32_t)(i % RN_TQ);
+                reinterpret_cast<double2 *>(pack + (size_t)rec_off[t] * 16)[j] = make_double2(w[0], w[1]);
+            } else {
+                const uint32_t t = ntAB + (uint32_t)((i - nAB) / RN_TQC), j = (uint32_t)((i - nAB) % RN_TQC);
+                reinterpret_cast<double4 *>(pack + (size_t)rec_off[t] * 16)[j] = make_double4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        if (i < nA) c3 = w[3];
+        if (SNAQ_HDR_KIND(h) != SNAQ_KIND_T5BD1) c3b = w[3];
     }
-    __shared__ double red[8];
-    for (int o = 16; o > 0; o >>= 1) c3 += __shfl_down_sync(0xffffffffu, c3, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c3;
+    __shared__ double red[16];
+    for (int o = 16; o > 0; o >>= 1) { c3 += __shfl_down_sync(0xffffffffu, c3, o); c3b += __shfl_down_sync(0xffffffffu, c3b, o); }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = c3; red[8 + (threadIdx.x >> 5)] = c3b; }
     __syncthreads();
-    if (threadIdx.x == 0) wpart[blockIdx.x] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+    if (threadIdx.x < 2) {
+        const double *r = red + 8 * threadIdx.x;
+        wpart[2 * blockIdx.x + threadIdx.x] = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    }
 }
 
 // parity descriptors: which / typeHyb per hybrid / formula, original order
@@ -413,8 +452,8 @@ __device__ __forceinline__ unsigned range_check(double v, double hi) { return (v
 // Expanded parameter vectors (snaq_expand_row); also the one place where the bounds of the reference's
 // update! are checked on the device (src/snaq_optimization.jl:213,221,228).
 //   tiled == 0: XF[p][row]                       (thread-per-quartet kernel)
-//   tiled == 1: XF[p/32][row][p%32], P padded up to a multiple of 32 with copies of the last candidate:
-//               the lane-per-candidate kernel copies one group's tile with a single TMA bulk copy
+//   tiled == w (32 or 64): XF[p/w][row][p%w], P padded up to a multiple of w with copies of the last candidate:
+//               the batched kernels copy one group's tile with a single TMA bulk copy
 __global__ void __launch_bounds__(256) k_expand_x(SnaqTables T, const double *__restrict__ X, const double *__restrict__ xconst,
                                                   int P, int nh, int nt, int tiled, double *__restrict__ XF,
                                                   uint32_t *__restrict__ status) {
@@ -430,12 +469,12 @@ __global__ void __launch_bounds__(256) k_expand_x(SnaqTables T, const double *__
         }
         XF[idx] = snaq_expand_row(T, M, x, xconst, row);
     } else {
-        const int Ppad = (P + 31) & ~31;
+        const int Ppad = (P + tiled - 1) / tiled * tiled;
         if (idx >= (int64_t)Ppad * T.n_full) return;
-        const int lane = (int)(idx & 31);
-        const int64_t gr = idx >> 5;                       // group * n_full + row
+        const int lane = (int)(idx % tiled);
+        const int64_t gr = idx / tiled;                    // group * n_full + row
         const int g = (int)(gr / T.n_full), row = (int)(gr - (int64_t)g * T.n_full);
-        const int p = min(g * 32 + lane, P - 1);
+        const int p = min(g * tiled + lane, P - 1);
         const double *x = X + (size_t)p * T.nparams;
         if (row < T.nparams) {
             const unsigned st = range_check(x[row], (row >= nh && row < nh + nt) ? 1.0e300 : 1.0);
@@ -1093,6 +1132,335 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
 }
 
 /*
+ * Run-length batched kernel (the default for P >= 16 on the plain table).
+ *
+ * The class-sorted table keeps quartets with the SAME program next to each other, and a quartet's expected CFs depend on
+ * its program only.  set_network therefore also builds a run table (one program per run of identical programs: off_u /
+ * prog_u) and from it a PACKED TILE STREAM: one self-contained record per tile of 64 tree-like (32 four-cycle) quartets,
+ *     [ 1024 B per-quartet weights | 32 B descriptor (bit mask of the run heads, ...) | program offsets | programs ],
+ * so that a tile arrives with ONE TMA bulk copy.  The kernel evaluates a program once per run and candidate and then
+ * streams the run's per-quartet weights: two FMAs per (quartet, candidate) for tree-like quartets (w0 * log(major) and
+ * w1 * (t1 + log 3)), three for 4-cycle quartets -- no compares, no offsets, no program loads per quartet.  The constants
+ * sum_q W3 are added once by the reduction pass (negw3[1]).  Bad-diamond-I 4-cycles keep the per-quartet -1e15 penalty
+ * semantics of src/pseudolik.jl:1394-1396 (snaq_loglik_t5).
+ *
+ * grid (gx, groups of 32 * CPL candidates); a lane holds CPL candidates (the weights are loaded once for all of them).
+ * Every WARP owns a ring of RN_NST stages and walks whole SEGMENTS (tps consecutive tiles; tps depends on the table
+ * only): one partial row per segment, summed in tile order by one warp, so a value depends neither on the grid nor on
+ * the batch the candidate was evaluated in.
+ */
+#define RN_NST 3
+#define RN_MIN_AVG_RUN 32   /* tables whose runs are shorter on average keep the per-quartet batched kernels */
+#define RN_W_BYTES 1024
+#define RN_DESC_AT RN_W_BYTES
+#define RN_OFF_AT (RN_W_BYTES + 32)
+#define RN_PROG_CHUNKS 128  /* program chunks a tile record can hold (else: read from the run table in global memory) */
+#define RN_STAGE_BYTES (RN_OFF_AT + 272 + RN_PROG_CHUNKS * 8)        /* 2352: the largest record */
+struct __align__(16) RunTile {
+    unsigned long long mask;   // bit j: quartet q0 + j starts a run
+    uint32_t q0;               // sorted position of the first quartet
+    uint32_t pbeg;             // first program chunk of the tile's runs in prog_u (used when the programs are not in the record)
+    uint16_t n;                // number of quartets
+    uint16_t prog_at;          // byte offset of the programs inside the record
+    uint16_t flags;            // bit 0: 4-cycle tile (weights are W[q], 32 B); bit 1: programs are in the record
+    uint16_t nruns;
+    uint32_t u0, pad;          // run of quartet q0
+};
+static_assert(sizeof(RunTile) == 32, "RunTile");
+struct RunsMeta {
+    uint32_t ntiles, nseg, tps, nul;
+    int64_t nA;                // sorted positions [0,nA) additive, then type-2/4 terms, then (own tiles) 4-cycles
+    int noreuse;
+};
+
+// pass 1 over the tiles: descriptor and record size (16-byte units); pass 2 (after the scan): offsets and programs
+__global__ void __launch_bounds__(256) k_run_tiles(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ uidx,
+                                                   const uint32_t *__restrict__ off_u, int64_t nq, int64_t nAB, uint32_t ntAB,
+                                                   uint32_t ntiles, RunTile *__restrict__ tdesc, uint32_t *__restrict__ size16) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    RunTile d;
+    const bool isC = t >= ntAB;
+    const int64_t q0 = isC ? nAB + (int64_t)(t - ntAB) * RN_TQC : (int64_t)t * RN_TQ;
+    const int64_t n = isC ? min((int64_t)RN_TQC, nq - q0) : min((int64_t)RN_TQ, nAB - q0);
+    unsigned long long m = 0ull;
+    for (int j = 0; j < (int)n; j++) m |= (unsigned long long)(flags[q0 + j] & 1u) << j;
+    d.mask = m;
+    d.u0 = uidx[q0] - 1u;
+    d.nruns = (uint16_t)(__popcll(m >> 1) + 1);
+    d.pbeg = off_u[d.u0];
+    const uint32_t plen = off_u[d.u0 + d.nruns] - d.pbeg;
+    const bool staged = plen <= (uint32_t)RN_PROG_CHUNKS;
+    const uint32_t ob = (((uint32_t)d.nruns + 1u) * 4u + 15u) & ~15u;
+    d.q0 = (uint32_t)q0; d.n = (uint16_t)n;
+    d.prog_at = (uint16_t)(RN_OFF_AT + ob);
+    d.flags = (uint16_t)((isC ? 1u : 0u) | (staged ? 2u : 0u));
+    d.pad = 0u;
+    tdesc[t] = d;
+    size16[t] = (RN_OFF_AT + ob + (staged ? ((plen * 8u + 15u) & ~15u) : 0u)) / 16u;
+}
+__global__ void __launch_bounds__(256) k_run_fill(const RunTile *__restrict__ tdesc, const uint32_t *__restrict__ rec_off,
+                                                  const uint32_t *__restrict__ off_u, const uint2 *__restrict__ prog_u, uint32_t ntiles,
+                                                  unsigned char *__restrict__ pack) {
+    // one warp per tile
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (t >= ntiles) return;
+    const RunTile d = tdesc[t];
+    unsigned char *rec = pack + (size_t)rec_off[t] * 16;
+    if (lane == 0) *reinterpret_cast<RunTile *>(rec + RN_DESC_AT) = d;
+    uint32_t *roff = reinterpret_cast<uint32_t *>(rec + RN_OFF_AT);
+    const uint32_t nslot = (d.prog_at - RN_OFF_AT) / 4u;
+    for (uint32_t k = lane; k < nslot; k += 32u) roff[k] = k <= d.nruns ? off_u[d.u0 + k] - d.pbeg : 0u;   // relative to the tile's first program
+    if (d.flags & 2u) {
+        const uint32_t plen = off_u[d.u0 + d.nruns] - d.pbeg;
+        uint2 *dst = reinterpret_cast<uint2 *>(rec + d.prog_at);
+        for (uint32_t c = lane; c < ((plen + 1u) & ~1u); c += 32u) dst[c] = c < plen ? prog_u[d.pbeg + c] : make_uint2(0u, 0u);
+    }
+}
+
+// the candidates of a lane in the xf tile [row][CPL * 32]: element (row, c, lane)
+struct XLaneS {
+    const double *p; unsigned stride;
+    __device__ __forceinline__ double operator()(unsigned s) const { return p[s * stride]; }
+};
+
+template <int WARPS, int CPL>
+__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && CPL == 1) ? 2 : 1) k_eval_runs(const unsigned char *__restrict__ pack, const uint32_t *__restrict__ rec_off,
+                                                        const uint2 *__restrict__ prog_u, const RunsMeta rm,
+                                                        const double *__restrict__ XFT, const int n_full,
+                                                        double *__restrict__ partial, const int Ppad, uint32_t *__restrict__ status) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int TW = 32 * CPL;                                                     // candidates per block = tile width
+    double *mt = reinterpret_cast<double *>(smem);                                   // 384 B
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 384);                       // [0] xf tile, [1 + warp * NST + s]
+    constexpr size_t BAR_BYTES = ((1 + WARPS * RN_NST) * 8 + 127) & ~size_t(127);
+    double *xs = reinterpret_cast<double *>(smem + 384 + BAR_BYTES);
+    unsigned char *ring = smem + 384 + BAR_BYTES + (size_t)n_full * TW * 8;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = blockIdx.y;
+    const unsigned gw = blockIdx.x * WARPS + warp, nwg = gridDim.x * WARPS;          // this warp among the group's warps
+    uint64_t *wbar = bars + 1 + warp * RN_NST;
+    unsigned char *wring = ring + (size_t)warp * RN_NST * RN_STAGE_BYTES;
+    const bool noreuse = rm.noreuse != 0;
+    const unsigned nul = rm.nul;
+    // the k-th tile of this warp: segments gw, gw + nwg, ... of tps consecutive tiles each
+    auto tile_of = [&](unsigned k) -> unsigned {
+        const unsigned seg = gw + (k / rm.tps) * nwg;
+        const unsigned t = seg * rm.tps + k % rm.tps;
+        return (seg < rm.nseg && t < rm.ntiles) ? t : 0xffffffffu;
+    };
+    // (a segment's tiles past ntiles only occur in the last segment: the warp's sequence ends there)
+    auto issue = [&](unsigned o0, unsigned o1, unsigned sg) {                        // lane 0 only: one bulk copy per tile
+        const unsigned bytes = (o1 - o0) * 16u;
+        mbar_expect_tx(&wbar[sg], bytes);
+        tma_load_1d(wring + sg * RN_STAGE_BYTES, pack + (size_t)o0 * 16, bytes, &wbar[sg]);
+    };
+    if (tid == 0) mbar_init(&bars[0], 1);
+    if (lane == 0) {
+        for (int k = 0; k < RN_NST; k++) mbar_init(&wbar[k], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bars[0], (unsigned)n_full * TW * 8u);
+        tma_load_1d(xs, XFT + (size_t)g * n_full * TW, (unsigned)n_full * TW * 8u, &bars[0]);
+    }
+    // the warp's first tiles are requested before anything else is waited for
+    unsigned kiss = 0;                                                               // tiles requested so far
+    for (; kiss < RN_NST; kiss++) {
+        const unsigned t = tile_of(kiss);
+        if (t == 0xffffffffu) break;
+        if (lane == 0) issue(__ldg(rec_off + t), __ldg(rec_off + t + 1), kiss);
+    }
+    unsigned tn = tile_of(kiss);                                                     // next tile to request, and its record
+    unsigned no0 = 0, no1 = 0;
+    if (tn != 0xffffffffu) { no0 = __ldg(rec_off + tn); no1 = __ldg(rec_off + tn + 1); }
+    __syncwarp();
+    const SnaqMath M = load_math_tables(mt, tid);
+    unsigned st = 0;
+    mbar_wait(&bars[0], 0);
+    __syncthreads();
+    const double *xl = xs + lane;
+    unsigned sg = 0, phase = 0;
+    // segment sums: w0*L (a0, b0, e0, f0), w1*T (a1, b1, e1, f1), 4-cycles.  Four independent accumulators per product
+    // and candidate: the FP64 pipe has a long dependent-issue latency and a block has few warps (the xf tile is large)
+    double a0[CPL], a1[CPL], b0[CPL], b1[CPL], e0[CPL], e1[CPL], f0[CPL], f1[CPL], cacc[CPL];
+    double cL[CPL], cT[CPL], c2[CPL];                           // the current run's constants: tree-like (L, T); 4-cycle (l0, l1, l2)
+    double cz[CPL][3];                                          // bad diamond I: the three expected CFs
+    bool cBD1 = false;
+#pragma unroll
+    for (int c = 0; c < CPL; c++) {
+        a0[c] = a1[c] = b0[c] = b1[c] = e0[c] = e1[c] = f0[c] = f1[c] = cacc[c] = 0.0;
+        cL[c] = cT[c] = c2[c] = 0.0; cz[c][0] = cz[c][1] = cz[c][2] = 0.0;
+    }
+#pragma unroll 1
+    for (unsigned k = 0;; k++) {
+        const unsigned t = tile_of(k);
+        if (t == 0xffffffffu) break;
+        mbar_wait(&wbar[sg], phase);
+        const unsigned char *stg = wring + sg * RN_STAGE_BYTES;
+        const RunTile d = *reinterpret_cast<const RunTile *>(stg + RN_DESC_AT);
+        const uint32_t *soff = reinterpret_cast<const uint32_t *>(stg + RN_OFF_AT);
+        const bool staged = (d.flags & 2u) != 0;
+        const uint2 *sprog = reinterpret_cast<const uint2 *>(stg + d.prog_at);
+        const bool isC = (d.flags & 1u) != 0;
+        const bool seg_first = (k % rm.tps) == 0;
+        auto chunk = [&](uint32_t c) { return staged ? sprog[c] : __ldg(prog_u + d.pbeg + c); };
+        // the constants of the r-th run of the tile, whose first quartet here sits at sorted position pos
+        auto compute = [&](uint32_t r, int64_t pos) {
+            const uint32_t c0 = soff[r], c1 = soff[r + 1];
+            if (isC) {
+                const uint2 w = chunk(c0);
+                cBD1 = (w.y & 0xffffu) == nul;
+#pragma unroll
+                for (int c = 0; c < CPL; c++) {
+                    const XLaneS xf{xl + 32 * c, (unsigned)TW};
+                    if (!cBD1) {
+                        const double g2 = xf(w.x & 0xffffu), ca = xf(w.x >> 16), cm = xf(w.y & 0xffffu), cb = xf(w.y >> 16);
+                        const double g1 = 1.0 - g2;
+                        const double y5 = snaq_exp(-snaq_clamp10(cm - ca), M), y6 = snaq_exp(-snaq_clamp10(cb - cm), M);
+                        const double cf0 = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;
+                        const double cf1 = g1 * 1.0 / 3.0 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
+                        const double cf2 = g1 * 1.0 / 3.0 * y5 + g2 * 1.0 / 3.0 * y6;
+                        cL[c] = snaq_log_pos(cf0, M); cT[c] = snaq_log_pos(cf1, M); c2[c] = snaq_log_pos(cf2, M);
+                    } else {
+                        const uint16_t pcw[4] = {(uint16_t)(w.x & 0xffffu), (uint16_t)(w.x >> 16), (uint16_t)nul, (uint16_t)nul};
+                        snaq_t5_cf(SNAQ_KIND_T5BD1, pcw, xf, M, cz[c]);
+                    }
+                }
+            } else if (pos >= rm.nA) {
+                const uint16_t *pc = staged ? reinterpret_cast<const uint16_t *>(sprog + c0)
+                                            : reinterpret_cast<const uint16_t *>(prog_u + d.pbeg + c0);
+#pragma unroll
+                for (int c = 0; c < CPL; c++) {
+                    const XLaneS xf{xl + 32 * c, (unsigned)TW};
+                    const double tt = snaq_tree_terms_t1(pc, xf, M, st);
+                    const double major = fma(SNAQ_K_M23, snaq_exp(-tt, M), 1.0);
+                    if (major < 0.0) st |= SNAQ_S_NEGLEN;
+                    cL[c] = snaq_log(major, M);
+                    cT[c] = tt + SNAQ_K_LOG3;
+                }
+            } else {
+                double t0[CPL], t1[CPL];
+#pragma unroll
+                for (int c = 0; c < CPL; c++) { t0[c] = 0.0; t1[c] = 0.0; }
+#pragma unroll 1
+                for (uint32_t cc = c0; cc < c1; ++cc) {
+                    const uint2 w = chunk(cc);
+#pragma unroll
+                    for (int c = 0; c < CPL; c++) {
+                        const XLaneS xf{xl + 32 * c, (unsigned)TW};
+                        t0[c] += xf(w.x & 0xffffu) - xf(w.x >> 16);
+                        t1[c] += xf(w.y & 0xffffu) - xf(w.y >> 16);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < CPL; c++) {
+                    const double tt = snaq_clamp10(t0[c] + t1[c]);
+                    cL[c] = snaq_log_pos(fma(SNAQ_K_M23, snaq_exp(-tt, M), 1.0), M);
+                    cT[c] = tt + SNAQ_K_LOG3;
+                }
+            }
+        };
+        const double2 *sw = reinterpret_cast<const double2 *>(stg);
+        if (!isC && !noreuse && (d.mask >> 1) == 0ull && d.n == RN_TQ) {
+            // the whole tile is one run (the common case on large tables): straight-line, no loop control
+            if ((d.mask & 1ull) || seg_first) compute(0u, (int64_t)d.q0);
+#pragma unroll
+            for (int i = 0; i < RN_TQ; i += 4) {
+                const double2 wa = sw[i], wb = sw[i + 1], wc = sw[i + 2], wd = sw[i + 3];
+#pragma unroll
+                for (int c = 0; c < CPL; c++) {
+                    a0[c] = fma(wa.x, cL[c], a0[c]); a1[c] = fma(wa.y, cT[c], a1[c]);
+                    b0[c] = fma(wb.x, cL[c], b0[c]); b1[c] = fma(wb.y, cT[c], b1[c]);
+                    e0[c] = fma(wc.x, cL[c], e0[c]); e1[c] = fma(wc.y, cT[c], e1[c]);
+                    f0[c] = fma(wd.x, cL[c], f0[c]); f1[c] = fma(wd.y, cT[c], f1[c]);
+                }
+            }
+        } else {
+            unsigned j = 0, r = 0;
+            const unsigned n = d.n;
+#pragma unroll 1
+            while (j < n) {
+                const unsigned long long rest = (d.mask >> j) >> 1;
+                const unsigned jend = rest ? min(j + (unsigned)__ffsll((long long)rest), n) : n;
+                if (j > 0) r++;
+                if (j > 0 || (d.mask & 1ull) || seg_first) compute(r, (int64_t)d.q0 + j);
+                if (!isC) {
+                    if (!noreuse) {
+                        unsigned i = j;
+#pragma unroll 1
+                        for (; i + 3 < jend; i += 4) {
+                            const double2 wa = sw[i], wb = sw[i + 1], wc = sw[i + 2], wd = sw[i + 3];
+#pragma unroll
+                            for (int c = 0; c < CPL; c++) {
+                                a0[c] = fma(wa.x, cL[c], a0[c]); a1[c] = fma(wa.y, cT[c], a1[c]);
+                                b0[c] = fma(wb.x, cL[c], b0[c]); b1[c] = fma(wb.y, cT[c], b1[c]);
+                                e0[c] = fma(wc.x, cL[c], e0[c]); e1[c] = fma(wc.y, cT[c], e1[c]);
+                                f0[c] = fma(wd.x, cL[c], f0[c]); f1[c] = fma(wd.y, cT[c], f1[c]);
+                            }
+                        }
+#pragma unroll 1
+                        for (; i < jend; i++) {
+                            const double2 wa = sw[i];
+#pragma unroll
+                            for (int c = 0; c < CPL; c++) { a0[c] = fma(wa.x, cL[c], a0[c]); a1[c] = fma(wa.y, cT[c], a1[c]); }
+                        }
+                    } else {
+                        // measurement aid (SNAQ_REUSE=0): the program is evaluated again for every quartet
+#pragma unroll 1
+                        for (unsigned i = j; i < jend; i++) {
+                            compute(r, (int64_t)d.q0 + j);
+                            const double2 wa = sw[i];
+#pragma unroll
+                            for (int c = 0; c < CPL; c++) { a0[c] = fma(wa.x, cL[c], a0[c]); a1[c] = fma(wa.y, cT[c], a1[c]); }
+                        }
+                    }
+                } else {
+                    const double4 *sw4 = reinterpret_cast<const double4 *>(stg);
+#pragma unroll 1
+                    for (unsigned i = j; i < jend; i++) {
+                        if (noreuse) compute(r, (int64_t)d.q0 + j);
+                        const double4 w4 = sw4[i];
+                        if (!cBD1) {
+#pragma unroll
+                            for (int c = 0; c < CPL; c++) {
+                                a0[c] = fma(w4.x, cL[c], a0[c]);
+                                b0[c] = fma(w4.y, cT[c], b0[c]);
+                                cacc[c] = fma(w4.z, c2[c], cacc[c]);
+                            }
+                        } else {
+                            const double wq[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                            for (int c = 0; c < CPL; c++) cacc[c] += snaq_loglik_t5(cz[c], wq, M, st, nullptr);   // its own W3 and the per-quartet penalty
+                        }
+                    }
+                }
+                j = jend;
+            }
+        }
+        __syncwarp();                                                  // every lane is done with this stage
+        if (tn != 0xffffffffu) {
+            if (lane == 0) issue(no0, no1, sg);
+            kiss++;
+            tn = tile_of(kiss);
+            if (tn != 0xffffffffu) { no0 = __ldg(rec_off + tn); no1 = __ldg(rec_off + tn + 1); }   // consumed one tile later
+        }
+        if (++sg == RN_NST) { sg = 0; phase ^= 1u; }
+        // the segment is complete after its last tile: one partial row per segment
+        if ((k % rm.tps) == rm.tps - 1 || t + 1 == rm.ntiles) {
+            const unsigned seg = t / rm.tps;
+#pragma unroll
+            for (int c = 0; c < CPL; c++) {
+                partial[(size_t)seg * Ppad + TW * g + 32 * c + lane] =
+                    (((a0[c] + b0[c]) + (e0[c] + f0[c])) - ((a1[c] + b1[c]) + (e1[c] + f1[c]))) + cacc[c];
+                a0[c] = a1[c] = b0[c] = b1[c] = e0[c] = e1[c] = f0[c] = f1[c] = cacc[c] = 0.0;
+            }
+        }
+    }
+    if (st) atomicOr(status, st);
+}
+
+/*
  * Thread per quartet (class-sorted order), at most PC candidates per launch: the HBM-bound path of a single
  * objective call (P = 1) and of small batches.  One persistent launch, no block-level synchronisation in the
  * main loops: every WARP owns a ring of QD_NST shared-memory stages fed by TMA bulk copies (cp.async.bulk +
@@ -1126,7 +1494,8 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
               double *__restrict__ partial, double *__restrict__ out, const double *__restrict__ negw3,
               unsigned int *__restrict__ ticket, double *__restrict__ expcf, double *__restrict__ logpl,
               double *__restrict__ deltacf, uint32_t *__restrict__ status, unsigned long long *__restrict__ trace,
-              uint32_t *__restrict__ status_out, const int use_xarg, const double *__restrict__ pen, const __grid_constant__ XArg xarg) {
+              uint32_t *__restrict__ status_out, const int use_xarg, const double *__restrict__ pen, const __grid_constant__ PeerBox box,
+              const __grid_constant__ XArg xarg) {
     constexpr int BLOCK = 256;
     extern __shared__ __align__(128) unsigned char smem[];
     double *mt = reinterpret_cast<double *>(smem);                        // 48 doubles, 128-byte aligned
@@ -1325,6 +1694,8 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
     if (s_last) {
         __threadfence();
         const double cst = OUT ? 0.0 : __ldcg(negw3);
+        __shared__ double s_val[4];
+        const bool fused = !OUT && box.seq != 0ull;        // quartet-sharded: the all-reduce over the ranks happens here
         for (int p = 0; p < P; p++) {
             double sp = 0.0;
             for (unsigned b = tid; b < gridDim.x; b += BLOCK) sp += __ldcg(partial + (size_t)b * PC + p);
@@ -1336,8 +1707,39 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
                 double tot = 0.0;
 #pragma unroll
                 for (int k = 0; k < BLOCK / 32; k++) tot += red[k];
-                out[p] = -tot - cst;
+                if (fused) s_val[p & 3] = -tot - cst;
+                else out[p] = -tot - cst;
             }
+        }
+        if (fused) {
+            __syncthreads();
+            const unsigned slot = (unsigned)(box.seq & 1ull);
+            if ((int)tid < box.world) {
+                // deliver this rank's partial sums to rank `tid` (plain stores through the peer mapping), then the flag
+                volatile PeerMail *m = box.peer[tid] + (size_t)slot * box.world + box.rank;
+                for (int p = 0; p < P; p++) m->v[p] = s_val[p];
+                __threadfence_system();
+                m->seq = box.seq;
+                // and wait for rank `tid`'s entry in our own box
+                const volatile PeerMail *in = box.peer[box.rank] + (size_t)slot * box.world + tid;
+                unsigned long long t0;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                while (in->seq != box.seq) {
+                    unsigned long long t1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 4000000000ull) { atomicOr(status, SNAQ_S_COMM); break; }      // 4 s: a peer is gone
+                }
+                __threadfence_system();
+            }
+            __syncthreads();
+            if ((int)tid < P) {
+                const volatile PeerMail *in = box.peer[box.rank] + (size_t)slot * box.world;
+                double tot = 0.0;
+                for (int r = 0; r < box.world; r++) tot += in[r].v[tid];           // rank order: the same bits on every rank
+                out[tid] = tot;
+            }
+            __threadfence_system();
+            __syncthreads();
         }
         if (tid == 0) {
             *ticket = 0u;
@@ -1361,6 +1763,40 @@ k_eval_direct(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__res
  * A block's bins are exact in double, and the last block adds the per-block rows in block order.  The chain rule through the expansion x -> xf is
  * snaq_grad_backprop on the host (a few hundred rows).
  */
+// One gradient bin = 96-bit two's-complement fixed point (2^-32) held as three 32-bit words in shared memory (a 64-bit
+// shared-memory atomic is a compare-and-swap loop on sm_100; 32-bit adds are native).  Adds the sign-extended 64-bit q:
+// the carry of the low word is known from the value its add returns and is folded into the add of the middle word,
+// whose own carry (rare) goes to the top word.  Range +-2^63 value units per block and slot: it cannot wrap, whatever
+// the table size and however close an expected CF comes to 0 (a single quartet's derivative is below 2^31 value units,
+// its weights being at most 100 and every denominator at least exp(-10) / 3).
+__device__ __forceinline__ void bin_add96(unsigned *lo, unsigned *hi, unsigned *ext, unsigned slot, long long q) {
+    const unsigned ql = (unsigned)q, qh = (unsigned)((unsigned long long)q >> 32), qe = q < 0 ? 0xffffffffu : 0u;
+    const unsigned old = atomicAdd(&lo[slot], ql);
+    const unsigned inc = qh + ((old + ql < old) ? 1u : 0u);
+    const unsigned c2a = (inc < qh) ? 1u : 0u;
+    const unsigned oldh = atomicAdd(&hi[slot], inc);
+    const unsigned e = qe + c2a + ((oldh + inc < oldh) ? 1u : 0u);
+    if (e) atomicAdd(&ext[slot], e);
+}
+// the same for a contribution of any size (|v| < 2^63 value units): integer part and 2^-32 fraction are formed separately.
+// Needed for the deduplicated table, where one entry stands for a whole run of quartets (its weights are sums) and a
+// single contribution can exceed the 2^31 value units that fit the 64-bit form
+__device__ __forceinline__ void bin_add96_wide(unsigned *lo, unsigned *hi, unsigned *ext, unsigned slot, double v) {
+    const long long I = __double2ll_rn(v);
+    const long long F = __double2ll_rn((v - (double)I) * 4294967296.0);      // |F| <= 2^31
+    const unsigned fl = (unsigned)F;
+    const unsigned old = atomicAdd(&lo[slot], fl);
+    const long long U = I + (F >> 32) + ((old + fl < old) ? 1ll : 0ll);       // upper 64 bits of (I << 32) + F, plus the carry
+    const unsigned uh = (unsigned)U, ue = (unsigned)((unsigned long long)U >> 32);
+    const unsigned oldh = atomicAdd(&hi[slot], uh);
+    const unsigned e = ue + ((oldh + uh < oldh) ? 1u : 0u);
+    if (e) atomicAdd(&ext[slot], e);
+}
+#define QG_WIDE_FROM 33554432.0     /* 2^25 value units: contributions of this size and more take bin_add96_wide (the warp-aggregated
+                                       sum of 32 smaller ones still fits 64 bits) */
+__device__ __forceinline__ double bin_value96(unsigned lo, unsigned hi, unsigned ext) {
+    return (double)(long long)(((unsigned long long)ext << 32) | (unsigned long long)hi) + (double)lo * (1.0 / 4294967296.0);
+}
 #define QG_SCALE 4294967296.0
 #ifndef QG_RUN
 #define QG_RUN 4        /* consecutive 64-quartet tiles a warp takes before the next warp's run begins */
@@ -1384,12 +1820,13 @@ k_eval_grad_small(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *_
     double *xs = reinterpret_cast<double *>(smem + 512 + 8 * QD_SPAN * 8);
     const int n_full = T.n_full;
     unsigned int *bins_lo = reinterpret_cast<unsigned int *>(xs + n_full);   // [n_full] low words
-    unsigned int *bins_hi = bins_lo + n_full;                                // [n_full] high words
-    unsigned int *hb_lo = bins_hi + n_full, *hb_hi = hb_lo + n_full;         // WANT_H: curvature bins (same format)
+    unsigned int *bins_hi = bins_lo + n_full;                                // [n_full] middle words
+    unsigned int *bins_ex = bins_hi + n_full;                                // [n_full] top words (see bin_add96)
+    unsigned int *hb_lo = bins_ex + n_full, *hb_hi = hb_lo + n_full, *hb_ex = hb_hi + n_full;   // WANT_H: curvature bins (same format)
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     unsigned st = 0;
     const SnaqMath M = load_math_tables(mt, (int)tid);
-    double *xraw = reinterpret_cast<double *>(bins_lo + (WANT_H ? 4 : 2) * n_full);     // [nparams] the candidate itself
+    double *xraw = reinterpret_cast<double *>(bins_lo + (((WANT_H ? 6 : 3) * n_full + 1) & ~1));     // [nparams] the candidate itself
     for (int row = (int)tid; row < T.nparams; row += BLOCK) {
         const double v = use_xarg ? xarg.v[row] : X[row];
         st |= range_check(v, (row >= nh && row < nh + nt) ? 1.0e300 : 1.0);
@@ -1400,28 +1837,28 @@ k_eval_grad_small(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *_
         xs[row] = snaq_expand_row(T, M, xraw, xconst, row);
         bins_lo[row] = 0u;
         bins_hi[row] = 0u;
-        if (WANT_H) { hb_lo[row] = 0u; hb_hi[row] = 0u; }
+        bins_ex[row] = 0u;
+        if (WANT_H) { hb_lo[row] = 0u; hb_hi[row] = 0u; hb_ex[row] = 0u; }
     }
     __syncthreads();
     const unsigned gwarp = blockIdx.x * (BLOCK / 32) + warp, nwarps = gridDim.x * (BLOCK / 32);
     const unsigned nul = (unsigned)T.n_xe;
     double acc = 0.0;
     auto addq = [&](unsigned slot, long long q) {
-        if (slot != nul) {
-            const unsigned lo = (unsigned)q, hi = (unsigned)((unsigned long long)q >> 32);
-            const unsigned old = atomicAdd(&bins_lo[slot], lo);
-            atomicAdd(&bins_hi[slot], hi + ((old + lo < old) ? 1u : 0u));
-        }
+        if (slot != nul) bin_add96(bins_lo, bins_hi, bins_ex, slot, q);
     };
-    auto add = [&](unsigned slot, double v) { addq(slot, __double2ll_rn(v * QG_SCALE)); };
+    auto add = [&](unsigned slot, double v) {
+        if (fabs(v) < QG_WIDE_FROM) addq(slot, __double2ll_rn(v * QG_SCALE));
+        else if (slot != nul) bin_add96_wide(bins_lo, bins_hi, bins_ex, slot, v);
+    };
     auto addhq = [&](unsigned slot, long long q) {
-        if (WANT_H && slot != nul) {
-            const unsigned lo = (unsigned)q, hi = (unsigned)((unsigned long long)q >> 32);
-            const unsigned old = atomicAdd(&hb_lo[slot], lo);
-            atomicAdd(&hb_hi[slot], hi + ((old + lo < old) ? 1u : 0u));
-        }
+        if (WANT_H && slot != nul) bin_add96(hb_lo, hb_hi, hb_ex, slot, q);
     };
-    auto addh = [&](unsigned slot, double v) { if (WANT_H) addhq(slot, __double2ll_rn(v * QG_SCALE)); };
+    auto addh = [&](unsigned slot, double v) {
+        if (!WANT_H) return;
+        if (fabs(v) < QG_WIDE_FROM) addhq(slot, __double2ll_rn(v * QG_SCALE));
+        else if (slot != nul) bin_add96_wide(hb_lo, hb_hi, hb_ex, slot, v);
+    };
     auto tree = [&](double t, const double2 &w, long long *gq, long long *hq) {   // additive quartet: value, dv/dt, -d2v/dt2
         const double t1 = snaq_clamp10(t);
         const double a = 2.0 / 3.0 * snaq_exp(-t1, M);
@@ -1557,9 +1994,8 @@ k_eval_grad_small(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *_
     }
     const int nrows = WANT_H ? 2 * n_full : n_full;                       // the curvature bins follow the gradient bins
     for (int row = (int)tid; row < nrows; row += BLOCK)
-        gpart[(size_t)blockIdx.x * nrows + row] =
-            (double)(long long)(((unsigned long long)bins_hi[row + (row >= n_full ? n_full : 0)] << 32) |
-                                (unsigned long long)bins_lo[row + (row >= n_full ? n_full : 0)]) * (1.0 / QG_SCALE);
+        gpart[(size_t)blockIdx.x * nrows + row] = row < n_full ? bin_value96(bins_lo[row], bins_hi[row], bins_ex[row])
+                                                               : bin_value96(hb_lo[row - n_full], hb_hi[row - n_full], hb_ex[row - n_full]);
     __threadfence();
     __shared__ unsigned int s_last;
     __syncthreads();
@@ -1621,8 +2057,9 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
     double *xs = reinterpret_cast<double *>(ring + 8 * QD_NST * QD_STAGE_BYTES);
     const int n_full = T.n_full;
     unsigned int *bins_lo = reinterpret_cast<unsigned int *>(xs + n_full);   // [n_full] low words
-    unsigned int *bins_hi = bins_lo + n_full;                                // [n_full] high words
-    unsigned int *hb_lo = bins_hi + n_full, *hb_hi = hb_lo + n_full;         // WANT_H: curvature bins (same format)
+    unsigned int *bins_hi = bins_lo + n_full;                                // [n_full] middle words
+    unsigned int *bins_ex = bins_hi + n_full;                                // [n_full] top words (see bin_add96)
+    unsigned int *hb_lo = bins_ex + n_full, *hb_hi = hb_lo + n_full, *hb_ex = hb_hi + n_full;   // WANT_H: curvature bins (same format)
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     unsigned st = 0;
     // class A (one- and two-chunk additive programs) is streamed through a warp-private ring of TMA bulk copies; every
@@ -1659,7 +2096,7 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
     }
     __syncwarp();
     const SnaqMath M = load_math_tables(mt, (int)tid);
-    double *xraw = reinterpret_cast<double *>(bins_lo + (WANT_H ? 4 : 2) * n_full);     // [nparams] the candidate itself
+    double *xraw = reinterpret_cast<double *>(bins_lo + (((WANT_H ? 6 : 3) * n_full + 1) & ~1));     // [nparams] the candidate itself
     for (int row = (int)tid; row < T.nparams; row += BLOCK) {
         const double v = (use_xarg & 1) ? xarg.v[row] : X[row];
         st |= range_check(v, (row >= nh && row < nh + nt) ? 1.0e300 : 1.0);
@@ -1670,18 +2107,15 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
         xs[row] = snaq_expand_row(T, M, xraw, xconst, row);
         bins_lo[row] = 0u;
         bins_hi[row] = 0u;
-        if (WANT_H) { hb_lo[row] = 0u; hb_hi[row] = 0u; }
+        bins_ex[row] = 0u;
+        if (WANT_H) { hb_lo[row] = 0u; hb_hi[row] = 0u; hb_ex[row] = 0u; }
     }
     __syncthreads();
     stamp(1);
     const unsigned nul = (unsigned)T.n_xe;
     double acc = 0.0;
     auto addq = [&](unsigned slot, long long q) {
-        if (slot != nul) {
-            const unsigned lo = (unsigned)q, hi = (unsigned)((unsigned long long)q >> 32);
-            const unsigned old = atomicAdd(&bins_lo[slot], lo);
-            atomicAdd(&bins_hi[slot], hi + ((old + lo < old) ? 1u : 0u));
-        }
+        if (slot != nul) bin_add96(bins_lo, bins_hi, bins_ex, slot, q);
     };
     // generic path: the lanes of a warp mostly run the SAME program (the classes are sorted by term and program), so they
     // add to the same slot at the same instruction; 32 atomics on one shared-memory word are served one after the other.
@@ -1705,20 +2139,22 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
             q = (long long)s0 + ((long long)s1 << 21) + ((long long)s2 << 42);
         }
         if (q == 0) return;
-        const unsigned lo = (unsigned)q, hi = (unsigned)((unsigned long long)q >> 32);
-        unsigned *blo = curv ? hb_lo : bins_lo, *bhi = curv ? hb_hi : bins_hi;
-        const unsigned old = atomicAdd(&blo[slot], lo);
-        atomicAdd(&bhi[slot], hi + ((old + lo < old) ? 1u : 0u));
+        if (curv) bin_add96(hb_lo, hb_hi, hb_ex, slot, q);
+        else bin_add96(bins_lo, bins_hi, bins_ex, slot, q);
     };
-    auto add = [&](unsigned slot, double v) { if (slot != nul) agg(slot, __double2ll_rn(v * QG_SCALE), false); };
+    auto add = [&](unsigned slot, double v) {
+        if (slot == nul) return;
+        if (fabs(v) < QG_WIDE_FROM) agg(slot, __double2ll_rn(v * QG_SCALE), false);
+        else bin_add96_wide(bins_lo, bins_hi, bins_ex, slot, v);
+    };
     auto addhq = [&](unsigned slot, long long q) {
-        if (WANT_H && slot != nul) {
-            const unsigned lo = (unsigned)q, hi = (unsigned)((unsigned long long)q >> 32);
-            const unsigned old = atomicAdd(&hb_lo[slot], lo);
-            atomicAdd(&hb_hi[slot], hi + ((old + lo < old) ? 1u : 0u));
-        }
+        if (WANT_H && slot != nul) bin_add96(hb_lo, hb_hi, hb_ex, slot, q);
     };
-    auto addh = [&](unsigned slot, double v) { if (WANT_H && slot != nul) agg(slot, __double2ll_rn(v * QG_SCALE), true); };
+    auto addh = [&](unsigned slot, double v) {
+        if (!WANT_H || slot == nul) return;
+        if (fabs(v) < QG_WIDE_FROM) agg(slot, __double2ll_rn(v * QG_SCALE), true);
+        else bin_add96_wide(hb_lo, hb_hi, hb_ex, slot, v);
+    };
     // additive quartet: everything that depends on the program only (t -> log of the major CF, t1 + log 3, the two
     // derivative factors); the quartet's own weights enter linearly
     struct TreeConsts { double L, T, r, h; bool in; };
@@ -1895,12 +2331,14 @@ k_eval_grad(SnaqTables T, const uint32_t *__restrict__ off, const uint2 *__restr
     }
     const int nrows = WANT_H ? 2 * n_full : n_full;                       // the curvature bins follow the gradient bins
     // the block's bins go to the grid's bins with 64-bit integer reductions (order independent, so bit-reproducible):
-    // gbins[row] takes the fraction words, gbins[nrows + row] the sign-extended integer words, each with 2^31 blocks of
-    // headroom; the last block only converts (no serial pass over per-block rows)
+    // gbins[row] takes the fraction words (2^32 blocks of headroom), gbins[nrows + row] the blocks' signed 64-bit integer
+    // parts (top and middle word of the 96-bit bins); the last block only converts (no serial pass over per-block rows)
     for (int row = (int)tid; row < nrows; row += BLOCK) {
-        const unsigned lo = bins_lo[row + (row >= n_full ? n_full : 0)], hi = bins_hi[row + (row >= n_full ? n_full : 0)];
+        const bool cv = row >= n_full;
+        const int r = cv ? row - n_full : row;
+        const unsigned lo = cv ? hb_lo[r] : bins_lo[r], hi = cv ? hb_hi[r] : bins_hi[r], ex = cv ? hb_ex[r] : bins_ex[r];
         if (lo) atomicAdd(gbins + row, (unsigned long long)lo);
-        if (hi) atomicAdd(gbins + nrows + row, (unsigned long long)(long long)(int)hi);
+        if (hi | ex) atomicAdd(gbins + nrows + row, ((unsigned long long)ex << 32) | (unsigned long long)hi);
     }
     stamp(7);
     __threadfence();
@@ -2059,11 +2497,31 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restric
     __syncthreads();
     if (tid == 0) out[p] = -(((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7])));
 }
+// first level of a two-level reduction over many rows (k_eval_runs writes one row per segment): block (x, y) adds rows
+// [y * rows_per, (y + 1) * rows_per) for candidates [32 x, 32 x + 32) in a fixed order into out[y][.]
+__global__ void __launch_bounds__(256) k_reduce_rows(const double *__restrict__ partial, int nrows, int rows_per, int stride, int P,
+                                                     double *__restrict__ out) {
+    __shared__ double sh[8][32];
+    const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int p = blockIdx.x * 32 + c;
+    const int r0 = blockIdx.y * rows_per, r1 = min(r0 + rows_per, nrows);
+    double s = 0.0;
+    if (p < P)
+        for (int b = r0 + r; b < r1; b += 8) s += partial[(size_t)b * stride + p];
+    sh[r][c] = s;
+    __syncthreads();
+    if (r == 0 && p < P) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) t += sh[k][c];
+        out[(size_t)blockIdx.y * stride + p] = t;
+    }
+}
 // variant for the lanes kernel (candidates contiguous in a row of partial): a block of 32 x 8 threads handles 32
 // candidates; thread (c, r) adds rows r, r+8, ... (coalesced 256-byte reads), then the 8 row groups are added
 // in a fixed order
 __global__ void __launch_bounds__(256) k_reduce_partials_t(const double *__restrict__ partial, int nblocks, int stride, int P,
-                                                           double *__restrict__ out) {
+                                                           double *__restrict__ out, const double *__restrict__ cst = nullptr) {
     __shared__ double sh[8][32];
     const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
     const int p = blockIdx.x * 32 + c;
@@ -2076,7 +2534,7 @@ __global__ void __launch_bounds__(256) k_reduce_partials_t(const double *__restr
         double t = 0.0;
 #pragma unroll
         for (int k = 0; k < 8; k++) t += sh[k][c];
-        out[p] = -t;
+        out[p] = cst ? -t - __ldg(cst) : -t;                 // cst = -(sum of the constants W3), see k_weights
     }
 }
 
@@ -2098,6 +2556,13 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, doubl
 // --------------------------------------------------------------------------------------------
 struct snaq_ctx {
     int device = 0, rank = 0, world = 1;
+    void *comm = nullptr;                 // ncclComm_t of a quartet-sharded context (snaq_comm_init), else nullptr
+    PeerMail *d_mail = nullptr;           // this rank's mailbox array [2][world] (fused epilogue of k_eval_direct)
+    PeerMail *peer_mail[SNAQ_MAX_WORLD] = {nullptr};   // every rank's mailbox array as mapped into this process
+    bool peer_ok = false;                 // the mailboxes of all peers are mapped (CUDA IPC over NVLink / PCIe peer access)
+    unsigned long long comm_seq = 0;      // sequence number of the fused launches (the same on every rank)
+    bool last_fused = false;              // the last k_eval_direct launch delivered totals, not partial sums
+    double *d_red = nullptr; size_t red_cap = 0;       // device staging of values that are all-reduced before they go to the host
     cudaStream_t stream = nullptr;
     XArg xarg;                            // kernel-argument copy of a small host batch
     bool xarg_on = false;
@@ -2147,6 +2612,14 @@ struct snaq_ctx {
     uint16_t *d_prog_u = nullptr; size_t prog_u_cap = 0; uint64_t prog_u_words = 0;
     double *d_W_u = nullptr; double2 *d_WA_u = nullptr; double *d_wpart_u = nullptr, *d_negw3_u = nullptr;
     double *d_pen_u = nullptr;            // [nU][4] per-run data of the -1e15 penalty (snaq_loglik_t5)
+    // run table of the plain table (k_eval_runs): off_u / prog_u above hold one program per run, tdesc one descriptor per tile
+    int runs_on = 1;                      // SNAQ_RUNS=0: the batched path uses the per-quartet kernels (k_eval_lanes / _p);
+                                          // 1: run-length kernel when the runs are long enough to pay (RN_MIN_AVG_RUN); 2: always
+    RunTile *d_tdesc = nullptr; size_t tdesc_cap = 0;
+    uint32_t *d_rec_off = nullptr; size_t rec_off_cap = 0;       // [ntiles + 1] record offsets of the packed tile stream (16-byte units)
+    unsigned char *d_pack = nullptr; size_t pack_cap = 0;         // the packed tile stream
+    double *d_partial2 = nullptr; size_t partial2_cap = 0;        // second level of the segment reduction
+    uint32_t rn_ntiles = 0, rn_nseg = 0, rn_tps = 1, rn_ntAB = 0;
     uint32_t *d_status = nullptr;          // [0] build, [1] eval
     unsigned long long *d_trace = nullptr; // SNAQ_TRACE=1: [blocks][8] phase timestamps of the last k_eval_direct launch
     int trace_blocks = 0;
@@ -2273,9 +2746,65 @@ static int status_to_error(snaq_ctx *ctx, uint32_t st) {
     if (!st) return SNAQ_OK;
     if (st & SNAQ_S_RANGE) { ctx->err = "new gamma / gammaz value should be between 0,1 and lengths nonnegative (src/snaq_optimization.jl:213,221,228; src/auxiliary.jl:119)"; return SNAQ_ERANGE; }
     if (st & SNAQ_S_NEGLEN) { ctx->err = "length can be negative, but not too negative (greater than -log(1.5)) or majorCF<0 (src/auxiliary.jl:120)"; return SNAQ_ENUMERIC; }
+    if (st & SNAQ_S_COMM) { ctx->err = "quartet-sharded evaluation: a peer's partial sums did not arrive within 4 s (did every rank make the same call?)"; return SNAQ_ECUDA; }
     if (st & SNAQ_S_ZEROSUM) { ctx->err = "expCF not updated for quartet: sum(expCF)==0 (src/pseudolik.jl:1391)"; return SNAQ_ENUMERIC; }
     ctx->err = "numerical error in the evaluation kernel";
     return SNAQ_ENUMERIC;
+}
+
+// ---- NCCL, resolved at run time: the library has no link-time dependency on it (a single-GPU caller never needs it), and
+// a process that already carries a libnccl.so.2 (e.g. PyTorch's) shares that copy -------------------------------------------
+struct NcclApi {
+    void *h = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+static NcclApi *nccl_api(std::string &err) {
+    static std::mutex mu;
+    static NcclApi api;
+    static bool tried = false;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!tried) {
+        tried = true;
+        const char *names[] = {getenv("SNAQ_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            if (!nm || api.h) continue;
+            api.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        }
+        if (api.h) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.h, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.h, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.h, "ncclCommDestroy");
+            api.AllReduce = (decltype(api.AllReduce))dlsym(api.h, "ncclAllReduce");
+            api.AllGather = (decltype(api.AllGather))dlsym(api.h, "ncclAllGather");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.h, "ncclGetErrorString");
+        }
+    }
+    if (!api.h || !api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.AllGather || !api.GetErrorString) {
+        err = "NCCL (libnccl.so.2) could not be loaded: quartet-sharded contexts need it for their all-reduce (set SNAQ_NCCL_LIB to its path)";
+        return nullptr;
+    }
+    return &api;
+}
+#define CKN(call)                                                                                              \
+    do {                                                                                                       \
+        ncclResult_t r_ = (call);                                                                              \
+        if (r_ != ncclSuccess) {                                                                               \
+            ctx->err = std::string(#call) + ": " + api->GetErrorString(r_);                                    \
+            return SNAQ_ECUDA;                                                                                 \
+        }                                                                                                      \
+    } while (0)
+
+// sum over the ranks of n doubles in device memory, in place, on `stream` (every rank of the communicator calls this)
+static int comm_allreduce(snaq_ctx *ctx, double *d, size_t n, cudaStream_t stream) {
+    NcclApi *api = nccl_api(ctx->err);
+    if (!api) return SNAQ_ECUDA;
+    CKN(api->AllReduce(d, d, n, ncclDouble, ncclSum, (ncclComm_t)ctx->comm, stream));
+    return SNAQ_OK;
 }
 
 // the table an evaluation kernel walks: the full one, or the deduplicated one (one entry per distinct program)
@@ -2295,9 +2824,10 @@ static int run_weights(snaq_ctx *ctx) {
     if (!ctx->has_net || ctx->nq == 0) return SNAQ_OK;
     int64_t nb = (ctx->nq + 255) / 256;
     k_weights<<<(unsigned)nb, 256, 0, ctx->stream>>>(ctx->d_perm, ctx->d_qhdr, ctx->d_obs, ctx->has_sampled ? ctx->d_sampled : nullptr, ctx->nq,
-                                                    ctx->nA1 + ctx->nA2, ctx->d_W, ctx->d_WA, ctx->d_wpart);
+                                                    ctx->nA1 + ctx->nA2, ctx->nA + ctx->nB, ctx->d_W, ctx->d_WA, ctx->d_wpart,
+                                                    ctx->d_rec_off, ctx->rn_ntAB, (ctx->runs_on && !ctx->dedup && ctx->rn_ntiles > 0) ? ctx->d_pack : nullptr);
     CK(cudaGetLastError());
-    k_reduce_partials<<<1, 256, 0, ctx->stream>>>(ctx->d_wpart, (int)nb, 1, 1, ctx->d_negw3);
+    k_reduce_partials<<<2, 256, 0, ctx->stream>>>(ctx->d_wpart, (int)nb, 2, 2, ctx->d_negw3);
     CK(cudaGetLastError());
     ctx->counters[5] += 2;
     if (ctx->dedup && ctx->nU > 0) {
@@ -2336,7 +2866,7 @@ static int build_dedup(snaq_ctx *ctx, int64_t pad_at) {
         const size_t n = (size_t)nu + 1 + (size_t)nu / 8;
         CK(cudaMalloc((void **)&ctx->d_rstart, (n + 1) * sizeof(uint32_t)));
         CK(cudaMalloc((void **)&ctx->d_ulen, (n + 1) * sizeof(uint32_t)));
-        CK(cudaMalloc((void **)&ctx->d_off_u, (n + 2) * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&ctx->d_off_u, (n + 8) * sizeof(uint32_t)));      // (+8: the tiles' aligned bulk copies read past the end)
         CK(cudaMalloc((void **)&ctx->d_qhdr_u, n + 1));
         CK(cudaMalloc((void **)&ctx->d_W_u, (n + 1) * 4 * sizeof(double)));
         CK(cudaMalloc((void **)&ctx->d_pen_u, (n + 1) * 4 * sizeof(double)));
@@ -2365,6 +2895,41 @@ static int build_dedup(snaq_ctx *ctx, int64_t pad_at) {
     return SNAQ_OK;
 }
 
+// the packed tile stream of the run table (k_eval_runs); tiles never straddle the tree-like / 4-cycle boundary
+static int build_run_tiles(snaq_ctx *ctx) {
+    const int64_t nAB = ctx->nA + ctx->nB, nC = ctx->nq - nAB;
+    const int64_t ntAB = (nAB + RN_TQ - 1) / RN_TQ, ntC = (nC + RN_TQC - 1) / RN_TQC;
+    const int64_t nt = ntAB + ntC;
+    if (nt >= 0x7fffffffLL) { ctx->err = "too many quartets on one GPU for the run table: shard them (world_size>1)"; return SNAQ_EINVAL; }
+    ctx->rn_ntiles = (uint32_t)nt; ctx->rn_ntAB = (uint32_t)ntAB;
+    ctx->rn_tps = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(16, nt / 2048));       // depends on the table only
+    ctx->rn_nseg = (uint32_t)((nt + ctx->rn_tps - 1) / ctx->rn_tps);
+    int rc = ensure(ctx, ctx->d_tdesc, ctx->tdesc_cap, (size_t)nt + 1);
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->d_rec_off, ctx->rec_off_cap, (size_t)nt + 2);
+    if (rc) return rc;
+    k_run_tiles<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_flags, ctx->d_uidx, ctx->d_off_u, ctx->nq, nAB, (uint32_t)ntAB,
+                                                                      (uint32_t)nt, ctx->d_tdesc, ctx->d_rec_off + 1);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(ctx->d_rec_off, 0, sizeof(uint32_t), ctx->stream));
+    size_t t1 = ctx->scan_tmp_cap;
+    CK(cub::DeviceScan::InclusiveSum(ctx->d_scan_tmp, t1, ctx->d_rec_off + 1, ctx->d_rec_off + 1, nt, ctx->stream));
+    uint32_t total16 = 0;
+    CK(cudaMemcpyAsync(&total16, ctx->d_rec_off + nt, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if ((uint64_t)nt * (RN_STAGE_BYTES / 16) >= 0xffffffffull) { ctx->err = "packed tile stream exceeds 64 GB: shard the quartets (world_size>1)"; return SNAQ_EINVAL; }
+    rc = ensure(ctx, ctx->d_pack, ctx->pack_cap, (size_t)total16 * 16 + 16);
+    if (rc) return rc;
+    k_run_fill<<<(unsigned)((nt * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_tdesc, ctx->d_rec_off, ctx->d_off_u,
+                                                                          reinterpret_cast<const uint2 *>(ctx->d_prog_u), (uint32_t)nt, ctx->d_pack);
+    CK(cudaGetLastError());
+    ctx->counters[5] += 3;
+    return SNAQ_OK;
+}
+
+// the fused epilogue needs every rank to launch k_eval_direct (a rank without quartets launches nothing)
+static bool fused_ok(const snaq_ctx *ctx) { return ctx->comm && ctx->peer_ok && ctx->nq_total >= ctx->world; }
+
 template <int PC, bool OUT>
 static int launch_direct(snaq_ctx *ctx, cudaStream_t stream, const double *dX, int Pc, double *dout, double *expcf, double *logpl,
                          double *deltacf) {
@@ -2386,13 +2951,22 @@ static int launch_direct(snaq_ctx *ctx, cudaStream_t stream, const double *dX, i
     int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)grid * PC);
     if (rc) return rc;
     if (ctx->d_trace) ctx->trace_blocks = grid;
+    PeerBox box;
+    std::memset(&box, 0, sizeof(box));
+    ctx->last_fused = false;
+    if (!OUT && fused_ok(ctx)) {                      // quartet-sharded: the all-reduce is fused into the kernel's epilogue
+        for (int r = 0; r < ctx->world; r++) box.peer[r] = ctx->peer_mail[r];
+        box.rank = ctx->rank; box.world = ctx->world;
+        box.seq = ++ctx->comm_seq;
+        ctx->last_fused = true;
+    }
     CK(raise_smem_limit(k_eval_direct<PC, OUT>, smem));
     k_eval_direct<PC, OUT><<<grid, 256, smem, stream>>>(
         ctx->T, tb.off, reinterpret_cast<const uint2 *>(tb.prog), tb.qhdr, ctx->d_perm, tb.WA,
         reinterpret_cast<const double4 *>(tb.W), ctx->d_obs, (uint32_t)tb.nA1, (uint32_t)tb.nA2,
         (uint32_t)(tb.nA1 + (tb.nA1 & 1)), (uint32_t)tb.nq, dX,
         ctx->d_xconst, H.nh, H.nt, Pc, ctx->d_partial, dout, tb.negw3, ctx->d_ticket, expcf, logpl, deltacf, ctx->d_status + 1, ctx->d_trace,
-        ctx->status_out, ctx->xarg_on ? 1 : 0, tb.pen, ctx->xarg);
+        ctx->status_out, ctx->xarg_on ? 1 : 0, tb.pen, box, ctx->xarg);
     CK(cudaGetLastError());
     ctx->counters[0] += 1;
     ctx->counters[1] += ctx->nq * (int64_t)Pc;
@@ -2426,8 +3000,8 @@ static int eval_quartets_launch(snaq_ctx *ctx, int P, const double *dX, double *
 }
 
 // dispatch one evaluation of P candidates whose X is already on the device
-static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cudaStream_t stream,
-                       double *expcf, double *logpl, double *deltacf) {
+static int eval_device_local(snaq_ctx *ctx, int P, const double *dX, double *dout, cudaStream_t stream,
+                             double *expcf, double *logpl, double *deltacf) {
     const SnaqHostTables &H = ctx->H;
     if (ctx->nq == 0) { CK(cudaMemsetAsync(dout, 0, sizeof(double) * P, stream)); return SNAQ_OK; }
     const bool per_quartet = expcf || logpl || deltacf;
@@ -2435,11 +3009,83 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
     const int64_t nq = tb.nq;
     const bool use_lanes = P >= LANES_MIN_P && !per_quartet;
     if (use_lanes) {
+        if (ctx->runs_on && !ctx->dedup && ctx->rn_ntiles > 0 &&
+            (ctx->runs_on > 1 || ctx->nq >= (int64_t)RN_MIN_AVG_RUN * std::max<int64_t>(ctx->nU, 1))) {
+            // run-length kernel: programs evaluated once per run of identical programs, weights streamed per quartet
+            RunsMeta rm;
+            rm.ntiles = ctx->rn_ntiles; rm.nseg = ctx->rn_nseg; rm.tps = ctx->rn_tps; rm.nul = (uint32_t)H.n_xe;
+            rm.nA = ctx->nA; rm.noreuse = ctx->reuse ? 0 : 1;
+            auto smem_of = [&](int warps, int cpl) {
+                return (size_t)384 + ((((size_t)1 + warps * RN_NST) * 8 + 127) & ~size_t(127)) + (size_t)H.n_full * 256 * cpl +
+                       (size_t)warps * RN_NST * RN_STAGE_BYTES;
+            };
+            // two candidates per lane (the weights of a quartet are loaded once for 64 candidates) when the batch has 64
+            // and the wider xf tile fits; 16-warp blocks when only one block fits per SM anyway
+            int cpl = (P > 32 && smem_of(8, 2) <= 200 * 1024) ? 2 : 1;
+            if (const char *ev = getenv("SNAQ_RUNS_CPL")) { const int v = atoi(ev); if (v == 1 || (v == 2 && smem_of(8, 2) <= 220 * 1024)) cpl = v; }
+            int warps = (cpl == 1 && smem_of(8, cpl) > 110 * 1024 && smem_of(16, cpl) <= 220 * 1024) ? 16 : 8;
+            if (const char *ev = getenv("SNAQ_RUNS_WARPS")) { const int v = atoi(ev); if (v == 8 || (v == 16 && smem_of(16, cpl) <= 220 * 1024)) warps = v; }
+            const size_t smem = smem_of(warps, cpl);
+            if (smem > 227 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_runs"; return SNAQ_EINVAL; }
+            const int tw = 32 * cpl;
+            const int ngr = (P + tw - 1) / tw, Pp = ngr * tw;
+            if (ngr > 65535) { ctx->err = "batch too large for one launch"; return SNAQ_EINVAL; }
+            { int rcx = ensure(ctx, ctx->d_XF, ctx->XF_cap, (size_t)Pp * H.n_full); if (rcx) return rcx; }
+            {
+                const int64_t totx = (int64_t)Pp * H.n_full;
+                k_expand_x<<<(unsigned)((totx + 255) / 256), 256, 0, stream>>>(ctx->T, dX, ctx->d_xconst, P, H.nh, H.nt, tw, ctx->d_XF,
+                                                                                ctx->d_status + 1);
+                CK(cudaGetLastError());
+            }
+            int per_sm = 1;
+#define OCC_RUNS(WN, CP) do { CK(raise_smem_limit(k_eval_runs<WN, CP>, smem)); CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_eval_runs<WN, CP>, WN * 32, smem)); } while (0)
+            if (warps == 16 && cpl == 2) OCC_RUNS(16, 2);
+            else if (warps == 16) OCC_RUNS(16, 1);
+            else if (cpl == 2) OCC_RUNS(8, 2);
+            else OCC_RUNS(8, 1);
+#undef OCC_RUNS
+            per_sm = std::max(per_sm, 1);
+            const int64_t slots = (int64_t)ctx->sm_count * per_sm;
+            const int64_t want = ((int64_t)rm.nseg + warps - 1) / warps;              // blocks that still have a segment per warp
+            const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(want, slots / ngr));
+            const int S = (int)std::max<int64_t>(1, std::min<int64_t>(64, rm.nseg / 32));    // depends on the table only
+            const int rows_per = ((int)rm.nseg + S - 1) / S;
+            int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)rm.nseg * Pp);
+            if (rc) return rc;
+            rc = ensure(ctx, ctx->d_partial2, ctx->partial2_cap, (size_t)S * Pp);
+            if (rc) return rc;
+            dim3 grid((unsigned)gx, (unsigned)ngr);
+            const uint2 *pu = reinterpret_cast<const uint2 *>(ctx->d_prog_u);
+#define LAUNCH_RUNS(WN, CP)                                                                                                    \
+    do {                                                                                                                       \
+        CK(raise_smem_limit(k_eval_runs<WN, CP>, smem));                                                                         \
+        k_eval_runs<WN, CP><<<grid, WN * 32, smem, stream>>>(ctx->d_pack, ctx->d_rec_off, pu, rm, ctx->d_XF, H.n_full,          \
+                                                            ctx->d_partial, Pp, ctx->d_status + 1);                             \
+    } while (0)
+            if (warps == 16 && cpl == 2) LAUNCH_RUNS(16, 2);
+            else if (warps == 16) LAUNCH_RUNS(16, 1);
+            else if (cpl == 2) LAUNCH_RUNS(8, 2);
+            else LAUNCH_RUNS(8, 1);
+#undef LAUNCH_RUNS
+            CK(cudaGetLastError());
+            if (S > 1) {
+                k_reduce_rows<<<dim3((unsigned)((P + 31) / 32), (unsigned)S), 256, 0, stream>>>(ctx->d_partial, (int)rm.nseg, rows_per, Pp, P,
+                                                                                                  ctx->d_partial2);
+                CK(cudaGetLastError());
+                k_reduce_partials_t<<<(P + 31) / 32, 256, 0, stream>>>(ctx->d_partial2, S, Pp, P, dout, ctx->d_negw3 + 1);
+            } else {
+                k_reduce_partials_t<<<(P + 31) / 32, 256, 0, stream>>>(ctx->d_partial, (int)rm.nseg, Pp, P, dout, ctx->d_negw3 + 1);
+            }
+            CK(cudaGetLastError());
+            ctx->counters[0] += 1;
+            ctx->counters[1] += ctx->nq * (int64_t)P;
+            return SNAQ_OK;
+        }
         const int Prows = (P + 31) & ~31;
         int rc0 = ensure(ctx, ctx->d_XF, ctx->XF_cap, (size_t)Prows * H.n_full);
         if (rc0) return rc0;
         const int64_t tot = (int64_t)Prows * H.n_full;
-        k_expand_x<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(ctx->T, dX, ctx->d_xconst, P, H.nh, H.nt, 1, ctx->d_XF,
+        k_expand_x<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(ctx->T, dX, ctx->d_xconst, P, H.nh, H.nt, 32, ctx->d_XF,
                                                                       ctx->d_status + 1);
         CK(cudaGetLastError());
         const double *dXF = ctx->d_XF;
@@ -2525,6 +3171,18 @@ static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cud
     return eval_quartets_launch(ctx, P, dX, dout, stream, expcf, logpl, deltacf);
 }
 
+// One evaluation of P candidates; on a quartet-sharded context with a communicator the values are the totals over all
+// ranks: small batches get them from the fused epilogue of k_eval_direct, everything else from an ncclAllReduce of the
+// P partial sums on the same stream (dout must then be device memory).
+static int eval_device(snaq_ctx *ctx, int P, const double *dX, double *dout, cudaStream_t stream,
+                       double *expcf, double *logpl, double *deltacf) {
+    ctx->last_fused = false;
+    int rc = eval_device_local(ctx, P, dX, dout, stream, expcf, logpl, deltacf);
+    if (rc) return rc;
+    if (ctx->comm && !(expcf || logpl || deltacf) && !ctx->last_fused) return comm_allreduce(ctx, dout, (size_t)P, stream);
+    return SNAQ_OK;
+}
+
 // --------------------------------------------------------------------------------------------
 // C ABI
 // --------------------------------------------------------------------------------------------
@@ -2569,6 +3227,7 @@ int snaq_create(const snaq_opts *opts, snaq_ctx **out) {
     }
     if (const char *ev = getenv("SNAQ_EVAL_CHUNKS")) { int v = atoi(ev); if (v >= 1 && v <= 4) ctx->eval_chunks = v; }
     if (const char *ev = getenv("SNAQ_REUSE")) ctx->reuse = atoi(ev) != 0;
+    if (const char *ev = getenv("SNAQ_RUNS")) ctx->runs_on = atoi(ev);
     if (const char *ev = getenv("SNAQ_LANES_CHUNK")) { int v = atoi(ev); if (v == 128 || v == 256 || v == 512 || v == 1024) ctx->lanes_chunk = v; }
     if (const char *ev = getenv("SNAQ_LANES_PERSISTENT")) ctx->lanes_persistent = atoi(ev);
     if (const char *ev = getenv("SNAQ_LANES_WARPS")) { int v = atoi(ev); if (v == 8 || v == 12 || v == 16) ctx->lanes_warps = v; }
@@ -2586,11 +3245,21 @@ int snaq_destroy(snaq_ctx *ctx) {
     for (snaq_ctx *w : ctx->workers) snaq_destroy(w);
     ctx->workers.clear();
     cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) {
+        for (int rk = 0; rk < ctx->world; rk++)
+            if (rk != ctx->rank && ctx->peer_mail[rk]) cudaIpcCloseMemHandle(ctx->peer_mail[rk]);
+        std::string e;
+        if (NcclApi *api = nccl_api(e)) api->CommDestroy((ncclComm_t)ctx->comm);
+        ctx->comm = nullptr;
+    }
+    cudaFree(ctx->d_mail); cudaFree(ctx->d_red);
     cudaFree(ctx->d_ci_lo); cudaFree(ctx->d_ci_hi);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_blob); cudaFree(ctx->d_xconst);
     cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_WA); cudaFree(ctx->d_wpart); cudaFree(ctx->d_negw3); cudaFree(ctx->d_status); cudaFree(ctx->d_total); cudaFree(ctx->d_ticket); cudaFree(ctx->d_trace);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_uidx); cudaFree(ctx->d_rstart); cudaFree(ctx->d_ulen); cudaFree(ctx->d_off_u); cudaFree(ctx->d_qhdr_u);
+    cudaFree(ctx->d_tdesc); cudaFree(ctx->d_rec_off); cudaFree(ctx->d_pack); cudaFree(ctx->d_partial2);
     cudaFree(ctx->d_prog_u); cudaFree(ctx->d_W_u); cudaFree(ctx->d_WA_u); cudaFree(ctx->d_wpart_u); cudaFree(ctx->d_negw3_u); cudaFree(ctx->d_pen_u);
     cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_XF); cudaFree(ctx->d_out); cudaFree(ctx->d_partial); cudaFree(ctx->d_gbins); cudaFree(ctx->d_gpart); cudaFree(ctx->d_rb_e); cudaFree(ctx->d_rb_l); cudaFree(ctx->d_rb_d); cudaFree(ctx->d_sq_w); cudaFree(ctx->d_sq_cum); cudaFree(ctx->d_sq_u); cudaFree(ctx->d_sq_idx); cudaFree(ctx->d_gout);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_qhdr); cudaFree(ctx->d_len4); cudaFree(ctx->d_iota); cudaFree(ctx->d_cls);
@@ -2599,6 +3268,81 @@ int snaq_destroy(snaq_ctx *ctx) {
     if (ctx->copy_stream) { for (int k = 0; k < 8; k++) cudaEventDestroy(ctx->copy_ev[k]); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+    return SNAQ_OK;
+}
+
+
+// ---- quartet-sharded mode: the collective lives inside the library ---------------------------------------------------
+int snaq_comm_unique_id(void *id128) {
+    if (!id128) return SNAQ_EINVAL;
+    NcclApi *api = nccl_api(g_create_err);
+    if (!api) return SNAQ_ECUDA;
+    ncclUniqueId id;
+    ncclResult_t r = api->GetUniqueId(&id);
+    if (r != ncclSuccess) { g_create_err = std::string("ncclGetUniqueId: ") + api->GetErrorString(r); return SNAQ_ECUDA; }
+    static_assert(sizeof(id) == 128, "ncclUniqueId");
+    std::memcpy(id128, &id, sizeof(id));
+    return SNAQ_OK;
+}
+
+int snaq_comm_init(snaq_ctx *ctx, const void *id128) {
+    if (!ctx || !id128) return SNAQ_EINVAL;
+    if (ctx->world <= 1) return SNAQ_OK;                                  // nothing to combine
+    if (ctx->comm) { ctx->err = "snaq_comm_init: the context already has a communicator"; return SNAQ_EINVAL; }
+    if (ctx->world > SNAQ_MAX_WORLD) { ctx->err = "snaq_comm_init: at most " + std::to_string(SNAQ_MAX_WORLD) + " ranks"; return SNAQ_EINVAL; }
+    NcclApi *api = nccl_api(ctx->err);
+    if (!api) return SNAQ_ECUDA;
+    CK(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    ncclComm_t comm = nullptr;
+    CKN(api->CommInitRank(&comm, ctx->world, id, ctx->rank));
+    ctx->comm = comm;
+    // mailboxes for the fused epilogue of k_eval_direct: every rank's array [2][world] mapped into every rank (CUDA IPC).
+    // If a mapping fails (no peer access between two devices) the small batches fall back to ncclAllReduce as well.
+    const size_t nmail = 2 * (size_t)ctx->world;
+    CK(cudaMalloc((void **)&ctx->d_mail, nmail * sizeof(PeerMail)));
+    CK(cudaMemset(ctx->d_mail, 0, nmail * sizeof(PeerMail)));
+    cudaIpcMemHandle_t mine;
+    CK(cudaIpcGetMemHandle(&mine, ctx->d_mail));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t");
+    unsigned char *d_h = nullptr;
+    CK(cudaMalloc((void **)&d_h, 64 * ((size_t)ctx->world + 1)));
+    CK(cudaMemcpy(d_h + 64 * (size_t)ctx->world, &mine, 64, cudaMemcpyHostToDevice));
+    ncclResult_t r = api->AllGather(d_h + 64 * (size_t)ctx->world, d_h, 64, ncclChar, comm, ctx->stream);
+    if (r != ncclSuccess) { cudaFree(d_h); ctx->err = std::string("ncclAllGather: ") + api->GetErrorString(r); return SNAQ_ECUDA; }
+    std::vector<cudaIpcMemHandle_t> all((size_t)ctx->world);
+    cudaError_t e = cudaMemcpyAsync(all.data(), d_h, 64 * (size_t)ctx->world, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_h);
+    if (e != cudaSuccess) { ctx->err = std::string("snaq_comm_init: ") + cudaGetErrorString(e); return SNAQ_ECUDA; }
+    int ok = getenv("SNAQ_NO_PEER_EPILOGUE") ? 0 : 1;
+    for (int rk = 0; rk < ctx->world && ok; rk++) {
+        if (rk == ctx->rank) { ctx->peer_mail[rk] = ctx->d_mail; continue; }
+        void *pp = nullptr;
+        if (cudaIpcOpenMemHandle(&pp, all[(size_t)rk], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        ctx->peer_mail[rk] = (PeerMail *)pp;
+    }
+    // every rank must take the same path: the fused epilogue is used only if ALL ranks mapped ALL mailboxes
+    int *d_ok = nullptr;
+    CK(cudaMalloc((void **)&d_ok, sizeof(int)));
+    CK(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    r = api->AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, comm, ctx->stream);
+    if (r == ncclSuccess) { e = cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); }
+    cudaFree(d_ok);
+    if (r != ncclSuccess) { ctx->err = std::string("ncclAllReduce: ") + api->GetErrorString(r); return SNAQ_ECUDA; }
+    if (e != cudaSuccess) { ctx->err = std::string("snaq_comm_init: ") + cudaGetErrorString(e); return SNAQ_ECUDA; }
+    ctx->peer_ok = ok != 0;
+    ctx->comm_seq = 0;
+    return SNAQ_OK;
+}
+
+int snaq_comm_info(snaq_ctx *ctx, int32_t *rank, int32_t *world_size, int32_t *has_comm, int32_t *fused_epilogue) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (rank) *rank = ctx->rank;
+    if (world_size) *world_size = ctx->world;
+    if (has_comm) *has_comm = ctx->comm ? 1 : 0;
+    if (fused_epilogue) *fused_epilogue = fused_ok(ctx) ? 1 : 0;
     return SNAQ_OK;
 }
 
@@ -2637,18 +3381,16 @@ int snaq_set_data(snaq_ctx *ctx, int32_t ntaxa, int64_t nq, const uint16_t *taxa
     CK(cudaMalloc((void **)&ctx->d_off, (n + 1) * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&ctx->d_W, n * 4 * sizeof(double)));
     CK(cudaMalloc((void **)&ctx->d_WA, n * sizeof(double2)));
-    CK(cudaMalloc((void **)&ctx->d_wpart, ((n + 255) / 256) * sizeof(double)));
-    CK(cudaMalloc((void **)&ctx->d_negw3, sizeof(double)));
+    CK(cudaMalloc((void **)&ctx->d_wpart, 2 * ((n + 255) / 256) * sizeof(double)));
+    CK(cudaMalloc((void **)&ctx->d_negw3, 2 * sizeof(double)));
     CK(cudaMalloc((void **)&ctx->d_perm, n * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&ctx->d_qhdr, n));
     CK(cudaMalloc((void **)&ctx->d_len4, n * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&ctx->d_iota, n * sizeof(uint32_t)));
     cudaFree(ctx->d_flags); cudaFree(ctx->d_uidx);
     ctx->d_flags = ctx->d_uidx = nullptr;
-    if (ctx->dedup) {
-        CK(cudaMalloc((void **)&ctx->d_flags, n * sizeof(uint32_t)));
-        CK(cudaMalloc((void **)&ctx->d_uidx, n * sizeof(uint32_t)));
-    }
+    CK(cudaMalloc((void **)&ctx->d_flags, n * sizeof(uint32_t)));      // run table (k_eval_runs) and program deduplication
+    CK(cudaMalloc((void **)&ctx->d_uidx, n * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&ctx->d_cls, n * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&ctx->d_cls_sorted, n * sizeof(uint32_t)));
     if (ctx->nq >= 0xFFFFFFFFLL) { ctx->err = "more than 2^32 quartets on one GPU: shard them (world_size>1)"; return SNAQ_EINVAL; }
@@ -2818,7 +3560,8 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
         CK(cudaGetLastError());
         ctx->counters[5] += 5;
         ctx->nU = 0;
-        if (ctx->dedup) { rc = build_dedup(ctx, pad_at); if (rc) return rc; }
+        if (ctx->dedup || ctx->runs_on) { rc = build_dedup(ctx, pad_at); if (rc) return rc; }
+        if (ctx->runs_on && !ctx->dedup) { rc = build_run_tiles(ctx); if (rc) return rc; }
         ctx->has_net = true;
         rc = run_weights(ctx);
         if (rc) { ctx->has_net = false; return rc; }
@@ -3018,7 +3761,7 @@ int snaq_eval(snaq_ctx *ctx, int32_t P, int32_t nparams, const double *X, double
     if (rc) return rc;
     rc = ensure_pin(ctx, nx + P + 2);
     if (rc) return rc;
-    if (P < LANES_MIN_P && ctx->nq > 0 && (size_t)std::min(P, 4) * nparams <= XARG_MAX) {
+    if (P < LANES_MIN_P && ctx->nq > 0 && (size_t)std::min(P, 4) * nparams <= XARG_MAX && (!ctx->comm || fused_ok(ctx))) {
         // small batch (a single objective call of the optimiser): the candidates travel as kernel arguments and the last
         // block writes the results and the status word straight into page-locked host memory: no copy calls at all
         double *h_out = ctx->h_pin;
@@ -3096,6 +3839,11 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
     if (!ctx) return SNAQ_EINVAL;
     if (!ctx->has_net) { ctx->err = "snaq_set_network has not been called"; return SNAQ_ENODATA; }
     if (!x || !f || !grad || nparams != ctx->H.nparams) { ctx->err = "bad arguments to snaq_eval_grad (x has wrong length?)"; return SNAQ_EINVAL; }
+    if (ctx->world > 1 && !ctx->comm) {
+        ctx->err = "snaq_eval_grad / snaq_optbl on a quartet-sharded context need a communicator (snaq_comm_init): a rank's partial "
+                   "sums are not the objective";
+        return SNAQ_EINVAL;
+    }
     int rc = check_x_host(ctx, 1, x);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
@@ -3103,9 +3851,9 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
     const int n_full = H.n_full;
     for (int i = 0; i < nparams; i++) grad[i] = 0.0;
     if (hdiag) for (int i = 0; i < nparams; i++) hdiag[i] = 0.0;
-    if (ctx->nq == 0) { *f = 0.0; return SNAQ_OK; }
+    if (ctx->nq == 0 && !ctx->comm) { *f = 0.0; return SNAQ_OK; }
     const int nrows = hdiag ? 2 * n_full : n_full;
-    const size_t smem_base = 640 + 8 * QD_SPAN * 8 + (size_t)n_full * 8 + (size_t)nrows * 8 + (size_t)nparams * 8;
+    const size_t smem_base = 640 + 8 * QD_SPAN * 8 + (size_t)n_full * 8 + (size_t)nrows * 12 + 8 + (size_t)nparams * 8;   // xf, 96-bit bins, x
     if (smem_base - 128 > 100 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_grad"; return SNAQ_EINVAL; }
     EvalTable tb = eval_table(ctx, false);
     if (ctx->dedup) tb.nA1 = tb.nA2 = 0;                    // see launch_direct
@@ -3142,6 +3890,18 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
     double *h_g = ctx->h_pin + nparams;
     uint32_t *h_st = reinterpret_cast<uint32_t *>(h_g + nrows + 1);
     *h_st = 0;
+    // quartet-sharded: the kernel leaves this rank's value and rows in device memory, they are summed over the ranks
+    // (ncclAllReduce on the same stream) and only then copied to the host: every rank gets the same totals
+    const bool sharded = ctx->comm != nullptr;
+    double *o_f = h_g;
+    uint32_t *o_st = h_st;
+    if (sharded) {
+        rc = ensure(ctx, ctx->d_red, ctx->red_cap, (size_t)nrows + 1);
+        if (rc) return rc;
+        o_f = ctx->d_red;
+        o_st = nullptr;
+        if (ctx->nq == 0) CK(cudaMemsetAsync(ctx->d_red, 0, sizeof(double) * ((size_t)nrows + 1), ctx->stream));
+    }
     if (by_arg) std::memcpy(ctx->xarg.v, x, sizeof(double) * nparams);
     else {
         std::memcpy(ctx->h_pin, x, sizeof(double) * nparams);
@@ -3156,7 +3916,7 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
                 ctx->T, tb.off, reinterpret_cast<const uint2 *>(tb.prog), tb.qhdr, tb.WA,                                       \
                 reinterpret_cast<const double4 *>(tb.W), (uint32_t)tb.nA1, (uint32_t)tb.nA2,                                    \
                 (uint32_t)(tb.nA1 + (tb.nA1 & 1)), (uint32_t)tb.nq, ctx->d_X, ctx->d_xconst, H.nh, H.nt, ctx->d_partial,        \
-                h_g, tb.negw3, ctx->d_ticket, ctx->d_gbins, h_g + 1, ctx->d_status + 1, h_st, (by_arg ? 1 : 0) | kflags,        \
+                o_f, tb.negw3, ctx->d_ticket, ctx->d_gbins, o_f + 1, ctx->d_status + 1, o_st, (by_arg ? 1 : 0) | kflags,        \
                 tb.pen, ctx->d_trace, ctx->xarg);                                                                               \
         } else {                                                                                                               \
             CK(raise_smem_limit(k_eval_grad_small<WH>, smem));                                                                   \
@@ -3164,13 +3924,19 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
                 ctx->T, tb.off, reinterpret_cast<const uint2 *>(tb.prog), tb.qhdr, tb.WA,                                       \
                 reinterpret_cast<const double4 *>(tb.W), (uint32_t)tb.nA1, (uint32_t)tb.nA2,                                    \
                 (uint32_t)(tb.nA1 + (tb.nA1 & 1)), (uint32_t)tb.nq, ctx->d_X, ctx->d_xconst, H.nh, H.nt, ctx->d_partial,        \
-                h_g, tb.negw3, ctx->d_ticket, ctx->d_gpart, h_g + 1, ctx->d_status + 1, h_st, by_arg ? 1 : 0, tb.pen, ctx->xarg); \
+                o_f, tb.negw3, ctx->d_ticket, ctx->d_gpart, o_f + 1, ctx->d_status + 1, o_st, by_arg ? 1 : 0, tb.pen, ctx->xarg); \
         }                                                                                                                      \
     } while (0)
-    if (hdiag) LAUNCH_GRAD(true); else LAUNCH_GRAD(false);
+    if (ctx->nq > 0) { if (hdiag) LAUNCH_GRAD(true); else LAUNCH_GRAD(false); }
 #undef LAUNCH_GRAD
     CK(cudaGetLastError());
-    CK(wait_done(ctx->stream, h_st));
+    if (sharded) {
+        rc = comm_allreduce(ctx, ctx->d_red, (size_t)nrows + 1, ctx->stream);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(h_g, ctx->d_red, sizeof(double) * ((size_t)nrows + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_st, ctx->d_status + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else CK(wait_done(ctx->stream, h_st));
     ctx->counters[0] += 1;
     ctx->counters[1] += ctx->nq;
     ctx->counters[2] += 8 * nparams;

@@ -36,6 +36,7 @@ struct Problem {
     int n;
     std::vector<double> lo, hi;
     int64_t nevals = 0, nlaunches = 0;
+    int64_t budget = 0;     // what maxeval bounds: objective values the optimiser asked for (a gradient, however obtained, counts as one)
     bool use_fd = false;
 };
 
@@ -45,6 +46,7 @@ inline double clampd(double v, double a, double b) { return v < a ? a : (v > b ?
 int eval_batch(Problem &pb, int P, const std::vector<double> &X, std::vector<double> &f) {
     f.assign(P, 0.0);
     pb.nevals += P;
+    pb.budget += P;
     pb.nlaunches += 1;
     return snaq_eval(pb.ctx, P, pb.n, X.data(), f.data());
 }
@@ -70,6 +72,7 @@ int fd_gradient(Problem &pb, const std::vector<double> &x, double f0, std::vecto
         h[i] = (mode[i] == 0) ? (r0[i] - r1[i]) * 0.5 : std::fabs(r0[i] - x[i]);    // the representable step
     }
     int rc = eval_batch(pb, 2 * n, X, f);
+    pb.budget -= 2 * n - 1;            // the stencil of one gradient
     if (rc) return rc;
     g.assign(n, 0.0);
     hdiag.assign(n, 0.0);
@@ -93,6 +96,7 @@ int gradient(Problem &pb, const std::vector<double> &x, double &f0, bool have_f,
         g.assign(pb.n, 0.0);
         if (want_h) hdiag.assign(pb.n, 0.0);
         pb.nevals += 1;
+        pb.budget += 1;
         pb.nlaunches += 1;
         return snaq_eval_grad(pb.ctx, pb.n, x.data(), &f0, g.data(), want_h ? hdiag.data() : nullptr);
     }
@@ -132,6 +136,16 @@ extern "C" int snaq_optbl(snaq_ctx *ctx, const snaq_optbl_opts *o, double *x_io,
     }
     std::vector<double> x(x_io, x_io + n);
     for (int i = 0; i < n; i++) x[i] = clampd(x[i], pb.lo[i], pb.hi[i]);
+    {   // a quartet-sharded context without a communicator only knows its own partial sums: refuse (the gradient call
+        // carries the message); with one, every rank runs this same loop on the same totals
+        int32_t world = 1, has_comm = 0;
+        if (snaq_comm_info(ctx, nullptr, &world, &has_comm, nullptr) == SNAQ_OK && world > 1 && !has_comm) {
+            double f0 = 0.0;
+            std::vector<double> g0(std::max(n, 1));
+            rc = snaq_eval_grad(ctx, n, x.data(), &f0, g0.data(), nullptr);
+            return rc ? rc : SNAQ_EINVAL;
+        }
+    }
     double f = 0.0;
     std::vector<double> g, hd;
     rc = gradient(pb, x, f, false, g, hd, true);
@@ -152,9 +166,9 @@ extern "C" int snaq_optbl(snaq_ctx *ctx, const snaq_optbl_opts *o, double *x_io,
     const bool no_unit_step = getenv("SNAQ_OPTBL_NO_UNIT_STEP") != nullptr;
     const int hd_every = getenv("SNAQ_OPTBL_HD_EVERY") ? std::max(1, atoi(getenv("SNAQ_OPTBL_HD_EVERY"))) : 8;
     const bool verbose = getenv("SNAQ_OPTBL_VERBOSE") != nullptr;      // "inside obj with x ..." of the reference (:369-378)
-    // maxeval bounds the number of parameter vectors evaluated, as NLopt.maxeval! does (:365); a ladder launch that starts
-    // below the bound is finished
-    while (pb.nevals < maxeval) {
+    // maxeval bounds the number of objective values asked for, as NLopt.maxeval! does (:365): every rung of a ladder counts,
+    // a gradient pass counts once; a launch that starts below the bound is finished
+    while (pb.budget < maxeval) {
         iter++;
         // free variables: not pinned at a bound by the gradient
         std::vector<char> freev(n, 1);

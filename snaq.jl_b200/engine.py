@@ -33,7 +33,8 @@ EXPORTS = ["snaq_create", "snaq_destroy", "snaq_last_error", "snaq_version", "sn
            "snaq_set_sampled", "snaq_set_network", "snaq_patch_network", "snaq_num_params", "snaq_get_params",
            "snaq_eval", "snaq_eval_device", "snaq_eval_quartets", "snaq_get_descriptors", "snaq_get_counters",
            "snaq_check_status", "snaq_measure_fp64_peak", "snaq_get_trace", "snaq_eval_grad", "snaq_optbl", "snaq_update_bl", "snaq_get_hasedge",
-           "snaq_eval_topologies", "snaq_optbl_topologies", "snaq_sample_quartets", "snaq_set_ci", "snaq_resample_obscf", "snaq_get_obscf"]
+           "snaq_eval_topologies", "snaq_optbl_topologies", "snaq_sample_quartets", "snaq_set_ci", "snaq_resample_obscf", "snaq_get_obscf",
+           "snaq_comm_unique_id", "snaq_comm_init", "snaq_comm_info"]
 
 
 class _OptblOpts(C.Structure):
@@ -81,8 +82,10 @@ class Engine:
         if rc:
             raise SnaqError(f"snaq_create failed ({rc}): {self.lib.snaq_last_error(None).decode()}")
         self.device = device
+        self.rank, self.world_size = rank, max(world_size, 1)
         self.nparams = None
         self.nq = 0
+        self.q_begin, self.nq_local = 0, 0
         self._data_id = None
 
     def close(self):
@@ -100,11 +103,37 @@ class Engine:
         if rc:
             raise SnaqError(self.lib.snaq_last_error(self.ctx).decode())
 
+    # -- quartet-sharded mode --------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """the 128-byte id rank 0 creates and hands to the other ranks (snaq_comm_unique_id)"""
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        if lib.snaq_comm_unique_id(buf):
+            raise SnaqError(lib.snaq_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, comm_id: bytes) -> None:
+        """collective over the ranks of a quartet-sharded context: afterwards eval / eval_device / eval_grad / optbl
+        return totals over all ranks (snaq_comm_init)"""
+        if len(comm_id) != 128:
+            raise SnaqError("the communicator id has 128 bytes")
+        self._chk(self.lib.snaq_comm_init(self.ctx, C.c_char_p(comm_id)))
+
+    def comm_info(self):
+        r = C.c_int32(); w = C.c_int32(); h = C.c_int32(); f = C.c_int32()
+        self._chk(self.lib.snaq_comm_info(self.ctx, C.byref(r), C.byref(w), C.byref(h), C.byref(f)))
+        return dict(rank=r.value, world_size=w.value, has_comm=bool(h.value), fused_epilogue=bool(f.value))
+
     # -- data ----------------------------------------------------------------------
     def set_data(self, d: DataCF) -> None:
         self._chk(self.lib.snaq_set_data(self.ctx, C.c_int32(len(d.taxa)), C.c_int64(d.numQuartets),
                                          _p(d.quartet_taxa), _p(d.obsCF)))
         self.nq = d.numQuartets
+        # a quartet-sharded context keeps the contiguous block [q_begin, q_begin + nq_local) (snaq_set_data); the per-quartet
+        # read-backs (eval_quartets, descriptors, hasedge) of such a context cover its own block
+        self.q_begin = self.nq * self.rank // self.world_size
+        self.nq_local = self.nq * (self.rank + 1) // self.world_size - self.q_begin
         self.nparams = None
         if not bool(np.all(d.sampled)):
             self.set_sampled(d.sampled)
@@ -203,9 +232,9 @@ class Engine:
 
     def eval_quartets(self, x, want=("expcf", "logpl", "deltacf")):
         x = np.ascontiguousarray(x, dtype=np.float64)
-        e = np.zeros((self.nq, 3)) if "expcf" in want else None
-        l = np.zeros(self.nq) if "logpl" in want else None
-        dl = np.zeros(self.nq) if "deltacf" in want else None
+        e = np.zeros((self.nq_local, 3)) if "expcf" in want else None
+        l = np.zeros(self.nq_local) if "logpl" in want else None
+        dl = np.zeros(self.nq_local) if "deltacf" in want else None
         self._chk(self.lib.snaq_eval_quartets(self.ctx, C.c_int32(x.size), _p(x), _p(e), _p(l), _p(dl)))
         return e, l, dl
 
@@ -243,11 +272,11 @@ class Engine:
     def hasedge(self):
         """(hasEdge [nq, nparams] 0/1, indexht lists) of every quartet: updateHasEdge! / parameters!(qnet,net)"""
         npar = max(self.nparams, 1)
-        he = np.zeros((self.nq, npar), np.uint8)
-        ix = np.full((self.nq, npar), -1, np.int32)
-        nix = np.zeros(self.nq, np.int32)
+        he = np.zeros((self.nq_local, npar), np.uint8)
+        ix = np.full((self.nq_local, npar), -1, np.int32)
+        nix = np.zeros(self.nq_local, np.int32)
         self._chk(self.lib.snaq_get_hasedge(self.ctx, _p(he), _p(ix), _p(nix)))
-        return he[:, : self.nparams], [list(ix[i, : nix[i]]) for i in range(self.nq)]
+        return he[:, : self.nparams], [list(ix[i, : nix[i]]) for i in range(self.nq_local)]
 
     def update_bl(self):
         """per edge-length parameter: (Nquartets, edgeL) of ``updateBL!`` (src/readquartetdata.jl:838-861)"""
@@ -257,8 +286,8 @@ class Engine:
         return nq[: self.nt], el[: self.nt]
 
     def descriptors(self, max_types: int = 8):
-        which = np.zeros(self.nq, np.int8); ntype = np.zeros(self.nq, np.int8)
-        types = np.zeros((self.nq, max_types), np.int8); formula = np.zeros((self.nq, 3), np.int8)
+        which = np.zeros(self.nq_local, np.int8); ntype = np.zeros(self.nq_local, np.int8)
+        types = np.zeros((self.nq_local, max_types), np.int8); formula = np.zeros((self.nq_local, 3), np.int8)
         self._chk(self.lib.snaq_get_descriptors(self.ctx, _p(which), _p(ntype), _p(types), C.c_int32(max_types),
                                                 _p(formula), None))
         return dict(which=which, ntype=ntype, types=types, formula=formula)

@@ -177,6 +177,13 @@ struct snaq_ctx {
     std::vector<double> W;
 };
 
+int snaq_comm_info(snaq_ctx *, int32_t *rank, int32_t *world_size, int32_t *has_comm, int32_t *fused) {
+    if (rank) *rank = 0;
+    if (world_size) *world_size = 1;
+    if (has_comm) *has_comm = 0;
+    if (fused) *fused = 0;
+    return 0;
+}
 int snaq_num_params(snaq_ctx *c, int32_t *nparams, int32_t *n_gamma, int32_t *n_t, int32_t *n_gammaz) {
     if (nparams) *nparams = c->H.nparams;
     if (n_gamma) *n_gamma = c->H.nh;
