@@ -1154,16 +1154,16 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
 #define RN_W_BYTES 1024
 #define RN_DESC_AT RN_W_BYTES
 #define RN_OFF_AT (RN_W_BYTES + 32)
-#define RN_PROG_CHUNKS 128  /* program chunks a tile record can hold (else: read from the run table in global memory) */
+#define RN_PROG_CHUNKS 64   /* program chunks a tile record can hold (else: read from the run table in global memory) */
 #define RN_STAGE_BYTES (RN_OFF_AT + 272 + RN_PROG_CHUNKS * 8)        /* 2352: the largest record */
 struct __align__(16) RunTile {
     unsigned long long mask;   // bit j: quartet q0 + j starts a run
+    uint16_t n;                // number of quartets
+    uint16_t flags;            // bit 0: 4-cycle tile (weights are W[q], 32 B); bit 1: programs are in the record
+    uint16_t prog_at;          // byte offset of the programs inside the record
+    uint16_t nruns;
     uint32_t q0;               // sorted position of the first quartet
     uint32_t pbeg;             // first program chunk of the tile's runs in prog_u (used when the programs are not in the record)
-    uint16_t n;                // number of quartets
-    uint16_t prog_at;          // byte offset of the programs inside the record
-    uint16_t flags;            // bit 0: 4-cycle tile (weights are W[q], 32 B); bit 1: programs are in the record
-    uint16_t nruns;
     uint32_t u0, pad;          // run of quartet q0
 };
 static_assert(sizeof(RunTile) == 32, "RunTile");
@@ -1243,13 +1243,11 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && CPL == 1) ? 2 : 1) 
     unsigned char *wring = ring + (size_t)warp * RN_NST * RN_STAGE_BYTES;
     const bool noreuse = rm.noreuse != 0;
     const unsigned nul = rm.nul;
-    // the k-th tile of this warp: segments gw, gw + nwg, ... of tps consecutive tiles each
-    auto tile_of = [&](unsigned k) -> unsigned {
-        const unsigned seg = gw + (k / rm.tps) * nwg;
-        const unsigned t = seg * rm.tps + k % rm.tps;
-        return (seg < rm.nseg && t < rm.ntiles) ? t : 0xffffffffu;
+    // this warp's segments: gw, gw + nwg, ... of tps consecutive tiles each; the request side runs RN_NST tiles ahead
+    unsigned i_seg = gw, i_t = gw * rm.tps, i_end = min(i_t + rm.tps, rm.ntiles);
+    auto i_advance = [&]() {
+        if (++i_t >= i_end) { i_seg += nwg; i_t = i_seg * rm.tps; i_end = min(i_t + rm.tps, rm.ntiles); }
     };
-    // (a segment's tiles past ntiles only occur in the last segment: the warp's sequence ends there)
     auto issue = [&](unsigned o0, unsigned o1, unsigned sg) {                        // lane 0 only: one bulk copy per tile
         const unsigned bytes = (o1 - o0) * 16u;
         mbar_expect_tx(&wbar[sg], bytes);
@@ -1265,15 +1263,12 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && CPL == 1) ? 2 : 1) 
         tma_load_1d(xs, XFT + (size_t)g * n_full * TW, (unsigned)n_full * TW * 8u, &bars[0]);
     }
     // the warp's first tiles are requested before anything else is waited for
-    unsigned kiss = 0;                                                               // tiles requested so far
-    for (; kiss < RN_NST; kiss++) {
-        const unsigned t = tile_of(kiss);
-        if (t == 0xffffffffu) break;
-        if (lane == 0) issue(__ldg(rec_off + t), __ldg(rec_off + t + 1), kiss);
+    for (unsigned k = 0; k < RN_NST && i_seg < rm.nseg; k++) {
+        if (lane == 0) issue(__ldg(rec_off + i_t), __ldg(rec_off + i_t + 1), k);
+        i_advance();
     }
-    unsigned tn = tile_of(kiss);                                                     // next tile to request, and its record
-    unsigned no0 = 0, no1 = 0;
-    if (tn != 0xffffffffu) { no0 = __ldg(rec_off + tn); no1 = __ldg(rec_off + tn + 1); }
+    unsigned no0 = 0, no1 = 0;                                                       // the record of the next tile to request
+    if (i_seg < rm.nseg) { no0 = __ldg(rec_off + i_t); no1 = __ldg(rec_off + i_t + 1); }
     __syncwarp();
     const SnaqMath M = load_math_tables(mt, tid);
     unsigned st = 0;
@@ -1283,178 +1278,182 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && CPL == 1) ? 2 : 1) 
     unsigned sg = 0, phase = 0;
     // segment sums: w0*L (a0, b0, e0, f0), w1*T (a1, b1, e1, f1), 4-cycles.  Four independent accumulators per product
     // and candidate: the FP64 pipe has a long dependent-issue latency and a block has few warps (the xf tile is large)
-    double a0[CPL], a1[CPL], b0[CPL], b1[CPL], e0[CPL], e1[CPL], f0[CPL], f1[CPL], cacc[CPL];
+    constexpr int NA = (CPL == 2 && WARPS == 16) ? 2 : 4;       // accumulators per product and candidate (register budget)
+    double aL[CPL][NA], aT[CPL][NA], cacc[CPL];
     double cL[CPL], cT[CPL], c2[CPL];                           // the current run's constants: tree-like (L, T); 4-cycle (l0, l1, l2)
     double cz[CPL][3];                                          // bad diamond I: the three expected CFs
     bool cBD1 = false;
 #pragma unroll
     for (int c = 0; c < CPL; c++) {
-        a0[c] = a1[c] = b0[c] = b1[c] = e0[c] = e1[c] = f0[c] = f1[c] = cacc[c] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NA; q++) { aL[c][q] = 0.0; aT[c][q] = 0.0; }
+        cacc[c] = 0.0;
         cL[c] = cT[c] = c2[c] = 0.0; cz[c][0] = cz[c][1] = cz[c][2] = 0.0;
     }
 #pragma unroll 1
-    for (unsigned k = 0;; k++) {
-        const unsigned t = tile_of(k);
-        if (t == 0xffffffffu) break;
-        mbar_wait(&wbar[sg], phase);
-        const unsigned char *stg = wring + sg * RN_STAGE_BYTES;
-        const RunTile d = *reinterpret_cast<const RunTile *>(stg + RN_DESC_AT);
-        const uint32_t *soff = reinterpret_cast<const uint32_t *>(stg + RN_OFF_AT);
-        const bool staged = (d.flags & 2u) != 0;
-        const uint2 *sprog = reinterpret_cast<const uint2 *>(stg + d.prog_at);
-        const bool isC = (d.flags & 1u) != 0;
-        const bool seg_first = (k % rm.tps) == 0;
-        auto chunk = [&](uint32_t c) { return staged ? sprog[c] : __ldg(prog_u + d.pbeg + c); };
-        // the constants of the r-th run of the tile, whose first quartet here sits at sorted position pos
-        auto compute = [&](uint32_t r, int64_t pos) {
-            const uint32_t c0 = soff[r], c1 = soff[r + 1];
-            if (isC) {
-                const uint2 w = chunk(c0);
-                cBD1 = (w.y & 0xffffu) == nul;
-#pragma unroll
-                for (int c = 0; c < CPL; c++) {
-                    const XLaneS xf{xl + 32 * c, (unsigned)TW};
-                    if (!cBD1) {
-                        const double g2 = xf(w.x & 0xffffu), ca = xf(w.x >> 16), cm = xf(w.y & 0xffffu), cb = xf(w.y >> 16);
-                        const double g1 = 1.0 - g2;
-                        const double y5 = snaq_exp(-snaq_clamp10(cm - ca), M), y6 = snaq_exp(-snaq_clamp10(cb - cm), M);
-                        const double cf0 = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;
-                        const double cf1 = g1 * 1.0 / 3.0 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
-                        const double cf2 = g1 * 1.0 / 3.0 * y5 + g2 * 1.0 / 3.0 * y6;
-                        cL[c] = snaq_log_pos(cf0, M); cT[c] = snaq_log_pos(cf1, M); c2[c] = snaq_log_pos(cf2, M);
-                    } else {
-                        const uint16_t pcw[4] = {(uint16_t)(w.x & 0xffffu), (uint16_t)(w.x >> 16), (uint16_t)nul, (uint16_t)nul};
-                        snaq_t5_cf(SNAQ_KIND_T5BD1, pcw, xf, M, cz[c]);
-                    }
-                }
-            } else if (pos >= rm.nA) {
-                const uint16_t *pc = staged ? reinterpret_cast<const uint16_t *>(sprog + c0)
-                                            : reinterpret_cast<const uint16_t *>(prog_u + d.pbeg + c0);
-#pragma unroll
-                for (int c = 0; c < CPL; c++) {
-                    const XLaneS xf{xl + 32 * c, (unsigned)TW};
-                    const double tt = snaq_tree_terms_t1(pc, xf, M, st);
-                    const double major = fma(SNAQ_K_M23, snaq_exp(-tt, M), 1.0);
-                    if (major < 0.0) st |= SNAQ_S_NEGLEN;
-                    cL[c] = snaq_log(major, M);
-                    cT[c] = tt + SNAQ_K_LOG3;
-                }
-            } else {
-                double t0[CPL], t1[CPL];
-#pragma unroll
-                for (int c = 0; c < CPL; c++) { t0[c] = 0.0; t1[c] = 0.0; }
+    for (unsigned seg = gw; seg < rm.nseg; seg += nwg) {
+        const unsigned t0 = seg * rm.tps, tend = min(t0 + rm.tps, rm.ntiles);
+        bool seg_first = true;
 #pragma unroll 1
-                for (uint32_t cc = c0; cc < c1; ++cc) {
-                    const uint2 w = chunk(cc);
-#pragma unroll
+        for (unsigned t = t0; t < tend; t++) {
+            mbar_wait(&wbar[sg], phase);
+            const unsigned char *stg = wring + sg * RN_STAGE_BYTES;
+            const RunTile d = *reinterpret_cast<const RunTile *>(stg + RN_DESC_AT);
+            const uint32_t *soff = reinterpret_cast<const uint32_t *>(stg + RN_OFF_AT);
+            const bool staged = (d.flags & 2u) != 0;
+            const uint2 *sprog = reinterpret_cast<const uint2 *>(stg + d.prog_at);
+            const bool isC = (d.flags & 1u) != 0;
+            auto chunk = [&](uint32_t c) { return staged ? sprog[c] : __ldg(prog_u + d.pbeg + c); };
+            // the constants of the r-th run of the tile, whose first quartet here sits at sorted position pos
+            auto compute = [&](uint32_t r, int64_t pos) {
+                const uint32_t c0 = soff[r], c1 = soff[r + 1];
+                if (isC) {
+                    const uint2 w = chunk(c0);
+                    cBD1 = (w.y & 0xffffu) == nul;
+    #pragma unroll
                     for (int c = 0; c < CPL; c++) {
                         const XLaneS xf{xl + 32 * c, (unsigned)TW};
-                        t0[c] += xf(w.x & 0xffffu) - xf(w.x >> 16);
-                        t1[c] += xf(w.y & 0xffffu) - xf(w.y >> 16);
+                        if (!cBD1) {
+                            const double g2 = xf(w.x & 0xffffu), ca = xf(w.x >> 16), cm = xf(w.y & 0xffffu), cb = xf(w.y >> 16);
+                            const double g1 = 1.0 - g2;
+                            const double y5 = snaq_exp(-snaq_clamp10(cm - ca), M), y6 = snaq_exp(-snaq_clamp10(cb - cm), M);
+                            const double cf0 = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;
+                            const double cf1 = g1 * 1.0 / 3.0 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
+                            const double cf2 = g1 * 1.0 / 3.0 * y5 + g2 * 1.0 / 3.0 * y6;
+                            cL[c] = snaq_log_pos(cf0, M); cT[c] = snaq_log_pos(cf1, M); c2[c] = snaq_log_pos(cf2, M);
+                        } else {
+                            const uint16_t pcw[4] = {(uint16_t)(w.x & 0xffffu), (uint16_t)(w.x >> 16), (uint16_t)nul, (uint16_t)nul};
+                            snaq_t5_cf(SNAQ_KIND_T5BD1, pcw, xf, M, cz[c]);
+                        }
                     }
-                }
-#pragma unroll
-                for (int c = 0; c < CPL; c++) {
-                    const double tt = snaq_clamp10(t0[c] + t1[c]);
-                    cL[c] = snaq_log_pos(fma(SNAQ_K_M23, snaq_exp(-tt, M), 1.0), M);
-                    cT[c] = tt + SNAQ_K_LOG3;
-                }
-            }
-        };
-        const double2 *sw = reinterpret_cast<const double2 *>(stg);
-        if (!isC && !noreuse && (d.mask >> 1) == 0ull && d.n == RN_TQ) {
-            // the whole tile is one run (the common case on large tables): straight-line, no loop control
-            if ((d.mask & 1ull) || seg_first) compute(0u, (int64_t)d.q0);
-#pragma unroll
-            for (int i = 0; i < RN_TQ; i += 4) {
-                const double2 wa = sw[i], wb = sw[i + 1], wc = sw[i + 2], wd = sw[i + 3];
-#pragma unroll
-                for (int c = 0; c < CPL; c++) {
-                    a0[c] = fma(wa.x, cL[c], a0[c]); a1[c] = fma(wa.y, cT[c], a1[c]);
-                    b0[c] = fma(wb.x, cL[c], b0[c]); b1[c] = fma(wb.y, cT[c], b1[c]);
-                    e0[c] = fma(wc.x, cL[c], e0[c]); e1[c] = fma(wc.y, cT[c], e1[c]);
-                    f0[c] = fma(wd.x, cL[c], f0[c]); f1[c] = fma(wd.y, cT[c], f1[c]);
-                }
-            }
-        } else {
-            unsigned j = 0, r = 0;
-            const unsigned n = d.n;
-#pragma unroll 1
-            while (j < n) {
-                const unsigned long long rest = (d.mask >> j) >> 1;
-                const unsigned jend = rest ? min(j + (unsigned)__ffsll((long long)rest), n) : n;
-                if (j > 0) r++;
-                if (j > 0 || (d.mask & 1ull) || seg_first) compute(r, (int64_t)d.q0 + j);
-                if (!isC) {
-                    if (!noreuse) {
-                        unsigned i = j;
-#pragma unroll 1
-                        for (; i + 3 < jend; i += 4) {
-                            const double2 wa = sw[i], wb = sw[i + 1], wc = sw[i + 2], wd = sw[i + 3];
-#pragma unroll
-                            for (int c = 0; c < CPL; c++) {
-                                a0[c] = fma(wa.x, cL[c], a0[c]); a1[c] = fma(wa.y, cT[c], a1[c]);
-                                b0[c] = fma(wb.x, cL[c], b0[c]); b1[c] = fma(wb.y, cT[c], b1[c]);
-                                e0[c] = fma(wc.x, cL[c], e0[c]); e1[c] = fma(wc.y, cT[c], e1[c]);
-                                f0[c] = fma(wd.x, cL[c], f0[c]); f1[c] = fma(wd.y, cT[c], f1[c]);
-                            }
-                        }
-#pragma unroll 1
-                        for (; i < jend; i++) {
-                            const double2 wa = sw[i];
-#pragma unroll
-                            for (int c = 0; c < CPL; c++) { a0[c] = fma(wa.x, cL[c], a0[c]); a1[c] = fma(wa.y, cT[c], a1[c]); }
-                        }
-                    } else {
-                        // measurement aid (SNAQ_REUSE=0): the program is evaluated again for every quartet
-#pragma unroll 1
-                        for (unsigned i = j; i < jend; i++) {
-                            compute(r, (int64_t)d.q0 + j);
-                            const double2 wa = sw[i];
-#pragma unroll
-                            for (int c = 0; c < CPL; c++) { a0[c] = fma(wa.x, cL[c], a0[c]); a1[c] = fma(wa.y, cT[c], a1[c]); }
-                        }
+                } else if (pos >= rm.nA) {
+                    const uint16_t *pc = staged ? reinterpret_cast<const uint16_t *>(sprog + c0)
+                                                : reinterpret_cast<const uint16_t *>(prog_u + d.pbeg + c0);
+    #pragma unroll
+                    for (int c = 0; c < CPL; c++) {
+                        const XLaneS xf{xl + 32 * c, (unsigned)TW};
+                        const double tt = snaq_tree_terms_t1(pc, xf, M, st);
+                        const double major = fma(SNAQ_K_M23, snaq_exp(-tt, M), 1.0);
+                        if (major < 0.0) st |= SNAQ_S_NEGLEN;
+                        cL[c] = snaq_log(major, M);
+                        cT[c] = tt + SNAQ_K_LOG3;
                     }
                 } else {
-                    const double4 *sw4 = reinterpret_cast<const double4 *>(stg);
-#pragma unroll 1
-                    for (unsigned i = j; i < jend; i++) {
-                        if (noreuse) compute(r, (int64_t)d.q0 + j);
-                        const double4 w4 = sw4[i];
-                        if (!cBD1) {
-#pragma unroll
-                            for (int c = 0; c < CPL; c++) {
-                                a0[c] = fma(w4.x, cL[c], a0[c]);
-                                b0[c] = fma(w4.y, cT[c], b0[c]);
-                                cacc[c] = fma(w4.z, c2[c], cacc[c]);
-                            }
-                        } else {
-                            const double wq[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-                            for (int c = 0; c < CPL; c++) cacc[c] += snaq_loglik_t5(cz[c], wq, M, st, nullptr);   // its own W3 and the per-quartet penalty
+                    double t0[CPL], t1[CPL];
+    #pragma unroll
+                    for (int c = 0; c < CPL; c++) { t0[c] = 0.0; t1[c] = 0.0; }
+    #pragma unroll 1
+                    for (uint32_t cc = c0; cc < c1; ++cc) {
+                        const uint2 w = chunk(cc);
+    #pragma unroll
+                        for (int c = 0; c < CPL; c++) {
+                            const XLaneS xf{xl + 32 * c, (unsigned)TW};
+                            t0[c] += xf(w.x & 0xffffu) - xf(w.x >> 16);
+                            t1[c] += xf(w.y & 0xffffu) - xf(w.y >> 16);
                         }
                     }
+    #pragma unroll
+                    for (int c = 0; c < CPL; c++) {
+                        const double tt = snaq_clamp10(t0[c] + t1[c]);
+                        cL[c] = snaq_log_pos(fma(SNAQ_K_M23, snaq_exp(-tt, M), 1.0), M);
+                        cT[c] = tt + SNAQ_K_LOG3;
+                    }
                 }
-                j = jend;
+            };
+            const double2 *sw = reinterpret_cast<const double2 *>(stg);
+            if (!isC && !noreuse && (d.mask >> 1) == 0ull && d.n == RN_TQ) {
+                // the whole tile is one run (the common case on large tables): straight-line, no loop control
+                if ((d.mask & 1ull) || seg_first) compute(0u, (int64_t)d.q0);
+    #pragma unroll
+                for (int i = 0; i < RN_TQ; i += NA) {
+                    double2 w[NA];
+    #pragma unroll
+                    for (int q = 0; q < NA; q++) w[q] = sw[i + q];
+    #pragma unroll
+                    for (int q = 0; q < NA; q++) {
+    #pragma unroll
+                        for (int c = 0; c < CPL; c++) { aL[c][q] = fma(w[q].x, cL[c], aL[c][q]); aT[c][q] = fma(w[q].y, cT[c], aT[c][q]); }
+                    }
+                }
+            } else {
+                unsigned j = 0, r = 0;
+                const unsigned n = d.n;
+    #pragma unroll 1
+                while (j < n) {
+                    const unsigned long long rest = (d.mask >> j) >> 1;
+                    const unsigned jend = rest ? min(j + (unsigned)__ffsll((long long)rest), n) : n;
+                    if (j > 0) r++;
+                    if (j > 0 || (d.mask & 1ull) || seg_first) compute(r, (int64_t)d.q0 + j);
+                    if (!isC) {
+                        if (!noreuse) {
+                            unsigned i = j;
+    #pragma unroll 1
+                            for (; i + 3 < jend; i += 4) {
+                                const double2 wa = sw[i], wb = sw[i + 1], wc = sw[i + 2], wd = sw[i + 3];
+    #pragma unroll
+                                for (int c = 0; c < CPL; c++) {
+                                    aL[c][0] = fma(wa.x, cL[c], aL[c][0]); aT[c][0] = fma(wa.y, cT[c], aT[c][0]);
+                                    aL[c][1] = fma(wb.x, cL[c], aL[c][1]); aT[c][1] = fma(wb.y, cT[c], aT[c][1]);
+                                    aL[c][2 % NA] = fma(wc.x, cL[c], aL[c][2 % NA]); aT[c][2 % NA] = fma(wc.y, cT[c], aT[c][2 % NA]);
+                                    aL[c][3 % NA] = fma(wd.x, cL[c], aL[c][3 % NA]); aT[c][3 % NA] = fma(wd.y, cT[c], aT[c][3 % NA]);
+                                }
+                            }
+    #pragma unroll 1
+                            for (; i < jend; i++) {
+                                const double2 wa = sw[i];
+    #pragma unroll
+                                for (int c = 0; c < CPL; c++) { aL[c][0] = fma(wa.x, cL[c], aL[c][0]); aT[c][0] = fma(wa.y, cT[c], aT[c][0]); }
+                            }
+                        } else {
+                            // measurement aid (SNAQ_REUSE=0): the program is evaluated again for every quartet
+    #pragma unroll 1
+                            for (unsigned i = j; i < jend; i++) {
+                                compute(r, (int64_t)d.q0 + j);
+                                const double2 wa = sw[i];
+    #pragma unroll
+                                for (int c = 0; c < CPL; c++) { aL[c][0] = fma(wa.x, cL[c], aL[c][0]); aT[c][0] = fma(wa.y, cT[c], aT[c][0]); }
+                            }
+                        }
+                    } else {
+                        const double4 *sw4 = reinterpret_cast<const double4 *>(stg);
+    #pragma unroll 1
+                        for (unsigned i = j; i < jend; i++) {
+                            if (noreuse) compute(r, (int64_t)d.q0 + j);
+                            const double4 w4 = sw4[i];
+                            if (!cBD1) {
+    #pragma unroll
+                                for (int c = 0; c < CPL; c++) {
+                                    aL[c][0] = fma(w4.x, cL[c], aL[c][0]);
+                                    aL[c][1] = fma(w4.y, cT[c], aL[c][1]);
+                                    cacc[c] = fma(w4.z, c2[c], cacc[c]);
+                                }
+                            } else {
+                                const double wq[4] = {w4.x, w4.y, w4.z, w4.w};
+    #pragma unroll
+                                for (int c = 0; c < CPL; c++) cacc[c] += snaq_loglik_t5(cz[c], wq, M, st, nullptr);   // its own W3 and the per-quartet penalty
+                            }
+                        }
+                    }
+                    j = jend;
+                }
             }
+            seg_first = false;
+            __syncwarp();                                              // every lane is done with this stage
+            if (i_seg < rm.nseg) {
+                if (lane == 0) issue(no0, no1, sg);
+                i_advance();
+                if (i_seg < rm.nseg) { no0 = __ldg(rec_off + i_t); no1 = __ldg(rec_off + i_t + 1); }   // consumed one tile later
+            }
+            if (++sg == RN_NST) { sg = 0; phase ^= 1u; }
         }
-        __syncwarp();                                                  // every lane is done with this stage
-        if (tn != 0xffffffffu) {
-            if (lane == 0) issue(no0, no1, sg);
-            kiss++;
-            tn = tile_of(kiss);
-            if (tn != 0xffffffffu) { no0 = __ldg(rec_off + tn); no1 = __ldg(rec_off + tn + 1); }   // consumed one tile later
-        }
-        if (++sg == RN_NST) { sg = 0; phase ^= 1u; }
-        // the segment is complete after its last tile: one partial row per segment
-        if ((k % rm.tps) == rm.tps - 1 || t + 1 == rm.ntiles) {
-            const unsigned seg = t / rm.tps;
+        // the segment is complete: one partial row per segment
 #pragma unroll
-            for (int c = 0; c < CPL; c++) {
-                partial[(size_t)seg * Ppad + TW * g + 32 * c + lane] =
-                    (((a0[c] + b0[c]) + (e0[c] + f0[c])) - ((a1[c] + b1[c]) + (e1[c] + f1[c]))) + cacc[c];
-                a0[c] = a1[c] = b0[c] = b1[c] = e0[c] = e1[c] = f0[c] = f1[c] = cacc[c] = 0.0;
-            }
+        for (int c = 0; c < CPL; c++) {
+            double sl = 0.0, stt = 0.0;
+#pragma unroll
+            for (int q = 0; q < NA; q++) { sl += aL[c][q]; stt += aT[c][q]; aL[c][q] = 0.0; aT[c][q] = 0.0; }
+            partial[(size_t)seg * Ppad + TW * g + 32 * c + lane] = (sl - stt) + cacc[c];
+            cacc[c] = 0.0;
         }
     }
     if (st) atomicOr(status, st);
@@ -3019,12 +3018,13 @@ static int eval_device_local(snaq_ctx *ctx, int P, const double *dX, double *dou
                 return (size_t)384 + ((((size_t)1 + warps * RN_NST) * 8 + 127) & ~size_t(127)) + (size_t)H.n_full * 256 * cpl +
                        (size_t)warps * RN_NST * RN_STAGE_BYTES;
             };
-            // two candidates per lane (the weights of a quartet are loaded once for 64 candidates) when the batch has 64
-            // and the wider xf tile fits; 16-warp blocks when only one block fits per SM anyway
-            int cpl = (P > 32 && smem_of(8, 2) <= 200 * 1024) ? 2 : 1;
-            if (const char *ev = getenv("SNAQ_RUNS_CPL")) { const int v = atoi(ev); if (v == 1 || (v == 2 && smem_of(8, 2) <= 220 * 1024)) cpl = v; }
-            int warps = (cpl == 1 && smem_of(8, cpl) > 110 * 1024 && smem_of(16, cpl) <= 220 * 1024) ? 16 : 8;
-            if (const char *ev = getenv("SNAQ_RUNS_WARPS")) { const int v = atoi(ev); if (v == 8 || (v == 16 && smem_of(16, cpl) <= 220 * 1024)) warps = v; }
+            // One candidate per lane and 16-warp blocks by default (measured, 100 taxa, 256 vectors: 0.39 ms; two candidates per
+            // lane with 8-warp blocks, which halves the shared-memory reads of the weights but leaves 2 warps per scheduler:
+            // 0.41 ms; SNAQ_RUNS_CPL / SNAQ_RUNS_WARPS select the variants for measurements)
+            int cpl = 1;
+            if (const char *ev = getenv("SNAQ_RUNS_CPL")) { const int v = atoi(ev); if (v == 1 || (v == 2 && P > 32 && smem_of(8, 2) <= 220 * 1024)) cpl = v; }
+            int warps = (cpl == 1 && smem_of(16, 1) <= 224 * 1024 && (smem_of(8, 1) > 110 * 1024 || (int64_t)ctx->rn_nseg >= 16 * (int64_t)ctx->sm_count)) ? 16 : 8;
+            if (const char *ev = getenv("SNAQ_RUNS_WARPS")) { const int v = atoi(ev); if (v == 8 || (v == 16 && cpl == 1 && smem_of(16, cpl) <= 224 * 1024)) warps = v; }
             const size_t smem = smem_of(warps, cpl);
             if (smem > 227 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_runs"; return SNAQ_EINVAL; }
             const int tw = 32 * cpl;
