@@ -1,17 +1,25 @@
 #!/usr/bin/env python
-"""bench.py — quartet pseudolikelihood evaluations per second (FP64).
+"""bench.py — quartet pseudolikelihood evaluations per second (FP64) and the search-shaped workloads around them.
 
-One "step" = one pass of the hot path over one batch: every quartet of the table
-evaluated under every parameter vector of an optBL!-style batch (BASELINE.json
-configs[1]: synthetic 30-taxon level-1 network, h=2, all 27,405 quartets x 4096
-parameter vectors = 112.3 M evals per step).
+One "step" = one pass of the hot path over one batch: every quartet of the table evaluated under every parameter
+vector of an optBL!-style batch (BASELINE.json configs[1]: synthetic 30-taxon level-1 network, h=2, all 27,405
+quartets x 4096 parameter vectors = 112.3 M evals per step).
 
   python bench.py --gpus N --steps K --warmup W            # the engine
   python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port)
 
-N>1 (torchrun): the path shards by independent units — every rank evaluates its own
-batch on its own GPU with no data-path collective (independent snaq! runs / bootstrap
-replicates) => weak scaling; value = all ranks' evals / max-over-ranks time.
+Legs of the JSON line (rank 0 prints it):
+  value / e2e / roofline      configs[1], one independent batch per GPU (weak scaling, no data-path collective)
+  north_star                  100 taxa, 3,921,225 quartets, 256 vectors per launch (the north star's config): device-timed,
+                              end to end from host buffers, roofline on EXECUTED double-precision flops
+  roofline_hbm                the same table, one objective call (P = 1): HBM roofline; optBL! timings
+  sharded                     configs[4]: 200 taxa, 64,684,950 quartets split over the N GPUs, collective inside the
+                              library (fused peer-memory epilogue for P = 1, ncclAllReduce for P = 64): strong scaling
+  search_chains               configs[2]'s shape: 8 hill-climbing chains of 50 candidate topologies (NNI proposals,
+                              descriptor rebuild + optBL! at the search tolerances) on the 100-taxon table, chains dealt to GPUs
+  bootstrap                   configs[3]'s shape: 96 replicates (CI resampling + updateBL! table + optBL!) at 50 taxa, dealt to GPUs
+  dedup, candidates           opt-in program deduplication; concurrent candidate optimisation on one GPU
+  cpu_baseline                the oracle port on the host cores (rank 0, N = 1 only)
 """
 import argparse
 import json
@@ -28,12 +36,9 @@ import numpy as np  # noqa: E402
 
 NTAXA, NHYB, NVEC = 30, 2, 4096
 NET_SEED, OBS_SEED, X_SEED = 20261020, 1, 7
-# algorithmic work per evaluation: F = 110 + 75*f5 + 90*cbar flop
+# SURVEY.md 8d's convention, kept as a secondary figure only (it counts work the kernels do not execute, see roofline)
 FLOP_TREE, FLOP_T5_EXTRA, FLOP_PER_TERM = 110.0, 75.0, 90.0
-
-
-NCU_TRAFFIC_LANES_BYTES = 4477952          # profiles/r01h_ncu_summary.md: 4.477952 MB read, 0 written per launch
-NCU_TRAFFIC_DIRECT_BYTES = 113707776       # profiles/r01h_ncu_summary.md: 109.73 MB read + 3.97 MB written per launch
+EXECUTED = os.path.join(ROOT, "profiles", "r02_executed_flops.json")
 
 
 def workload(ntaxa=NTAXA, nhyb=NHYB, nvec=NVEC):
@@ -42,6 +47,22 @@ def workload(ntaxa=NTAXA, nhyb=NHYB, nvec=NVEC):
     taxa = [f"t{i + 1}" for i in range(ntaxa)]
     qt = S.simulate.all_quartets(ntaxa)
     return S, net, taxa, qt
+
+
+def executed(key):
+    """Per-launch counts of the timed kernel from the committed ncu capture of this very command (profiles/): thread-level
+    DFMA / DADD / DMUL instructions and DRAM bytes.  They are deterministic for a given table and batch."""
+    try:
+        return json.load(open(EXECUTED)).get(key)
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def hbm_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback of B200_PROFILING.md"
 
 
 class ClockSampler(threading.Thread):
@@ -128,6 +149,44 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def timed_launches(torch, eng, dX, dout, stream, flush, reps, warm=3):
+    """mean ms per eng.eval_device launch: CUDA events on the launching stream, L2 flushed before every timed launch"""
+    with torch.cuda.stream(stream):
+        for _ in range(warm):
+            eng.eval_device(dX, dout, stream)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    with torch.cuda.stream(stream):
+        for a, b in ev:
+            if flush is not None:
+                flush.fill_(1)
+            a.record(stream)
+            eng.eval_device(dX, dout, stream)
+            b.record(stream)
+    torch.cuda.synchronize()
+    return np.array([a.elapsed_time(b) for a, b in ev])
+
+
+def fp64_roofline(key, kernel_s, peak_tf, evals, convention_flop_per_eval):
+    """roofline.frac = EXECUTED double-precision flops / time / measured DFMA peak.  Executed flops per launch come from
+    the committed ncu capture (2 x DFMA + DADD + DMUL thread instructions of the dominant kernel); the SURVEY 8d
+    convention (one exp/log set per quartet and vector) is reported beside it but is NOT the fraction: the kernels
+    evaluate a program once per run of identical programs, so the convention counts work that is not executed."""
+    ex = executed(key)
+    out = {"bound": "fp64", "peak": peak_tf, "unit": "TFLOP/s",
+           "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+           "convention_flop_per_eval": convention_flop_per_eval,
+           "convention_tflops": evals * convention_flop_per_eval / kernel_s / 1e12}
+    if ex:
+        flops = 2.0 * ex["dfma"] + ex["dadd"] + ex["dmul"]
+        out.update({"achieved": flops / kernel_s / 1e12, "frac": flops / kernel_s / 1e12 / peak_tf, "traffic": ex.get("dram_bytes"),
+                    "executed_flop_per_launch": flops, "executed_flop_per_eval": flops / evals, "kernel": ex.get("kernel"),
+                    "fp64_pipe_active_pct_ncu": ex.get("fp64_pipe_pct"), "source": ex.get("source")})
+    else:
+        out.update({"achieved": None, "frac": None, "traffic": None, "note": "profiles/r02_executed_flops.json missing"})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -137,7 +196,9 @@ def main():
     ap.add_argument("--ref-vectors", type=int, default=128, help="parameter vectors per step of the CPU arms")
     ap.add_argument("--cpu-vectors", type=int, default=4096, help="parameter vectors of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-hbm", action="store_true", help="skip the secondary 100-taxon P=1 HBM-roofline measurement")
+    ap.add_argument("--no-hbm", action="store_true", help="skip the secondary single-GPU legs (north star, P=1, dedup, candidates)")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the 200-taxon quartet-sharded leg")
+    ap.add_argument("--no-search", action="store_true", help="skip the search-chain and bootstrap legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -218,7 +279,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed = float(t.item())
     value = world * evals_per_step * args.steps / elapsed
-    launches = (c1["eval_launches"] - c0["eval_launches"]) * 3      # k_expand_x + k_eval_lanes + k_reduce_partials_t per step
+    launches = (c1["eval_launches"] - c0["eval_launches"]) * 3      # x expansion + batched kernel + fixed-order reduction per step
 
     # ---- end to end through the public API: host X (pinned staging inside the C ABI) -> out on host
     pinX = torch.from_numpy(Xh).pin_memory()
@@ -237,23 +298,16 @@ def main():
     e2e_val = world * evals_per_step * args.steps / e2e_dt
     assert np.allclose(res, dout.cpu().numpy(), rtol=1e-12)
 
+    line = None
+    peak_tf = None
     if rank == 0:
-        # ---- roofline of the dominant kernel (k_eval_lanes): FP64 pipe
         desc = eng.descriptors()
         f5 = float(np.mean(desc["which"] == 2))
         cbar = float(np.mean(np.sum((desc["types"] >= 2) & (desc["types"] <= 4), axis=1)))
         flop_per_eval = FLOP_TREE + FLOP_T5_EXTRA * f5 + FLOP_PER_TERM * cbar
-        kernel_s = float(ms.mean()) * 1e-3           # per launch (eval kernel + its tiny reduction pass)
-        achieved_tf = evals_per_step * flop_per_eval / kernel_s / 1e12
+        kernel_s = float(ms.mean()) * 1e-3           # per launch (batched kernel + x expansion + its reduction pass)
         peak_tf = eng.measure_fp64_peak()
-        roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                    "traffic": NCU_TRAFFIC_LANES_BYTES, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_eval_lanes "
-                    "launch in the committed ncu --set full capture (profiles/*_ncu_summary.md); inputs are L2/shared-memory resident", "flop_per_eval": flop_per_eval, "f5": f5, "cbar": cbar,
-                    "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
-                    "note": "achieved = evaluations x SURVEY 8d's flop count per evaluation (one exp/log set per quartet and per "
-                            "hybridisation term). The kernel sorts quartets by program and reuses t1/exp/log and the terms while they "
-                            "repeat between neighbours, so it executes fewer flops than the convention counts and frac can exceed 1; "
-                            "every quartet still gets its own weighted contribution"}
+        roofline = fp64_roofline("config2", kernel_s, peak_tf, evals_per_step, flop_per_eval)
         line = {"metric": "quartet pseudolik evals/s (FP64)", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": float(ms.mean()), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -262,57 +316,34 @@ def main():
                            "nparams": npar, "l2": "flushed between timed iterations (inputs < L2)", "descriptor_build_s": t_build},
                 "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(P * npar * 8), "d2h_bytes_per_step": int(P * 8 + 4)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
-        # ---- the same launch with the reuse between neighbouring quartets switched off (SNAQ_REUSE=0): every quartet gets its
-        # own exp/log and its own terms, which is what SURVEY 8d's flop count describes
-        try:
-            os.environ["SNAQ_REUSE"] = "0"
-            eng0 = eng.__class__(local)
-            del os.environ["SNAQ_REUSE"]
-            eng0.set_data(S.DataCF(taxa, qt, obs))
-            eng0.set_network(flat)
-            out0 = torch.zeros(P, dtype=torch.float64, device=dev)
-            with torch.cuda.stream(stream):
-                for _ in range(3):
-                    eng0.eval_device(dX, out0, stream)
-            torch.cuda.synchronize()
-            ev0 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-            with torch.cuda.stream(stream):
-                for a, b in ev0:
-                    flush.fill_(1)
-                    a.record(stream)
-                    eng0.eval_device(dX, out0, stream)
-                    b.record(stream)
-            torch.cuda.synchronize()
-            ms0 = float(np.mean([a.elapsed_time(b) for a, b in ev0]))
-            tf0 = evals_per_step * flop_per_eval / (ms0 * 1e-3) / 1e12
-            line["roofline_no_reuse"] = {"bound": "fp64", "value": evals_per_step / (ms0 * 1e-3), "unit_value": "evals/s", "ms_per_step": ms0,
-                                         "achieved": tf0, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf0 / peak_tf,
-                                         "max_rel_diff_vs_default": float(((out0 - dout).abs() / dout.abs()).max().item()),
-                                         "note": "same kernel, same sorted table, reuse disabled: one full evaluation per (quartet, vector)"}
-            del eng0
-        except Exception as exc:  # noqa: BLE001
-            os.environ.pop("SNAQ_REUSE", None)
-            line["roofline_no_reuse"] = {"error": str(exc)[:200]}
-        # ---- opt-in program deduplication (SNAQ_OPT_DEDUP): the same batch on the table with one entry per DISTINCT program.
-        # Reported apart from `value`: it evaluates fewer programs, so it says nothing about the kernel's roofline.
-        try:
-            line["dedup"] = dedup_leg(S, eng.__class__, local, torch, taxa, qt, obs, flat, dX, dout, stream, flush, evals_per_step,
-                                      with_100_taxa=not args.no_hbm)
-        except Exception as exc:  # noqa: BLE001
-            line["dedup"] = {"error": str(exc)[:200]}
-        # ---- secondary: the 100-taxon table (3.92 M quartets): one objective call (P=1, HBM-bound) and a batch
-        if not args.no_hbm:
+    single = world == 1 and not args.no_hbm
+    if rank == 0 and single:
+        for name, fn in (("north_star", lambda: north_star_leg(S, eng.__class__, local, torch, peak_tf)),
+                         ("roofline_hbm", lambda: hbm_leg(S, eng.__class__, local, torch)),
+                         ("dedup", lambda: dedup_leg(S, eng.__class__, local, torch, taxa, qt, obs, flat, dX, dout, stream, flush, evals_per_step)),
+                         ("candidates", lambda: candidates_leg(S, eng, taxa, qt, obs))):
             try:
-                line["roofline_hbm"] = hbm_leg(S, eng.__class__, local, torch, peak_tf)
+                line[name] = fn()
             except Exception as exc:  # noqa: BLE001
-                line["roofline_hbm"] = {"error": str(exc)[:200]}
-        # ---- secondary: candidate topologies optimised concurrently on this GPU (snaq_optbl_topologies)
-        if not args.no_hbm:
+                line[name] = {"error": str(exc)[:300]}
+    del eng, dX, dout
+    torch.cuda.empty_cache()
+    # ---- legs that use all N GPUs (every rank takes part) ---------------------------------------------------------
+    multi = {}
+    if not args.no_search:
+        for name, fn in (("search_chains", search_chains_leg), ("bootstrap", bootstrap_leg)):
             try:
-                line["candidates"] = candidates_leg(S, eng, taxa, qt, obs)
+                multi[name] = fn(S, local, rank, world, dist, torch)
             except Exception as exc:  # noqa: BLE001
-                line["candidates"] = {"error": str(exc)[:200]}
-        if not args.no_cpu_baseline:
+                multi[name] = {"error": str(exc)[:300]}
+    if not args.no_sharded:
+        try:
+            multi["sharded"] = sharded_leg(S, local, rank, world, dist, torch, flush)
+        except Exception as exc:  # noqa: BLE001
+            multi["sharded"] = {"error": str(exc)[:300]}
+    if rank == 0:
+        line.update(multi)
+        if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             v, dt = cpu_port(S, net, taxa, qt, obs, Xh[: args.cpu_vectors], cores)
             line["cpu_baseline"] = {"value": v, "unit": "evals/s", "cores": cores, "kind": "port", "seconds": dt,
@@ -320,10 +351,57 @@ def main():
                                               f"(C++ restatement of the reference, OpenMP over quartets)"}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
-def dedup_leg(S, Engine, local, torch, taxa, qt, obs, flat, dX, dout, stream, flush, evals_per_step, with_100_taxa=True):
+def table100(S):
+    n = 100
+    net = S.simulate.random_level1_network(n, 3, 20261021)
+    taxa = [f"t{i + 1}" for i in range(n)]
+    qt = S.simulate.all_quartets(n)
+    return n, net, taxa, qt
+
+
+def north_star_leg(S, Engine, local, torch, peak_tf):
+    """BASELINE.json north_star: batched logPseudoLik at 100 taxa (3,921,225 quartets), 256 parameter vectors per launch."""
+    n, net, taxa, qt = table100(S)
+    eng = Engine(local)
+    eng.set_data(S.DataCF(taxa, qt, np.full((len(qt), 3), 1 / 3)))
+    flat = net.flatten(taxa)
+    eng.set_network(flat)
+    x0, _, upper = eng.get_params()
+    e0, _, _ = eng.eval_quartets(x0)
+    eng.set_obscf(S.simulate.obs_from_expcf(e0, 300, 5))
+    P = 256
+    X = S.simulate.parameter_batch(x0, upper, P, 11)
+    dev = torch.device("cuda", local)
+    dX = torch.from_numpy(X).to(dev)
+    dout = torch.zeros(P, dtype=torch.float64, device=dev)
+    stream = torch.cuda.Stream(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    ms = timed_launches(torch, eng, dX, dout, stream, flush, 20)
+    eng.check_status()
+    evals = len(qt) * P
+    desc = eng.descriptors()
+    f5 = float(np.mean(desc["which"] == 2))
+    cbar = float(np.mean(np.sum((desc["types"] >= 2) & (desc["types"] <= 4), axis=1)))
+    out = {"workload": f"100-taxon h=3, {len(qt)} quartets x {P} parameter vectors per launch, L2 flushed before every timed launch",
+           "ms_per_launch": float(ms.mean()), "value": evals / (float(ms.mean()) * 1e-3), "unit": "evals/s"}
+    out["roofline"] = fp64_roofline("north_star", float(ms.mean()) * 1e-3, peak_tf, evals, FLOP_TREE + FLOP_T5_EXTRA * f5 + FLOP_PER_TERM * cbar)
+    # end to end: host X (pageable, as a Julia caller's) -> out on the host, through snaq_eval
+    for _ in range(2):
+        r = eng.eval(X)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        r = eng.eval(X)
+    dt = (time.perf_counter() - t0) / 10
+    assert np.allclose(r, dout.cpu().numpy(), rtol=1e-12)
+    out["e2e"] = {"value": evals / dt, "unit": "evals/s", "ms_per_call": dt * 1e3, "h2d_bytes_per_step": int(X.nbytes), "d2h_bytes_per_step": int(P * 8 + 4)}
+    return out
+
+
+def dedup_leg(S, Engine, local, torch, taxa, qt, obs, flat, dX, dout, stream, flush, evals_per_step):
     """Same work as the main step, on an engine created with dedup=True (include/snaq_b200.h: SNAQ_OPT_DEDUP)."""
     eng = Engine(local, dedup=True)
     eng.set_data(S.DataCF(taxa, qt, obs))
@@ -332,58 +410,42 @@ def dedup_leg(S, Engine, local, torch, taxa, qt, obs, flat, dX, dout, stream, fl
                    "'effective' rates count every quartet of the table", "quartets": int(len(qt)),
            "distinct_programs": int(eng.counters()["distinct_programs"])}
     ref = dout.clone()
-    with torch.cuda.stream(stream):
-        for _ in range(3):
-            eng.eval_device(dX, dout, stream)
-    torch.cuda.synchronize()
+    ms = timed_launches(torch, eng, dX, dout, stream, flush, 20)
     out["max_rel_diff_vs_plain"] = float(((dout - ref).abs() / ref.abs()).max().item())
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
-    with torch.cuda.stream(stream):
-        for a, b in ev:
-            flush.fill_(1)
-            a.record(stream)
-            eng.eval_device(dX, dout, stream)
-            b.record(stream)
-    torch.cuda.synchronize()
-    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    out["config2_ms_per_step"] = ms
-    out["config2_effective_evals_per_s"] = evals_per_step / (ms * 1e-3)
-    if with_100_taxa:
-        n = 100
-        net = S.simulate.random_level1_network(n, 3, 20261021)
-        tx = [f"t{i + 1}" for i in range(n)]
-        q100 = S.simulate.all_quartets(n)
-        e2 = Engine(local, dedup=True)
-        e2.set_data(S.DataCF(tx, q100, np.full((len(q100), 3), 1 / 3)))
-        fl = net.flatten(tx)
+    out["config2_ms_per_step"] = float(ms.mean())
+    out["config2_effective_evals_per_s"] = evals_per_step / (float(ms.mean()) * 1e-3)
+    n, net, tx, q100 = table100(S)
+    e2 = Engine(local, dedup=True)
+    e2.set_data(S.DataCF(tx, q100, np.full((len(q100), 3), 1 / 3)))
+    fl = net.flatten(tx)
+    e2.set_network(fl)
+    t0 = time.perf_counter()
+    for _ in range(5):
         e2.set_network(fl)
+    out["t100_set_network_ms"] = (time.perf_counter() - t0) / 5 * 1e3
+    out["t100_quartets"] = int(len(q100))
+    out["t100_distinct_programs"] = int(e2.counters()["distinct_programs"])
+    x0, _, upper = e2.get_params()
+    exp0, _, _ = e2.eval_quartets(x0)
+    e2.set_obscf(S.simulate.obs_from_expcf(exp0, 300, 5))
+    rng = np.random.default_rng(0)
+    start = np.clip(x0 * rng.uniform(0.7, 1.3, len(x0)), 0, upper)
+    for _ in range(3):
+        e2.eval(start)
+        e2.eval_grad(start)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        e2.eval(start)
+    out["t100_objective_call_from_host_us"] = (time.perf_counter() - t0) / 50 * 1e6
+    t0 = time.perf_counter()
+    for _ in range(50):
+        e2.eval_grad(start)
+    out["t100_objective_plus_gradient_pass_us"] = (time.perf_counter() - t0) / 50 * 1e6
+    e2.optbl(start, 1e-6, 1e-6, 1e-2, 1e-3)                   # untimed warm-up
+    for name, tol in (("search_tolerances", (1e-6, 1e-6, 1e-2, 1e-3)), ("final_tolerances", (1e-12, 1e-10, 1e-10, 1e-10))):
         t0 = time.perf_counter()
-        for _ in range(5):
-            e2.set_network(fl)
-        out["t100_set_network_ms"] = (time.perf_counter() - t0) / 5 * 1e3
-        out["t100_quartets"] = int(len(q100))
-        out["t100_distinct_programs"] = int(e2.counters()["distinct_programs"])
-        x0, _, upper = e2.get_params()
-        exp0, _, _ = e2.eval_quartets(x0)
-        e2.set_obscf(S.simulate.obs_from_expcf(exp0, 300, 5))
-        rng = np.random.default_rng(0)
-        start = np.clip(x0 * rng.uniform(0.7, 1.3, len(x0)), 0, upper)
-        for _ in range(3):
-            e2.eval(start)
-            e2.eval_grad(start)
-        t0 = time.perf_counter()
-        for _ in range(50):
-            e2.eval(start)
-        out["t100_objective_call_from_host_us"] = (time.perf_counter() - t0) / 50 * 1e6
-        t0 = time.perf_counter()
-        for _ in range(50):
-            e2.eval_grad(start)
-        out["t100_objective_plus_gradient_pass_us"] = (time.perf_counter() - t0) / 50 * 1e6
-        e2.optbl(start, 1e-6, 1e-6, 1e-2, 1e-3)                   # untimed warm-up
-        for name, tol in (("search_tolerances", (1e-6, 1e-6, 1e-2, 1e-3)), ("final_tolerances", (1e-12, 1e-10, 1e-10, 1e-10))):
-            t0 = time.perf_counter()
-            _, r = e2.optbl(start, *tol)
-            out["t100_optbl_" + name] = {"seconds": time.perf_counter() - t0, "fmin": r["fmin"], "nlaunches": r["nlaunches"]}
+        _, r = e2.optbl(start, *tol)
+        out["t100_optbl_" + name] = {"seconds": time.perf_counter() - t0, "fmin": r["fmin"], "nlaunches": r["nlaunches"]}
     return out
 
 
@@ -414,15 +476,12 @@ def candidates_leg(S, eng, taxa, qt, obs, ncand=32):
     return out
 
 
-def hbm_leg(S, Engine, local, torch, peak_tf=None):
+def hbm_leg(S, Engine, local, torch):
     """P=1 on 100 taxa / h=3 / 3,921,225 quartets: one optBL! objective call.  Bytes per launch = what the
     layout makes k_eval_direct read once (engine counter: 16 B weights + 8 B per program chunk for additive
     quartets, 37 B + programs for the rest); peak = MEASURED_PEAKS.json hbm_gbs.  Timed cold (L2 flushed before
     every call: the table is smaller than L2) and warm (back-to-back calls, as inside one optBL!)."""
-    n = 100
-    net = S.simulate.random_level1_network(n, 3, 20261021)
-    taxa = [f"t{i + 1}" for i in range(n)]
-    qt = S.simulate.all_quartets(n)
+    n, net, taxa, qt = table100(S)
     eng = Engine(local)
     eng.set_data(S.DataCF(taxa, qt, np.full((len(qt), 3), 1 / 3)))
     t0 = time.perf_counter()
@@ -433,60 +492,13 @@ def hbm_leg(S, Engine, local, torch, peak_tf=None):
     dX = torch.from_numpy(x0.reshape(1, -1)).to(dev)
     dout = torch.zeros(1, dtype=torch.float64, device=dev)
     stream = torch.cuda.Stream(dev)
-    torch.cuda.synchronize()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    with torch.cuda.stream(stream):
-        for _ in range(5):
-            eng.eval_device(dX, dout, stream)
-    torch.cuda.synchronize()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
-    with torch.cuda.stream(stream):
-        for a, b in ev:
-            flush.fill_(1)                            # L2 flush: every timed call streams from HBM
-            a.record(stream)
-            eng.eval_device(dX, dout, stream)
-            b.record(stream)
-    torch.cuda.synchronize()
-    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    evw = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(50)]
-    with torch.cuda.stream(stream):
-        for a, b in evw:
-            a.record(stream)
-            eng.eval_device(dX, dout, stream)
-            b.record(stream)
-    torch.cuda.synchronize()
-    ms_warm = float(np.mean([a.elapsed_time(b) for a, b in evw]))
+    ms = float(timed_launches(torch, eng, dX, dout, stream, flush, 20, warm=5).mean())
+    ms_warm = float(timed_launches(torch, eng, dX, dout, stream, None, 50, warm=5).mean())
     bytes_alg = eng.counters()["single_call_bytes"]
-    peak = None
-    try:
-        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-        src = "MEASURED_PEAKS.json hbm_gbs"
-    except Exception:  # noqa: BLE001
-        peak, src = 6650.0, "fallback of B200_PROFILING.md"
+    peak, src = hbm_peak()
     ach = bytes_alg / (ms * 1e-3) / 1e9
-    # batched logPseudoLik on the same table: 256 parameter vectors per launch (lane-per-candidate kernel)
-    Pb = 256
-    Xb = torch.from_numpy(S.simulate.parameter_batch(x0, upper, Pb, 11)).to(dev)
-    outb = torch.zeros(Pb, dtype=torch.float64, device=dev)
-    for _ in range(2):
-        eng.eval_device(Xb, outb, stream)
-    torch.cuda.synchronize()
-    evb = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
-    for a, b in evb:
-        a.record(stream)
-        eng.eval_device(Xb, outb, stream)
-        b.record(stream)
-    torch.cuda.synchronize()
-    eng.check_status()
-    msb = float(np.mean([a.elapsed_time(b) for a, b in evb]))
-    desc = eng.descriptors()
-    f5 = float(np.mean(desc["which"] == 2))
-    cbar = float(np.mean(np.sum((desc["types"] >= 2) & (desc["types"] <= 4), axis=1)))
-    fpe = FLOP_TREE + FLOP_T5_EXTRA * f5 + FLOP_PER_TERM * cbar
-    batched = {"P": Pb, "ms_per_launch": msb, "evals_per_s": len(qt) * Pb / (msb * 1e-3), "flop_per_eval": fpe,
-               "achieved_tflops": len(qt) * Pb * fpe / (msb * 1e-3) / 1e12}
-    if peak_tf:
-        batched["frac_fp64"] = batched["achieved_tflops"] / peak_tf
+    ex = executed("hbm_p1") or {}
     # optBL! on the same table (src/snaq_optimization.jl:341-390): whole optimisations through snaq_optbl, from a
     # start 30 % off the simulating parameters, with the search-time and the final tolerances of the reference
     exp0, _, _ = eng.eval_quartets(x0)
@@ -506,11 +518,181 @@ def hbm_leg(S, Engine, local, torch, peak_tf=None):
         _, r = eng.optbl(start, *tol)
         r["seconds"] = time.perf_counter() - t0
         optbl[name] = r
-    return {"batched": batched, "optbl": optbl, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_DIRECT_BYTES, "peak_source": src,
+    return {"optbl": optbl, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": ex.get("dram_bytes"), "peak_source": src,
             "workload": f"100-taxon h=3, {len(qt)} quartets, P=1 (one objective call), L2 flushed before every timed call",
             "ms_per_call": ms, "ms_per_call_warm_l2": ms_warm, "evals_per_s_warm_l2": len(qt) / (ms_warm * 1e-3),
-            "achieved_at_survey_8d_56B_per_quartet": len(qt) * 56 / (ms * 1e-3) / 1e9,
             "evals_per_s": len(qt) / (ms * 1e-3), "bytes_per_quartet": bytes_alg / len(qt), "descriptor_build_s": t_build}
+
+
+def gather_max(dist, torch, world, v, dev):
+    if world == 1:
+        return v
+    t = torch.tensor([v], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sharded_leg(S, local, rank, world, dist, torch, flush):
+    """BASELINE.json configs[4]: 200 taxa, h=5, 64,684,950 quartets split over the N GPUs (contiguous blocks); every rank
+    evaluates the same parameter vectors and the library combines the per-candidate partial sums itself: a fused
+    peer-memory epilogue for the single objective call, ncclAllReduce for the batch of 64.  Strong scaling: the table is
+    fixed, N grows.  Timed on the device (CUDA events on the launching stream), max over ranks."""
+    n, h = 200, 5
+    net = S.simulate.random_level1_network(n, h, 20261022)
+    taxa = [f"t{i + 1}" for i in range(n)]
+    qt = S.simulate.all_quartets(n)
+    nq = len(qt)
+    rng = np.random.default_rng(3)
+    obs = rng.random((nq, 3)) + 0.05
+    obs /= obs.sum(axis=1, keepdims=True)
+    dev = torch.device("cuda", local)
+    eng = S.Engine(local, rank=rank, world_size=world)
+    eng.set_data(S.DataCF(taxa, qt, obs))
+    del obs
+    t0 = time.perf_counter()
+    eng.set_network(net.flatten(taxa))
+    t_build = time.perf_counter() - t0
+    if world > 1:
+        ids = [S.Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        eng.comm_init(ids[0])
+    x0, _, upper = eng.get_params()
+    X = S.simulate.parameter_batch(x0, upper, 64, 5)
+    out = {"workload": f"200-taxon h={h}, {nq} quartets in {world} contiguous shard(s), same parameter vectors on every rank",
+           "scaling": "strong", "comm": eng.comm_info(), "descriptor_build_s": t_build}
+    stream = torch.cuda.Stream(dev)
+    vals = {}
+    for P in (1, 64):
+        dX = torch.from_numpy(X[:P].copy()).to(dev)
+        dout = torch.zeros(P, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.barrier()
+        ms = float(timed_launches(torch, eng, dX, dout, stream, None, 20, warm=5).mean())
+        ms = gather_max(dist, torch, world, ms, dev)
+        vals[P] = dout.cpu().numpy().copy()
+        out[f"P{P}"] = {"ms_per_launch": ms, "evals_per_s": nq * P / (ms * 1e-3), "value0": float(vals[P][0])}
+        t0 = time.perf_counter()
+        for _ in range(10):
+            eng.eval(X[:P])
+        out[f"P{P}"]["host_call_ms"] = gather_max(dist, torch, world, (time.perf_counter() - t0) / 10 * 1e3, dev)
+    eng.check_status()
+    if world > 1:
+        mine = np.concatenate([vals[1], vals[64]]).tobytes()
+        allv = [None] * world
+        dist.all_gather_object(allv, mine)
+        out["identical_on_all_ranks"] = all(b == allv[0] for b in allv)
+    out["P1_equals_P64_row0_rel"] = float(abs(vals[1][0] - vals[64][0]) / abs(vals[64][0]))
+    return out
+
+
+def search_chains_leg(S, local, rank, world, dist, torch, nchains=8, K=50):
+    """The engine's side of `snaq! hmax=3 runs=8` on 100 taxa (BASELINE.json configs[2]) without the Julia control plane:
+    8 independent hill-climbing chains (one per run, dealt to the GPUs), each proposing K = 50 candidate topologies (a
+    nearest-neighbour interchange of the current network), and for every candidate what optTopLevel! does
+    (src/snaq_optimization.jl:1380-1412): descriptor table for the candidate + optBL! at the search tolerances, accept iff
+    the pseudo-deviance improves by more than liktolAbs = 1e-6, else undo.  Host-side Python (move + flattening of the
+    network) is the stand-in for the Julia search and is timed apart."""
+    n, net0, taxa, qt = table100(S)
+    eng = S.Engine(local)
+    eng.set_data(S.DataCF(taxa, qt, np.full((len(qt), 3), 1 / 3)))
+    eng.set_network(net0.flatten(taxa))
+    x_true, _, _ = eng.get_params()
+    e0, _, _ = eng.eval_quartets(x_true)
+    eng.set_obscf(S.simulate.obs_from_expcf(e0, 300, 5))
+    t_net = t_opt = t_host = 0.0
+    ncand = nacc = 0
+    launches = 0
+    results = []
+    if world > 1:
+        dist.barrier()
+    t_wall0 = time.perf_counter()
+    for chain in range(rank, nchains, world):
+        rng = np.random.default_rng(1000 + chain)
+        net = S.simulate.random_level1_network(n, 3, 20261021)          # the simulating topology ...
+        for _ in range(6):
+            S.simulate.nni_move(net, rng)                                # ... six interchanges away: the start of the run
+        eng.set_network(net.flatten(taxa))
+        x, _, _ = eng.get_params()
+        xcur, r = eng.optbl(x)
+        fcur = r["fmin"]
+        net.update_parameters(list(xcur))
+        for _ in range(K):
+            th = time.perf_counter()
+            tok = S.simulate.nni_move(net, rng)
+            flat = net.flatten(taxa)
+            t1 = time.perf_counter()
+            eng.set_network(flat)
+            x, _, _ = eng.get_params()
+            t2 = time.perf_counter()
+            xn, r = eng.optbl(x)
+            t3 = time.perf_counter()
+            ncand += 1
+            launches += r["nlaunches"]
+            if r["fmin"] < fcur - 1e-6:
+                fcur = r["fmin"]
+                net.update_parameters(list(xn))
+                nacc += 1
+            else:
+                S.simulate.nni_undo(net, tok)
+            t4 = time.perf_counter()
+            t_host += (t1 - th) + (t4 - t3)
+            t_net += t2 - t1
+            t_opt += t3 - t2
+        results.append(fcur)
+    wall = time.perf_counter() - t_wall0
+    dev = torch.device("cuda", local)
+    wall = gather_max(dist, torch, world, wall, dev)
+    mine = [ncand, nacc, t_net, t_opt, t_host, launches]
+    allv = [mine]
+    if world > 1:
+        allv = [None] * world
+        dist.all_gather_object(allv, mine)
+    tot = np.sum(np.array(allv, dtype=float), axis=0)
+    return {"workload": f"{nchains} chains x {K} NNI candidates on the 100-taxon h=3 table ({len(qt)} quartets), search tolerances, "
+                        f"chains dealt to {world} GPU(s)", "wall_s": wall, "candidates": int(tot[0]), "accepted": int(tot[1]),
+            "candidates_per_s": tot[0] / wall, "engine_ms_per_candidate": {"descriptor_table": tot[2] / tot[0] * 1e3, "optBL": tot[3] / tot[0] * 1e3},
+            "host_standin_ms_per_candidate": tot[4] / tot[0] * 1e3, "engine_launches_per_optBL": tot[5] / tot[0],
+            "final_deviance_rank0": results}
+
+
+def bootstrap_leg(S, local, rank, world, dist, torch, nrep=96):
+    """The engine's side of `bootsnaq` with 96 replicates on a 50-taxon table with credibility intervals (BASELINE.json
+    configs[3]), replicates dealt to the GPUs: per replicate sampleCFfromCI! + readtableCF! on the device
+    (snaq_resample_obscf), the updateBL! table of the start tree (snaq_update_bl), and optBL! of the start network at the
+    search and then the final tolerances."""
+    n, h = 50, 2
+    net = S.simulate.random_level1_network(n, h, 20261022)
+    tree = S.simulate.random_level1_network(n, 0, 20261022)
+    taxa = [f"t{i + 1}" for i in range(n)]
+    qt = S.simulate.all_quartets(n)
+    eng = S.Engine(local)
+    eng.set_data(S.DataCF(taxa, qt, np.full((len(qt), 3), 1 / 3)))
+    fnet, ftree = net.flatten(taxa), tree.flatten(taxa)
+    eng.set_network(fnet)
+    x0, _, upper = eng.get_params()
+    obs = S.simulate.obs_from_expcf(eng.eval_quartets(x0)[0], 300, 4)
+    eng.set_ci(np.clip(obs - 0.05, 0, 1), np.clip(obs + 0.05, 0, 1))           # SURVEY 8d: CI = obs -/+ 0.05 clipped
+    eng.resample_obscf(0)
+    eng.optbl(x0)                                                              # untimed warm-up
+    if world > 1:
+        dist.barrier()
+    fm = []
+    t0 = time.perf_counter()
+    for rep in range(rank, nrep, world):
+        eng.resample_obscf(5000 + rep)
+        eng.set_network(ftree)
+        eng.update_bl()
+        eng.set_network(fnet)
+        xm, r = eng.optbl(x0)
+        xm, r = eng.optbl(xm, 1e-12, 1e-10, 1e-10, 1e-10)
+        fm.append(r["fmin"])
+    wall = time.perf_counter() - t0
+    wall = gather_max(dist, torch, world, wall, torch.device("cuda", local))
+    return {"workload": f"{nrep} bootstrap replicates at 50 taxa ({len(qt)} quartets, h={h}): CI resampling + updateBL! table + optBL! "
+                        f"(search, then final tolerances), replicates dealt to {world} GPU(s)", "wall_s": wall,
+            "replicates_per_s": nrep / wall, "ms_per_replicate_per_gpu": wall / max(1, len(range(rank, nrep, world))) * 1e3,
+            "deviance_range_rank0": [float(min(fm)), float(max(fm))]}
 
 
 if __name__ == "__main__":

@@ -269,3 +269,46 @@ def parameter_batch(x0: np.ndarray, upper: np.ndarray, P: int, seed: int) -> np.
         T = np.exp(rng.uniform(np.log(1e-3), np.log(10.0), size=(m, n)))
         X[r:] = np.where(isT[None, :], T, U)
     return X
+
+
+def nni_candidates(net: HybridNetwork):
+    """internal tree edges on which :func:`nni_move` can act: both ends tree nodes outside every cycle"""
+    out = []
+    for e in net.edge:
+        if e.hybrid:
+            continue
+        u, v = e.node
+        if u.leaf or v.leaf or u.hybrid or v.hybrid or u.inCycle != -1 or v.inCycle != -1:
+            continue
+        out.append(e)
+    return out
+
+
+def nni_move(net: HybridNetwork, rng: np.random.Generator) -> Optional[Tuple]:
+    """A nearest-neighbour interchange around a random internal tree edge away from the cycles, in place (the tree part
+    of the reference's NNI move, src/moves_snaq.jl:1209-1330): one subtree hanging off each end of the edge is swapped.
+    Returns a token for :func:`nni_undo` (the search's `undoMove`), or None when the network has no such edge."""
+    cands = nni_candidates(net)
+    if not cands:
+        return None
+    e = cands[int(rng.integers(len(cands)))]
+    u, v = e.node
+    a = [x for x in u.edge if x is not e][int(rng.integers(2))]
+    c = [x for x in v.edge if x is not e][int(rng.integers(2))]
+    _swap_ends(a, u, c, v)
+    net.update_all()
+    return (a, u, c, v)
+
+
+def _swap_ends(a: Edge, u: Node, c: Edge, v: Node) -> None:
+    """edge a leaves node u for v, edge c leaves v for u (positions in node.edge and edge.node are kept)"""
+    a.node[a.node.index(u)] = v
+    c.node[c.node.index(v)] = u
+    iu, iv = u.edge.index(a), v.edge.index(c)
+    u.edge[iu], v.edge[iv] = c, a
+
+
+def nni_undo(net: HybridNetwork, token: Tuple) -> None:
+    a, u, c, v = token
+    _swap_ends(a, v, c, u)
+    net.update_all()
