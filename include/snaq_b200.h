@@ -161,12 +161,24 @@ int snaq_set_sampled(snaq_ctx *ctx, const uint8_t *mask);
 /* Full rebuild of the device descriptor table from a flat network.  Also does
  * parameters!(net): fixes the x layout.                                       */
 int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net);
-/* Incremental variant: only quartets whose taxa see one of the touched cycles /
- * edges are re-described.  touched_taxa is a bitmap-free list of taxon ids whose
- * pruned sub-network may have changed; quartets containing none of them keep
- * their descriptor.  Falls back to a full rebuild when n_touched<0.            */
+/* Incremental variant for the search loop, which edits ONE network in place and re-extracts every quartet at each optBL!
+ * (proposedTop!, src/snaq_optimization.jl:1154-1198; extractQuartet! at :354).  The new host tables are rooted where
+ * the current ones are; a quartet's program is a function of the root paths and cycle blocks of its four taxa, so the
+ * engine compares the two sets of tables itself and classifies again only the quartets that contain a taxon whose root
+ * path or block changed (after a nearest-neighbour interchange: the taxa of the two subtrees that changed places).
+ * Everything downstream of the classification (class sort, offsets, emission from the staged programs, run table,
+ * weights) is redone for the whole table, so the device table is BIT-IDENTICAL to what a build from scratch with the
+ * same root gives (tests/test_gpu_patch.py); only the expensive pass (two thirds of a rebuild) shrinks.
+ * touched_taxa / n_touched: taxon ids the caller knows to be affected (advisory: added to the engine's own list; may be
+ * NULL / 0).  n_touched < 0: re-describe everything (a rebuild that keeps the current root).  Also re-described in
+ * full: edits that change the parameter layout or a cycle (hybrid added or removed, bad-diamond status changed), or that
+ * touch more than half of the taxa.  snaq_patch_info: taxa re-described by the last call (-1: everything).          */
 int snaq_patch_network(snaq_ctx *ctx, const snaq_flatnet *net,
                        const int32_t *touched_taxa, int32_t n_touched);
+int snaq_patch_info(snaq_ctx *ctx, int64_t *touched_taxa);
+/* order-dependent checksums of the device table: [0] sort permutation, headers, offsets; [1] program words; [2] weights;
+ * [3] (runs << 32) | tiles of the run table.  Test aid: a patched table against a rebuilt one.                        */
+int snaq_table_checksum(snaq_ctx *ctx, uint64_t out[4]);
 
 /* topologyQpseudolik! (src/pseudolik.jl:1342-1378) for a list of candidate topologies on the resident data:
  * out[c] = pseudo-deviance of nets[c] at its own parameters (each is a descriptor rebuild + one objective call).

@@ -34,6 +34,7 @@
  */
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges around build / expand / eval / reduce (no-ops without a profiler)
 #include <nccl.h>            // types and prototypes only: the library is resolved at run time (snaq_comm_init), never linked
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -55,6 +56,7 @@
 #include "snaq_tables.h"
 
 #define SNAQ_S_RANGE 8u   /* a parameter outside its bounds reached the device */
+#define SNAQ_STAGE_WORDS 12   /* program words per quartet kept from the classification pass (3 chunks: all but the longest programs) */
 // Small batches from the host travel as a kernel ARGUMENT (no host->device copy call, no staging buffer), and the
 // results are written by the last block straight into page-locked host memory (no device->host copy call).
 #define XARG_MAX 448      /* doubles (3.5 KB of kernel parameter space) */
@@ -142,15 +144,24 @@ __device__ __forceinline__ uint32_t term_hash(unsigned a, unsigned b, unsigned c
 __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_t *__restrict__ taxa, int64_t nq, const int dedup,
                                                      uint32_t *__restrict__ len4, uint32_t *__restrict__ cls,
                                                      uint32_t *__restrict__ iota, unsigned long long *__restrict__ stats,
-                                                     uint32_t *__restrict__ status) {
+                                                     uint32_t *__restrict__ status, const uint8_t *__restrict__ dirty_taxon,
+                                                     uint16_t *__restrict__ stage, uint8_t *__restrict__ hdr0) {
     // stats: [0] total chunks, [1] max chunks, [2..6] quartets per sort class
     // sort classes: 0 = class A with a one-chunk program, 1 = class A with two chunks, 2 = longer class A,
     //               3 = class B, 4 = class C
+    // stage / hdr0 (original quartet order): the first SNAQ_STAGE_WORDS words of the program, NULL padded, and the header
+    // byte: k_build_emit copies short programs from there instead of deriving them a second time.
+    // dirty_taxon (snaq_patch_network): only quartets with a flagged taxon are re-described; the others keep the length,
+    // sort key, staged program and header of the previous topology (their root paths and blocks have not changed).
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned n = 0, c = 5;
     if (q < nq) {
         uint16_t tx[4];
         load_taxa(taxa, q, tx);
+        if (dirty_taxon && !(dirty_taxon[tx[0]] | dirty_taxon[tx[1]] | dirty_taxon[tx[2]] | dirty_taxon[tx[3]])) {
+            n = len4[q];
+            c = cls[q] >> 28;
+        } else {
         uint16_t head[24];                                     // the first words of the program: enough for the term key
         SnaqWriter w{head, 0, 24};
         uint8_t hdr = 0;
@@ -181,6 +192,19 @@ __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_
         len4[q] = n;
         cls[q] = (c << 28) | key;
         iota[q] = (uint32_t)q;
+        hdr0[q] = e ? 0 : hdr;
+        {
+            const unsigned nul = (unsigned)T.n_xe;
+            uint2 *st = reinterpret_cast<uint2 *>(stage + (size_t)q * SNAQ_STAGE_WORDS);
+#pragma unroll
+            for (int k = 0; k < SNAQ_STAGE_WORDS / 4; k++) {
+                unsigned v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = (4 * k + j < w.n && !e) ? (unsigned)head[4 * k + j] : nul;
+                st[k] = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
+            }
+        }
+        }
     }
     __shared__ unsigned long long ssum[4];
     __shared__ unsigned smax[4], scnt[5];
@@ -215,14 +239,26 @@ __global__ void __launch_bounds__(256) k_gather_len(const uint32_t *__restrict__
 __global__ void __launch_bounds__(128) k_build_emit(SnaqTables T, const uint16_t *__restrict__ taxa, int64_t nq,
                                                     const uint32_t *__restrict__ perm, const uint32_t *__restrict__ off,
                                                     uint16_t *__restrict__ prog, uint8_t *__restrict__ qhdr,
-                                                    uint32_t *__restrict__ status) {
+                                                    uint32_t *__restrict__ status, const uint32_t *__restrict__ len4,
+                                                    const uint16_t *__restrict__ stage, const uint8_t *__restrict__ hdr0) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
-    uint16_t tx[4];
-    load_taxa(taxa, perm[i], tx);
+    const uint32_t q = perm[i];
     const uint32_t o0 = off[i], o1 = off[i + 1];
     uint16_t *dst = prog + (size_t)o0 * 4;
     const int cap = (int)(o1 - o0) * 4;
+    const uint32_t n = len4[q];
+    if (n * 4u <= (uint32_t)SNAQ_STAGE_WORDS) {
+        // short program: the classification pass kept it (NULL padded); a pad chunk, if any, is all NULL
+        const uint2 *st = reinterpret_cast<const uint2 *>(stage + (size_t)q * SNAQ_STAGE_WORDS);
+        uint2 *d2 = reinterpret_cast<uint2 *>(dst);
+        const unsigned nul2 = (unsigned)T.n_xe * 0x10001u;
+        for (uint32_t k = 0; k < o1 - o0; k++) d2[k] = k < n ? st[k] : make_uint2(nul2, nul2);
+        qhdr[i] = hdr0[q];
+        return;
+    }
+    uint16_t tx[4];
+    load_taxa(taxa, q, tx);
     SnaqWriter w{dst, 0, cap};
     uint8_t hdr = 0;
     int e = snaq_build_quartet(T, tx, w, &hdr, nullptr);
@@ -2550,6 +2586,29 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, doubl
     if (s == 12345.6789) out[0] = s;   // never true in practice; keeps the chains alive
 }
 
+// order-dependent checksums of the device table (snaq_table_checksum): tests compare a patched table with a rebuilt one
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256) k_checksum(const uint32_t *__restrict__ perm, const uint8_t *__restrict__ qhdr,
+                                                  const uint32_t *__restrict__ off, const unsigned long long *__restrict__ prog8,
+                                                  const unsigned long long *__restrict__ W8, int64_t nq, int64_t nchunks,
+                                                  unsigned long long *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long a = 0, b = 0, c = 0;
+    if (i < nq) {
+        a = mix64((unsigned long long)i * 0x9E3779B97F4A7C15ull + (((unsigned long long)perm[i] << 32) | ((unsigned long long)qhdr[i] << 24)) + off[i]);
+        for (int k = 0; k < 4; k++) c += mix64((unsigned long long)(4 * i + k) * 0x9E3779B97F4A7C15ull ^ W8[4 * i + k]);
+    }
+    for (int64_t j = i; j < nchunks; j += (int64_t)gridDim.x * blockDim.x) b += mix64((unsigned long long)j * 0x9E3779B97F4A7C15ull ^ prog8[j]);
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); c += __shfl_down_sync(0xffffffffu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out, a); atomicAdd(out + 1, b); atomicAdd(out + 2, c); }
+}
+
 // --------------------------------------------------------------------------------------------
 // context
 // --------------------------------------------------------------------------------------------
@@ -2600,6 +2659,10 @@ struct snaq_ctx {
     uint32_t *d_perm = nullptr;           // [nq] sorted position -> original quartet
     uint8_t *d_qhdr = nullptr;            // [nq] header bytes, sorted order
     uint32_t *d_len4 = nullptr, *d_iota = nullptr;   // [nq] scratch of the build
+    uint16_t *d_stage = nullptr;          // [nq][SNAQ_STAGE_WORDS] first words of every program, original order (k_build_count -> k_build_emit)
+    uint8_t *d_hdr0 = nullptr;            // [nq] header bytes, original order
+    uint8_t *d_dirty = nullptr; size_t dirty_cap = 0;   // snaq_patch_network: one byte per taxon
+    int64_t patch_touched = -1;           // taxa re-described by the last snaq_patch_network (-1: everything)
     uint32_t *d_cls = nullptr, *d_cls_sorted = nullptr;   // sort keys (class, term hash)
     int64_t nA1 = 0, nA2 = 0, nA = 0, nB = 0, nC = 0;   // nA1: leading class-A quartets whose program is exactly one chunk (off[i] == i)
     // program deduplication (SNAQ_OPT_DEDUP): the compressed table the evaluation kernels read instead of the full one
@@ -2652,6 +2715,11 @@ struct snaq_ctx {
 };
 
 static thread_local std::string g_create_err;
+
+struct nvtx_range {           // NVTX ranges for Nsight Systems / Compute timelines
+    explicit nvtx_range(const char *name) { nvtxRangePushA(name); }
+    ~nvtx_range() { nvtxRangePop(); }
+};
 
 #define CK(call)                                                                                          \
     do {                                                                                                  \
@@ -3259,6 +3327,7 @@ int snaq_destroy(snaq_ctx *ctx) {
     cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_blob); cudaFree(ctx->d_xconst);
     cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_WA); cudaFree(ctx->d_wpart); cudaFree(ctx->d_negw3); cudaFree(ctx->d_status); cudaFree(ctx->d_total); cudaFree(ctx->d_ticket); cudaFree(ctx->d_trace);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_uidx); cudaFree(ctx->d_rstart); cudaFree(ctx->d_ulen); cudaFree(ctx->d_off_u); cudaFree(ctx->d_qhdr_u);
+    cudaFree(ctx->d_stage); cudaFree(ctx->d_hdr0); cudaFree(ctx->d_dirty);
     cudaFree(ctx->d_tdesc); cudaFree(ctx->d_rec_off); cudaFree(ctx->d_pack); cudaFree(ctx->d_partial2);
     cudaFree(ctx->d_prog_u); cudaFree(ctx->d_W_u); cudaFree(ctx->d_WA_u); cudaFree(ctx->d_wpart_u); cudaFree(ctx->d_negw3_u); cudaFree(ctx->d_pen_u);
     cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_XF); cudaFree(ctx->d_out); cudaFree(ctx->d_partial); cudaFree(ctx->d_gbins); cudaFree(ctx->d_gpart); cudaFree(ctx->d_rb_e); cudaFree(ctx->d_rb_l); cudaFree(ctx->d_rb_d); cudaFree(ctx->d_sq_w); cudaFree(ctx->d_sq_cum); cudaFree(ctx->d_sq_u); cudaFree(ctx->d_sq_idx); cudaFree(ctx->d_gout);
@@ -3387,6 +3456,10 @@ int snaq_set_data(snaq_ctx *ctx, int32_t ntaxa, int64_t nq, const uint16_t *taxa
     CK(cudaMalloc((void **)&ctx->d_qhdr, n));
     CK(cudaMalloc((void **)&ctx->d_len4, n * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&ctx->d_iota, n * sizeof(uint32_t)));
+    cudaFree(ctx->d_stage); cudaFree(ctx->d_hdr0);
+    ctx->d_stage = nullptr; ctx->d_hdr0 = nullptr;
+    CK(cudaMalloc((void **)&ctx->d_stage, n * SNAQ_STAGE_WORDS * sizeof(uint16_t)));
+    CK(cudaMalloc((void **)&ctx->d_hdr0, n));
     cudaFree(ctx->d_flags); cudaFree(ctx->d_uidx);
     ctx->d_flags = ctx->d_uidx = nullptr;
     CK(cudaMalloc((void **)&ctx->d_flags, n * sizeof(uint32_t)));      // run table (k_eval_runs) and program deduplication
@@ -3491,15 +3564,13 @@ int snaq_set_sampled(snaq_ctx *ctx, const uint8_t *mask) {
     return SNAQ_OK;
 }
 
-int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
-    if (!ctx) return SNAQ_EINVAL;
-    if (!ctx->d_taxa) { ctx->err = "snaq_set_data has not been called"; return SNAQ_ENODATA; }
-    CK(cudaSetDevice(ctx->device));
-    ctx->has_net = false;
-    int rc = snaq_build_tables(net, ctx->ntaxa, ctx->H, ctx->err);
-    if (rc) return rc;
+// Device side of snaq_set_network / snaq_patch_network: uploads the host tables ctx->H and (re)builds the class-sorted
+// program table, the run table and the weights.  d_dirty (device, one byte per taxon) or nullptr: with it, only the quartets
+// that contain a flagged taxon are classified again; everything downstream (sort, offsets, emission from the staged
+// programs, runs, weights) is redone for the whole table, so the result is bit-identical to a build from scratch.
+static int build_table(snaq_ctx *ctx, const uint8_t *d_dirty) {
     const SnaqHostTables &H = ctx->H;
-    rc = ensure(ctx, ctx->d_blob, ctx->blob_cap, H.blob.size());
+    int rc = ensure(ctx, ctx->d_blob, ctx->blob_cap, H.blob.size());
     if (rc) return rc;
     rc = ensure(ctx, ctx->d_xconst, ctx->xconst_cap, std::max<size_t>(H.xconst.size(), 1));
     if (rc) return rc;
@@ -3518,7 +3589,7 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
         CK(cudaMemsetAsync(ctx->d_status, 0, 4 * sizeof(uint32_t), ctx->stream));
         const int64_t nb = (nq + 127) / 128;
         k_build_count<<<(unsigned)nb, 128, 0, ctx->stream>>>(ctx->T, ctx->d_taxa, nq, ctx->dedup ? 1 : 0, ctx->d_len4, ctx->d_cls, ctx->d_iota,
-                                                            ctx->d_total, ctx->d_status);
+                                                            ctx->d_total, ctx->d_status, d_dirty, ctx->d_stage, ctx->d_hdr0);
         CK(cudaGetLastError());
         unsigned long long stt[7] = {0, 0, 0, 0, 0, 0, 0};
         uint32_t st[4];
@@ -3556,7 +3627,7 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
         rc = ensure(ctx, ctx->d_prog, ctx->prog_cap, (size_t)ctx->prog_words + 8);
         if (rc) return rc;
         k_build_emit<<<(unsigned)nb, 128, 0, ctx->stream>>>(ctx->T, ctx->d_taxa, nq, ctx->d_perm, ctx->d_off, ctx->d_prog, ctx->d_qhdr,
-                                                           ctx->d_status);
+                                                           ctx->d_status, ctx->d_len4, ctx->d_stage, ctx->d_hdr0);
         CK(cudaGetLastError());
         ctx->counters[5] += 5;
         ctx->nU = 0;
@@ -3581,12 +3652,78 @@ int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
     return SNAQ_OK;
 }
 
+int snaq_set_network(snaq_ctx *ctx, const snaq_flatnet *net) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (!ctx->d_taxa) { ctx->err = "snaq_set_data has not been called"; return SNAQ_ENODATA; }
+    CK(cudaSetDevice(ctx->device));
+    ctx->has_net = false;
+    int rc = snaq_build_tables(net, ctx->ntaxa, ctx->H, ctx->err);
+    if (rc) return rc;
+    nvtx_range r("snaq_set_network");
+    return build_table(ctx, nullptr);
+}
+
 int snaq_patch_network(snaq_ctx *ctx, const snaq_flatnet *net, const int32_t *touched_taxa, int32_t n_touched) {
-    // Round 1: the descriptor table is a CSR whose program lengths change with the topology, so a
-    // patch is a full rebuild (two thread-per-quartet kernels + one scan).  The argument list is the
-    // final one; see DESIGN.md "incremental patch".
-    (void)touched_taxa; (void)n_touched;
-    return snaq_set_network(ctx, net);
+    if (!ctx) return SNAQ_EINVAL;
+    if (!ctx->d_taxa) { ctx->err = "snaq_set_data has not been called"; return SNAQ_ENODATA; }
+    if (n_touched > 0 && !touched_taxa) { ctx->err = "bad arguments to snaq_patch_network"; return SNAQ_EINVAL; }
+    CK(cudaSetDevice(ctx->device));
+    const bool had = ctx->has_net;
+    ctx->has_net = false;
+    // the new tables are rooted where the current ones are, so that taxa away from the edit keep their root paths
+    SnaqHostTables Hn;
+    int rc = snaq_build_tables(net, ctx->ntaxa, Hn, ctx->err, had ? ctx->H.root : -1);
+    if (rc) return rc;
+    std::vector<uint8_t> touched;
+    bool partial = had && n_touched >= 0 && snaq_tables_touched(ctx->H, Hn, touched);
+    if (partial) {
+        for (int32_t k = 0; k < n_touched; k++) {                 // the caller's list is advisory: added to what the tables show
+            if (touched_taxa[k] < 0 || touched_taxa[k] >= ctx->ntaxa) { ctx->err = "touched taxon id out of range"; return SNAQ_EINVAL; }
+            touched[(size_t)touched_taxa[k]] = 1;
+        }
+        size_t nd = 0;
+        for (uint8_t t : touched) nd += t;
+        ctx->patch_touched = (int64_t)nd;
+        if (nd * 2 > touched.size()) partial = false;             // most quartets would be re-described anyway
+    }
+    if (!partial) ctx->patch_touched = -1;
+    ctx->H = std::move(Hn);
+    nvtx_range r("snaq_patch_network");
+    if (partial) {
+        rc = ensure(ctx, ctx->d_dirty, ctx->dirty_cap, touched.size());
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(ctx->d_dirty, touched.data(), touched.size(), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return build_table(ctx, partial ? ctx->d_dirty : nullptr);
+}
+
+int snaq_patch_info(snaq_ctx *ctx, int64_t *touched_taxa) {
+    if (!ctx || !touched_taxa) return SNAQ_EINVAL;
+    *touched_taxa = ctx->patch_touched;
+    return SNAQ_OK;
+}
+
+int snaq_table_checksum(snaq_ctx *ctx, uint64_t out[4]) {
+    if (!ctx || !out) return SNAQ_EINVAL;
+    if (!ctx->has_net) { ctx->err = "snaq_set_network has not been called"; return SNAQ_ENODATA; }
+    CK(cudaSetDevice(ctx->device));
+    out[0] = out[1] = out[2] = 0;
+    out[3] = ((uint64_t)ctx->nU << 32) | (uint64_t)ctx->rn_ntiles;
+    if (ctx->nq == 0) return SNAQ_OK;
+    unsigned long long *d = nullptr;
+    CK(cudaMalloc((void **)&d, 3 * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d, 0, 3 * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) {
+        k_checksum<<<(unsigned)((ctx->nq + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_perm, ctx->d_qhdr, ctx->d_off,
+            reinterpret_cast<const unsigned long long *>(ctx->d_prog), reinterpret_cast<const unsigned long long *>(ctx->d_W), ctx->nq,
+            (int64_t)(ctx->prog_words / 4), d);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return SNAQ_ECUDA; }
+    return SNAQ_OK;
 }
 
 int snaq_eval_topologies(snaq_ctx *ctx, int32_t C, const snaq_flatnet *nets, double *out) {

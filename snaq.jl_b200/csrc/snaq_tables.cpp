@@ -45,7 +45,7 @@ SnaqTables SnaqHostTables::view(const unsigned char *b) const {
     return T;
 }
 
-int snaq_build_tables(const snaq_flatnet *f, int ntaxa, SnaqHostTables &o, std::string &err) {
+int snaq_build_tables(const snaq_flatnet *f, int ntaxa, SnaqHostTables &o, std::string &err, int keep_root) {
     try {
         if (!f) fail(SNAQ_EINVAL, "null network");
         const int N = f->n_nodes, E = f->n_edges, H = f->n_hybrids;
@@ -232,6 +232,8 @@ int snaq_build_tables(const snaq_flatnet *f, int ntaxa, SnaqHostTables &o, std::
         int far2 = bfs(far1, par, pe, dep);
         int root = far2;
         for (int i = 0; i < dep[far2] / 2; i++) root = par[root];     // middle of a diameter: small depths
+        if (keep_root >= 0 && keep_root < nt) root = keep_root;
+        o.root = root;
         bfs(root, par, pe, dep);
         std::vector<uint16_t> t_parent(nt), t_depth(nt), t_pslot(nt);
         std::vector<int16_t> t_cycle(nt, -1);
@@ -375,4 +377,40 @@ int snaq_build_tables(const snaq_flatnet *f, int ntaxa, SnaqHostTables &o, std::
         err = e.what();
         return SNAQ_EINVAL;
     }
+}
+
+bool snaq_tables_touched(const SnaqHostTables &a, const SnaqHostTables &b, std::vector<uint8_t> &touched) {
+    if (a.ntaxa != b.ntaxa || a.n_tnodes != b.n_tnodes || a.n_cycles != b.n_cycles || a.nparams != b.nparams || a.n_xe != b.n_xe ||
+        a.n_int != b.n_int || a.n_full != b.n_full || a.root != b.root || a.blob.size() != b.blob.size())
+        return false;
+    const SnaqTables A = a.view(a.blob.data()), B = b.view(b.blob.data());
+    const int nt = a.n_tnodes, nc = a.n_cycles, n = a.ntaxa;
+    auto same = [&](const void *x, const void *y, size_t bytes) { return std::memcmp(x, y, bytes) == 0; };
+    size_t ncs = 0;
+    for (int c = 0; c < nc; c++) ncs = std::max<size_t>(ncs, (size_t)A.cyc_off[c] + A.cyc_k[c]);
+    // everything a program depends on that is not a property of one taxon's root path
+    if (!same(A.leaf_tnode, B.leaf_tnode, sizeof(uint16_t) * n) || !same(A.tcycle, B.tcycle, sizeof(int16_t) * nt) ||
+        !same(A.dslot, B.dslot, sizeof(uint16_t) * nt) || !same(A.torder, B.torder, sizeof(uint16_t) * nt) ||
+        !same(A.cyc_k, B.cyc_k, sizeof(uint16_t) * std::max(nc, 1)) || !same(A.cyc_off, B.cyc_off, sizeof(uint16_t) * std::max(nc, 1)) ||
+        !same(A.cyc_gslot, B.cyc_gslot, sizeof(uint16_t) * std::max(nc, 1)) || !same(A.cyc_flags, B.cyc_flags, std::max(nc, 1)) ||
+        !same(A.cyc_hyb, B.cyc_hyb, std::max(nc, 1)) || !same(A.crow, B.crow, sizeof(uint16_t) * std::max(nc, 1)))
+        return false;
+    for (int c = 0; c < nc; c++) {
+        const size_t o0 = A.cyc_off[c], k = A.cyc_k[c];
+        if (!same(A.cyc_slot + o0, B.cyc_slot + o0, sizeof(uint16_t) * k) || !same(A.cyc_order + o0, B.cyc_order + o0, sizeof(uint16_t) * k))
+            return false;
+    }
+    touched.assign((size_t)n, 0);
+    for (int t = 0; t < n; t++) {
+        int u = A.leaf_tnode[t];
+        if (u == 0xFFFF) continue;
+        bool ch = false;
+        for (int c = 0; c < nc && !ch; c++) ch = A.blk[(size_t)c * n + t] != B.blk[(size_t)c * n + t];
+        for (int v = u; !ch; v = A.parent[v]) {
+            if (A.parent[v] != B.parent[v] || A.depth[v] != B.depth[v] || A.pslot[v] != B.pslot[v]) ch = true;
+            if (A.parent[v] == v) break;
+        }
+        touched[(size_t)t] = ch ? 1 : 0;
+    }
+    return true;
 }

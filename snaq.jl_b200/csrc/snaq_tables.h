@@ -27,10 +27,18 @@ struct SnaqHostTables {
            off_cyc_k = 0, off_cyc_off = 0, off_cyc_slot = 0, off_cyc_gslot = 0, off_cyc_flags = 0, off_cyc_hyb = 0, off_torder = 0, off_cyc_order = 0, off_dslot = 0, off_dnode = 0, off_crow = 0, off_dpath_off = 0, off_dpath_slot = 0, off_blkmax = 0, off_hmax2 = 0, off_hmaxtax = 0;
     // extra tables used only by the hasEdge (parity descriptor) kernel
     std::vector<int32_t> edge_slot;                  // per net edge: xe slot or -1
+    int root = -1;                                   // blob-tree node the tree is rooted at
     SnaqTables view(const unsigned char *base) const;
 };
 
-// returns SNAQ_OK or an error code with `err` set
-int snaq_build_tables(const snaq_flatnet *f, int ntaxa, SnaqHostTables &out, std::string &err);
+// returns SNAQ_OK or an error code with `err` set.  keep_root >= 0: root the blob tree at that blob-tree node (if it
+// exists) instead of the middle of a diameter, so that two successive topologies share root paths (snaq_patch_network).
+int snaq_build_tables(const snaq_flatnet *f, int ntaxa, SnaqHostTables &out, std::string &err, int keep_root = -1);
+
+// Which quartets can keep their program when the tables change from `a` to `b`?  A program is a function of the root
+// paths of its four taxa (blob-tree nodes, depths, edge slots), of their block positions in every cycle, and of the
+// tables that are not per taxon.  Returns false when the latter differ (every quartet must be re-described); else
+// touched[t] = 1 for every taxon whose root path or block positions changed.
+bool snaq_tables_touched(const SnaqHostTables &a, const SnaqHostTables &b, std::vector<uint8_t> &touched);
 
 #endif

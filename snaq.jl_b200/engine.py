@@ -34,7 +34,7 @@ EXPORTS = ["snaq_create", "snaq_destroy", "snaq_last_error", "snaq_version", "sn
            "snaq_eval", "snaq_eval_device", "snaq_eval_quartets", "snaq_get_descriptors", "snaq_get_counters",
            "snaq_check_status", "snaq_measure_fp64_peak", "snaq_get_trace", "snaq_eval_grad", "snaq_optbl", "snaq_update_bl", "snaq_get_hasedge",
            "snaq_eval_topologies", "snaq_optbl_topologies", "snaq_sample_quartets", "snaq_set_ci", "snaq_resample_obscf", "snaq_get_obscf",
-           "snaq_comm_unique_id", "snaq_comm_init", "snaq_comm_info"]
+           "snaq_comm_unique_id", "snaq_comm_init", "snaq_comm_info", "snaq_patch_info", "snaq_table_checksum"]
 
 
 class _OptblOpts(C.Structure):
@@ -170,6 +170,22 @@ class Engine:
     def set_network(self, flat: FlatNet) -> None:
         self._chk(self.lib.snaq_set_network(self.ctx, flat.ptr()))
         self.set_network_meta()
+
+    def patch_network(self, flat: FlatNet, touched_taxa=None, force_all: bool = False) -> int:
+        """``extractQuartet!`` after an in-place edit of the network (snaq_patch_network): only quartets with a taxon whose
+        root path changed are classified again.  Returns the number of taxa re-described (-1: all)."""
+        tt = None if touched_taxa is None else np.ascontiguousarray(touched_taxa, dtype=np.int32)
+        n = -1 if force_all else (0 if tt is None else int(tt.size))
+        self._chk(self.lib.snaq_patch_network(self.ctx, flat.ptr(), _p(tt), C.c_int32(n)))
+        self.set_network_meta()
+        out = C.c_int64(0)
+        self._chk(self.lib.snaq_patch_info(self.ctx, C.byref(out)))
+        return out.value
+
+    def table_checksum(self):
+        out = (C.c_uint64 * 4)()
+        self._chk(self.lib.snaq_table_checksum(self.ctx, out))
+        return tuple(int(v) for v in out)
 
     def set_network_meta(self) -> None:
         n = C.c_int32(); nh = C.c_int32(); nt = C.c_int32(); nz = C.c_int32()
