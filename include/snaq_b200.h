@@ -240,9 +240,9 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f,
 #define SNAQ_OPTBL_MAXEVAL  5
 typedef struct snaq_optbl_opts {
     double ftol_rel, ftol_abs, xtol_rel, xtol_abs;   /* optBL!'s ftolRel, ftolAbs, xtolRel, xtolAbs (all > 0, :350) */
-    int32_t maxeval;     /* NLopt.maxeval! = 1000 in the reference (:365): objective values asked for (every rung of a
-                            ladder counts, a gradient pass counts once; a batch that starts below the bound is
-                            finished, so the count can exceed it by one ladder)                                     */
+    int32_t maxeval;     /* NLopt.maxeval! = 1000 in the reference (:365) bounds BOBYQA's sequential objective calls;
+                            here it bounds the engine LAUNCHES (a gradient pass or one ladder of vectors evaluated
+                            together is one sequential step); result.nevals counts the vectors evaluated          */
     int32_t ladder;      /* step lengths tried per line-search launch (default 20)                              */
     uint32_t flags;      /* SNAQ_OPTBL_*                                                                         */
     uint32_t reserved;
@@ -307,11 +307,13 @@ int snaq_get_descriptors(snaq_ctx *ctx, int8_t *which, int8_t *ntype,
                          uint8_t *hasedge);
 
 /* q.qnet.hasEdge and q.qnet.indexht (updateHasEdge!, src/pseudolik.jl:392-464; parameters!(qnet,net),
- * src/snaq_optimization.jl:106-180): hasedge[nq*nparams] 0/1 aligned with x; indexht[nq*nparams] the 1-based
- * positions of x the quartet uses, -1 padded, nindexht[nq] their number (either may be NULL).  Networks with at
- * most one hybrid node only (the reference defines hasEdge operationally and, with nested cycles, by the order in
- * which leaves are pruned): otherwise SNAQ_EINVAL.  These arrays only gate recomputation in the
- * reference (src/snaq_optimization.jl:185-206); they never change a value.                                      */
+ * src/snaq_optimization.jl:106-180) for any level-1 network: hasedge[nq*nparams] 0/1 aligned with x; indexht[nq*nparams]
+ * the 1-based positions of x the quartet uses in the reference's order, -1 padded, nindexht[nq] their number (either may
+ * be NULL).  The reference defines hasEdge operationally ("the edge number still exists in the pruned quartet network").
+ * With at most one hybrid node that is a structural property of the quartet; with nested cycles it depends on the order
+ * in which extractQuartet! deletes the other leaves (net.leaf order, which the flat network carries), and the engine
+ * simulates that pruning per quartet (integer state only, csrc/snaq_hesim.h).  Bit-exact against the oracle for h = 0..5.
+ * These arrays only gate recomputation in the reference (src/snaq_optimization.jl:185-206); they never change a value. */
 int snaq_get_hasedge(snaq_ctx *ctx, uint8_t *hasedge, int32_t *indexht, int32_t *nindexht);
 
 /* engine counters: [0] launches of the eval kernel, [1] quartet-evals done,

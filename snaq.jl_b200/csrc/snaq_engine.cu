@@ -471,6 +471,25 @@ __global__ void __launch_bounds__(128) k_hasedge(SnaqTables T, const uint16_t *_
     bd1[q] = (uint8_t)flag;
 }
 
+// the same for ANY level-1 network: every thread simulates extractQuartet! for its quartets on a private integer copy of the
+// network (snaq_hesim.h); zpos: position in net.edge of the edge behind every gammaz slot (orders indexht)
+__global__ void __launch_bounds__(64) k_hasedge_sim(SnaqSimNet net, const uint16_t *__restrict__ taxa, int64_t nq, uint8_t *__restrict__ hasedge,
+                                                    uint8_t *__restrict__ bd1, int16_t *__restrict__ zpos, int nz, uint32_t *__restrict__ status) {
+    SnaqSim g;
+    uint32_t bits[SNAQ_HE_WORDS(SNAQ_MAX_SLOT + 1)];
+    int16_t zp[64];
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+        uint16_t tx[4];
+        load_taxa(taxa, q, tx);
+        int flag = 0;
+        const int e = snaq_hasedge_sim(net, tx, g, bits, &flag, nz > 0 ? zp : nullptr);
+        if (e) atomicMax(status, (uint32_t)e);
+        for (int i = 0; i < net.nparams; i++) hasedge[q * net.nparams + i] = e ? 0 : (uint8_t)((bits[i >> 5] >> (i & 31)) & 1u);
+        for (int i = 0; i < nz; i++) zpos[q * nz + i] = e ? (int16_t)-1 : zp[i];
+        bd1[q] = (uint8_t)flag;
+    }
+}
+
 // --------------------------------------------------------------------------------------------
 // evaluation
 // --------------------------------------------------------------------------------------------
@@ -4227,43 +4246,66 @@ int snaq_get_hasedge(snaq_ctx *ctx, uint8_t *hasedge, int32_t *indexht, int32_t 
     if (!ctx->has_net) { ctx->err = "snaq_set_network has not been called"; return SNAQ_ENODATA; }
     if (!hasedge) { ctx->err = "bad arguments to snaq_get_hasedge"; return SNAQ_EINVAL; }
     const SnaqHostTables &H = ctx->H;
-    if (H.n_hybrids > 1) {
-        // with two or more hybrids what extractQuartet! leaves behind depends on the ORDER in which the other leaves are
-        // deleted across nested cycles; the structural rule is exact (checked against the oracle) for h <= 1
-        ctx->err = "hasEdge read-back is implemented for networks with at most one hybrid node";
-        return SNAQ_EINVAL;
-    }
     CK(cudaSetDevice(ctx->device));
     const int64_t nq = ctx->nq;
     const int np = H.nparams;
     if (nq == 0 || np == 0) { if (nindexht) for (int64_t q = 0; q < nq; q++) nindexht[q] = 0; return SNAQ_OK; }
-    uint8_t *d_he = nullptr, *d_bd1 = nullptr;
+    // One hybrid node at most: what extractQuartet! leaves behind is a structural property of the quartet (snaq_hasedge.h).
+    // Nested cycles: it depends on the order in which the other leaves are deleted, so the pruning is simulated
+    // (snaq_hesim.h).  SNAQ_HASEDGE_SIM=1 forces the simulation for every network (the tests compare the two).
+    const bool sim = H.n_hybrids > 1 || (getenv("SNAQ_HASEDGE_SIM") && atoi(getenv("SNAQ_HASEDGE_SIM")) != 0);
+    const int nz = sim ? H.nhz : 0;
+    if (sim && (H.sim.n_nodes > SNAQ_SIM_MAX || H.sim.n_edges > SNAQ_SIM_MAX || nz > 64)) {
+        ctx->err = "network too large for the hasEdge read-back (more than " + std::to_string(SNAQ_SIM_MAX) + " nodes or edges)";
+        return SNAQ_EINVAL;
+    }
+    uint8_t *d_he = nullptr, *d_bd1 = nullptr, *d_sim = nullptr;
+    int16_t *d_z = nullptr;
     CK(cudaMalloc((void **)&d_he, (size_t)nq * np));
-    CK(cudaMalloc((void **)&d_bd1, (size_t)nq));
-    CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream));
-    k_hasedge<<<(unsigned)((nq + 127) / 128), 128, 0, ctx->stream>>>(ctx->T, ctx->d_taxa, nq, d_he, d_bd1, ctx->d_status);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = cudaMalloc((void **)&d_bd1, (size_t)nq);
+    if (e == cudaSuccess && nz > 0) e = cudaMalloc((void **)&d_z, (size_t)nq * nz * sizeof(int16_t));
+    if (e == cudaSuccess && sim) e = cudaMalloc((void **)&d_sim, H.sim_blob.size());
+    if (e == cudaSuccess && sim) e = cudaMemcpyAsync(d_sim, H.sim_blob.data(), H.sim_blob.size(), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream);
+    if (e == cudaSuccess) {
+        if (sim) {
+            const int64_t blocks = std::min<int64_t>((nq + 63) / 64, (int64_t)ctx->sm_count * 16);
+            k_hasedge_sim<<<(unsigned)blocks, 64, 0, ctx->stream>>>(H.sim_view(d_sim), ctx->d_taxa, nq, d_he, d_bd1, d_z, nz, ctx->d_status);
+        } else {
+            k_hasedge<<<(unsigned)((nq + 127) / 128), 128, 0, ctx->stream>>>(ctx->T, ctx->d_taxa, nq, d_he, d_bd1, ctx->d_status);
+        }
+        e = cudaGetLastError();
+    }
     std::vector<uint8_t> hb((size_t)nq);
+    std::vector<int16_t> hz((size_t)nq * std::max(nz, 1), -1);
     uint32_t st = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(hasedge, d_he, (size_t)nq * np, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(hb.data(), d_bd1, (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && nz > 0) e = cudaMemcpyAsync(hz.data(), d_z, (size_t)nq * nz * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(&st, ctx->d_status, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_he); cudaFree(d_bd1);
+    cudaFree(d_he); cudaFree(d_bd1); cudaFree(d_z); cudaFree(d_sim);
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return SNAQ_ECUDA; }
     if (st) { ctx->err = build_err_text(st); return SNAQ_ETOPOLOGY; }
     ctx->counters[5]++;
-    ctx->counters[3] += (int64_t)nq * (np + 1);
+    ctx->counters[3] += (int64_t)nq * (np + 1 + 2 * nz);
     if (indexht || nindexht) {
-        // parameters!(qnet,net): positions of x the quartet uses, 1-based, in x order; a quartet that keeps a bad
-        // diamond I hybrid lists only its two gammaz (src/snaq_optimization.jl:120-146)
+        // parameters!(qnet,net) (src/snaq_optimization.jl:106-180): positions of x the quartet uses, 1-based: gammas, then
+        // edge lengths (both in x order = qnet.edge order), then the gammaz slots in qnet.edge order of the edges that
+        // carry them; a quartet that keeps a bad diamond I hybrid lists only its two gammaz (:120-146)
+        const int nht = H.nh + H.nt;
         for (int64_t q = 0; q < nq; q++) {
             int n = 0;
-            for (int i = 0; i < np; i++) {
-                const bool on = hasedge[(size_t)q * np + i] != 0 && (!hb[q] || i >= H.nh + H.nt);
-                if (on) { if (indexht) indexht[(size_t)q * np + n] = i + 1; n++; }
+            const uint8_t *he = hasedge + (size_t)q * np;
+            int32_t *ix = indexht ? indexht + (size_t)q * np : nullptr;
+            if (!hb[q]) for (int i = 0; i < nht; i++) if (he[i]) { if (ix) ix[n] = i + 1; n++; }
+            const int n0 = n;
+            for (int i = nht; i < np; i++) if (he[i]) { if (ix) ix[n] = i + 1; n++; }
+            if (ix && nz > 0 && !hb[q] && n - n0 > 1) {
+                const int16_t *zp = hz.data() + (size_t)q * nz;
+                std::stable_sort(ix + n0, ix + n, [&](int32_t a, int32_t b) { return zp[a - 1 - nht] < zp[b - 1 - nht]; });
             }
-            if (indexht) for (int i = n; i < np; i++) indexht[(size_t)q * np + i] = -1;
+            if (ix) for (int i = n; i < np; i++) ix[i] = -1;
             if (nindexht) nindexht[q] = n;
         }
     }

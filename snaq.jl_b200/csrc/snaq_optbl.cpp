@@ -166,9 +166,10 @@ extern "C" int snaq_optbl(snaq_ctx *ctx, const snaq_optbl_opts *o, double *x_io,
     const bool no_unit_step = getenv("SNAQ_OPTBL_NO_UNIT_STEP") != nullptr;
     const int hd_every = getenv("SNAQ_OPTBL_HD_EVERY") ? std::max(1, atoi(getenv("SNAQ_OPTBL_HD_EVERY"))) : 8;
     const bool verbose = getenv("SNAQ_OPTBL_VERBOSE") != nullptr;      // "inside obj with x ..." of the reference (:369-378)
-    // maxeval bounds the number of objective values asked for, as NLopt.maxeval! does (:365): every rung of a ladder counts,
-    // a gradient pass counts once; a launch that starts below the bound is finished
-    while (pb.budget < maxeval) {
+    // maxeval bounds the number of engine launches: NLopt.maxeval! (:365) bounds BOBYQA's SEQUENTIAL objective calls, and a
+    // launch (one gradient pass, or one ladder of up to `ladder` vectors evaluated together) is this optimiser's
+    // sequential step; res->nevals reports the parameter vectors evaluated
+    while (pb.nlaunches < maxeval) {
         iter++;
         // free variables: not pinned at a bound by the gradient
         std::vector<char> freev(n, 1);

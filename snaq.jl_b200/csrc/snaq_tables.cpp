@@ -45,6 +45,21 @@ SnaqTables SnaqHostTables::view(const unsigned char *b) const {
     return T;
 }
 
+SnaqSimNet SnaqHostTables::sim_view(const unsigned char *b) const {
+    SnaqSimNet v = sim;
+    v.node_edge = (const int16_t *)(b + so_node_edge);
+    v.node_flags = (const uint8_t *)(b + so_node_flags);
+    v.node_incycle = (const int16_t *)(b + so_node_incycle);
+    v.node_taxon = (const int16_t *)(b + so_node_taxon);
+    v.edge_node = (const int16_t *)(b + so_edge_node);
+    v.edge_flags = (const uint8_t *)(b + so_edge_flags);
+    v.leaf_order = (const int16_t *)(b + so_leaf_order);
+    v.hyb_order = (const int16_t *)(b + so_hyb_order);
+    v.slot_ref = (const int16_t *)(b + so_slot_ref);
+    v.slot_alias = (const int16_t *)(b + so_slot_alias);
+    return v;
+}
+
 int snaq_build_tables(const snaq_flatnet *f, int ntaxa, SnaqHostTables &o, std::string &err, int keep_root) {
     try {
         if (!f) fail(SNAQ_EINVAL, "null network");
@@ -369,6 +384,74 @@ int snaq_build_tables(const snaq_flatnet *f, int ntaxa, SnaqHostTables &o, std::
         o.off_blkmax = put(o.blob, blkmax);
         o.off_hmax2 = put(o.blob, hmax2);
         o.off_hmaxtax = put(o.blob, hmaxtax);
+
+        // ---- the network for the hasEdge simulation (snaq_hesim.h): adjacency and flags in net.node / net.edge positions --
+        {
+            std::vector<int> nodeOfNumber;                      // hybrid node number -> node index (inCycle carries numbers)
+            std::vector<int16_t> s_node_edge((size_t)N * 3, -1), s_incyc(N, -1), s_taxon(N, -1), s_edge_node((size_t)E * 2, -1);
+            std::vector<uint8_t> s_nfl(N, 0), s_efl(E, 0);
+            for (int n = 0; n < N; n++) {
+                for (int j = 0; j < 3; j++) s_node_edge[(size_t)3 * n + j] = (int16_t)f->node_edge[3 * n + j];
+                const uint32_t fl = f->node_flags[n];
+                s_nfl[n] = (uint8_t)(((fl & SNAQ_NODE_LEAF) ? SIM_N_LEAF : 0u) | ((fl & SNAQ_NODE_HYBRID) ? SIM_N_HYB : 0u) |
+                                     ((fl & SNAQ_NODE_HASHYBEDGE) ? SIM_N_HASHYB : 0u) | ((fl & SNAQ_NODE_BADDIAMOND1) ? SIM_N_BD1 : 0u) |
+                                     ((fl & SNAQ_NODE_BADDIAMOND2) ? SIM_N_BD2 : 0u) | ((fl & SNAQ_NODE_BADTRIANGLE) ? SIM_N_BADTRI : 0u));
+                s_taxon[n] = (int16_t)(isLeaf(n) ? f->node_taxon[n] : -1);
+                if (f->node_incycle[n] != -1)
+                    for (int h = 0; h < H; h++) if (f->node_number[f->hybrid[h]] == f->node_incycle[n]) s_incyc[n] = (int16_t)f->hybrid[h];
+            }
+            for (int e = 0; e < E; e++) {
+                s_edge_node[(size_t)2 * e] = (int16_t)f->edge_node[2 * e];
+                s_edge_node[(size_t)2 * e + 1] = (int16_t)f->edge_node[2 * e + 1];
+                const uint32_t fl = f->edge_flags[e];
+                s_efl[e] = (uint8_t)(((fl & SNAQ_EDGE_HYBRID) ? SIM_E_HYB : 0u) | ((fl & SNAQ_EDGE_MAJOR) ? SIM_E_MAJOR : 0u) |
+                                     ((fl & SNAQ_EDGE_IDENTIFIABLE) ? SIM_E_IDENT : 0u) | ((fl & SNAQ_EDGE_FROMBD1) ? SIM_E_FROMBD1 : 0u) |
+                                     (f->edge_incycle[e] != -1 ? SIM_E_INCYC : 0u));
+            }
+            std::vector<int16_t> s_leaf(std::max(f->n_leaves, 1), 0), s_hyb(std::max(H, 1), 0);
+            for (int i = 0; i < f->n_leaves; i++) s_leaf[i] = (int16_t)f->leaf[i];
+            for (int h = 0; h < H; h++) s_hyb[h] = (int16_t)f->hybrid[h];
+            // parameter slots in x order: gamma | t | gammaz (parameters!, src/snaq_optimization.jl:64-91)
+            std::vector<int16_t> s_ref(std::max(o.nparams, 1), -1), s_alias(std::max(o.nparams, 1), -1);
+            auto pseudo = [&](int node, int ind) { return std::stoi(std::to_string(f->node_number[node]) + std::to_string(ind)); };
+            int ig = 0, it = 0, iz = 0;
+            for (int e = 0; e < E; e++) {
+                if (eIdent(e)) {
+                    const int s = o.nh + it++;
+                    s_ref[s] = (int16_t)e;
+                    for (int h = 0; h < H; h++) {
+                        const int hn = f->hybrid[h];
+                        if (!(f->node_flags[hn] & SNAQ_NODE_BADDIAMOND1)) continue;
+                        for (int ind = 1; ind <= 2; ind++) if (pseudo(hn, ind) == f->edge_number[e]) s_alias[s] = (int16_t)(2 * hn + ind - 1);
+                    }
+                }
+                if (eHyb(e) && !eMaj(e)) {
+                    const int node = hybChild(e);
+                    if (!(f->node_flags[node] & SNAQ_NODE_BADDIAMOND1)) s_ref[ig++] = (int16_t)node;
+                    else {
+                        for (int ind = 1; ind <= 2; ind++) {
+                            const int s = o.nh + o.nt + iz++;
+                            s_ref[s] = (int16_t)node;
+                            for (int e2 = 0; e2 < E; e2++) if (f->edge_number[e2] == pseudo(node, ind) && s_alias[s] < 0) s_alias[s] = (int16_t)e2;
+                        }
+                    }
+                }
+            }
+            o.sim = SnaqSimNet{};
+            o.sim.n_nodes = N; o.sim.n_edges = E; o.sim.n_leaves = f->n_leaves; o.sim.n_hybrids = H;
+            o.sim.nparams = o.nparams; o.sim.nh = o.nh; o.sim.nt = o.nt;
+            o.sim_blob.clear();
+            o.so_node_edge = put(o.sim_blob, s_node_edge);
+            o.so_node_flags = put(o.sim_blob, s_nfl);
+            o.so_node_incycle = put(o.sim_blob, s_incyc);
+            o.so_node_taxon = put(o.sim_blob, s_taxon);
+            o.so_edge_node = put(o.sim_blob, s_edge_node);
+            o.so_edge_flags = put(o.sim_blob, s_efl);
+            o.so_leaf_order = put(o.sim_blob, s_leaf);
+            o.so_hyb_order = put(o.sim_blob, s_hyb);
+            o.so_slot_ref = put(o.sim_blob, s_ref);
+            o.so_slot_alias = put(o.sim_blob, s_alias);
+        }
         return SNAQ_OK;
     } catch (const Fail &e) {
         err = e.msg;

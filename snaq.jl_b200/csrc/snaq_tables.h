@@ -14,6 +14,7 @@
 
 #include "../../include/snaq_b200.h"
 #include "snaq_core.h"
+#include "snaq_hesim.h"
 
 struct SnaqHostTables {
     int ntaxa = 0, n_tnodes = 0, n_cycles = 0, nparams = 0, n_xe = 0, n_hybrids = 0;
@@ -29,6 +30,12 @@ struct SnaqHostTables {
     std::vector<int32_t> edge_slot;                  // per net edge: xe slot or -1
     int root = -1;                                   // blob-tree node the tree is rooted at
     SnaqTables view(const unsigned char *base) const;
+    // the network as the hasEdge simulation starts from it (snaq_hesim.h): its own blob, uploaded on demand
+    std::vector<unsigned char> sim_blob;
+    SnaqSimNet sim{};                                // counts filled in; pointers are set by sim_view()
+    size_t so_node_edge = 0, so_node_flags = 0, so_node_incycle = 0, so_node_taxon = 0, so_edge_node = 0, so_edge_flags = 0,
+           so_leaf_order = 0, so_hyb_order = 0, so_slot_ref = 0, so_slot_alias = 0;
+    SnaqSimNet sim_view(const unsigned char *base) const;
 };
 
 // returns SNAQ_OK or an error code with `err` set.  keep_root >= 0: root the blob tree at that blob-tree node (if it

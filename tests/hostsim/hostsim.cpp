@@ -44,6 +44,33 @@ int hostsim_params(const snaq_flatnet *f, int ntaxa, int32_t *nparams, int32_t *
     return 0;
 }
 
+int hostsim_counts(const snaq_flatnet *f, int ntaxa, int32_t *nh, int32_t *nt, int32_t *nhz) {
+    SnaqHostTables H;
+    int rc = snaq_build_tables(f, ntaxa, H, g_err);
+    if (rc) return rc;
+    *nh = H.nh; *nt = H.nt; *nhz = H.nhz;
+    return 0;
+}
+
+/* the same through the simulation of extractQuartet! (snaq_hesim.h): any level-1 network */
+int hostsim_hasedge_sim(const snaq_flatnet *f, int ntaxa, int64_t nq, const uint16_t *taxa, uint8_t *hasedge, uint8_t *bd1, int16_t *zpos) {
+    SnaqHostTables H;
+    int rc = snaq_build_tables(f, ntaxa, H, g_err);
+    if (rc) return rc;
+    const SnaqSimNet net = H.sim_view(H.sim_blob.data());
+    std::vector<uint32_t> bits((H.nparams + 31) / 32 + 1);
+    std::vector<SnaqSim> scratch(1);
+    for (int64_t q = 0; q < nq; q++) {
+        int flag = 0;
+        const int nz = H.nparams - H.nh - H.nt;
+        int e = snaq_hasedge_sim(net, taxa + 4 * q, scratch[0], bits.data(), &flag, (zpos && nz > 0) ? zpos + q * nz : nullptr);
+        if (e) { g_err = "hasedge simulation error " + std::to_string(e) + " (line " + std::to_string(scratch[0].err) + ") at quartet " + std::to_string(q); return SNAQ_ETOPOLOGY; }
+        for (int i = 0; i < H.nparams; i++) hasedge[q * H.nparams + i] = (bits[i >> 5] >> (i & 31)) & 1u;
+        if (bd1) bd1[q] = (uint8_t)flag;
+    }
+    return 0;
+}
+
 /* hasEdge bits (one byte per parameter) and the "bad diamond I kept whole" flag of every quartet */
 int hostsim_hasedge(const snaq_flatnet *f, int ntaxa, int64_t nq, const uint16_t *taxa, uint8_t *hasedge, uint8_t *bd1) {
     SnaqHostTables H;

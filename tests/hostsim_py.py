@@ -68,6 +68,33 @@ def hasedge(flat, ntaxa, qt):
     return he[:, :npar], bd1
 
 
+def hasedge_sim(flat, ntaxa, qt):
+    """hasEdge / bad-diamond-I flag through the simulation of extractQuartet! (snaq_hesim.h): any level-1 network"""
+    qt = np.ascontiguousarray(qt, dtype=np.uint16).reshape(-1, 4)
+    nq = qt.shape[0]
+    npar = len(params(flat, ntaxa)[0])
+    he = np.zeros((nq, max(npar, 1)), np.uint8)
+    bd1 = np.zeros(nq, np.uint8)
+    cnh = C.c_int32(); cnt = C.c_int32(); cnz = C.c_int32()
+    if lib().hostsim_counts(flat.ptr(), ntaxa, C.byref(cnh), C.byref(cnt), C.byref(cnz)):
+        raise RuntimeError(lib().hostsim_last_error().decode())
+    nh, nt, nz = cnh.value, cnt.value, cnz.value
+    zp = np.full((nq, max(nz, 1)), -1, np.int16)
+    rc = lib().hostsim_hasedge_sim(flat.ptr(), ntaxa, C.c_int64(nq), _p(qt), _p(he), _p(bd1), _p(zp))
+    if rc:
+        raise RuntimeError(lib().hostsim_last_error().decode())
+    return he[:, :npar], bd1, zp[:, :nz], (nh, nt)
+
+
+def indexht_from(he, bd1, zpos, nh, nt):
+    """parameters!(qnet,net): gamma slots, t slots (slot order = qnet.edge order), then the gammaz slots in qnet.edge order"""
+    if bd1:
+        return [i + 1 for i in range(nh + nt, len(he)) if he[i]]
+    out = [i + 1 for i in range(nh + nt) if he[i]]
+    z = [(int(zpos[i - nh - nt]), i + 1) for i in range(nh + nt, len(he)) if he[i]]
+    return out + [s for _, s in sorted(z)]
+
+
 def grad(flat, ntaxa, qt, obs, x, sampled=None):
     """objective and analytic gradient at x (the device functions behind snaq_eval_grad, compiled for the CPU)"""
     qt = np.ascontiguousarray(qt, dtype=np.uint16).reshape(-1, 4)
