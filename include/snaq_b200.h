@@ -316,6 +316,13 @@ int snaq_get_descriptors(snaq_ctx *ctx, int8_t *which, int8_t *ntype,
  * These arrays only gate recomputation in the reference (src/snaq_optimization.jl:185-206); they never change a value. */
 int snaq_get_hasedge(snaq_ctx *ctx, uint8_t *hasedge, int32_t *indexht, int32_t *nindexht);
 
+/* Step 2 of sampleEdgeQuartetWeighted (src/moves_snaq.jl:1451-1463) reads `q.qnet.edge` of the ONE quartet it has drawn:
+ * the engine keeps no per-quartet network objects, so this returns the edge numbers of that pruned quartet network, in
+ * qnet.edge order (an edge renamed by the bad-diamond-I rewrite carries "<hybrid node number><1|2>", as in the
+ * reference).  q: index in the data's quartet order (snaq_sample_quartets returns such indices).  *n = their number; at
+ * most cap are written.                                                                                              */
+int snaq_get_quartet_edges(snaq_ctx *ctx, int64_t q, int32_t *edge_numbers, int32_t cap, int32_t *n);
+
 /* engine counters: [0] launches of the eval kernel, [1] quartet-evals done,
  * [2] H2D bytes, [3] D2H bytes, [4] descriptor words in HBM, [5] launches of
  * the descriptor-build kernels, [6] bytes one single-call evaluation (P <= 4)

@@ -76,6 +76,15 @@ def extract(flat, quartet_taxa, x=None, max_types=8):
     return out
 
 
+def quartet_edges(flat, taxa4):
+    """edge numbers of q.qnet.edge after extractQuartet!(net, quartet), in order"""
+    t = np.ascontiguousarray(taxa4, dtype=np.uint16)
+    out = np.zeros(4096, np.int32)
+    n = C.c_int32()
+    _chk(lib().oracle_quartet_edges(flat.ptr(), _p(t), _p(out), C.c_int32(out.size), C.byref(n)))
+    return [int(v) for v in out[: n.value]]
+
+
 def evaluate(flat, quartet_taxa, obscf, X, sampled=None, threads=0, want_expcf=False):
     """logPseudoLik for each row of X (optBL! objective, stateless)."""
     qt = np.ascontiguousarray(quartet_taxa, dtype=np.uint16).reshape(-1, 4)

@@ -1276,6 +1276,20 @@ int oracle_extract(const snaq_flatnet *f, int64_t nq, const uint16_t *taxa, cons
     return SNAQ_OK;
 }
 
+/* edge numbers of q.qnet.edge after extractQuartet!(net, quartet), in order: what sampleEdgeQuartetWeighted
+ * (src/moves_snaq.jl:1451-1453) intersects with its candidate edges.  *n = count (at most cap written). */
+int oracle_quartet_edges(const snaq_flatnet *f, const uint16_t *taxa, int32_t *numbers, int32_t cap, int32_t *n) {
+    return run([&] {
+        Net g; fromFlat(f, g);
+        Params p = parameters(g);
+        int tx[4] = {taxa[0], taxa[1], taxa[2], taxa[3]};
+        Net q; extractQuartet(g, p, tx, q);
+        int k = 0;
+        for (int ei : q.edge) { if (k < cap) numbers[k] = q.E[ei].number; k++; }
+        *n = k;
+    });
+}
+
 /*
  * out[p] = logPseudoLik(d) (src/pseudolik.jl:1417-1425) after a stateless
  * calculateExpCFAll!(d, X[p,:], net): serial sum in quartet order, unsampled

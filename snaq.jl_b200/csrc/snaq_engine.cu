@@ -490,6 +490,15 @@ __global__ void __launch_bounds__(64) k_hasedge_sim(SnaqSimNet net, const uint16
     }
 }
 
+// q.qnet.edge of ONE quartet (edge numbers, in order): one thread runs the pruning
+__global__ void k_quartet_edges(SnaqSimNet net, const uint16_t *__restrict__ taxa, int64_t q, int32_t *__restrict__ out, int cap,
+                                int32_t *__restrict__ n) {
+    SnaqSim g;
+    uint16_t tx[4];
+    load_taxa(taxa, q, tx);
+    *n = snaq_quartet_edges_sim(net, tx, g, out, cap);
+}
+
 // --------------------------------------------------------------------------------------------
 // evaluation
 // --------------------------------------------------------------------------------------------
@@ -4309,6 +4318,38 @@ int snaq_get_hasedge(snaq_ctx *ctx, uint8_t *hasedge, int32_t *indexht, int32_t 
             if (nindexht) nindexht[q] = n;
         }
     }
+    return SNAQ_OK;
+}
+
+int snaq_get_quartet_edges(snaq_ctx *ctx, int64_t q, int32_t *edge_numbers, int32_t cap, int32_t *n) {
+    if (!ctx) return SNAQ_EINVAL;
+    if (!ctx->has_net) { ctx->err = "snaq_set_network has not been called"; return SNAQ_ENODATA; }
+    if (!n || cap < 0 || (cap > 0 && !edge_numbers) || q < ctx->q_begin || q >= ctx->q_begin + ctx->nq) {
+        ctx->err = "bad arguments to snaq_get_quartet_edges (quartet index outside this context's block?)";
+        return SNAQ_EINVAL;
+    }
+    const SnaqHostTables &H = ctx->H;
+    if (H.sim.n_nodes > SNAQ_SIM_MAX || H.sim.n_edges > SNAQ_SIM_MAX) { ctx->err = "network too large for the quartet read-back"; return SNAQ_EINVAL; }
+    CK(cudaSetDevice(ctx->device));
+    const int capd = std::max(H.sim.n_edges, 1);
+    uint8_t *d_sim = nullptr;
+    int32_t *d_out = nullptr;
+    CK(cudaMalloc((void **)&d_sim, H.sim_blob.size()));
+    cudaError_t e = cudaMalloc((void **)&d_out, ((size_t)capd + 1) * sizeof(int32_t));
+    std::vector<int32_t> h((size_t)capd + 1, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_sim, H.sim_blob.data(), H.sim_blob.size(), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        k_quartet_edges<<<1, 1, 0, ctx->stream>>>(H.sim_view(d_sim), ctx->d_taxa, q - ctx->q_begin, d_out + 1, capd, d_out);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), d_out, h.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_sim); cudaFree(d_out);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return SNAQ_ECUDA; }
+    if (h[0] < 0) { ctx->err = build_err_text(SNAQ_B_BLOCKS); return SNAQ_ETOPOLOGY; }
+    *n = h[0];
+    for (int i = 0; i < std::min(h[0], cap); i++) edge_numbers[i] = h[(size_t)i + 1];
+    ctx->counters[5]++;
     return SNAQ_OK;
 }
 

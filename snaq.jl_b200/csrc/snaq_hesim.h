@@ -46,6 +46,8 @@ typedef struct SnaqSimNet {
     const int16_t *node_taxon;    /* [n_nodes] taxon id of a leaf, else -1   */
     const int16_t *edge_node;     /* [n_edges][2] edge.node order             */
     const uint8_t *edge_flags;    /* [n_edges]                                */
+    const int32_t *edge_number;   /* [n_edges] PN edge.number                 */
+    const int32_t *node_number;   /* [n_nodes] PN node.number                 */
     const int16_t *leaf_order;    /* [n_leaves] net.leaf                      */
     const int16_t *hyb_order;     /* [n_hybrids] net.hybrid                   */
     /* parameters: slot s of x is ... */
@@ -439,7 +441,81 @@ SNAQ_HD void sim_redundantCycleNode(SnaqSim &g, int n) {
 /* zpos (may be NULL): for every gammaz slot (nparams - nh - nt entries) the position in net.edge of the edge that carries
  * it in qnet, or -1: parameters!(qnet,net) lists these slots in qnet.edge order (src/snaq_optimization.jl:150-160),
  * which differs from slot order when two pruned bad diamonds I are left in one quartet network */
+/* extractQuartet!(net, quartet) on the integer state: the un-merged q.qnet is what is alive in g afterwards */
+SNAQ_HD int snaq_sim_prune(const SnaqSimNet &net, const uint16_t tx[4], SnaqSim &g);
+
 SNAQ_HD int snaq_hasedge_sim(const SnaqSimNet &net, const uint16_t tx[4], SnaqSim &g, uint32_t *bits, int *bd1_type5, int16_t *zpos = nullptr) {
+    const int N = net.n_nodes, E = net.n_edges;
+    const int nw = (net.nparams + 31) / 32;
+    for (int i = 0; i < nw; i++) bits[i] = 0;
+    if (zpos) for (int i = net.nh + net.nt; i < net.nparams; i++) zpos[i - net.nh - net.nt] = -1;
+    *bd1_type5 = 0;
+    const int rc = snaq_sim_prune(net, tx, g);
+    if (rc) return rc;
+    (void)N;
+    /* updateHasEdge!: src/pseudolik.jl:392-464.  An edge number is looked up among the surviving edges: the edge itself if
+     * it was not renamed, or an edge that the bad-diamond-I rewrite gave the same number (first in net.edge order) */
+    auto alive_e = [&](int e) { return e >= 0 && (g.efl[e] & SIM_E_ALIVE); };
+    auto renamed_to = [&](int code) {                               /* surviving edge renamed to pseudo number `code`, or -1 */
+        for (int e = 0; e < E; e++) if ((g.efl[e] & SIM_E_ALIVE) && g.ren[e] == code) return e;
+        return -1;
+    };
+    auto internalNonId = [&](int e) { return !(g.efl[e] & SIM_E_IDENT) && !sim_leaf(g, g.en2[e][0]) && !sim_leaf(g, g.en2[e][1]); };
+    auto setbit = [&](int s) { bits[s >> 5] |= 1u << (s & 31); };
+    for (int s = 0; s < net.nparams; s++) {
+        const int ref = net.slot_ref[s];
+        if (s < net.nh) {                                           /* gamma: the hybrid node is still a hybrid of qnet */
+            if (sim_alive(g, ref) && sim_hyb(g, ref)) setbit(s);
+        } else if (s < net.nh + net.nt) {
+            int found = (alive_e(ref) && g.ren[ref] < 0) ? ref : -1;
+            if (net.slot_alias[s] >= 0) {
+                const int r = renamed_to(net.slot_alias[s]);
+                if (r >= 0 && (found < 0 || r < found)) found = r;
+            }
+            if (found >= 0 && (g.efl[found] & SIM_E_IDENT)) setbit(s);
+        } else {                                                    /* gammaz pair of hybrid node ref: slots s (ind 1), s+1 (ind 2) */
+            if (sim_alive(g, ref) && sim_hyb(g, ref)) { setbit(s); setbit(s + 1); }
+            else {
+                int idx[2];
+                for (int k = 0; k < 2; k++) {
+                    int f = renamed_to(2 * ref + k);
+                    const int al = net.slot_alias[s + k];
+                    if (alive_e(al) && g.ren[al] < 0 && (f < 0 || al < f)) f = al;
+                    idx[k] = f;
+                }
+                if (idx[0] >= 0 && idx[1] < 0) { if (internalNonId(idx[0])) { setbit(s); if (zpos) zpos[s - net.nh - net.nt] = (int16_t)idx[0]; } }
+                else if (idx[1] >= 0 && idx[0] < 0) { if (internalNonId(idx[1])) { setbit(s + 1); if (zpos) zpos[s + 1 - net.nh - net.nt] = (int16_t)idx[1]; } }
+                else if (idx[0] >= 0 && idx[1] >= 0 && internalNonId(idx[0]) && internalNonId(idx[1])) return SNAQ_B_BLOCKS;
+            }
+            s++;
+        }
+    }
+    for (int i = 0; i < net.n_hybrids; i++) {
+        const int h = net.hyb_order[i];
+        if (sim_alive(g, h) && sim_hyb(g, h) && (g.nfl[h] & SIM_N_BD1)) { *bd1_type5 = 1; break; }
+    }
+    return SNAQ_B_OK;
+}
+
+/* the edge numbers of q.qnet.edge, in order (sampleEdgeQuartetWeighted step 2, src/moves_snaq.jl:1451-1453); an edge
+ * renamed by the bad-diamond-I rewrite carries "<hybrid node number><ind>".  Returns the count (<= cap written) or -1 */
+SNAQ_HD int snaq_quartet_edges_sim(const SnaqSimNet &net, const uint16_t tx[4], SnaqSim &g, int32_t *out, int cap) {
+    if (snaq_sim_prune(net, tx, g)) return -1;
+    int n = 0;
+    for (int e = 0; e < net.n_edges; e++) {
+        if (!(g.efl[e] & SIM_E_ALIVE)) continue;
+        int32_t num = net.edge_number[e];
+        if (g.ren[e] >= 0) {
+            const int32_t base = net.node_number[g.ren[e] >> 1], ind = (g.ren[e] & 1) + 1;
+            num = base >= 0 ? base * 10 + ind : base * 10 - ind;    /* parse(Int, string(number) * string(ind)) */
+        }
+        if (n < cap) out[n] = num;
+        n++;
+    }
+    return n;
+}
+
+SNAQ_HD int snaq_sim_prune(const SnaqSimNet &net, const uint16_t tx[4], SnaqSim &g) {
     const int N = net.n_nodes, E = net.n_edges;
     if (N > SNAQ_SIM_MAX || E > SNAQ_SIM_MAX) return SNAQ_B_OVERFLOW;
     g.nN = N; g.nE = E; g.err = 0;
@@ -484,53 +560,7 @@ SNAQ_HD int snaq_hasedge_sim(const SnaqSimNet &net, const uint16_t tx[4], SnaqSi
         if (g.nne[lf] != 1) { g.err = __LINE__; break; }
         sim_deleteIntLeafWhile(g, sim_other(g, g.ne3[lf][0], lf), lf);
     }
-    const int nw = (net.nparams + 31) / 32;
-    for (int i = 0; i < nw; i++) bits[i] = 0;
-    if (zpos) for (int i = net.nh + net.nt; i < net.nparams; i++) zpos[i - net.nh - net.nt] = -1;
-    *bd1_type5 = 0;
-    if (g.err) return SNAQ_B_BLOCKS;
-    /* updateHasEdge!: src/pseudolik.jl:392-464.  An edge number is looked up among the surviving edges: the edge itself if
-     * it was not renamed, or an edge that the bad-diamond-I rewrite gave the same number (first in net.edge order) */
-    auto alive_e = [&](int e) { return e >= 0 && (g.efl[e] & SIM_E_ALIVE); };
-    auto renamed_to = [&](int code) {                               /* surviving edge renamed to pseudo number `code`, or -1 */
-        for (int e = 0; e < E; e++) if ((g.efl[e] & SIM_E_ALIVE) && g.ren[e] == code) return e;
-        return -1;
-    };
-    auto internalNonId = [&](int e) { return !(g.efl[e] & SIM_E_IDENT) && !sim_leaf(g, g.en2[e][0]) && !sim_leaf(g, g.en2[e][1]); };
-    auto setbit = [&](int s) { bits[s >> 5] |= 1u << (s & 31); };
-    for (int s = 0; s < net.nparams; s++) {
-        const int ref = net.slot_ref[s];
-        if (s < net.nh) {                                           /* gamma: the hybrid node is still a hybrid of qnet */
-            if (sim_alive(g, ref) && sim_hyb(g, ref)) setbit(s);
-        } else if (s < net.nh + net.nt) {
-            int found = (alive_e(ref) && g.ren[ref] < 0) ? ref : -1;
-            if (net.slot_alias[s] >= 0) {
-                const int r = renamed_to(net.slot_alias[s]);
-                if (r >= 0 && (found < 0 || r < found)) found = r;
-            }
-            if (found >= 0 && (g.efl[found] & SIM_E_IDENT)) setbit(s);
-        } else {                                                    /* gammaz pair of hybrid node ref: slots s (ind 1), s+1 (ind 2) */
-            if (sim_alive(g, ref) && sim_hyb(g, ref)) { setbit(s); setbit(s + 1); }
-            else {
-                int idx[2];
-                for (int k = 0; k < 2; k++) {
-                    int f = renamed_to(2 * ref + k);
-                    const int al = net.slot_alias[s + k];
-                    if (alive_e(al) && g.ren[al] < 0 && (f < 0 || al < f)) f = al;
-                    idx[k] = f;
-                }
-                if (idx[0] >= 0 && idx[1] < 0) { if (internalNonId(idx[0])) { setbit(s); if (zpos) zpos[s - net.nh - net.nt] = (int16_t)idx[0]; } }
-                else if (idx[1] >= 0 && idx[0] < 0) { if (internalNonId(idx[1])) { setbit(s + 1); if (zpos) zpos[s + 1 - net.nh - net.nt] = (int16_t)idx[1]; } }
-                else if (idx[0] >= 0 && idx[1] >= 0 && internalNonId(idx[0]) && internalNonId(idx[1])) return SNAQ_B_BLOCKS;
-            }
-            s++;
-        }
-    }
-    for (int i = 0; i < net.n_hybrids; i++) {
-        const int h = net.hyb_order[i];
-        if (sim_alive(g, h) && sim_hyb(g, h) && (g.nfl[h] & SIM_N_BD1)) { *bd1_type5 = 1; break; }
-    }
-    return SNAQ_B_OK;
+    return g.err ? SNAQ_B_BLOCKS : SNAQ_B_OK;
 }
 
 #endif /* SNAQ_HESIM_H */

@@ -57,6 +57,8 @@ SnaqSimNet SnaqHostTables::sim_view(const unsigned char *b) const {
     v.hyb_order = (const int16_t *)(b + so_hyb_order);
     v.slot_ref = (const int16_t *)(b + so_slot_ref);
     v.slot_alias = (const int16_t *)(b + so_slot_alias);
+    v.edge_number = (const int32_t *)(b + so_edge_number);
+    v.node_number = (const int32_t *)(b + so_node_number);
     return v;
 }
 
@@ -451,6 +453,8 @@ int snaq_build_tables(const snaq_flatnet *f, int ntaxa, SnaqHostTables &o, std::
             o.so_hyb_order = put(o.sim_blob, s_hyb);
             o.so_slot_ref = put(o.sim_blob, s_ref);
             o.so_slot_alias = put(o.sim_blob, s_alias);
+            o.so_edge_number = put(o.sim_blob, std::vector<int32_t>(f->edge_number, f->edge_number + E));
+            o.so_node_number = put(o.sim_blob, std::vector<int32_t>(f->node_number, f->node_number + N));
         }
         return SNAQ_OK;
     } catch (const Fail &e) {

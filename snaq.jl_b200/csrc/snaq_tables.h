@@ -34,7 +34,7 @@ struct SnaqHostTables {
     std::vector<unsigned char> sim_blob;
     SnaqSimNet sim{};                                // counts filled in; pointers are set by sim_view()
     size_t so_node_edge = 0, so_node_flags = 0, so_node_incycle = 0, so_node_taxon = 0, so_edge_node = 0, so_edge_flags = 0,
-           so_leaf_order = 0, so_hyb_order = 0, so_slot_ref = 0, so_slot_alias = 0;
+           so_leaf_order = 0, so_hyb_order = 0, so_slot_ref = 0, so_slot_alias = 0, so_edge_number = 0, so_node_number = 0;
     SnaqSimNet sim_view(const unsigned char *base) const;
 };
 

@@ -34,7 +34,7 @@ EXPORTS = ["snaq_create", "snaq_destroy", "snaq_last_error", "snaq_version", "sn
            "snaq_eval", "snaq_eval_device", "snaq_eval_quartets", "snaq_get_descriptors", "snaq_get_counters",
            "snaq_check_status", "snaq_measure_fp64_peak", "snaq_get_trace", "snaq_eval_grad", "snaq_optbl", "snaq_update_bl", "snaq_get_hasedge",
            "snaq_eval_topologies", "snaq_optbl_topologies", "snaq_sample_quartets", "snaq_set_ci", "snaq_resample_obscf", "snaq_get_obscf",
-           "snaq_comm_unique_id", "snaq_comm_init", "snaq_comm_info", "snaq_patch_info", "snaq_table_checksum"]
+           "snaq_comm_unique_id", "snaq_comm_init", "snaq_comm_info", "snaq_patch_info", "snaq_table_checksum", "snaq_get_quartet_edges"]
 
 
 class _OptblOpts(C.Structure):
@@ -293,6 +293,13 @@ class Engine:
         nix = np.zeros(self.nq_local, np.int32)
         self._chk(self.lib.snaq_get_hasedge(self.ctx, _p(he), _p(ix), _p(nix)))
         return he[:, : self.nparams], [list(ix[i, : nix[i]]) for i in range(self.nq_local)]
+
+    def quartet_edges(self, q: int):
+        """edge numbers of ``d.quartet[q].qnet.edge`` (0-based q in the data's order): step 2 of sampleEdgeQuartetWeighted"""
+        out = np.zeros(4096, np.int32)
+        n = C.c_int32()
+        self._chk(self.lib.snaq_get_quartet_edges(self.ctx, C.c_int64(q), _p(out), C.c_int32(out.size), C.byref(n)))
+        return [int(v) for v in out[: n.value]]
 
     def update_bl(self):
         """per edge-length parameter: (Nquartets, edgeL) of ``updateBL!`` (src/readquartetdata.jl:838-861)"""

@@ -153,3 +153,25 @@ def test_hasedge_at_100_taxa_on_sampled_quartets(oracle):
     o = oracle.extract(flat, qt)
     assert np.array_equal(he, o["hasedge"])
     assert all(ix[i] == list(o["indexht"][i][: o["nindexht"][i]]) for i in range(len(qt)))
+
+
+@pytest.mark.gpu
+def test_quartet_edges_for_the_weighted_edge_choice(oracle):
+    """snaq_get_quartet_edges = [e.number for e in d.quartet[idx].qnet.edge] (src/moves_snaq.jl:1451-1453)"""
+    for seed, h in ((5, 0), (6, 1), (7, 3), (9, 4)):
+        n = 14
+        net = None
+        for attempt in range(20):
+            try:
+                net = simulate.random_level1_network(n, h, 300 + seed + 1000 * attempt, min_cycle=3 if seed % 2 else 4)
+                break
+            except S.SnaqError:
+                pass
+        taxa = [f"t{i + 1}" for i in range(n)]
+        flat = net.flatten(taxa)
+        qt = simulate.all_quartets(n)
+        eng = S.Engine(0)
+        eng.set_data(S.DataCF(taxa, qt, np.full((len(qt), 3), 1 / 3)))
+        eng.set_network(flat)
+        for q in range(0, len(qt), 37):
+            assert eng.quartet_edges(q) == oracle.quartet_edges(flat, qt[q]), (seed, q)

@@ -149,3 +149,44 @@ def test_optbl_from_a_start_on_the_boundary_with_infinite_deviance(oracle):
     inside = np.clip(start, 1e-4 * upper, upper * (1 - 1e-4))
     assert res["fmin"] <= oracle.evaluate(flat, qt, obs, inside)[0]  # a local optimum reachable from there (not necessarily the global one)
     assert np.all(xmin >= 0) and np.all(xmin <= upper)
+
+
+def test_search_tolerance_stop_is_no_looser_than_a_derivative_free_method(oracle):
+    """Under the reference's search tolerances (fRel = fAbs = 1e-6, xRel = 1e-2, xAbs = 1e-3; src/snaq_optimization.jl:36-39) optBL!
+    stops short of the converged optimum, and the search compares such values with liktolAbs = 1e-6 (:1389).  NLopt's BOBYQA
+    cannot be run here; against a bound-constrained derivative-free method of its class on the ORACLE objective
+    with the same tolerances (scipy's Powell), snaq_optbl's gap to the converged optimum is smaller (32 networks:
+    profiles/r02_optimizer_fidelity.json; 8 of them here)."""
+    from scipy.optimize import minimize
+    ours, powell = [], []
+    for k in range(8):
+        n, h = 9 + k % 8, k % 4
+        net = other = None
+        for attempt in range(30):
+            try:
+                net = simulate.random_level1_network(n, h, 4000 + k + 1000 * attempt)
+                other = simulate.random_level1_network(n, h, 9000 + k + 1000 * attempt)
+                break
+            except S.SnaqError:
+                continue
+        taxa = [f"t{i + 1}" for i in range(n)]
+        qt = simulate.all_quartets(n)
+        flat = net.flatten(taxa)
+        src = flat if k % 2 == 0 else other.flatten(taxa)
+        obs = simulate.obs_from_expcf(oracle.extract(src, qt)["expcf"], 100, k)
+        p = oracle.parameters(flat)
+        x0, upper = p["x"], p["upper"]
+        start = np.clip(x0 * np.random.default_rng(k).uniform(0.5, 1.5, len(x0)), 1e-3, upper - 1e-3)
+
+        def fo(x):
+            return float(oracle.evaluate(flat, qt, obs, np.clip(x, 0, upper).reshape(1, -1))[0])
+
+        _, rt = hs.optbl(flat, n, qt, obs, start, 1e-12, 1e-10, 1e-10, 1e-10)
+        _, rs = hs.optbl(flat, n, qt, obs, start)
+        pw = minimize(fo, start, method="Powell", bounds=list(zip(np.zeros_like(upper), upper)), options=dict(xtol=1e-2, ftol=1e-6, maxfev=1000))
+        fstar = min(rt["fmin"], float(pw.fun))
+        ours.append(rs["fmin"] - fstar)
+        powell.append(float(pw.fun) - fstar)
+        assert ours[-1] <= 1e-3 * abs(fstar) + 1.0
+    assert np.median(ours) <= np.median(powell)
+    assert sum(o <= q + 1e-9 for o, q in zip(ours, powell)) >= 6

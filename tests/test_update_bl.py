@@ -98,3 +98,70 @@ def test_updateBL_host_mirror_applies_the_reference_rule(oracle):
     hyb = simulate.random_level1_network(10, 1, 5)
     with pytest.raises(S.SnaqError):
         S.updateBL_(hyb, S.DataCF([f"t{i + 1}" for i in range(10)], simulate.all_quartets(10), np.full((210, 3), 1 / 3)))
+
+
+# ---- a known-answer vector worked out by hand on the reference's own example data -------------------------------------
+# examples/tableCF.txt (15 quartets of A,B,C,D,E,O) and the ASTRAL tree of examples/astral.tre (docs/src/man/snaq_est.md:197-206),
+# (E,(O,((C,D),(A,B)))).  edgesParts (src/readquartetdata.jl:866-889) gives an internal edge the four subtrees around it, and
+# makeTable (:935-960) the quartets with ONE taxon in each, with the observed CF of the resolution the tree displays:
+#   edge {A,B} | rest : parts {A},{B},{C,D},{E,O} -> ABCE, ABCO, ABDE, ABDO, CF12_34 = 0.8333.., 0.8666.., 0.8333.., 0.8666..
+#                       mean 0.85      -> edgeL = -log(3/2 (1 - 0.85)) = -log 0.225
+#   edge {C,D} | rest : parts {C},{D},{A,B},{E,O} -> ACDE, ACDO, BCDE, BCDO, the displayed split CD|xy is CF14_23 = 1, 1, 1, 1
+#                       mean 1.0       -> edgeL = -log 0 = Inf (the reference does not guard it, :846)
+#   edge {A,B,C,D} | {E,O} : parts {A,B},{C,D},{E},{O} -> ACEO, ADEO, BCEO, BDEO, CF12_34 = 0.5333.., 0.5333.., 0.6666.., 0.6666..
+#                       mean 0.6       -> edgeL = -log(3/2 * 0.4) = -log 0.6
+HAND = {frozenset("AB"): (4, -np.log(0.225)), frozenset("CD"): (4, np.inf), frozenset("EO"): (4, -np.log(0.6))}
+
+
+def _hand_case():
+    import os
+    d = S.readtableCF(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tableCF.txt"))
+    net = S.readnewicklevel1("(E,(O,((C,D),(A,B))));")
+    names = {n.number: n.name for n in net.node if n.leaf}
+
+    def side(edge):                                       # the smaller side of the bipartition an internal edge induces
+        seen, stack = {edge.node[0].number}, [edge.node[0]]
+        while stack:
+            u = stack.pop()
+            for e in u.edge:
+                if e is edge:
+                    continue
+                v = e.node[1] if e.node[0] is u else e.node[0]
+                if v.number not in seen:
+                    seen.add(v.number)
+                    stack.append(v)
+        s = frozenset(names[k] for k in seen if k in names)
+        return s if len(s) <= 3 and s in HAND else frozenset(names.values()) - s
+
+    internal = {e.number: side(e) for e in net.edge if not e.node[0].leaf and not e.node[1].leaf}
+    assert sorted(map(sorted, internal.values())) == sorted(map(sorted, HAND))
+    return d, net, internal
+
+
+def test_update_bl_restatement_reproduces_the_hand_computed_vector():
+    d, net, internal = _hand_case()
+    tab = ubl.update_bl_table(net.flatten(d.taxa), d.quartet_taxa, d.obsCF)
+    assert sorted(tab) == sorted(internal)
+    for num, s in internal.items():
+        n, el = HAND[s]
+        assert tab[num][0] == n
+        assert (np.isinf(el) and np.isinf(tab[num][1])) or abs(tab[num][1] - el) < 1e-12
+
+
+@pytest.mark.gpu
+def test_device_update_bl_reproduces_the_hand_computed_vector():
+    d, net, internal = _hand_case()
+    eng = S.Engine(0)
+    eng.set_data(d)
+    eng.set_network(net.flatten(d.taxa))
+    nq, el = eng.update_bl()
+    _, numht, _ = eng.get_params()
+    got = {int(numht[eng.nh + i]): (int(nq[i]), float(el[i])) for i in range(eng.nt)}
+    for num, s in internal.items():
+        n, want = HAND[s]
+        assert got[num][0] == n
+        assert (np.isinf(want) and np.isinf(got[num][1])) or abs(got[num][1] - want) < 1e-9
+    # updateBL!'s rule (:850-858): lengths that readnewicklevel1 left at 1.0 are replaced, Inf is capped by setLength! at 10
+    S.updateBL_(net, d)
+    by = {s: next(e for e in net.edge if e.number == num).length for num, s in internal.items()}
+    assert abs(by[frozenset("AB")] + np.log(0.225)) < 1e-9 and by[frozenset("CD")] == 10.0 and abs(by[frozenset("EO")] + np.log(0.6)) < 1e-9
