@@ -314,62 +314,12 @@ __global__ void __launch_bounds__(256) k_dedup_copy(const uint32_t *__restrict__
     for (uint32_t c = 0; c < n; c++) prog_u[dst + c] = prog2[src + c];
     if (u == pad_u) prog_u[dst + n] = make_uint2(nullslot * 0x10001u, nullslot * 0x10001u);
 }
-// weights of a run = sum of the weights of its quartets.  One block per run (runs are very uneven: from one quartet to
-// hundreds of thousands).  Every thread keeps a compensated (Kahan) sum of its strided share, then the 128 (sum, error)
-// pairs are combined by a fixed tree of error-free additions: deterministic, and accurate to about one rounding, which
-// matters because on data that fit well the deviance is a small difference of these sums.
+// error-free addition (run-summed weights: k_wu_combine)
 __device__ __forceinline__ void two_sum(double a, double b, double &s, double &e) {
     s = __dadd_rn(a, b);
     const double bb = __dsub_rn(s, a);
     e = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
 }
-__global__ void __launch_bounds__(128) k_weights_u(const uint32_t *__restrict__ rstart, const double4 *__restrict__ W, int64_t nu,
-                                                   int64_t nq, double4 *__restrict__ Wu, double4 *__restrict__ pen) {
-    // components 0..3: the weights; 4..6: E_j = sum of w_j log(w_j / 100) (the obs*log(obs) share of program slot j);
-    // 7: number of sampled quartets of the run.  4..7 are only read when an expected CF is negative (snaq_loglik_t5).
-    constexpr int NC = 8;
-    const int64_t u = blockIdx.x;
-    const int64_t i0 = rstart[u], i1 = (u + 1 < nu) ? (int64_t)rstart[u + 1] : nq;
-    double s[NC], c[NC];
-#pragma unroll
-    for (int k = 0; k < NC; k++) { s[k] = 0.0; c[k] = 0.0; }
-    for (int64_t i = i0 + threadIdx.x; i < i1; i += 128) {
-        const double4 w = W[i];
-        const bool smp = (w.x != 0.0 || w.y != 0.0 || w.z != 0.0);
-        const double v[NC] = {w.x, w.y, w.z, w.w, w.x != 0.0 ? w.x * log(w.x / 100.0) : 0.0, w.y != 0.0 ? w.y * log(w.y / 100.0) : 0.0,
-                              w.z != 0.0 ? w.z * log(w.z / 100.0) : 0.0, smp ? 1.0 : 0.0};
-#pragma unroll
-        for (int k = 0; k < NC; k++) {
-            const double y = __dsub_rn(v[k], c[k]);
-            const double t = __dadd_rn(s[k], y);
-            c[k] = __dsub_rn(__dsub_rn(t, s[k]), y);
-            s[k] = t;
-        }
-    }
-    __shared__ double sh[2][NC][128];
-#pragma unroll
-    for (int k = 0; k < NC; k++) { sh[0][k][threadIdx.x] = s[k]; sh[1][k][threadIdx.x] = -c[k]; }   // value = sum + error
-    __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) {
-#pragma unroll
-            for (int k = 0; k < NC; k++) {
-                double ss, ee;
-                two_sum(sh[0][k][threadIdx.x], sh[0][k][threadIdx.x + o], ss, ee);
-                sh[0][k][threadIdx.x] = ss;
-                sh[1][k][threadIdx.x] = __dadd_rn(__dadd_rn(sh[1][k][threadIdx.x], sh[1][k][threadIdx.x + o]), ee);
-            }
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        Wu[u] = make_double4(__dadd_rn(sh[0][0][0], sh[1][0][0]), __dadd_rn(sh[0][1][0], sh[1][1][0]), __dadd_rn(sh[0][2][0], sh[1][2][0]),
-                             __dadd_rn(sh[0][3][0], sh[1][3][0]));
-        pen[u] = make_double4(__dadd_rn(sh[0][4][0], sh[1][4][0]), __dadd_rn(sh[0][5][0], sh[1][5][0]), __dadd_rn(sh[0][6][0], sh[1][6][0]),
-                              __dadd_rn(sh[0][7][0], sh[1][7][0]));
-    }
-}
-
 // W[i] (all classes) and, for the class-A quartets with one- and two-chunk programs [0,nA), the pair
 // WA[i] = (W0, W1) that the single-call kernel streams; their constants W3 are summed once into wpart (one
 // partial per block, fixed order)
@@ -1263,6 +1213,10 @@ __global__ void __launch_bounds__(256) k_run_tiles(const uint32_t *__restrict__ 
     tdesc[t] = d;
     size16[t] = (RN_OFF_AT + ob + (staged ? ((plen * 8u + 15u) & ~15u) : 0u)) / 16u;
 }
+__global__ void __launch_bounds__(256) k_tile_nruns(const RunTile *__restrict__ tdesc, uint32_t ntiles, uint32_t *__restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t <= ntiles) out[t] = t < ntiles ? (uint32_t)tdesc[t].nruns : 0u;
+}
 __global__ void __launch_bounds__(256) k_run_fill(const RunTile *__restrict__ tdesc, const uint32_t *__restrict__ rec_off,
                                                   const uint32_t *__restrict__ off_u, const uint2 *__restrict__ prog_u, uint32_t ntiles,
                                                   unsigned char *__restrict__ pack) {
@@ -1279,6 +1233,90 @@ __global__ void __launch_bounds__(256) k_run_fill(const RunTile *__restrict__ td
         const uint32_t plen = off_u[d.u0 + d.nruns] - d.pbeg;
         uint2 *dst = reinterpret_cast<uint2 *>(rec + d.prog_at);
         for (uint32_t c = lane; c < ((plen + 1u) & ~1u); c += 32u) dst[c] = c < plen ? prog_u[d.pbeg + c] : make_uint2(0u, 0u);
+    }
+}
+
+// ---- run-summed weights: W_u[u] = sum of the weights of run u's quartets (and the penalty data of snaq_loglik_t5).  Runs are very
+// uneven (one quartet to hundreds of thousands), so the sum is formed over the TILES of the run table: k_wu_partials, one warp
+// per tile, adds the tile's quartets per run (fixed shuffle tree); k_wu_combine, one warp per run, adds the run's consecutive
+// partials with compensated sums and a fixed tree of error-free additions.  Deterministic, balanced, accurate to a rounding.
+__global__ void __launch_bounds__(128) k_wu_partials(const RunTile *__restrict__ tdesc, const uint32_t *__restrict__ pidx,
+                                                     const double4 *__restrict__ W, uint32_t ntiles, double *__restrict__ part) {
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (t >= ntiles) return;
+    const RunTile d = tdesc[t];
+    const unsigned long long m = d.mask | 1ull;
+    double v[2][8];
+    int r[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const unsigned j = lane + 32u * k;
+        r[k] = -1;
+#pragma unroll
+        for (int c = 0; c < 8; c++) v[k][c] = 0.0;
+        if (j < d.n) {
+            const double4 w = W[(size_t)d.q0 + j];
+            r[k] = __popcll(m & ((2ull << j) - 1ull)) - 1;
+            v[k][0] = w.x; v[k][1] = w.y; v[k][2] = w.z; v[k][3] = w.w;
+            v[k][4] = w.x != 0.0 ? w.x * log(w.x / 100.0) : 0.0;
+            v[k][5] = w.y != 0.0 ? w.y * log(w.y / 100.0) : 0.0;
+            v[k][6] = w.z != 0.0 ? w.z * log(w.z / 100.0) : 0.0;
+            v[k][7] = (w.x != 0.0 || w.y != 0.0 || w.z != 0.0) ? 1.0 : 0.0;
+        }
+    }
+    double *out = part + (size_t)pidx[t] * 8;
+    for (int rr = 0; rr < (int)d.nruns; rr++) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            double x = (r[0] == rr ? v[0][c] : 0.0) + (r[1] == rr ? v[1][c] : 0.0);
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) out[(size_t)rr * 8 + c] = x;
+        }
+    }
+}
+__global__ void __launch_bounds__(128) k_wu_combine(const uint32_t *__restrict__ rstart, const RunTile *__restrict__ tdesc,
+                                                    const uint32_t *__restrict__ pidx, const double *__restrict__ part, int64_t nu,
+                                                    int64_t nq, int64_t nAB, uint32_t ntAB, double4 *__restrict__ Wu,
+                                                    double4 *__restrict__ pen) {
+    const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    if (u >= nu) return;
+    const int64_t i0 = rstart[u], i1 = (u + 1 < nu) ? (int64_t)rstart[u + 1] : nq;
+    auto tile_of = [&](int64_t i) { return i < nAB ? (uint32_t)(i / RN_TQ) : ntAB + (uint32_t)((i - nAB) / RN_TQC); };
+    const uint32_t t0 = tile_of(i0), t1 = tile_of(i1 - 1);
+    const size_t first = (size_t)pidx[t0] + ((uint32_t)u - tdesc[t0].u0);
+    const uint32_t cnt = t1 - t0 + 1;
+    double s[8], c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { s[k] = 0.0; c[k] = 0.0; }
+    for (uint32_t k = lane; k < cnt; k += 32u) {
+        const double *p = part + (first + k) * 8;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const double y = __dsub_rn(p[q], c[q]);
+            const double tt = __dadd_rn(s[q], y);
+            c[q] = __dsub_rn(__dsub_rn(tt, s[q]), y);
+            s[q] = tt;
+        }
+    }
+    double res[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        double hi = s[q], lo = -c[q];
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ohi = __shfl_xor_sync(0xffffffffu, hi, o), olo = __shfl_xor_sync(0xffffffffu, lo, o);
+            // (a symmetric combination: both partners form the same pair)
+            const double a = (lane & o) ? ohi : hi, b = (lane & o) ? hi : ohi;
+            double ss, ee;
+            two_sum(a, b, ss, ee);
+            hi = ss;
+            lo = __dadd_rn(__dadd_rn(lo, olo), ee);
+        }
+        res[q] = __dadd_rn(hi, lo);
+    }
+    if (lane == 0) {
+        Wu[u] = make_double4(res[0], res[1], res[2], res[3]);
+        pen[u] = make_double4(res[4], res[5], res[6], res[7]);
     }
 }
 
@@ -2709,6 +2747,10 @@ struct snaq_ctx {
     uint32_t *d_rec_off = nullptr; size_t rec_off_cap = 0;       // [ntiles + 1] record offsets of the packed tile stream (16-byte units)
     unsigned char *d_pack = nullptr; size_t pack_cap = 0;         // the packed tile stream
     double *d_partial2 = nullptr; size_t partial2_cap = 0;        // second level of the segment reduction
+    uint32_t *d_pidx = nullptr; size_t pidx_cap = 0;              // [ntiles + 1] first (tile, run) partial of every tile (k_wu_partials)
+    double *d_wupart = nullptr; size_t wupart_cap = 0;            // [(tile, run) pairs][8] per-tile sums of the run weights
+    bool sv_dedup = true;                 // single-vector paths (one objective call, gradient pass, optBL!) walk the compressed table
+                                          // with run-summed weights (SNAQ_SV_DEDUP=0: the per-quartet table, as the batched path)
     uint32_t rn_ntiles = 0, rn_nseg = 0, rn_tps = 1, rn_ntAB = 0;
     uint32_t *d_status = nullptr;          // [0] build, [1] eval
     unsigned long long *d_trace = nullptr; // SNAQ_TRACE=1: [blocks][8] phase timestamps of the last k_eval_direct launch
@@ -2908,8 +2950,11 @@ struct EvalTable {
     int64_t nq, nA1, nA2, nA, nB, nC;
     const double *pen;      // deduplicated table: per-run penalty data, else nullptr
 };
-static EvalTable eval_table(const snaq_ctx *ctx, bool full) {
-    if (ctx->dedup && !full) return EvalTable{ctx->d_off_u, ctx->d_prog_u, ctx->d_qhdr_u, ctx->d_W_u, ctx->d_WA_u, ctx->d_negw3_u,
+static bool use_compressed(const snaq_ctx *ctx, bool full, bool single_vector) {
+    return !full && ctx->nU > 0 && (ctx->dedup || (single_vector && ctx->sv_dedup));
+}
+static EvalTable eval_table(const snaq_ctx *ctx, bool full, bool single_vector = false) {
+    if (use_compressed(ctx, full, single_vector)) return EvalTable{ctx->d_off_u, ctx->d_prog_u, ctx->d_qhdr_u, ctx->d_W_u, ctx->d_WA_u, ctx->d_negw3_u,
                                               ctx->nU, ctx->uA1, ctx->uA2, ctx->uA, ctx->uB, ctx->uC, ctx->d_pen_u};
     return EvalTable{ctx->d_off, ctx->d_prog, ctx->d_qhdr, ctx->d_W, ctx->d_WA, ctx->d_negw3, ctx->nq, ctx->nA1, ctx->nA2, ctx->nA, ctx->nB, ctx->nC,
                      nullptr};
@@ -2920,17 +2965,24 @@ static int run_weights(snaq_ctx *ctx) {
     int64_t nb = (ctx->nq + 255) / 256;
     k_weights<<<(unsigned)nb, 256, 0, ctx->stream>>>(ctx->d_perm, ctx->d_qhdr, ctx->d_obs, ctx->has_sampled ? ctx->d_sampled : nullptr, ctx->nq,
                                                     ctx->nA1 + ctx->nA2, ctx->nA + ctx->nB, ctx->d_W, ctx->d_WA, ctx->d_wpart,
-                                                    ctx->d_rec_off, ctx->rn_ntAB, (ctx->runs_on && !ctx->dedup && ctx->rn_ntiles > 0) ? ctx->d_pack : nullptr);
+                                                    ctx->d_rec_off, ctx->rn_ntAB, (ctx->runs_on && ctx->rn_ntiles > 0) ? ctx->d_pack : nullptr);
     CK(cudaGetLastError());
     k_reduce_partials<<<2, 256, 0, ctx->stream>>>(ctx->d_wpart, (int)nb, 2, 2, ctx->d_negw3);
     CK(cudaGetLastError());
     ctx->counters[5] += 2;
-    if (ctx->dedup && ctx->nU > 0) {
-        // no separate class-A constant for the compressed table (negw3_u stays 0): see launch_direct
-        k_weights_u<<<(unsigned)ctx->nU, 128, 0, ctx->stream>>>(ctx->d_rstart, reinterpret_cast<const double4 *>(ctx->d_W), ctx->nU, ctx->nq,
-                                                               reinterpret_cast<double4 *>(ctx->d_W_u), reinterpret_cast<double4 *>(ctx->d_pen_u));
+    if (ctx->nU > 0 && ctx->rn_ntiles > 0) {
+        // the run-summed weights of the compressed table (single-vector paths; SNAQ_OPT_DEDUP: every path).  No separate
+        // class-A constant there (negw3_u stays 0): see launch_direct
+        const uint32_t nt = ctx->rn_ntiles;
+        k_wu_partials<<<(nt * 32 + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_tdesc, ctx->d_pidx, reinterpret_cast<const double4 *>(ctx->d_W), nt,
+                                                                      ctx->d_wupart);
         CK(cudaGetLastError());
-        ctx->counters[5] += 1;
+        k_wu_combine<<<(unsigned)((ctx->nU * 32 + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_rstart, ctx->d_tdesc, ctx->d_pidx, ctx->d_wupart, ctx->nU,
+                                                                                     ctx->nq, ctx->nA + ctx->nB, ctx->rn_ntAB,
+                                                                                     reinterpret_cast<double4 *>(ctx->d_W_u),
+                                                                                     reinterpret_cast<double4 *>(ctx->d_pen_u));
+        CK(cudaGetLastError());
+        ctx->counters[5] += 2;
     }
     return SNAQ_OK;
 }
@@ -3018,7 +3070,16 @@ static int build_run_tiles(snaq_ctx *ctx) {
     k_run_fill<<<(unsigned)((nt * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_tdesc, ctx->d_rec_off, ctx->d_off_u,
                                                                           reinterpret_cast<const uint2 *>(ctx->d_prog_u), (uint32_t)nt, ctx->d_pack);
     CK(cudaGetLastError());
-    ctx->counters[5] += 3;
+    // first (tile, run) partial of every tile: exclusive scan of the tiles' run counts; their total is at most nt + nU
+    rc = ensure(ctx, ctx->d_pidx, ctx->pidx_cap, (size_t)nt + 2);
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->d_wupart, ctx->wupart_cap, ((size_t)nt + (size_t)ctx->nU + 2) * 8);
+    if (rc) return rc;
+    k_tile_nruns<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_tdesc, (uint32_t)nt, ctx->d_pidx);
+    CK(cudaGetLastError());
+    t1 = ctx->scan_tmp_cap;
+    CK(cub::DeviceScan::ExclusiveSum(ctx->d_scan_tmp, t1, ctx->d_pidx, ctx->d_pidx, nt + 1, ctx->stream));
+    ctx->counters[5] += 5;
     return SNAQ_OK;
 }
 
@@ -3037,10 +3098,10 @@ static int launch_direct(snaq_ctx *ctx, cudaStream_t stream, const double *dX, i
                         (size_t)PC * (H.n_full + H.nparams) * 8;
     if (smem > 200 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_direct"; return SNAQ_EINVAL; }
     const int per_sm = (int)std::min<size_t>(OUT ? 2 : 3, (225 * 1024) / (smem + 1024));
-    EvalTable tb = eval_table(ctx, OUT);                    // the per-quartet read-back walks the full table
-    // deduplicated table: every entry through the generic path, which subtracts the run's own constant W3 entry by entry
+    EvalTable tb = eval_table(ctx, OUT, true);              // the per-quartet read-back walks the full table
+    // compressed table: every entry through the generic path, which subtracts the run's own constant W3 entry by entry
     // (the separate class-A constant would turn the deviance into the difference of two large sums); the table is tiny
-    if (ctx->dedup && !OUT) tb.nA1 = tb.nA2 = 0;
+    if (use_compressed(ctx, OUT, true)) tb.nA1 = tb.nA2 = 0;
     const int64_t work = (tb.nq + 255) / 256;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(work, (int64_t)ctx->sm_count * per_sm));
     int rc = ensure(ctx, ctx->d_partial, ctx->partial_cap, (size_t)grid * PC);
@@ -3324,6 +3385,7 @@ int snaq_create(const snaq_opts *opts, snaq_ctx **out) {
     if (const char *ev = getenv("SNAQ_EVAL_CHUNKS")) { int v = atoi(ev); if (v >= 1 && v <= 4) ctx->eval_chunks = v; }
     if (const char *ev = getenv("SNAQ_REUSE")) ctx->reuse = atoi(ev) != 0;
     if (const char *ev = getenv("SNAQ_RUNS")) ctx->runs_on = atoi(ev);
+    if (const char *ev = getenv("SNAQ_SV_DEDUP")) ctx->sv_dedup = atoi(ev) != 0;
     if (const char *ev = getenv("SNAQ_LANES_CHUNK")) { int v = atoi(ev); if (v == 128 || v == 256 || v == 512 || v == 1024) ctx->lanes_chunk = v; }
     if (const char *ev = getenv("SNAQ_LANES_PERSISTENT")) ctx->lanes_persistent = atoi(ev);
     if (const char *ev = getenv("SNAQ_LANES_WARPS")) { int v = atoi(ev); if (v == 8 || v == 12 || v == 16) ctx->lanes_warps = v; }
@@ -3355,7 +3417,7 @@ int snaq_destroy(snaq_ctx *ctx) {
     cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_blob); cudaFree(ctx->d_xconst);
     cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_WA); cudaFree(ctx->d_wpart); cudaFree(ctx->d_negw3); cudaFree(ctx->d_status); cudaFree(ctx->d_total); cudaFree(ctx->d_ticket); cudaFree(ctx->d_trace);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_uidx); cudaFree(ctx->d_rstart); cudaFree(ctx->d_ulen); cudaFree(ctx->d_off_u); cudaFree(ctx->d_qhdr_u);
-    cudaFree(ctx->d_stage); cudaFree(ctx->d_hdr0); cudaFree(ctx->d_dirty);
+    cudaFree(ctx->d_stage); cudaFree(ctx->d_hdr0); cudaFree(ctx->d_dirty); cudaFree(ctx->d_pidx); cudaFree(ctx->d_wupart);
     cudaFree(ctx->d_tdesc); cudaFree(ctx->d_rec_off); cudaFree(ctx->d_pack); cudaFree(ctx->d_partial2);
     cudaFree(ctx->d_prog_u); cudaFree(ctx->d_W_u); cudaFree(ctx->d_WA_u); cudaFree(ctx->d_wpart_u); cudaFree(ctx->d_negw3_u); cudaFree(ctx->d_pen_u);
     cudaFree(ctx->d_scan_tmp); cudaFree(ctx->d_X); cudaFree(ctx->d_XF); cudaFree(ctx->d_out); cudaFree(ctx->d_partial); cudaFree(ctx->d_gbins); cudaFree(ctx->d_gpart); cudaFree(ctx->d_rb_e); cudaFree(ctx->d_rb_l); cudaFree(ctx->d_rb_d); cudaFree(ctx->d_sq_w); cudaFree(ctx->d_sq_cum); cudaFree(ctx->d_sq_u); cudaFree(ctx->d_sq_idx); cudaFree(ctx->d_gout);
@@ -3659,8 +3721,10 @@ static int build_table(snaq_ctx *ctx, const uint8_t *d_dirty) {
         CK(cudaGetLastError());
         ctx->counters[5] += 5;
         ctx->nU = 0;
-        if (ctx->dedup || ctx->runs_on) { rc = build_dedup(ctx, pad_at); if (rc) return rc; }
-        if (ctx->runs_on && !ctx->dedup) { rc = build_run_tiles(ctx); if (rc) return rc; }
+        rc = build_dedup(ctx, pad_at);                     // run table: one program per run of identical programs
+        if (rc) return rc;
+        rc = build_run_tiles(ctx);                         // tiles of the run table (k_eval_runs, run-summed weights)
+        if (rc) return rc;
         ctx->has_net = true;
         rc = run_weights(ctx);
         if (rc) { ctx->has_net = false; return rc; }
@@ -3674,7 +3738,7 @@ static int build_table(snaq_ctx *ctx, const uint8_t *d_dirty) {
         const int64_t nG = ctx->nq - ctx->nA1 - ctx->nA2;
         const int64_t chunksG = (int64_t)(ctx->prog_words / 4) - ctx->nA1 - 2 * ctx->nA2;
         ctx->counters[6] = ctx->nA1 * 24 + ctx->nA2 * 32 + nG * (32 + 4 + 1) + chunksG * 8;
-        ctx->counters[7] = ctx->dedup ? ctx->nU : 0;
+        ctx->counters[7] = ctx->nU;
     }
     ctx->has_net = true;
     return SNAQ_OK;
@@ -4020,14 +4084,15 @@ int snaq_eval_grad(snaq_ctx *ctx, int32_t nparams, const double *x, double *f, d
     const int nrows = hdiag ? 2 * n_full : n_full;
     const size_t smem_base = 640 + 8 * QD_SPAN * 8 + (size_t)n_full * 8 + (size_t)nrows * 12 + 8 + (size_t)nparams * 8;   // xf, 96-bit bins, x
     if (smem_base - 128 > 100 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_grad"; return SNAQ_EINVAL; }
-    EvalTable tb = eval_table(ctx, false);
-    if (ctx->dedup) tb.nA1 = tb.nA2 = 0;                    // see launch_direct
+    EvalTable tb = eval_table(ctx, false, true);
+    const bool compressed = use_compressed(ctx, false, true);
+    if (compressed) tb.nA1 = tb.nA2 = 0;                    // see launch_direct
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((tb.nq + 255) / 256, (int64_t)ctx->sm_count * 3));
     // the streaming kernel (class-A ring, program memo, grid-wide integer bins) pays from about 65,000 class-A quartets on
     // (measured: 50 taxa and up; at 30 taxa the two are equal, below the small kernel wins by 4-8 us); else k_eval_grad_small
     const int64_t tilesA = (tb.nA1 + QD_TQ - 1) / QD_TQ + (tb.nA2 + QD_TQ - 1) / QD_TQ;
     const bool use_ring = tilesA >= 1024 && smem_base + 8 * QD_NST * QD_STAGE_BYTES <= 110 * 1024;   // (a very large network: no room for the ring)
-    const bool agg_on = !ctx->dedup && tb.nq >= 65536;
+    const bool agg_on = !compressed && tb.nq >= 65536;
     // (k_eval_grad_small lays its shared memory out without the barrier area: 128 bytes less)
     const size_t smem = use_ring ? smem_base + 8 * QD_NST * QD_STAGE_BYTES : smem_base - 128;
     if (!use_ring) {
