@@ -477,27 +477,47 @@ def candidates_leg(S, eng, taxa, qt, obs, ncand=32):
 
 
 def hbm_leg(S, Engine, local, torch):
-    """P=1 on 100 taxa / h=3 / 3,921,225 quartets: one optBL! objective call.  Bytes per launch = what the
-    layout makes k_eval_direct read once (engine counter: 16 B weights + 8 B per program chunk for additive
-    quartets, 37 B + programs for the rest); peak = MEASURED_PEAKS.json hbm_gbs.  Timed cold (L2 flushed before
-    every call: the table is smaller than L2) and warm (back-to-back calls, as inside one optBL!)."""
+    """One optBL! objective call (P = 1) on 100 taxa / h=3 / 3,921,225 quartets, two ways.
+    (a) the per-quartet streaming kernel (k_eval_direct over the full table, SNAQ_SV_DEDUP=0; also the kernel behind the
+        per-quartet read-backs): HBM roofline, bytes per launch = what the layout makes it read once (engine counter: 16 B
+        weights + 8 B per program chunk for additive quartets, 37 B + programs for the rest), peak = MEASURED_PEAKS.json
+        hbm_gbs, timed cold (L2 flushed before every call) and warm;
+    (b) the default: the same call on the run table with run-summed weights (one entry per distinct program; the sums are
+        formed once per set_obscf), which reads ~100x less and is launch-latency bound; and optBL! on top of it."""
     n, net, taxa, qt = table100(S)
-    eng = Engine(local)
-    eng.set_data(S.DataCF(taxa, qt, np.full((len(qt), 3), 1 / 3)))
-    t0 = time.perf_counter()
-    eng.set_network(net.flatten(taxa))
-    t_build = time.perf_counter() - t0
-    x0, _, upper = eng.get_params()
     dev = torch.device("cuda", local)
-    dX = torch.from_numpy(x0.reshape(1, -1)).to(dev)
-    dout = torch.zeros(1, dtype=torch.float64, device=dev)
     stream = torch.cuda.Stream(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    ms = float(timed_launches(torch, eng, dX, dout, stream, flush, 20, warm=5).mean())
-    ms_warm = float(timed_launches(torch, eng, dX, dout, stream, None, 50, warm=5).mean())
-    bytes_alg = eng.counters()["single_call_bytes"]
+    flat = net.flatten(taxa)
+    res = {}
+    for name, env in (("per_quartet_kernel", "0"), ("default", "1")):
+        os.environ["SNAQ_SV_DEDUP"] = env
+        eng = Engine(local)
+        del os.environ["SNAQ_SV_DEDUP"]
+        eng.set_data(S.DataCF(taxa, qt, np.full((len(qt), 3), 1 / 3)))
+        t0 = time.perf_counter()
+        eng.set_network(flat)
+        t_build = time.perf_counter() - t0
+        x0, _, upper = eng.get_params()
+        dX = torch.from_numpy(x0.reshape(1, -1)).to(dev)
+        dout = torch.zeros(1, dtype=torch.float64, device=dev)
+        ms = float(timed_launches(torch, eng, dX, dout, stream, flush, 20, warm=5).mean())
+        ms_warm = float(timed_launches(torch, eng, dX, dout, stream, None, 50, warm=5).mean())
+        for _ in range(5):
+            eng.eval(x0)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            eng.eval(x0)
+        host_us = (time.perf_counter() - t0) / 50 * 1e6
+        res[name] = {"ms_per_call": ms, "ms_per_call_warm_l2": ms_warm, "host_call_us": host_us, "evals_per_s": len(qt) / (ms * 1e-3),
+                     "value": float(dout.item()), "descriptor_build_s": t_build}
+        if name == "per_quartet_kernel":
+            bytes_alg = eng.counters()["single_call_bytes"]
+            res[name]["bytes_per_quartet"] = bytes_alg / len(qt)
+        else:
+            res[name]["distinct_programs"] = eng.counters()["distinct_programs"]
     peak, src = hbm_peak()
-    ach = bytes_alg / (ms * 1e-3) / 1e9
+    ach = bytes_alg / (res["per_quartet_kernel"]["ms_per_call"] * 1e-3) / 1e9
     ex = executed("hbm_p1") or {}
     # optBL! on the same table (src/snaq_optimization.jl:341-390): whole optimisations through snaq_optbl, from a
     # start 30 % off the simulating parameters, with the search-time and the final tolerances of the reference
@@ -518,11 +538,11 @@ def hbm_leg(S, Engine, local, torch):
         _, r = eng.optbl(start, *tol)
         r["seconds"] = time.perf_counter() - t0
         optbl[name] = r
+    rel = abs(res["default"]["value"] - res["per_quartet_kernel"]["value"]) / abs(res["per_quartet_kernel"]["value"])
     return {"optbl": optbl, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": ex.get("dram_bytes"), "peak_source": src,
+            "traffic": ex.get("dram_bytes"), "peak_source": src, "kernel": "k_eval_direct on the per-quartet table (SNAQ_SV_DEDUP=0)",
             "workload": f"100-taxon h=3, {len(qt)} quartets, P=1 (one objective call), L2 flushed before every timed call",
-            "ms_per_call": ms, "ms_per_call_warm_l2": ms_warm, "evals_per_s_warm_l2": len(qt) / (ms_warm * 1e-3),
-            "evals_per_s": len(qt) / (ms * 1e-3), "bytes_per_quartet": bytes_alg / len(qt), "descriptor_build_s": t_build}
+            "per_quartet_kernel": res["per_quartet_kernel"], "default_run_table": res["default"], "rel_diff_default_vs_per_quartet": rel}
 
 
 def gather_max(dist, torch, world, v, dev):

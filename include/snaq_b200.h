@@ -323,6 +323,12 @@ int snaq_get_hasedge(snaq_ctx *ctx, uint8_t *hasedge, int32_t *indexht, int32_t 
  * most cap are written.                                                                                              */
 int snaq_get_quartet_edges(snaq_ctx *ctx, int64_t q, int32_t *edge_numbers, int32_t cap, int32_t *n);
 
+/* Bounds-checked build of the library (csrc/Makefile: libsnaqb200_dbg.so, -DSNAQ_BOUNDS): every slot index an evaluation
+ * kernel derives from a program word is checked against the expanded parameter vector, every tile record / run / chunk index
+ * of the run-length kernel against its stage; *checks and *violations are the process-wide device counters.  The normal
+ * build returns -1, -1.  (compute-sanitizer is not available on the GPU pool; profiles/r02_bounds_check.md)            */
+int snaq_debug_bounds(snaq_ctx *ctx, int64_t *checks, int64_t *violations);
+
 /* engine counters: [0] launches of the eval kernel, [1] quartet-evals done,
  * [2] H2D bytes, [3] D2H bytes, [4] descriptor words in HBM, [5] launches of
  * the descriptor-build kernels, [6] bytes one single-call evaluation (P <= 4)

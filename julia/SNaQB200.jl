@@ -2,6 +2,10 @@
 # through libsnaqb200.so (include/snaq_b200.h).  NOT TESTED HERE: there is no Julia in the build image.
 # It touches nothing but the call sites listed in INTEGRATION.md; the public API (snaq!, optBL!,
 # topologyQpseudolik!, bootsnaq, readtableCF, DataCF, HybridNetwork) is unchanged.
+#
+#   using SNaQ, SNaQB200
+#   SNaQB200.install!()                  # SNaQ.optBL!, topologyQpseudolik!, sampleEdgeQuartetWeighted, readtableCF! now use the engine
+#   net = snaq!(startnet, d; hmax = 1)   # unchanged user code; one engine per (worker process, DataCF), GPU (myid()-1) % 8
 module SNaQB200
 
 using SNaQ, PhyloNetworks
@@ -25,14 +29,16 @@ mutable struct Engine
     ctx::Ptr{Cvoid}
     taxa::Vector{String}
     nq::Int
+    last_x::Vector{Float64}      # parameters of the last optimisation (weights of the deltaCF-weighted quartet draw)
+    has_net::Bool
 end
 
 check(e::Engine, rc) = rc == 0 || error(unsafe_string(ccall((:snaq_last_error, LIB), Cstring, (Ptr{Cvoid},), e.ctx)))
 
 "one engine per Julia worker process; worker i uses GPU (i-1) % ngpus (pmap over runs: src/snaq_optimization.jl:1681)"
-function Engine(d::DataCF; device::Integer = (Distributed.myid() - 1) % 8, dedup::Bool = false)
+function Engine(d::DataCF; device::Integer = (Distributed.myid() - 1) % 8, dedup::Bool = false, rank::Integer = 0, world_size::Integer = 1)
     ctx = Ref{Ptr{Cvoid}}(C_NULL)   # dedup: evaluate each distinct quartet program once with summed weights (SNAQ_OPT_DEDUP)
-    rc = ccall((:snaq_create, LIB), Cint, (Ref{Opts}, Ref{Ptr{Cvoid}}), Opts(device, 0, 1, dedup ? 1 : 0), ctx)
+    rc = ccall((:snaq_create, LIB), Cint, (Ref{Opts}, Ref{Ptr{Cvoid}}), Opts(device, rank, world_size, dedup ? 1 : 0), ctx)
     rc == 0 || error(unsafe_string(ccall((:snaq_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
     taxa = SNaQ.tiplabels(d)                               # src/readquartetdata.jl:440
     tid = Dict(t => UInt16(i - 1) for (i, t) in enumerate(taxa))
@@ -41,7 +47,7 @@ function Engine(d::DataCF; device::Integer = (Distributed.myid() - 1) % 8, dedup
         for i in 1:4 qt[i, j] = tid[q.taxon[i]] end
         obs[:, j] = q.obsCF
     end
-    e = Engine(ctx[], taxa, d.numQuartets)
+    e = Engine(ctx[], taxa, d.numQuartets, Float64[], false)
     check(e, ccall((:snaq_set_data, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{UInt16}, Ptr{Cdouble}),
                    e.ctx, length(taxa), d.numQuartets, qt, obs))
     finalizer(x -> ccall((:snaq_destroy, LIB), Cint, (Ptr{Cvoid},), x.ctx), e)
@@ -80,9 +86,15 @@ function flatnet(e::Engine, net::HybridNetwork)
     return f, keep
 end
 
-function set_network!(e::Engine, net::HybridNetwork)
+"extractQuartet!(net,d) on the device.  patch=true (the search loop edits ONE network in place, src/snaq_optimization.jl:1154-1198):
+snaq_patch_network re-describes only the quartets with a taxon whose root path changed; the table is bit-identical to a rebuild"
+function set_network!(e::Engine, net::HybridNetwork; patch::Bool = false)
     f, keep = flatnet(e, net)
-    GC.@preserve keep check(e, ccall((:snaq_set_network, LIB), Cint, (Ptr{Cvoid}, Ref{FlatNet}), e.ctx, f))
+    if patch
+        GC.@preserve keep check(e, ccall((:snaq_patch_network, LIB), Cint, (Ptr{Cvoid}, Ref{FlatNet}, Ptr{Cint}, Cint), e.ctx, f, C_NULL, 0))
+    else
+        GC.@preserve keep check(e, ccall((:snaq_set_network, LIB), Cint, (Ptr{Cvoid}, Ref{FlatNet}), e.ctx, f))
+    end
 end
 
 "objective value for one x (the body of `obj` in optBL!, src/snaq_optimization.jl:368-380)"
@@ -115,7 +127,8 @@ end
 # (fittedquartetCF, writeExpCF) needs them once the weighted draw of the proposals uses `sample_quartet`: off by default.
 function optBL!(net::HybridNetwork, d::DataCF, e::Engine, verbose::Bool, ftolRel, ftolAbs, xtolRel, xtolAbs; readback::Bool = false)
     SNaQ.parameters!(net)                       # :353
-    set_network!(e, net)                        # replaces extractQuartet!(net,d), :354
+    set_network!(e, net; patch = e.has_net)     # replaces extractQuartet!(net,d), :354 (incremental after the first topology)
+    e.has_net = true
     nht = length(ht(net))
     opt = SNaQ.NLopt.Opt(:LN_BOBYQA, nht)
     SNaQ.NLopt.ftol_rel!(opt, ftolRel); SNaQ.NLopt.ftol_abs!(opt, ftolAbs)
@@ -127,6 +140,7 @@ function optBL!(net::HybridNetwork, d::DataCF, e::Engine, verbose::Bool, ftolRel
     fmin, xmin, ret = SNaQ.NLopt.optimize(opt, ht(net))
     SNaQ.updateParameters!(net, xmin)           # :387
     SNaQ.loglik!(net, fmin)                     # :388
+    e.last_x = copy(xmin)
     readback && readback!(e, d, xmin)           # (quirk: the reference leaves the LAST x it tried there, not xmin)
 end
 
@@ -139,13 +153,15 @@ function optBL_device!(net::HybridNetwork, d::DataCF, e::Engine, ftolRel = SNaQ.
                        readback::Bool = false)
     (ftolRel > 0 && ftolAbs > 0 && xtolAbs > 0 && xtolRel > 0) || error("tolerances have to be positive, ftol (rel,abs), xtol (rel,abs): $([ftolRel, ftolAbs, xtolRel, xtolAbs])")
     SNaQ.parameters!(net)
-    set_network!(e, net)
+    set_network!(e, net; patch = e.has_net)
+    e.has_net = true
     x = copy(ht(net))
     res = OptblResult(0, 0, 0, 0, 0, 0)
     check(e, ccall((:snaq_optbl, LIB), Cint, (Ptr{Cvoid}, Ref{OptblOpts}, Ptr{Cdouble}, Ref{OptblResult}), e.ctx,
                    OptblOpts(ftolRel, ftolAbs, xtolRel, xtolAbs, 1000, 0, 0, 0), x, res))
     SNaQ.updateParameters!(net, x)
     SNaQ.loglik!(net, res.fmin)
+    e.last_x = copy(x)
     readback && readback!(e, d, x)
     return res
 end
@@ -218,5 +234,106 @@ function updateBL_device!(net::HybridNetwork, d::DataCF, e::Engine)
         ed.length < 0.0 && SNaQ.setLength!(ed, 1.0)             # :855-858
     end
 end
+
+# ---- quartet-sharded mode: the collective lives in the library (snaq_comm_unique_id / snaq_comm_init) ----
+"rank 0 creates the 128-byte id and hands it to the other ranks (Distributed.remotecall / a file / MPI.bcast)"
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    ccall((:snaq_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id) == 0 || error(unsafe_string(ccall((:snaq_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    return id
+end
+"collective: every rank of a sharded engine (Engine(d; rank, world_size)) calls it with the same id; afterwards\npseudodeviance / pseudodeviance_grad! / optBL_device! return totals over all ranks"
+comm_init!(e::Engine, id::Vector{UInt8}) = check(e, ccall((:snaq_comm_init, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), e.ctx, id))
+
+"edge numbers of d.quartet[idx].qnet.edge (1-based idx), for step 2 of sampleEdgeQuartetWeighted (src/moves_snaq.jl:1451-1453)"
+function quartet_edges(e::Engine, idx::Integer)
+    out = Vector{Cint}(undef, 4096); n = Ref{Cint}(0)
+    check(e, ccall((:snaq_get_quartet_edges, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Cint}, Cint, Ref{Cint}), e.ctx, idx - 1, out, length(out), n))
+    return Int.(out[1:n[]])
+end
+
+# ---- the drop-in hook ---------------------------------------------------------------------------------------------------
+# snaq!, bootsnaq, topologymaxQpseudolik! and topologyQpseudolik! reach the hot path through SNaQ's OWN functions
+# (optTopLevel! calls optBL! at src/snaq_optimization.jl:1346, :1387, :1435; afterOptBL! at :727; gammaZero! at :581).
+# install!() replaces those methods (same signatures) so that nothing above them changes.  Engines are kept in a registry
+# keyed by the DataCF object: one per worker process and data set, created on first use, data resident in HBM.
+const ENGINES = IdDict{Any,Engine}()
+const MODE = Ref(:nlopt)            # :nlopt  = phase 1: NLopt's BOBYQA in Julia, objective on the device (the reference's search path)
+                                    # :device = phase 2: snaq_optbl (projected quasi-Newton on the analytic gradient)
+engine_for(d::DataCF; kwargs...) = get!(() -> Engine(d; kwargs...), ENGINES, d)
+
+"push q.sampled to the engine (writers: updateSubsetQuartets!, updateUninformativeQuartets!, src/update.jl:386,406,442)"
+function sync_sampled!(e::Engine, d::DataCF)
+    mask = UInt8[q.sampled ? 1 : 0 for q in d.quartet]
+    check(e, ccall((:snaq_set_sampled, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), e.ctx, mask))
+end
+"push the observed CFs again (bootstrap: readtableCF!(data, df, cols) overwrites q.obsCF in place, src/readquartetdata.jl:211-217)"
+function sync_obscf!(e::Engine, d::DataCF)
+    obs = Matrix{Float64}(undef, 3, d.numQuartets)
+    for (j, q) in enumerate(d.quartet) obs[:, j] = q.obsCF end
+    check(e, ccall((:snaq_set_obscf, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), e.ctx, obs))
+end
+
+function install!(; mode::Symbol = :nlopt)
+    mode in (:nlopt, :device) || error("mode is :nlopt or :device")
+    MODE[] = mode
+    @eval SNaQ begin
+        # optBL!: src/snaq_optimization.jl:341-390
+        function optBL!(net::HybridNetwork, d::DataCF, verbose::Bool, ftolRel::Float64, ftolAbs::Float64, xtolRel::Float64, xtolAbs::Float64)
+            (ftolRel > 0 && ftolAbs > 0 && xtolAbs > 0 && xtolRel > 0) || error("tolerances have to be positive, ftol (rel,abs), xtol (rel,abs): $([ftolRel, ftolAbs, xtolRel, xtolAbs])")
+            e = $(engine_for)(d)
+            if $(MODE)[] === :device
+                $(optBL_device!)(net, d, e, ftolRel, ftolAbs, xtolRel, xtolAbs)
+            else
+                $(optBL!)(net, d, e, verbose, ftolRel, ftolAbs, xtolRel, xtolAbs)
+            end
+            return nothing
+        end
+        # topologyQpseudolik!: src/pseudolik.jl:1342-1378 (same preparation of the network; the quartet loop runs on the device)
+        function topologyQpseudolik!(net0::HybridNetwork, d::DataCF; verbose = false::Bool)
+            for ed in net0.edge
+                !ed.hybrid || (ed.gamma >= 0.0) || error("hybrid edge has missing γ value. Cannot compute quartet pseudo-likelihood.\nTry `topologymaxQpseudolik!` instead, to estimate these γ's.")
+            end
+            net = readTopologyUpdate(writenewick_level1(net0))
+            if !isempty(d.repSpecies)
+                expandLeaves!(d.repSpecies, net)
+                net = readnewicklevel1(writenewick_level1(net))
+            end
+            try checkNet(net) catch; error("starting topology not a level 1 network") end
+            e = $(engine_for)(d)
+            parameters!(net)
+            $(set_network!)(e, net)
+            val = $(pseudodeviance)(e, ht(net))
+            $(readback!)(e, d, ht(net))                 # q.qnet.expCF for fittedquartetCF / writeExpCF
+            loglik!(net0, val)
+            return val
+        end
+        # sampleEdgeQuartetWeighted: src/moves_snaq.jl:1434-1468.  The weighted draw and the quartet's edge list come from the
+        # engine; the RNG calls are the reference's (one rand() for the quartet, one sample() among its edges).
+        function sampleEdgeQuartetWeighted(edges::Vector{Edge}, d::DataCF)
+            e = $(engine_for)(d)
+            x = $(current_x)(e)
+            edge_numbers = [ed.number for ed in edges]
+            while true
+                idx = $(sample_quartet)(e, x, rand())
+                q_edges = [n for n in $(quartet_edges)(e, idx) if n in edge_numbers]
+                isempty(q_edges) && continue
+                edge = sample(q_edges, 1)[1]
+                return findfirst(isequal(edge), q_edges)
+            end
+        end
+        # data refresh hooks: the engine's copy follows the DataCF object
+        function readtableCF!(data::DataCF, df::DataFrames.DataFrame, cols::Vector{<:Integer})
+            for i in 1:size(df, 1), j in 1:3
+                data.quartet[i].obsCF[j] = df[i, cols[j]]
+            end
+            haskey($(ENGINES), data) && $(sync_obscf!)($(ENGINES)[data], data)
+        end
+    end
+    return nothing
+end
+
+"the parameter vector of the last optBL! on this engine (the weights of the next proposal's quartet draw are deltaCF there)"
+current_x(e::Engine) = e.last_x
 
 end # module

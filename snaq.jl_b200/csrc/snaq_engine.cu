@@ -452,15 +452,39 @@ __global__ void k_quartet_edges(SnaqSimNet net, const uint16_t *__restrict__ tax
 // --------------------------------------------------------------------------------------------
 // evaluation
 // --------------------------------------------------------------------------------------------
+// Bounds-checked build (make libsnaqb200_dbg.so, -DSNAQ_BOUNDS): compute-sanitizer is not available on the GPU pool, so the
+// debug library counts, on the device, every slot index outside the expanded parameter vector and every tile record /
+// run / chunk index outside its stage (snaq_debug_bounds).  Any program word read from the wrong place is such an index.
+#ifdef SNAQ_BOUNDS
+__device__ unsigned long long g_bounds_bad = 0ull;
+__device__ unsigned long long g_bounds_checks = 0ull;
+__device__ int g_dbg_nfull = 0;
+#define SNAQ_BCHK(cond) do { atomicAdd(&g_bounds_checks, 1ull); if (!(cond)) atomicAdd(&g_bounds_bad, 1ull); } while (0)
+#else
+#define SNAQ_BCHK(cond) do { } while (0)
+#endif
 struct XLane {   // candidate = lane; xs is [slot][32] (already offset by the lane)
     const double *xs;
-    __device__ __forceinline__ double operator()(unsigned s) const { return xs[s * 32u]; }
+    __device__ __forceinline__ double operator()(unsigned s) const {
+#ifdef SNAQ_BOUNDS
+        SNAQ_BCHK((int)s < g_dbg_nfull);
+#endif
+        return xs[s * 32u];
+    }
 };
 struct XRow {    // one candidate's xe, contiguous
     const double *x;
-    __device__ __forceinline__ double operator()(unsigned s) const { return x[s]; }
+    __device__ __forceinline__ double operator()(unsigned s) const {
+#ifdef SNAQ_BOUNDS
+        SNAQ_BCHK((int)s < g_dbg_nfull);
+#endif
+        return x[s];
+    }
 };
 
+#ifdef SNAQ_BOUNDS
+__device__ __forceinline__ unsigned dbg_slot(unsigned s) { SNAQ_BCHK((int)s < g_dbg_nfull); return (int)s < g_dbg_nfull ? s : 0u; }
+#endif
 __device__ __forceinline__ unsigned range_check(double v, double hi) { return (v >= 0.0 && v <= hi) ? 0u : SNAQ_S_RANGE; }
 
 // Expanded parameter vectors (snaq_expand_row); also the one place where the bounds of the reference's
@@ -588,8 +612,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
     // One PRMT per slot builds the byte offset slot*256 + lane*8 of xf[slot] for this lane.
     const unsigned lane8 = (unsigned)lane * 8u;
     const char *xb = reinterpret_cast<const char *>(xs);
+#ifdef SNAQ_BOUNDS
+#define XLO(w) (*(xl + 32u * dbg_slot((w) & 0xffffu)))
+#define XHI(w) (*(xl + 32u * dbg_slot((w) >> 16)))
+#else
 #define XLO(w) (*reinterpret_cast<const double *>(xb + __byte_perm((w), lane8, 0x5104)))
 #define XHI(w) (*reinterpret_cast<const double *>(xb + __byte_perm((w), lane8, 0x5324)))
+#endif
     // a warp takes a CONTIGUOUS share of the chunk: neighbours in the sorted table share programs / terms
     const int wper = (nqc + WARPS - 1) / WARPS, wbeg = min(warp * wper, nqc), wend = min(wbeg + wper, nqc);
     if (cls == 0) {
@@ -894,8 +923,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
     // One PRMT per slot builds the byte offset slot*256 + lane*8 of xf[slot] for this lane.
     const unsigned lane8 = (unsigned)lane * 8u;
     const char *xb = reinterpret_cast<const char *>(xs);
+#ifdef SNAQ_BOUNDS
+#define XLO(w) (*(xl + 32u * dbg_slot((w) & 0xffffu)))
+#define XHI(w) (*(xl + 32u * dbg_slot((w) >> 16)))
+#else
 #define XLO(w) (*reinterpret_cast<const double *>(xb + __byte_perm((w), lane8, 0x5104)))
 #define XHI(w) (*reinterpret_cast<const double *>(xb + __byte_perm((w), lane8, 0x5324)))
+#endif
     // A block walks SUPER-CHUNKS (LANESP_SUPER consecutive chunks; the host derives it from the table size only) sc = blockIdx.x, blockIdx.x + gx, ... and writes one
     // partial row per super-chunk: the sums do not depend on how many blocks the launch has (hence not on P).
     auto next_chunk = [&](int cb) {
@@ -1323,7 +1357,12 @@ __global__ void __launch_bounds__(128) k_wu_combine(const uint32_t *__restrict__
 // the candidates of a lane in the xf tile [row][CPL * 32]: element (row, c, lane)
 struct XLaneS {
     const double *p; unsigned stride;
-    __device__ __forceinline__ double operator()(unsigned s) const { return p[s * stride]; }
+    __device__ __forceinline__ double operator()(unsigned s) const {
+#ifdef SNAQ_BOUNDS
+        SNAQ_BCHK((int)s < g_dbg_nfull);
+#endif
+        return p[s * stride];
+    }
 };
 
 template <int WARPS, int CPL>
@@ -1401,6 +1440,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && CPL == 1) ? 2 : 1) 
             mbar_wait(&wbar[sg], phase);
             const unsigned char *stg = wring + sg * RN_STAGE_BYTES;
             const RunTile d = *reinterpret_cast<const RunTile *>(stg + RN_DESC_AT);
+            SNAQ_BCHK(d.n >= 1 && d.n <= RN_TQ && d.nruns >= 1 && d.nruns <= d.n && d.prog_at >= RN_OFF_AT + 16 && d.prog_at <= RN_OFF_AT + 272);
             const uint32_t *soff = reinterpret_cast<const uint32_t *>(stg + RN_OFF_AT);
             const bool staged = (d.flags & 2u) != 0;
             const uint2 *sprog = reinterpret_cast<const uint2 *>(stg + d.prog_at);
@@ -1408,7 +1448,9 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && CPL == 1) ? 2 : 1) 
             auto chunk = [&](uint32_t c) { return staged ? sprog[c] : __ldg(prog_u + d.pbeg + c); };
             // the constants of the r-th run of the tile, whose first quartet here sits at sorted position pos
             auto compute = [&](uint32_t r, int64_t pos) {
+                SNAQ_BCHK(r < d.nruns);
                 const uint32_t c0 = soff[r], c1 = soff[r + 1];
+                SNAQ_BCHK(c0 < c1 && (!staged || d.prog_at + c1 * 8u <= (unsigned)RN_STAGE_BYTES));
                 if (isC) {
                     const uint2 w = chunk(c0);
                     cBD1 = (w.y & 0xffffu) == nul;
@@ -3669,6 +3711,9 @@ static int build_table(snaq_ctx *ctx, const uint8_t *d_dirty) {
         CK(cudaMemcpyAsync(ctx->d_xconst, H.xconst.data(), H.xconst.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     ctx->counters[2] += (int64_t)H.blob.size() + (int64_t)H.xconst.size() * 8;
     ctx->T = H.view(ctx->d_blob);
+#ifdef SNAQ_BOUNDS
+    { const int nf = H.n_full; CK(cudaStreamSynchronize(ctx->stream)); CK(cudaMemcpyToSymbol(g_dbg_nfull, &nf, sizeof(int))); }
+#endif
     const int64_t nq = ctx->nq;
     ctx->prog_words = 0;
     ctx->maxlen = 1;
@@ -3787,6 +3832,21 @@ int snaq_patch_network(snaq_ctx *ctx, const snaq_flatnet *net, const int32_t *to
         CK(cudaMemcpyAsync(ctx->d_dirty, touched.data(), touched.size(), cudaMemcpyHostToDevice, ctx->stream));
     }
     return build_table(ctx, partial ? ctx->d_dirty : nullptr);
+}
+
+int snaq_debug_bounds(snaq_ctx *ctx, int64_t *checks, int64_t *violations) {
+    if (!ctx || !checks || !violations) return SNAQ_EINVAL;
+#ifdef SNAQ_BOUNDS
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    unsigned long long c = 0, b = 0;
+    CK(cudaMemcpyFromSymbol(&c, g_bounds_checks, sizeof(c)));
+    CK(cudaMemcpyFromSymbol(&b, g_bounds_bad, sizeof(b)));
+    *checks = (int64_t)c; *violations = (int64_t)b;
+#else
+    *checks = -1; *violations = -1;            // not a bounds-checked build
+#endif
+    return SNAQ_OK;
 }
 
 int snaq_patch_info(snaq_ctx *ctx, int64_t *touched_taxa) {

@@ -26,7 +26,7 @@ from .datacf import DataCF
 from .network import FlatNet, HybridNetwork, SnaqError, set_length
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsnaqb200.so")
+LIB_PATH = os.environ.get("SNAQ_B200_LIB") or os.path.join(_HERE, "csrc", "libsnaqb200.so")   # (override: the bounds-checked build)
 _LIB = None
 
 EXPORTS = ["snaq_create", "snaq_destroy", "snaq_last_error", "snaq_version", "snaq_set_data", "snaq_set_obscf",
@@ -34,7 +34,7 @@ EXPORTS = ["snaq_create", "snaq_destroy", "snaq_last_error", "snaq_version", "sn
            "snaq_eval", "snaq_eval_device", "snaq_eval_quartets", "snaq_get_descriptors", "snaq_get_counters",
            "snaq_check_status", "snaq_measure_fp64_peak", "snaq_get_trace", "snaq_eval_grad", "snaq_optbl", "snaq_update_bl", "snaq_get_hasedge",
            "snaq_eval_topologies", "snaq_optbl_topologies", "snaq_sample_quartets", "snaq_set_ci", "snaq_resample_obscf", "snaq_get_obscf",
-           "snaq_comm_unique_id", "snaq_comm_init", "snaq_comm_info", "snaq_patch_info", "snaq_table_checksum", "snaq_get_quartet_edges"]
+           "snaq_comm_unique_id", "snaq_comm_init", "snaq_comm_info", "snaq_patch_info", "snaq_table_checksum", "snaq_get_quartet_edges", "snaq_debug_bounds"]
 
 
 class _OptblOpts(C.Structure):
@@ -181,6 +181,12 @@ class Engine:
         out = C.c_int64(0)
         self._chk(self.lib.snaq_patch_info(self.ctx, C.byref(out)))
         return out.value
+
+    def debug_bounds(self):
+        """(checks, violations) of the bounds-checked build (libsnaqb200_dbg.so); (-1, -1) for the normal library"""
+        c = C.c_int64(); v = C.c_int64()
+        self._chk(self.lib.snaq_debug_bounds(self.ctx, C.byref(c), C.byref(v)))
+        return c.value, v.value
 
     def table_checksum(self):
         out = (C.c_uint64 * 4)()

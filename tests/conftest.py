@@ -17,3 +17,18 @@ def oracle():
     from oracle import oracle as o
     o.build()
     return o
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """with the bounds-checked library (SNAQ_B200_LIB=.../libsnaqb200_dbg.so) report the device-side index checks of the run"""
+    if not os.environ.get("SNAQ_B200_LIB"):
+        return
+    try:
+        import snaq_jl_b200 as S
+        eng = S.Engine(0)
+        checks, bad = eng.debug_bounds()
+        print(f"\n[snaq bounds-checked build] {checks} index checks, {bad} violations")
+        if bad > 0:
+            session.exitstatus = 1
+    except Exception as exc:  # noqa: BLE001
+        print(f"\n[snaq bounds-checked build] could not read the counters: {exc}")
