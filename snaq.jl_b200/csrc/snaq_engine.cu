@@ -483,7 +483,7 @@ struct XRow {    // one candidate's xe, contiguous
 };
 
 #ifdef SNAQ_BOUNDS
-__device__ __forceinline__ unsigned dbg_slot(unsigned s) { SNAQ_BCHK((int)s < g_dbg_nfull); return (int)s < g_dbg_nfull ? s : 0u; }
+__device__ __forceinline__ unsigned dbg_slot(unsigned s) { SNAQ_BCHK((int)s < g_dbg_nfull); return s; }
 #endif
 __device__ __forceinline__ unsigned range_check(double v, double hi) { return (v >= 0.0 && v <= hi) ? 0u : SNAQ_S_RANGE; }
 
@@ -1365,6 +1365,78 @@ struct XLaneS {
     }
 };
 
+template <int CPL> struct RunConsts {       // what a run of identical programs contributes per candidate
+    double cL[CPL], cT[CPL], c2[CPL];         // tree-like: log(major), t1 + log 3; 4-cycle: the three logs
+    double cz[CPL][3];                        // bad diamond I: the three expected CFs
+    bool bd1;
+};
+// Evaluation of the r-th run's program of a tile for the CPL candidates of this lane.  Out of line: it runs once per run,
+// and keeping its temporaries out of the streaming loop's register allocation is what lets the loop hold its accumulators
+template <int CPL>
+__device__ __noinline__ void runs_compute(const RunTile &d, const uint32_t *soff, const uint2 *sprog, const uint2 *__restrict__ prog_u,
+                                          const double *xl, const SnaqMath &M, const unsigned nul, const int64_t nA, const uint32_t r,
+                                          const int64_t pos, RunConsts<CPL> &K, unsigned &st) {
+    constexpr int TW = 32 * CPL;
+    const bool staged = (d.flags & 2u) != 0, isC = (d.flags & 1u) != 0;
+    auto chunk = [&](uint32_t c) { return staged ? sprog[c] : __ldg(prog_u + d.pbeg + c); };
+
+                SNAQ_BCHK(r < d.nruns);
+                const uint32_t c0 = soff[r], c1 = soff[r + 1];
+                SNAQ_BCHK(c0 < c1 && (!staged || d.prog_at + c1 * 8u <= (unsigned)RN_STAGE_BYTES));
+                if (isC) {
+                    const uint2 w = chunk(c0);
+                    K.bd1 = (w.y & 0xffffu) == nul;
+    #pragma unroll
+                    for (int c = 0; c < CPL; c++) {
+                        const XLaneS xf{xl + 32 * c, (unsigned)TW};
+                        if (!K.bd1) {
+                            const double g2 = xf(w.x & 0xffffu), ca = xf(w.x >> 16), cm = xf(w.y & 0xffffu), cb = xf(w.y >> 16);
+                            const double g1 = 1.0 - g2;
+                            const double y5 = snaq_exp(-snaq_clamp10(cm - ca), M), y6 = snaq_exp(-snaq_clamp10(cb - cm), M);
+                            const double cf0 = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;
+                            const double cf1 = g1 * 1.0 / 3.0 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
+                            const double cf2 = g1 * 1.0 / 3.0 * y5 + g2 * 1.0 / 3.0 * y6;
+                            K.cL[c] = snaq_log_pos(cf0, M); K.cT[c] = snaq_log_pos(cf1, M); K.c2[c] = snaq_log_pos(cf2, M);
+                        } else {
+                            const uint16_t pcw[4] = {(uint16_t)(w.x & 0xffffu), (uint16_t)(w.x >> 16), (uint16_t)nul, (uint16_t)nul};
+                            snaq_t5_cf(SNAQ_KIND_T5BD1, pcw, xf, M, K.cz[c]);
+                        }
+                    }
+                } else if (pos >= nA) {
+                    const uint16_t *pc = staged ? reinterpret_cast<const uint16_t *>(sprog + c0)
+                                                : reinterpret_cast<const uint16_t *>(prog_u + d.pbeg + c0);
+    #pragma unroll
+                    for (int c = 0; c < CPL; c++) {
+                        const XLaneS xf{xl + 32 * c, (unsigned)TW};
+                        const double tt = snaq_tree_terms_t1(pc, xf, M, st);
+                        const double major = fma(SNAQ_K_M23, snaq_exp(-tt, M), 1.0);
+                        if (major < 0.0) st |= SNAQ_S_NEGLEN;
+                        K.cL[c] = snaq_log(major, M);
+                        K.cT[c] = tt + SNAQ_K_LOG3;
+                    }
+                } else {
+                    double t0[CPL], t1[CPL];
+    #pragma unroll
+                    for (int c = 0; c < CPL; c++) { t0[c] = 0.0; t1[c] = 0.0; }
+    #pragma unroll 1
+                    for (uint32_t cc = c0; cc < c1; ++cc) {
+                        const uint2 w = chunk(cc);
+    #pragma unroll
+                        for (int c = 0; c < CPL; c++) {
+                            const XLaneS xf{xl + 32 * c, (unsigned)TW};
+                            t0[c] += xf(w.x & 0xffffu) - xf(w.x >> 16);
+                            t1[c] += xf(w.y & 0xffffu) - xf(w.y >> 16);
+                        }
+                    }
+    #pragma unroll
+                    for (int c = 0; c < CPL; c++) {
+                        const double tt = snaq_clamp10(t0[c] + t1[c]);
+                        K.cL[c] = snaq_log_pos(fma(SNAQ_K_M23, snaq_exp(-tt, M), 1.0), M);
+                        K.cT[c] = tt + SNAQ_K_LOG3;
+                    }
+                }
+            }
+
 template <int WARPS, int CPL>
 __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && CPL == 1) ? 2 : 1) k_eval_runs(const unsigned char *__restrict__ pack, const uint32_t *__restrict__ rec_off,
                                                         const uint2 *__restrict__ prog_u, const RunsMeta rm,
@@ -1419,17 +1491,17 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && CPL == 1) ? 2 : 1) 
     unsigned sg = 0, phase = 0;
     // segment sums: w0*L (a0, b0, e0, f0), w1*T (a1, b1, e1, f1), 4-cycles.  Four independent accumulators per product
     // and candidate: the FP64 pipe has a long dependent-issue latency and a block has few warps (the xf tile is large)
-    constexpr int NA = (CPL == 2 && WARPS == 16) ? 2 : 4;       // accumulators per product and candidate (register budget)
+    constexpr int NA = 4;                                       // accumulators per product and candidate
     double aL[CPL][NA], aT[CPL][NA], cacc[CPL];
     double cL[CPL], cT[CPL], c2[CPL];                           // the current run's constants: tree-like (L, T); 4-cycle (l0, l1, l2)
-    double cz[CPL][3];                                          // bad diamond I: the three expected CFs
+    RunConsts<CPL> K;
     bool cBD1 = false;
 #pragma unroll
     for (int c = 0; c < CPL; c++) {
 #pragma unroll
         for (int q = 0; q < NA; q++) { aL[c][q] = 0.0; aT[c][q] = 0.0; }
         cacc[c] = 0.0;
-        cL[c] = cT[c] = c2[c] = 0.0; cz[c][0] = cz[c][1] = cz[c][2] = 0.0;
+        cL[c] = cT[c] = c2[c] = 0.0;
     }
 #pragma unroll 1
     for (unsigned seg = gw; seg < rm.nseg; seg += nwg) {
@@ -1442,67 +1514,13 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && CPL == 1) ? 2 : 1) 
             const RunTile d = *reinterpret_cast<const RunTile *>(stg + RN_DESC_AT);
             SNAQ_BCHK(d.n >= 1 && d.n <= RN_TQ && d.nruns >= 1 && d.nruns <= d.n && d.prog_at >= RN_OFF_AT + 16 && d.prog_at <= RN_OFF_AT + 272);
             const uint32_t *soff = reinterpret_cast<const uint32_t *>(stg + RN_OFF_AT);
-            const bool staged = (d.flags & 2u) != 0;
             const uint2 *sprog = reinterpret_cast<const uint2 *>(stg + d.prog_at);
             const bool isC = (d.flags & 1u) != 0;
-            auto chunk = [&](uint32_t c) { return staged ? sprog[c] : __ldg(prog_u + d.pbeg + c); };
-            // the constants of the r-th run of the tile, whose first quartet here sits at sorted position pos
             auto compute = [&](uint32_t r, int64_t pos) {
-                SNAQ_BCHK(r < d.nruns);
-                const uint32_t c0 = soff[r], c1 = soff[r + 1];
-                SNAQ_BCHK(c0 < c1 && (!staged || d.prog_at + c1 * 8u <= (unsigned)RN_STAGE_BYTES));
-                if (isC) {
-                    const uint2 w = chunk(c0);
-                    cBD1 = (w.y & 0xffffu) == nul;
-    #pragma unroll
-                    for (int c = 0; c < CPL; c++) {
-                        const XLaneS xf{xl + 32 * c, (unsigned)TW};
-                        if (!cBD1) {
-                            const double g2 = xf(w.x & 0xffffu), ca = xf(w.x >> 16), cm = xf(w.y & 0xffffu), cb = xf(w.y >> 16);
-                            const double g1 = 1.0 - g2;
-                            const double y5 = snaq_exp(-snaq_clamp10(cm - ca), M), y6 = snaq_exp(-snaq_clamp10(cb - cm), M);
-                            const double cf0 = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;
-                            const double cf1 = g1 * 1.0 / 3.0 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
-                            const double cf2 = g1 * 1.0 / 3.0 * y5 + g2 * 1.0 / 3.0 * y6;
-                            cL[c] = snaq_log_pos(cf0, M); cT[c] = snaq_log_pos(cf1, M); c2[c] = snaq_log_pos(cf2, M);
-                        } else {
-                            const uint16_t pcw[4] = {(uint16_t)(w.x & 0xffffu), (uint16_t)(w.x >> 16), (uint16_t)nul, (uint16_t)nul};
-                            snaq_t5_cf(SNAQ_KIND_T5BD1, pcw, xf, M, cz[c]);
-                        }
-                    }
-                } else if (pos >= rm.nA) {
-                    const uint16_t *pc = staged ? reinterpret_cast<const uint16_t *>(sprog + c0)
-                                                : reinterpret_cast<const uint16_t *>(prog_u + d.pbeg + c0);
-    #pragma unroll
-                    for (int c = 0; c < CPL; c++) {
-                        const XLaneS xf{xl + 32 * c, (unsigned)TW};
-                        const double tt = snaq_tree_terms_t1(pc, xf, M, st);
-                        const double major = fma(SNAQ_K_M23, snaq_exp(-tt, M), 1.0);
-                        if (major < 0.0) st |= SNAQ_S_NEGLEN;
-                        cL[c] = snaq_log(major, M);
-                        cT[c] = tt + SNAQ_K_LOG3;
-                    }
-                } else {
-                    double t0[CPL], t1[CPL];
-    #pragma unroll
-                    for (int c = 0; c < CPL; c++) { t0[c] = 0.0; t1[c] = 0.0; }
-    #pragma unroll 1
-                    for (uint32_t cc = c0; cc < c1; ++cc) {
-                        const uint2 w = chunk(cc);
-    #pragma unroll
-                        for (int c = 0; c < CPL; c++) {
-                            const XLaneS xf{xl + 32 * c, (unsigned)TW};
-                            t0[c] += xf(w.x & 0xffffu) - xf(w.x >> 16);
-                            t1[c] += xf(w.y & 0xffffu) - xf(w.y >> 16);
-                        }
-                    }
-    #pragma unroll
-                    for (int c = 0; c < CPL; c++) {
-                        const double tt = snaq_clamp10(t0[c] + t1[c]);
-                        cL[c] = snaq_log_pos(fma(SNAQ_K_M23, snaq_exp(-tt, M), 1.0), M);
-                        cT[c] = tt + SNAQ_K_LOG3;
-                    }
-                }
+                runs_compute<CPL>(d, soff, sprog, prog_u, xl, M, nul, rm.nA, r, pos, K, st);
+#pragma unroll
+                for (int c = 0; c < CPL; c++) { cL[c] = K.cL[c]; cT[c] = K.cT[c]; c2[c] = K.c2[c]; }
+                cBD1 = K.bd1;
             };
             const double2 *sw = reinterpret_cast<const double2 *>(stg);
             if (!isC && !noreuse && (d.mask >> 1) == 0ull && d.n == RN_TQ) {
@@ -1574,7 +1592,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && CPL == 1) ? 2 : 1) 
                             } else {
                                 const double wq[4] = {w4.x, w4.y, w4.z, w4.w};
     #pragma unroll
-                                for (int c = 0; c < CPL; c++) cacc[c] += snaq_loglik_t5(cz[c], wq, M, st, nullptr);   // its own W3 and the per-quartet penalty
+                                for (int c = 0; c < CPL; c++) cacc[c] += snaq_loglik_t5(K.cz[c], wq, M, st, nullptr);   // its own W3 and the per-quartet penalty
                             }
                         }
                     }
@@ -3217,13 +3235,14 @@ static int eval_device_local(snaq_ctx *ctx, int P, const double *dX, double *dou
                 return (size_t)384 + ((((size_t)1 + warps * RN_NST) * 8 + 127) & ~size_t(127)) + (size_t)H.n_full * 256 * cpl +
                        (size_t)warps * RN_NST * RN_STAGE_BYTES;
             };
-            // One candidate per lane and 16-warp blocks by default (measured, 100 taxa, 256 vectors: 0.39 ms; two candidates per
-            // lane with 8-warp blocks, which halves the shared-memory reads of the weights but leaves 2 warps per scheduler:
-            // 0.41 ms; SNAQ_RUNS_CPL / SNAQ_RUNS_WARPS select the variants for measurements)
-            int cpl = 1;
+            // Two candidates per lane (the weights of a quartet are read from shared memory once for 64 candidates) with
+            // 16-warp blocks when the wider xf tile fits; else one candidate per lane.  Measured at 100 taxa: 256 vectors
+            // 0.40 ms either way (FP64 pipe 46 % against 36 % active), 4096 vectors 4.3 against 5.6 ms.
+            // SNAQ_RUNS_CPL / SNAQ_RUNS_WARPS select the variants for measurements.
+            int cpl = (P > 32 && smem_of(16, 2) <= 224 * 1024) ? 2 : 1;
             if (const char *ev = getenv("SNAQ_RUNS_CPL")) { const int v = atoi(ev); if (v == 1 || (v == 2 && P > 32 && smem_of(8, 2) <= 220 * 1024)) cpl = v; }
-            int warps = (cpl == 1 && smem_of(16, 1) <= 224 * 1024 && (smem_of(8, 1) > 110 * 1024 || (int64_t)ctx->rn_nseg >= 16 * (int64_t)ctx->sm_count)) ? 16 : 8;
-            if (const char *ev = getenv("SNAQ_RUNS_WARPS")) { const int v = atoi(ev); if (v == 8 || (v == 16 && cpl == 1 && smem_of(16, cpl) <= 224 * 1024)) warps = v; }
+            int warps = (smem_of(16, cpl) <= 224 * 1024 && (smem_of(8, cpl) > 110 * 1024 || (int64_t)ctx->rn_nseg >= 16 * (int64_t)ctx->sm_count)) ? 16 : 8;
+            if (const char *ev = getenv("SNAQ_RUNS_WARPS")) { const int v = atoi(ev); if (v == 8 || (v == 16 && smem_of(16, cpl) <= 224 * 1024)) warps = v; }
             const size_t smem = smem_of(warps, cpl);
             if (smem > 227 * 1024) { ctx->err = "network too large for the shared-memory tile of k_eval_runs"; return SNAQ_EINVAL; }
             const int tw = 32 * cpl;
@@ -3712,7 +3731,12 @@ static int build_table(snaq_ctx *ctx, const uint8_t *d_dirty) {
     ctx->counters[2] += (int64_t)H.blob.size() + (int64_t)H.xconst.size() * 8;
     ctx->T = H.view(ctx->d_blob);
 #ifdef SNAQ_BOUNDS
-    { const int nf = H.n_full; CK(cudaStreamSynchronize(ctx->stream)); CK(cudaMemcpyToSymbol(g_dbg_nfull, &nf, sizeof(int))); }
+    {   // process-wide bound: the largest expanded vector of any live network (contexts run concurrently)
+        static std::mutex mu;
+        static int nf_max = 0;
+        std::lock_guard<std::mutex> lock(mu);
+        if (H.n_full > nf_max) { nf_max = H.n_full; CK(cudaDeviceSynchronize()); CK(cudaMemcpyToSymbol(g_dbg_nfull, &nf_max, sizeof(int))); }
+    }
 #endif
     const int64_t nq = ctx->nq;
     ctx->prog_words = 0;
