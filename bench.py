@@ -8,17 +8,23 @@ quartets x 4096 parameter vectors = 112.3 M evals per step).
   python bench.py --gpus N --steps K --warmup W            # the engine
   python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port)
 
+The engine's default evaluates every distinct quartet program once per parameter vector with the summed weights of its
+quartets (the run table, include/snaq_b200.h); every (quartet, vector) pair is in the result, so `value` counts them all.
+The per-quartet kernels (SNAQ_OPT_PER_QUARTET: one weighted contribution computed per pair) are timed beside it.
+
 Legs of the JSON line (rank 0 prints it):
   value / e2e / roofline      configs[1], one independent batch per GPU (weak scaling, no data-path collective)
   north_star                  100 taxa, 3,921,225 quartets, 256 vectors per launch (the north star's config): device-timed,
                               end to end from host buffers, roofline on EXECUTED double-precision flops
-  roofline_hbm                the same table, one objective call (P = 1): HBM roofline; optBL! timings
+  per_quartet                 both of the above on the per-quartet kernels (k_eval_lanes / k_eval_runs), with their rooflines
+  roofline_hbm                the 100-taxon table, one objective call (P = 1): HBM roofline of the per-quartet streaming
+                              kernel, the default beside it; optBL! timings
   sharded                     configs[4]: 200 taxa, 64,684,950 quartets split over the N GPUs, collective inside the
                               library (fused peer-memory epilogue for P = 1, ncclAllReduce for P = 64): strong scaling
   search_chains               configs[2]'s shape: 8 hill-climbing chains of 50 candidate topologies (NNI proposals,
                               descriptor patch + optBL! at the search tolerances) on the 100-taxon table, chains dealt to GPUs
   bootstrap                   configs[3]'s shape: 96 replicates (CI resampling + updateBL! table + optBL!) at 50 taxa, dealt to GPUs
-  dedup, candidates           opt-in program deduplication; concurrent candidate optimisation on one GPU
+  candidates                  concurrent candidate optimisation on one GPU (worker contexts)
   cpu_baseline                the oracle port on the host cores (rank 0, N = 1 only)
 """
 import argparse
@@ -318,9 +324,11 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     single = world == 1 and not args.no_hbm
     if rank == 0 and single:
+        line["config"]["distinct_programs"] = int(eng.counters()["distinct_programs"])
         for name, fn in (("north_star", lambda: north_star_leg(S, eng.__class__, local, torch, peak_tf)),
+                         ("per_quartet", lambda: per_quartet_leg(S, eng.__class__, local, torch, taxa, qt, obs, flat, dX, dout, stream, flush,
+                                                                 evals_per_step, peak_tf, flop_per_eval)),
                          ("roofline_hbm", lambda: hbm_leg(S, eng.__class__, local, torch)),
-                         ("dedup", lambda: dedup_leg(S, eng.__class__, local, torch, taxa, qt, obs, flat, dX, dout, stream, flush, evals_per_step)),
                          ("candidates", lambda: candidates_leg(S, eng, taxa, qt, obs))):
             try:
                 line[name] = fn()
@@ -363,10 +371,10 @@ def table100(S):
     return n, net, taxa, qt
 
 
-def north_star_leg(S, Engine, local, torch, peak_tf):
+def north_star_leg(S, Engine, local, torch, peak_tf, dedup=None, key="north_star"):
     """BASELINE.json north_star: batched logPseudoLik at 100 taxa (3,921,225 quartets), 256 parameter vectors per launch."""
     n, net, taxa, qt = table100(S)
-    eng = Engine(local)
+    eng = Engine(local, dedup=dedup)
     eng.set_data(S.DataCF(taxa, qt, np.full((len(qt), 3), 1 / 3)))
     flat = net.flatten(taxa)
     eng.set_network(flat)
@@ -387,8 +395,9 @@ def north_star_leg(S, Engine, local, torch, peak_tf):
     f5 = float(np.mean(desc["which"] == 2))
     cbar = float(np.mean(np.sum((desc["types"] >= 2) & (desc["types"] <= 4), axis=1)))
     out = {"workload": f"100-taxon h=3, {len(qt)} quartets x {P} parameter vectors per launch, L2 flushed before every timed launch",
-           "ms_per_launch": float(ms.mean()), "value": evals / (float(ms.mean()) * 1e-3), "unit": "evals/s"}
-    out["roofline"] = fp64_roofline("north_star", float(ms.mean()) * 1e-3, peak_tf, evals, FLOP_TREE + FLOP_T5_EXTRA * f5 + FLOP_PER_TERM * cbar)
+           "ms_per_launch": float(ms.mean()), "value": evals / (float(ms.mean()) * 1e-3), "unit": "evals/s",
+           "distinct_programs": int(eng.counters()["distinct_programs"])}
+    out["roofline"] = fp64_roofline(key, float(ms.mean()) * 1e-3, peak_tf, evals, FLOP_TREE + FLOP_T5_EXTRA * f5 + FLOP_PER_TERM * cbar)
     # end to end: host X (pageable, as a Julia caller's) -> out on the host, through snaq_eval
     for _ in range(2):
         r = eng.eval(X)
@@ -401,51 +410,21 @@ def north_star_leg(S, Engine, local, torch, peak_tf):
     return out
 
 
-def dedup_leg(S, Engine, local, torch, taxa, qt, obs, flat, dX, dout, stream, flush, evals_per_step):
-    """Same work as the main step, on an engine created with dedup=True (include/snaq_b200.h: SNAQ_OPT_DEDUP)."""
-    eng = Engine(local, dedup=True)
+def per_quartet_leg(S, Engine, local, torch, taxa, qt, obs, flat, dX, dout, stream, flush, evals_per_step, peak_tf, flop_per_eval):
+    """The main step and the north-star launch on engines created with dedup=False (SNAQ_OPT_PER_QUARTET): one weighted
+    contribution computed per (quartet, vector) pair -- k_eval_lanes on configs[1] (short runs), k_eval_runs at 100 taxa."""
+    eng = Engine(local, dedup=False)
     eng.set_data(S.DataCF(taxa, qt, obs))
     eng.set_network(flat)
-    out = {"note": "opt-in: quartets with identical evaluation programs are evaluated once with the sum of their weights; "
-                   "'effective' rates count every quartet of the table", "quartets": int(len(qt)),
-           "distinct_programs": int(eng.counters()["distinct_programs"])}
     ref = dout.clone()
     ms = timed_launches(torch, eng, dX, dout, stream, flush, 20)
-    out["max_rel_diff_vs_plain"] = float(((dout - ref).abs() / ref.abs()).max().item())
-    out["config2_ms_per_step"] = float(ms.mean())
-    out["config2_effective_evals_per_s"] = evals_per_step / (float(ms.mean()) * 1e-3)
-    n, net, tx, q100 = table100(S)
-    e2 = Engine(local, dedup=True)
-    e2.set_data(S.DataCF(tx, q100, np.full((len(q100), 3), 1 / 3)))
-    fl = net.flatten(tx)
-    e2.set_network(fl)
-    t0 = time.perf_counter()
-    for _ in range(5):
-        e2.set_network(fl)
-    out["t100_set_network_ms"] = (time.perf_counter() - t0) / 5 * 1e3
-    out["t100_quartets"] = int(len(q100))
-    out["t100_distinct_programs"] = int(e2.counters()["distinct_programs"])
-    x0, _, upper = e2.get_params()
-    exp0, _, _ = e2.eval_quartets(x0)
-    e2.set_obscf(S.simulate.obs_from_expcf(exp0, 300, 5))
-    rng = np.random.default_rng(0)
-    start = np.clip(x0 * rng.uniform(0.7, 1.3, len(x0)), 0, upper)
-    for _ in range(3):
-        e2.eval(start)
-        e2.eval_grad(start)
-    t0 = time.perf_counter()
-    for _ in range(50):
-        e2.eval(start)
-    out["t100_objective_call_from_host_us"] = (time.perf_counter() - t0) / 50 * 1e6
-    t0 = time.perf_counter()
-    for _ in range(50):
-        e2.eval_grad(start)
-    out["t100_objective_plus_gradient_pass_us"] = (time.perf_counter() - t0) / 50 * 1e6
-    e2.optbl(start, 1e-6, 1e-6, 1e-2, 1e-3)                   # untimed warm-up
-    for name, tol in (("search_tolerances", (1e-6, 1e-6, 1e-2, 1e-3)), ("final_tolerances", (1e-12, 1e-10, 1e-10, 1e-10))):
-        t0 = time.perf_counter()
-        _, r = e2.optbl(start, *tol)
-        out["t100_optbl_" + name] = {"seconds": time.perf_counter() - t0, "fmin": r["fmin"], "nlaunches": r["nlaunches"]}
+    eng.check_status()
+    out = {"note": "SNAQ_OPT_PER_QUARTET: every (quartet, vector) contribution computed, programs of neighbouring quartets memoised",
+           "max_rel_diff_vs_default": float(((dout - ref).abs() / ref.abs()).max().item()),
+           "config2": {"ms_per_step": float(ms.mean()), "value": evals_per_step / (float(ms.mean()) * 1e-3), "unit": "evals/s",
+                       "roofline": fp64_roofline("config2_per_quartet", float(ms.mean()) * 1e-3, peak_tf, evals_per_step, flop_per_eval)}}
+    del eng
+    out["north_star"] = north_star_leg(S, Engine, local, torch, peak_tf, dedup=False, key="north_star_per_quartet")
     return out
 
 
@@ -478,7 +457,7 @@ def candidates_leg(S, eng, taxa, qt, obs, ncand=32):
 
 def hbm_leg(S, Engine, local, torch):
     """One optBL! objective call (P = 1) on 100 taxa / h=3 / 3,921,225 quartets, two ways.
-    (a) the per-quartet streaming kernel (k_eval_direct over the full table, SNAQ_SV_DEDUP=0; also the kernel behind the
+    (a) the per-quartet streaming kernel (k_eval_direct over the full table, SNAQ_OPT_PER_QUARTET; also the kernel behind the
         per-quartet read-backs): HBM roofline, bytes per launch = what the layout makes it read once (engine counter: 16 B
         weights + 8 B per program chunk for additive quartets, 37 B + programs for the rest), peak = MEASURED_PEAKS.json
         hbm_gbs, timed cold (L2 flushed before every call) and warm;
@@ -490,10 +469,8 @@ def hbm_leg(S, Engine, local, torch):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     flat = net.flatten(taxa)
     res = {}
-    for name, env in (("per_quartet_kernel", "0"), ("default", "1")):
-        os.environ["SNAQ_SV_DEDUP"] = env
-        eng = Engine(local)
-        del os.environ["SNAQ_SV_DEDUP"]
+    for name, mode in (("per_quartet_kernel", False), ("default", None)):
+        eng = Engine(local, dedup=mode)
         eng.set_data(S.DataCF(taxa, qt, np.full((len(qt), 3), 1 / 3)))
         t0 = time.perf_counter()
         eng.set_network(flat)
@@ -540,7 +517,7 @@ def hbm_leg(S, Engine, local, torch):
         optbl[name] = r
     rel = abs(res["default"]["value"] - res["per_quartet_kernel"]["value"]) / abs(res["per_quartet_kernel"]["value"])
     return {"optbl": optbl, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": ex.get("dram_bytes"), "peak_source": src, "kernel": "k_eval_direct on the per-quartet table (SNAQ_SV_DEDUP=0)",
+            "traffic": ex.get("dram_bytes"), "peak_source": src, "kernel": "k_eval_direct on the per-quartet table (SNAQ_OPT_PER_QUARTET)",
             "workload": f"100-taxon h=3, {len(qt)} quartets, P=1 (one objective call), L2 flushed before every timed call",
             "per_quartet_kernel": res["per_quartet_kernel"], "default_run_table": res["default"], "rel_diff_default_vs_per_quartet": rel}
 

@@ -94,12 +94,21 @@ typedef struct snaq_flatnet {
 
 typedef struct snaq_ctx snaq_ctx;   /* opaque: one ctx <=> one CUDA device + stream */
 
-/* Program deduplication (opt-in).  The expected CFs of a quartet depend only on its split and on the pieces of the
- * network between its two junctions, and the pseudo-deviance is linear in the weights 100*obsCF: quartets whose
- * evaluation programs are identical are evaluated ONCE with the sum of their weights (27,405 quartets -> 1,136 programs
- * at 30 taxa; 3,921,225 -> ~8,700 at 100 taxa).  Values agree with the plain path to rounding (the order of the sum
- * changes); per-quartet read-backs (snaq_eval_quartets) always use the full table.  Env: SNAQ_DEDUP=1.             */
+/* Run table (default).  The expected CFs of a quartet depend only on its split and on the pieces of the network between its
+ * two junctions, i.e. on its evaluation PROGRAM, and the pseudo-deviance is linear in the weights 100*obsCF: quartets whose
+ * programs are identical (they differ in taxa of the same clades) are evaluated ONCE per parameter vector with the SUM of
+ * their weights.  The sums are formed when the observed CFs change (snaq_set_data / _set_obscf / _set_sampled /
+ * _resample_obscf), per run of identical programs of the class-sorted table, with compensated arithmetic
+ * (27,405 quartets -> 1,290 programs at 30 taxa; 3,921,225 -> 9,419 at 100 taxa).  Every (quartet, vector) pair is in the
+ * result exactly as before, to rounding (<= 2e-15 relative: the order of the sum changes); the -1e15 penalty of a negative
+ * expected CF stays per sampled quartet; per-quartet read-backs (snaq_eval_quartets) use the full table.
+ * SNAQ_OPT_PER_QUARTET (env SNAQ_DEDUP=0) selects the per-quartet kernels instead: one weighted contribution computed per
+ * (quartet, vector) -- k_eval_runs for batches (the program still evaluated once per run, the weights streamed per
+ * quartet), k_eval_lanes for tables with short runs, k_eval_direct / k_eval_grad streaming the per-quartet table for
+ * single-vector calls (objective, gradient, optBL!; SNAQ_SV_DEDUP=1 puts only those back on the run table).
+ * SNAQ_OPT_DEDUP is kept for source compatibility (it is the default).                                                 */
 #define SNAQ_OPT_DEDUP 1u
+#define SNAQ_OPT_PER_QUARTET 2u
 
 typedef struct snaq_opts {
     int32_t device;        /* CUDA device ordinal                                  */

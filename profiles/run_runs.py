@@ -1,5 +1,7 @@
-"""Times the batched path (device-resident X) on BASELINE configs[1] (30 taxa, 4096 vectors) and on the north-star table
-(100 taxa, 3.92 M quartets, 256 vectors): run-length kernel (default) against the per-quartet kernels (SNAQ_RUNS=0)."""
+"""Times the batched path (device-resident X) on BASELINE configs[1] (30 taxa, 4096 vectors), on the north-star table
+(100 taxa, 3.92 M quartets, 256 vectors) and two larger ones: the default run table (runs = -1), and on the per-quartet
+table (SNAQ_OPT_PER_QUARTET) the run-length kernel k_eval_runs (runs = 2: forced, 1: when runs are long) and k_eval_lanes
+(runs = 0).  One leg with few repetitions for ncu:  python profiles/run_runs.py n h P seed runs"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -7,11 +9,11 @@ import torch
 import snaq_jl_b200 as S
 
 def leg(n, h, P, seed, runs, reps=20):
-    os.environ["SNAQ_RUNS"] = str(int(runs))
+    os.environ["SNAQ_RUNS"] = str(max(int(runs), 0))
     net = S.simulate.random_level1_network(n, h, seed)
     taxa = [f"t{i + 1}" for i in range(n)]
     qt = S.simulate.all_quartets(n)
-    eng = S.Engine(0)
+    eng = S.Engine(0, dedup=None if int(runs) < 0 else False)
     eng.set_data(S.DataCF(taxa, qt, np.full((len(qt), 3), 1 / 3)))
     eng.set_network(net.flatten(taxa))
     t0 = time.perf_counter()
@@ -46,7 +48,7 @@ if __name__ == "__main__":
         print(json.dumps(leg(int(a[0]), int(a[1]), int(a[2]), int(a[3]), int(a[4]), reps=3)))
         sys.exit(0)
     for n, h, P, seed in ((30, 2, 4096, 20261020), (100, 3, 256, 20261021), (100, 3, 4096, 20261021), (200, 5, 64, 20261022)):
-        for runs in (2, 0):
+        for runs in (-1, 1, 0):
             r = leg(n, h, P, seed, runs)
             print(json.dumps(r), flush=True)
             res.append(r)

@@ -10,7 +10,8 @@ import sys
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 GO = "gpurun_out"
 
-KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+KEYS = ["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum",
+        "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -100,16 +101,18 @@ def launches(path, fh):
 
 
 with open(f"profiles/{tag}_ncu_summary.md", "w") as fh:
-    fh.write(f"# ncu summaries ({tag})\n\nCommand profiled: `python bench.py --steps 3 --warmup 3 --no-cpu-baseline` on one B200 "
-             "(`--clock-control none`; per-launch times are cold-cache and serialised: compare shares, not absolutes).\n\n")
-    fh.write("## launch list (`ncu --metrics gpu__time_duration.sum -c 400`)\n\n")
-    launches(f"{GO}/{tag}_launches.csv", fh)
-    kernel_summary(f"{GO}/{tag}_lanes.ncu-rep", "k_eval_lanes (config 2: 27,405 quartets x 4096 vectors)", fh)
     import os
-    if os.path.exists(f"{GO}/{tag}_quartets.ncu-rep"):
-        kernel_summary(f"{GO}/{tag}_quartets.ncu-rep", "first-version single-call kernel (100 taxa, 3.92 M quartets, P=1)", fh)
-    if os.path.exists(f"{GO}/{tag}_grad.ncu-rep"):
-        kernel_summary(f"{GO}/{tag}_grad.ncu-rep", "k_eval_grad (100 taxa, 3.92 M quartets, objective + gradient; `python profiles/run_optbl.py 100 3`)", fh)
-    if os.path.exists(f"{GO}/{tag}_direct.ncu-rep"):
-        kernel_summary(f"{GO}/{tag}_direct.ncu-rep", "k_eval_direct (100 taxa, 3.92 M quartets, P=1; `python profiles/run_single_call.py`)", fh)
+    fh.write(f"# ncu summaries ({tag})\n\nCommand profiled: `python bench.py --steps 2 --warmup 3 --no-sharded --no-search --no-cpu-baseline` on one B200 "
+             "(`--clock-control none`; per-launch times are cold-cache and serialised: compare shares, not absolutes).\n\n")
+    fh.write("## launch list (`ncu --metrics gpu__time_duration.sum -c 600`)\n\n")
+    launches(f"{GO}/{tag}_launches.csv", fh)
+    for suffix, title in (("lanes", "k_eval_lanes (config 2: 27,405 quartets x 4096 vectors)"),
+                          ("lanes_config2", "k_eval_lanes (config 2: 27,405 quartets x 4096 vectors; the main line of bench.py)"),
+                          ("runs_northstar", "k_eval_runs (north star: 100 taxa, 3,921,225 quartets x 256 vectors; bench.py `north_star`)"),
+                          ("direct_p1", "k_eval_direct (100 taxa, 3.92 M quartets, P = 1, per-quartet table; bench.py `roofline_hbm`)"),
+                          ("quartets", "first-version single-call kernel (100 taxa, 3.92 M quartets, P=1)"),
+                          ("grad", "k_eval_grad (100 taxa, 3.92 M quartets, objective + gradient)"),
+                          ("direct", "k_eval_direct (100 taxa, 3.92 M quartets, P=1)")):
+        if os.path.exists(f"{GO}/{tag}_{suffix}.ncu-rep"):
+            kernel_summary(f"{GO}/{tag}_{suffix}.ncu-rep", title, fh)
 print("wrote", f"profiles/{tag}_ncu_summary.md")

@@ -51,6 +51,18 @@
 #define SNAQ_UNROLL1
 #endif
 
+/* Lanes that enter a loop with a data-dependent trip count together are made to leave it together: without the explicit
+ * barrier the compiler lets the early finishers run ahead and the rest of the builder executes once per group of lanes. */
+#if defined(__CUDA_ARCH__)
+#define SNAQ_LANES()        __activemask()
+#define SNAQ_REJOIN(m)      __syncwarp(m)
+#define SNAQ_ANY(m, c)      __any_sync(m, c)      /* loop while any of the lanes has work: the lanes step through it together */
+#else
+#define SNAQ_LANES()        0u
+#define SNAQ_REJOIN(m)      ((void)(m))
+#define SNAQ_ANY(m, c)      (c)
+#endif
+
 #define SNAQ_MAX_HYB 32          /* max hybrid nodes tracked in the parity descriptor */
 #define SNAQ_MAX_SLOT 4095       /* slots are 12 bit inside term headers */
 #define SNAQ_MAX_PATH 512        /* max blob-tree nodes on a quartet's internal path */
@@ -141,6 +153,9 @@ typedef struct SnaqTables {
     const uint16_t *blkmax;      /* per cycle position (offsets as cyc_slot): largest net.leaf index in that block */
     const uint16_t *hmax2;       /* [n_cycles] second largest net.leaf index in the hybrid's block, 0xFFFF if single */
     const uint16_t *hmaxtax;     /* [n_cycles] taxon with the largest net.leaf index in the hybrid's block */
+    /* optional (NULL: walk the parent pointers): blob-tree LCA of every pair of taxa, [ntaxa*ntaxa], filled on the device
+     * once per topology (k_leaf_lca) so that the per-quartet builder does six lookups instead of six walks */
+    const uint16_t *leaf_lca;
 } SnaqTables;
 #define SNAQ_CROW(T, c, j)   ((unsigned)(T).crow[c] + (unsigned)(j))
 #define SNAQ_T3ROW(T, c, o)  ((unsigned)(T).crow[c] + (unsigned)(T).cyc_k[c] + (unsigned)(o))
@@ -169,6 +184,12 @@ SNAQ_HD int snaq_lca(const SnaqTables &T, int u, int v) {
     while (T.depth[v] > T.depth[u]) v = T.parent[v];
     while (u != v) { u = T.parent[u]; v = T.parent[v]; }
     return u;
+}
+
+/* LCA of the blob-tree leaves of taxa tx[i], tx[j] */
+SNAQ_HD int snaq_lca_taxa(const SnaqTables &T, const uint16_t tx[4], const int L[4], int i, int j) {
+    if (T.leaf_lca) return T.leaf_lca[(size_t)tx[i] * (size_t)T.ntaxa + tx[j]];
+    return snaq_lca(T, L[i], L[j]);
 }
 
 /* emit the slots of cycle edges j = lo .. hi-1 (the arc between positions lo and hi) */
@@ -285,9 +306,9 @@ SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWr
         info->formula[0] = info->formula[1] = info->formula[2] = 2;
         for (int i = 0; i < SNAQ_MAX_HYB; i++) info->type[i] = 0;
     }
-    int l01 = snaq_lca(T, L[0], L[1]), l23 = snaq_lca(T, L[2], L[3]);
-    int l02 = snaq_lca(T, L[0], L[2]), l13 = snaq_lca(T, L[1], L[3]);
-    int l03 = snaq_lca(T, L[0], L[3]), l12 = snaq_lca(T, L[1], L[2]);
+    int l01 = snaq_lca_taxa(T, tx, L, 0, 1), l23 = snaq_lca_taxa(T, tx, L, 2, 3);
+    int l02 = snaq_lca_taxa(T, tx, L, 0, 2), l13 = snaq_lca_taxa(T, tx, L, 1, 3);
+    int l03 = snaq_lca_taxa(T, tx, L, 0, 3), l12 = snaq_lca_taxa(T, tx, L, 1, 2);
     int S0 = T.depth[l01] + T.depth[l23], S1 = T.depth[l02] + T.depth[l13], S2 = T.depth[l03] + T.depth[l12];
     int pos[4];
     *hdr = 0;
@@ -349,35 +370,56 @@ SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWr
     int J1 = snaq_deeper(T, snaq_deeper(T, lca6[p][q], lca6[p][r]), lca6[q][r]);
     int J2 = snaq_deeper(T, snaq_deeper(T, lca6[r][s], lca6[r][p]), lca6[s][p]);
     if (J1 == J2) return SNAQ_B_BLOCKS;
-    int apex = snaq_lca(T, J1, J2);
+    int apex;
+    if (T.leaf_lca) {
+        /* J1 is the LCA of a pair that holds taxon a, J2 of a pair that holds c: lca(J1, J2) is the shallowest of J1, J2 and
+         * lca(a, c) (an ancestor of the other is itself the answer, else lca(a, c) lies strictly above both; candidates of equal
+         * depth that share a descendant leaf are the same node) */
+        const int a = (J1 == lca6[p][q] || J1 == lca6[p][r]) ? p : q;
+        const int c = (J2 == lca6[r][s] || J2 == lca6[r][p]) ? r : s;
+        const int lac = lca6[a][c];
+        apex = T.depth[J1] <= T.depth[J2] ? J1 : J2;
+        if (T.depth[lac] < T.depth[apex]) apex = lac;
+    } else apex = snaq_lca(T, J1, J2);
     /* the internal path in order J1 .. apex .. J2 */
+    /* (no `return` inside a loop with a data-dependent trip count: the lanes of a warp would not reconverge behind it) */
     uint16_t seq[SNAQ_MAX_PATH];
-    int ns = 0;
+    int ns = 0, err = SNAQ_B_OK;
+    const unsigned lanes = SNAQ_LANES();
     for (int v = J1;; v = T.parent[v]) {
-        if (ns >= SNAQ_MAX_PATH) return SNAQ_B_OVERFLOW;
+        if (ns >= SNAQ_MAX_PATH) { err = SNAQ_B_OVERFLOW; break; }
         seq[ns++] = (uint16_t)v;
         if (v == apex) break;
     }
+    SNAQ_REJOIN(lanes);
     const int iapex = ns - 1;
-    {
-        int cnt = 0;
-        for (int v = J2; v != apex; v = T.parent[v]) cnt++;
-        if (ns + cnt > SNAQ_MAX_PATH) return SNAQ_B_OVERFLOW;
+    int cnt = 0;
+    for (int v = J2; v != apex; v = T.parent[v]) cnt++;
+    SNAQ_REJOIN(lanes);
+    if (ns + cnt > SNAQ_MAX_PATH) err = SNAQ_B_OVERFLOW;
+    if (!err) {
         int idx = ns + cnt - 1;
         for (int v = J2; v != apex; v = T.parent[v]) seq[idx--] = (uint16_t)v;
         ns += cnt;
     }
+    SNAQ_REJOIN(lanes);
+    if (err) return err;
     /* classify the two ends; find the type-4 ends (the only terms that can be negative, so the only
      * ones for which the reference's merge order matters once the 10.0 cap is reached) */
     SnaqCyc e1, e2;
     e1.cls = e2.cls = SNAQ_C_OPEN; e1.lo = e1.hi = e2.lo = e2.hi = 0; e1.rep = e2.rep = 0; e1.other = e2.other = 0;
     const int c1 = T.tcycle[J1], c2 = T.tcycle[J2];
-    if (c1 >= 0) { snaq_positions(T, c1, tx, pos); e1 = snaq_classify_cycle(T, c1, pos, p, q, r, s, 1); if (e1.cls < 0) return SNAQ_B_BLOCKS; }
-    if (c2 >= 0) { snaq_positions(T, c2, tx, pos); e2 = snaq_classify_cycle(T, c2, pos, p, q, r, s, 2); if (e2.cls < 0) return SNAQ_B_BLOCKS; }
+    const unsigned lanes1 = SNAQ_LANES();
+    if (c1 >= 0) { snaq_positions(T, c1, tx, pos); e1 = snaq_classify_cycle(T, c1, pos, p, q, r, s, 1); if (e1.cls < 0) err = SNAQ_B_BLOCKS; }
+    SNAQ_REJOIN(lanes1);
+    if (c2 >= 0) { snaq_positions(T, c2, tx, pos); e2 = snaq_classify_cycle(T, c2, pos, p, q, r, s, 2); if (e2.cls < 0) err = SNAQ_B_BLOCKS; }
+    SNAQ_REJOIN(lanes1);
+    if (err) return err;
     const int t4a = (c1 >= 0 && e1.cls == SNAQ_C_T4), t4b = (c2 >= 0 && e2.cls == SNAQ_C_T4);
     /* chains: edges 0..ja belong to the type-4 term at J1, edges jb..ns-2 to the one at J2 */
     int ja = -1, jb = ns - 1, nearA = 1;
     int aArc = 0, bArc = 0;   /* the chain runs through the open end cycle at the other junction */
+    const unsigned lanes3 = SNAQ_LANES();
     if (t4a || t4b) {
         /* cleanUpNode! runs (and pre-merges the path below each hybrid node up to the next degree-3
          * node) iff the pruned quartet network holds more than one hybrid: src/pseudolik.jl:826-830 */
@@ -399,7 +441,7 @@ SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWr
                     if (c >= 0) {
                         snaq_positions(T, c, tx, pos);
                         SnaqCyc m = snaq_classify_cycle(T, c, pos, p, q, r, s, 0);
-                        if (m.cls < 0) return SNAQ_B_BLOCKS;
+                        if (m.cls < 0) { err = SNAQ_B_BLOCKS; break; }
                         if (m.cls == SNAQ_C_T3) break;
                     }
                     ja++;
@@ -415,7 +457,7 @@ SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWr
                     if (c >= 0) {
                         snaq_positions(T, c, tx, pos);
                         SnaqCyc m = snaq_classify_cycle(T, c, pos, p, q, r, s, 0);
-                        if (m.cls < 0) return SNAQ_B_BLOCKS;
+                        if (m.cls < 0) { err = SNAQ_B_BLOCKS; break; }
                         if (m.cls == SNAQ_C_T3) break;
                     }
                     jb--;
@@ -435,6 +477,8 @@ SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWr
             aArc = bArc = 0;
         }
     }
+    SNAQ_REJOIN(lanes3);
+    if (err) return err;
     /* owner of a path element: 0 main list, 1 chain of the term at J1, 2 chain of the term at J2.
      * element kinds: edge i (between seq[i] and seq[i+1]); arc of interior node i; end arcs.
      * Terms evaluated on the fly (class B): type 2 and type 4.  Type 3 and gammaz terms are rows. */
@@ -449,34 +493,40 @@ SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWr
         if (J1 != apex) n0 += snaq_put_pair(w, T.dslot[J1], T.dslot[apex]);
         if (J2 != apex) n0 += snaq_put_pair(w, T.dslot[J2], T.dslot[apex]);
     }
-    for (int i = 0; i < ns; i++) {
-        if (i < ns - 1 && (t4a || t4b)) {
-            int owner = (t4a && i <= ja) ? 1 : ((t4b && i >= jb) ? 2 : 0);
-            if (owner == 0) n0 += snaq_put_pair(w, i < iapex ? T.pslot[seq[i]] : T.pslot[seq[i + 1]], NUL);
-        }
-        int c = T.tcycle[seq[i]];
-        if (c < 0) continue;
-        SnaqCyc m;
-        int owner = 0;
-        if (i == 0) { m = e1; owner = (t4b && bArc) ? 2 : 0; }
-        else if (i == ns - 1) { m = e2; owner = (t4a && aArc) ? 1 : 0; }
-        else {
-            snaq_positions(T, c, tx, pos);
-            m = snaq_classify_cycle(T, c, pos, p, q, r, s, 0);
-            if (m.cls < 0) return SNAQ_B_BLOCKS;
-            owner = (t4a && i <= ja) ? 1 : ((t4b && i >= jb + 1) ? 2 : 0);
-        }
-        if (m.cls == SNAQ_C_OPEN) {
-            if (owner == 0) n0 += snaq_put_arc(T, c, m.lo, m.hi, w);
-        } else if (m.cls == SNAQ_C_T3) {
-            n0 += snaq_put_pair(w, SNAQ_T3ROW(T, c, m.lo), NUL);
-            if (info) info->type[T.cyc_hyb[c]] = 3;
-        } else if (m.cls == SNAQ_C_TZ) {
-            /* the edge -log(1-gammaz) of a pruned bad diamond I already exists when cleanUpNode! runs: if the chain of a
-             * type-4 term at the other end reaches this junction, the edge is merged with that chain (owner != 0) */
-            if (owner == 0) n0 += snaq_put_pair(w, SNAQ_TZROW(T, c, m.other == 1 ? 0 : 1), NUL);
-        }
+    const unsigned lanes2 = SNAQ_LANES();
+    for (int i = 0; SNAQ_ANY(lanes2, i < ns && !err); i++) {
+        if (i < ns && !err) do {
+            if (i < ns - 1 && (t4a || t4b)) {
+                int owner = (t4a && i <= ja) ? 1 : ((t4b && i >= jb) ? 2 : 0);
+                if (owner == 0) n0 += snaq_put_pair(w, i < iapex ? T.pslot[seq[i]] : T.pslot[seq[i + 1]], NUL);
+            }
+            int c = T.tcycle[seq[i]];
+            if (c < 0) break;
+            SnaqCyc m;
+            int owner = 0;
+            if (i == 0) { m = e1; owner = (t4b && bArc) ? 2 : 0; }
+            else if (i == ns - 1) { m = e2; owner = (t4a && aArc) ? 1 : 0; }
+            else {
+                snaq_positions(T, c, tx, pos);
+                m = snaq_classify_cycle(T, c, pos, p, q, r, s, 0);
+                if (m.cls < 0) { err = SNAQ_B_BLOCKS; break; }
+                owner = (t4a && i <= ja) ? 1 : ((t4b && i >= jb + 1) ? 2 : 0);
+            }
+            if (m.cls == SNAQ_C_OPEN) {
+                if (owner == 0) n0 += snaq_put_arc(T, c, m.lo, m.hi, w);
+            } else if (m.cls == SNAQ_C_T3) {
+                n0 += snaq_put_pair(w, SNAQ_T3ROW(T, c, m.lo), NUL);
+                if (info) info->type[T.cyc_hyb[c]] = 3;
+            } else if (m.cls == SNAQ_C_TZ) {
+                /* the edge -log(1-gammaz) of a pruned bad diamond I already exists when cleanUpNode! runs: if the chain of a
+                 * type-4 term at the other end reaches this junction, the edge is merged with that chain (owner != 0) */
+                if (owner == 0) n0 += snaq_put_pair(w, SNAQ_TZROW(T, c, m.other == 1 ? 0 : 1), NUL);
+            }
+        } while (0);
+        SNAQ_REJOIN(lanes2);
     }
+    SNAQ_REJOIN(lanes2);
+    if (err) return err;
     /* on-the-fly terms, in path order */
     for (int i = 0; i < ns; i += (ns > 1 ? ns - 1 : 1)) {
         int c = T.tcycle[seq[i]];
@@ -523,11 +573,12 @@ SNAQ_HD int snaq_build_quartet(const SnaqTables &T, const uint16_t tx[4], SnaqWr
                     if (mm.cls == SNAQ_C_OPEN) nchain += snaq_put_arc(T, cc, mm.lo, mm.hi, w);
                 }
             }
-            if (nchain > 65535) return SNAQ_B_OVERFLOW;
+            if (nchain > 65535) err = SNAQ_B_OVERFLOW;
             if (w.out && cnt_at < w.cap) w.out[cnt_at] = (uint16_t)nchain;
             if (info) info->type[T.cyc_hyb[c]] = 4;
         }
     }
+    if (err) return err;
     if (n0 > 255 || nterms > 255 || nterms != nfly_pre) return SNAQ_B_OVERFLOW;
     if (info) info->formula[maj] = 1;
     if (nterms > 0 && w.out && cnt_word_at < w.cap) w.out[cnt_word_at] = (uint16_t)(n0 | (nterms << 8));

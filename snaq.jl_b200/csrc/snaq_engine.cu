@@ -41,6 +41,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -56,6 +57,7 @@
 #include "snaq_tables.h"
 
 #define SNAQ_S_RANGE 8u   /* a parameter outside its bounds reached the device */
+#define SNAQ_LCA_MAX_TAXA 4096          // pair table of LCAs: 2*ntaxa^2 bytes (32 MB at the cap), beyond it the builder walks
 #define SNAQ_STAGE_WORDS 12   /* program words per quartet kept from the classification pass (3 chunks: all but the longest programs) */
 // Small batches from the host travel as a kernel ARGUMENT (no host->device copy call, no staging buffer), and the
 // results are written by the last block straight into page-locked host memory (no device->host copy call).
@@ -140,6 +142,15 @@ __device__ __forceinline__ uint32_t term_hash(unsigned a, unsigned b, unsigned c
     h = (h ^ c) * 0xC2B2AE3Du;
     h = (h ^ d) * 0x27D4EB2Fu;
     return (h ^ (h >> 15)) & 0x0FFFFFFFu;
+}
+// blob-tree LCA of every pair of taxa (SnaqTables::leaf_lca): one thread per ordered pair, once per topology
+__global__ void __launch_bounds__(256) k_leaf_lca(SnaqTables T, uint16_t *__restrict__ out) {
+    const int n = T.ntaxa;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    const int i = idx / n, j = idx - i * n;
+    const int u = T.leaf_tnode[i], v = T.leaf_tnode[j];
+    out[idx] = (u == 0xFFFF || v == 0xFFFF) ? (uint16_t)0xFFFF : (uint16_t)snaq_lca(T, u, v);
 }
 __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_t *__restrict__ taxa, int64_t nq, const int dedup,
                                                      uint32_t *__restrict__ len4, uint32_t *__restrict__ cls,
@@ -2769,6 +2780,8 @@ struct snaq_ctx {
     bool has_net = false;
     SnaqHostTables H;
     unsigned char *d_blob = nullptr;
+    uint16_t *d_lca = nullptr;            // pair table of blob-tree LCAs (k_leaf_lca), ntaxa <= SNAQ_LCA_MAX_TAXA
+    size_t lca_cap = 0;
     size_t blob_cap = 0;
     SnaqTables T{};
     double *d_xconst = nullptr;
@@ -3424,7 +3437,10 @@ int snaq_create(const snaq_opts *opts, snaq_ctx **out) {
     ctx->device = opts ? opts->device : 0;
     ctx->rank = opts ? opts->rank : 0;
     ctx->world = (opts && opts->world_size > 0) ? opts->world_size : 1;
-    ctx->dedup = (opts && (opts->flags & SNAQ_OPT_DEDUP)) || (getenv("SNAQ_DEDUP") && atoi(getenv("SNAQ_DEDUP")) != 0);
+    // every path walks the run table with run-summed weights unless the caller asks for one FMA pair per (quartet, vector)
+    ctx->dedup = !(opts && (opts->flags & SNAQ_OPT_PER_QUARTET));
+    if (const char *ev = getenv("SNAQ_DEDUP")) ctx->dedup = atoi(ev) != 0;
+    ctx->sv_dedup = ctx->dedup;            // single-vector paths follow (SNAQ_SV_DEDUP overrides, below)
     if (ctx->device < 0 || ctx->device >= ndev || ctx->rank < 0 || ctx->rank >= ctx->world) {
         g_create_err = "bad device ordinal or rank";
         delete ctx;
@@ -3475,7 +3491,7 @@ int snaq_destroy(snaq_ctx *ctx) {
     cudaFree(ctx->d_mail); cudaFree(ctx->d_red);
     cudaFree(ctx->d_ci_lo); cudaFree(ctx->d_ci_hi);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_blob); cudaFree(ctx->d_xconst);
+    cudaFree(ctx->d_taxa); cudaFree(ctx->d_obs); cudaFree(ctx->d_sampled); cudaFree(ctx->d_blob); cudaFree(ctx->d_lca); cudaFree(ctx->d_xconst);
     cudaFree(ctx->d_off); cudaFree(ctx->d_prog); cudaFree(ctx->d_W); cudaFree(ctx->d_WA); cudaFree(ctx->d_wpart); cudaFree(ctx->d_negw3); cudaFree(ctx->d_status); cudaFree(ctx->d_total); cudaFree(ctx->d_ticket); cudaFree(ctx->d_trace);
     cudaFree(ctx->d_flags); cudaFree(ctx->d_uidx); cudaFree(ctx->d_rstart); cudaFree(ctx->d_ulen); cudaFree(ctx->d_off_u); cudaFree(ctx->d_qhdr_u);
     cudaFree(ctx->d_stage); cudaFree(ctx->d_hdr0); cudaFree(ctx->d_dirty); cudaFree(ctx->d_pidx); cudaFree(ctx->d_wupart);
@@ -3715,12 +3731,36 @@ int snaq_set_sampled(snaq_ctx *ctx, const uint8_t *mask) {
     return SNAQ_OK;
 }
 
+// SNAQ_BUILD_TIMING=1: host wall time of the stages of one table build (between the points where the host waits), to stderr
+struct BuildClock {
+    bool on;
+    std::chrono::steady_clock::time_point t0, last;
+    std::string line;
+    BuildClock() : on(getenv("SNAQ_BUILD_TIMING") && atoi(getenv("SNAQ_BUILD_TIMING")) != 0) { t0 = last = std::chrono::steady_clock::now(); }
+    void mark(snaq_ctx *ctx, const char *what);
+    ~BuildClock() {
+        if (on) fprintf(stderr, "[snaq build] %s total %.1f us\n", line.c_str(),
+                        std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
+
 // Device side of snaq_set_network / snaq_patch_network: uploads the host tables ctx->H and (re)builds the class-sorted
 // program table, the run table and the weights.  d_dirty (device, one byte per taxon) or nullptr: with it, only the quartets
 // that contain a flagged taxon are classified again; everything downstream (sort, offsets, emission from the staged
 // programs, runs, weights) is redone for the whole table, so the result is bit-identical to a build from scratch.
+void BuildClock::mark(snaq_ctx *ctx, const char *what) {
+    if (!on) return;
+    cudaStreamSynchronize(ctx->stream);
+    const auto now = std::chrono::steady_clock::now();
+    char buf[64];
+    snprintf(buf, sizeof buf, "%s %.1f | ", what, std::chrono::duration<double, std::micro>(now - last).count());
+    line += buf;
+    last = now;
+}
+
 static int build_table(snaq_ctx *ctx, const uint8_t *d_dirty) {
     const SnaqHostTables &H = ctx->H;
+    BuildClock clk;
     int rc = ensure(ctx, ctx->d_blob, ctx->blob_cap, H.blob.size());
     if (rc) return rc;
     rc = ensure(ctx, ctx->d_xconst, ctx->xconst_cap, std::max<size_t>(H.xconst.size(), 1));
@@ -3730,6 +3770,15 @@ static int build_table(snaq_ctx *ctx, const uint8_t *d_dirty) {
         CK(cudaMemcpyAsync(ctx->d_xconst, H.xconst.data(), H.xconst.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     ctx->counters[2] += (int64_t)H.blob.size() + (int64_t)H.xconst.size() * 8;
     ctx->T = H.view(ctx->d_blob);
+    if (ctx->nq > 0 && H.ntaxa > 0 && H.ntaxa <= SNAQ_LCA_MAX_TAXA) {
+        const size_t n2 = (size_t)H.ntaxa * H.ntaxa;
+        rc = ensure(ctx, ctx->d_lca, ctx->lca_cap, n2);
+        if (rc) return rc;
+        SnaqTables Tw = ctx->T;
+        k_leaf_lca<<<(unsigned)((n2 + 255) / 256), 256, 0, ctx->stream>>>(Tw, ctx->d_lca);
+        CK(cudaGetLastError());
+        ctx->T.leaf_lca = ctx->d_lca;
+    }
 #ifdef SNAQ_BOUNDS
     {   // process-wide bound: the largest expanded vector of any live network (contexts run concurrently)
         static std::mutex mu;
@@ -3738,6 +3787,7 @@ static int build_table(snaq_ctx *ctx, const uint8_t *d_dirty) {
         if (H.n_full > nf_max) { nf_max = H.n_full; CK(cudaDeviceSynchronize()); CK(cudaMemcpyToSymbol(g_dbg_nfull, &nf_max, sizeof(int))); }
     }
 #endif
+    clk.mark(ctx, "upload+lca");
     const int64_t nq = ctx->nq;
     ctx->prog_words = 0;
     ctx->maxlen = 1;
@@ -3755,6 +3805,7 @@ static int build_table(snaq_ctx *ctx, const uint8_t *d_dirty) {
         CK(cudaMemcpyAsync(stt, ctx->d_total, sizeof(stt), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(st, ctx->d_status, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        clk.mark(ctx, "count");
         if (st[0]) { ctx->err = build_err_text(st[0]); return SNAQ_ETOPOLOGY; }
         if (stt[0] >= 0xFFFFFFFFull) { ctx->err = "descriptor table exceeds 2^32 chunks on one GPU: shard the quartets (world_size>1)"; return SNAQ_EINVAL; }
         ctx->prog_words = stt[0] * 4;
@@ -3790,13 +3841,17 @@ static int build_table(snaq_ctx *ctx, const uint8_t *d_dirty) {
         CK(cudaGetLastError());
         ctx->counters[5] += 5;
         ctx->nU = 0;
+        clk.mark(ctx, "sort+emit");
         rc = build_dedup(ctx, pad_at);                     // run table: one program per run of identical programs
         if (rc) return rc;
+        clk.mark(ctx, "runs");
         rc = build_run_tiles(ctx);                         // tiles of the run table (k_eval_runs, run-summed weights)
         if (rc) return rc;
+        clk.mark(ctx, "tiles");
         ctx->has_net = true;
         rc = run_weights(ctx);
         if (rc) { ctx->has_net = false; return rc; }
+        clk.mark(ctx, "weights");
         CK(cudaMemcpyAsync(st, ctx->d_status, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         if (st[0]) { ctx->has_net = false; ctx->err = build_err_text(st[0]); return SNAQ_ETOPOLOGY; }
@@ -3955,7 +4010,7 @@ int snaq_optbl_topologies(snaq_ctx *ctx, int32_t C, const snaq_flatnet *nets, co
     CK(cudaSetDevice(ctx->device));
     const size_t W = (size_t)std::min<int32_t>(workers > 0 ? workers : 8, C);
     while (ctx->workers.size() < W) {
-        snaq_opts o{ctx->device, 0, 1, ctx->dedup ? SNAQ_OPT_DEDUP : 0u};
+        snaq_opts o{ctx->device, 0, 1, ctx->dedup ? SNAQ_OPT_DEDUP : SNAQ_OPT_PER_QUARTET};
         snaq_ctx *wk = nullptr;
         int rc = snaq_create(&o, &wk);
         if (rc) { ctx->err = std::string("worker context: ") + snaq_last_error(nullptr); return rc; }

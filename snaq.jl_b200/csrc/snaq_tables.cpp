@@ -42,6 +42,7 @@ SnaqTables SnaqHostTables::view(const unsigned char *b) const {
     T.blkmax = (const uint16_t *)(b + off_blkmax);
     T.hmax2 = (const uint16_t *)(b + off_hmax2);
     T.hmaxtax = (const uint16_t *)(b + off_hmaxtax);
+    T.leaf_lca = nullptr;
     return T;
 }
 

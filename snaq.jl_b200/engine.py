@@ -73,11 +73,17 @@ def _p(a):
 class Engine:
     """One engine context = one GPU + one stream (``snaq_ctx``)."""
 
-    def __init__(self, device: int = 0, rank: int = 0, world_size: int = 1, dedup: bool = False):
-        """dedup: evaluate each distinct quartet program once with summed weights (SNAQ_OPT_DEDUP, include/snaq_b200.h)"""
+    DEFAULT_DEDUP: Optional[bool] = None     # what dedup=None means (the test suite runs both table modes through it)
+
+    def __init__(self, device: int = 0, rank: int = 0, world_size: int = 1, dedup: Optional[bool] = None):
+        """dedup: None / True = the default run table (each distinct quartet program evaluated once per vector with the
+        summed weights of its quartets); False = the per-quartet kernels (SNAQ_OPT_PER_QUARTET, include/snaq_b200.h)"""
         self.lib = load_library()
         self.ctx = C.c_void_p()
-        opts = _Opts(device, rank, world_size, 1 if dedup else 0)
+        if dedup is None:
+            dedup = Engine.DEFAULT_DEDUP
+        self.per_quartet = dedup is False
+        opts = _Opts(device, rank, world_size, 2 if dedup is False else (1 if dedup else 0))
         rc = self.lib.snaq_create(C.byref(opts), C.byref(self.ctx))
         if rc:
             raise SnaqError(f"snaq_create failed ({rc}): {self.lib.snaq_last_error(None).decode()}")

@@ -96,13 +96,22 @@ int hostsim_run(const snaq_flatnet *f, int ntaxa, int64_t nq, const uint16_t *ta
     int rc = snaq_build_tables(f, ntaxa, H, g_err);
     if (rc) return rc;
     SnaqTables T = H.view(H.blob.data());
+    // the pair table the device fills (k_leaf_lca): the counting pass walks the parent pointers, the emitting pass and a
+    // third, compared word by word, look the six LCAs up
+    std::vector<uint16_t> pair_lca((size_t)ntaxa * ntaxa, 0xFFFF);
+    for (int i = 0; i < ntaxa; i++)
+        for (int j = 0; j < ntaxa; j++)
+            if (T.leaf_tnode[i] != 0xFFFF && T.leaf_tnode[j] != 0xFFFF) pair_lca[(size_t)i * ntaxa + j] = (uint16_t)snaq_lca(T, T.leaf_tnode[i], T.leaf_tnode[j]);
+    SnaqTables TL = T;
+    TL.leaf_lca = pair_lca.data();
     SnaqMath M{g_et, g_li, g_lc};
     std::vector<std::vector<uint16_t>> progs(nq);
     std::vector<uint8_t> hdrs(nq);
+    std::vector<uint16_t> chk;
     for (int64_t q = 0; q < nq; q++) {
         SnaqWriter w{nullptr, 0, 0};
         SnaqQuartetInfo info;
-        uint8_t h1 = 0, h2 = 0;
+        uint8_t h1 = 0, h2 = 0, h3 = 0;
         int e = snaq_build_quartet(T, taxa + 4 * q, w, &h1, &info);
         if (e) { g_err = "build error " + std::to_string(e) + " at quartet " + std::to_string(q); return SNAQ_ETOPOLOGY; }
         const int padded = (w.n + 3) & ~3;
@@ -110,6 +119,11 @@ int hostsim_run(const snaq_flatnet *f, int ntaxa, int64_t nq, const uint16_t *ta
         SnaqWriter w2{progs[q].data(), 0, w.n};
         snaq_build_quartet(T, taxa + 4 * q, w2, &h2, nullptr);
         if (w2.n != w.n || h1 != h2) { g_err = "count/emit mismatch"; return SNAQ_EINVAL; }
+        chk.assign(padded, (uint16_t)H.n_xe);
+        SnaqWriter w3{chk.data(), 0, w.n};
+        if (snaq_build_quartet(TL, taxa + 4 * q, w3, &h3, nullptr) || w3.n != w.n || h3 != h1 || chk != progs[q]) {
+            g_err = "pair-table LCA path differs from the walks at quartet " + std::to_string(q); return SNAQ_EINVAL;
+        }
         hdrs[q] = h1;
         if (proglen) proglen[q] = w.n;
         if (which) which[q] = info.which;

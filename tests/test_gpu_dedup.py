@@ -23,7 +23,7 @@ def pair(n, h, seed, ngenes=80):
     taxa = [f"t{i + 1}" for i in range(n)]
     qt = simulate.all_quartets(n)
     flat = net.flatten(taxa)
-    plain, dd = S.Engine(0), S.Engine(0, dedup=True)
+    plain, dd = S.Engine(0, dedup=False), S.Engine(0, dedup=True)
     for e in (plain, dd):
         e.set_data(S.DataCF(taxa, qt, np.full((len(qt), 3), 1 / 3)))
         e.set_network(flat)
@@ -82,7 +82,7 @@ def test_dedup_at_100_taxa_collapses_the_table():
     net = simulate.random_level1_network(n, 3, 20261021)
     taxa = [f"t{i + 1}" for i in range(n)]
     qt = simulate.all_quartets(n)
-    plain, dd = S.Engine(0), S.Engine(0, dedup=True)
+    plain, dd = S.Engine(0, dedup=False), S.Engine(0, dedup=True)
     rng = np.random.default_rng(3)
     obs = rng.dirichlet([4, 2, 2], size=len(qt))
     for e in (plain, dd):

@@ -9,6 +9,14 @@ from snaq_jl_b200 import simulate
 pytestmark = pytest.mark.gpu
 
 
+
+@pytest.fixture(params=[None, False], ids=["run_table", "per_quartet"], autouse=True)
+def table_mode(request, monkeypatch):
+    """every test of this module runs on the default run table (distinct programs, summed weights) and on the per-quartet
+    kernels (SNAQ_OPT_PER_QUARTET)"""
+    monkeypatch.setattr(S.Engine, "DEFAULT_DEDUP", request.param)
+
+
 def build(n, h, seed, qt=None, ngenes=30):
     net = None
     for attempt in range(30):

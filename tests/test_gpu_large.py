@@ -16,6 +16,13 @@ pytestmark = pytest.mark.gpu
 NSAMPLE = 5000
 
 
+@pytest.fixture(params=[None, False], ids=["run_table", "per_quartet"])
+def table_mode(request, monkeypatch):
+    """the default run table (distinct programs, summed weights) and the per-quartet kernels (SNAQ_OPT_PER_QUARTET)"""
+    monkeypatch.setattr(S.Engine, "DEFAULT_DEDUP", request.param)
+    return request.param
+
+
 def loglik_rows(expcf, obs):
     """logPseudoLik(quartet), src/pseudolik.jl:1388-1410, from expected and observed CFs (numpy restatement)."""
     with np.errstate(divide="ignore", invalid="ignore"):
@@ -51,7 +58,7 @@ def check_against_oracle(oracle, flat, qt, obs, sample, vectors, read_rows, desc
         assert np.max(np.abs(lp[ok] - ref[ok]) / np.maximum(1.0, np.abs(ref[ok]))) <= 1e-10
 
 
-def test_config3_100_taxa_against_oracle(oracle):
+def test_config3_100_taxa_against_oracle(oracle, table_mode):
     n = 100
     net = simulate.random_level1_network(n, 3, 20261021)
     taxa = [f"t{i + 1}" for i in range(n)]
@@ -108,7 +115,7 @@ def table200():
     return net, taxa, qt
 
 
-def test_config5_200_taxa_sharded_against_oracle(oracle, table200):
+def test_config5_200_taxa_sharded_against_oracle(oracle, table200, table_mode):
     """two quartet-sharded contexts (rank 0 and 1 of 2) hold the 64.7 M quartets between them"""
     net, taxa, qt = table200
     flat = net.flatten(taxa)
@@ -173,7 +180,7 @@ def test_config5_gradient_64M_quartets_bad_start(table200):
     nq = len(qt)
     obs = np.full((nq, 3), 1 / 3)
     d = S.DataCF(taxa, qt, obs)
-    eng = S.Engine(0)
+    eng = S.Engine(0, dedup=False)
     eng.set_data(d)
     eng.set_network(flat)
     x0, _, upper = eng.get_params()
@@ -216,7 +223,7 @@ def test_gradient_bins_at_the_corners():
     obs = np.full((len(qt), 3), 1 / 3)
     d = S.DataCF(taxa, qt, obs)
     flat = net.flatten(taxa)
-    eng = S.Engine(0); eng.set_data(d); eng.set_network(flat)
+    eng = S.Engine(0, dedup=False); eng.set_data(d); eng.set_network(flat)
     dd = S.Engine(0, dedup=True); dd.set_data(d); dd.set_network(flat)
     x0, _, upper = eng.get_params()
     x = upper.copy()                                               # every length 10

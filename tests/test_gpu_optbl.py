@@ -14,6 +14,13 @@ from snaq_jl_b200 import simulate
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[None, False], ids=["run_table", "per_quartet"])
+def table_mode(request, monkeypatch):
+    """the default run table (distinct programs, summed weights) and the per-quartet kernels (SNAQ_OPT_PER_QUARTET)"""
+    monkeypatch.setattr(S.Engine, "DEFAULT_DEDUP", request.param)
+    return request.param
+
+
 def make(n, h, seed, ngenes=None):
     net = None
     for attempt in range(30):                                   # small trees cannot always take h reticulations
@@ -37,7 +44,7 @@ def make(n, h, seed, ngenes=None):
 
 
 @pytest.mark.parametrize("seed", range(8))
-def test_gradient_matches_central_differences_of_the_oracle(oracle, seed):
+def test_gradient_matches_central_differences_of_the_oracle(oracle, seed, table_mode):
     n, h = 9 + 2 * seed, seed % 5
     eng, flat, qt, obs, x0, upper = make(n, h, 300 + seed, ngenes=60)
     x = np.clip(simulate.parameter_batch(x0, upper, 4, seed)[2], 1e-3, upper - 1e-3)
@@ -56,10 +63,11 @@ def test_gradient_matches_central_differences_of_the_oracle(oracle, seed):
 
 
 @pytest.mark.parametrize("n,h,seed", [(45, 3, 11), (60, 4, 12)])
-def test_streaming_gradient_kernel_on_large_tables(oracle, n, h, seed):
+def test_streaming_gradient_kernel_on_large_tables(oracle, n, h, seed, monkeypatch):
     """tables with more than 65,536 additive quartets take k_eval_grad (TMA ring, program memo, grid-wide integer bins);
     the deduplicated engine takes the small kernel and the generic path for every entry: two independent routes to the
     same gradient and curvature, plus central differences of the oracle on a few coordinates"""
+    monkeypatch.setattr(S.Engine, "DEFAULT_DEDUP", False)       # per-quartet table for `eng`
     eng, flat, qt, obs, x0, upper = make(n, h, seed, ngenes=80)
     rng = np.random.default_rng(seed)
     mask = (rng.uniform(size=len(qt)) < 0.8).astype(np.uint8)
@@ -98,7 +106,7 @@ def test_streaming_gradient_kernel_on_large_tables(oracle, n, h, seed):
     assert f3 == f and np.array_equal(g3, g)
 
 
-def test_curvature_diagonal_is_the_hessian_diagonal_on_a_tree(oracle):
+def test_curvature_diagonal_is_the_hessian_diagonal_on_a_tree(oracle, table_mode):
     eng, flat, qt, obs, x0, upper = make(12, 0, 41, ngenes=80)
     x = np.clip(x0 * 1.1, 1e-2, upper - 1e-2)
     f, g, hd = eng.eval_grad(x, want_hdiag=True)
@@ -134,7 +142,7 @@ def test_optbl_recovers_the_simulating_parameters_on_perfect_data(seed):
 
 
 @pytest.mark.parametrize("seed", range(4))
-def test_optbl_matches_a_tight_optimisation_of_the_oracle_objective(oracle, seed):
+def test_optbl_matches_a_tight_optimisation_of_the_oracle_objective(oracle, seed, table_mode):
     from scipy.optimize import minimize
     n, h = 8 + seed, seed % 3
     eng, flat, qt, obs, x0, upper = make(n, h, 700 + seed, ngenes=100)

@@ -18,6 +18,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 RTOL_LIK = 1e-10
 
 
+
+@pytest.fixture(params=[None, False], ids=["run_table", "per_quartet"], autouse=True)
+def table_mode(request, monkeypatch):
+    """every test of this module runs on the default run table (distinct programs, summed weights) and on the per-quartet
+    kernels (SNAQ_OPT_PER_QUARTET)"""
+    monkeypatch.setattr(S.Engine, "DEFAULT_DEDUP", request.param)
+
+
 def make_engine(net, taxa, qt, obs, **kw):
     d = S.DataCF(taxa, qt, obs)
     eng = S.Engine(0, **kw)
