@@ -534,7 +534,10 @@ def sharded_leg(S, local, rank, world, dist, torch, flush):
     """BASELINE.json configs[4]: 200 taxa, h=5, 64,684,950 quartets split over the N GPUs (contiguous blocks); every rank
     evaluates the same parameter vectors and the library combines the per-candidate partial sums itself: a fused
     peer-memory epilogue for the single objective call, ncclAllReduce for the batch of 64.  Strong scaling: the table is
-    fixed, N grows.  Timed on the device (CUDA events on the launching stream), max over ranks."""
+    fixed, N grows.  Timed on the device (CUDA events on the launching stream), max over ranks.  Both table modes: the
+    default run table (each rank sums the weights of ITS quartets per distinct program: the evaluation is then a few tens of
+    microseconds on any N, what shards is the table build and the memory) and the per-quartet kernels, where the
+    evaluation itself scales with the shard."""
     n, h = 200, 5
     net = S.simulate.random_level1_network(n, h, 20261022)
     taxa = [f"t{i + 1}" for i in range(n)]
@@ -544,42 +547,52 @@ def sharded_leg(S, local, rank, world, dist, torch, flush):
     obs = rng.random((nq, 3)) + 0.05
     obs /= obs.sum(axis=1, keepdims=True)
     dev = torch.device("cuda", local)
-    eng = S.Engine(local, rank=rank, world_size=world)
-    eng.set_data(S.DataCF(taxa, qt, obs))
-    del obs
-    t0 = time.perf_counter()
-    eng.set_network(net.flatten(taxa))
-    t_build = time.perf_counter() - t0
-    if world > 1:
-        ids = [S.Engine.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        eng.comm_init(ids[0])
-    x0, _, upper = eng.get_params()
-    X = S.simulate.parameter_batch(x0, upper, 64, 5)
+    data = S.DataCF(taxa, qt, obs)
+    flat = net.flatten(taxa)
     out = {"workload": f"200-taxon h={h}, {nq} quartets in {world} contiguous shard(s), same parameter vectors on every rank",
-           "scaling": "strong", "comm": eng.comm_info(), "descriptor_build_s": t_build}
+           "scaling": "strong"}
     stream = torch.cuda.Stream(dev)
-    vals = {}
-    for P in (1, 64):
-        dX = torch.from_numpy(X[:P].copy()).to(dev)
-        dout = torch.zeros(P, dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.barrier()
-        ms = float(timed_launches(torch, eng, dX, dout, stream, None, 20, warm=5).mean())
-        ms = gather_max(dist, torch, world, ms, dev)
-        vals[P] = dout.cpu().numpy().copy()
-        out[f"P{P}"] = {"ms_per_launch": ms, "evals_per_s": nq * P / (ms * 1e-3), "value0": float(vals[P][0])}
+    allvals = []
+    for mode, dd in (("default", None), ("per_quartet", False)):
+        eng = S.Engine(local, rank=rank, world_size=world, dedup=dd)
+        eng.set_data(data)
         t0 = time.perf_counter()
-        for _ in range(10):
-            eng.eval(X[:P])
-        out[f"P{P}"]["host_call_ms"] = gather_max(dist, torch, world, (time.perf_counter() - t0) / 10 * 1e3, dev)
-    eng.check_status()
-    if world > 1:
-        mine = np.concatenate([vals[1], vals[64]]).tobytes()
-        allv = [None] * world
-        dist.all_gather_object(allv, mine)
-        out["identical_on_all_ranks"] = all(b == allv[0] for b in allv)
-    out["P1_equals_P64_row0_rel"] = float(abs(vals[1][0] - vals[64][0]) / abs(vals[64][0]))
+        eng.set_network(flat)
+        t_build = time.perf_counter() - t0
+        if world > 1:
+            ids = [S.Engine.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            eng.comm_init(ids[0])
+        x0, _, upper = eng.get_params()
+        X = S.simulate.parameter_batch(x0, upper, 64, 5)
+        res = {"comm": eng.comm_info(), "descriptor_build_s": gather_max(dist, torch, world, t_build, dev),
+               "distinct_programs_rank0": int(eng.counters()["distinct_programs"])}
+        vals = {}
+        for P in (1, 64):
+            dX = torch.from_numpy(X[:P].copy()).to(dev)
+            dout = torch.zeros(P, dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.barrier()
+            ms = float(timed_launches(torch, eng, dX, dout, stream, None, 20, warm=5).mean())
+            ms = gather_max(dist, torch, world, ms, dev)
+            vals[P] = dout.cpu().numpy().copy()
+            res[f"P{P}"] = {"ms_per_launch": ms, "evals_per_s": nq * P / (ms * 1e-3), "value0": float(vals[P][0])}
+            t0 = time.perf_counter()
+            for _ in range(10):
+                eng.eval(X[:P])
+            res[f"P{P}"]["host_call_ms"] = gather_max(dist, torch, world, (time.perf_counter() - t0) / 10 * 1e3, dev)
+        eng.check_status()
+        if world > 1:
+            mine = np.concatenate([vals[1], vals[64]]).tobytes()
+            allv = [None] * world
+            dist.all_gather_object(allv, mine)
+            res["identical_on_all_ranks"] = all(b == allv[0] for b in allv)
+        res["P1_equals_P64_row0_rel"] = float(abs(vals[1][0] - vals[64][0]) / abs(vals[64][0]))
+        allvals.append(vals[64])
+        out[mode] = res
+        del eng
+        torch.cuda.empty_cache()
+    out["max_rel_diff_default_vs_per_quartet"] = float(np.max(np.abs(allvals[0] - allvals[1]) / np.abs(allvals[1])))
     return out
 
 

@@ -29,3 +29,8 @@ print("patch_network ms (touched taxa):", " ".join(f"{a:.2f}({b})" for a, b in t
 os.environ["SNAQ_BUILD_TIMING"] = "1"
 eng.set_network(fl)
 eng.set_network(fl)
+for _ in range(4):
+    tok = S.simulate.nni_move(net, rng)
+    t0 = time.perf_counter()
+    touched = eng.patch_network(net.flatten(taxa))
+    print("patch with stage timing: touched", touched, "ms", (time.perf_counter() - t0) * 1e3)

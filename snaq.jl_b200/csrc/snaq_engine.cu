@@ -152,27 +152,90 @@ __global__ void __launch_bounds__(256) k_leaf_lca(SnaqTables T, uint16_t *__rest
     const int u = T.leaf_tnode[i], v = T.leaf_tnode[j];
     out[idx] = (u == 0xFFFF || v == 0xFFFF) ? (uint16_t)0xFFFF : (uint16_t)snaq_lca(T, u, v);
 }
+// snaq_patch_network: the quartets that hold a flagged taxon, as a dense list (their order does not matter: every result is
+// stored by quartet index); the others keep their length, sort key, staged program and header and only enter the
+// statistics (stats as in k_build_count)
+__global__ void __launch_bounds__(256) k_dirty_list(const uint16_t *__restrict__ taxa, int64_t nq, const uint8_t *__restrict__ dirty_taxon,
+                                                    const uint32_t *__restrict__ len4, const uint32_t *__restrict__ cls,
+                                                    uint32_t *__restrict__ list, uint32_t *__restrict__ nlist,
+                                                    unsigned long long *__restrict__ stats) {
+    // a block takes 1024 consecutive quartets (four per thread) and one contiguous piece of the list: one atomic per block
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ unsigned long long ssum[8];
+    __shared__ unsigned smax[8], scnt[5], wcnt[32], wbase[32];
+    if (threadIdx.x < 5) scnt[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long s = 0;
+    unsigned mx = 0, mk[4];
+    bool dirty[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int64_t q = (int64_t)blockIdx.x * 1024 + k * 256 + threadIdx.x;
+        dirty[k] = false;
+        unsigned n = 0, c = 5;
+        if (q < nq) {
+            uint16_t tx[4];
+            load_taxa(taxa, q, tx);
+            dirty[k] = (dirty_taxon[tx[0]] | dirty_taxon[tx[1]] | dirty_taxon[tx[2]] | dirty_taxon[tx[3]]) != 0;
+            if (!dirty[k]) { n = len4[q]; c = cls[q] >> 28; }
+        }
+        mk[k] = __ballot_sync(0xffffffffu, dirty[k]);
+        if (lane == 0) wcnt[k * 8 + warp] = (unsigned)__popc(mk[k]);
+        if (c < 5) atomicAdd(&scnt[c], 1u);
+        s += n;
+        mx = max(mx, n);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int k = 0; k < 32; k++) { wbase[k] = t; t += wcnt[k]; }
+        const unsigned b0 = t ? atomicAdd(nlist, t) : 0u;
+        for (int k = 0; k < 32; k++) wbase[k] += b0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (dirty[k]) list[wbase[k * 8 + warp] + __popc(mk[k] & ((1u << lane) - 1u))] = (uint32_t)((int64_t)blockIdx.x * 1024 + k * 256 + threadIdx.x);
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, o);
+        mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { ssum[warp] = s; smax[warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        unsigned tm = 0;
+        for (int k = 0; k < 8; k++) { t += ssum[k]; tm = max(tm, smax[k]); }
+        if (t) atomicAdd(&stats[0], t);
+        if (tm) atomicMax(&stats[1], (unsigned long long)tm);
+        for (int k = 0; k < 5; k++) if (scnt[k]) atomicAdd(&stats[2 + k], (unsigned long long)scnt[k]);
+    }
+}
+
 __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_t *__restrict__ taxa, int64_t nq, const int dedup,
                                                      uint32_t *__restrict__ len4, uint32_t *__restrict__ cls,
                                                      uint32_t *__restrict__ iota, unsigned long long *__restrict__ stats,
-                                                     uint32_t *__restrict__ status, const uint8_t *__restrict__ dirty_taxon,
+                                                     uint32_t *__restrict__ status, const uint32_t *__restrict__ list,
+                                                     const uint32_t *__restrict__ nlist,
                                                      uint16_t *__restrict__ stage, uint8_t *__restrict__ hdr0) {
     // stats: [0] total chunks, [1] max chunks, [2..6] quartets per sort class
     // sort classes: 0 = class A with a one-chunk program, 1 = class A with two chunks, 2 = longer class A,
     //               3 = class B, 4 = class C
     // stage / hdr0 (original quartet order): the first SNAQ_STAGE_WORDS words of the program, NULL padded, and the header
     // byte: k_build_emit copies short programs from there instead of deriving them a second time.
-    // dirty_taxon (snaq_patch_network): only quartets with a flagged taxon are re-described; the others keep the length,
+    // list / nlist (snaq_patch_network, k_dirty_list): only the listed quartets are re-described; the others keep the length,
     // sort key, staged program and header of the previous topology (their root paths and blocks have not changed).
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (list) {                                                // k_dirty_list's quartets only (the grid covers the whole table)
+        const uint32_t nl = *nlist;
+        if ((int64_t)blockIdx.x * blockDim.x >= (int64_t)nl) return;
+        q = q < (int64_t)nl ? (int64_t)list[q] : nq;
+    }
     unsigned n = 0, c = 5;
     if (q < nq) {
         uint16_t tx[4];
         load_taxa(taxa, q, tx);
-        if (dirty_taxon && !(dirty_taxon[tx[0]] | dirty_taxon[tx[1]] | dirty_taxon[tx[2]] | dirty_taxon[tx[3]])) {
-            n = len4[q];
-            c = cls[q] >> 28;
-        } else {
+        {
         uint16_t head[24];                                     // the first words of the program: enough for the term key
         SnaqWriter w{head, 0, 24};
         uint8_t hdr = 0;
@@ -231,8 +294,9 @@ __global__ void __launch_bounds__(128) k_build_count(SnaqTables T, const uint16_
     if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = s; smax[threadIdx.x >> 5] = m; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        atomicAdd(&stats[0], ssum[0] + ssum[1] + ssum[2] + ssum[3]);
-        atomicMax(&stats[1], (unsigned long long)max(max(smax[0], smax[1]), max(smax[2], smax[3])));
+        const unsigned long long t = ssum[0] + ssum[1] + ssum[2] + ssum[3];
+        if (t) atomicAdd(&stats[0], t);
+        if (t) atomicMax(&stats[1], (unsigned long long)max(max(smax[0], smax[1]), max(smax[2], smax[3])));
         for (int k = 0; k < 5; k++) if (scnt[k]) atomicAdd(&stats[2 + k], (unsigned long long)scnt[k]);
     }
 }
@@ -2825,6 +2889,7 @@ struct snaq_ctx {
     bool sv_dedup = true;                 // single-vector paths (one objective call, gradient pass, optBL!) walk the compressed table
                                           // with run-summed weights (SNAQ_SV_DEDUP=0: the per-quartet table, as the batched path)
     uint32_t rn_ntiles = 0, rn_nseg = 0, rn_tps = 1, rn_ntAB = 0;
+    bool pack_on = false;                 // the packed tile stream of k_eval_runs exists (per-quartet mode, SNAQ_RUNS != 0)
     uint32_t *d_status = nullptr;          // [0] build, [1] eval
     unsigned long long *d_trace = nullptr; // SNAQ_TRACE=1: [blocks][8] phase timestamps of the last k_eval_direct launch
     int trace_blocks = 0;
@@ -2850,6 +2915,7 @@ struct snaq_ctx {
     bool reuse = true;                    // SNAQ_REUSE=0: the batched kernels evaluate every quartet in full (measurement aid)
     int lanes_chunk = 256;                // quartets per block of k_eval_lanes (SNAQ_LANES_CHUNK)
     int lanes_warps = 8;                  // warps per block of k_eval_lanes (SNAQ_LANES_WARPS = 8, 12 or 16)
+    bool lanes_warps_set = false;
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // snaq_optbl_topologies: worker contexts on the same device, each with a copy of this context's data
     uint64_t data_version = 1;            // bumped by snaq_set_data / snaq_set_obscf / snaq_set_sampled
@@ -2922,11 +2988,15 @@ static cudaError_t wait_done(cudaStream_t stream, volatile uint32_t *flag) {
 
 template <class T> static int ensure(snaq_ctx *ctx, T *&p, size_t &cap, size_t need) {
     if (need <= cap && p) return SNAQ_OK;
+    const bool regrow = p != nullptr;
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
-    size_t n = std::max<size_t>(need, 16);
+    // a buffer that has to grow gets 25 % headroom: candidate topologies of a search differ a little in every size, and a
+    // cudaFree + cudaMalloc pair costs more than the whole table build
+    size_t n = std::max<size_t>(regrow ? need + need / 4 : need, 16);
     cudaError_t e = cudaMalloc((void **)&p, n * sizeof(T));
+    if (e != cudaSuccess && n > need) { n = std::max<size_t>(need, 16); e = cudaMalloc((void **)&p, n * sizeof(T)); }
     if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return SNAQ_ENOMEM; }
     cap = n;
     return SNAQ_OK;
@@ -3038,7 +3108,7 @@ static int run_weights(snaq_ctx *ctx) {
     int64_t nb = (ctx->nq + 255) / 256;
     k_weights<<<(unsigned)nb, 256, 0, ctx->stream>>>(ctx->d_perm, ctx->d_qhdr, ctx->d_obs, ctx->has_sampled ? ctx->d_sampled : nullptr, ctx->nq,
                                                     ctx->nA1 + ctx->nA2, ctx->nA + ctx->nB, ctx->d_W, ctx->d_WA, ctx->d_wpart,
-                                                    ctx->d_rec_off, ctx->rn_ntAB, (ctx->runs_on && ctx->rn_ntiles > 0) ? ctx->d_pack : nullptr);
+                                                    ctx->d_rec_off, ctx->rn_ntAB, (ctx->pack_on && ctx->rn_ntiles > 0) ? ctx->d_pack : nullptr);
     CK(cudaGetLastError());
     k_reduce_partials<<<2, 256, 0, ctx->stream>>>(ctx->d_wpart, (int)nb, 2, 2, ctx->d_negw3);
     CK(cudaGetLastError());
@@ -3102,10 +3172,8 @@ static int build_dedup(snaq_ctx *ctx, int64_t pad_at) {
     CK(cudaMemsetAsync(ctx->d_off_u, 0, sizeof(uint32_t), ctx->stream));
     t1 = ctx->scan_tmp_cap;
     CK(cub::DeviceScan::InclusiveSum(ctx->d_scan_tmp, t1, ctx->d_ulen, ctx->d_off_u + 1, nu, ctx->stream));
-    uint32_t total = 0;
-    CK(cudaMemcpyAsync(&total, ctx->d_off_u + nu, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->prog_u_words = (uint64_t)total * 4;
+    // no run is longer than the longest program (+ the one pad chunk): the bound saves a wait for the exact total
+    ctx->prog_u_words = ((uint64_t)nu * ctx->maxlen + 1) * 4;
     int rc = ensure(ctx, ctx->d_prog_u, ctx->prog_u_cap, (size_t)ctx->prog_u_words + 8);
     if (rc) return rc;
     k_dedup_copy<<<(unsigned)((nu + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_rstart, ctx->d_off, prog2, ctx->d_off_u, nu, pad_u,
@@ -3131,18 +3199,23 @@ static int build_run_tiles(snaq_ctx *ctx) {
     k_run_tiles<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_flags, ctx->d_uidx, ctx->d_off_u, ctx->nq, nAB, (uint32_t)ntAB,
                                                                       (uint32_t)nt, ctx->d_tdesc, ctx->d_rec_off + 1);
     CK(cudaGetLastError());
-    CK(cudaMemsetAsync(ctx->d_rec_off, 0, sizeof(uint32_t), ctx->stream));
     size_t t1 = ctx->scan_tmp_cap;
-    CK(cub::DeviceScan::InclusiveSum(ctx->d_scan_tmp, t1, ctx->d_rec_off + 1, ctx->d_rec_off + 1, nt, ctx->stream));
-    uint32_t total16 = 0;
-    CK(cudaMemcpyAsync(&total16, ctx->d_rec_off + nt, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if ((uint64_t)nt * (RN_STAGE_BYTES / 16) >= 0xffffffffull) { ctx->err = "packed tile stream exceeds 64 GB: shard the quartets (world_size>1)"; return SNAQ_EINVAL; }
-    rc = ensure(ctx, ctx->d_pack, ctx->pack_cap, (size_t)total16 * 16 + 16);
-    if (rc) return rc;
-    k_run_fill<<<(unsigned)((nt * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_tdesc, ctx->d_rec_off, ctx->d_off_u,
-                                                                          reinterpret_cast<const uint2 *>(ctx->d_prog_u), (uint32_t)nt, ctx->d_pack);
-    CK(cudaGetLastError());
+    ctx->pack_on = ctx->runs_on && !ctx->dedup;
+    if (ctx->pack_on) {
+        // the packed stream k_eval_runs reads (per-quartet weights + programs per tile); the run table of the default mode
+        // needs only the tile descriptors (run-summed weights)
+        CK(cudaMemsetAsync(ctx->d_rec_off, 0, sizeof(uint32_t), ctx->stream));
+        CK(cub::DeviceScan::InclusiveSum(ctx->d_scan_tmp, t1, ctx->d_rec_off + 1, ctx->d_rec_off + 1, nt, ctx->stream));
+        uint32_t total16 = 0;
+        CK(cudaMemcpyAsync(&total16, ctx->d_rec_off + nt, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if ((uint64_t)nt * (RN_STAGE_BYTES / 16) >= 0xffffffffull) { ctx->err = "packed tile stream exceeds 64 GB: shard the quartets (world_size>1)"; return SNAQ_EINVAL; }
+        rc = ensure(ctx, ctx->d_pack, ctx->pack_cap, (size_t)total16 * 16 + 16);
+        if (rc) return rc;
+        k_run_fill<<<(unsigned)((nt * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_tdesc, ctx->d_rec_off, ctx->d_off_u,
+                                                                              reinterpret_cast<const uint2 *>(ctx->d_prog_u), (uint32_t)nt, ctx->d_pack);
+        CK(cudaGetLastError());
+    }
     // first (tile, run) partial of every tile: exclusive scan of the tiles' run counts; their total is at most nt + nU
     rc = ensure(ctx, ctx->d_pidx, ctx->pidx_cap, (size_t)nt + 2);
     if (rc) return rc;
@@ -3235,10 +3308,11 @@ static int eval_device_local(snaq_ctx *ctx, int P, const double *dX, double *dou
     if (ctx->nq == 0) { CK(cudaMemsetAsync(dout, 0, sizeof(double) * P, stream)); return SNAQ_OK; }
     const bool per_quartet = expcf || logpl || deltacf;
     const EvalTable tb = eval_table(ctx, per_quartet);
+    const bool compressed_tb = use_compressed(ctx, per_quartet, false);
     const int64_t nq = tb.nq;
     const bool use_lanes = P >= LANES_MIN_P && !per_quartet;
     if (use_lanes) {
-        if (ctx->runs_on && !ctx->dedup && ctx->rn_ntiles > 0 &&
+        if (ctx->pack_on && ctx->rn_ntiles > 0 &&
             (ctx->runs_on > 1 || ctx->nq >= (int64_t)RN_MIN_AVG_RUN * std::max<int64_t>(ctx->nU, 1))) {
             // run-length kernel: programs evaluated once per run of identical programs, weights streamed per quartet
             RunsMeta rm;
@@ -3332,7 +3406,9 @@ static int eval_device_local(snaq_ctx *ctx, int P, const double *dX, double *dou
         // (200 taxa, P = 64: 31.2 -> 16.9 ms; 100 taxa, P = 256: 339 -> 383 G evals/s).  With small tiles the
         // one-block-per-chunk kernel is faster (config 2: 329 vs 254 G evals/s): more, independent blocks per SM.
         const bool big_tile = lanesp_smem_layout(H.n_full, 64, 8, ctx->maxlen).total > 110 * 1024;
-        const bool mid_tile = (size_t)H.n_full * 256 >= 48 * 1024;      // ~100 taxa: the tile reload is most of the L2 traffic
+        // ~100 taxa: the tile reload is most of the L2 traffic -- of a long table; a run table of a few thousand programs is
+        // faster with one block per (chunk, group) (100 taxa, 9,419 programs, P = 256: 0.043 vs 0.052 ms per step)
+        const bool mid_tile = (size_t)H.n_full * 256 >= 48 * 1024 && nq >= 262144;
         if (ctx->lanes_persistent == 1 ? (big_tile || mid_tile) : ctx->lanes_persistent > 1) {
             // persistent blocks: the xf tile stays in shared memory, chunks stream through two TMA stages; 16 warps per block
             int warps = big_tile ? 16 : ctx->lanes_warps, chunk = 256;
@@ -3369,7 +3445,8 @@ static int eval_device_local(snaq_ctx *ctx, int P, const double *dX, double *dou
             return SNAQ_OK;
         }
         // one block per (chunk, group): quartets per block.  Enough blocks to fill the machine, bounded by shared memory.
-        const int warps = ctx->lanes_warps;
+        // run table (every entry a different program: no reuse between neighbours, long dependent chains of exp / log): 16 warps
+        const int warps = (compressed_tb && !ctx->lanes_warps_set) ? 16 : ctx->lanes_warps;
         int chunk = ctx->lanes_chunk;
         while (chunk > 64 && (int64_t)ngroups * ((nq + chunk - 1) / chunk) < (int64_t)ctx->sm_count * 8) chunk >>= 1;
         while (chunk > 32 && lanes_smem_layout(H.n_full, chunk, warps, ctx->maxlen).total > 200 * 1024) chunk >>= 1;
@@ -3465,7 +3542,7 @@ int snaq_create(const snaq_opts *opts, snaq_ctx **out) {
     if (const char *ev = getenv("SNAQ_SV_DEDUP")) ctx->sv_dedup = atoi(ev) != 0;
     if (const char *ev = getenv("SNAQ_LANES_CHUNK")) { int v = atoi(ev); if (v == 128 || v == 256 || v == 512 || v == 1024) ctx->lanes_chunk = v; }
     if (const char *ev = getenv("SNAQ_LANES_PERSISTENT")) ctx->lanes_persistent = atoi(ev);
-    if (const char *ev = getenv("SNAQ_LANES_WARPS")) { int v = atoi(ev); if (v == 8 || v == 12 || v == 16) ctx->lanes_warps = v; }
+    if (const char *ev = getenv("SNAQ_LANES_WARPS")) { int v = atoi(ev); if (v == 8 || v == 12 || v == 16) { ctx->lanes_warps = v; ctx->lanes_warps_set = true; } }
     if ((e = cudaMalloc((void **)&ctx->d_status, 4 * sizeof(uint32_t))) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cudaMalloc((void **)&ctx->d_total, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
     cudaMemset(ctx->d_status, 0, 4 * sizeof(uint32_t));
@@ -3797,8 +3874,16 @@ static int build_table(snaq_ctx *ctx, const uint8_t *d_dirty) {
         CK(cudaMemsetAsync(ctx->d_total, 0, 8 * sizeof(unsigned long long), ctx->stream));
         CK(cudaMemsetAsync(ctx->d_status, 0, 4 * sizeof(uint32_t), ctx->stream));
         const int64_t nb = (nq + 127) / 128;
+        const uint32_t *d_list = nullptr, *d_nlist = nullptr;
+        if (d_dirty) {
+            // (d_perm is rebuilt by the sort below: until then it holds the list; d_total[7] its length)
+            d_list = ctx->d_perm; d_nlist = reinterpret_cast<const uint32_t *>(ctx->d_total + 7);
+            k_dirty_list<<<(unsigned)((nq + 1023) / 1024), 256, 0, ctx->stream>>>(ctx->d_taxa, nq, d_dirty, ctx->d_len4, ctx->d_cls, ctx->d_perm,
+                                                                                reinterpret_cast<uint32_t *>(ctx->d_total + 7), ctx->d_total);
+            CK(cudaGetLastError());
+        }
         k_build_count<<<(unsigned)nb, 128, 0, ctx->stream>>>(ctx->T, ctx->d_taxa, nq, ctx->dedup ? 1 : 0, ctx->d_len4, ctx->d_cls, ctx->d_iota,
-                                                            ctx->d_total, ctx->d_status, d_dirty, ctx->d_stage, ctx->d_hdr0);
+                                                            ctx->d_total, ctx->d_status, d_list, d_nlist, ctx->d_stage, ctx->d_hdr0);
         CK(cudaGetLastError());
         unsigned long long stt[7] = {0, 0, 0, 0, 0, 0, 0};
         uint32_t st[4];
