@@ -23,7 +23,7 @@ struct FlatNet            # mirrors `snaq_flatnet` field for field
     edge_gamma::Ptr{Cdouble}; edge_node::Ptr{Cint}
     hybrid::Ptr{Cint}; leaf::Ptr{Cint}
 end
-struct Opts; device::Cint; rank::Cint; world_size::Cint; flags::Cuint; end     # flags: 1 = program deduplication
+struct Opts; device::Cint; rank::Cint; world_size::Cint; flags::Cuint; end     # flags: 2 = SNAQ_OPT_PER_QUARTET (default 0: run table)
 
 mutable struct Engine
     ctx::Ptr{Cvoid}
@@ -36,9 +36,9 @@ end
 check(e::Engine, rc) = rc == 0 || error(unsafe_string(ccall((:snaq_last_error, LIB), Cstring, (Ptr{Cvoid},), e.ctx)))
 
 "one engine per Julia worker process; worker i uses GPU (i-1) % ngpus (pmap over runs: src/snaq_optimization.jl:1681)"
-function Engine(d::DataCF; device::Integer = (Distributed.myid() - 1) % 8, dedup::Bool = false, rank::Integer = 0, world_size::Integer = 1)
-    ctx = Ref{Ptr{Cvoid}}(C_NULL)   # dedup: evaluate each distinct quartet program once with summed weights (SNAQ_OPT_DEDUP)
-    rc = ccall((:snaq_create, LIB), Cint, (Ref{Opts}, Ref{Ptr{Cvoid}}), Opts(device, rank, world_size, dedup ? 1 : 0), ctx)
+function Engine(d::DataCF; device::Integer = (Distributed.myid() - 1) % 8, per_quartet::Bool = false, rank::Integer = 0, world_size::Integer = 1)
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)   # per_quartet: the per-quartet kernels instead of the run table with run-summed weights (include/snaq_b200.h)
+    rc = ccall((:snaq_create, LIB), Cint, (Ref{Opts}, Ref{Ptr{Cvoid}}), Opts(device, rank, world_size, per_quartet ? 2 : 0), ctx)
     rc == 0 || error(unsafe_string(ccall((:snaq_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
     taxa = SNaQ.tiplabels(d)                               # src/readquartetdata.jl:440
     tid = Dict(t => UInt16(i - 1) for (i, t) in enumerate(taxa))

@@ -108,3 +108,46 @@ def readtableCF(path: str, delim: str = ",") -> DataCF:
             row.append(r[cn])
         rows.append(row)
     return DataCF.from_rows(rows)
+
+
+# ---- read-back tables (src/descriptive.jl:24-59, src/readquartetdata.jl:4-14) -------------------------------------------
+def fittedquartetCF(d: DataCF, format: str = "wide") -> dict:
+    """Observed and expected CFs after a fit, as columns (a dict of equal-length lists / arrays in the reference's column
+    order).  ``d.expCF`` is what ``Engine.eval_quartets`` / ``topologyQpseudolik_`` left there (q.qnet.expCF).
+    wide: tx1..tx4, obsCF12, obsCF13, obsCF14, expCF12, expCF13, expCF14 (one row per four-taxon set);
+    long: tx1..tx4, quartet ("12_34", "13_24", "14_23"), obsCF, expCF (three rows per four-taxon set)."""
+    if d.expCF is None:
+        raise SnaqError("expected CFs have not been calculated: evaluate the network on this DataCF first")
+    names = [[d.taxa[t] for t in col] for col in d.quartet_taxa.T]
+    if format == "wide":
+        out = {f"tx{k + 1}": names[k] for k in range(4)}
+        for j, s in enumerate(("12", "13", "14")):
+            out["obsCF" + s] = d.obsCF[:, j].copy()
+        for j, s in enumerate(("12", "13", "14")):
+            out["expCF" + s] = d.expCF[:, j].copy()
+        return out
+    if format == "long":
+        nq = d.numQuartets
+        out = {f"tx{k + 1}": [v for v in names[k] for _ in range(3)] for k in range(4)}
+        out["quartet"] = ["12_34", "13_24", "14_23"] * nq
+        out["obsCF"] = d.obsCF.reshape(-1).copy()
+        out["expCF"] = d.expCF.reshape(-1).copy()
+        return out
+    raise SnaqError(f"format {format} was not recognized. Should be :wide or :long.")
+
+
+def writeExpCF(d: DataCF, path: Optional[str] = None, delim: str = ",") -> dict:
+    """The expected CFs as the table readtableCF reads back: t1..t4, CF12_34, CF13_24, CF14_23 (src/readquartetdata.jl:4-14);
+    written as CSV when ``path`` is given."""
+    if d.expCF is None:
+        raise SnaqError("expected CFs have not been calculated: evaluate the network on this DataCF first")
+    cols = {f"t{k + 1}": [d.taxa[t] for t in d.quartet_taxa[:, k]] for k in range(4)}
+    for j, s in enumerate(("CF12_34", "CF13_24", "CF14_23")):
+        cols[s] = d.expCF[:, j].copy()
+    if path is not None:
+        with open(path, "w", newline="") as fh:
+            w = csv.writer(fh, delimiter=delim)
+            w.writerow(list(cols))
+            for i in range(d.numQuartets):
+                w.writerow([cols[f"t{k + 1}"][i] for k in range(4)] + [repr(float(cols[s][i])) for s in ("CF12_34", "CF13_24", "CF14_23")])
+    return cols
