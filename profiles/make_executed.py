@@ -1,7 +1,7 @@
 """Turns the committed ncu captures of bench.py's timed kernels into profiles/r02_executed_flops.json: per launch, the
 thread-level DFMA / DADD / DMUL instruction counts (executed double-precision flops = 2 DFMA + DADD + DMUL), DRAM bytes and
 the FP64-pipe activity.  bench.py divides these by the launch time it measures live.
-Usage: python profiles/make_executed.py  (reads gpurun_out/r02m_*.ncu-rep)"""
+Usage: python profiles/make_executed.py [tag]  (reads gpurun_out/<tag>_*.ncu-rep written by profiles/capture.sh)"""
 import csv, io, json, subprocess, sys
 
 def raw(rep):
@@ -20,9 +20,12 @@ def f(hdr, row, units, k):
     if u == "ns": v *= 1e-9
     return v
 
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r02t"
 out = {}
-for key, rep in (("config2", "gpurun_out/r02m_lanes_config2.ncu-rep"), ("north_star", "gpurun_out/r02m_runs_northstar.ncu-rep"),
-                 ("hbm_p1", "gpurun_out/r02m_direct_p1.ncu-rep")):
+for key, rep in (("config2", f"gpurun_out/{TAG}_default_config2.ncu-rep"), ("north_star", f"gpurun_out/{TAG}_default_northstar.ncu-rep"),
+                 ("config2_per_quartet", f"gpurun_out/{TAG}_perq_config2.ncu-rep"),
+                 ("north_star_per_quartet", f"gpurun_out/{TAG}_perq_northstar.ncu-rep"),
+                 ("hbm_p1", f"gpurun_out/{TAG}_direct_p1.ncu-rep")):
     hdr, units, row = raw(rep)
     g = lambda k: f(hdr, row, units, k)
     out[key] = {"kernel": row[hdr.index("Kernel Name")][:80], "grid": row[hdr.index("launch__grid_size")],
@@ -32,6 +35,6 @@ for key, rep in (("config2", "gpurun_out/r02m_lanes_config2.ncu-rep"), ("north_s
                 "fp64_pipe_pct": g("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
                 "issue_active_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                 "warp_inst": g("smsp__inst_executed.sum"), "ncu_duration_s": g("gpu__time_duration.sum"),
-                "source": "profiles/" + rep.split("/")[-1].replace(".ncu-rep", "") + " (ncu --set full of `python bench.py`, see profiles/r02_ncu_summary.md)"}
+                "source": rep.split("/")[-1].replace(".ncu-rep", "") + ": ncu --set full capture by profiles/capture.sh, summarised in profiles/" + TAG + "_ncu_summary.md"}
 json.dump(out, open("profiles/r02_executed_flops.json", "w"), indent=1)
 print(json.dumps(out, indent=1))

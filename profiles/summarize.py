@@ -104,9 +104,14 @@ with open(f"profiles/{tag}_ncu_summary.md", "w") as fh:
     import os
     fh.write(f"# ncu summaries ({tag})\n\nCommand profiled: `python bench.py --steps 2 --warmup 3 --no-sharded --no-search --no-cpu-baseline` on one B200 "
              "(`--clock-control none`; per-launch times are cold-cache and serialised: compare shares, not absolutes).\n\n")
-    fh.write("## launch list (`ncu --metrics gpu__time_duration.sum -c 600`)\n\n")
+    fh.write("## launch list (`ncu --metrics gpu__time_duration.sum`)\n\n")
     launches(f"{GO}/{tag}_launches.csv", fh)
-    for suffix, title in (("lanes", "k_eval_lanes (config 2: 27,405 quartets x 4096 vectors)"),
+    for suffix, title in (("default_config2", "DEFAULT (run table) k_eval_lanes, config 2: 27,405 quartets = 1,290 programs x 4096 vectors; the main line of bench.py"),
+                          ("default_northstar", "DEFAULT (run table) k_eval_lanes, north star: 100 taxa, 3,921,225 quartets = 9,430 programs x 256 vectors; bench.py `north_star`"),
+                          ("perq_config2", "PER-QUARTET k_eval_lanes, config 2: 27,405 quartets x 4096 vectors; bench.py `per_quartet.config2`"),
+                          ("perq_northstar", "PER-QUARTET k_eval_runs, north star: 3,921,225 quartets x 256 vectors; bench.py `per_quartet.north_star`"),
+                          ("build_count", "k_build_count (descriptor build, 100 taxa, 3,921,225 quartets)"),
+                          ("lanes", "k_eval_lanes (config 2: 27,405 quartets x 4096 vectors)"),
                           ("lanes_config2", "k_eval_lanes (config 2: 27,405 quartets x 4096 vectors; the main line of bench.py)"),
                           ("runs_northstar", "k_eval_runs (north star: 100 taxa, 3,921,225 quartets x 256 vectors; bench.py `north_star`)"),
                           ("direct_p1", "k_eval_direct (100 taxa, 3.92 M quartets, P = 1, per-quartet table; bench.py `roofline_hbm`)"),
