@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--cpu-vectors", type=int, default=4096, help="parameter vectors of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm", action="store_true", help="skip the secondary single-GPU legs (north star, P=1, dedup, candidates)")
+    ap.add_argument("--no-candidates", action="store_true", help="skip the concurrent-candidates leg (thousands of small launches)")
     ap.add_argument("--no-sharded", action="store_true", help="skip the 200-taxon quartet-sharded leg")
     ap.add_argument("--no-search", action="store_true", help="skip the search-chain and bootstrap legs")
     args = ap.parse_args()
@@ -330,6 +331,8 @@ def main():
                                                                  evals_per_step, peak_tf, flop_per_eval)),
                          ("roofline_hbm", lambda: hbm_leg(S, eng.__class__, local, torch)),
                          ("candidates", lambda: candidates_leg(S, eng, taxa, qt, obs))):
+            if name == "candidates" and args.no_candidates:
+                continue
             try:
                 line[name] = fn()
             except Exception as exc:  # noqa: BLE001

@@ -36,5 +36,6 @@ for key, rep in (("config2", f"gpurun_out/{TAG}_default_config2.ncu-rep"), ("nor
                 "issue_active_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                 "warp_inst": g("smsp__inst_executed.sum"), "ncu_duration_s": g("gpu__time_duration.sum"),
                 "source": rep.split("/")[-1].replace(".ncu-rep", "") + ": ncu --set full capture by profiles/capture.sh, summarised in profiles/" + TAG + "_ncu_summary.md"}
-json.dump(out, open("profiles/r02_executed_flops.json", "w"), indent=1)
+import os
+json.dump(out, open(os.path.join(os.environ.get("SNAQ_PROFILE_OUT", "profiles"), "r02_executed_flops.json"), "w"), indent=1)
 print(json.dumps(out, indent=1))

@@ -100,9 +100,10 @@ def launches(path, fh):
     fh.write("\n")
 
 
-with open(f"profiles/{tag}_ncu_summary.md", "w") as fh:
-    import os
-    fh.write(f"# ncu summaries ({tag})\n\nCommand profiled: `python bench.py --steps 2 --warmup 3 --no-sharded --no-search --no-cpu-baseline` on one B200 "
+import os
+OUTDIR = os.environ.get("SNAQ_PROFILE_OUT", "profiles")
+with open(f"{OUTDIR}/{tag}_ncu_summary.md", "w") as fh:
+    fh.write(f"# ncu summaries ({tag})\n\nCommand profiled: `python bench.py --steps 2 --warmup 3 --no-sharded --no-search --no-cpu-baseline --no-candidates` on one B200 "
              "(`--clock-control none`; per-launch times are cold-cache and serialised: compare shares, not absolutes).\n\n")
     fh.write("## launch list (`ncu --metrics gpu__time_duration.sum`)\n\n")
     launches(f"{GO}/{tag}_launches.csv", fh)
@@ -120,4 +121,4 @@ with open(f"profiles/{tag}_ncu_summary.md", "w") as fh:
                           ("direct", "k_eval_direct (100 taxa, 3.92 M quartets, P=1)")):
         if os.path.exists(f"{GO}/{tag}_{suffix}.ncu-rep"):
             kernel_summary(f"{GO}/{tag}_{suffix}.ncu-rep", title, fh)
-print("wrote", f"profiles/{tag}_ncu_summary.md")
+print("wrote", f"{OUTDIR}/{tag}_ncu_summary.md")
