@@ -1,4 +1,4 @@
-"""Randomized parity sweep on the GPU: updateBL! tables, hasEdge/indexht (<= 1 hybrid) and the per-quartet
+"""Randomized parity sweep on the GPU: updateBL! tables, hasEdge/indexht (0-4 hybrids, nested cycles) and the per-quartet
 read-backs under a sampling mask, each against the oracle.  Usage: python profiles/run_sweep.py [n_seeds [first_seed]]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -33,7 +33,7 @@ for seed in range(first, first + nseeds):
         assert got[k][0] == tab[k][0] and same, (seed, k, got[k], tab[k])
     nb += 1
     # hasEdge with <= 1 hybrid
-    h = seed % 2
+    h = seed % 5
     try:
         net = simulate.random_level1_network(n + 2, h, 300 + seed, min_cycle=3 if seed % 3 == 0 else 4)
     except S.SnaqError:

@@ -38,7 +38,7 @@ for seed in range(first, first + ncases):
     if seed % 4 == 0:
         X[-1] = np.where(rng.uniform(size=X.shape[1]) < 0.5, 0.0, p["upper"])     # a corner of the box
     want = oracle.evaluate(flat, qt, obs, X, sampled=mask)
-    eng = S.Engine(0)
+    eng = S.Engine(0, dedup=False)
     ded = S.Engine(0, dedup=True)
     for e in (eng, ded):
         e.set_data(S.DataCF(taxa, qt, obs))
