@@ -124,6 +124,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
         : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with launch_pdl may start while its predecessor in the stream is still
+// running; it calls grid_dependency_wait() before the first access to anything the predecessor writes (a no-op when the
+// kernel was launched the ordinary way).  Used for the expand -> evaluate -> reduce chain of one batched step, whose two
+// launch gaps are 7-14 % of the step.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// the dependent kernel may be scheduled once every block of this grid has got here (it still waits for this grid's memory)
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // --------------------------------------------------------------------------------------------
 // descriptor build
 // --------------------------------------------------------------------------------------------
@@ -574,6 +592,7 @@ __device__ __forceinline__ unsigned range_check(double v, double hi) { return (v
 __global__ void __launch_bounds__(256) k_expand_x(SnaqTables T, const double *__restrict__ X, const double *__restrict__ xconst,
                                                   int P, int nh, int nt, int tiled, double *__restrict__ XF,
                                                   uint32_t *__restrict__ status) {
+    grid_launch_dependents();
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const SnaqMath M{g_math_tab, g_math_tab + 16, g_math_tab + 32};
     if (!tiled) {
@@ -657,6 +676,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
     uint32_t *soff = reinterpret_cast<uint32_t *>(smem + L.soff);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = blockIdx.y;
+    grid_launch_dependents();
     const bool noreuse = cr.noreuse != 0;          // measurement aid (SNAQ_REUSE=0): every quartet evaluated in full
     // heavy classes first: C, B, then A
     int cls, cb = blockIdx.x;
@@ -676,9 +696,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
     if (tid == 0) {
         const unsigned xs_bytes = (unsigned)n_full * 256u, w_bytes = (unsigned)nqc * 32u;
         mbar_expect_tx(bar, xs_bytes + w_bytes + prog_bytes);
-        tma_load_1d(xs, XFT + (size_t)g * n_full * 32, xs_bytes, bar);
         tma_load_1d(sW, W + (size_t)q0 * 4, w_bytes, bar);
         tma_load_1d(sprog_raw, reinterpret_cast<const uint2 *>(prog) + base16, prog_bytes, bar);
+        grid_dependency_wait();                                  // the tile is k_expand_x's output (same step)
+        tma_load_1d(xs, XFT + (size_t)g * n_full * 32, xs_bytes, bar);
     }
     const SnaqMath M = load_math_tables(mt, tid);
     for (int i = tid; i <= nqc; i += WARPS * 32) soff[i] = off[q0 + i] - base;
@@ -988,10 +1009,12 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
     };
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1); }
     __syncthreads();
+    grid_launch_dependents();
     if (tid == 0) {
-        mbar_expect_tx(&bar[0], (unsigned)n_full * 256u);
-        tma_load_1d(xs, XFT + (size_t)g * n_full * 32, (unsigned)n_full * 256u, &bar[0]);
         if ((int)blockIdx.x * LANESP_SUPER < nchunks_tot) issue(meta((int)blockIdx.x * LANESP_SUPER), 0);
+        mbar_expect_tx(&bar[0], (unsigned)n_full * 256u);
+        grid_dependency_wait();                                  // the tile is k_expand_x's output (same step)
+        tma_load_1d(xs, XFT + (size_t)g * n_full * 32, (unsigned)n_full * 256u, &bar[0]);
     }
     const SnaqMath M = load_math_tables(mt, tid);
     unsigned st = 0;
@@ -1550,8 +1573,10 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && CPL == 1) ? 2 : 1) 
         for (int k = 0; k < RN_NST; k++) mbar_init(&wbar[k], 1);
     }
     __syncthreads();
+    grid_launch_dependents();
     if (tid == 0) {
         mbar_expect_tx(&bars[0], (unsigned)n_full * TW * 8u);
+        grid_dependency_wait();                                  // the tile is k_expand_x's output (same step)
         tma_load_1d(xs, XFT + (size_t)g * n_full * TW, (unsigned)n_full * TW * 8u, &bars[0]);
     }
     // the warp's first tiles are requested before anything else is waited for
@@ -2766,6 +2791,7 @@ __global__ void __launch_bounds__(256) k_reduce_partials_t(const double *__restr
     const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
     const int p = blockIdx.x * 32 + c;
     double s = 0.0;
+    grid_dependency_wait();                                      // the rows are the evaluation kernel's output
     if (p < P)
         for (int b = r; b < nblocks; b += 8) s += partial[(size_t)b * stride + p];
     sh[r][c] = s;
@@ -2920,6 +2946,7 @@ struct snaq_ctx {
     int lanes_chunk = 256;                // quartets per block of k_eval_lanes (SNAQ_LANES_CHUNK)
     int lanes_warps = 8;                  // warps per block of k_eval_lanes (SNAQ_LANES_WARPS = 8, 12 or 16)
     bool lanes_warps_set = false;
+    bool pdl = true;                      // SNAQ_PDL=0: ordinary launches for the expand -> evaluate -> reduce chain
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // snaq_optbl_topologies: worker contexts on the same device, each with a copy of this context's data
     uint64_t data_version = 1;            // bumped by snaq_set_data / snaq_set_obscf / snaq_set_sampled
@@ -3368,8 +3395,11 @@ static int eval_device_local(snaq_ctx *ctx, int P, const double *dX, double *dou
 #define LAUNCH_RUNS(WN, CP)                                                                                                    \
     do {                                                                                                                       \
         CK(raise_smem_limit(k_eval_runs<WN, CP>, smem));                                                                         \
-        k_eval_runs<WN, CP><<<grid, WN * 32, smem, stream>>>(ctx->d_pack, ctx->d_rec_off, pu, rm, ctx->d_XF, H.n_full,          \
-                                                            ctx->d_partial, Pp, ctx->d_status + 1);                             \
+        if (ctx->pdl) CK(launch_pdl(k_eval_runs<WN, CP>, grid, dim3(WN * 32), smem, stream, (const unsigned char *)ctx->d_pack,    \
+                                    (const uint32_t *)ctx->d_rec_off, pu, rm, (const double *)ctx->d_XF, H.n_full, ctx->d_partial, Pp, \
+                                    ctx->d_status + 1));                                                                       \
+        else k_eval_runs<WN, CP><<<grid, WN * 32, smem, stream>>>(ctx->d_pack, ctx->d_rec_off, pu, rm, ctx->d_XF, H.n_full,     \
+                                                                 ctx->d_partial, Pp, ctx->d_status + 1);                        \
     } while (0)
             if (warps == 16 && cpl == 2) LAUNCH_RUNS(16, 2);
             else if (warps == 16) LAUNCH_RUNS(16, 1);
@@ -3434,15 +3464,19 @@ static int eval_device_local(snaq_ctx *ctx, int P, const double *dX, double *dou
 #define LAUNCH_LANESP(WN)                                                                                                      \
     do {                                                                                                                       \
         CK(raise_smem_limit(k_eval_lanes_p<WN>, smem));                                                                          \
-        k_eval_lanes_p<WN><<<grid, WN * 32, smem, stream>>>(tb.off, tb.prog, tb.qhdr, tb.W, cr, chunk, ctx->maxlen,             \
-                                                           dXF, H.n_full, ctx->d_partial, Ppad, ctx->d_status + 1, LANESP_SUPER); \
+        if (ctx->pdl) CK(launch_pdl(k_eval_lanes_p<WN>, grid, dim3(WN * 32), smem, stream, tb.off, tb.prog, tb.qhdr, tb.W, cr, chunk, \
+                                    ctx->maxlen, dXF, H.n_full, ctx->d_partial, Ppad, ctx->d_status + 1, LANESP_SUPER));        \
+        else k_eval_lanes_p<WN><<<grid, WN * 32, smem, stream>>>(tb.off, tb.prog, tb.qhdr, tb.W, cr, chunk, ctx->maxlen,        \
+                                                                dXF, H.n_full, ctx->d_partial, Ppad, ctx->d_status + 1, LANESP_SUPER); \
     } while (0)
             if (warps == 8) LAUNCH_LANESP(8);
             else if (warps == 12) LAUNCH_LANESP(12);
             else LAUNCH_LANESP(16);
 #undef LAUNCH_LANESP
             CK(cudaGetLastError());
-            k_reduce_partials_t<<<(P + 31) / 32, 256, 0, stream>>>(ctx->d_partial, (int)nsuper, Ppad, P, dout);
+            if (ctx->pdl) CK(launch_pdl(k_reduce_partials_t, dim3((P + 31) / 32), dim3(256), 0, stream, (const double *)ctx->d_partial, (int)nsuper,
+                                        Ppad, P, dout, (const double *)nullptr));
+            else k_reduce_partials_t<<<(P + 31) / 32, 256, 0, stream>>>(ctx->d_partial, (int)nsuper, Ppad, P, dout);
             CK(cudaGetLastError());
             ctx->counters[0] += 1;
             ctx->counters[1] += ctx->nq * (int64_t)P;
@@ -3465,15 +3499,19 @@ static int eval_device_local(snaq_ctx *ctx, int P, const double *dX, double *dou
 #define LAUNCH_LANES(WN)                                                                                                       \
     do {                                                                                                                       \
         CK(raise_smem_limit(k_eval_lanes<WN>, smem));                                                                            \
-        k_eval_lanes<WN><<<grid, WN * 32, smem, stream>>>(tb.off, tb.prog, tb.qhdr, tb.W, cr, chunk, ctx->maxlen, dXF,         \
-                                                         H.n_full, ctx->d_partial, Ppad, ctx->d_status + 1);                    \
+        if (ctx->pdl) CK(launch_pdl(k_eval_lanes<WN>, grid, dim3(WN * 32), smem, stream, tb.off, tb.prog, tb.qhdr, tb.W, cr, chunk, \
+                                    ctx->maxlen, dXF, H.n_full, ctx->d_partial, Ppad, ctx->d_status + 1));                     \
+        else k_eval_lanes<WN><<<grid, WN * 32, smem, stream>>>(tb.off, tb.prog, tb.qhdr, tb.W, cr, chunk, ctx->maxlen, dXF,    \
+                                                              H.n_full, ctx->d_partial, Ppad, ctx->d_status + 1);              \
     } while (0)
         if (warps == 8) LAUNCH_LANES(8);
         else if (warps == 12) LAUNCH_LANES(12);
         else LAUNCH_LANES(16);
 #undef LAUNCH_LANES
         CK(cudaGetLastError());
-        k_reduce_partials_t<<<(P + 31) / 32, 256, 0, stream>>>(ctx->d_partial, (int)nchunks, Ppad, P, dout);
+        if (ctx->pdl) CK(launch_pdl(k_reduce_partials_t, dim3((P + 31) / 32), dim3(256), 0, stream, (const double *)ctx->d_partial, (int)nchunks,
+                                    Ppad, P, dout, (const double *)nullptr));
+        else k_reduce_partials_t<<<(P + 31) / 32, 256, 0, stream>>>(ctx->d_partial, (int)nchunks, Ppad, P, dout);
         CK(cudaGetLastError());
         ctx->counters[0] += 1;
         ctx->counters[1] += ctx->nq * (int64_t)P;
@@ -3546,6 +3584,7 @@ int snaq_create(const snaq_opts *opts, snaq_ctx **out) {
     if (const char *ev = getenv("SNAQ_SV_DEDUP")) ctx->sv_dedup = atoi(ev) != 0;
     if (const char *ev = getenv("SNAQ_LANES_CHUNK")) { int v = atoi(ev); if (v == 128 || v == 256 || v == 512 || v == 1024) ctx->lanes_chunk = v; }
     if (const char *ev = getenv("SNAQ_LANES_PERSISTENT")) ctx->lanes_persistent = atoi(ev);
+    if (const char *ev = getenv("SNAQ_PDL")) ctx->pdl = atoi(ev) != 0;
     if (const char *ev = getenv("SNAQ_LANES_WARPS")) { int v = atoi(ev); if (v == 8 || v == 12 || v == 16) { ctx->lanes_warps = v; ctx->lanes_warps_set = true; } }
     if ((e = cudaMalloc((void **)&ctx->d_status, 4 * sizeof(uint32_t))) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cudaMalloc((void **)&ctx->d_total, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
