@@ -99,7 +99,7 @@ typedef struct snaq_ctx snaq_ctx;   /* opaque: one ctx <=> one CUDA device + str
  * programs are identical (they differ in taxa of the same clades) are evaluated ONCE per parameter vector with the SUM of
  * their weights.  The sums are formed when the observed CFs change (snaq_set_data / _set_obscf / _set_sampled /
  * _resample_obscf), per run of identical programs of the class-sorted table, with compensated arithmetic
- * (27,405 quartets -> 1,290 programs at 30 taxa; 3,921,225 -> 9,419 at 100 taxa).  Every (quartet, vector) pair is in the
+ * (27,405 quartets -> 1,290 programs at 30 taxa; 3,921,225 -> 9,430 at 100 taxa).  Every (quartet, vector) pair is in the
  * result exactly as before, to rounding (<= 2e-15 relative: the order of the sum changes); the -1e15 penalty of a negative
  * expected CF stays per sampled quartet; per-quartet read-backs (snaq_eval_quartets) use the full table.
  * SNAQ_OPT_PER_QUARTET (env SNAQ_DEDUP=0) selects the per-quartet kernels instead: one weighted contribution computed per
@@ -341,7 +341,7 @@ int snaq_debug_bounds(snaq_ctx *ctx, int64_t *checks, int64_t *violations);
 /* engine counters: [0] launches of the eval kernel, [1] quartet-evals done,
  * [2] H2D bytes, [3] D2H bytes, [4] descriptor words in HBM, [5] launches of
  * the descriptor-build kernels, [6] bytes one single-call evaluation (P <= 4)
- * streams from HBM, [7] distinct programs (deduplication on), else 0            */
+ * streams from HBM, [7] distinct programs = runs of the class-sorted table (the run table is built in both table modes)            */
 int snaq_get_counters(snaq_ctx *ctx, int64_t out[8]);
 
 /* diagnostics (only when the context was created with SNAQ_TRACE=1 in the environment): phase
