@@ -907,9 +907,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes(const uint32_t *__res
                     const double g2 = XLO(w.x), ca = XHI(w.x), cm = XLO(w.y), cb = XHI(w.y);
                     const double g1 = 1.0 - g2;
                     const double y5 = snaq_exp(-snaq_clamp10(cm - ca), M), y6 = snaq_exp(-snaq_clamp10(cb - cm), M);
-                    const double cf0 = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;
-                    const double cf1 = g1 * 1.0 / 3.0 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
-                    const double cf2 = g1 * 1.0 / 3.0 * y5 + g2 * 1.0 / 3.0 * y6;
+                    const double g13 = snaq_div3(g1), g23 = snaq_div3(g2);          // = g/3.0 bit for bit, no division
+                    const double cf0 = g1 * (1.0 - 2.0 / 3.0 * y5) + g23 * y6;
+                    const double cf1 = g13 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
+                    const double cf2 = g13 * y5 + g23 * y6;
                     m5_l0 = snaq_log_pos(cf0, M); m5_l1 = snaq_log_pos(cf1, M); m5_l2 = snaq_log_pos(cf2, M);
                     m5_k0 = w.x; m5_k1 = w.y;
                 }
@@ -1245,9 +1246,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_eval_lanes_p(const uint32_t *__r
                         const double g2 = XLO(w.x), ca = XHI(w.x), cm = XLO(w.y), cb = XHI(w.y);
                         const double g1 = 1.0 - g2;
                         const double y5 = snaq_exp(-snaq_clamp10(cm - ca), M), y6 = snaq_exp(-snaq_clamp10(cb - cm), M);
-                        const double cf0 = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;
-                        const double cf1 = g1 * 1.0 / 3.0 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
-                        const double cf2 = g1 * 1.0 / 3.0 * y5 + g2 * 1.0 / 3.0 * y6;
+                        const double g13 = snaq_div3(g1), g23 = snaq_div3(g2);          // = g/3.0 bit for bit, no division
+                        const double cf0 = g1 * (1.0 - 2.0 / 3.0 * y5) + g23 * y6;
+                        const double cf1 = g13 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
+                        const double cf2 = g13 * y5 + g23 * y6;
                         m5_l0 = snaq_log_pos(cf0, M); m5_l1 = snaq_log_pos(cf1, M); m5_l2 = snaq_log_pos(cf2, M);
                         m5_k0 = w.x; m5_k1 = w.y;
                     }
@@ -1495,9 +1497,10 @@ __device__ __noinline__ void runs_compute(const RunTile &d, const uint32_t *soff
                             const double g2 = xf(w.x & 0xffffu), ca = xf(w.x >> 16), cm = xf(w.y & 0xffffu), cb = xf(w.y >> 16);
                             const double g1 = 1.0 - g2;
                             const double y5 = snaq_exp(-snaq_clamp10(cm - ca), M), y6 = snaq_exp(-snaq_clamp10(cb - cm), M);
-                            const double cf0 = g1 * (1.0 - 2.0 / 3.0 * y5) + g2 * 1.0 / 3.0 * y6;
-                            const double cf1 = g1 * 1.0 / 3.0 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
-                            const double cf2 = g1 * 1.0 / 3.0 * y5 + g2 * 1.0 / 3.0 * y6;
+                            const double g13 = snaq_div3(g1), g23 = snaq_div3(g2);          // = g/3.0 bit for bit, no division
+                            const double cf0 = g1 * (1.0 - 2.0 / 3.0 * y5) + g23 * y6;
+                            const double cf1 = g13 * y5 + g2 * (1.0 - 2.0 / 3.0 * y6);
+                            const double cf2 = g13 * y5 + g23 * y6;
                             K.cL[c] = snaq_log_pos(cf0, M); K.cT[c] = snaq_log_pos(cf1, M); K.c2[c] = snaq_log_pos(cf2, M);
                         } else {
                             const uint16_t pcw[4] = {(uint16_t)(w.x & 0xffffu), (uint16_t)(w.x >> 16), (uint16_t)nul, (uint16_t)nul};

@@ -34,6 +34,10 @@ void hostsim_math(int n, const double *u, double *e, double *l) {
     }
 }
 
+void hostsim_div3(int n, const double *g, double *q) {
+    for (int i = 0; i < n; i++) q[i] = snaq_div3(g[i]);
+}
+
 int hostsim_params(const snaq_flatnet *f, int ntaxa, int32_t *nparams, int32_t *n_xe, double *x0, int32_t *numht) {
     SnaqHostTables H;
     int rc = snaq_build_tables(f, ntaxa, H, g_err);

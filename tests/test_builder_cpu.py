@@ -37,6 +37,16 @@ def test_specialised_exp_log_accuracy():
     assert l[0] == -np.inf and np.isnan(l[1]) and l[2] == np.inf  # rare arguments fall back to the library log
 
 
+def test_division_by_three_without_a_division():
+    """snaq_div3 (two FMAs after a multiplication) is g / 3.0 bit for bit: the reference's g*1/3 (src/pseudolik.jl:985-991)"""
+    rng = np.random.default_rng(0)
+    g = np.concatenate([rng.random(200000), rng.random(20000) * 2.0 ** -rng.integers(0, 60, 20000), rng.random(20000) * 3 - 1,
+                        [0.0, 1.0, 0.5, 1 / 3, 2 / 3, 0.1, 3.0, 1e-300, -0.25]])
+    q = np.zeros_like(g)
+    hs.lib().hostsim_div3(len(g), hs._p(g), hs._p(q))
+    assert np.array_equal(q, g / 3.0)
+
+
 @pytest.mark.parametrize("case", ["G", "F", "I"])
 def test_golden_cases_through_the_device_functions(case):
     net = {"G": S.readnewicklevel1(kat.CASE_G), "F": kat.case_f_network(S), "I": S.readnewicklevel1(kat.CASE_I)}[case]
