@@ -34,6 +34,38 @@ void hostsim_math(int n, const double *u, double *e, double *l) {
     }
 }
 
+// the host side of snaq_patch_network: the new tables rooted where the old ones are, and the taxa whose quartets have to be
+// re-described.  Returns 1 and fills touched[ntaxa], or 0 when the patch falls back to a full classification; < 0 on error.
+int hostsim_touched(const snaq_flatnet *f_old, const snaq_flatnet *f_new, int ntaxa, uint8_t *touched) {
+    SnaqHostTables A, B;
+    if (snaq_build_tables(f_old, ntaxa, A, g_err)) return -1;
+    if (snaq_build_tables(f_new, ntaxa, B, g_err, A.root)) return -2;
+    std::vector<uint8_t> t;
+    if (!snaq_tables_touched(A, B, t)) return 0;
+    for (int i = 0; i < ntaxa; i++) touched[i] = t[(size_t)i];
+    return 1;
+}
+
+// programs of every quartet on tables rooted at `keep_root` (-1: the default root): first 8 words, length, header
+int hostsim_progs_rooted(const snaq_flatnet *f_root, const snaq_flatnet *f, int ntaxa, int64_t nq, const uint16_t *taxa, uint16_t *words8,
+                         int32_t *len, uint8_t *hdr) {
+    SnaqHostTables R, H;
+    if (snaq_build_tables(f_root, ntaxa, R, g_err)) return -1;
+    if (snaq_build_tables(f, ntaxa, H, g_err, R.root)) return -2;
+    SnaqTables T = H.view(H.blob.data());
+    for (int64_t q = 0; q < nq; q++) {
+        uint16_t buf[256];
+        for (auto &b : buf) b = (uint16_t)H.n_xe;
+        SnaqWriter w{buf, 0, 256};
+        uint8_t h1 = 0;
+        if (snaq_build_quartet(T, taxa + 4 * q, w, &h1, nullptr)) { g_err = "build error"; return -3; }
+        for (int k = 0; k < 8; k++) words8[8 * q + k] = buf[k];
+        len[q] = w.n;
+        hdr[q] = h1;
+    }
+    return 0;
+}
+
 void hostsim_div3(int n, const double *g, double *q) {
     for (int i = 0; i < n; i++) q[i] = snaq_div3(g[i]);
 }
